@@ -1,0 +1,192 @@
+/*
+ * mae_clip_b200 - C ABI of the B200-native training-loss hot path.
+ *
+ * The reference (ykojima4020/mae_clip) is pure Python and has no FFI of its
+ * own; its boundary is the Python API (CLIPModel.forward / ProjectionHead /
+ * cross_entropy).  This header is the NEW C boundary that sits directly
+ * underneath that API: each entry point names the reference lines whose
+ * arithmetic it replaces.  INTEGRATION.md shows the ctypes stub a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *  - tensors are dense row-major unless strides are passed explicitly;
+ *  - `stream` is a cudaStream_t passed as void* (0 = default stream);
+ *  - no entry point allocates device memory: scratch comes in through
+ *    `ws`/`ws_bytes`, sized by the matching `*_workspace_bytes` query;
+ *  - every entry point returns an mc_status (0 = ok) and never throws;
+ *    mc_last_error_string() describes the last failure on the calling thread;
+ *  - entry points are re-entrant; the library keeps no mutable global state
+ *    except cached TMA descriptors keyed by (pointer, shape).
+ *  - the library refuses to run on anything but compute capability 10.x
+ *    (MC_ERR_ARCH); there is no fallback path.
+ */
+#ifndef MAE_CLIP_B200_H_
+#define MAE_CLIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  MC_OK = 0,
+  MC_ERR_BAD_ARG = 1,     /* null pointer, non-positive size, unsupported shape */
+  MC_ERR_ALIGN = 2,       /* pointer not aligned for the vector width used      */
+  MC_ERR_ARCH = 3,        /* device is not sm_100                               */
+  MC_ERR_CUDA = 4,        /* a CUDA runtime / driver call failed                */
+  MC_ERR_WORKSPACE = 5,   /* ws_bytes smaller than *_workspace_bytes()          */
+  MC_ERR_UNSUPPORTED = 6  /* valid request this build does not implement        */
+} mc_status;
+
+/* precision / engine of the contrastive-loss and projection GEMMs */
+typedef enum {
+  MC_GEMM_SIMT_FP32 = 0, /* plain fp32 FMA tiles (bring-up / cross-check path)            */
+  MC_GEMM_TC_BF16X3 = 1, /* tcgen05 kind::f16, operands split hi+mid bf16, 3 passes:
+                            ~2^-17 relative operand error, meets the fp32 tolerance        */
+  MC_GEMM_TC_BF16 = 2    /* tcgen05 kind::f16, single bf16 pass (looser tolerance)         */
+} mc_gemm_mode;
+
+int mc_version(void);                       /* major*10000 + minor*100 + patch */
+const char* mc_last_error_string(void);
+int mc_device_supported(int device);        /* 1 when `device` is compute capability 10.x */
+
+/* ---------------------------------------------------------------------------
+ * L5  cross_entropy(preds, targets, reduction)            CLIP.py:46-52
+ * loss_rows[r] = -sum_c targets[r,c] * log_softmax(preds[r,:])[c]
+ * Strides are in elements so the transposed views of CLIP.py:41 are accepted
+ * without a copy.  row_lse / row_tsum (rows floats each) are kept for backward.
+ * ------------------------------------------------------------------------- */
+int mc_soft_ce_fwd(const float* preds, int64_t p_row_stride, int64_t p_col_stride,
+                   const float* targets, int64_t t_row_stride, int64_t t_col_stride,
+                   int rows, int cols, float* loss_rows, float* row_lse, float* row_tsum,
+                   void* stream);
+/* dpreds / dtargets (either may be NULL) are written through their own element strides, so the
+ * caller can give them the layout of the (possibly transposed) inputs and keep stores coalesced. */
+int mc_soft_ce_bwd(const float* preds, int64_t p_row_stride, int64_t p_col_stride,
+                   const float* targets, int64_t t_row_stride, int64_t t_col_stride,
+                   int rows, int cols, const float* row_lse, const float* row_tsum,
+                   const float* grad_rows, float* dpreds, int64_t dp_row_stride,
+                   int64_t dp_col_stride, float* dtargets, int64_t dt_row_stride,
+                   int64_t dt_col_stride, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * L3-L6  contrastive soft-target loss on embeddings        CLIP.py:34-43 (+ autograd, main.py:58)
+ *
+ * Rows are partitioned: this rank owns `b` rows of the global batch `B`
+ * starting at `row_offset`; *_loc pointers have b rows/entries, *_all have B.
+ * On one GPU b == B, row_offset == 0 and loc == all.  Three phases, each one
+ * sweep over the (b x B) strip; the caller all-gathers the small statistic
+ * vectors between phases when B > b (mae_clip_b200/dist.py).
+ *
+ *   stats  : row_lse_s[i] = LSE_j S_ij,  col_lse_s[i] = LSE_j S_ji,
+ *            row_lse_z[i] = LSE_j Z_ij            (S = T I^T / tau, Z = (I I^T + T T^T) tau/2)
+ *   rowloss: row_g[i] = sum_j P_ij G_ij, col_sum_p[i] = sum_k P_ki, loss_part = sum_i row_g[i]
+ *            (P = softmax_row(Z), G = -(2S - r_i - c_j)/(2B); loss = sum over ranks of loss_part)
+ *   bwd    : dI_loc, dT_loc = grad_loss * d loss / d (I_loc, T_loc), every term of the owned rows
+ *            (the strip of dS, the transposed strip of dS and dZ + dZ^T), so no gradient
+ *            exchange is needed afterwards.
+ * ------------------------------------------------------------------------- */
+size_t mc_clip_loss_workspace_bytes(int b, int B, int D, int mode);
+
+/* prepare(): mode-specific operand staging (bf16 hi/mid planes for the tcgen05 modes; no-op for
+ * SIMT).  `planes_all` receives the staged copy of the *local* rows at row_offset; when B > b the
+ * caller all-gathers the planes instead of the fp32 embeddings.  planes layout: see DESIGN.md. */
+size_t mc_clip_planes_bytes(int B, int D, int mode);
+int mc_clip_prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row_offset,
+                    int mode, void* planes_all, void* stream);
+
+int mc_clip_stats(const float* I_all, const float* T_all, const void* planes_all, int b, int B,
+                  int D, int row_offset, float tau, int mode, float* row_lse_s_loc,
+                  float* col_lse_s_loc, float* row_lse_z_loc, void* ws, size_t ws_bytes,
+                  void* stream);
+int mc_clip_rowloss(const float* I_all, const float* T_all, const void* planes_all, int b, int B,
+                    int D, int row_offset, float tau, int mode, const float* row_lse_s_all,
+                    const float* col_lse_s_all, const float* row_lse_z_all, float* row_g_loc,
+                    float* col_sum_p_loc, float* loss_part, void* ws, size_t ws_bytes,
+                    void* stream);
+int mc_clip_bwd(const float* I_all, const float* T_all, const void* planes_all, int b, int B, int D,
+                int row_offset, float tau, int mode, const float* row_lse_s_all,
+                const float* col_lse_s_all, const float* row_lse_z_all, const float* row_g_all,
+                const float* col_sum_p_all, const float* grad_loss /* device scalar or NULL = 1 */,
+                float* dI_loc, float* dT_loc, void* ws, size_t ws_bytes, void* stream);
+
+/* Single-GPU convenience: prepare + three phases, forward and backward in one call
+ * (loss_out: device scalar; dI/dT may both be NULL for forward only). */
+size_t mc_clip_loss_fused_workspace_bytes(int B, int D, int mode);
+int mc_clip_loss_fwd_bwd(const float* I, const float* T, int B, int D, float tau, int mode,
+                         float* loss_out, float* dI, float* dT, void* ws, size_t ws_bytes,
+                         void* stream);
+/* Same through HOST buffers (pinned or pageable): copies in, computes, copies loss/grads out
+ * and synchronises the stream.  `dws`/`dws_bytes` is DEVICE scratch of at least
+ * mc_clip_loss_host_workspace_bytes(). */
+size_t mc_clip_loss_host_workspace_bytes(int B, int D, int mode);
+int mc_clip_loss_fwd_bwd_host(const float* I_host, const float* T_host, int B, int D, float tau,
+                              int mode, float* loss_host, float* dI_host, float* dT_host,
+                              void* dws, size_t dws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * L1-L2  ProjectionHead                                    modules.py:55-76
+ *   projected = x Wp^T + bp; hidden = gelu(projected); y = hidden Wf^T + bf;
+ *   z = keep*y/(1-p) + projected; out = LayerNorm(z) * gamma + beta
+ * keep_mask: (B, P) bytes of 0/1 or NULL (eval mode).  projected / hidden / z /
+ * mean / rstd are written for backward (all (B,P) or (B)); pass NULL for
+ * hidden/z/mean/rstd under no_grad to skip the stores.
+ * ------------------------------------------------------------------------- */
+size_t mc_proj_head_workspace_bytes(int B, int E, int P, int mode);
+int mc_proj_head_fwd(const float* x, int B, int E, int P, const float* w_proj, const float* b_proj,
+                     const float* w_fc, const float* b_fc, const float* gamma, const float* beta,
+                     const uint8_t* keep_mask, float p_drop, float eps, int mode, float* projected,
+                     float* hidden, float* z, float* mean, float* rstd, float* out, void* ws,
+                     size_t ws_bytes, void* stream);
+/* dx may be NULL (frozen tower below the head: modules.py:35 / CLIP.py:18). */
+int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
+                     const float* w_proj, const float* w_fc, const float* gamma,
+                     const uint8_t* keep_mask, float p_drop, int mode, const float* projected,
+                     const float* hidden, const float* z, const float* mean, const float* rstd,
+                     float* dx, float* dw_proj, float* db_proj, float* dw_fc, float* db_fc,
+                     float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * M1  MAE per-sample random masking        (NOT in the reference: north_star; oracle/mae_ref.py)
+ * noise (N,L) fp32; stable ascending argsort (ties -> lower index).  Outputs:
+ * ids_restore (N,L) int64, mask (N,L) fp32 (0 keep / 1 removed), ids_keep
+ * (N,len_keep) int64, x_masked (N,len_keep,Dm) gathered rows of x (N,L,Dm).
+ * elem_size 2 (bf16/fp16) or 4 (fp32).  x / x_masked may be NULL (indices only).
+ * ------------------------------------------------------------------------- */
+int mc_random_masking(const void* x, int elem_size, const float* noise, int N, int L, int Dm,
+                      int len_keep, void* x_masked, float* mask, int64_t* ids_restore,
+                      int64_t* ids_keep, void* stream);
+/* backward of the gather: grad_x (N,L,Dm) = scatter(grad_x_masked) with zeros elsewhere */
+int mc_random_masking_bwd(const void* grad_x_masked, int elem_size, const float* mask,
+                          const int64_t* ids_restore, int N, int L, int Dm, int len_keep,
+                          void* grad_x, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * M2-M3  patchify + normalised-pixel target + masked MSE   (NOT in the reference)
+ * pred (N,L,p*p*3) in pred_elem_size (2 = bf16, 4 = fp32); imgs (N,3,H,W) fp32;
+ * mask (N,L) fp32.  loss = sum(mask * mean_e (pred-target)^2) / sum(mask).
+ * The target is never materialised.  `ws` needs mc_masked_mse_workspace_bytes().
+ * ------------------------------------------------------------------------- */
+size_t mc_masked_mse_workspace_bytes(int N, int L);
+int mc_masked_mse_fwd(const void* pred, int pred_elem_size, const float* imgs, const float* mask,
+                      int N, int H, int W, int p, int norm_pix, float* loss_out,
+                      float* mask_sum_out, void* ws, size_t ws_bytes, void* stream);
+int mc_masked_mse_bwd(const void* pred, int pred_elem_size, const float* imgs, const float* mask,
+                      int N, int H, int W, int p, int norm_pix, const float* mask_sum,
+                      const float* grad_loss /* device scalar or NULL = 1 */, void* dpred,
+                      void* stream);
+
+/* "next" rows (SURVEY.md section 8 f, rank 2): standalone patchify and decoder-side un-shuffle */
+int mc_patchify(const float* imgs, int N, int H, int W, int p, int norm_pix, float* out,
+                void* stream);
+int mc_restore_tokens(const void* x_kept, int elem_size, const void* mask_token,
+                      const int64_t* ids_restore, int N, int L, int Dm, int len_keep, void* out,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAE_CLIP_B200_H_ */

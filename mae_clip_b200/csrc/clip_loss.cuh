@@ -1,0 +1,46 @@
+// Internal interface between the C-ABI dispatcher (clip_loss.cu) and the two engines.
+#pragma once
+#include "common.cuh"
+
+namespace mc {
+
+struct ClipProblem {
+  const float* I_all;
+  const float* T_all;
+  const void* planes_all;
+  int b, B, D, row_offset;
+  float tau;
+};
+
+struct ClipStatsAll {  // length-B vectors (device)
+  const float* r;   // row LSE of S
+  const float* c;   // col LSE of S
+  const float* rz;  // row LSE of Z
+  const float* g;   // row sums of G*P
+  const float* q;   // col sums of P
+};
+
+namespace simt {
+size_t workspace_bytes(int b, int B, int D);
+int stats(const ClipProblem& p, float* r_loc, float* c_loc, float* rz_loc, void* ws, size_t ws_bytes,
+          cudaStream_t st);
+int rowloss(const ClipProblem& p, const ClipStatsAll& s, float* g_loc, float* q_loc,
+            float* loss_part, void* ws, size_t ws_bytes, cudaStream_t st);
+int bwd(const ClipProblem& p, const ClipStatsAll& s, const float* grad_loss, float* dI, float* dT,
+        void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace simt
+
+namespace tc {
+size_t workspace_bytes(int b, int B, int D, int mode);
+size_t planes_bytes(int B, int D, int mode);
+int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row_offset, int mode,
+            void* planes_all, cudaStream_t st);
+int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, void* ws,
+          size_t ws_bytes, cudaStream_t st);
+int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, float* g_loc, float* q_loc,
+            float* loss_part, void* ws, size_t ws_bytes, cudaStream_t st);
+int bwd(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, float* dI,
+        float* dT, void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace tc
+
+}  // namespace mc

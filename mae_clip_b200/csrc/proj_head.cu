@@ -1,0 +1,359 @@
+// L1-L2: ProjectionHead forward/backward (/root/reference modules.py:55-76).
+//   projected = x Wp^T + bp ; hidden = gelu(projected) ; y = hidden Wf^T + bf
+//   z = keep * y / (1-p) + projected ; out = LayerNorm(z) * gamma + beta
+// GEMMs: bias and exact-erf GELU are fused into the GEMM epilogue; dropout + residual +
+// LayerNorm are one warp-per-row pass (K2), its backward another (K2b) that also emits the
+// gamma/beta column partials.  The dropout keep-mask is an INPUT (SURVEY.md section 7 f).
+#include "common.cuh"
+
+namespace mc {
+
+// ---------------- K2: dropout + residual + LayerNorm forward (warp per row) ----------------
+template <int NV>  // float4 slots per lane: P <= 128*NV
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ y,
+                                                     const float* __restrict__ projected,
+                                                     const uint8_t* __restrict__ keep, float scale,
+                                                     const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float eps, int B,
+                                                     int P, float* __restrict__ z_out,
+                                                     float* __restrict__ mean_out,
+                                                     float* __restrict__ rstd_out,
+                                                     float* __restrict__ out) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const int nvec = P >> 2;
+  const size_t off = (size_t)row * P;
+  float4 zv[NV];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int v = lane + 32 * k;
+    zv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (v < nvec) {
+      float4 a = *reinterpret_cast<const float4*>(y + off + 4 * v);
+      float4 pr = *reinterpret_cast<const float4*>(projected + off + 4 * v);
+      if (keep) {
+        uchar4 m = *reinterpret_cast<const uchar4*>(keep + off + 4 * v);
+        a.x = m.x ? a.x * scale : 0.f;
+        a.y = m.y ? a.y * scale : 0.f;
+        a.z = m.z ? a.z * scale : 0.f;
+        a.w = m.w ? a.w * scale : 0.f;
+      }
+      zv[k] = make_float4(a.x + pr.x, a.y + pr.y, a.z + pr.z, a.w + pr.w);
+      sum += (zv[k].x + zv[k].y) + (zv[k].z + zv[k].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)P;
+  float var = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    if (lane + 32 * k < nvec) {
+      float a = zv[k].x - mean, b = zv[k].y - mean, c = zv[k].z - mean, d = zv[k].w - mean;
+      var += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(var) / (float)P + eps);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nvec) {
+      float4 g = *reinterpret_cast<const float4*>(gamma + 4 * v);
+      float4 bt = *reinterpret_cast<const float4*>(beta + 4 * v);
+      float4 o;
+      o.x = (zv[k].x - mean) * rstd * g.x + bt.x;
+      o.y = (zv[k].y - mean) * rstd * g.y + bt.y;
+      o.z = (zv[k].z - mean) * rstd * g.z + bt.z;
+      o.w = (zv[k].w - mean) * rstd * g.w + bt.w;
+      *reinterpret_cast<float4*>(out + off + 4 * v) = o;
+      if (z_out) *reinterpret_cast<float4*>(z_out + off + 4 * v) = zv[k];
+    }
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+// ---------------- K2b: LayerNorm + dropout backward (warp per row, grid-stride rows) ---------
+// dz = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)), dxhat = dO * gamma
+// dy = dz * keep / (1-p);  per-block partials of dgamma = sum dO*xhat, dbeta = sum dO
+template <int NV>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ grad_out,
+                                                     const float* __restrict__ z,
+                                                     const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd,
+                                                     const float* __restrict__ gamma,
+                                                     const uint8_t* __restrict__ keep, float scale,
+                                                     int B, int P, float* __restrict__ dz_out,
+                                                     float* __restrict__ dy_out,
+                                                     float* __restrict__ partials /*[grid][2][P]*/) {
+  extern __shared__ float sm[];  // [8 warps][2][P]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = P >> 2;
+  float4 dg[NV], db[NV], gm[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    dg[k] = db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int v = lane + 32 * k;
+    gm[k] = (v < nvec) ? *reinterpret_cast<const float4*>(gamma + 4 * v) : dg[k];
+  }
+  for (int row = blockIdx.x * 8 + warp; row < B; row += gridDim.x * 8) {
+    const size_t off = (size_t)row * P;
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[NV], dxh[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      xh[k] = dxh[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v < nvec) {
+        float4 go = *reinterpret_cast<const float4*>(grad_out + off + 4 * v);
+        float4 zz = *reinterpret_cast<const float4*>(z + off + 4 * v);
+        xh[k] = make_float4((zz.x - mu) * rs, (zz.y - mu) * rs, (zz.z - mu) * rs, (zz.w - mu) * rs);
+        dxh[k] = make_float4(go.x * gm[k].x, go.y * gm[k].y, go.z * gm[k].z, go.w * gm[k].w);
+        dg[k].x += go.x * xh[k].x; dg[k].y += go.y * xh[k].y;
+        dg[k].z += go.z * xh[k].z; dg[k].w += go.w * xh[k].w;
+        db[k].x += go.x; db[k].y += go.y; db[k].z += go.z; db[k].w += go.w;
+        s1 += (dxh[k].x + dxh[k].y) + (dxh[k].z + dxh[k].w);
+        s2 += (dxh[k].x * xh[k].x + dxh[k].y * xh[k].y) + (dxh[k].z * xh[k].z + dxh[k].w * xh[k].w);
+      }
+    }
+    const float m1 = warp_sum(s1) / (float)P, m2 = warp_sum(s2) / (float)P;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) {
+        float4 d;
+        d.x = rs * (dxh[k].x - m1 - xh[k].x * m2);
+        d.y = rs * (dxh[k].y - m1 - xh[k].y * m2);
+        d.z = rs * (dxh[k].z - m1 - xh[k].z * m2);
+        d.w = rs * (dxh[k].w - m1 - xh[k].w * m2);
+        *reinterpret_cast<float4*>(dz_out + off + 4 * v) = d;
+        if (keep) {
+          uchar4 m = *reinterpret_cast<const uchar4*>(keep + off + 4 * v);
+          d.x = m.x ? d.x * scale : 0.f;
+          d.y = m.y ? d.y * scale : 0.f;
+          d.z = m.z ? d.z * scale : 0.f;
+          d.w = m.w ? d.w * scale : 0.f;
+        }
+        *reinterpret_cast<float4*>(dy_out + off + 4 * v) = d;
+      }
+    }
+  }
+  // block-level column partials
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nvec) {
+      *reinterpret_cast<float4*>(sm + (warp * 2 + 0) * P + 4 * v) = dg[k];
+      *reinterpret_cast<float4*>(sm + (warp * 2 + 1) * P + 4 * v) = db[k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * P; i += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) acc += sm[w * 2 * P + i];
+    partials[(size_t)blockIdx.x * 2 * P + i] = acc;
+  }
+}
+
+// out[c] = sum_r in[r][c]   (rows x cols, ld = cols); one block per 32 columns
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ in, int rows,
+                                                      int cols, float* __restrict__ out) {
+  __shared__ float sm[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < cols)
+    for (int r = threadIdx.y; r < rows; r += 32) acc += in[(size_t)r * cols + c];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  float v = sm[threadIdx.x][threadIdx.y];
+  v = warp_sum(v);
+  const int oc = blockIdx.x * 32 + threadIdx.y;
+  if (threadIdx.x == 0 && oc < cols) out[oc] = v;
+}
+
+// dp = dh * gelu'(projected) + dz   (in place on dh)
+__global__ void __launch_bounds__(256) gelu_bwd_add_kernel(float* __restrict__ dh,
+                                                           const float* __restrict__ projected,
+                                                           const float* __restrict__ dz, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float4 h = reinterpret_cast<float4*>(dh)[i];
+    float4 p = reinterpret_cast<const float4*>(projected)[i];
+    float4 d = reinterpret_cast<const float4*>(dz)[i];
+    h.x = fmaf(h.x, gelu_erf_grad(p.x), d.x);
+    h.y = fmaf(h.y, gelu_erf_grad(p.y), d.y);
+    h.z = fmaf(h.z, gelu_erf_grad(p.z), d.z);
+    h.w = fmaf(h.w, gelu_erf_grad(p.w), d.w);
+    reinterpret_cast<float4*>(dh)[i] = h;
+  }
+}
+
+static int ln_blocks(int B) {
+  int nb = (B + 7) / 8;
+  int cap = num_sms() * 2;
+  return nb < cap ? nb : cap;
+}
+
+template <int NV>
+static int launch_ln_fwd(const float* y, const float* projected, const uint8_t* keep, float scale,
+                         const float* gamma, const float* beta, float eps, int B, int P, float* z,
+                         float* mean, float* rstd, float* out, cudaStream_t st) {
+  ln_fwd_kernel<NV><<<(B + 7) / 8, 256, 0, st>>>(y, projected, keep, scale, gamma, beta, eps, B, P, z,
+                                                 mean, rstd, out);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
+template <int NV>
+static int launch_ln_bwd(const float* go, const float* z, const float* mean, const float* rstd,
+                         const float* gamma, const uint8_t* keep, float scale, int B, int P,
+                         float* dz, float* dy, float* partials, int blocks, cudaStream_t st) {
+  size_t smem = (size_t)8 * 2 * P * sizeof(float);
+  ln_bwd_kernel<NV><<<blocks, 256, smem, st>>>(go, z, mean, rstd, gamma, keep, scale, B, P, dz, dy,
+                                               partials);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
+#define MC_DISPATCH_NV(P, CALL)                                \
+  do {                                                         \
+    if ((P) <= 128) { constexpr int NV = 1; rc = CALL; }       \
+    else if ((P) <= 256) { constexpr int NV = 2; rc = CALL; }  \
+    else if ((P) <= 512) { constexpr int NV = 4; rc = CALL; }  \
+    else { constexpr int NV = 8; rc = CALL; }                  \
+  } while (0)
+
+struct HeadWs {
+  float *y, *hidden_tmp, *dz, *dy, *dh, *partials;
+  size_t total;
+};
+static HeadWs head_ws(void* ws, int B, int /*E*/, int P) {
+  size_t bp = round_up((size_t)B * P * 4, 256);
+  size_t part = round_up((size_t)ln_blocks(B) * 2 * P * 4, 256);
+  char* p = static_cast<char*>(ws);
+  HeadWs w;
+  w.y = reinterpret_cast<float*>(p);
+  w.hidden_tmp = reinterpret_cast<float*>(p + bp);
+  w.dz = reinterpret_cast<float*>(p);           // backward reuses the same region
+  w.dy = reinterpret_cast<float*>(p + bp);
+  w.dh = reinterpret_cast<float*>(p + 2 * bp);
+  w.partials = reinterpret_cast<float*>(p + 3 * bp);
+  w.total = 3 * bp + part;
+  return w;
+}
+
+}  // namespace mc
+
+using namespace mc;
+
+extern "C" {
+
+size_t mc_proj_head_workspace_bytes(int B, int E, int P, int /*mode*/) {
+  if (B <= 0 || E <= 0 || P <= 0) return 0;
+  return head_ws(nullptr, B, E, P).total;
+}
+
+int mc_proj_head_fwd(const float* x, int B, int E, int P, const float* w_proj, const float* b_proj,
+                     const float* w_fc, const float* b_fc, const float* gamma, const float* beta,
+                     const uint8_t* keep_mask, float p_drop, float eps, int mode, float* projected,
+                     float* hidden, float* z, float* mean, float* rstd, float* out, void* ws,
+                     size_t ws_bytes, void* stream) {
+  MC_ARCH_GUARD();
+  MC_REQUIRE(x && w_proj && b_proj && w_fc && b_fc && gamma && beta && projected && out && ws,
+             MC_ERR_BAD_ARG, "proj_head_fwd: null pointer");
+  MC_REQUIRE(B > 0 && E > 0 && P > 0, MC_ERR_BAD_ARG, "proj_head_fwd: bad sizes B=%d E=%d P=%d", B, E,
+             P);
+  MC_REQUIRE(P % 4 == 0 && P <= 1024, MC_ERR_UNSUPPORTED,
+             "proj_head_fwd: projection_dim %d must be a multiple of 4 and <= 1024", P);
+  MC_REQUIRE(p_drop >= 0.f && p_drop < 1.f, MC_ERR_BAD_ARG, "proj_head_fwd: dropout p=%g", p_drop);
+  MC_REQUIRE(mode == MC_GEMM_SIMT_FP32, MC_ERR_UNSUPPORTED,
+             "proj_head_fwd: only MC_GEMM_SIMT_FP32 is built in this version");
+  MC_REQUIRE(aligned(projected, 16) && aligned(out, 16) && aligned(gamma, 16) && aligned(beta, 16) &&
+                 (!keep_mask || aligned(keep_mask, 4)) && (!z || aligned(z, 16)),
+             MC_ERR_ALIGN, "proj_head_fwd: pointers must be 16-byte aligned");
+  HeadWs w = head_ws(ws, B, E, P);
+  MC_REQUIRE(ws_bytes >= w.total, MC_ERR_WORKSPACE, "proj_head_fwd: workspace %zu < %zu", ws_bytes,
+             w.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* hid = hidden ? hidden : w.hidden_tmp;
+  int rc;
+  SgemmArgs g1{x, E, 1, w_proj, 1, E, projected, P, B, P, E, 1.f, b_proj, hid, 0};
+  if ((rc = sgemm(g1, st))) return rc;
+  SgemmArgs g2{hid, P, 1, w_fc, 1, P, w.y, P, B, P, P, 1.f, b_fc, nullptr, 0};
+  if ((rc = sgemm(g2, st))) return rc;
+  const float scale = 1.f / (1.f - p_drop);
+  MC_DISPATCH_NV(P, (launch_ln_fwd<NV>(w.y, projected, keep_mask, scale, gamma, beta, eps, B, P, z,
+                                       mean, rstd, out, st)));
+  return rc;
+}
+
+int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
+                     const float* w_proj, const float* w_fc, const float* gamma,
+                     const uint8_t* keep_mask, float p_drop, int mode, const float* projected,
+                     const float* hidden, const float* z, const float* mean, const float* rstd,
+                     float* dx, float* dw_proj, float* db_proj, float* dw_fc, float* db_fc,
+                     float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream) {
+  MC_ARCH_GUARD();
+  MC_REQUIRE(grad_out && x && w_proj && w_fc && gamma && projected && hidden && z && mean && rstd &&
+                 dw_proj && db_proj && dw_fc && db_fc && dgamma && dbeta && ws,
+             MC_ERR_BAD_ARG, "proj_head_bwd: null pointer");
+  MC_REQUIRE(B > 0 && E > 0 && P > 0, MC_ERR_BAD_ARG, "proj_head_bwd: bad sizes");
+  MC_REQUIRE(P % 4 == 0 && P <= 1024, MC_ERR_UNSUPPORTED, "proj_head_bwd: projection_dim %d", P);
+  MC_REQUIRE(mode == MC_GEMM_SIMT_FP32, MC_ERR_UNSUPPORTED,
+             "proj_head_bwd: only MC_GEMM_SIMT_FP32 is built in this version");
+  MC_REQUIRE(aligned(grad_out, 16) && aligned(z, 16) && aligned(projected, 16) && aligned(gamma, 16) &&
+                 (!keep_mask || aligned(keep_mask, 4)),
+             MC_ERR_ALIGN, "proj_head_bwd: pointers must be 16-byte aligned");
+  HeadWs w = head_ws(ws, B, E, P);
+  MC_REQUIRE(ws_bytes >= w.total, MC_ERR_WORKSPACE, "proj_head_bwd: workspace %zu < %zu", ws_bytes,
+             w.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float scale = 1.f / (1.f - p_drop);
+  const int blocks = ln_blocks(B);
+  int rc;
+  MC_DISPATCH_NV(P, (launch_ln_bwd<NV>(grad_out, z, mean, rstd, gamma, keep_mask, scale, B, P, w.dz,
+                                       w.dy, w.partials, blocks, st)));
+  if (rc) return rc;
+  // dgamma / dbeta: column sums of the block partials ([blocks][2P] viewed as rows x 2P)
+  {
+    dim3 blk(32, 32);
+    // partial rows are [dgamma(P) | dbeta(P)]
+    colsum_kernel<<<(2 * P + 31) / 32, blk, 0, st>>>(w.partials, blocks, 2 * P, w.dh);
+    MC_LAUNCH_CHECK();
+    MC_CUDA(cudaMemcpyAsync(dgamma, w.dh, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
+    MC_CUDA(cudaMemcpyAsync(dbeta, w.dh + P, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
+    colsum_kernel<<<(P + 31) / 32, blk, 0, st>>>(w.dy, B, P, db_fc);
+    MC_LAUNCH_CHECK();
+  }
+  // dWf[n,k] = sum_m dy[m,n] hidden[m,k]
+  SgemmArgs g1{w.dy, 1, P, hidden, P, 1, dw_fc, P, P, P, B, 1.f, nullptr, nullptr, 0};
+  if ((rc = sgemm(g1, st))) return rc;
+  // dh[m,k] = sum_n dy[m,n] Wf[n,k]
+  SgemmArgs g2{w.dy, P, 1, w_fc, P, 1, w.dh, P, B, P, P, 1.f, nullptr, nullptr, 0};
+  if ((rc = sgemm(g2, st))) return rc;
+  {
+    size_t n4 = (size_t)B * P / 4;
+    int nb = (int)((n4 + 255) / 256);
+    int cap = num_sms() * 8;
+    if (nb > cap) nb = cap;
+    gelu_bwd_add_kernel<<<nb, 256, 0, st>>>(w.dh, projected, w.dz, n4);
+    MC_LAUNCH_CHECK();
+    dim3 blk(32, 32);
+    colsum_kernel<<<(P + 31) / 32, blk, 0, st>>>(w.dh, B, P, db_proj);
+    MC_LAUNCH_CHECK();
+  }
+  // dWp[n,e] = sum_m dp[m,n] x[m,e]
+  SgemmArgs g3{w.dh, 1, P, x, E, 1, dw_proj, E, P, E, B, 1.f, nullptr, nullptr, 0};
+  if ((rc = sgemm(g3, st))) return rc;
+  if (dx) {
+    // dx[m,e] = sum_n dp[m,n] Wp[n,e]
+    SgemmArgs g4{w.dh, P, 1, w_proj, E, 1, dx, E, B, E, P, 1.f, nullptr, nullptr, 0};
+    if ((rc = sgemm(g4, st))) return rc;
+  }
+  return MC_OK;
+}
+
+}  // extern "C"

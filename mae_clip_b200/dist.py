@@ -1,0 +1,145 @@
+"""Global-batch contrastive loss across ranks (SURVEY.md section 8 e; not in the reference, which is
+single-process - the semantics are "the reference loss, ``CLIP.py:34-43``, on the concatenated
+batch").
+
+One process per GPU.  Rank r owns rows [r*b, (r+1)*b) of the global (B, D) embeddings.
+
+  forward   all-gather the local embeddings (NCCL over NVLink)            2 x B x D
+            sweep 1 over the owned (b x B) strip  -> row/col LSE of S, row LSE of Z (owned rows)
+            all-gather the three statistic vectors                         3 x B floats
+            sweep 2 -> row_g, col_sum_p (owned rows) and the loss partial
+            all-gather those + the partial                                  2 x B + W floats
+  backward  sweep 3 -> dI_loc, dT_loc with EVERY term of the owned rows (strip of dS, transposed
+            strip of dS, dZ + dZ^T by symmetry of Z): no gradient reduce-scatter is needed, only the
+            small vectors above ever cross NVLink after the embedding all-gather.
+
+The sweeps are the C-ABI phases ``mc_clip_stats / mc_clip_rowloss / mc_clip_bwd``.  The engine is
+injectable so the collective choreography can be tested on CPU with gloo (tests supply a torch
+engine; the product engine below is CUDA-only).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, cur_stream, lib, ptr, require_cuda, workspace
+
+
+class CudaStripEngine:
+    """The product engine: the three sweeps through the C ABI on this rank's GPU."""
+
+    def __init__(self, mode="simt_fp32"):
+        self.mode = _lib.GEMM_MODES[mode] if isinstance(mode, str) else int(mode)
+
+    def _ws(self, b, B, D, dev):
+        return workspace(lib().mc_clip_loss_workspace_bytes(b, B, D, self.mode), dev)
+
+    def stats(self, I_all, T_all, b, row_offset, tau):
+        require_cuda(I_all, T_all)
+        B, D = I_all.shape
+        dev = I_all.device
+        out = torch.empty(3, b, device=dev, dtype=torch.float32)
+        planes = None
+        with torch.cuda.device(dev):
+            nb = lib().mc_clip_planes_bytes(B, D, self.mode)
+            if nb:
+                # every rank stages all B rows locally from the gathered fp32 embeddings
+                planes = torch.empty(nb, device=dev, dtype=torch.uint8)
+                check(lib().mc_clip_prepare(ptr(I_all), ptr(T_all), B, B, D, 0, self.mode, ptr(planes),
+                                            cur_stream()), "mc_clip_prepare")
+            ws = self._ws(b, B, D, dev)
+            check(lib().mc_clip_stats(ptr(I_all), ptr(T_all), ptr(planes), b, B, D, row_offset,
+                                      float(tau), self.mode, ptr(out[0]), ptr(out[1]), ptr(out[2]),
+                                      ptr(ws), ws.numel(), cur_stream()), "mc_clip_stats")
+        return out, planes
+
+    def rowloss(self, I_all, T_all, planes, b, row_offset, tau, stats_all):
+        B, D = I_all.shape
+        dev = I_all.device
+        out = torch.empty(2, b, device=dev, dtype=torch.float32)
+        part = torch.empty(1, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            ws = self._ws(b, B, D, dev)
+            check(lib().mc_clip_rowloss(ptr(I_all), ptr(T_all), ptr(planes), b, B, D, row_offset,
+                                        float(tau), self.mode, ptr(stats_all[0]), ptr(stats_all[1]),
+                                        ptr(stats_all[2]), ptr(out[0]), ptr(out[1]), ptr(part), ptr(ws),
+                                        ws.numel(), cur_stream()), "mc_clip_rowloss")
+        return out, part
+
+    def bwd(self, I_all, T_all, planes, b, row_offset, tau, stats_all, gq_all, grad_loss):
+        B, D = I_all.shape
+        dev = I_all.device
+        dI = torch.empty(b, D, device=dev, dtype=torch.float32)
+        dT = torch.empty(b, D, device=dev, dtype=torch.float32)
+        gl = grad_loss.reshape(1).to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            ws = self._ws(b, B, D, dev)
+            check(lib().mc_clip_bwd(ptr(I_all), ptr(T_all), ptr(planes), b, B, D, row_offset,
+                                    float(tau), self.mode, ptr(stats_all[0]), ptr(stats_all[1]),
+                                    ptr(stats_all[2]), ptr(gq_all[0]), ptr(gq_all[1]), ptr(gl), ptr(dI),
+                                    ptr(dT), ptr(ws), ws.numel(), cur_stream()), "mc_clip_bwd")
+        return dI, dT
+
+
+def _all_gather_rows(x: torch.Tensor, group) -> torch.Tensor:
+    """(k, b) per rank -> (k, W*b): concatenates along the last dim in rank order."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return x
+    k, b = x.shape
+    buf = torch.empty(world, k, b, device=x.device, dtype=x.dtype)
+    dist.all_gather_into_tensor(buf, x.contiguous(), group=group)
+    return buf.permute(1, 0, 2).reshape(k, world * b).contiguous()
+
+
+class _GlobalClipLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image_emb, text_emb, temperature, engine, group):
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        I = image_emb.detach().float().contiguous()
+        T = text_emb.detach().float().contiguous()
+        b, D = I.shape
+        B = b * world
+        if world > 1:
+            both = torch.stack([I, T])  # one collective for both towers
+            buf = torch.empty(world, 2, b, D, device=I.device, dtype=torch.float32)
+            dist.all_gather_into_tensor(buf, both, group=group)
+            I_all = buf[:, 0].reshape(B, D)
+            T_all = buf[:, 1].reshape(B, D)
+            I_all, T_all = I_all.contiguous(), T_all.contiguous()
+        else:
+            I_all, T_all = I, T
+        row_offset = rank * b
+        stats_loc, planes = engine.stats(I_all, T_all, b, row_offset, temperature)
+        stats_all = _all_gather_rows(stats_loc, group) if world > 1 else stats_loc
+        gq_loc, part = engine.rowloss(I_all, T_all, planes, b, row_offset, temperature, stats_all)
+        if world > 1:
+            gq_all = _all_gather_rows(gq_loc, group)
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+        else:
+            gq_all = gq_loc
+        ctx.engine, ctx.cfg = engine, (b, row_offset, float(temperature))
+        ctx.save_for_backward(I_all, T_all, stats_all, gq_all)
+        ctx.planes = planes
+        ctx.in_dtypes = (image_emb.dtype, text_emb.dtype)
+        return part.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        I_all, T_all, stats_all, gq_all = ctx.saved_tensors
+        b, row_offset, tau = ctx.cfg
+        dI, dT = ctx.engine.bwd(I_all, T_all, ctx.planes, b, row_offset, tau, stats_all, gq_all,
+                                grad_loss)
+        return dI.to(ctx.in_dtypes[0]), dT.to(ctx.in_dtypes[1]), None, None, None
+
+
+def global_clip_loss(image_emb_local, text_emb_local, temperature: float = 1.0, mode="simt_fp32",
+                     group=None, engine=None):
+    """Loss of the reference on the concatenation of every rank's (b, D) embeddings; the value is
+    identical on all ranks and ``backward`` yields d loss_global / d (local embeddings) in full.
+    (Under DDP, which averages parameter gradients over ranks, multiply the loss by the world
+    size to obtain the single-process gradient.)"""
+    engine = engine if engine is not None else CudaStripEngine(mode)
+    return _GlobalClipLoss.apply(image_emb_local, text_emb_local, float(temperature), engine, group)
