@@ -1,0 +1,470 @@
+#!/usr/bin/env python
+"""Benchmark of the mae_clip training-loss hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload c4|c2] [--mode tc_bf16x3|tc_bf16|simt_fp32] [--batch B]
+
+Workload (BASELINE.json): the metric "contrastive+MAE loss fwd/bwd samples/s at 1/2/4/8 B200; % TC
+/HBM roofline" is quoted on config 4, the global-batch contrastive loss at B = 32768, D = 256: it
+is the only config that names 1..8 GPUs, it fits one B200 because no B x B tensor is ever
+materialised, and the tensor-core roofline is only meaningful at that size (C2's B = 1024 is a
+3.8 GFLOP, launch-bound problem).  The global batch is FIXED as N grows ("strong" scaling): rank r
+owns rows [r B/N, (r+1) B/N).  A step = one forward + backward of the loss over the whole global
+batch from fp32 embeddings already in HBM: stage operands, row/col statistics sweep, row-loss
+sweep, gradient sweep (+ NCCL all-gathers when N > 1).  At N = 1 the line also carries the C2
+latency and C5 MAE numbers under "extra".
+
+e2e is the same step through the C-ABI entry point that takes HOST buffers
+(mc_clip_loss_fwd_bwd_host at N = 1; pinned-host shards -> H2D -> dist loss -> D2H at N > 1).
+
+--impl reference times the reference's own CPU implementation of the path (the op-for-op oracle
+port of CLIP.py:34-43 + autograd; the Python reference cannot travel to the GPU box) with all host
+threads on a bounded sample; see cpu_baseline.sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D_EMB = 256
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2"])
+    ap.add_argument("--mode", default="auto")
+    ap.add_argument("--batch", type=int, default=0, help="global batch (default: 32768 for c4, 1024 for c2)")
+    ap.add_argument("--cpu-sample-batch", type=int, default=4096)
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_shard(b, seed, scale=1.0):
+    """Embeddings with the distribution ProjectionHead emits (LayerNorm'd gaussian rows)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(b, D_EMB, generator=g)
+    return torch.nn.functional.layer_norm(x, (D_EMB,)) * scale
+
+
+def cpu_reference_leg(args, B_work, steps, warmup):
+    """The oracle port of the reference loss (CLIP.py:34-43 + autograd) on host cores."""
+    import torch
+
+    from oracle import loss_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = min(args.cpu_sample_batch, B_work)
+    I = make_shard(Bs, 0)
+    T = make_shard(Bs, 1)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss_ref.clip_loss_fwd_bwd_ref(I, T, 1.0)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    raw = Bs / t
+    # cost per sample is linear in B (the loss is O(B^2 D)): project the sample to the workload's B
+    value = raw * (Bs / B_work)
+    sample = (f"full reference loss fwd+bwd (oracle port, torch CPU fp32, {cores} threads) at B={Bs}: "
+              f"{t * 1e3:.1f} ms/step = {raw:.0f} samples/s at that B; projected to the workload's B={B_work} "
+              f"by the O(B^2) cost (x {Bs}/{B_work})") if Bs != B_work else \
+             (f"full reference loss fwd+bwd (oracle port, torch CPU fp32, {cores} threads) at B={Bs}: "
+              f"{t * 1e3:.1f} ms/step")
+    return {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample,
+            "ms_per_sample_step": t * 1e3, "sample_batch": Bs}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.batch or (32768 if args.workload == "c4" else 1024)
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    cb = cpu_reference_leg(args, B, steps, warmup)
+    line = {"impl": "reference", "metric": "contrastive loss fwd+bwd samples/s", "value": cb["value"],
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": cb["ms_per_sample_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": workload_config(args, B, "cpu"),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, B, mode):
+    name = ("c4: global-batch contrastive soft-target loss fwd+bwd, B=%d D=%d, rows sharded over ranks" % (B, D_EMB)
+            if args.workload == "c4" else
+            "c2: CLIP loss-only microbench fwd+bwd, B=%d D=%d fp32" % (B, D_EMB))
+    return {"workload": name, "global_batch": B, "dim": D_EMB, "temperature": 1.0, "engine": mode,
+            "parallelism": f"row-sharded x{args.gpus}", "l2": "flushed between timed steps (256 MiB write)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def pick_mode(args):
+    from mae_clip_b200 import _lib
+    if args.mode != "auto":
+        return args.mode
+    return "tc_bf16x3" if _lib.lib().mc_clip_planes_bytes(128, D_EMB, _lib.GEMM_MODES["tc_bf16x3"]) > 256 \
+        else "simt_fp32"
+
+
+class Phases:
+    """One step on one rank through the C ABI, with CUDA events between the phases so the dominant
+    kernel's duration is measured live on the launching stream."""
+
+    def __init__(self, B, b, row_offset, mode, device):
+        import torch
+
+        from mae_clip_b200 import _lib
+        self.torch, self._lib, self.lib = torch, _lib, _lib.lib()
+        self.B, self.b, self.off, self.mode = B, b, row_offset, _lib.GEMM_MODES[mode]
+        f32 = dict(device=device, dtype=torch.float32)
+        self.stats_loc = torch.empty(3, b, **f32)
+        self.gq_loc = torch.empty(2, b, **f32)
+        self.part = torch.empty(1, **f32)
+        self.dI = torch.empty(b, D_EMB, **f32)
+        self.dT = torch.empty(b, D_EMB, **f32)
+        nb = self.lib.mc_clip_planes_bytes(B, D_EMB, self.mode)
+        self.planes = torch.empty(max(nb, 1), device=device, dtype=torch.uint8)
+        nws = self.lib.mc_clip_loss_workspace_bytes(b, B, D_EMB, self.mode)
+        self.ws = torch.empty(max(nws, 1), device=device, dtype=torch.uint8)
+        self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
+    def step(self, I_all, T_all, gather_vec=None, record=False):
+        lib, ck, p = self.lib, self._lib.check, self._lib.ptr
+        st = self._lib.cur_stream()
+        B, b, off, mode = self.B, self.b, self.off, self.mode
+        ev = self.ev
+        if record: ev[0].record()
+        ck(lib.mc_clip_prepare(p(I_all), p(T_all), B, B, D_EMB, 0, mode, p(self.planes), st), "prepare")
+        if record: ev[1].record()
+        ck(lib.mc_clip_stats(p(I_all), p(T_all), p(self.planes), b, B, D_EMB, off, 1.0, mode, p(self.stats_loc[0]),
+                             p(self.stats_loc[1]), p(self.stats_loc[2]), p(self.ws), self.ws.numel(), st), "stats")
+        stats_all = gather_vec(self.stats_loc) if gather_vec else self.stats_loc
+        if record: ev[2].record()
+        ck(lib.mc_clip_rowloss(p(I_all), p(T_all), p(self.planes), b, B, D_EMB, off, 1.0, mode, p(stats_all[0]),
+                               p(stats_all[1]), p(stats_all[2]), p(self.gq_loc[0]), p(self.gq_loc[1]), p(self.part),
+                               p(self.ws), self.ws.numel(), st), "rowloss")
+        gq_all = gather_vec(self.gq_loc) if gather_vec else self.gq_loc
+        if record: ev[3].record()
+        ck(lib.mc_clip_bwd(p(I_all), p(T_all), p(self.planes), b, B, D_EMB, off, 1.0, mode, p(stats_all[0]),
+                           p(stats_all[1]), p(stats_all[2]), p(gq_all[0]), p(gq_all[1]), None, p(self.dI), p(self.dT),
+                           p(self.ws), self.ws.numel(), st), "bwd")
+        if record: ev[4].record()
+        return self.part
+
+    def phase_ms(self):
+        e = self.ev
+        return [e[i].elapsed_time(e[i + 1]) for i in range(4)]
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from mae_clip_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    B = args.batch or (32768 if args.workload == "c4" else 1024)
+    assert B % world == 0
+    b = B // world
+    mode = pick_mode(args)
+    lib = _lib.lib()
+    peaks = load_peaks()
+
+    # this rank's shard; C4 seeds 1000 + r per 4096-row block so the global batch is the same for every N
+    blk = 4096 if B % 4096 == 0 and b % 4096 == 0 else b
+    shard_I = torch.cat([make_shard(blk, 1000 + (rank * b) // blk + i) for i in range(b // blk)])
+    shard_T = torch.cat([make_shard(blk, 5000 + (rank * b) // blk + i) for i in range(b // blk)])
+    host_I, host_T = shard_I.pin_memory(), shard_T.pin_memory()
+    I_loc, T_loc = host_I.to(dev), host_T.to(dev)
+
+    def gather_rows(x):  # (b, D) per rank -> (B, D)
+        if world == 1:
+            return x
+        out = torch.empty(world * x.shape[0], x.shape[1], device=dev, dtype=x.dtype)
+        dist.all_gather_into_tensor(out, x)
+        return out
+
+    def gather_vec(x):  # (k, b) per rank -> (k, B)
+        k = x.shape[0]
+        buf = torch.empty(world, k, b, device=dev, dtype=x.dtype)
+        dist.all_gather_into_tensor(buf.view(-1), x.contiguous().view(-1))
+        return buf.permute(1, 0, 2).reshape(k, B).contiguous()
+
+    ph = Phases(B, b, rank * b, mode, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def one_step(record=False):
+        I_all, T_all = gather_rows(I_loc), gather_rows(T_loc)
+        part = ph.step(I_all, T_all, gather_vec if world > 1 else None, record=record)
+        if world > 1:
+            dist.all_reduce(part)
+        return part
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = lib.mc_kernel_launch_count()
+    total_ms, phase_ms = 0.0, [0.0] * 4
+    for _ in range(args.steps):
+        flush.fill_(1)  # evict L2 between timed iterations (outside the timed region)
+        barrier()
+        t_start.record()
+        one_step(record=True)
+        t_end.record()
+        barrier()
+        total_ms += t_start.elapsed_time(t_end)
+        for i, v in enumerate(ph.phase_ms()):
+            phase_ms[i] += v
+    launches = lib.mc_kernel_launch_count() - launches0
+    loss_val = float(ph.part.item())
+    tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = tmax.item()
+    ms_per_step = total_ms / args.steps
+    value = B / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers in, loss + gradients out, copies inside the timed region
+    e2e_ms = 0.0
+    h2d = 2 * b * D_EMB * 4
+    d2h = 2 * b * D_EMB * 4 + 4
+    if world == 1:
+        nws = lib.mc_clip_loss_host_workspace_bytes(B, D_EMB, _lib.GEMM_MODES[mode])
+        dws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        out_dI, out_dT = torch.empty_like(host_I).pin_memory(), torch.empty_like(host_T).pin_memory()
+        out_loss = torch.zeros(1).pin_memory()
+        st = torch.cuda.current_stream().cuda_stream
+
+        def e2e_step():
+            _lib.check(lib.mc_clip_loss_fwd_bwd_host(host_I.data_ptr(), host_T.data_ptr(), B, D_EMB, 1.0,
+                                                     _lib.GEMM_MODES[mode], out_loss.data_ptr(), out_dI.data_ptr(),
+                                                     out_dT.data_ptr(), dws.data_ptr(), nws, ctypes.c_void_p(st)),
+                       "mc_clip_loss_fwd_bwd_host")
+    else:
+        out_dI, out_dT = torch.empty_like(host_I).pin_memory(), torch.empty_like(host_T).pin_memory()
+        out_loss = torch.zeros(1).pin_memory()
+
+        def e2e_step():
+            Il = host_I.to(dev, non_blocking=True)
+            Tl = host_T.to(dev, non_blocking=True)
+            part = ph.step(gather_rows(Il), gather_rows(Tl), gather_vec)
+            dist.all_reduce(part)
+            out_dI.copy_(ph.dI, non_blocking=True)
+            out_dT.copy_(ph.dT, non_blocking=True)
+            out_loss.copy_(part, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    e_steps = max(1, min(args.steps, 5))
+    for _ in range(e_steps):
+        flush.fill_(1)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms += (time.perf_counter() - t0) * 1e3
+    emax = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(emax, op=dist.ReduceOp.MAX)
+    e2e_value = B / (emax.item() / e_steps * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        flops_step = 14.0 * B * B * D_EMB / world          # algorithmic, this rank's strip
+        bwd_ms = phase_ms[3] / args.steps
+        flops_bwd = 8.0 * B * B * D_EMB / world            # the gradient sweep: 4 GEMMs
+        achieved = flops_bwd / (bwd_ms * 1e-3) / 1e12
+        peak = peaks["tc_sustained"] or peaks["tc_burst"]
+        line = {
+            "metric": "contrastive loss fwd+bwd samples/s", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": {"simt_fp32": "fp32", "tc_bf16x3": "fp32 (fp16 hi+lo split operands, 3 tcgen05 passes, fp32 accumulate)",
+                      "tc_bf16": "fp16 operands, fp32 accumulate"}[mode],
+            "data": "synthetic", "config": workload_config(args, B, mode), "loss": loss_val,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "ms_per_step": emax.item() / e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "phases_ms": {"prepare": phase_ms[0] / args.steps, "stats": phase_ms[1] / args.steps,
+                          "rowloss": phase_ms[2] / args.steps, "bwd": bwd_ms},
+            "roofline": {"bound": "tensor", "kernel": "gradient sweep (mc_clip_bwd)", "achieved": achieved,
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": peaks["source"] + ", bf16 sustained", "traffic": None,
+                         "algorithmic_flops_per_launch": flops_bwd,
+                         "step_achieved": flops_step / (ms_per_step * 1e-3) / 1e12,
+                         "step_frac": flops_step / (ms_per_step * 1e-3) / 1e12 / peak},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cb = cpu_reference_leg(args, B, 2, 1)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if not args.no_extra and world == 1:
+            line["extra"] = extras(dev, mode, peaks)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extras(dev, mode, peaks):
+    """C2 latency and C5 MAE numbers (not the headline; same process, CUDA events, L2 not flushed
+    for the latency figure, inputs > L2 for the MAE sweeps)."""
+    import torch
+
+    import mae_clip_b200 as m
+    out = {}
+
+    def timeit(fn, iters=20, warm=5):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    I = make_shard(1024, 0).to(dev).requires_grad_(True)
+    T = make_shard(1024, 1).to(dev).requires_grad_(True)
+
+    def c2():
+        I.grad = T.grad = None
+        m.clip_contrastive_loss(I, T, 1.0, mode=mode).backward()
+    ms = timeit(c2)
+    out["c2_loss_fwd_bwd_B1024"] = {"ms": ms, "samples_per_s": 1024 / (ms * 1e-3)}
+
+    N, L, P = 1024, 196, 768
+    x = torch.randn(N, L, P, device=dev)
+    noise = torch.rand(N, L, device=dev)
+    imgs = torch.randn(N, 3, 224, 224, device=dev)
+    pred = torch.randn(N, L, P, device=dev, requires_grad=True)
+    keep = int(L * 0.25)
+    ms = timeit(lambda: m.random_masking(x, 0.75, noise), iters=10)
+    bytes_m1 = 16 * N * L + 2 * N * keep * P * 4
+    out["c5_random_masking_N1024_r075"] = {"ms": ms, "GBps": bytes_m1 / ms / 1e6, "frac_hbm": bytes_m1 / ms / 1e6 / peaks["hbm"]}
+    _xm, mask, _r = m.random_masking(x, 0.75, noise)
+    r_eff = (L - keep) / L
+    ms_f = timeit(lambda: m.masked_mse_loss(pred.detach(), imgs, mask), iters=10)
+    bytes_f = r_eff * N * L * P * 8 + 4 * N * L
+    out["c5_masked_mse_fwd_N1024_r075"] = {"ms": ms_f, "GBps": bytes_f / ms_f / 1e6, "frac_hbm": bytes_f / ms_f / 1e6 / peaks["hbm"]}
+
+    def fb():
+        pred.grad = None
+        m.masked_mse_loss(pred, imgs, mask).backward()
+    ms_fb = timeit(fb, iters=10)
+    bytes_fb = 2 * bytes_f + N * L * P * 4
+    out["c5_masked_mse_fwd_bwd_N1024_r075"] = {"ms": ms_fb, "GBps": bytes_fb / ms_fb / 1e6,
+                                               "frac_hbm": bytes_fb / ms_fb / 1e6 / peaks["hbm"],
+                                               "samples_per_s": N / (ms_fb * 1e-3)}
+    return out
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

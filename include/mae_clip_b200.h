@@ -52,6 +52,9 @@ typedef enum {
 int mc_version(void);                       /* major*10000 + minor*100 + patch */
 const char* mc_last_error_string(void);
 int mc_device_supported(int device);        /* 1 when `device` is compute capability 10.x */
+/* kernels launched by this library since load (process-wide, monotonic): callers difference it
+ * around a region to count launches */
+unsigned long long mc_kernel_launch_count(void);
 
 /* ---------------------------------------------------------------------------
  * L5  cross_entropy(preds, targets, reduction)            CLIP.py:46-52

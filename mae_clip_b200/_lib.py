@@ -29,6 +29,7 @@ SIGNATURES = {
     "mc_version": (_i, []),
     "mc_last_error_string": (C.c_char_p, []),
     "mc_device_supported": (_i, [_i]),
+    "mc_kernel_launch_count": (C.c_ulonglong, []),
     "mc_soft_ce_fwd": (_i, [_p, _i64, _i64, _p, _i64, _i64, _i, _i, _p, _p, _p, _p]),
     "mc_soft_ce_bwd": (_i, [_p, _i64, _i64, _p, _i64, _i64, _i, _i, _p, _p, _p, _p, _i64, _i64, _p,
                             _i64, _i64, _p]),

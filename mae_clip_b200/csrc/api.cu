@@ -1,11 +1,16 @@
 // Version, error string and architecture guard of the C ABI (include/mae_clip_b200.h).
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace mc {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -44,6 +49,10 @@ extern "C" {
 int mc_version(void) { return 0 * 10000 + 1 * 100 + 0; }
 
 const char* mc_last_error_string(void) { return mc::g_err; }
+
+unsigned long long mc_kernel_launch_count(void) {
+  return mc::g_launches.load(std::memory_order_relaxed);
+}
 
 int mc_device_supported(int device) {
   int major = 0;

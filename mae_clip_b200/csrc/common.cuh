@@ -33,7 +33,14 @@ int arch_check();  // MC_OK when the current device is compute capability 10.x
     }                                                                              \
   } while (0)
 
-#define MC_LAUNCH_CHECK() MC_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this: error check + launch counter
+// (mc_kernel_launch_count(): bench.py reports how many of OUR kernels ran in the timed region)
+void count_launch();
+#define MC_LAUNCH_CHECK()          \
+  do {                             \
+    ::mc::count_launch();          \
+    MC_CUDA(cudaGetLastError());   \
+  } while (0)
 
 #define MC_ARCH_GUARD()            \
   do {                             \

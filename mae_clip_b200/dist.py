@@ -88,9 +88,16 @@ def _all_gather_rows(x: torch.Tensor, group) -> torch.Tensor:
     if world == 1:
         return x
     k, b = x.shape
-    buf = torch.empty(world, k, b, device=x.device, dtype=x.dtype)
-    dist.all_gather_into_tensor(buf, x.contiguous(), group=group)
+    buf = _all_gather(x, group)
     return buf.permute(1, 0, 2).reshape(k, world * b).contiguous()
+
+
+def _all_gather(x: torch.Tensor, group) -> torch.Tensor:
+    """x (any shape) per rank -> (world, *x.shape); flat 1-D buffers so NCCL and gloo agree."""
+    world = dist.get_world_size(group)
+    buf = torch.empty((world,) + tuple(x.shape), device=x.device, dtype=x.dtype)
+    dist.all_gather_into_tensor(buf.view(-1), x.contiguous().view(-1), group=group)
+    return buf
 
 
 class _GlobalClipLoss(torch.autograd.Function):
@@ -104,8 +111,7 @@ class _GlobalClipLoss(torch.autograd.Function):
         B = b * world
         if world > 1:
             both = torch.stack([I, T])  # one collective for both towers
-            buf = torch.empty(world, 2, b, D, device=I.device, dtype=torch.float32)
-            dist.all_gather_into_tensor(buf, both, group=group)
+            buf = _all_gather(both, group)
             I_all = buf[:, 0].reshape(B, D)
             T_all = buf[:, 1].reshape(B, D)
             I_all, T_all = I_all.contiguous(), T_all.contiguous()

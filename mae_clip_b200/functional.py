@@ -41,6 +41,9 @@ class _SoftCE(torch.autograd.Function):
         loss = torch.empty(rows, device=preds.device, dtype=torch.float32)
         lse = torch.empty_like(loss)
         tsum = torch.empty_like(loss)
+        if rows == 0:  # empty tensors have no storage to point at
+            ctx.save_for_backward(preds, targets, lse, tsum)
+            return loss
         with torch.cuda.device(preds.device):
             check(lib().mc_soft_ce_fwd(ptr(preds), preds.stride(0), preds.stride(1), ptr(targets),
                                        targets.stride(0), targets.stride(1), rows, cols, ptr(loss),
@@ -54,6 +57,8 @@ class _SoftCE(torch.autograd.Function):
         rows, cols = preds.shape
         grad = _f32c(grad)
         need_p, need_t = ctx.needs_input_grad
+        if rows == 0:
+            return (torch.zeros_like(preds) if need_p else None, torch.zeros_like(targets) if need_t else None)
         # gradients take the memory layout of their inputs so stores stay coalesced for `.T` views
         dp = torch.empty_strided(preds.shape, preds.stride(), device=preds.device,
                                  dtype=torch.float32) if need_p and _dense(preds) else (
@@ -211,9 +216,14 @@ class _RandomMasking(torch.autograd.Function):
         ids_restore = torch.empty(N, L, device=dev, dtype=torch.int64)
         ids_keep = torch.empty(N, len_keep, device=dev, dtype=torch.int64)
         with torch.cuda.device(dev):
-            check(lib().mc_random_masking(ptr(x), x.element_size(), ptr(noise), N, L, Dm, len_keep,
-                                          ptr(x_masked), ptr(mask), ptr(ids_restore), ptr(ids_keep),
-                                          cur_stream()), "mc_random_masking")
+            if len_keep > 0 and N > 0:
+                check(lib().mc_random_masking(ptr(x), x.element_size(), ptr(noise), N, L, Dm, len_keep,
+                                              ptr(x_masked), ptr(mask), ptr(ids_restore), ptr(ids_keep),
+                                              cur_stream()), "mc_random_masking")
+            elif N > 0:  # nothing kept: indices and mask only (empty tensors have no storage)
+                check(lib().mc_random_masking(None, x.element_size(), ptr(noise), N, L, Dm, 0, None,
+                                              ptr(mask), ptr(ids_restore), None, cur_stream()),
+                      "mc_random_masking")
         ctx.save_for_backward(mask, ids_restore)
         ctx.cfg = (N, L, Dm, len_keep)
         ctx.mark_non_differentiable(mask, ids_restore, ids_keep)

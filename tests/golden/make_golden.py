@@ -57,6 +57,9 @@ def gen_loss_cases(ref_clip):
         "b48_soft_tau05": dict(B=48, scale=0.25, tau=0.5, dup=False),
         "b33_dup_tau2": dict(B=33, scale=0.35, tau=2.0, dup=True),
         "b130_soft": dict(B=130, scale=0.2, tau=1.0, dup=False),
+        # genuinely soft targets: Z_ii = 256 * 0.08^2 * tau / ... ~ 2, so P is far from one-hot and
+        # the gradient through the (non-detached) targets is O(1) of the total
+        "b64_verysoft": dict(B=64, scale=0.08, tau=1.5, dup=True),
     }
     out = {}
     for name, c in cases.items():

@@ -1,0 +1,145 @@
+"""GPU parity of ProjectionHead (modules.py:55-76) and the CLIPModel.forward glue (CLIP.py:23-43)
+against the fixtures of the unmodified reference: same weights, same inputs, and the dropout keep
+masks the reference itself drew ("identical inputs and noise")."""
+import pytest
+import torch
+from torch import nn
+
+from conftest import rel_err
+from oracle import proj_head_ref
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ["projection.weight", "projection.bias", "fc.weight", "fc.bias", "layer_norm.weight", "layer_norm.bias"]
+OUT_TOL, GRAD_TOL, LOSS_TOL = 1e-5, 1e-3, 1e-4
+
+
+def _head(z, tag, E, mode):
+    import mae_clip_b200 as m
+    h = m.ProjectionHead(E, gemm_mode=mode)
+    h.load_state_dict({k: torch.from_numpy(z[f"{tag}.{k}"]) for k in KEYS})
+    return h.cuda()
+
+
+@pytest.mark.parametrize("mode", ["simt_fp32", "tc_bf16x3"])
+def test_head_eval_golden(golden, mode):
+    z = golden("proj_head_model")
+    for tag, E in (("img", 160), ("txt", 96)):
+        h = _head(z, tag, E, mode).eval()
+        with torch.no_grad():
+            out = h(torch.from_numpy(z[f"x_{tag}"]).cuda())
+        assert rel_err(out, z[f"ref_eval_out_{tag}"]) < OUT_TOL
+
+
+class _Feed(nn.Module):
+    def forward(self, input_ids=None, attention_mask=None):
+        return input_ids
+
+
+class _MaskedHead(nn.Module):
+    """Feeds the reference's recorded dropout mask into the drop-in head."""
+
+    def __init__(self, head, keep):
+        super().__init__()
+        self.head, self.keep = head, keep
+
+    def forward(self, x):
+        return self.head(x, keep_mask=self.keep)
+
+
+@pytest.mark.parametrize("mode", ["simt_fp32", "tc_bf16x3"])
+@pytest.mark.parametrize("tt,tau", [("tau1", 1.0), ("tau05", 0.5)])
+def test_model_train_step_golden(golden, tt, tau, mode):
+    """heads (train mode, reference masks) + loss, forward and backward, through CLIPModel.forward."""
+    import mae_clip_b200 as m
+    z = golden("proj_head_model")
+    hi, ht = _head(z, "img", 160, mode), _head(z, "txt", 96, mode)
+    model = m.CLIPModel(temperature=tau, image_embedding=160, text_embedding=96, image_encoder=nn.Identity(),
+                        text_encoder=_Feed(), gemm_mode=mode)
+    model.image_projection = _MaskedHead(hi, torch.from_numpy(z[f"{tt}.keep_img"]).cuda())
+    model.text_projection = _MaskedHead(ht, torch.from_numpy(z[f"{tt}.keep_txt"]).cuda())
+    model.train()
+    xi = torch.from_numpy(z["x_img"]).cuda().requires_grad_(True)
+    xt = torch.from_numpy(z["x_txt"]).cuda().requires_grad_(True)
+    loss = model({"image": xi, "input_ids": xt, "attention_mask": None})
+    assert loss.dim() == 0 and loss.grad_fn is not None
+    loss.backward()
+    ref = float(z[f"{tt}.ref_loss"])
+    assert abs(loss.item() - ref) < LOSS_TOL * abs(ref)
+    assert rel_err(xi.grad, z[f"{tt}.ref_dx_img"]) < GRAD_TOL
+    assert rel_err(xt.grad, z[f"{tt}.ref_dx_txt"]) < GRAD_TOL
+    if tt == "tau1":
+        for tag, h in (("img", hi), ("txt", ht)):
+            for k, p in h.named_parameters():
+                assert rel_err(p.grad, z[f"tau1.ref_grad.{tag}.{k}"]) < GRAD_TOL, (tag, k)
+
+
+def test_model_eval_loss_golden(golden):
+    import mae_clip_b200 as m
+    z = golden("proj_head_model")
+    model = m.CLIPModel(image_embedding=160, text_embedding=96, image_encoder=nn.Identity(), text_encoder=_Feed())
+    model.image_projection, model.text_projection = _head(z, "img", 160, None), _head(z, "txt", 96, None)
+    model.eval()
+    with torch.no_grad():
+        loss = model({"image": torch.from_numpy(z["x_img"]).cuda(), "input_ids": torch.from_numpy(z["x_txt"]).cuda(),
+                      "attention_mask": None})
+    assert abs(loss.item() - float(z["ref_eval_loss"])) < LOSS_TOL * abs(float(z["ref_eval_loss"]))
+
+
+@pytest.mark.parametrize("B,E", [(1, 768), (32, 2048), (256, 768), (1000, 2048)])
+@pytest.mark.parametrize("need_dx", [True, False])
+def test_head_vs_oracle(B, E, need_dx):
+    """Reference shapes (E = 2048 image / 768 text; the text tower is frozen so dx is optional,
+    modules.py:35) with a seeded dropout mask, against the CPU oracle."""
+    import mae_clip_b200 as m
+    g = torch.Generator().manual_seed(B + E)
+    h = m.ProjectionHead(E)
+    with torch.no_grad():
+        h.layer_norm.weight.mul_(0.5).add_(torch.randn(256, generator=g) * 0.05)
+        h.layer_norm.bias.add_(torch.randn(256, generator=g) * 0.1)
+    x = torch.randn(B, E, generator=g)
+    keep = (torch.rand(B, 256, generator=g) > 0.1).to(torch.uint8)
+    go = torch.randn(B, 256, generator=g)
+    params = [p.detach().clone() for p in h.parameters()]
+    out_ref, grads = proj_head_ref.proj_head_fwd_bwd_ref(x, params, keep, 0.1, go, need_dx=need_dx)
+    hc = h.cuda().train()
+    xc = x.cuda().requires_grad_(need_dx)
+    out = hc(xc, keep_mask=keep.cuda())
+    out.backward(go.cuda())
+    assert rel_err(out, out_ref) < OUT_TOL
+    names = ["w_proj", "b_proj", "w_fc", "b_fc", "ln_w", "ln_b"]
+    for n, p in zip(names, hc.parameters()):
+        assert rel_err(p.grad, grads[n]) < GRAD_TOL, n
+    if need_dx:
+        assert rel_err(xc.grad, grads["x"]) < GRAD_TOL
+    else:
+        assert xc.grad is None
+
+
+def test_head_train_mode_draws_dropout():
+    """Without an injected mask, train mode drops ~p of the fc outputs and eval mode none."""
+    import mae_clip_b200 as m
+    h = m.ProjectionHead(64).cuda()
+    x = torch.randn(512, 64, device="cuda")
+    h.eval()
+    with torch.no_grad():
+        a, b = h(x), h(x)
+    assert torch.equal(a, b)
+    h.train()
+    with torch.no_grad():
+        c = h(x)
+    assert not torch.equal(a, c)
+    assert c.shape == (512, 256) and torch.isfinite(c).all()
+    # LayerNorm output: rows have mean ~0 / var ~1 at default affine
+    assert c.mean(1).abs().max() < 1e-4 and (c.var(1, unbiased=False) - 1).abs().max() < 1e-2
+
+
+def test_head_leading_dims_and_nograd():
+    import mae_clip_b200 as m
+    h = m.ProjectionHead(48).cuda().eval()
+    x = torch.randn(3, 5, 48, device="cuda")
+    with torch.no_grad():
+        out = h(x)
+    assert out.shape == (3, 5, 256)
+    ref = proj_head_ref.proj_head_ref(x.cpu().reshape(15, 48), *[p.detach().cpu() for p in h.parameters()])
+    assert rel_err(out.reshape(15, 256), ref) < OUT_TOL
