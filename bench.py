@@ -2,7 +2,7 @@
 """Benchmark of the mae_clip training-loss hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--workload c4|c2] [--mode tc_bf16x3|tc_bf16|simt_fp32] [--batch B]
+                    [--workload c4|c2] [--mode tc_f16x3|tc_f16|simt_fp32] [--batch B]
 
 Workload (BASELINE.json): the metric "contrastive+MAE loss fwd/bwd samples/s at 1/2/4/8 B200; % TC
 /HBM roofline" is quoted on config 4, the global-batch contrastive loss at B = 32768, D = 256: it
@@ -182,7 +182,7 @@ def pick_mode(args):
     from mae_clip_b200 import _lib
     if args.mode != "auto":
         return args.mode
-    return "tc_bf16x3" if _lib.lib().mc_clip_planes_bytes(128, D_EMB, _lib.GEMM_MODES["tc_bf16x3"]) > 256 \
+    return "tc_f16x3" if _lib.lib().mc_clip_planes_bytes(128, D_EMB, _lib.GEMM_MODES["tc_f16x3"]) > 256 \
         else "simt_fp32"
 
 
@@ -381,8 +381,8 @@ def run_b200(args):
             "metric": "contrastive loss fwd+bwd samples/s", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"simt_fp32": "fp32", "tc_bf16x3": "fp32 (fp16 hi+lo split operands, 3 tcgen05 passes, fp32 accumulate)",
-                      "tc_bf16": "fp16 operands, fp32 accumulate"}[mode],
+            "dtype": {"simt_fp32": "fp32", "tc_f16x3": "fp32 (fp16 hi+lo split operands, 3 tcgen05 passes, fp32 accumulate)",
+                      "tc_f16": "fp16 operands, fp32 accumulate"}[mode],
             "data": "synthetic", "config": workload_config(args, B, mode), "loss": loss_val,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": emax.item() / e_steps},

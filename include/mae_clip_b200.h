@@ -44,9 +44,10 @@ typedef enum {
 /* precision / engine of the contrastive-loss and projection GEMMs */
 typedef enum {
   MC_GEMM_SIMT_FP32 = 0, /* plain fp32 FMA tiles (bring-up / cross-check path)            */
-  MC_GEMM_TC_BF16X3 = 1, /* tcgen05 kind::f16, operands split hi+mid bf16, 3 passes:
-                            ~2^-17 relative operand error, meets the fp32 tolerance        */
-  MC_GEMM_TC_BF16 = 2    /* tcgen05 kind::f16, single bf16 pass (looser tolerance)         */
+  MC_GEMM_TC_F16X3 = 1, /* tcgen05 kind::f16, operands split into fp16 hi + lo planes, 3 passes
+                            (hi*hi + hi*lo + lo*hi): ~2^-22 relative operand error, fp32 accumulate:
+                            meets the fp32 tolerance                                       */
+  MC_GEMM_TC_F16 = 2    /* tcgen05 kind::f16, single fp16 pass (looser, stated tolerance)  */
 } mc_gemm_mode;
 
 int mc_version(void);                       /* major*10000 + minor*100 + patch */
@@ -94,7 +95,7 @@ int mc_soft_ce_bwd(const float* preds, int64_t p_row_stride, int64_t p_col_strid
  * ------------------------------------------------------------------------- */
 size_t mc_clip_loss_workspace_bytes(int b, int B, int D, int mode);
 
-/* prepare(): mode-specific operand staging (bf16 hi/mid planes for the tcgen05 modes; no-op for
+/* prepare(): mode-specific operand staging (fp16 hi/lo planes for the tcgen05 modes; no-op for
  * SIMT).  `planes_all` receives the staged copy of the *local* rows at row_offset; when B > b the
  * caller all-gathers the planes instead of the fp32 embeddings.  planes layout: see DESIGN.md. */
 size_t mc_clip_planes_bytes(int B, int D, int mode);

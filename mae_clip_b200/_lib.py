@@ -14,9 +14,9 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libmae_clip_b200.so")
 
 GEMM_SIMT_FP32 = 0
-GEMM_TC_BF16X3 = 1
-GEMM_TC_BF16 = 2
-GEMM_MODES = {"simt_fp32": GEMM_SIMT_FP32, "tc_bf16x3": GEMM_TC_BF16X3, "tc_bf16": GEMM_TC_BF16}
+GEMM_TC_F16X3 = 1
+GEMM_TC_F16 = 2
+GEMM_MODES = {"simt_fp32": GEMM_SIMT_FP32, "tc_f16x3": GEMM_TC_F16X3, "tc_f16": GEMM_TC_F16}
 
 _p = C.c_void_p
 _i = C.c_int

@@ -20,5 +20,5 @@ size = 224
 projection_dim = 256
 dropout = 0.1
 
-# engine of the contrastive-loss / projection GEMMs: "simt_fp32", "tc_bf16x3" or "tc_bf16"
+# engine of the contrastive-loss / projection GEMMs: "simt_fp32", "tc_f16x3" or "tc_f16"
 gemm_mode = "simt_fp32"

@@ -13,9 +13,15 @@ static int check_problem(const char* who, const float* I_all, const float* T_all
   MC_REQUIRE(row_offset >= 0 && row_offset + b <= B, MC_ERR_BAD_ARG, "%s: row_offset %d out of range",
              who, row_offset);
   MC_REQUIRE(tau > 0.f, MC_ERR_BAD_ARG, "%s: temperature must be positive (got %g)", who, tau);
-  MC_REQUIRE(mode >= MC_GEMM_SIMT_FP32 && mode <= MC_GEMM_TC_BF16, MC_ERR_BAD_ARG, "%s: bad mode %d",
+  MC_REQUIRE(mode >= MC_GEMM_SIMT_FP32 && mode <= MC_GEMM_TC_F16, MC_ERR_BAD_ARG, "%s: bad mode %d",
              who, mode);
   return MC_OK;
+}
+
+// Shapes the tcgen05 engine does not cover (D not a multiple of 64 or > 256) run on the fp32 SIMT
+// engine: same device, same ABI, true-fp32 arithmetic - never a CPU path.
+static int eff_mode(int mode, int D) {
+  return (mode != MC_GEMM_SIMT_FP32 && !tc::supported(D)) ? (int)MC_GEMM_SIMT_FP32 : mode;
 }
 
 struct FusedLayout {
@@ -23,10 +29,11 @@ struct FusedLayout {
   size_t vec_stride;
 };
 static FusedLayout fused_layout(int B, int D, int mode) {
+  mode = eff_mode(mode, D);
   FusedLayout l;
   l.vec_stride = round_up((size_t)B * 4, 256);
   l.off_vec = 0;
-  l.off_planes = 5 * l.vec_stride + 256;  // + loss scalar slot
+  l.off_planes = round_up(5 * l.vec_stride + 256, 1024);  // + loss scalar slot; planes 1024-aligned
   size_t planes = (mode == MC_GEMM_SIMT_FP32) ? 0 : tc::planes_bytes(B, D, mode);
   l.off_phase = l.off_planes + round_up(planes, 256);
   size_t phase = (mode == MC_GEMM_SIMT_FP32) ? simt::workspace_bytes(B, B, D)
@@ -43,11 +50,12 @@ extern "C" {
 
 size_t mc_clip_loss_workspace_bytes(int b, int B, int D, int mode) {
   if (b <= 0 || B <= 0 || D <= 0) return 0;
+  mode = eff_mode(mode, D);
   return mode == MC_GEMM_SIMT_FP32 ? simt::workspace_bytes(b, B, D) : tc::workspace_bytes(b, B, D, mode);
 }
 
 size_t mc_clip_planes_bytes(int B, int D, int mode) {
-  if (B <= 0 || D <= 0 || mode == MC_GEMM_SIMT_FP32) return 0;
+  if (B <= 0 || D <= 0 || eff_mode(mode, D) == MC_GEMM_SIMT_FP32) return 0;
   return tc::planes_bytes(B, D, mode);
 }
 
@@ -57,7 +65,8 @@ int mc_clip_prepare(const float* I_loc, const float* T_loc, int b, int B, int D,
   MC_REQUIRE(I_loc && T_loc, MC_ERR_BAD_ARG, "clip_prepare: null pointer");
   MC_REQUIRE(b > 0 && B >= b && D > 0 && row_offset >= 0 && row_offset + b <= B, MC_ERR_BAD_ARG,
              "clip_prepare: bad sizes");
-  if (mode == MC_GEMM_SIMT_FP32) return MC_OK;
+  MC_REQUIRE(mode >= MC_GEMM_SIMT_FP32 && mode <= MC_GEMM_TC_F16, MC_ERR_BAD_ARG, "clip_prepare: bad mode %d", mode);
+  if (eff_mode(mode, D) == MC_GEMM_SIMT_FP32) return MC_OK;
   MC_REQUIRE(planes_all, MC_ERR_BAD_ARG, "clip_prepare: planes_all is null");
   return tc::prepare(I_loc, T_loc, b, B, D, row_offset, mode, planes_all,
                      static_cast<cudaStream_t>(stream));
@@ -72,6 +81,7 @@ int mc_clip_stats(const float* I_all, const float* T_all, const void* planes_all
   MC_REQUIRE(r_loc && c_loc && rz_loc && ws, MC_ERR_BAD_ARG, "clip_stats: null output/workspace");
   ClipProblem p{I_all, T_all, planes_all, b, B, D, row_offset, tau};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mode = eff_mode(mode, D);
   if (mode == MC_GEMM_SIMT_FP32) return simt::stats(p, r_loc, c_loc, rz_loc, ws, ws_bytes, st);
   return tc::stats(p, mode, r_loc, c_loc, rz_loc, ws, ws_bytes, st);
 }
@@ -88,6 +98,7 @@ int mc_clip_rowloss(const float* I_all, const float* T_all, const void* planes_a
   ClipProblem p{I_all, T_all, planes_all, b, B, D, row_offset, tau};
   ClipStatsAll s{r_all, c_all, rz_all, nullptr, nullptr};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mode = eff_mode(mode, D);
   if (mode == MC_GEMM_SIMT_FP32) return simt::rowloss(p, s, g_loc, q_loc, loss_part, ws, ws_bytes, st);
   return tc::rowloss(p, mode, s, g_loc, q_loc, loss_part, ws, ws_bytes, st);
 }
@@ -104,6 +115,7 @@ int mc_clip_bwd(const float* I_all, const float* T_all, const void* planes_all, 
   ClipProblem p{I_all, T_all, planes_all, b, B, D, row_offset, tau};
   ClipStatsAll s{r_all, c_all, rz_all, g_all, q_all};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mode = eff_mode(mode, D);
   if (mode == MC_GEMM_SIMT_FP32) return simt::bwd(p, s, grad_loss, dI_loc, dT_loc, ws, ws_bytes, st);
   return tc::bwd(p, mode, s, grad_loss, dI_loc, dT_loc, ws, ws_bytes, st);
 }

@@ -31,6 +31,7 @@ int bwd(const ClipProblem& p, const ClipStatsAll& s, const float* grad_loss, flo
 }  // namespace simt
 
 namespace tc {
+bool supported(int D);  // embedding widths the tcgen05 engine covers (others run on the fp32 SIMT engine)
 size_t workspace_bytes(int b, int B, int D, int mode);
 size_t planes_bytes(int B, int D, int mode);
 int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row_offset, int mode,

@@ -1,29 +1,957 @@
-// L3-L6, engines MC_GEMM_TC_BF16X3 / MC_GEMM_TC_BF16: tcgen05 fused tiles (placeholder until the
-// kernels land; every entry reports MC_ERR_UNSUPPORTED so nothing silently falls back).
+// L3-L6, engines MC_GEMM_TC_F16X3 / MC_GEMM_TC_F16: the contrastive soft-target loss on the 5th-gen
+// tensor cores.  Reference arithmetic: /root/reference CLIP.py:34-43 and its autograd (main.py:58),
+// closed form in SURVEY.md section 8 row L6.  No B x B tensor ever reaches HBM: every sweep
+// recomputes the 128 x 128 tiles of
+//     S  = T_i I_j^T / tau      St = I_i T_j^T / tau  (= S_ji)      Z = (I_i I_j^T + T_i T_j^T) tau/2
+// in tensor memory and reduces them in the epilogue.
+//
+// Execution model (one kernel template, three phases):
+//   * a CTA PAIR (cluster of 2, tcgen05 cta_group::2, M = 128) owns 128 samples i, 64 per CTA; the
+//     64 x N accumulator tile of a CTA lives in TMEM as 128 lanes x N/2 columns (lanes 0-63: first
+//     half of the tile's columns, lanes 64-127: second half);
+//   * operands are fp16 planes of X = [I || T] (row-scaled by a power of two): `hi` = fp16(x),
+//     `lo` = fp16(x - hi).  F16X3 issues hi*hi + hi*lo + lo*hi (relative operand error ~2^-22, i.e.
+//     fp32-class logits); F16 issues hi*hi only;
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA) + TMEM allocator, warps 2-5 = epilogue
+//     (one thread per TMEM lane).  The hi plane of the pair's own rows stays resident in shared
+//     memory for the whole job; lo planes and the column tiles stream through an mbarrier ring;
+//   * the gradient sweep converts each tile into fp16 weight tiles (dS, dS^T, dZ + dZ^T) in shared
+//     memory and feeds them straight back to the tensor cores against X^T tiles, accumulating
+//     dT_i and dI_i (64 x D each per CTA) in TMEM for the whole job.
 #include "clip_loss.cuh"
+#include "tc_ptx.cuh"
 
 namespace mc {
 namespace tc {
 
-size_t workspace_bytes(int, int, int, int) { return 256; }
-size_t planes_bytes(int, int, int) { return 256; }
-int prepare(const float*, const float*, int, int, int, int, int, void*, cudaStream_t) {
-  set_error("tcgen05 contrastive-loss engine not built yet");
-  return MC_ERR_UNSUPPORTED;
+using namespace ptx;
+
+constexpr int kTileN = 128;             // columns j per pair tile
+constexpr int kRowsCta = 64;            // samples per CTA
+constexpr int kChunkBytes = 64 * 128;   // 64 rows x 64 fp16
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kMaxSplit = 16;
+
+enum Phase { kStats = 0, kRowLoss = 1, kBwd = 2 };
+
+// shared-memory map (offsets from a 1024-byte aligned base)
+constexpr int kOffA = 0;                      // resident hi plane of the CTA's 64 rows: 2D/64 chunks
+constexpr int kOffStage = 65536;              // TMA ring, 96 KB
+constexpr int kStageRegion = 98304;
+constexpr int kOffW = kOffStage + kStageRegion;   // three 64 x 64 fp16 weight half-tiles (24 KB)
+constexpr int kOffXT = kOffW + 3 * kChunkBytes;   // X^T half tiles: 2 x (D/2 rows x 64 j) (<= 32 KB)
+constexpr int kOffConst = kOffXT + 32768;         // per-column constants, 2 x 128 x 8 floats
+constexpr int kOffBar = kOffConst + 8192;
+constexpr int kSmemBytes = kOffBar + 256 + 1024;  // + alignment slack
+
+enum Bar {
+  kFull0 = 0,        // +stage (<= 6)
+  kEmpty0 = 6,       // +stage
+  kAFull = 12,
+  kJobDone = 13,
+  kTmemFull0 = 14,   // +buf
+  kTmemEmpty0 = 16,  // +buf
+  kWFull = 18,
+  kGradDone = 19,
+  kXTFull = 20,
+  kAccFull = 21,
+  kAccEmpty = 22,
+  kNumBars = 23
+};
+
+struct PairParams {
+  int b, B, Bp, D, row_offset;
+  int n_row_blocks, n_tiles, nsplit, tiles_per_split, bpad;
+  float inv_tau, half_tau, inv_2B;
+  const float* colfac;                 // [Bp] 1 / row scale
+  const float *r, *c, *rz, *g, *q;     // length-B statistics (phase dependent, may be null)
+  float* part;                         // partial results of this phase
+  const float* wscale;                 // gradient sweep: power-of-two scale of the fp16 weight tiles
+};
+
+struct PlanesLayout {
+  size_t off_colfac, off_norm_i, off_norm_t, off_hi, off_lo, off_hiT, total;
+  int Bp;
+};
+static PlanesLayout planes_layout(int B, int D) {
+  PlanesLayout l;
+  l.Bp = (int)round_up((size_t)B, 128);
+  size_t plane = (size_t)l.Bp * 2 * D * sizeof(__half);
+  size_t vec = round_up((size_t)l.Bp * 4, 1024);
+  l.off_colfac = 0;           // 1 / row scale
+  l.off_norm_i = vec;         // ||I_i||_2
+  l.off_norm_t = 2 * vec;     // ||T_i||_2
+  l.off_hi = 3 * vec;
+  l.off_lo = l.off_hi + plane;
+  l.off_hiT = l.off_lo + plane;
+  l.total = l.off_hiT + plane;
+  return l;
 }
-int stats(const ClipProblem&, int, float*, float*, float*, void*, size_t, cudaStream_t) {
-  set_error("tcgen05 contrastive-loss engine not built yet");
-  return MC_ERR_UNSUPPORTED;
+
+bool supported(int D) { return D % 64 == 0 && D >= 64 && D <= 256; }
+
+// ------------------------------------------------------------------------------------------
+// staging: fp32 embeddings -> scaled fp16 hi / lo planes of X = [I || T], the per-row scale, and
+// the transposed hi plane (K-major B operand of the gradient GEMMs).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stage_planes_kernel(const float* __restrict__ I_loc,
+                                                           const float* __restrict__ T_loc, int b, int B,
+                                                           int Bp, int D, int row_offset, int rows_total,
+                                                           __half* __restrict__ Xh, __half* __restrict__ Xl,
+                                                           float* __restrict__ colfac, float* __restrict__ norm_i,
+                                                           float* __restrict__ norm_t) {
+  const int wrow = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wrow >= rows_total) return;
+  // rows [0, b): local rows; rows [b, rows_total): zero padding rows B .. Bp-1
+  const bool pad = wrow >= b;
+  const int gi = pad ? (B + (wrow - b)) : (row_offset + wrow);
+  const int K2 = 2 * D;
+  __half* xh = Xh + (size_t)gi * K2;
+  __half* xl = Xl + (size_t)gi * K2;
+  if (pad) {
+    for (int k = lane; k < K2; k += 32) { xh[k] = __float2half_rn(0.f); xl[k] = __float2half_rn(0.f); }
+    if (lane == 0) { colfac[gi] = 1.f; norm_i[gi] = 0.f; norm_t[gi] = 0.f; }
+    return;
+  }
+  const float* pi = I_loc + (size_t)wrow * D;
+  const float* pt = T_loc + (size_t)wrow * D;
+  float amax = 0.f, ni = 0.f, nt = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float a = pi[k], c = pt[k];
+    amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(c)));
+    ni = fmaf(a, a, ni);
+    nt = fmaf(c, c, nt);
+  }
+  amax = warp_max(amax);
+  ni = warp_sum(ni);
+  nt = warp_sum(nt);
+  // power-of-two scale bringing the row's largest magnitude into [1, 2): exact in fp32; hi keeps 11
+  // significant bits of every element and hi + lo is exact to ~2^-25 of the row maximum for any
+  // finite input, however large or small
+  float s = 1.f;
+  if (amax > 0.f && amax < INFINITY) {
+    int e;
+    frexpf(amax, &e);        // amax = f * 2^e, f in [0.5, 1)
+    s = ldexpf(1.f, 1 - e);  // amax * s in [1, 2)
+  }
+  for (int k = lane; k < K2; k += 32) {
+    float x = (k < D ? pi[k] : pt[k - D]) * s;
+    __half h = __float2half_rn(x);
+    xh[k] = h;
+    xl[k] = __float2half_rn(x - __half2float(h));
+  }
+  if (lane == 0) { colfac[gi] = 1.f / s; norm_i[gi] = sqrtf(ni); norm_t[gi] = sqrtf(nt); }
 }
-int rowloss(const ClipProblem&, int, const ClipStatsAll&, float*, float*, float*, void*, size_t,
-            cudaStream_t) {
-  set_error("tcgen05 contrastive-loss engine not built yet");
-  return MC_ERR_UNSUPPORTED;
+
+// XhT[k][j] = Xh[j][k] for j in [j_begin, j_end), 64 x 64 tiles through shared memory
+__global__ void __launch_bounds__(256) transpose_hi_kernel(const __half* __restrict__ Xh,
+                                                           __half* __restrict__ XhT, int Bp, int K2, int j_begin,
+                                                           int j_end) {
+  __shared__ __half tile[64][66];
+  const int j0 = j_begin + blockIdx.x * 64, k0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+  for (int r = ty; r < 64; r += 4) {
+    int j = j0 + r;
+    tile[r][tx] = (j < j_end) ? Xh[(size_t)j * K2 + k0 + tx] : __float2half_rn(0.f);
+  }
+  __syncthreads();
+  for (int r = ty; r < 64; r += 4) {
+    int j = j0 + tx;
+    if (j < j_end) XhT[(size_t)(k0 + r) * Bp + j] = tile[tx][r];
+  }
 }
-int bwd(const ClipProblem&, int, const ClipStatsAll&, const float*, float*, float*, void*, size_t,
-        cudaStream_t) {
-  set_error("tcgen05 contrastive-loss engine not built yet");
-  return MC_ERR_UNSUPPORTED;
+
+// ------------------------------------------------------------------------------------------
+// the pair kernel
+// ------------------------------------------------------------------------------------------
+template <int PASSES>
+struct StageCfg {
+  static constexpr int kStageBytes = (PASSES == 3 ? 6 : 2) * kChunkBytes;
+  static constexpr int kStages = kStageRegion / kStageBytes;  // 2 (x3) or 6 (x1)
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct OnlineLse2 {  // running log2-domain log-sum-exp
+  float m, s;
+  __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; }
+  __device__ __forceinline__ void add32(const float* x) {
+    float cm = x[0];
+#pragma unroll
+    for (int e = 1; e < 32; ++e) cm = fmaxf(cm, x[e]);
+    const float mn = fmaxf(m, cm);
+    if (mn == -INFINITY) return;
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) acc += ex2f(x[e] - mn);
+    s = s * ex2f(m - mn) + acc;
+    m = mn;
+  }
+  __device__ __forceinline__ void merge(float m2, float s2) {
+    const float mn = fmaxf(m, m2);
+    if (mn == -INFINITY) return;
+    s = s * ex2f(m - mn) + s2 * ex2f(m2 - mn);
+    m = mn;
+  }
+};
+
+template <int PHASE, int PASSES>
+__global__ void __launch_bounds__(kThreads, 1)
+pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+            const __grid_constant__ CUtensorMap map_t, const PairParams p) {
+  using SC = StageCfg<PASSES>;
+  constexpr int kStages = SC::kStages;
+  constexpr int kStageBytes = SC::kStageBytes;
+  constexpr int kNBuf = (PHASE == kBwd) ? 1 : 2;   // TMEM tile buffers (3 x 64 columns each)
+  constexpr uint32_t kAccCol = 256;                // gradient accumulators: dT at 256, dI at 256 + D/2
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* const sbase = smem_raw + (base - raw);
+  const uint32_t bar0 = base + kOffBar;
+  auto bar = [&](int i) -> uint32_t { return bar0 + 8u * i; };
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(sbase + kOffBar + 8 * kNumBars);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int D = p.D, nkc = D >> 6;
+  const int njobs = p.n_row_blocks * p.nsplit;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kFull0 + s), 1); mbar_init(bar(kEmpty0 + s), 1); }
+    mbar_init(bar(kAFull), 1);
+    mbar_init(bar(kJobDone), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(kTmemFull0 + i), 1); mbar_init(bar(kTmemEmpty0 + i), 2 * kEpiThreads); }
+    mbar_init(bar(kWFull), 2 * kEpiThreads);
+    mbar_init(bar(kGradDone), 1);
+    mbar_init(bar(kXTFull), 1);
+    mbar_init(bar(kAccFull), 1);
+    mbar_init(bar(kAccEmpty), 2 * kEpiThreads);
+    fence_mbar_init();
+    prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_b_hi); prefetch_tmap(&map_b_lo);
+    prefetch_tmap(&map_t);
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(smem_u32(tmem_slot), 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================================================== TMA producer (one lane per CTA)
+    if (lane == 0) {
+      uint32_t it = 0, hh = 0, jj = 0;
+      for (int job = pair_id; job < njobs; job += npairs, ++jj) {
+        const int rb = job / p.nsplit, sp = job % p.nsplit;
+        const int row_a = p.row_offset + rb * 128 + (int)rank * kRowsCta;
+        const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+        mbar_wait(bar(kJobDone), (jj & 1) ^ 1);
+        if (leader) mbar_arrive_expect_tx(bar(kAFull), 2u * 2u * nkc * kChunkBytes);
+        for (int c = 0; c < 2 * nkc; ++c) tma_load_2d_pair(base + kOffA + c * kChunkBytes, &map_a_hi, bar(kAFull), c * 64, row_a);
+        for (int t = t0; t < t1; ++t) {
+          const int j0 = t * kTileN + 32 * (int)rank, j1 = j0 + 64;
+          for (int c = 0; c < nkc; ++c, ++it) {
+            const uint32_t stage = it % kStages, par = (it / kStages) & 1;
+            mbar_wait(bar(kEmpty0 + stage), par ^ 1);
+            const uint32_t fb = bar(kFull0 + stage);
+            if (leader) mbar_arrive_expect_tx(fb, 2u * kStageBytes);
+            const uint32_t sb = base + kOffStage + stage * kStageBytes;
+            const int ci = c * 64, ct = D + c * 64;
+            if (PASSES == 3) {
+              tma_load_2d_pair(sb + 0 * kChunkBytes, &map_a_lo, fb, ci, row_a);            // I_i lo
+              tma_load_2d_pair(sb + 1 * kChunkBytes, &map_a_lo, fb, ct, row_a);            // T_i lo
+              tma_load_2d_pair(sb + 2 * kChunkBytes, &map_b_hi, fb, ci, j0);               // I_j hi
+              tma_load_2d_pair(sb + 2 * kChunkBytes + 4096, &map_b_hi, fb, ci, j1);
+              tma_load_2d_pair(sb + 3 * kChunkBytes, &map_b_lo, fb, ci, j0);               // I_j lo
+              tma_load_2d_pair(sb + 3 * kChunkBytes + 4096, &map_b_lo, fb, ci, j1);
+              tma_load_2d_pair(sb + 4 * kChunkBytes, &map_b_hi, fb, ct, j0);               // T_j hi
+              tma_load_2d_pair(sb + 4 * kChunkBytes + 4096, &map_b_hi, fb, ct, j1);
+              tma_load_2d_pair(sb + 5 * kChunkBytes, &map_b_lo, fb, ct, j0);               // T_j lo
+              tma_load_2d_pair(sb + 5 * kChunkBytes + 4096, &map_b_lo, fb, ct, j1);
+            } else {
+              tma_load_2d_pair(sb + 0 * kChunkBytes, &map_b_hi, fb, ci, j0);               // I_j hi
+              tma_load_2d_pair(sb + 0 * kChunkBytes + 4096, &map_b_hi, fb, ci, j1);
+              tma_load_2d_pair(sb + 1 * kChunkBytes, &map_b_hi, fb, ct, j0);               // T_j hi
+              tma_load_2d_pair(sb + 1 * kChunkBytes + 4096, &map_b_hi, fb, ct, j1);
+            }
+          }
+          if (PHASE == kBwd) {
+            const uint32_t xt_bytes = (uint32_t)(D / 2) * 128u;  // D/2 rows x 64 j fp16
+            for (int h = 0; h < 2; ++h, ++hh) {
+              mbar_wait(bar(kGradDone), (hh & 1) ^ 1);
+              if (leader) mbar_arrive_expect_tx(bar(kXTFull), 2u * 2u * xt_bytes);
+              const int jx = t * kTileN + 64 * h;
+              tma_load_2d_pair(base + kOffXT, &map_t, bar(kXTFull), jx, (int)rank * (D / 2));
+              tma_load_2d_pair(base + kOffXT + xt_bytes, &map_t, bar(kXTFull), jx, D + (int)rank * (D / 2));
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer (leader CTA, one lane)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc_tile = idesc_f16(128, kTileN);
+      const uint32_t idesc_grad = idesc_f16(128, D);
+      uint32_t it = 0, tt = 0, hh = 0, jj = 0;
+      for (int job = pair_id; job < njobs; job += npairs, ++jj) {
+        const int sp = job % p.nsplit;
+        const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+        mbar_wait(bar(kAFull), jj & 1);
+        tc_fence_after();
+        for (int t = t0; t < t1; ++t, ++tt) {
+          const uint32_t buf = tt % kNBuf, use = tt / kNBuf;
+          mbar_wait(bar(kTmemEmpty0 + buf), (use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tS = tmem_base + buf * 192, tSt = tS + 64, tZ = tS + 128;
+          for (int c = 0; c < nkc; ++c, ++it) {
+            const uint32_t stage = it % kStages, par = (it / kStages) & 1;
+            mbar_wait(bar(kFull0 + stage), par);
+            tc_fence_after();
+            const uint32_t sb = base + kOffStage + stage * kStageBytes;
+            const uint64_t aI = smem_desc_sw128(base + kOffA + c * kChunkBytes);
+            const uint64_t aT = smem_desc_sw128(base + kOffA + (nkc + c) * kChunkBytes);
+            uint64_t aIl = 0, aTl = 0, bI, bIl = 0, bT, bTl = 0;
+            if (PASSES == 3) {
+              aIl = smem_desc_sw128(sb + 0 * kChunkBytes);
+              aTl = smem_desc_sw128(sb + 1 * kChunkBytes);
+              bI = smem_desc_sw128(sb + 2 * kChunkBytes);
+              bIl = smem_desc_sw128(sb + 3 * kChunkBytes);
+              bT = smem_desc_sw128(sb + 4 * kChunkBytes);
+              bTl = smem_desc_sw128(sb + 5 * kChunkBytes);
+            } else {
+              bI = smem_desc_sw128(sb + 0 * kChunkBytes);
+              bT = smem_desc_sw128(sb + 1 * kChunkBytes);
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
+              const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
+              const uint64_t kbI = desc_advance_k(bI, ks), kbT = desc_advance_k(bT, ks);
+              // S = T_i I_j^T
+              mma_f16_pair(tS, kT, kbI, idesc_tile, acc);
+              if (PASSES == 3) {
+                mma_f16_pair(tS, kT, desc_advance_k(bIl, ks), idesc_tile, 1u);
+                mma_f16_pair(tS, desc_advance_k(aTl, ks), kbI, idesc_tile, 1u);
+              }
+              // St = I_i T_j^T
+              if (PHASE != kRowLoss) {
+                mma_f16_pair(tSt, kI, kbT, idesc_tile, acc);
+                if (PASSES == 3) {
+                  mma_f16_pair(tSt, kI, desc_advance_k(bTl, ks), idesc_tile, 1u);
+                  mma_f16_pair(tSt, desc_advance_k(aIl, ks), kbT, idesc_tile, 1u);
+                }
+              }
+              // Z = I_i I_j^T + T_i T_j^T
+              mma_f16_pair(tZ, kI, kbI, idesc_tile, acc);
+              mma_f16_pair(tZ, kT, kbT, idesc_tile, 1u);
+              if (PASSES == 3) {
+                mma_f16_pair(tZ, kI, desc_advance_k(bIl, ks), idesc_tile, 1u);
+                mma_f16_pair(tZ, desc_advance_k(aIl, ks), kbI, idesc_tile, 1u);
+                mma_f16_pair(tZ, kT, desc_advance_k(bTl, ks), idesc_tile, 1u);
+                mma_f16_pair(tZ, desc_advance_k(aTl, ks), kbT, idesc_tile, 1u);
+              }
+            }
+            mma_commit_pair(bar(kEmpty0 + stage), 3);
+          }
+          mma_commit_pair(bar(kTmemFull0 + buf), 3);
+          if (PHASE == kBwd) {
+            if (t == t0) {
+              mbar_wait(bar(kAccEmpty), (jj & 1) ^ 1);
+              tc_fence_after();
+            }
+            const uint32_t tDT = tmem_base + kAccCol, tDI = tDT + (uint32_t)(D / 2);
+            const uint32_t xt_bytes = (uint32_t)(D / 2) * 128u;
+            const uint64_t wS = smem_desc_sw128(base + kOffW), wSt = smem_desc_sw128(base + kOffW + kChunkBytes);
+            const uint64_t wZ = smem_desc_sw128(base + kOffW + 2 * kChunkBytes);
+            const uint64_t xI = smem_desc_sw128(base + kOffXT), xT = smem_desc_sw128(base + kOffXT + xt_bytes);
+            for (int h = 0; h < 2; ++h, ++hh) {
+              mbar_wait(bar(kWFull), hh & 1);
+              mbar_wait(bar(kXTFull), hh & 1);
+              tc_fence_after();
+              const uint32_t first = (t == t0 && h == 0) ? 0u : 1u;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
+                const uint64_t kxI = desc_advance_k(xI, ks), kxT = desc_advance_k(xT, ks);
+                const uint64_t kwZ = desc_advance_k(wZ, ks);
+                mma_f16_pair(tDT, desc_advance_k(wS, ks), kxI, idesc_grad, acc);   // dT += (dS/tau) I_j
+                mma_f16_pair(tDT, kwZ, kxT, idesc_grad, 1u);                       // dT += (tau/2 dZs) T_j
+                mma_f16_pair(tDI, desc_advance_k(wSt, ks), kxT, idesc_grad, acc);  // dI += (dS^T/tau) T_j
+                mma_f16_pair(tDI, kwZ, kxI, idesc_grad, 1u);                       // dI += (tau/2 dZs) I_j
+              }
+              mma_commit_pair(bar(kGradDone), 3);
+            }
+          }
+        }
+        if (PHASE == kBwd) mma_commit_pair(bar(kAccFull), 3);
+        mma_commit_pair(bar(kJobDone), 3);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================================== epilogue: one thread per TMEM lane
+    const int quarter = warp & 3;
+    const int lane_t = quarter * 32 + lane;
+    const int m = lane_t & 63, n1 = lane_t >> 6;
+    const int tid_e = threadIdx.x - 64;
+    const uint32_t lane_field = (uint32_t)(quarter * 32) << 16;
+    float* const consts = reinterpret_cast<float*>(sbase + kOffConst);  // [2][128][8]
+    const float kL2e = 1.4426950408889634f;
+    uint32_t tt = 0, hh = 0, jj = 0;
+    for (int job = pair_id; job < njobs; job += npairs, ++jj) {
+      const int rb = job / p.nsplit, sp = job % p.nsplit;
+      const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+      const int lrow = rb * 128 + (int)rank * kRowsCta + m;  // row within this rank's strip
+      const int gi = p.row_offset + lrow;
+      const bool row_ok = lrow < p.b;
+      const float rowfac = p.colfac[gi];  // gi < Bp always
+      const float fS = rowfac * p.inv_tau, fZ = rowfac * p.half_tau;
+      float r_i = 0.f, c_i = 0.f, rz_i = 0.f, g_i = 0.f, q_i = 0.f;
+      if (PHASE != kStats && row_ok) { r_i = p.r[gi]; c_i = p.c[gi]; rz_i = p.rz[gi]; }
+      if (PHASE == kBwd && row_ok) { g_i = p.g[gi]; q_i = p.q[gi]; }
+      const float wsc = (PHASE == kBwd) ? *p.wscale : 1.f;
+      OnlineLse2 lS, lSt, lZ;
+      lS.init(); lSt.init(); lZ.init();
+      float acc_g = 0.f, acc_q = 0.f;
+
+      for (int t = t0; t < t1; ++t, ++tt) {
+        // ---- per-column constants of this tile -> shared memory (column jl handled by thread jl)
+        float* cst = consts + (tt & 1) * (128 * 8);
+        {
+          const int j = t * kTileN + tid_e;
+          const bool ok = j < p.B;
+          float4 a, b2;
+          a.x = (PHASE == kBwd && ok) ? p.r[j] : 0.f;
+          a.y = (PHASE != kStats && ok) ? p.c[j] : 0.f;
+          a.z = (PHASE != kStats && ok) ? p.rz[j] * kL2e : 0.f;
+          a.w = (PHASE == kBwd && ok) ? p.g[j] : 0.f;
+          b2.x = (PHASE == kBwd && ok) ? p.q[j] : 0.f;
+          b2.y = p.colfac[j];           // j < Bp
+          if (PHASE == kBwd) {          // weight factors: colfac_j * {1/tau, tau/2} * wscale
+            a.w *= 2.f * (float)p.B;    // 2B g_j
+            b2.z = b2.y * p.inv_tau * wsc;
+            b2.w = b2.y * p.half_tau * wsc;
+          } else {
+            b2.z = ok ? 0.f : -INFINITY;  // additive mask for the log-domain values
+            b2.w = 0.f;
+          }
+          reinterpret_cast<float4*>(cst)[tid_e * 2] = a;
+          reinterpret_cast<float4*>(cst)[tid_e * 2 + 1] = b2;
+        }
+        named_bar_sync(1, kEpiThreads);
+        const uint32_t buf = tt % kNBuf, use = tt / kNBuf;
+        mbar_wait(bar(kTmemFull0 + buf), use & 1);
+        tc_fence_after();
+        const uint32_t tS = tmem_base + buf * 192 + lane_field, tSt = tS + 64, tZ = tS + 128;
+
+        if (PHASE == kStats) {
+          const float fS2 = fS * kL2e, fZ2 = fZ * kL2e;
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            const float* cc = cst + (64 * h + 32 * n1) * 8;
+            float v[32];
+            tmem_ld32(tS + 32 * h, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = fmaf(v[e], fS2 * cc[e * 8 + 5], cc[e * 8 + 6]);
+            lS.add32(v);
+            tmem_ld32(tSt + 32 * h, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = fmaf(v[e], fS2 * cc[e * 8 + 5], cc[e * 8 + 6]);
+            lSt.add32(v);
+            tmem_ld32(tZ + 32 * h, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = fmaf(v[e], fZ2 * cc[e * 8 + 5], cc[e * 8 + 6]);
+            lZ.add32(v);
+          }
+          tc_fence_before();
+          mbar_arrive_cluster(bar(kTmemEmpty0 + buf), 0);
+        } else if (PHASE == kRowLoss) {
+          const float fZ2 = fZ * kL2e, rz2_i = rz_i * kL2e;
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            const float* cc = cst + (64 * h + 32 * n1) * 8;
+            float vs[32], vz[32];
+            tmem_ld32(tS + 32 * h, vs);
+            tmem_ld32(tZ + 32 * h, vz);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float cf = cc[e * 8 + 5];
+              const float s = vs[e] * (fS * cf);
+              const float z2 = fmaf(vz[e], fZ2 * cf, cc[e * 8 + 6]);
+              const float P = ex2f(z2 - rz2_i);
+              const float G = (r_i + cc[e * 8 + 1]) - 2.f * s;  // 2B * G_ij
+              acc_g = fmaf(P, G, acc_g);
+              acc_q += ex2f(z2 - cc[e * 8 + 2]);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive_cluster(bar(kTmemEmpty0 + buf), 0);
+        } else {
+          // ---- gradient sweep: tile -> fp16 weight half-tiles -> tensor cores
+          const float r2_i = r_i * kL2e, c2_i = c_i * kL2e, rz2_i = rz_i * kL2e;
+          const float g2B_i = g_i * (2.f * (float)p.B);
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h, ++hh) {
+            const float* cc = cst + (64 * h + 32 * n1) * 8;
+            float vs[32], vt[32], vz[32];
+            tmem_ld32(tS + 32 * h, vs);
+            tmem_ld32(tSt + 32 * h, vt);
+            tmem_ld32(tZ + 32 * h, vz);
+            tmem_ld_wait();
+            if (h == 1) {
+              tc_fence_before();
+              mbar_arrive_cluster(bar(kTmemEmpty0 + buf), 0);
+            }
+            uint32_t wS[16], wSt[16], wZ[16];
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              float ms[2], mst[2], mz[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const float4 ca = *reinterpret_cast<const float4*>(cc + (e + u) * 8);      // r_j c_j rz2_j 2B*g_j
+                const float4 cb = *reinterpret_cast<const float4*>(cc + (e + u) * 8 + 4);  // q_j colfac_j wS_j wZ_j
+                const float cf = cb.y;
+                const float s = vs[e + u] * (fS * cf), st = vt[e + u] * (fS * cf), z = vz[e + u] * (fZ * cf);
+                const float z2 = z * kL2e;
+                const float e1 = ex2f(fmaf(s, kL2e, -r2_i));           // softmax_row(S)_ij
+                const float e2 = ex2f(fmaf(s, kL2e, -ca.y * kL2e));    // softmax_col(S)_ij
+                const float e3 = ex2f(fmaf(st, kL2e, -ca.x * kL2e));   // softmax_row(S)_ji
+                const float e4 = ex2f(fmaf(st, kL2e, -c2_i));          // softmax_col(S)_ji
+                const float P = ex2f(z2 - rz2_i), Pt = ex2f(z2 - ca.z);
+                const float dS = fmaf(e2, cb.x, e1) - 2.f * P;         // 2B dS_ij
+                const float dSt = fmaf(e4, q_i, e3) - 2.f * Pt;        // 2B dS_ji
+                const float G = (r_i + ca.y) - 2.f * s;                // 2B G_ij
+                const float Gt = (ca.x + c_i) - 2.f * st;              // 2B G_ji
+                const float dZs = fmaf(P, G - g2B_i, Pt * (Gt - ca.w));
+                ms[u] = dS * cb.z;
+                mst[u] = dSt * cb.z;
+                mz[u] = dZs * cb.w;
+              }
+              __half2 a = __floats2half2_rn(ms[0], ms[1]), b2 = __floats2half2_rn(mst[0], mst[1]);
+              __half2 c2 = __floats2half2_rn(mz[0], mz[1]);
+              wS[e >> 1] = *reinterpret_cast<uint32_t*>(&a);
+              wSt[e >> 1] = *reinterpret_cast<uint32_t*>(&b2);
+              wZ[e >> 1] = *reinterpret_cast<uint32_t*>(&c2);
+            }
+            // the previous half's gradient MMAs must have drained the weight buffers
+            mbar_wait(bar(kGradDone), (hh & 1) ^ 1);
+            // row m of a 64 x 64 fp16 tile (128 B rows, SWIZZLE_128B): this thread owns K = 32 n1 .. +31
+            uint8_t* wrow = sbase + kOffW + m * 128;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int chunk = ((4 * n1 + k) ^ (m & 7)) * 16;
+              *reinterpret_cast<uint4*>(wrow + chunk) = make_uint4(wS[4 * k], wS[4 * k + 1], wS[4 * k + 2], wS[4 * k + 3]);
+              *reinterpret_cast<uint4*>(wrow + kChunkBytes + chunk) =
+                  make_uint4(wSt[4 * k], wSt[4 * k + 1], wSt[4 * k + 2], wSt[4 * k + 3]);
+              *reinterpret_cast<uint4*>(wrow + 2 * kChunkBytes + chunk) =
+                  make_uint4(wZ[4 * k], wZ[4 * k + 1], wZ[4 * k + 2], wZ[4 * k + 3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive_cluster(bar(kWFull), 0);
+          }
+        }
+      }
+
+      // ---- end of job: write this job's partial results
+      if (PHASE == kStats || PHASE == kRowLoss) {
+        float* scratch = reinterpret_cast<float*>(sbase + kOffW);  // [6][64]
+        named_bar_sync(2, kEpiThreads);
+        if (n1 == 1) {
+          if (PHASE == kStats) {
+            scratch[0 * 64 + m] = lS.m; scratch[1 * 64 + m] = lS.s;
+            scratch[2 * 64 + m] = lSt.m; scratch[3 * 64 + m] = lSt.s;
+            scratch[4 * 64 + m] = lZ.m; scratch[5 * 64 + m] = lZ.s;
+          } else {
+            scratch[0 * 64 + m] = acc_g; scratch[1 * 64 + m] = acc_q;
+          }
+        }
+        named_bar_sync(2, kEpiThreads);
+        if (n1 == 0) {
+          if (PHASE == kStats) {
+            lS.merge(scratch[0 * 64 + m], scratch[1 * 64 + m]);
+            lSt.merge(scratch[2 * 64 + m], scratch[3 * 64 + m]);
+            lZ.merge(scratch[4 * 64 + m], scratch[5 * 64 + m]);
+            float2* out = reinterpret_cast<float2*>(p.part);
+            const size_t o = (size_t)sp * 3 * p.bpad + lrow;
+            out[o] = make_float2(lS.m, lS.s);
+            out[o + p.bpad] = make_float2(lSt.m, lSt.s);
+            out[o + 2 * (size_t)p.bpad] = make_float2(lZ.m, lZ.s);
+          } else {
+            const size_t o = (size_t)sp * 2 * p.bpad + lrow;
+            p.part[o] = acc_g + scratch[0 * 64 + m];
+            p.part[o + p.bpad] = acc_q + scratch[1 * 64 + m];
+          }
+        }
+      } else {
+        mbar_wait(bar(kAccFull), jj & 1);
+        tc_fence_after();
+        const int half_d = D / 2;
+        float* out_t = p.part + ((size_t)sp * 2 * p.bpad + lrow) * D + n1 * half_d;
+        float* out_i = out_t + (size_t)p.bpad * D;
+        for (int c0 = 0; c0 < half_d; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + lane_field + kAccCol + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(out_t + c0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+          tmem_ld32(tmem_base + lane_field + kAccCol + half_d + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(out_i + c0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        }
+        tc_fence_before();
+        mbar_arrive_cluster(bar(kAccEmpty), 0);
+      }
+    }
+  }
+
+  // teardown: nobody leaves while the peer may still touch this CTA's shared memory or TMEM
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize kernels: merge the per-split partials
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stats_finalize_kernel(const float2* __restrict__ part, int nsplit, int bpad,
+                                                             int b, float* __restrict__ r, float* __restrict__ c,
+                                                             float* __restrict__ rz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  float* outs[3] = {r, c, rz};
+  for (int k = 0; k < 3; ++k) {
+    OnlineLse2 l;
+    l.init();
+    for (int s = 0; s < nsplit; ++s) {
+      float2 v = part[((size_t)s * 3 + k) * bpad + i];
+      l.merge(v.x, v.y);
+    }
+    outs[k][i] = (l.m + log2f(l.s)) * kLn2;
+  }
+}
+
+__global__ void __launch_bounds__(256) rowloss_finalize_kernel(const float* __restrict__ part, int nsplit,
+                                                               int bpad, int b, float inv_2B,
+                                                               float* __restrict__ g, float* __restrict__ q) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  float ag = 0.f, aq = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    ag += part[((size_t)s * 2) * bpad + i];
+    aq += part[((size_t)s * 2 + 1) * bpad + i];
+  }
+  g[i] = ag * inv_2B;
+  q[i] = aq;
+}
+
+__global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  __shared__ double sm[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)v[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) *out = (float)t;
+  }
+}
+
+// Power-of-two scale of the fp16 gradient-weight tiles, from bounds that hold for every element:
+//   |2B dS_ij| <= 2 + q_j               (softmax terms in [0,1], P in [0,1], q = colsum(P))
+//   0 <= 2B G_ij = r_i + c_j - 2 S_ij <= max r + max c + 2 max||T|| max||I|| / tau   (Cauchy-Schwarz)
+//   |2B (dZ_ij + dZ_ji)| <= 2 max(2B G)  (g_i is a P-weighted mean of G_i.)
+// The largest possible weight is mapped just below 2^15 so that nothing overflows fp16 and the
+// small weights of the soft-target regime stay in the normal range.
+__global__ void __launch_bounds__(1024) wscale_kernel(const float* __restrict__ r, const float* __restrict__ c,
+                                                      const float* __restrict__ q, int B,
+                                                      const float* __restrict__ colfac,
+                                                      const float* __restrict__ norm_i,
+                                                      const float* __restrict__ norm_t, float inv_tau, float tau,
+                                                      float* __restrict__ out) {
+  __shared__ float sm[6][32];
+  float v[6] = {-INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    v[0] = fmaxf(v[0], r[i]); v[1] = fmaxf(v[1], c[i]); v[2] = fmaxf(v[2], q[i]);
+    v[3] = fmaxf(v[3], colfac[i]); v[4] = fmaxf(v[4], norm_i[i]); v[5] = fmaxf(v[5], norm_t[i]);
+  }
+  for (int k = 0; k < 6; ++k) {
+    v[k] = warp_max(v[k]);
+    if ((threadIdx.x & 31) == 0) sm[k][threadIdx.x >> 5] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    for (int k = 0; k < 6; ++k) v[k] = warp_max(sm[k][threadIdx.x]);
+    if (threadIdx.x == 0) {
+      const float gmax = fmaxf(v[0] + v[1] + 2.f * v[4] * v[5] * inv_tau, 1.f);
+      const float b1 = (2.f + v[2]) * v[3] * inv_tau;
+      const float b3 = 2.f * gmax * v[3] * 0.5f * tau;
+      const float bound = fmaxf(fmaxf(b1, b3), 1e-30f);
+      int e;
+      frexpf(bound, &e);  // bound < 2^e
+      int k = 15 - e;
+      k = k < -60 ? -60 : (k > 60 ? 60 : k);
+      out[0] = ldexpf(1.f, k);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bwd_finalize_kernel(const float* __restrict__ part, int nsplit, int bpad,
+                                                           int b, int D, float inv_2B,
+                                                           const float* __restrict__ grad_loss,
+                                                           const float* __restrict__ wscale,
+                                                           float* __restrict__ dT, float* __restrict__ dI) {
+  const float scale = (grad_loss ? *grad_loss : 1.f) * inv_2B / *wscale;
+  const size_t n4 = (size_t)b * D / 4;
+  const size_t plane = (size_t)bpad * D;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 at = make_float4(0.f, 0.f, 0.f, 0.f), ai = at;
+    for (int s = 0; s < nsplit; ++s) {
+      const float4 a = reinterpret_cast<const float4*>(part + (size_t)s * 2 * plane)[i];
+      const float4 c = reinterpret_cast<const float4*>(part + ((size_t)s * 2 + 1) * plane)[i];
+      at.x += a.x; at.y += a.y; at.z += a.z; at.w += a.w;
+      ai.x += c.x; ai.y += c.y; ai.z += c.z; ai.w += c.w;
+    }
+    reinterpret_cast<float4*>(dT)[i] = make_float4(at.x * scale, at.y * scale, at.z * scale, at.w * scale);
+    reinterpret_cast<float4*>(dI)[i] = make_float4(ai.x * scale, ai.y * scale, ai.z * scale, ai.w * scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+// 2-D fp16 tensor [rows][cols] (cols contiguous), box {64 cols, box_rows}, 128-byte swizzle
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  MC_REQUIRE(fn != nullptr, MC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(__half)};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MC_REQUIRE(r == CUDA_SUCCESS, MC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return MC_OK;
+}
+
+struct Split {
+  int n_row_blocks, n_tiles, nsplit, tiles_per_split, bpad;
+};
+static Split choose_split(int b, int B) {
+  Split s;
+  s.n_row_blocks = (b + 127) / 128;
+  s.bpad = s.n_row_blocks * 128;
+  s.n_tiles = (int)(round_up((size_t)B, 128) / 128);
+  const int npairs = num_sms() / 2;
+  int best = 1;
+  double best_cost = 1e30;
+  const int max_split = s.n_tiles < kMaxSplit ? s.n_tiles : kMaxSplit;
+  for (int ns = 1; ns <= max_split; ++ns) {
+    const int tps = (s.n_tiles + ns - 1) / ns;
+    const long jobs = (long)s.n_row_blocks * ns;
+    const long rounds = (jobs + npairs - 1) / npairs;
+    const double cost = (double)rounds * (tps + 0.5) + 0.02 * ns;  // 0.5 tile of per-job overhead
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
+  }
+  s.nsplit = best;
+  s.tiles_per_split = (s.n_tiles + best - 1) / best;
+  return s;
+}
+
+size_t planes_bytes(int B, int D, int /*mode*/) { return supported(D) ? planes_layout(B, D).total : 0; }
+
+size_t workspace_bytes(int b, int B, int D, int /*mode*/) {
+  Split s = choose_split(b, B);
+  size_t stats = (size_t)s.nsplit * 3 * s.bpad * sizeof(float2);
+  size_t bwdp = (size_t)s.nsplit * 2 * s.bpad * D * sizeof(float);
+  return round_up(stats > bwdp ? stats : bwdp, 256) + 256;  // + the weight-scale slot
+}
+static float* wscale_slot(void* ws, int b, int B, int D) {
+  return reinterpret_cast<float*>(static_cast<char*>(ws) + workspace_bytes(b, B, D, 0) - 256);
+}
+
+int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row_offset, int /*mode*/,
+            void* planes_all, cudaStream_t st) {
+  MC_REQUIRE(supported(D), MC_ERR_UNSUPPORTED, "tcgen05 engine needs D in {64,128,192,256} (got %d)", D);
+  MC_REQUIRE(aligned(planes_all, 256), MC_ERR_ALIGN, "clip_prepare: planes buffer must be 256-byte aligned");
+  PlanesLayout l = planes_layout(B, D);
+  char* base = static_cast<char*>(planes_all);
+  __half* Xh = reinterpret_cast<__half*>(base + l.off_hi);
+  __half* Xl = reinterpret_cast<__half*>(base + l.off_lo);
+  __half* XhT = reinterpret_cast<__half*>(base + l.off_hiT);
+  float* colfac = reinterpret_cast<float*>(base + l.off_colfac);
+  float* norm_i = reinterpret_cast<float*>(base + l.off_norm_i);
+  float* norm_t = reinterpret_cast<float*>(base + l.off_norm_t);
+  const bool last = row_offset + b == B;
+  const int rows_total = b + (last ? l.Bp - B : 0);
+  stage_planes_kernel<<<(rows_total + 7) / 8, 256, 0, st>>>(I_loc, T_loc, b, B, l.Bp, D, row_offset, rows_total, Xh,
+                                                           Xl, colfac, norm_i, norm_t);
+  MC_LAUNCH_CHECK();
+  const int j_begin = row_offset, j_end = last ? l.Bp : row_offset + b;
+  dim3 grid((j_end - j_begin + 63) / 64, 2 * D / 64);
+  transpose_hi_kernel<<<grid, 256, 0, st>>>(Xh, XhT, l.Bp, 2 * D, j_begin, j_end);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
+template <int PHASE, int PASSES>
+static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, float* part, const float* wscale,
+                       cudaStream_t st) {
+  MC_REQUIRE(supported(p.D), MC_ERR_UNSUPPORTED, "tcgen05 engine needs D in {64,128,192,256} (got %d)", p.D);
+  MC_REQUIRE(p.row_offset % 128 == 0, MC_ERR_UNSUPPORTED, "tcgen05 engine needs row_offset %% 128 == 0 (got %d)",
+             p.row_offset);
+  MC_REQUIRE(p.planes_all != nullptr && aligned(p.planes_all, 256), MC_ERR_BAD_ARG,
+             "tcgen05 engine: planes buffer missing or not 256-byte aligned (call mc_clip_prepare first)");
+  PlanesLayout l = planes_layout(p.B, p.D);
+  const char* base = static_cast<const char*>(p.planes_all);
+  const void* Xh = base + l.off_hi;
+  const void* Xl = base + l.off_lo;
+  const void* XhT = base + l.off_hiT;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mt;
+  int rc;
+  if ((rc = make_map(&ma_hi, Xh, l.Bp, 2 * p.D, 64))) return rc;
+  if ((rc = make_map(&ma_lo, Xl, l.Bp, 2 * p.D, 64))) return rc;
+  if ((rc = make_map(&mb_hi, Xh, l.Bp, 2 * p.D, 32))) return rc;
+  if ((rc = make_map(&mb_lo, Xl, l.Bp, 2 * p.D, 32))) return rc;
+  if ((rc = make_map(&mt, XhT, 2 * p.D, l.Bp, p.D / 2))) return rc;
+
+  Split sp = choose_split(p.b, p.B);
+  PairParams pp;
+  pp.b = p.b; pp.B = p.B; pp.Bp = l.Bp; pp.D = p.D; pp.row_offset = p.row_offset;
+  pp.n_row_blocks = sp.n_row_blocks; pp.n_tiles = sp.n_tiles; pp.nsplit = sp.nsplit;
+  pp.tiles_per_split = sp.tiles_per_split; pp.bpad = sp.bpad;
+  pp.inv_tau = 1.f / p.tau; pp.half_tau = 0.5f * p.tau; pp.inv_2B = 0.5f / (float)p.B;
+  pp.colfac = reinterpret_cast<const float*>(base + l.off_colfac);
+  pp.r = s.r; pp.c = s.c; pp.rz = s.rz; pp.g = s.g; pp.q = s.q;
+  pp.part = part;
+  pp.wscale = wscale;
+
+  auto kern = pair_kernel<PHASE, PASSES>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const long njobs = (long)sp.n_row_blocks * sp.nsplit;
+  int npairs = num_sms() / 2;
+  if (njobs < npairs) npairs = (int)njobs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * npairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MC_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, mt, pp));
+  count_launch();
+  return MC_OK;
+}
+
+template <int PHASE>
+static int launch_phase(int mode, const ClipProblem& p, const ClipStatsAll& s, float* part, const float* wscale,
+                        cudaStream_t st) {
+  if (mode == MC_GEMM_TC_F16X3) return launch_pair<PHASE, 3>(p, s, part, wscale, st);
+  return launch_pair<PHASE, 1>(p, s, part, wscale, st);
+}
+
+int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, void* ws, size_t ws_bytes,
+          cudaStream_t st) {
+  MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_stats(tc): workspace %zu < %zu",
+             ws_bytes, workspace_bytes(p.b, p.B, p.D, mode));
+  ClipStatsAll none{nullptr, nullptr, nullptr, nullptr, nullptr};
+  int rc = launch_phase<kStats>(mode, p, none, static_cast<float*>(ws), nullptr, st);
+  if (rc) return rc;
+  Split sp = choose_split(p.b, p.B);
+  stats_finalize_kernel<<<(p.b + 255) / 256, 256, 0, st>>>(static_cast<const float2*>(ws), sp.nsplit, sp.bpad, p.b,
+                                                          r_loc, c_loc, rz_loc);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
+int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, float* g_loc, float* q_loc, float* loss_part,
+            void* ws, size_t ws_bytes, cudaStream_t st) {
+  MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_rowloss(tc): workspace too small");
+  int rc = launch_phase<kRowLoss>(mode, p, s, static_cast<float*>(ws), nullptr, st);
+  if (rc) return rc;
+  Split sp = choose_split(p.b, p.B);
+  rowloss_finalize_kernel<<<(p.b + 255) / 256, 256, 0, st>>>(static_cast<const float*>(ws), sp.nsplit, sp.bpad, p.b,
+                                                            0.5f / (float)p.B, g_loc, q_loc);
+  MC_LAUNCH_CHECK();
+  sum_kernel<<<1, 1024, 0, st>>>(g_loc, p.b, loss_part);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
+int bwd(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, float* dI, float* dT, void* ws,
+        size_t ws_bytes, cudaStream_t st) {
+  MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_bwd(tc): workspace too small");
+  MC_REQUIRE(aligned(dI, 16) && aligned(dT, 16), MC_ERR_ALIGN, "clip_bwd(tc): gradients must be 16-byte aligned");
+  PlanesLayout l = planes_layout(p.B, p.D);
+  const char* pbase = static_cast<const char*>(p.planes_all);
+  float* wsc = wscale_slot(ws, p.b, p.B, p.D);
+  MC_REQUIRE(p.planes_all != nullptr, MC_ERR_BAD_ARG, "clip_bwd(tc): planes buffer missing");
+  wscale_kernel<<<1, 1024, 0, st>>>(s.r, s.c, s.q, p.B, reinterpret_cast<const float*>(pbase + l.off_colfac),
+                                   reinterpret_cast<const float*>(pbase + l.off_norm_i),
+                                   reinterpret_cast<const float*>(pbase + l.off_norm_t), 1.f / p.tau, p.tau, wsc);
+  MC_LAUNCH_CHECK();
+  int rc = launch_phase<kBwd>(mode, p, s, static_cast<float*>(ws), wsc, st);
+  if (rc) return rc;
+  Split sp = choose_split(p.b, p.B);
+  size_t n4 = (size_t)p.b * p.D / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  int cap = num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  bwd_finalize_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(ws), sp.nsplit, sp.bpad, p.b, p.D,
+                                              0.5f / (float)p.B, grad_loss, wsc, dT, dI);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
 }
 
 }  // namespace tc

@@ -269,8 +269,8 @@ int mc_proj_head_fwd(const float* x, int B, int E, int P, const float* w_proj, c
   MC_REQUIRE(P % 4 == 0 && P <= 1024, MC_ERR_UNSUPPORTED,
              "proj_head_fwd: projection_dim %d must be a multiple of 4 and <= 1024", P);
   MC_REQUIRE(p_drop >= 0.f && p_drop < 1.f, MC_ERR_BAD_ARG, "proj_head_fwd: dropout p=%g", p_drop);
-  MC_REQUIRE(mode == MC_GEMM_SIMT_FP32, MC_ERR_UNSUPPORTED,
-             "proj_head_fwd: only MC_GEMM_SIMT_FP32 is built in this version");
+  // the head GEMMs run on the fp32 FMA engine for every mode until their tcgen05 variant lands
+  MC_REQUIRE(mode >= MC_GEMM_SIMT_FP32 && mode <= MC_GEMM_TC_F16, MC_ERR_BAD_ARG, "proj_head_fwd: bad mode %d", mode);
   MC_REQUIRE(aligned(projected, 16) && aligned(out, 16) && aligned(gamma, 16) && aligned(beta, 16) &&
                  (!keep_mask || aligned(keep_mask, 4)) && (!z || aligned(z, 16)),
              MC_ERR_ALIGN, "proj_head_fwd: pointers must be 16-byte aligned");
@@ -302,8 +302,7 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
              MC_ERR_BAD_ARG, "proj_head_bwd: null pointer");
   MC_REQUIRE(B > 0 && E > 0 && P > 0, MC_ERR_BAD_ARG, "proj_head_bwd: bad sizes");
   MC_REQUIRE(P % 4 == 0 && P <= 1024, MC_ERR_UNSUPPORTED, "proj_head_bwd: projection_dim %d", P);
-  MC_REQUIRE(mode == MC_GEMM_SIMT_FP32, MC_ERR_UNSUPPORTED,
-             "proj_head_bwd: only MC_GEMM_SIMT_FP32 is built in this version");
+  MC_REQUIRE(mode >= MC_GEMM_SIMT_FP32 && mode <= MC_GEMM_TC_F16, MC_ERR_BAD_ARG, "proj_head_bwd: bad mode %d", mode);
   MC_REQUIRE(aligned(grad_out, 16) && aligned(z, 16) && aligned(projected, 16) && aligned(gamma, 16) &&
                  (!keep_mask || aligned(keep_mask, 4)),
              MC_ERR_ALIGN, "proj_head_bwd: pointers must be 16-byte aligned");

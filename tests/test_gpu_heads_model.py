@@ -21,7 +21,7 @@ def _head(z, tag, E, mode):
     return h.cuda()
 
 
-@pytest.mark.parametrize("mode", ["simt_fp32", "tc_bf16x3"])
+@pytest.mark.parametrize("mode", ["simt_fp32", "tc_f16x3"])
 def test_head_eval_golden(golden, mode):
     z = golden("proj_head_model")
     for tag, E in (("img", 160), ("txt", 96)):
@@ -47,7 +47,7 @@ class _MaskedHead(nn.Module):
         return self.head(x, keep_mask=self.keep)
 
 
-@pytest.mark.parametrize("mode", ["simt_fp32", "tc_bf16x3"])
+@pytest.mark.parametrize("mode", ["simt_fp32", "tc_f16x3"])
 @pytest.mark.parametrize("tt,tau", [("tau1", 1.0), ("tau05", 0.5)])
 def test_model_train_step_golden(golden, tt, tau, mode):
     """heads (train mode, reference masks) + loss, forward and backward, through CLIPModel.forward."""

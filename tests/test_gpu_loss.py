@@ -19,13 +19,13 @@ LOSS_TOL, GRAD_TOL = 1e-4, 1e-3
 # single-pass 16-bit operand engine: stated looser tolerance
 LOOSE_LOSS_TOL, LOOSE_GRAD_TOL = 2e-3, 3e-2
 
-FP32_MODES = ["simt_fp32", "tc_bf16x3"]
-ALL_MODES = FP32_MODES + ["tc_bf16"]
+FP32_MODES = ["simt_fp32", "tc_f16x3"]
+ALL_MODES = FP32_MODES + ["tc_f16"]
 CASES = ["b8_default", "b48_soft_tau05", "b33_dup_tau2", "b130_soft", "b64_verysoft"]
 
 
 def _tols(mode):
-    return (LOOSE_LOSS_TOL, LOOSE_GRAD_TOL) if mode == "tc_bf16" else (LOSS_TOL, GRAD_TOL)
+    return (LOOSE_LOSS_TOL, LOOSE_GRAD_TOL) if mode == "tc_f16" else (LOSS_TOL, GRAD_TOL)
 
 
 def _run(I, T, tau, mode, grad_scale=1.0):

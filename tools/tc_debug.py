@@ -1,0 +1,68 @@
+"""GPU bring-up script for the tcgen05 engine: phase-by-phase comparison with the fp32 SIMT engine
+through the C ABI (not a test; run under gpurun)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from mae_clip_b200 import _lib
+from mae_clip_b200._lib import check, ptr, cur_stream
+
+lib = _lib.lib()
+
+
+def emb(B, D, seed, scale):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.nn.functional.layer_norm(torch.randn(B, D, generator=g), (D,)) * scale).cuda()
+
+
+def phases(I, T, tau, mode, b=None, off=0):
+    B, D = I.shape
+    b = b or B
+    dev = I.device
+    nb = lib.mc_clip_planes_bytes(B, D, mode)
+    planes = torch.zeros(max(nb, 1), dtype=torch.uint8, device=dev)
+    ws = torch.zeros(max(lib.mc_clip_loss_workspace_bytes(b, B, D, mode), 1), dtype=torch.uint8, device=dev)
+    st = cur_stream()
+    check(lib.mc_clip_prepare(ptr(I), ptr(T), B, B, D, 0, mode, ptr(planes), st), "prepare")
+    s = torch.zeros(3, b, device=dev)
+    check(lib.mc_clip_stats(ptr(I), ptr(T), ptr(planes), b, B, D, off, tau, mode, ptr(s[0]), ptr(s[1]), ptr(s[2]),
+                            ptr(ws), ws.numel(), st), "stats")
+    torch.cuda.synchronize()
+    return planes, ws, s
+
+
+def full(I, T, tau, mode):
+    B, D = I.shape
+    dev = I.device
+    n = lib.mc_clip_loss_fused_workspace_bytes(B, D, mode)
+    ws = torch.zeros(n, dtype=torch.uint8, device=dev)
+    loss = torch.zeros(1, device=dev)
+    dI, dT = torch.zeros_like(I), torch.zeros_like(T)
+    check(lib.mc_clip_loss_fwd_bwd(ptr(I), ptr(T), B, D, tau, mode, ptr(loss), ptr(dI), ptr(dT), ptr(ws), n,
+                                   cur_stream()), "fwd_bwd")
+    torch.cuda.synchronize()
+    return loss, dI, dT
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+which = sys.argv[1] if len(sys.argv) > 1 else "stats"
+sizes = [(128, 256, 0.1), (256, 256, 1.0), (1000, 256, 0.25), (4096, 256, 1.0), (384, 128, 0.3)]
+for B, D, scale in sizes:
+    I, T = emb(B, D, 0, scale), emb(B, D, 1, scale)
+    if which == "stats":
+        _, _, s0 = phases(I, T, 1.0, 0)
+        for mode in (1, 2):
+            _, _, s1 = phases(I, T, 1.0, mode)
+            print(f"B={B} D={D} scale={scale} mode={mode} stats maxabs diff r/c/rz:",
+                  [(s1[k] - s0[k]).abs().max().item() for k in range(3)], "ref range", s0.min().item(), s0.max().item(),
+                  flush=True)
+            if not torch.isfinite(s1).all() or (s1 - s0).abs().max() > 1e-2:
+                print("   first rows tc:", s1[:, :4].tolist(), " simt:", s0[:, :4].tolist())
+    else:
+        l0, dI0, dT0 = full(I, T, 1.0, 0)
+        for mode in (1, 2):
+            l1, dI1, dT1 = full(I, T, 1.0, mode)
+            print(f"B={B} D={D} scale={scale} mode={mode} loss {l1.item():.6f} vs {l0.item():.6f} "
+                  f"rel dI {rel(dI1, dI0):.2e} dT {rel(dT1, dT0):.2e}", flush=True)
