@@ -165,11 +165,13 @@ __global__ void __launch_bounds__(256) transpose_hi_kernel(const __half* __restr
 // ------------------------------------------------------------------------------------------
 // the pair kernel
 // ------------------------------------------------------------------------------------------
-template <int PASSES>
-struct StageCfg {
-  static constexpr int kStageBytes = (PASSES == 3 ? 6 : 2) * kChunkBytes;
-  static constexpr int kStages = kStageRegion / kStageBytes;  // 2 (x3) or 6 (x1)
-};
+// The TMA ring is made of 16 KB slots (two 64 x 64 fp16 chunks).  Per 64-wide K chunk c:
+//   F16X3: slot A  = [I_i lo | T_i lo]   (this CTA's rows; the hi plane is resident)
+//          slot BI = [I_j hi | I_j lo],  slot BT = [T_j hi | T_j lo]
+//   F16  : slot B  = [I_j hi | T_j hi]
+// Small slots keep 4-5 loads in flight ahead of the tensor cores, which hides the L2 latency.
+constexpr int kSlotBytes = 2 * kChunkBytes;
+constexpr int kSlots = kStageRegion / kSlotBytes;  // 6
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -210,9 +212,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
             const __grid_constant__ CUtensorMap map_t, const PairParams p) {
-  using SC = StageCfg<PASSES>;
-  constexpr int kStages = SC::kStages;
-  constexpr int kStageBytes = SC::kStageBytes;
   constexpr int kNBuf = (PHASE == kBwd) ? 1 : 2;   // TMEM tile buffers (3 x 64 columns each)
   constexpr uint32_t kAccCol = 256;                // gradient accumulators: dT at 256, dI at 256 + D/2
 
@@ -232,7 +231,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   const int njobs = p.n_row_blocks * p.nsplit;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kFull0 + s), 1); mbar_init(bar(kEmpty0 + s), 1); }
+    for (int s = 0; s < kSlots; ++s) { mbar_init(bar(kFull0 + s), 1); mbar_init(bar(kEmpty0 + s), 1); }
     mbar_init(bar(kAFull), 1);
     mbar_init(bar(kJobDone), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(bar(kTmemFull0 + i), 1); mbar_init(bar(kTmemEmpty0 + i), 2 * kEpiThreads); }
@@ -255,8 +254,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // =========================================================== TMA producer (one lane per CTA)
-    if (lane == 0) {
+    // =========================================================== TMA producer (one elected lane per CTA)
+    if (elect_one()) {
       uint32_t it = 0, hh = 0, jj = 0;
       for (int job = pair_id; job < njobs; job += npairs, ++jj) {
         const int rb = job / p.nsplit, sp = job % p.nsplit;
@@ -267,29 +266,37 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         for (int c = 0; c < 2 * nkc; ++c) tma_load_2d_pair(base + kOffA + c * kChunkBytes, &map_a_hi, bar(kAFull), c * 64, row_a);
         for (int t = t0; t < t1; ++t) {
           const int j0 = t * kTileN + 32 * (int)rank, j1 = j0 + 64;
-          for (int c = 0; c < nkc; ++c, ++it) {
-            const uint32_t stage = it % kStages, par = (it / kStages) & 1;
-            mbar_wait(bar(kEmpty0 + stage), par ^ 1);
-            const uint32_t fb = bar(kFull0 + stage);
-            if (leader) mbar_arrive_expect_tx(fb, 2u * kStageBytes);
-            const uint32_t sb = base + kOffStage + stage * kStageBytes;
+          for (int c = 0; c < nkc; ++c) {
             const int ci = c * 64, ct = D + c * 64;
+            uint32_t fb;
+            auto acquire = [&]() -> uint32_t {  // next ring slot: wait until the MMAs released it, arm its barrier
+              const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
+              ++it;
+              mbar_wait(bar(kEmpty0 + slot), par ^ 1);
+              fb = bar(kFull0 + slot);
+              if (leader) mbar_arrive_expect_tx(fb, 2u * kSlotBytes);
+              return base + kOffStage + slot * kSlotBytes;
+            };
             if (PASSES == 3) {
-              tma_load_2d_pair(sb + 0 * kChunkBytes, &map_a_lo, fb, ci, row_a);            // I_i lo
-              tma_load_2d_pair(sb + 1 * kChunkBytes, &map_a_lo, fb, ct, row_a);            // T_i lo
-              tma_load_2d_pair(sb + 2 * kChunkBytes, &map_b_hi, fb, ci, j0);               // I_j hi
-              tma_load_2d_pair(sb + 2 * kChunkBytes + 4096, &map_b_hi, fb, ci, j1);
-              tma_load_2d_pair(sb + 3 * kChunkBytes, &map_b_lo, fb, ci, j0);               // I_j lo
-              tma_load_2d_pair(sb + 3 * kChunkBytes + 4096, &map_b_lo, fb, ci, j1);
-              tma_load_2d_pair(sb + 4 * kChunkBytes, &map_b_hi, fb, ct, j0);               // T_j hi
-              tma_load_2d_pair(sb + 4 * kChunkBytes + 4096, &map_b_hi, fb, ct, j1);
-              tma_load_2d_pair(sb + 5 * kChunkBytes, &map_b_lo, fb, ct, j0);               // T_j lo
-              tma_load_2d_pair(sb + 5 * kChunkBytes + 4096, &map_b_lo, fb, ct, j1);
+              uint32_t sb = acquire();
+              tma_load_2d_pair(sb, &map_a_lo, fb, ci, row_a);                         // I_i lo
+              tma_load_2d_pair(sb + kChunkBytes, &map_a_lo, fb, ct, row_a);           // T_i lo
+              sb = acquire();
+              tma_load_2d_pair(sb, &map_b_hi, fb, ci, j0);                            // I_j hi
+              tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ci, j1);
+              tma_load_2d_pair(sb + kChunkBytes, &map_b_lo, fb, ci, j0);              // I_j lo
+              tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_lo, fb, ci, j1);
+              sb = acquire();
+              tma_load_2d_pair(sb, &map_b_hi, fb, ct, j0);                            // T_j hi
+              tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ct, j1);
+              tma_load_2d_pair(sb + kChunkBytes, &map_b_lo, fb, ct, j0);              // T_j lo
+              tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_lo, fb, ct, j1);
             } else {
-              tma_load_2d_pair(sb + 0 * kChunkBytes, &map_b_hi, fb, ci, j0);               // I_j hi
-              tma_load_2d_pair(sb + 0 * kChunkBytes + 4096, &map_b_hi, fb, ci, j1);
-              tma_load_2d_pair(sb + 1 * kChunkBytes, &map_b_hi, fb, ct, j0);               // T_j hi
-              tma_load_2d_pair(sb + 1 * kChunkBytes + 4096, &map_b_hi, fb, ct, j1);
+              const uint32_t sb = acquire();
+              tma_load_2d_pair(sb, &map_b_hi, fb, ci, j0);                            // I_j hi
+              tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ci, j1);
+              tma_load_2d_pair(sb + kChunkBytes, &map_b_hi, fb, ct, j0);              // T_j hi
+              tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_hi, fb, ct, j1);
             }
           }
           if (PHASE == kBwd) {
@@ -307,8 +314,10 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     }
     __syncwarp();
   } else if (warp == 1) {
-    // =========================================================== MMA issuer (leader CTA, one lane)
-    if (leader && lane == 0) {
+    // =========================================================== MMA issuer (leader CTA, one elected lane:
+    // inside elect.sync the compiler knows a single thread is active and feeds the uniform-register
+    // operands of UTCHMMA / UTMALDG directly instead of a per-lane waterfall loop)
+    if (leader && elect_one()) {
       constexpr uint32_t idesc_tile = idesc_f16(128, kTileN);
       const uint32_t idesc_grad = idesc_f16(128, D);
       uint32_t it = 0, tt = 0, hh = 0, jj = 0;
@@ -322,55 +331,75 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           mbar_wait(bar(kTmemEmpty0 + buf), (use & 1) ^ 1);
           tc_fence_after();
           const uint32_t tS = tmem_base + buf * 192, tSt = tS + 64, tZ = tS + 128;
-          for (int c = 0; c < nkc; ++c, ++it) {
-            const uint32_t stage = it % kStages, par = (it / kStages) & 1;
-            mbar_wait(bar(kFull0 + stage), par);
-            tc_fence_after();
-            const uint32_t sb = base + kOffStage + stage * kStageBytes;
+          for (int c = 0; c < nkc; ++c) {
+            uint32_t slot_bar = 0;
+            auto next_full = [&]() -> uint32_t {  // wait for the next ring slot to land
+              const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
+              ++it;
+              mbar_wait(bar(kFull0 + slot), par);
+              tc_fence_after();
+              slot_bar = bar(kEmpty0 + slot);
+              return base + kOffStage + slot * kSlotBytes;
+            };
             const uint64_t aI = smem_desc_sw128(base + kOffA + c * kChunkBytes);
             const uint64_t aT = smem_desc_sw128(base + kOffA + (nkc + c) * kChunkBytes);
-            uint64_t aIl = 0, aTl = 0, bI, bIl = 0, bT, bTl = 0;
+            const uint32_t first = (c > 0) ? 1u : 0u;
             if (PASSES == 3) {
-              aIl = smem_desc_sw128(sb + 0 * kChunkBytes);
-              aTl = smem_desc_sw128(sb + 1 * kChunkBytes);
-              bI = smem_desc_sw128(sb + 2 * kChunkBytes);
-              bIl = smem_desc_sw128(sb + 3 * kChunkBytes);
-              bT = smem_desc_sw128(sb + 4 * kChunkBytes);
-              bTl = smem_desc_sw128(sb + 5 * kChunkBytes);
-            } else {
-              bI = smem_desc_sw128(sb + 0 * kChunkBytes);
-              bT = smem_desc_sw128(sb + 1 * kChunkBytes);
-            }
+              const uint32_t sa = next_full();
+              const uint32_t a_bar = slot_bar;
+              const uint64_t aIl = smem_desc_sw128(sa), aTl = smem_desc_sw128(sa + kChunkBytes);
+              uint32_t sb = next_full();
+              {
+                const uint64_t bI = smem_desc_sw128(sb), bIl = smem_desc_sw128(sb + kChunkBytes);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
-              const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
-              const uint64_t kbI = desc_advance_k(bI, ks), kbT = desc_advance_k(bT, ks);
-              // S = T_i I_j^T
-              mma_f16_pair(tS, kT, kbI, idesc_tile, acc);
-              if (PASSES == 3) {
-                mma_f16_pair(tS, kT, desc_advance_k(bIl, ks), idesc_tile, 1u);
-                mma_f16_pair(tS, desc_advance_k(aTl, ks), kbI, idesc_tile, 1u);
-              }
-              // St = I_i T_j^T
-              if (PHASE != kRowLoss) {
-                mma_f16_pair(tSt, kI, kbT, idesc_tile, acc);
-                if (PASSES == 3) {
-                  mma_f16_pair(tSt, kI, desc_advance_k(bTl, ks), idesc_tile, 1u);
-                  mma_f16_pair(tSt, desc_advance_k(aIl, ks), kbT, idesc_tile, 1u);
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
+                  const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
+                  const uint64_t kb = desc_advance_k(bI, ks), kbl = desc_advance_k(bIl, ks);
+                  mma_f16_pair(tS, kT, kb, idesc_tile, acc);                         // S  = T_i I_j^T
+                  mma_f16_pair(tS, kT, kbl, idesc_tile, 1u);
+                  mma_f16_pair(tS, desc_advance_k(aTl, ks), kb, idesc_tile, 1u);
+                  mma_f16_pair(tZ, kI, kb, idesc_tile, acc);                         // Z += I_i I_j^T
+                  mma_f16_pair(tZ, kI, kbl, idesc_tile, 1u);
+                  mma_f16_pair(tZ, desc_advance_k(aIl, ks), kb, idesc_tile, 1u);
                 }
               }
-              // Z = I_i I_j^T + T_i T_j^T
-              mma_f16_pair(tZ, kI, kbI, idesc_tile, acc);
-              mma_f16_pair(tZ, kT, kbT, idesc_tile, 1u);
-              if (PASSES == 3) {
-                mma_f16_pair(tZ, kI, desc_advance_k(bIl, ks), idesc_tile, 1u);
-                mma_f16_pair(tZ, desc_advance_k(aIl, ks), kbI, idesc_tile, 1u);
-                mma_f16_pair(tZ, kT, desc_advance_k(bTl, ks), idesc_tile, 1u);
-                mma_f16_pair(tZ, desc_advance_k(aTl, ks), kbT, idesc_tile, 1u);
+              mma_commit_pair(slot_bar, 3);
+              sb = next_full();
+              {
+                const uint64_t bT = smem_desc_sw128(sb), bTl = smem_desc_sw128(sb + kChunkBytes);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
+                  const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
+                  const uint64_t kb = desc_advance_k(bT, ks), kbl = desc_advance_k(bTl, ks);
+                  if (PHASE != kRowLoss) {
+                    mma_f16_pair(tSt, kI, kb, idesc_tile, acc);                      // St = I_i T_j^T
+                    mma_f16_pair(tSt, kI, kbl, idesc_tile, 1u);
+                    mma_f16_pair(tSt, desc_advance_k(aIl, ks), kb, idesc_tile, 1u);
+                  }
+                  mma_f16_pair(tZ, kT, kb, idesc_tile, 1u);                          // Z += T_i T_j^T
+                  mma_f16_pair(tZ, kT, kbl, idesc_tile, 1u);
+                  mma_f16_pair(tZ, desc_advance_k(aTl, ks), kb, idesc_tile, 1u);
+                }
               }
+              mma_commit_pair(slot_bar, 3);
+              mma_commit_pair(a_bar, 3);
+            } else {
+              const uint32_t sb = next_full();
+              const uint64_t bI = smem_desc_sw128(sb), bT = smem_desc_sw128(sb + kChunkBytes);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
+                const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
+                const uint64_t kbI = desc_advance_k(bI, ks), kbT = desc_advance_k(bT, ks);
+                mma_f16_pair(tS, kT, kbI, idesc_tile, acc);
+                if (PHASE != kRowLoss) mma_f16_pair(tSt, kI, kbT, idesc_tile, acc);
+                mma_f16_pair(tZ, kI, kbI, idesc_tile, acc);
+                mma_f16_pair(tZ, kT, kbT, idesc_tile, 1u);
+              }
+              mma_commit_pair(slot_bar, 3);
             }
-            mma_commit_pair(bar(kEmpty0 + stage), 3);
           }
           mma_commit_pair(bar(kTmemFull0 + buf), 3);
           if (PHASE == kBwd) {
