@@ -64,14 +64,14 @@ struct PairParams {
   int b, B, Bp, D, row_offset;
   int n_row_blocks, n_tiles, nsplit, tiles_per_split, bpad;
   float inv_tau, half_tau, inv_2B;
-  const float* colfac;                 // [Bp] 1 / row scale
+  const float* scale;                  // {s, 1/s, 1/s^2}: global power-of-two scale of the fp16 planes
   const float *r, *c, *rz, *g, *q;     // length-B statistics (phase dependent, may be null)
   float* part;                         // partial results of this phase
   const float* wscale;                 // gradient sweep: power-of-two scale of the fp16 weight tiles
 };
 
 struct PlanesLayout {
-  size_t off_colfac, off_norm_i, off_norm_t, off_hi, off_lo, off_hiT, total;
+  size_t off_hdr, off_norm_i, off_norm_t, off_hi, off_lo, off_hiT, total;
   int Bp;
 };
 static PlanesLayout planes_layout(int B, int D) {
@@ -79,10 +79,10 @@ static PlanesLayout planes_layout(int B, int D) {
   l.Bp = (int)round_up((size_t)B, 128);
   size_t plane = (size_t)l.Bp * 2 * D * sizeof(__half);
   size_t vec = round_up((size_t)l.Bp * 4, 1024);
-  l.off_colfac = 0;           // 1 / row scale
-  l.off_norm_i = vec;         // ||I_i||_2
-  l.off_norm_t = 2 * vec;     // ||T_i||_2
-  l.off_hi = 3 * vec;
+  l.off_hdr = 0;              // {amax bits, s, 1/s, 1/s^2}
+  l.off_norm_i = 1024;        // ||I_i||_2
+  l.off_norm_t = 1024 + vec;  // ||T_i||_2
+  l.off_hi = 1024 + 2 * vec;
   l.off_lo = l.off_hi + plane;
   l.off_hiT = l.off_lo + plane;
   l.total = l.off_hiT + plane;
@@ -95,14 +95,34 @@ bool supported(int D) { return D % 64 == 0 && D >= 64 && D <= 256; }
 // staging: fp32 embeddings -> scaled fp16 hi / lo planes of X = [I || T], the per-row scale, and
 // the transposed hi plane (K-major B operand of the gradient GEMMs).
 // ------------------------------------------------------------------------------------------
+// largest magnitude over both embedding matrices (non-negative floats order like their bit patterns)
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ I, const float* __restrict__ T,
+                                                   size_t n, unsigned int* __restrict__ amax_bits) {
+  float a = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    a = fmaxf(a, fmaxf(fabsf(I[i]), fabsf(T[i])));
+  a = warp_max(a);
+  if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(amax_bits, __float_as_uint(a));
+}
+
 __global__ void __launch_bounds__(256) stage_planes_kernel(const float* __restrict__ I_loc,
                                                            const float* __restrict__ T_loc, int b, int B,
                                                            int Bp, int D, int row_offset, int rows_total,
                                                            __half* __restrict__ Xh, __half* __restrict__ Xl,
-                                                           float* __restrict__ colfac, float* __restrict__ norm_i,
+                                                           float* __restrict__ hdr, float* __restrict__ norm_i,
                                                            float* __restrict__ norm_t) {
   const int wrow = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wrow >= rows_total) return;
+  // One power-of-two scale for both matrices, bringing the largest magnitude into [1, 2): exact in
+  // fp32; hi keeps 11 significant bits of an element, hi + lo is exact to ~2^-25 of the global maximum.
+  const float amax = __uint_as_float(reinterpret_cast<const unsigned int*>(hdr)[0]);
+  float s = 1.f;
+  if (amax > 0.f && amax < INFINITY) {
+    int e;
+    frexpf(amax, &e);        // amax = f * 2^e, f in [0.5, 1)
+    s = ldexpf(1.f, 1 - e);  // amax * s in [1, 2)
+  }
+  if (wrow == 0 && lane == 0) { hdr[1] = s; hdr[2] = 1.f / s; hdr[3] = (1.f / s) * (1.f / s); }
   // rows [0, b): local rows; rows [b, rows_total): zero padding rows B .. Bp-1
   const bool pad = wrow >= b;
   const int gi = pad ? (B + (wrow - b)) : (row_offset + wrow);
@@ -111,37 +131,23 @@ __global__ void __launch_bounds__(256) stage_planes_kernel(const float* __restri
   __half* xl = Xl + (size_t)gi * K2;
   if (pad) {
     for (int k = lane; k < K2; k += 32) { xh[k] = __float2half_rn(0.f); xl[k] = __float2half_rn(0.f); }
-    if (lane == 0) { colfac[gi] = 1.f; norm_i[gi] = 0.f; norm_t[gi] = 0.f; }
+    if (lane == 0) { norm_i[gi] = 0.f; norm_t[gi] = 0.f; }
     return;
   }
   const float* pi = I_loc + (size_t)wrow * D;
   const float* pt = T_loc + (size_t)wrow * D;
-  float amax = 0.f, ni = 0.f, nt = 0.f;
-  for (int k = lane; k < D; k += 32) {
-    const float a = pi[k], c = pt[k];
-    amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(c)));
-    ni = fmaf(a, a, ni);
-    nt = fmaf(c, c, nt);
-  }
-  amax = warp_max(amax);
-  ni = warp_sum(ni);
-  nt = warp_sum(nt);
-  // power-of-two scale bringing the row's largest magnitude into [1, 2): exact in fp32; hi keeps 11
-  // significant bits of every element and hi + lo is exact to ~2^-25 of the row maximum for any
-  // finite input, however large or small
-  float s = 1.f;
-  if (amax > 0.f && amax < INFINITY) {
-    int e;
-    frexpf(amax, &e);        // amax = f * 2^e, f in [0.5, 1)
-    s = ldexpf(1.f, 1 - e);  // amax * s in [1, 2)
-  }
+  float ni = 0.f, nt = 0.f;
   for (int k = lane; k < K2; k += 32) {
-    float x = (k < D ? pi[k] : pt[k - D]) * s;
-    __half h = __float2half_rn(x);
+    const float raw = (k < D ? pi[k] : pt[k - D]);
+    if (k < D) ni = fmaf(raw, raw, ni); else nt = fmaf(raw, raw, nt);
+    const float x = raw * s;
+    const __half h = __float2half_rn(x);
     xh[k] = h;
     xl[k] = __float2half_rn(x - __half2float(h));
   }
-  if (lane == 0) { colfac[gi] = 1.f / s; norm_i[gi] = sqrtf(ni); norm_t[gi] = sqrtf(nt); }
+  ni = warp_sum(ni);
+  nt = warp_sum(nt);
+  if (lane == 0) { norm_i[gi] = sqrtf(ni); norm_t[gi] = sqrtf(nt); }
 }
 
 // XhT[k][j] = Xh[j][k] for j in [j_begin, j_end), 64 x 64 tiles through shared memory
@@ -438,13 +444,17 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     __syncwarp();
   } else {
     // =========================================================== epilogue: one thread per TMEM lane
+    // Everything inside exponentials lives in the log2 domain (ex2.approx); the raw accumulators are
+    // products of the scaled planes, so S = acc * inv_s2 / tau and Z = acc * inv_s2 * tau / 2.
     const int quarter = warp & 3;
     const int lane_t = quarter * 32 + lane;
     const int m = lane_t & 63, n1 = lane_t >> 6;
     const int tid_e = threadIdx.x - 64;
     const uint32_t lane_field = (uint32_t)(quarter * 32) << 16;
-    float* const consts = reinterpret_cast<float*>(sbase + kOffConst);  // [2][128][8]
+    float* const consts = reinterpret_cast<float*>(sbase + kOffConst);  // [2 buffers][8 fields][128 columns]
     const float kL2e = 1.4426950408889634f;
+    const float inv_s = p.scale[1], inv_s2 = p.scale[2];
+    const float cS2 = inv_s2 * p.inv_tau * kL2e, cZ2 = inv_s2 * p.half_tau * kL2e;  // raw acc -> log2 domain
     uint32_t tt = 0, hh = 0, jj = 0;
     for (int job = pair_id; job < njobs; job += npairs, ++jj) {
       const int rb = job / p.nsplit, sp = job % p.nsplit;
@@ -452,99 +462,131 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       const int lrow = rb * 128 + (int)rank * kRowsCta + m;  // row within this rank's strip
       const int gi = p.row_offset + lrow;
       const bool row_ok = lrow < p.b;
-      const float rowfac = p.colfac[gi];  // gi < Bp always
-      const float fS = rowfac * p.inv_tau, fZ = rowfac * p.half_tau;
-      float r_i = 0.f, c_i = 0.f, rz_i = 0.f, g_i = 0.f, q_i = 0.f;
-      if (PHASE != kStats && row_ok) { r_i = p.r[gi]; c_i = p.c[gi]; rz_i = p.rz[gi]; }
-      if (PHASE == kBwd && row_ok) { g_i = p.g[gi]; q_i = p.q[gi]; }
-      const float wsc = (PHASE == kBwd) ? *p.wscale : 1.f;
-      OnlineLse2 lS, lSt, lZ;
-      lS.init(); lSt.init(); lZ.init();
+      // per-row statistics, log2 domain: r2 = r log2(e), ... ; gh = 2B g log2(e)
+      float r2_i = 0.f, c2_i = 0.f, rz2_i = 0.f, gh_i = 0.f, q_i = 0.f;
+      if (PHASE != kStats && row_ok) { r2_i = p.r[gi] * kL2e; c2_i = p.c[gi] * kL2e; rz2_i = p.rz[gi] * kL2e; }
+      if (PHASE == kBwd && row_ok) { gh_i = p.g[gi] * (2.f * (float)p.B) * kL2e; q_i = p.q[gi]; }
+      float wS = 0.f, wZ = 0.f;
+      if (PHASE == kBwd) {
+        const float wsc = *p.wscale;
+        wS = inv_s * p.inv_tau * wsc;              // 2B dS      -> fp16 weight of X_j (scaled plane)
+        wZ = inv_s * p.half_tau * wsc * kLn2;      // 2B dZs (log2 units) -> fp16 weight
+      }
+      float mS = -INFINITY, sS = 0.f, mSt = -INFINITY, sSt = 0.f, mZ = -INFINITY, sZ = 0.f;  // raw-domain max, sums
       float acc_g = 0.f, acc_q = 0.f;
 
       for (int t = t0; t < t1; ++t, ++tt) {
-        // ---- per-column constants of this tile -> shared memory (column jl handled by thread jl)
-        float* cst = consts + (tt & 1) * (128 * 8);
-        {
-          const int j = t * kTileN + tid_e;
-          const bool ok = j < p.B;
-          float4 a, b2;
-          a.x = (PHASE == kBwd && ok) ? p.r[j] : 0.f;
-          a.y = (PHASE != kStats && ok) ? p.c[j] : 0.f;
-          a.z = (PHASE != kStats && ok) ? p.rz[j] * kL2e : 0.f;
-          a.w = (PHASE == kBwd && ok) ? p.g[j] : 0.f;
-          b2.x = (PHASE == kBwd && ok) ? p.q[j] : 0.f;
-          b2.y = p.colfac[j];           // j < Bp
-          if (PHASE == kBwd) {          // weight factors: colfac_j * {1/tau, tau/2} * wscale
-            a.w *= 2.f * (float)p.B;    // 2B g_j
-            b2.z = b2.y * p.inv_tau * wsc;
-            b2.w = b2.y * p.half_tau * wsc;
-          } else {
-            b2.z = ok ? 0.f : -INFINITY;  // additive mask for the log-domain values
-            b2.w = 0.f;
-          }
-          reinterpret_cast<float4*>(cst)[tid_e * 2] = a;
-          reinterpret_cast<float4*>(cst)[tid_e * 2 + 1] = b2;
+        // ---- per-column statistics of this tile -> shared memory, one field per 128-float row
+        float* cst = consts + (tt & 1) * (8 * 128);
+        const int jcol = t * kTileN + tid_e;
+        if (PHASE != kStats) {
+          const bool ok = jcol < p.B;
+          cst[0 * 128 + tid_e] = (PHASE == kBwd && ok) ? -p.r[jcol] * kL2e : 0.f;                       // -r2_j
+          cst[1 * 128 + tid_e] = ok ? -p.c[jcol] * kL2e : 0.f;                                          // -c2_j
+          cst[2 * 128 + tid_e] = ok ? -p.rz[jcol] * kL2e : 0.f;                                         // -rz2_j
+          cst[3 * 128 + tid_e] = (PHASE == kBwd && ok) ? p.g[jcol] * (2.f * (float)p.B) * kL2e : 0.f;   // gh_j
+          cst[4 * 128 + tid_e] = (PHASE == kBwd && ok) ? p.q[jcol] : 0.f;                               // q_j
+          named_bar_sync(1, kEpiThreads);
         }
-        named_bar_sync(1, kEpiThreads);
+        const bool ragged = (t + 1) * kTileN > p.B;  // last tile of a batch that is not a multiple of 128
+        const int jlim = p.B - t * kTileN;           // columns jl < jlim are real
         const uint32_t buf = tt % kNBuf, use = tt / kNBuf;
         mbar_wait(bar(kTmemFull0 + buf), use & 1);
         tc_fence_after();
         const uint32_t tS = tmem_base + buf * 192 + lane_field, tSt = tS + 64, tZ = tS + 128;
 
         if (PHASE == kStats) {
-          const float fS2 = fS * kL2e, fZ2 = fZ * kL2e;
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            const float* cc = cst + (64 * h + 32 * n1) * 8;
-            float v[32];
-            tmem_ld32(tS + 32 * h, v);
-            tmem_ld_wait();
+          auto lse_add32 = [&](float* v, int jl0, float c, float& mx, float& sm) {
+            if (ragged) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = fmaf(v[e], fS2 * cc[e * 8 + 5], cc[e * 8 + 6]);
-            lS.add32(v);
-            tmem_ld32(tSt + 32 * h, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = fmaf(v[e], fS2 * cc[e * 8 + 5], cc[e * 8 + 6]);
-            lSt.add32(v);
-            tmem_ld32(tZ + 32 * h, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = fmaf(v[e], fZ2 * cc[e * 8 + 5], cc[e * 8 + 6]);
-            lZ.add32(v);
-          }
-          tc_fence_before();
-          mbar_arrive_cluster(bar(kTmemEmpty0 + buf), 0);
-        } else if (PHASE == kRowLoss) {
-          const float fZ2 = fZ * kL2e, rz2_i = rz_i * kL2e;
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            const float* cc = cst + (64 * h + 32 * n1) * 8;
-            float vs[32], vz[32];
-            tmem_ld32(tS + 32 * h, vs);
-            tmem_ld32(tZ + 32 * h, vz);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float cf = cc[e * 8 + 5];
-              const float s = vs[e] * (fS * cf);
-              const float z2 = fmaf(vz[e], fZ2 * cf, cc[e * 8 + 6]);
-              const float P = ex2f(z2 - rz2_i);
-              const float G = (r_i + cc[e * 8 + 1]) - 2.f * s;  // 2B * G_ij
-              acc_g = fmaf(P, G, acc_g);
-              acc_q += ex2f(z2 - cc[e * 8 + 2]);
+              for (int e = 0; e < 32; ++e) if (jl0 + e >= jlim) v[e] = -INFINITY;
             }
-          }
+            float c4[4] = {fmaxf(v[0], v[4]), fmaxf(v[1], v[5]), fmaxf(v[2], v[6]), fmaxf(v[3], v[7])};
+#pragma unroll
+            for (int e = 8; e < 32; e += 4) {  // four independent chains: the warp has no other ILP
+#pragma unroll
+              for (int u = 0; u < 4; ++u) c4[u] = fmaxf(c4[u], v[e + u]);
+            }
+            const float cm = fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3]));
+            const float mn = fmaxf(mx, cm);
+            if (mn == -INFINITY) return;
+            // (v - mn) * c, not fma(v, c, -mn c): the difference is exact, so an unchanged maximum
+            // rescales the running sum by exactly 1 (a rounded offset would compound over the row)
+            float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) a4[u] += ex2f((v[e + u] - mn) * c);
+            }
+            sm = sm * ex2f((mx - mn) * c) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
+            mx = mn;
+          };
+          // software-pipelined TMEM reads: the load of the next 32 columns is in flight while the
+          // current ones are reduced (one warp per scheduler: nothing else hides the latency)
+          float va[32], vb[32];
+          const int jlA = 32 * n1, jlB = 64 + 32 * n1;
+          tmem_ld32(tS, va);
+          tmem_ld_wait();
+          tmem_ld32(tSt, vb);
+          lse_add32(va, jlA, cS2, mS, sS);
+          tmem_ld_wait();
+          tmem_ld32(tZ, va);
+          lse_add32(vb, jlA, cS2, mSt, sSt);
+          tmem_ld_wait();
+          tmem_ld32(tS + 32, vb);
+          lse_add32(va, jlA, cZ2, mZ, sZ);
+          tmem_ld_wait();
+          tmem_ld32(tSt + 32, va);
+          lse_add32(vb, jlB, cS2, mS, sS);
+          tmem_ld_wait();
+          tmem_ld32(tZ + 32, vb);
+          lse_add32(va, jlB, cS2, mSt, sSt);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive_cluster(bar(kTmemEmpty0 + buf), 0);  // all six reads landed: the MMA may reuse the buffer
+          lse_add32(vb, jlB, cZ2, mZ, sZ);
+        } else if (PHASE == kRowLoss) {
+          const float m2cS2 = -2.f * cS2;
+          float ag4[4] = {0.f, 0.f, 0.f, 0.f}, aq4[4] = {0.f, 0.f, 0.f, 0.f};
+          auto rowloss32 = [&](float* vs, float* vz, int jl0) {
+            if (ragged) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) if (jl0 + e >= jlim) vz[e] = -INFINITY;
+            }
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 nc = *reinterpret_cast<const float4*>(cst + 1 * 128 + jl0 + e);
+              const float4 nrz = *reinterpret_cast<const float4*>(cst + 2 * 128 + jl0 + e);
+              const float ncv[4] = {nc.x, nc.y, nc.z, nc.w}, nrzv[4] = {nrz.x, nrz.y, nrz.z, nrz.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {  // four independent accumulation chains
+                const float z2 = vz[e + u] * cZ2;
+                const float P = ex2f(z2 - rz2_i);
+                const float G = fmaf(vs[e + u], m2cS2, r2_i - ncv[u]);  // 2B G_ij log2(e)
+                ag4[u] = fmaf(P, G, ag4[u]);
+                aq4[u] += ex2f(z2 + nrzv[u]);
+              }
+            }
+          };
+          float vs0[32], vz0[32], vs1[32], vz1[32];
+          tmem_ld32(tS, vs0);
+          tmem_ld32(tZ, vz0);
+          tmem_ld_wait();
+          tmem_ld32(tS + 32, vs1);   // in flight while the first half is reduced
+          tmem_ld32(tZ + 32, vz1);
+          rowloss32(vs0, vz0, 32 * n1);
+          tmem_ld_wait();
           tc_fence_before();
           mbar_arrive_cluster(bar(kTmemEmpty0 + buf), 0);
+          rowloss32(vs1, vz1, 64 + 32 * n1);
+          acc_g += (ag4[0] + ag4[1]) + (ag4[2] + ag4[3]);
+          acc_q += (aq4[0] + aq4[1]) + (aq4[2] + aq4[3]);
         } else {
           // ---- gradient sweep: tile -> fp16 weight half-tiles -> tensor cores
-          const float r2_i = r_i * kL2e, c2_i = c_i * kL2e, rz2_i = rz_i * kL2e;
-          const float g2B_i = g_i * (2.f * (float)p.B);
+          const float m2cS2 = -2.f * cS2;
 #pragma unroll 1
           for (int h = 0; h < 2; ++h, ++hh) {
-            const float* cc = cst + (64 * h + 32 * n1) * 8;
+            const int jl0 = 64 * h + 32 * n1;
             float vs[32], vt[32], vz[32];
             tmem_ld32(tS + 32 * h, vs);
             tmem_ld32(tSt + 32 * h, vt);
@@ -554,36 +596,44 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               tc_fence_before();
               mbar_arrive_cluster(bar(kTmemEmpty0 + buf), 0);
             }
-            uint32_t wS[16], wSt[16], wZ[16];
+            uint32_t wSp[16], wStp[16], wZp[16];
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              float ms[2], mst[2], mz[2];
+            for (int e = 0; e < 32; e += 4) {
+              const float4 f0 = *reinterpret_cast<const float4*>(cst + 0 * 128 + jl0 + e);  // -r2_j
+              const float4 f1 = *reinterpret_cast<const float4*>(cst + 1 * 128 + jl0 + e);  // -c2_j
+              const float4 f2 = *reinterpret_cast<const float4*>(cst + 2 * 128 + jl0 + e);  // -rz2_j
+              const float4 f3 = *reinterpret_cast<const float4*>(cst + 3 * 128 + jl0 + e);  // gh_j
+              const float4 f4 = *reinterpret_cast<const float4*>(cst + 4 * 128 + jl0 + e);  // q_j
+              const float nr[4] = {f0.x, f0.y, f0.z, f0.w}, nc[4] = {f1.x, f1.y, f1.z, f1.w};
+              const float nrz[4] = {f2.x, f2.y, f2.z, f2.w}, gh[4] = {f3.x, f3.y, f3.z, f3.w};
+              const float qj[4] = {f4.x, f4.y, f4.z, f4.w};
+              float ms[4], mst[4], mz[4];
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const float4 ca = *reinterpret_cast<const float4*>(cc + (e + u) * 8);      // r_j c_j rz2_j 2B*g_j
-                const float4 cb = *reinterpret_cast<const float4*>(cc + (e + u) * 8 + 4);  // q_j colfac_j wS_j wZ_j
-                const float cf = cb.y;
-                const float s = vs[e + u] * (fS * cf), st = vt[e + u] * (fS * cf), z = vz[e + u] * (fZ * cf);
-                const float z2 = z * kL2e;
-                const float e1 = ex2f(fmaf(s, kL2e, -r2_i));           // softmax_row(S)_ij
-                const float e2 = ex2f(fmaf(s, kL2e, -ca.y * kL2e));    // softmax_col(S)_ij
-                const float e3 = ex2f(fmaf(st, kL2e, -ca.x * kL2e));   // softmax_row(S)_ji
-                const float e4 = ex2f(fmaf(st, kL2e, -c2_i));          // softmax_col(S)_ji
-                const float P = ex2f(z2 - rz2_i), Pt = ex2f(z2 - ca.z);
-                const float dS = fmaf(e2, cb.x, e1) - 2.f * P;         // 2B dS_ij
-                const float dSt = fmaf(e4, q_i, e3) - 2.f * Pt;        // 2B dS_ji
-                const float G = (r_i + ca.y) - 2.f * s;                // 2B G_ij
-                const float Gt = (ca.x + c_i) - 2.f * st;              // 2B G_ji
-                const float dZs = fmaf(P, G - g2B_i, Pt * (Gt - ca.w));
-                ms[u] = dS * cb.z;
-                mst[u] = dSt * cb.z;
-                mz[u] = dZs * cb.w;
+              for (int u = 0; u < 4; ++u) {
+                const float a = vs[e + u], bt = vt[e + u];
+                const float z2 = vz[e + u] * cZ2;
+                const float e1 = ex2f(fmaf(a, cS2, -r2_i));     // softmax_row(S)_ij
+                const float e2 = ex2f(fmaf(a, cS2, nc[u]));     // softmax_col(S)_ij
+                const float e3 = ex2f(fmaf(bt, cS2, nr[u]));    // softmax_row(S)_ji
+                const float e4 = ex2f(fmaf(bt, cS2, -c2_i));    // softmax_col(S)_ji
+                const float P = ex2f(z2 - rz2_i), Pt = ex2f(z2 + nrz[u]);
+                const float dS = fmaf(-2.f, P, fmaf(e2, qj[u], e1));    // 2B dS_ij
+                const float dSt = fmaf(-2.f, Pt, fmaf(e4, q_i, e3));    // 2B dS_ji
+                const float G = fmaf(a, m2cS2, r2_i - nc[u]);           // 2B G_ij log2(e)
+                const float Gt = fmaf(bt, m2cS2, c2_i - nr[u]);         // 2B G_ji log2(e)
+                const float dZs = fmaf(P, G - gh_i, Pt * (Gt - gh[u]));
+                ms[u] = dS * wS;
+                mst[u] = dSt * wS;
+                mz[u] = dZs * wZ;
               }
-              __half2 a = __floats2half2_rn(ms[0], ms[1]), b2 = __floats2half2_rn(mst[0], mst[1]);
-              __half2 c2 = __floats2half2_rn(mz[0], mz[1]);
-              wS[e >> 1] = *reinterpret_cast<uint32_t*>(&a);
-              wSt[e >> 1] = *reinterpret_cast<uint32_t*>(&b2);
-              wZ[e >> 1] = *reinterpret_cast<uint32_t*>(&c2);
+#pragma unroll
+              for (int u = 0; u < 4; u += 2) {
+                __half2 x = __floats2half2_rn(ms[u], ms[u + 1]), y = __floats2half2_rn(mst[u], mst[u + 1]);
+                __half2 w = __floats2half2_rn(mz[u], mz[u + 1]);
+                wSp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&x);
+                wStp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&y);
+                wZp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&w);
+              }
             }
             // the previous half's gradient MMAs must have drained the weight buffers
             mbar_wait(bar(kGradDone), (hh & 1) ^ 1);
@@ -592,11 +642,11 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int chunk = ((4 * n1 + k) ^ (m & 7)) * 16;
-              *reinterpret_cast<uint4*>(wrow + chunk) = make_uint4(wS[4 * k], wS[4 * k + 1], wS[4 * k + 2], wS[4 * k + 3]);
+              *reinterpret_cast<uint4*>(wrow + chunk) = make_uint4(wSp[4 * k], wSp[4 * k + 1], wSp[4 * k + 2], wSp[4 * k + 3]);
               *reinterpret_cast<uint4*>(wrow + kChunkBytes + chunk) =
-                  make_uint4(wSt[4 * k], wSt[4 * k + 1], wSt[4 * k + 2], wSt[4 * k + 3]);
+                  make_uint4(wStp[4 * k], wStp[4 * k + 1], wStp[4 * k + 2], wStp[4 * k + 3]);
               *reinterpret_cast<uint4*>(wrow + 2 * kChunkBytes + chunk) =
-                  make_uint4(wZ[4 * k], wZ[4 * k + 1], wZ[4 * k + 2], wZ[4 * k + 3]);
+                  make_uint4(wZp[4 * k], wZp[4 * k + 1], wZp[4 * k + 2], wZp[4 * k + 3]);
             }
             fence_proxy_async_smem();
             mbar_arrive_cluster(bar(kWFull), 0);
@@ -607,6 +657,9 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       // ---- end of job: write this job's partial results
       if (PHASE == kStats || PHASE == kRowLoss) {
         float* scratch = reinterpret_cast<float*>(sbase + kOffW);  // [6][64]
+        // log2-domain (max, sum) pairs
+        OnlineLse2 lS, lSt, lZ;
+        lS.m = mS * cS2; lS.s = sS; lSt.m = mSt * cS2; lSt.s = sSt; lZ.m = mZ * cZ2; lZ.s = sZ;
         named_bar_sync(2, kEpiThreads);
         if (n1 == 1) {
           if (PHASE == kStats) {
@@ -630,7 +683,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             out[o + 2 * (size_t)p.bpad] = make_float2(lZ.m, lZ.s);
           } else {
             const size_t o = (size_t)sp * 2 * p.bpad + lrow;
-            p.part[o] = acc_g + scratch[0 * 64 + m];
+            p.part[o] = (acc_g + scratch[0 * 64 + m]) * kLn2;   // back from log2 units: 2B g_i
             p.part[o + p.bpad] = acc_q + scratch[1 * 64 + m];
           }
         }
@@ -719,7 +772,7 @@ __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ v, 
 // small weights of the soft-target regime stay in the normal range.
 __global__ void __launch_bounds__(1024) wscale_kernel(const float* __restrict__ r, const float* __restrict__ c,
                                                       const float* __restrict__ q, int B,
-                                                      const float* __restrict__ colfac,
+                                                      const float* __restrict__ scale,
                                                       const float* __restrict__ norm_i,
                                                       const float* __restrict__ norm_t, float inv_tau, float tau,
                                                       float* __restrict__ out) {
@@ -727,7 +780,7 @@ __global__ void __launch_bounds__(1024) wscale_kernel(const float* __restrict__ 
   float v[6] = {-INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f};
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
     v[0] = fmaxf(v[0], r[i]); v[1] = fmaxf(v[1], c[i]); v[2] = fmaxf(v[2], q[i]);
-    v[3] = fmaxf(v[3], colfac[i]); v[4] = fmaxf(v[4], norm_i[i]); v[5] = fmaxf(v[5], norm_t[i]);
+    v[4] = fmaxf(v[4], norm_i[i]); v[5] = fmaxf(v[5], norm_t[i]);
   }
   for (int k = 0; k < 6; ++k) {
     v[k] = warp_max(v[k]);
@@ -737,6 +790,7 @@ __global__ void __launch_bounds__(1024) wscale_kernel(const float* __restrict__ 
   if (threadIdx.x < 32) {
     for (int k = 0; k < 6; ++k) v[k] = warp_max(sm[k][threadIdx.x]);
     if (threadIdx.x == 0) {
+      v[3] = scale[1];  // 1 / s: weights multiply the scaled plane
       const float gmax = fmaxf(v[0] + v[1] + 2.f * v[4] * v[5] * inv_tau, 1.f);
       const float b1 = (2.f + v[2]) * v[3] * inv_tau;
       const float b3 = 2.f * gmax * v[3] * 0.5f * tau;
@@ -844,23 +898,30 @@ static float* wscale_slot(void* ws, int b, int B, int D) {
 int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row_offset, int /*mode*/,
             void* planes_all, cudaStream_t st) {
   MC_REQUIRE(supported(D), MC_ERR_UNSUPPORTED, "tcgen05 engine needs D in {64,128,192,256} (got %d)", D);
+  MC_REQUIRE(b == B && row_offset == 0, MC_ERR_UNSUPPORTED,
+             "tcgen05 engine stages all B rows in one call (the scale is global): got b=%d B=%d row_offset=%d", b, B,
+             row_offset);
   MC_REQUIRE(aligned(planes_all, 256), MC_ERR_ALIGN, "clip_prepare: planes buffer must be 256-byte aligned");
   PlanesLayout l = planes_layout(B, D);
   char* base = static_cast<char*>(planes_all);
   __half* Xh = reinterpret_cast<__half*>(base + l.off_hi);
   __half* Xl = reinterpret_cast<__half*>(base + l.off_lo);
   __half* XhT = reinterpret_cast<__half*>(base + l.off_hiT);
-  float* colfac = reinterpret_cast<float*>(base + l.off_colfac);
+  float* hdr = reinterpret_cast<float*>(base + l.off_hdr);
   float* norm_i = reinterpret_cast<float*>(base + l.off_norm_i);
   float* norm_t = reinterpret_cast<float*>(base + l.off_norm_t);
-  const bool last = row_offset + b == B;
-  const int rows_total = b + (last ? l.Bp - B : 0);
-  stage_planes_kernel<<<(rows_total + 7) / 8, 256, 0, st>>>(I_loc, T_loc, b, B, l.Bp, D, row_offset, rows_total, Xh,
-                                                           Xl, colfac, norm_i, norm_t);
+  MC_CUDA(cudaMemsetAsync(hdr, 0, 16, st));
+  const size_t n = (size_t)B * D;
+  int ab = (int)((n + 255) / 256);
+  if (ab > num_sms() * 8) ab = num_sms() * 8;
+  amax_kernel<<<ab, 256, 0, st>>>(I_loc, T_loc, n, reinterpret_cast<unsigned int*>(hdr));
   MC_LAUNCH_CHECK();
-  const int j_begin = row_offset, j_end = last ? l.Bp : row_offset + b;
-  dim3 grid((j_end - j_begin + 63) / 64, 2 * D / 64);
-  transpose_hi_kernel<<<grid, 256, 0, st>>>(Xh, XhT, l.Bp, 2 * D, j_begin, j_end);
+  const int rows_total = l.Bp;
+  stage_planes_kernel<<<(rows_total + 7) / 8, 256, 0, st>>>(I_loc, T_loc, b, B, l.Bp, D, row_offset, rows_total, Xh,
+                                                           Xl, hdr, norm_i, norm_t);
+  MC_LAUNCH_CHECK();
+  dim3 grid((l.Bp + 63) / 64, 2 * D / 64);
+  transpose_hi_kernel<<<grid, 256, 0, st>>>(Xh, XhT, l.Bp, 2 * D, 0, l.Bp);
   MC_LAUNCH_CHECK();
   return MC_OK;
 }
@@ -892,7 +953,7 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, float* part,
   pp.n_row_blocks = sp.n_row_blocks; pp.n_tiles = sp.n_tiles; pp.nsplit = sp.nsplit;
   pp.tiles_per_split = sp.tiles_per_split; pp.bpad = sp.bpad;
   pp.inv_tau = 1.f / p.tau; pp.half_tau = 0.5f * p.tau; pp.inv_2B = 0.5f / (float)p.B;
-  pp.colfac = reinterpret_cast<const float*>(base + l.off_colfac);
+  pp.scale = reinterpret_cast<const float*>(base + l.off_hdr) + 1;
   pp.r = s.r; pp.c = s.c; pp.rz = s.rz; pp.g = s.g; pp.q = s.q;
   pp.part = part;
   pp.wscale = wscale;
@@ -966,7 +1027,7 @@ int bwd(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad
   const char* pbase = static_cast<const char*>(p.planes_all);
   float* wsc = wscale_slot(ws, p.b, p.B, p.D);
   MC_REQUIRE(p.planes_all != nullptr, MC_ERR_BAD_ARG, "clip_bwd(tc): planes buffer missing");
-  wscale_kernel<<<1, 1024, 0, st>>>(s.r, s.c, s.q, p.B, reinterpret_cast<const float*>(pbase + l.off_colfac),
+  wscale_kernel<<<1, 1024, 0, st>>>(s.r, s.c, s.q, p.B, reinterpret_cast<const float*>(pbase + l.off_hdr) + 1,
                                    reinterpret_cast<const float*>(pbase + l.off_norm_i),
                                    reinterpret_cast<const float*>(pbase + l.off_norm_t), 1.f / p.tau, p.tau, wsc);
   MC_LAUNCH_CHECK();

@@ -16,7 +16,7 @@ __device__ __forceinline__ void commit_1cta(uint32_t bar) {
 }
 
 // mode 0: cta_group::2, mode 1: cta_group::1.  nb = number of distinct B tiles cycled (reuse pattern)
-__global__ void __launch_bounds__(128, 1) bench(int mode, int M, int N, int iters, int distinctA, int nacc, int accstride, long long* out) {
+__global__ void __launch_bounds__(128, 1) bench(int mode, int M, int N, int iters, int pattern, int nacc, int accstride, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -39,16 +39,22 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int M, int N, int iter
   tc_fence_after();
   const uint32_t tm = slot;
   const bool leader = cluster_ctarank() == 0;
-  if (warp == 1 && (threadIdx.x & 31) == 0 && (leader || mode == 1)) {
+  if (warp == 1 && (leader || mode == 1) && elect_one()) {
     const uint32_t idesc = idesc_f16(M, N);
     const uint64_t a0 = smem_desc_sw128(base), b0 = smem_desc_sw128(base + 16384);
     long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) {
-      // 4 k-steps within a 128-byte row, cycling over `distinctA` A chunks (8 KB apart)
-      const uint64_t a = a0 + (uint64_t)(((i >> 2) % distinctA) * (8192 >> 4)) + 2 * (i & 3);
-      const uint64_t b = b0 + 2 * (i & 3);
-      const uint32_t td = tm + (uint32_t)((i % nacc) * accstride);
-      if (mode == 0) mma_f16_pair(td, a, b, idesc, i >= nacc); else mma_f16_1cta(td, a, b, idesc, i >= nacc);
+    // 8 MMAs per iteration, descriptor offsets are immediates: 4 k-steps x 2 A chunks; accumulators
+    // rotate over `nacc` TMEM regions (nacc in {1,2,4})
+    for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        // pattern bit0: A fixed, bit1: B fixed, bit2: operands change only every other MMA
+        const int uu = (pattern & 4) ? (u >> 1) : u;
+        const uint64_t a = (pattern & 1) ? a0 : a0 + (uint64_t)(((uu >> 2) & 1) * (8192 >> 4)) + 2 * (uu & 3);
+        const uint64_t b = (pattern & 2) ? b0 : b0 + (uint64_t)(((uu >> 2) & 1) * (8192 >> 4)) + 2 * (uu & 3);
+        const uint32_t td = tm + (uint32_t)((u & (nacc - 1)) * accstride);
+        if (mode == 0) mma_f16_pair(td, a, b, idesc, (i | u) >= nacc); else mma_f16_1cta(td, a, b, idesc, (i | u) >= nacc);
+      }
     }
     if (mode == 0) mma_commit_pair(bar, 1); else commit_1cta(bar);
     mbar_wait(bar, 0);
@@ -67,23 +73,27 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int M, int N, int iter
 int main() {
   long long* d; cudaMalloc(&d, 8);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  struct C { int mode, M, N, nacc; } cfgs[] = {{0,128,128,1},{0,128,128,2},{0,128,128,3},{0,128,128,4},{0,128,128,8},{0,128,256,1},{0,128,256,2},{0,128,256,4},
-      {0,256,128,1},{0,256,128,2},{0,256,128,4},{0,256,256,1},{0,256,256,2},{1,128,128,1},{1,128,128,2},{1,128,128,4},{1,128,256,1},{1,128,256,2}};
+  struct C { int mode, M, N, nacc, pattern; } cfgs[] = {
+      {0,128,128,2,0},{0,128,128,2,1},{0,128,128,2,2},{0,128,128,2,3},{0,128,128,2,4},
+      {0,128,256,2,0},{0,128,256,2,1},{0,128,256,2,2},{0,128,256,2,3},
+      {0,256,128,2,0},{0,256,128,2,1},{0,256,128,2,2},{0,256,128,2,3},
+      {0,256,256,2,0},{0,256,256,2,3},
+      {1,128,128,2,0},{1,128,128,2,1},{1,128,128,2,2},{1,128,128,2,3},{1,128,256,2,0},{1,128,256,2,3}};
   for (auto c : cfgs) {
     const int iters = 4096;
-    // TMEM columns per accumulator: cta_group::2 M=128 -> N/2, otherwise N
     const int accstride = (c.mode == 0 && c.M == 128) ? c.N / 2 : c.N;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(148); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 64 * 1024;
     cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim = {2,1,1};
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, bench, c.mode, c.M, c.N, iters, 4, c.nacc, accstride, d);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, bench, c.mode, c.M, c.N, iters, c.pattern, c.nacc, accstride, d);
     cudaError_t e2 = cudaDeviceSynchronize();
     long long cyc = 0; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
     double per = (double)cyc / iters;
     double macs = (double)c.M * c.N * 16 / per / (c.mode == 0 ? 2 : 1);
-    printf("cta_group::%d M=%3d N=%3d nacc=%d : %7.2f cyc/MMA  -> %7.1f MAC/cycle/SM (%s %s)\n", c.mode == 0 ? 2 : 1, c.M, c.N,
-           c.nacc, per, macs, cudaGetErrorString(e), cudaGetErrorString(e2));
+    printf("cta_group::%d M=%3d N=%3d pattern=%d (%s%s%s): %7.2f cyc/MMA -> %7.1f MAC/cycle/SM (%s %s)\n", c.mode == 0 ? 2 : 1, c.M, c.N,
+           c.pattern, (c.pattern & 1) ? "A fixed " : "A varies ", (c.pattern & 2) ? "B fixed" : "B varies", (c.pattern & 4) ? " pairs" : "", per, macs,
+           cudaGetErrorString(e), cudaGetErrorString(e2));
   }
   return 0;
 }

@@ -66,3 +66,27 @@ for B, D, scale in sizes:
             l1, dI1, dT1 = full(I, T, 1.0, mode)
             print(f"B={B} D={D} scale={scale} mode={mode} loss {l1.item():.6f} vs {l0.item():.6f} "
                   f"rel dI {rel(dI1, dI0):.2e} dT {rel(dT1, dT0):.2e}", flush=True)
+
+if which == "rowloss":
+    for B, D, scale in [(256, 256, 1.0), (4096, 256, 1.0)]:
+        I, T = emb(B, D, 0, scale), emb(B, D, 1, scale)
+        res = {}
+        for mode in (0, 1):
+            planes, ws, s = phases(I, T, 1.0, mode)
+            gq = torch.zeros(2, B, device="cuda"); part = torch.zeros(1, device="cuda")
+            check(lib.mc_clip_rowloss(ptr(I), ptr(T), ptr(planes), B, B, D, 0, 1.0, mode, ptr(s[0]), ptr(s[1]), ptr(s[2]),
+                                      ptr(gq[0]), ptr(gq[1]), ptr(part), ptr(ws), ws.numel(), cur_stream()), "rowloss")
+            torch.cuda.synchronize()
+            res[mode] = (s.clone(), gq.clone(), part.clone())
+        s0, gq0, p0 = res[0]; s1, gq1, p1 = res[1]
+        print(f"B={B}: stats maxdiff {[(s1[k]-s0[k]).abs().max().item() for k in range(3)]}  g rel {rel(gq1[0], gq0[0]):.2e} "
+              f"q maxdiff {(gq1[1]-gq0[1]).abs().max().item():.2e} loss {p1.item():.6f} vs {p0.item():.6f}")
+        # feed SIMT stats into the TC bwd and vice versa to localise the error
+        for mode_b, (ss, gg) in (("tc bwd with simt stats", (s0, gq0)), ("tc bwd with tc stats", (s1, gq1))):
+            planes, ws, _ = phases(I, T, 1.0, 1)
+            dI = torch.zeros_like(I); dT = torch.zeros_like(T)
+            check(lib.mc_clip_bwd(ptr(I), ptr(T), ptr(planes), B, B, D, 0, 1.0, 1, ptr(ss[0]), ptr(ss[1]), ptr(ss[2]),
+                                  ptr(gg[0]), ptr(gg[1]), None, ptr(dI), ptr(dT), ptr(ws), ws.numel(), cur_stream()), "bwd")
+            torch.cuda.synchronize()
+            l0, dI0, dT0 = full(I, T, 1.0, 0)
+            print("   ", mode_b, f"rel dI {rel(dI, dI0):.2e} dT {rel(dT, dT0):.2e}")
