@@ -18,7 +18,7 @@ static int check_problem(const char* who, const float* I_all, const float* T_all
   return MC_OK;
 }
 
-// Shapes the tcgen05 engine does not cover (D not a multiple of 64 or > 256) run on the fp32 SIMT
+// Shapes the tcgen05 engine does not cover (D other than 128 / 256) run on the fp32 SIMT
 // engine: same device, same ABI, true-fp32 arithmetic - never a CPU path.
 static int eff_mode(int mode, int D) {
   return (mode != MC_GEMM_SIMT_FP32 && !tc::supported(D)) ? (int)MC_GEMM_SIMT_FP32 : mode;

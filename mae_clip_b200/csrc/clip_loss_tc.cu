@@ -29,9 +29,10 @@ using namespace ptx;
 constexpr int kTileN = 128;             // columns j per pair tile
 constexpr int kRowsCta = 64;            // samples per CTA
 constexpr int kChunkBytes = 64 * 128;   // 64 rows x 64 fp16
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 384;      // warps 0-3: TMA / MMA / X^T producer / spare; warps 4-11: epilogue
+constexpr int kEpiThreads = 256;
 constexpr int kMaxSplit = 16;
+constexpr int kIssuers = 1;         // MMA-issuing warps per leader CTA (see the issuer role)
 
 enum Phase { kStats = 0, kRowLoss = 1, kBwd = 2 };
 
@@ -57,7 +58,8 @@ enum Bar {
   kXTFull = 20,
   kAccFull = 21,
   kAccEmpty = 22,
-  kNumBars = 23
+  kGradDone1 = 23,   // kGradDone: column half 0, kGradDone1: column half 1
+  kNumBars = 24
 };
 
 struct PairParams {
@@ -89,7 +91,8 @@ static PlanesLayout planes_layout(int B, int D) {
   return l;
 }
 
-bool supported(int D) { return D % 64 == 0 && D >= 64 && D <= 256; }
+// D/4 accumulator columns per epilogue thread must be a multiple of the 32-column TMEM load
+bool supported(int D) { return D == 128 || D == 256; }
 
 // ------------------------------------------------------------------------------------------
 // staging: fp32 embeddings -> scaled fp16 hi / lo planes of X = [I || T], the per-row scale, and
@@ -218,8 +221,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
             const __grid_constant__ CUtensorMap map_t, const PairParams p) {
-  constexpr int kNBuf = (PHASE == kBwd) ? 1 : 2;   // TMEM tile buffers (3 x 64 columns each)
-  constexpr uint32_t kAccCol = 256;                // gradient accumulators: dT at 256, dI at 256 + D/2
+  // TMEM: tile buffers of 3 x 64 columns (S, St, Z) from column 0; the gradient sweep keeps one tile
+  // buffer (the epilogue empties it into registers at once) and its accumulators at 256 (dT), 256 + D/2 (dI)
+  constexpr int kNBuf = (PHASE == kBwd) ? 1 : 2;
+  constexpr uint32_t kAccCol = 256;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -229,7 +234,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   auto bar = [&](int i) -> uint32_t { return bar0 + 8u * i; };
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(sbase + kOffBar + 8 * kNumBars);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches (and setmaxnreg) are uniform
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -237,14 +243,15 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   const int njobs = p.n_row_blocks * p.nsplit;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kSlots; ++s) { mbar_init(bar(kFull0 + s), 1); mbar_init(bar(kEmpty0 + s), 1); }
+    for (int s = 0; s < kSlots; ++s) { mbar_init(bar(kFull0 + s), 1); mbar_init(bar(kEmpty0 + s), kIssuers); }
     mbar_init(bar(kAFull), 1);
-    mbar_init(bar(kJobDone), 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar(kTmemFull0 + i), 1); mbar_init(bar(kTmemEmpty0 + i), 2 * kEpiThreads); }
-    mbar_init(bar(kWFull), 2 * kEpiThreads);
-    mbar_init(bar(kGradDone), 1);
+    mbar_init(bar(kJobDone), kIssuers);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(kTmemFull0 + i), kIssuers); mbar_init(bar(kTmemEmpty0 + i), 2 * kEpiThreads); }
+    mbar_init(bar(kWFull), kEpiThreads);  // one column half at a time: 2 CTAs x 128 threads
+    mbar_init(bar(kGradDone), kIssuers);
+    mbar_init(bar(kGradDone1), kIssuers);
     mbar_init(bar(kXTFull), 1);
-    mbar_init(bar(kAccFull), 1);
+    mbar_init(bar(kAccFull), kIssuers);
     mbar_init(bar(kAccEmpty), 2 * kEpiThreads);
     fence_mbar_init();
     prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_b_hi); prefetch_tmap(&map_b_lo);
@@ -259,56 +266,72 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // =========================================================== TMA producer (one elected lane per CTA)
-    if (elect_one()) {
-      uint32_t it = 0, hh = 0, jj = 0;
-      for (int job = pair_id; job < njobs; job += npairs, ++jj) {
-        const int rb = job / p.nsplit, sp = job % p.nsplit;
-        const int row_a = p.row_offset + rb * 128 + (int)rank * kRowsCta;
-        const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-        mbar_wait(bar(kJobDone), (jj & 1) ^ 1);
-        if (leader) mbar_arrive_expect_tx(bar(kAFull), 2u * 2u * nkc * kChunkBytes);
-        for (int c = 0; c < 2 * nkc; ++c) tma_load_2d_pair(base + kOffA + c * kChunkBytes, &map_a_hi, bar(kAFull), c * 64, row_a);
-        for (int t = t0; t < t1; ++t) {
-          const int j0 = t * kTileN + 32 * (int)rank, j1 = j0 + 64;
-          for (int c = 0; c < nkc; ++c) {
-            const int ci = c * 64, ct = D + c * 64;
-            uint32_t fb;
-            auto acquire = [&]() -> uint32_t {  // next ring slot: wait until the MMAs released it, arm its barrier
-              const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
-              ++it;
-              mbar_wait(bar(kEmpty0 + slot), par ^ 1);
-              fb = bar(kFull0 + slot);
-              if (leader) mbar_arrive_expect_tx(fb, 2u * kSlotBytes);
-              return base + kOffStage + slot * kSlotBytes;
-            };
-            if (PASSES == 3) {
-              uint32_t sb = acquire();
-              tma_load_2d_pair(sb, &map_a_lo, fb, ci, row_a);                         // I_i lo
-              tma_load_2d_pair(sb + kChunkBytes, &map_a_lo, fb, ct, row_a);           // T_i lo
-              sb = acquire();
-              tma_load_2d_pair(sb, &map_b_hi, fb, ci, j0);                            // I_j hi
-              tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ci, j1);
-              tma_load_2d_pair(sb + kChunkBytes, &map_b_lo, fb, ci, j0);              // I_j lo
-              tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_lo, fb, ci, j1);
-              sb = acquire();
-              tma_load_2d_pair(sb, &map_b_hi, fb, ct, j0);                            // T_j hi
-              tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ct, j1);
-              tma_load_2d_pair(sb + kChunkBytes, &map_b_lo, fb, ct, j0);              // T_j lo
-              tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_lo, fb, ct, j1);
-            } else {
-              const uint32_t sb = acquire();
-              tma_load_2d_pair(sb, &map_b_hi, fb, ci, j0);                            // I_j hi
-              tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ci, j1);
-              tma_load_2d_pair(sb + kChunkBytes, &map_b_hi, fb, ct, j0);              // T_j hi
-              tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_hi, fb, ct, j1);
+  if (warp < 4) {
+    // warpgroup 0: data movement and MMA issue need few registers; hand the rest to the epilogue.
+    // The pool is what the launch allocated (384 x 168): 128 x 120 + 256 x 192 uses it exactly.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+    if (warp == 0) {
+      // ========================================================= TMA producer: resident rows + ring
+      if (elect_one()) {
+        uint32_t it = 0, jj = 0;
+        for (int job = pair_id; job < njobs; job += npairs, ++jj) {
+          const int rb = job / p.nsplit, sp = job % p.nsplit;
+          const int row_a = p.row_offset + rb * 128 + (int)rank * kRowsCta;
+          const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+          mbar_wait(bar(kJobDone), (jj & 1) ^ 1);
+          if (leader) mbar_arrive_expect_tx(bar(kAFull), 2u * 2u * nkc * kChunkBytes);
+          for (int c = 0; c < 2 * nkc; ++c)
+            tma_load_2d_pair(base + kOffA + c * kChunkBytes, &map_a_hi, bar(kAFull), c * 64, row_a);
+          for (int t = t0; t < t1; ++t) {
+            const int j0 = t * kTileN + 32 * (int)rank, j1 = j0 + 64;
+            for (int c = 0; c < nkc; ++c) {
+              const int ci = c * 64, ct = D + c * 64;
+              uint32_t fb;
+              auto acquire = [&]() -> uint32_t {  // next ring slot: wait until the MMAs released it, arm its barrier
+                const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
+                ++it;
+                mbar_wait(bar(kEmpty0 + slot), par ^ 1);
+                fb = bar(kFull0 + slot);
+                if (leader) mbar_arrive_expect_tx(fb, 2u * kSlotBytes);
+                return base + kOffStage + slot * kSlotBytes;
+              };
+              if (PASSES == 3) {
+                uint32_t sb = acquire();
+                tma_load_2d_pair(sb, &map_a_lo, fb, ci, row_a);                         // I_i lo
+                tma_load_2d_pair(sb + kChunkBytes, &map_a_lo, fb, ct, row_a);           // T_i lo
+                sb = acquire();
+                tma_load_2d_pair(sb, &map_b_hi, fb, ci, j0);                            // I_j hi
+                tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ci, j1);
+                tma_load_2d_pair(sb + kChunkBytes, &map_b_lo, fb, ci, j0);              // I_j lo
+                tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_lo, fb, ci, j1);
+                sb = acquire();
+                tma_load_2d_pair(sb, &map_b_hi, fb, ct, j0);                            // T_j hi
+                tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ct, j1);
+                tma_load_2d_pair(sb + kChunkBytes, &map_b_lo, fb, ct, j0);              // T_j lo
+                tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_lo, fb, ct, j1);
+              } else {
+                const uint32_t sb = acquire();
+                tma_load_2d_pair(sb, &map_b_hi, fb, ci, j0);                            // I_j hi
+                tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ci, j1);
+                tma_load_2d_pair(sb + kChunkBytes, &map_b_hi, fb, ct, j0);              // T_j hi
+                tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_hi, fb, ct, j1);
+              }
             }
           }
-          if (PHASE == kBwd) {
-            const uint32_t xt_bytes = (uint32_t)(D / 2) * 128u;  // D/2 rows x 64 j fp16
-            for (int h = 0; h < 2; ++h, ++hh) {
-              mbar_wait(bar(kGradDone), (hh & 1) ^ 1);
+        }
+      }
+    } else if (warp == 2) {
+      // ========================================================= TMA producer: X^T half tiles (gradient GEMMs)
+      if (PHASE == kBwd && elect_one()) {
+        const uint32_t xt_bytes = (uint32_t)(D / 2) * 128u;  // D/2 rows x 64 j fp16
+        uint32_t tt = 0;
+        for (int job = pair_id; job < njobs; job += npairs) {
+          const int sp = job % p.nsplit;
+          const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+          for (int t = t0; t < t1; ++t, ++tt) {
+            for (int h = 0; h < 2; ++h) {
+              // the previous half's MMAs are done with the buffer: (tt-1, 1) before (tt, 0); (tt, 0) before (tt, 1)
+              if (h == 0) mbar_wait(bar(kGradDone1), (tt & 1) ^ 1); else mbar_wait(bar(kGradDone), tt & 1);
               if (leader) mbar_arrive_expect_tx(bar(kXTFull), 2u * 2u * xt_bytes);
               const int jx = t * kTileN + 64 * h;
               tma_load_2d_pair(base + kOffXT, &map_t, bar(kXTFull), jx, (int)rank * (D / 2));
@@ -317,145 +340,181 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           }
         }
       }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // =========================================================== MMA issuer (leader CTA, one elected lane:
-    // inside elect.sync the compiler knows a single thread is active and feeds the uniform-register
-    // operands of UTCHMMA / UTMALDG directly instead of a per-lane waterfall loop)
-    if (leader && elect_one()) {
-      constexpr uint32_t idesc_tile = idesc_f16(128, kTileN);
-      const uint32_t idesc_grad = idesc_f16(128, D);
-      uint32_t it = 0, tt = 0, hh = 0, jj = 0;
-      for (int job = pair_id; job < njobs; job += npairs, ++jj) {
-        const int sp = job % p.nsplit;
-        const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-        mbar_wait(bar(kAFull), jj & 1);
-        tc_fence_after();
-        for (int t = t0; t < t1; ++t, ++tt) {
-          const uint32_t buf = tt % kNBuf, use = tt / kNBuf;
-          mbar_wait(bar(kTmemEmpty0 + buf), (use & 1) ^ 1);
+    } else if (warp == 1 || (kIssuers == 2 && warp == 3)) {
+      // ========================================================= MMA issuer (leader CTA, one elected lane:
+      // inside elect.sync the compiler knows a single thread is active and feeds the uniform-register
+      // operands of UTCHMMA from vector registers without a per-lane waterfall loop).
+      // kIssuers == 2 splits the stream over warps 1 (S, St, dT) and 3 (Z, dI); measured SLOWER on
+      // B200 (the 128 x 128 x 16 pair MMA itself sustains ~45 cycles, not the issuing thread), kept off.
+      const bool do_s = kIssuers == 1 || warp == 1, do_z = kIssuers == 1 || warp == 3;
+      if (leader && elect_one()) {
+        constexpr uint32_t idesc_tile = idesc_f16(128, kTileN);
+        const uint32_t idesc_grad = idesc_f16(128, D);
+        const uint32_t tDT = tmem_base + kAccCol, tDI = tDT + (uint32_t)(D / 2);
+        const uint32_t xt_bytes = (uint32_t)(D / 2) * 128u;
+        const uint64_t wS = smem_desc_sw128(base + kOffW), wSt = smem_desc_sw128(base + kOffW + kChunkBytes);
+        const uint64_t wZ = smem_desc_sw128(base + kOffW + 2 * kChunkBytes);
+        const uint64_t xI = smem_desc_sw128(base + kOffXT), xT = smem_desc_sw128(base + kOffXT + xt_bytes);
+        uint32_t it = 0, tt = 0, hh = 0, jj = 0;
+        // one column half of a tile's gradient GEMMs: dT += W_S I_j + W_Z T_j, dI += W_St T_j + W_Z I_j
+        auto grad_half = [&](int h, bool first_of_job) {
+          mbar_wait(bar(kWFull), hh & 1);
+          mbar_wait(bar(kXTFull), hh & 1);
+          ++hh;
           tc_fence_after();
-          const uint32_t tS = tmem_base + buf * 192, tSt = tS + 64, tZ = tS + 128;
-          for (int c = 0; c < nkc; ++c) {
-            uint32_t slot_bar = 0;
-            auto next_full = [&]() -> uint32_t {  // wait for the next ring slot to land
-              const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
-              ++it;
-              mbar_wait(bar(kFull0 + slot), par);
-              tc_fence_after();
-              slot_bar = bar(kEmpty0 + slot);
-              return base + kOffStage + slot * kSlotBytes;
-            };
-            const uint64_t aI = smem_desc_sw128(base + kOffA + c * kChunkBytes);
-            const uint64_t aT = smem_desc_sw128(base + kOffA + (nkc + c) * kChunkBytes);
-            const uint32_t first = (c > 0) ? 1u : 0u;
-            if (PASSES == 3) {
-              const uint32_t sa = next_full();
-              const uint32_t a_bar = slot_bar;
-              const uint64_t aIl = smem_desc_sw128(sa), aTl = smem_desc_sw128(sa + kChunkBytes);
-              uint32_t sb = next_full();
-              {
-                const uint64_t bI = smem_desc_sw128(sb), bIl = smem_desc_sw128(sb + kChunkBytes);
+          const uint32_t first = (first_of_job && h == 0) ? 0u : 1u;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
-                  const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
-                  const uint64_t kb = desc_advance_k(bI, ks), kbl = desc_advance_k(bIl, ks);
-                  mma_f16_pair(tS, kT, kb, idesc_tile, acc);                         // S  = T_i I_j^T
-                  mma_f16_pair(tS, kT, kbl, idesc_tile, 1u);
-                  mma_f16_pair(tS, desc_advance_k(aTl, ks), kb, idesc_tile, 1u);
-                  mma_f16_pair(tZ, kI, kb, idesc_tile, acc);                         // Z += I_i I_j^T
-                  mma_f16_pair(tZ, kI, kbl, idesc_tile, 1u);
-                  mma_f16_pair(tZ, desc_advance_k(aIl, ks), kb, idesc_tile, 1u);
-                }
-              }
-              mma_commit_pair(slot_bar, 3);
-              sb = next_full();
-              {
-                const uint64_t bT = smem_desc_sw128(sb), bTl = smem_desc_sw128(sb + kChunkBytes);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
+            const uint64_t kxI = desc_advance_k(xI, ks), kxT = desc_advance_k(xT, ks);
+            const uint64_t kwZ = desc_advance_k(wZ, ks);
+            if (do_s) {
+              mma_f16_pair(tDT, desc_advance_k(wS, ks), kxI, idesc_grad, acc);   // dT += (dS/tau) I_j
+              mma_f16_pair(tDT, kwZ, kxT, idesc_grad, 1u);                       // dT += (tau/2 dZs) T_j
+            }
+            if (do_z) {
+              mma_f16_pair(tDI, desc_advance_k(wSt, ks), kxT, idesc_grad, acc);  // dI += (dS^T/tau) T_j
+              mma_f16_pair(tDI, kwZ, kxI, idesc_grad, 1u);                       // dI += (tau/2 dZs) I_j
+            }
+          }
+          mma_commit_pair(bar(h == 0 ? kGradDone : kGradDone1), 3);
+        };
+        for (int job = pair_id; job < njobs; job += npairs, ++jj) {
+          const int sp = job % p.nsplit;
+          const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+          mbar_wait(bar(kAFull), jj & 1);
+          tc_fence_after();
+          for (int t = t0; t < t1; ++t, ++tt) {
+            const uint32_t buf = tt % kNBuf, use = tt / kNBuf;
+            mbar_wait(bar(kTmemEmpty0 + buf), (use & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tS = tmem_base + buf * 192, tSt = tS + 64, tZ = tS + 128;
+            // The gradient GEMMs of tile t-1 are woven into the recompute of tile t: half 0 after the
+            // first chunks (its weights are ready by then), half 1 after the last chunk, so the
+            // single weight / X^T buffers are refilled while the tensor cores stay busy.
+            const bool lagged = PHASE == kBwd && t > t0;
+            for (int c = 0; c < nkc; ++c) {
+              if (lagged && c == nkc / 2) grad_half(0, t - 1 == t0);
+              uint32_t slot_bar = 0;
+              auto next_full = [&]() -> uint32_t {  // wait for the next ring slot to land
+                const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
+                ++it;
+                mbar_wait(bar(kFull0 + slot), par);
+                tc_fence_after();
+                slot_bar = bar(kEmpty0 + slot);
+                return base + kOffStage + slot * kSlotBytes;
+              };
+              const uint64_t aI = smem_desc_sw128(base + kOffA + c * kChunkBytes);
+              const uint64_t aT = smem_desc_sw128(base + kOffA + (nkc + c) * kChunkBytes);
+              const uint32_t first = (c > 0) ? 1u : 0u;
+              if (PASSES == 3) {
+                const uint32_t sa = next_full();
+                const uint32_t a_bar = slot_bar;
+                const uint64_t aIl = smem_desc_sw128(sa), aTl = smem_desc_sw128(sa + kChunkBytes);
+                uint32_t sb = next_full();
+                {
+                  const uint64_t bI = smem_desc_sw128(sb), bIl = smem_desc_sw128(sb + kChunkBytes);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
-                  const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
-                  const uint64_t kb = desc_advance_k(bT, ks), kbl = desc_advance_k(bTl, ks);
-                  if (PHASE != kRowLoss) {
-                    mma_f16_pair(tSt, kI, kb, idesc_tile, acc);                      // St = I_i T_j^T
-                    mma_f16_pair(tSt, kI, kbl, idesc_tile, 1u);
-                    mma_f16_pair(tSt, desc_advance_k(aIl, ks), kb, idesc_tile, 1u);
+                  for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
+                    const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
+                    const uint64_t kb = desc_advance_k(bI, ks), kbl = desc_advance_k(bIl, ks);
+                    if (do_s) {
+                      mma_f16_pair(tS, kT, kb, idesc_tile, acc);                       // S  = T_i I_j^T
+                      mma_f16_pair(tS, kT, kbl, idesc_tile, 1u);
+                      mma_f16_pair(tS, desc_advance_k(aTl, ks), kb, idesc_tile, 1u);
+                    }
+                    if (do_z) {
+                      mma_f16_pair(tZ, kI, kb, idesc_tile, acc);                       // Z += I_i I_j^T
+                      mma_f16_pair(tZ, kI, kbl, idesc_tile, 1u);
+                      mma_f16_pair(tZ, desc_advance_k(aIl, ks), kb, idesc_tile, 1u);
+                    }
                   }
-                  mma_f16_pair(tZ, kT, kb, idesc_tile, 1u);                          // Z += T_i T_j^T
-                  mma_f16_pair(tZ, kT, kbl, idesc_tile, 1u);
-                  mma_f16_pair(tZ, desc_advance_k(aTl, ks), kb, idesc_tile, 1u);
                 }
-              }
-              mma_commit_pair(slot_bar, 3);
-              mma_commit_pair(a_bar, 3);
-            } else {
-              const uint32_t sb = next_full();
-              const uint64_t bI = smem_desc_sw128(sb), bT = smem_desc_sw128(sb + kChunkBytes);
+                mma_commit_pair(slot_bar, 3);
+                sb = next_full();
+                {
+                  const uint64_t bT = smem_desc_sw128(sb), bTl = smem_desc_sw128(sb + kChunkBytes);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
-                const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
-                const uint64_t kbI = desc_advance_k(bI, ks), kbT = desc_advance_k(bT, ks);
-                mma_f16_pair(tS, kT, kbI, idesc_tile, acc);
-                if (PHASE != kRowLoss) mma_f16_pair(tSt, kI, kbT, idesc_tile, acc);
-                mma_f16_pair(tZ, kI, kbI, idesc_tile, acc);
-                mma_f16_pair(tZ, kT, kbT, idesc_tile, 1u);
+                  for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
+                    const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
+                    const uint64_t kb = desc_advance_k(bT, ks), kbl = desc_advance_k(bTl, ks);
+                    if (do_s) {
+                      if (PHASE != kRowLoss) {
+                        mma_f16_pair(tSt, kI, kb, idesc_tile, acc);                    // St = I_i T_j^T
+                        mma_f16_pair(tSt, kI, kbl, idesc_tile, 1u);
+                        mma_f16_pair(tSt, desc_advance_k(aIl, ks), kb, idesc_tile, 1u);
+                      }
+                    }
+                    if (do_z) {
+                      mma_f16_pair(tZ, kT, kb, idesc_tile, 1u);                        // Z += T_i T_j^T
+                      mma_f16_pair(tZ, kT, kbl, idesc_tile, 1u);
+                      mma_f16_pair(tZ, desc_advance_k(aTl, ks), kb, idesc_tile, 1u);
+                    }
+                  }
+                }
+                mma_commit_pair(slot_bar, 3);
+                mma_commit_pair(a_bar, 3);
+              } else {
+                const uint32_t sb = next_full();
+                const uint64_t bI = smem_desc_sw128(sb), bT = smem_desc_sw128(sb + kChunkBytes);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
+                  const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
+                  const uint64_t kbI = desc_advance_k(bI, ks), kbT = desc_advance_k(bT, ks);
+                  if (do_s) {
+                    mma_f16_pair(tS, kT, kbI, idesc_tile, acc);
+                    if (PHASE != kRowLoss) mma_f16_pair(tSt, kI, kbT, idesc_tile, acc);
+                  }
+                  if (do_z) {
+                    mma_f16_pair(tZ, kI, kbI, idesc_tile, acc);
+                    mma_f16_pair(tZ, kT, kbT, idesc_tile, 1u);
+                  }
+                }
+                mma_commit_pair(slot_bar, 3);
               }
-              mma_commit_pair(slot_bar, 3);
+            }
+            mma_commit_pair(bar(kTmemFull0 + buf), 3);
+            if (PHASE == kBwd) {
+              if (t == t0) {
+                mbar_wait(bar(kAccEmpty), (jj & 1) ^ 1);  // the previous job's accumulators were read out
+                tc_fence_after();
+              } else {
+                grad_half(1, false);
+              }
             }
           }
-          mma_commit_pair(bar(kTmemFull0 + buf), 3);
           if (PHASE == kBwd) {
-            if (t == t0) {
-              mbar_wait(bar(kAccEmpty), (jj & 1) ^ 1);
-              tc_fence_after();
-            }
-            const uint32_t tDT = tmem_base + kAccCol, tDI = tDT + (uint32_t)(D / 2);
-            const uint32_t xt_bytes = (uint32_t)(D / 2) * 128u;
-            const uint64_t wS = smem_desc_sw128(base + kOffW), wSt = smem_desc_sw128(base + kOffW + kChunkBytes);
-            const uint64_t wZ = smem_desc_sw128(base + kOffW + 2 * kChunkBytes);
-            const uint64_t xI = smem_desc_sw128(base + kOffXT), xT = smem_desc_sw128(base + kOffXT + xt_bytes);
-            for (int h = 0; h < 2; ++h, ++hh) {
-              mbar_wait(bar(kWFull), hh & 1);
-              mbar_wait(bar(kXTFull), hh & 1);
-              tc_fence_after();
-              const uint32_t first = (t == t0 && h == 0) ? 0u : 1u;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
-                const uint64_t kxI = desc_advance_k(xI, ks), kxT = desc_advance_k(xT, ks);
-                const uint64_t kwZ = desc_advance_k(wZ, ks);
-                mma_f16_pair(tDT, desc_advance_k(wS, ks), kxI, idesc_grad, acc);   // dT += (dS/tau) I_j
-                mma_f16_pair(tDT, kwZ, kxT, idesc_grad, 1u);                       // dT += (tau/2 dZs) T_j
-                mma_f16_pair(tDI, desc_advance_k(wSt, ks), kxT, idesc_grad, acc);  // dI += (dS^T/tau) T_j
-                mma_f16_pair(tDI, kwZ, kxI, idesc_grad, 1u);                       // dI += (tau/2 dZs) I_j
-              }
-              mma_commit_pair(bar(kGradDone), 3);
-            }
+            grad_half(0, t1 - 1 == t0);
+            grad_half(1, false);
+            mma_commit_pair(bar(kAccFull), 3);
           }
+          mma_commit_pair(bar(kJobDone), 3);
         }
-        if (PHASE == kBwd) mma_commit_pair(bar(kAccFull), 3);
-        mma_commit_pair(bar(kJobDone), 3);
       }
     }
     __syncwarp();
   } else {
-    // =========================================================== epilogue: one thread per TMEM lane
+    // =========================================================== epilogue: two threads per TMEM lane
+    // Warps 4-7 take the first 32 TMEM columns of every tile, warps 8-11 the second 32 (column half h).
     // Everything inside exponentials lives in the log2 domain (ex2.approx); the raw accumulators are
     // products of the scaled planes, so S = acc * inv_s2 / tau and Z = acc * inv_s2 * tau / 2.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     const int quarter = warp & 3;
+    const int h = (warp - 4) >> 2;
     const int lane_t = quarter * 32 + lane;
     const int m = lane_t & 63, n1 = lane_t >> 6;
-    const int tid_e = threadIdx.x - 64;
+    const int tid_e = threadIdx.x - 128;  // 0..255
     const uint32_t lane_field = (uint32_t)(quarter * 32) << 16;
+    const int jl0 = 64 * h + 32 * n1;     // first tile column of this thread's 32
     float* const consts = reinterpret_cast<float*>(sbase + kOffConst);  // [2 buffers][8 fields][128 columns]
     const float kL2e = 1.4426950408889634f;
     const float inv_s = p.scale[1], inv_s2 = p.scale[2];
     const float cS2 = inv_s2 * p.inv_tau * kL2e, cZ2 = inv_s2 * p.half_tau * kL2e;  // raw acc -> log2 domain
-    uint32_t tt = 0, hh = 0, jj = 0;
+    const float m2cS2 = -2.f * cS2;
+    uint32_t tt = 0, jj = 0;
     for (int job = pair_id; job < njobs; job += npairs, ++jj) {
       const int rb = job / p.nsplit, sp = job % p.nsplit;
       const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
@@ -473,19 +532,24 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         wZ = inv_s * p.half_tau * wsc * kLn2;      // 2B dZs (log2 units) -> fp16 weight
       }
       float mS = -INFINITY, sS = 0.f, mSt = -INFINITY, sSt = 0.f, mZ = -INFINITY, sZ = 0.f;  // raw-domain max, sums
-      float acc_g = 0.f, acc_q = 0.f;
+      float ag4[4] = {0.f, 0.f, 0.f, 0.f}, aq4[4] = {0.f, 0.f, 0.f, 0.f};
 
       for (int t = t0; t < t1; ++t, ++tt) {
         // ---- per-column statistics of this tile -> shared memory, one field per 128-float row
         float* cst = consts + (tt & 1) * (8 * 128);
-        const int jcol = t * kTileN + tid_e;
         if (PHASE != kStats) {
-          const bool ok = jcol < p.B;
-          cst[0 * 128 + tid_e] = (PHASE == kBwd && ok) ? -p.r[jcol] * kL2e : 0.f;                       // -r2_j
-          cst[1 * 128 + tid_e] = ok ? -p.c[jcol] * kL2e : 0.f;                                          // -c2_j
-          cst[2 * 128 + tid_e] = ok ? -p.rz[jcol] * kL2e : 0.f;                                         // -rz2_j
-          cst[3 * 128 + tid_e] = (PHASE == kBwd && ok) ? p.g[jcol] * (2.f * (float)p.B) * kL2e : 0.f;   // gh_j
-          cst[4 * 128 + tid_e] = (PHASE == kBwd && ok) ? p.q[jcol] : 0.f;                               // q_j
+          if (tid_e < 128) {
+            const int jcol = t * kTileN + tid_e;
+            const bool ok = jcol < p.B;
+            cst[1 * 128 + tid_e] = ok ? -p.c[jcol] * kL2e : 0.f;                                        // -c2_j
+            cst[2 * 128 + tid_e] = ok ? -p.rz[jcol] * kL2e : 0.f;                                       // -rz2_j
+            if (PHASE == kBwd) cst[4 * 128 + tid_e] = ok ? p.q[jcol] : 0.f;                             // q_j
+          } else if (PHASE == kBwd) {
+            const int jcol = t * kTileN + tid_e - 128;
+            const bool ok = jcol < p.B;
+            cst[0 * 128 + tid_e - 128] = ok ? -p.r[jcol] * kL2e : 0.f;                                  // -r2_j
+            cst[3 * 128 + tid_e - 128] = ok ? p.g[jcol] * (2.f * (float)p.B) * kL2e : 0.f;              // gh_j
+          }
           named_bar_sync(1, kEpiThreads);
         }
         const bool ragged = (t + 1) * kTileN > p.B;  // last tile of a batch that is not a multiple of 128
@@ -493,17 +557,27 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const uint32_t buf = tt % kNBuf, use = tt / kNBuf;
         mbar_wait(bar(kTmemFull0 + buf), use & 1);
         tc_fence_after();
-        const uint32_t tS = tmem_base + buf * 192 + lane_field, tSt = tS + 64, tZ = tS + 128;
+        const uint32_t tS = tmem_base + buf * 192 + lane_field + 32 * h, tSt = tS + 64, tZ = tS + 128;
+
+        // this thread's 32 columns of the three tiles go to registers at once; the tile buffer is
+        // handed back to the tensor cores before any arithmetic starts
+        float vs[32], vt[32], vz[32];
+        tmem_ld32(tS, vs);
+        if (PHASE != kRowLoss) tmem_ld32(tSt, vt);
+        tmem_ld32(tZ, vz);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive_cluster(bar(kTmemEmpty0 + buf), 0);
 
         if (PHASE == kStats) {
-          auto lse_add32 = [&](float* v, int jl0, float c, float& mx, float& sm) {
+          auto lse_add32 = [&](float* v, float c, float& mx, float& sm) {
             if (ragged) {
 #pragma unroll
               for (int e = 0; e < 32; ++e) if (jl0 + e >= jlim) v[e] = -INFINITY;
             }
             float c4[4] = {fmaxf(v[0], v[4]), fmaxf(v[1], v[5]), fmaxf(v[2], v[6]), fmaxf(v[3], v[7])};
 #pragma unroll
-            for (int e = 8; e < 32; e += 4) {  // four independent chains: the warp has no other ILP
+            for (int e = 8; e < 32; e += 4) {  // four independent chains
 #pragma unroll
               for (int u = 0; u < 4; ++u) c4[u] = fmaxf(c4[u], v[e + u]);
             }
@@ -521,185 +595,146 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             sm = sm * ex2f((mx - mn) * c) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
             mx = mn;
           };
-          // software-pipelined TMEM reads: the load of the next 32 columns is in flight while the
-          // current ones are reduced (one warp per scheduler: nothing else hides the latency)
-          float va[32], vb[32];
-          const int jlA = 32 * n1, jlB = 64 + 32 * n1;
-          tmem_ld32(tS, va);
-          tmem_ld_wait();
-          tmem_ld32(tSt, vb);
-          lse_add32(va, jlA, cS2, mS, sS);
-          tmem_ld_wait();
-          tmem_ld32(tZ, va);
-          lse_add32(vb, jlA, cS2, mSt, sSt);
-          tmem_ld_wait();
-          tmem_ld32(tS + 32, vb);
-          lse_add32(va, jlA, cZ2, mZ, sZ);
-          tmem_ld_wait();
-          tmem_ld32(tSt + 32, va);
-          lse_add32(vb, jlB, cS2, mS, sS);
-          tmem_ld_wait();
-          tmem_ld32(tZ + 32, vb);
-          lse_add32(va, jlB, cS2, mSt, sSt);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive_cluster(bar(kTmemEmpty0 + buf), 0);  // all six reads landed: the MMA may reuse the buffer
-          lse_add32(vb, jlB, cZ2, mZ, sZ);
+          lse_add32(vs, cS2, mS, sS);
+          lse_add32(vt, cS2, mSt, sSt);
+          lse_add32(vz, cZ2, mZ, sZ);
         } else if (PHASE == kRowLoss) {
-          const float m2cS2 = -2.f * cS2;
-          float ag4[4] = {0.f, 0.f, 0.f, 0.f}, aq4[4] = {0.f, 0.f, 0.f, 0.f};
-          auto rowloss32 = [&](float* vs, float* vz, int jl0) {
-            if (ragged) {
+          if (ragged) {
 #pragma unroll
-              for (int e = 0; e < 32; ++e) if (jl0 + e >= jlim) vz[e] = -INFINITY;
-            }
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const float4 nc = *reinterpret_cast<const float4*>(cst + 1 * 128 + jl0 + e);
-              const float4 nrz = *reinterpret_cast<const float4*>(cst + 2 * 128 + jl0 + e);
-              const float ncv[4] = {nc.x, nc.y, nc.z, nc.w}, nrzv[4] = {nrz.x, nrz.y, nrz.z, nrz.w};
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {  // four independent accumulation chains
-                const float z2 = vz[e + u] * cZ2;
-                const float P = ex2f(z2 - rz2_i);
-                const float G = fmaf(vs[e + u], m2cS2, r2_i - ncv[u]);  // 2B G_ij log2(e)
-                ag4[u] = fmaf(P, G, ag4[u]);
-                aq4[u] += ex2f(z2 + nrzv[u]);
-              }
-            }
-          };
-          float vs0[32], vz0[32], vs1[32], vz1[32];
-          tmem_ld32(tS, vs0);
-          tmem_ld32(tZ, vz0);
-          tmem_ld_wait();
-          tmem_ld32(tS + 32, vs1);   // in flight while the first half is reduced
-          tmem_ld32(tZ + 32, vz1);
-          rowloss32(vs0, vz0, 32 * n1);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive_cluster(bar(kTmemEmpty0 + buf), 0);
-          rowloss32(vs1, vz1, 64 + 32 * n1);
-          acc_g += (ag4[0] + ag4[1]) + (ag4[2] + ag4[3]);
-          acc_q += (aq4[0] + aq4[1]) + (aq4[2] + aq4[3]);
-        } else {
-          // ---- gradient sweep: tile -> fp16 weight half-tiles -> tensor cores
-          const float m2cS2 = -2.f * cS2;
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h, ++hh) {
-            const int jl0 = 64 * h + 32 * n1;
-            float vs[32], vt[32], vz[32];
-            tmem_ld32(tS + 32 * h, vs);
-            tmem_ld32(tSt + 32 * h, vt);
-            tmem_ld32(tZ + 32 * h, vz);
-            tmem_ld_wait();
-            if (h == 1) {
-              tc_fence_before();
-              mbar_arrive_cluster(bar(kTmemEmpty0 + buf), 0);
-            }
-            uint32_t wSp[16], wStp[16], wZp[16];
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const float4 f0 = *reinterpret_cast<const float4*>(cst + 0 * 128 + jl0 + e);  // -r2_j
-              const float4 f1 = *reinterpret_cast<const float4*>(cst + 1 * 128 + jl0 + e);  // -c2_j
-              const float4 f2 = *reinterpret_cast<const float4*>(cst + 2 * 128 + jl0 + e);  // -rz2_j
-              const float4 f3 = *reinterpret_cast<const float4*>(cst + 3 * 128 + jl0 + e);  // gh_j
-              const float4 f4 = *reinterpret_cast<const float4*>(cst + 4 * 128 + jl0 + e);  // q_j
-              const float nr[4] = {f0.x, f0.y, f0.z, f0.w}, nc[4] = {f1.x, f1.y, f1.z, f1.w};
-              const float nrz[4] = {f2.x, f2.y, f2.z, f2.w}, gh[4] = {f3.x, f3.y, f3.z, f3.w};
-              const float qj[4] = {f4.x, f4.y, f4.z, f4.w};
-              float ms[4], mst[4], mz[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float a = vs[e + u], bt = vt[e + u];
-                const float z2 = vz[e + u] * cZ2;
-                const float e1 = ex2f(fmaf(a, cS2, -r2_i));     // softmax_row(S)_ij
-                const float e2 = ex2f(fmaf(a, cS2, nc[u]));     // softmax_col(S)_ij
-                const float e3 = ex2f(fmaf(bt, cS2, nr[u]));    // softmax_row(S)_ji
-                const float e4 = ex2f(fmaf(bt, cS2, -c2_i));    // softmax_col(S)_ji
-                const float P = ex2f(z2 - rz2_i), Pt = ex2f(z2 + nrz[u]);
-                const float dS = fmaf(-2.f, P, fmaf(e2, qj[u], e1));    // 2B dS_ij
-                const float dSt = fmaf(-2.f, Pt, fmaf(e4, q_i, e3));    // 2B dS_ji
-                const float G = fmaf(a, m2cS2, r2_i - nc[u]);           // 2B G_ij log2(e)
-                const float Gt = fmaf(bt, m2cS2, c2_i - nr[u]);         // 2B G_ji log2(e)
-                const float dZs = fmaf(P, G - gh_i, Pt * (Gt - gh[u]));
-                ms[u] = dS * wS;
-                mst[u] = dSt * wS;
-                mz[u] = dZs * wZ;
-              }
-#pragma unroll
-              for (int u = 0; u < 4; u += 2) {
-                __half2 x = __floats2half2_rn(ms[u], ms[u + 1]), y = __floats2half2_rn(mst[u], mst[u + 1]);
-                __half2 w = __floats2half2_rn(mz[u], mz[u + 1]);
-                wSp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&x);
-                wStp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&y);
-                wZp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&w);
-              }
-            }
-            // the previous half's gradient MMAs must have drained the weight buffers
-            mbar_wait(bar(kGradDone), (hh & 1) ^ 1);
-            // row m of a 64 x 64 fp16 tile (128 B rows, SWIZZLE_128B): this thread owns K = 32 n1 .. +31
-            uint8_t* wrow = sbase + kOffW + m * 128;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int chunk = ((4 * n1 + k) ^ (m & 7)) * 16;
-              *reinterpret_cast<uint4*>(wrow + chunk) = make_uint4(wSp[4 * k], wSp[4 * k + 1], wSp[4 * k + 2], wSp[4 * k + 3]);
-              *reinterpret_cast<uint4*>(wrow + kChunkBytes + chunk) =
-                  make_uint4(wStp[4 * k], wStp[4 * k + 1], wStp[4 * k + 2], wStp[4 * k + 3]);
-              *reinterpret_cast<uint4*>(wrow + 2 * kChunkBytes + chunk) =
-                  make_uint4(wZp[4 * k], wZp[4 * k + 1], wZp[4 * k + 2], wZp[4 * k + 3]);
-            }
-            fence_proxy_async_smem();
-            mbar_arrive_cluster(bar(kWFull), 0);
+            for (int e = 0; e < 32; ++e) if (jl0 + e >= jlim) vz[e] = -INFINITY;
           }
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 nc = *reinterpret_cast<const float4*>(cst + 1 * 128 + jl0 + e);
+            const float4 nrz = *reinterpret_cast<const float4*>(cst + 2 * 128 + jl0 + e);
+            const float ncv[4] = {nc.x, nc.y, nc.z, nc.w}, nrzv[4] = {nrz.x, nrz.y, nrz.z, nrz.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // four independent accumulation chains
+              const float z2 = vz[e + u] * cZ2;
+              const float P = ex2f(z2 - rz2_i);
+              const float G = fmaf(vs[e + u], m2cS2, r2_i - ncv[u]);  // 2B G_ij log2(e)
+              ag4[u] = fmaf(P, G, ag4[u]);
+              aq4[u] += ex2f(z2 + nrzv[u]);
+            }
+          }
+        } else {
+          // ---- gradient sweep: tile -> fp16 weight half-tile h -> tensor cores
+          uint32_t wSp[16], wStp[16], wZp[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 f0 = *reinterpret_cast<const float4*>(cst + 0 * 128 + jl0 + e);  // -r2_j
+            const float4 f1 = *reinterpret_cast<const float4*>(cst + 1 * 128 + jl0 + e);  // -c2_j
+            const float4 f2 = *reinterpret_cast<const float4*>(cst + 2 * 128 + jl0 + e);  // -rz2_j
+            const float4 f3 = *reinterpret_cast<const float4*>(cst + 3 * 128 + jl0 + e);  // gh_j
+            const float4 f4 = *reinterpret_cast<const float4*>(cst + 4 * 128 + jl0 + e);  // q_j
+            const float nr[4] = {f0.x, f0.y, f0.z, f0.w}, nc[4] = {f1.x, f1.y, f1.z, f1.w};
+            const float nrz[4] = {f2.x, f2.y, f2.z, f2.w}, gh[4] = {f3.x, f3.y, f3.z, f3.w};
+            const float qj[4] = {f4.x, f4.y, f4.z, f4.w};
+            float ms[4], mst[4], mz[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float a = vs[e + u], bt = vt[e + u];
+              const float z2 = vz[e + u] * cZ2;
+              const float e1 = ex2f(fmaf(a, cS2, -r2_i));     // softmax_row(S)_ij
+              const float e2 = ex2f(fmaf(a, cS2, nc[u]));     // softmax_col(S)_ij
+              const float e3 = ex2f(fmaf(bt, cS2, nr[u]));    // softmax_row(S)_ji
+              const float e4 = ex2f(fmaf(bt, cS2, -c2_i));    // softmax_col(S)_ji
+              const float P = ex2f(z2 - rz2_i), Pt = ex2f(z2 + nrz[u]);
+              const float dS = fmaf(-2.f, P, fmaf(e2, qj[u], e1));    // 2B dS_ij
+              const float dSt = fmaf(-2.f, Pt, fmaf(e4, q_i, e3));    // 2B dS_ji
+              const float G = fmaf(a, m2cS2, r2_i - nc[u]);           // 2B G_ij log2(e)
+              const float Gt = fmaf(bt, m2cS2, c2_i - nr[u]);         // 2B G_ji log2(e)
+              const float dZs = fmaf(P, G - gh_i, Pt * (Gt - gh[u]));
+              ms[u] = dS * wS;
+              mst[u] = dSt * wS;
+              mz[u] = dZs * wZ;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u += 2) {
+              __half2 x = __floats2half2_rn(ms[u], ms[u + 1]), y = __floats2half2_rn(mst[u], mst[u + 1]);
+              __half2 w = __floats2half2_rn(mz[u], mz[u + 1]);
+              wSp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&x);
+              wStp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&y);
+              wZp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&w);
+            }
+          }
+          // The single weight buffer is used by column half 0, then half 1, of every tile: wait until
+          // the gradient MMAs of the preceding half have drained it.  One barrier per half keeps every
+          // waiter at most one phase behind, which the parity test needs.
+          if (h == 0) mbar_wait(bar(kGradDone1), (tt & 1) ^ 1);  // half 1 of the previous tile consumed
+          else mbar_wait(bar(kGradDone), tt & 1);                // half 0 of this tile consumed
+          // row m of a 64 x 64 fp16 tile (128 B rows, SWIZZLE_128B): this thread owns K = 32 n1 .. +31
+          uint8_t* wrow = sbase + kOffW + m * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int chunk = ((4 * n1 + k) ^ (m & 7)) * 16;
+            *reinterpret_cast<uint4*>(wrow + chunk) = make_uint4(wSp[4 * k], wSp[4 * k + 1], wSp[4 * k + 2], wSp[4 * k + 3]);
+            *reinterpret_cast<uint4*>(wrow + kChunkBytes + chunk) =
+                make_uint4(wStp[4 * k], wStp[4 * k + 1], wStp[4 * k + 2], wStp[4 * k + 3]);
+            *reinterpret_cast<uint4*>(wrow + 2 * kChunkBytes + chunk) =
+                make_uint4(wZp[4 * k], wZp[4 * k + 1], wZp[4 * k + 2], wZp[4 * k + 3]);
+          }
+          fence_proxy_async_smem();
+          mbar_arrive_cluster(bar(kWFull), 0);
         }
       }
 
       // ---- end of job: write this job's partial results
       if (PHASE == kStats || PHASE == kRowLoss) {
-        float* scratch = reinterpret_cast<float*>(sbase + kOffW);  // [6][64]
-        // log2-domain (max, sum) pairs
-        OnlineLse2 lS, lSt, lZ;
+        // four threads hold pieces of row m (lane half n1 x column half h): combine through shared memory
+        float* scratch = reinterpret_cast<float*>(sbase + kOffW);  // [3 partners][6][64]
+        OnlineLse2 lS, lSt, lZ;  // log2-domain (max, sum) pairs
         lS.m = mS * cS2; lS.s = sS; lSt.m = mSt * cS2; lSt.s = sSt; lZ.m = mZ * cZ2; lZ.s = sZ;
+        const float acc_g = (ag4[0] + ag4[1]) + (ag4[2] + ag4[3]), acc_q = (aq4[0] + aq4[1]) + (aq4[2] + aq4[3]);
+        const int part = 2 * h + n1;  // 0 = the row's writer
         named_bar_sync(2, kEpiThreads);
-        if (n1 == 1) {
+        if (part != 0) {
+          float* sc = scratch + (part - 1) * 6 * 64;
           if (PHASE == kStats) {
-            scratch[0 * 64 + m] = lS.m; scratch[1 * 64 + m] = lS.s;
-            scratch[2 * 64 + m] = lSt.m; scratch[3 * 64 + m] = lSt.s;
-            scratch[4 * 64 + m] = lZ.m; scratch[5 * 64 + m] = lZ.s;
+            sc[0 * 64 + m] = lS.m; sc[1 * 64 + m] = lS.s;
+            sc[2 * 64 + m] = lSt.m; sc[3 * 64 + m] = lSt.s;
+            sc[4 * 64 + m] = lZ.m; sc[5 * 64 + m] = lZ.s;
           } else {
-            scratch[0 * 64 + m] = acc_g; scratch[1 * 64 + m] = acc_q;
+            sc[0 * 64 + m] = acc_g; sc[1 * 64 + m] = acc_q;
           }
         }
         named_bar_sync(2, kEpiThreads);
-        if (n1 == 0) {
+        if (part == 0) {
           if (PHASE == kStats) {
-            lS.merge(scratch[0 * 64 + m], scratch[1 * 64 + m]);
-            lSt.merge(scratch[2 * 64 + m], scratch[3 * 64 + m]);
-            lZ.merge(scratch[4 * 64 + m], scratch[5 * 64 + m]);
+            for (int k = 0; k < 3; ++k) {
+              const float* sc = scratch + k * 6 * 64;
+              lS.merge(sc[0 * 64 + m], sc[1 * 64 + m]);
+              lSt.merge(sc[2 * 64 + m], sc[3 * 64 + m]);
+              lZ.merge(sc[4 * 64 + m], sc[5 * 64 + m]);
+            }
             float2* out = reinterpret_cast<float2*>(p.part);
             const size_t o = (size_t)sp * 3 * p.bpad + lrow;
             out[o] = make_float2(lS.m, lS.s);
             out[o + p.bpad] = make_float2(lSt.m, lSt.s);
             out[o + 2 * (size_t)p.bpad] = make_float2(lZ.m, lZ.s);
           } else {
+            float g = acc_g, q = acc_q;
+            for (int k = 0; k < 3; ++k) { g += scratch[k * 6 * 64 + m]; q += scratch[k * 6 * 64 + 64 + m]; }
             const size_t o = (size_t)sp * 2 * p.bpad + lrow;
-            p.part[o] = (acc_g + scratch[0 * 64 + m]) * kLn2;   // back from log2 units: 2B g_i
-            p.part[o + p.bpad] = acc_q + scratch[1 * 64 + m];
+            p.part[o] = g * kLn2;   // back from log2 units: 2B g_i
+            p.part[o + p.bpad] = q;
           }
         }
       } else {
+        // accumulators: lanes 0-63 hold d in [0, D/2), lanes 64-127 hold [D/2, D); this thread reads the
+        // column half h of its lane's D/2 columns
         mbar_wait(bar(kAccFull), jj & 1);
         tc_fence_after();
-        const int half_d = D / 2;
-        float* out_t = p.part + ((size_t)sp * 2 * p.bpad + lrow) * D + n1 * half_d;
+        const int half_d = D / 2, quart_d = D / 4;
+        float* out_t = p.part + ((size_t)sp * 2 * p.bpad + lrow) * D + n1 * half_d + h * quart_d;
         float* out_i = out_t + (size_t)p.bpad * D;
-        for (int c0 = 0; c0 < half_d; c0 += 32) {
+        for (int c0 = 0; c0 < quart_d; c0 += 32) {
           float v[32];
-          tmem_ld32(tmem_base + lane_field + kAccCol + c0, v);
+          tmem_ld32(tmem_base + lane_field + kAccCol + h * quart_d + c0, v);
           tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(out_t + c0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-          tmem_ld32(tmem_base + lane_field + kAccCol + half_d + c0, v);
+          tmem_ld32(tmem_base + lane_field + kAccCol + half_d + h * quart_d + c0, v);
           tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(out_i + c0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
@@ -897,7 +932,7 @@ static float* wscale_slot(void* ws, int b, int B, int D) {
 
 int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row_offset, int /*mode*/,
             void* planes_all, cudaStream_t st) {
-  MC_REQUIRE(supported(D), MC_ERR_UNSUPPORTED, "tcgen05 engine needs D in {64,128,192,256} (got %d)", D);
+  MC_REQUIRE(supported(D), MC_ERR_UNSUPPORTED, "tcgen05 engine needs D in {128, 256} (got %d)", D);
   MC_REQUIRE(b == B && row_offset == 0, MC_ERR_UNSUPPORTED,
              "tcgen05 engine stages all B rows in one call (the scale is global): got b=%d B=%d row_offset=%d", b, B,
              row_offset);
@@ -929,7 +964,7 @@ int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row
 template <int PHASE, int PASSES>
 static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, float* part, const float* wscale,
                        cudaStream_t st) {
-  MC_REQUIRE(supported(p.D), MC_ERR_UNSUPPORTED, "tcgen05 engine needs D in {64,128,192,256} (got %d)", p.D);
+  MC_REQUIRE(supported(p.D), MC_ERR_UNSUPPORTED, "tcgen05 engine needs D in {128, 256} (got %d)", p.D);
   MC_REQUIRE(p.row_offset % 128 == 0, MC_ERR_UNSUPPORTED, "tcgen05 engine needs row_offset %% 128 == 0 (got %d)",
              p.row_offset);
   MC_REQUIRE(p.planes_all != nullptr && aligned(p.planes_all, 256), MC_ERR_BAD_ARG,

@@ -48,14 +48,18 @@ __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
       : "memory");
 }
+// Default (.acquire.cta) semantics on purpose: a cluster-scope acquire makes ptxas emit CCTL.IVALL (an L1
+// invalidate) after every successful wait, which costs the issuing warp hundreds of cycles per ring slot.
+// What the waits order here travels through the async proxy (TMA bytes, tcgen05.commit) or is fenced by
+// the writer (fence.proxy.async / tcgen05.fence) before its arrive.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
