@@ -377,6 +377,16 @@ def run_b200(args):
         flops_bwd = 8.0 * B * B * D_EMB / world            # the gradient sweep: 4 GEMMs
         achieved = flops_bwd / (bwd_ms * 1e-3) / 1e12
         peak = peaks["tc_sustained"] or peaks["tc_burst"]
+        # executed tensor-core work of the gradient sweep: 4 recomputed GEMM units (S, S^T, Z with K = 2D) x passes
+        # + 4 gradient GEMM units, each 2 B^2 D / world FLOPs; the algorithmic count is the 4 gradient GEMMs
+        passes = 3 if mode == "tc_f16x3" else 1
+        exec_units = (4 * passes + 4) if mode != "simt_fp32" else 8
+        executed = exec_units * 2.0 * B * B * D_EMB / world / (bwd_ms * 1e-3) / 1e12
+        ncu = {}
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_roofline_ncu.json")))
+        except Exception:
+            pass
         line = {
             "metric": "contrastive loss fwd+bwd samples/s", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -392,7 +402,10 @@ def run_b200(args):
                           "rowloss": phase_ms[2] / args.steps, "bwd": bwd_ms},
             "roofline": {"bound": "tensor", "kernel": "gradient sweep (mc_clip_bwd)", "achieved": achieved,
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_source": peaks["source"] + ", bf16 sustained", "traffic": None,
+                         "peak_source": peaks["source"] + ", bf16 sustained (fp16 runs at the same tensor rate)",
+                         "traffic": ncu.get("traffic_bytes_per_launch") if (mode == "tc_f16x3" and world == 1 and B == 32768) else None,
+                         "executed_tflops": executed, "executed_frac": executed / peak,
+                         "ncu_tensor_pipe_active_pct": ncu.get("tensor_pipe_active_pct"), "ncu_source": ncu.get("source"),
                          "algorithmic_flops_per_launch": flops_bwd,
                          "step_achieved": flops_step / (ms_per_step * 1e-3) / 1e12,
                          "step_frac": flops_step / (ms_per_step * 1e-3) / 1e12 / peak},

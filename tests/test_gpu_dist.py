@@ -1,0 +1,58 @@
+"""Global-batch contrastive loss over NCCL (SURVEY.md section 8 e): world_size 2 on two B200s.
+The sharded loss / gradients must equal the single-GPU loss on the concatenated batch and the CPU
+oracle.  Skipped when fewer than two GPUs are visible."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import rel_err
+from oracle import loss_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, b, mode, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from mae_clip_b200.dist import global_clip_loss
+        I = loss_ref.make_embeddings(b, 256, seed=1000 + rank, scale=0.15).cuda().requires_grad_(True)
+        T = loss_ref.make_embeddings(b, 256, seed=2000 + rank, scale=0.15).cuda().requires_grad_(True)
+        loss = global_clip_loss(I, T, 1.0, mode=mode)
+        (loss * 2.0).backward()
+        ret[rank] = (loss.detach().cpu(), I.grad.cpu(), T.grad.cpu())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["simt_fp32", "tc_f16x3"])
+def test_global_loss_two_gpus(mode):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world, b = 2, 384
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), b, mode, ret), nprocs=world, join=True)
+    I = torch.cat([loss_ref.make_embeddings(b, 256, seed=1000 + r, scale=0.15) for r in range(world)])
+    T = torch.cat([loss_ref.make_embeddings(b, 256, seed=2000 + r, scale=0.15) for r in range(world)])
+    ref_loss, ref_dI, ref_dT, _ = loss_ref.clip_loss_closed_form(I.numpy(), T.numpy(), 1.0, grad_loss=2.0)
+    for r in range(world):
+        loss, dI, dT = ret[r]
+        assert abs(loss.item() - ref_loss) < 1e-4 * abs(ref_loss)
+        assert rel_err(dI, ref_dI[r * b:(r + 1) * b]) < 1e-3
+        assert rel_err(dT, ref_dT[r * b:(r + 1) * b]) < 1e-3
