@@ -153,8 +153,75 @@ __device__ __forceinline__ void patch_stats(const float* base, const PatchGeom& 
   rstd = rsqrtf(warp_sum(v) / (float)(g.PE - 1) + 1e-6f);
 }
 
-template <typename PT>
-__global__ void __launch_bounds__(256) masked_mse_fwd_kernel(const PT* __restrict__ pred,
+
+// ---- p = 16 fast path -------------------------------------------------------------------------
+// A 16 x 16 x 3 patch is 48 image rows of 64 contiguous bytes.  The warp reads them with 16-byte
+// loads (4 lanes per row, 8 rows per instruction), keeps them in registers for the mean / variance,
+// and parks the target in a per-warp shared-memory tile [c][pixel] (plane stride 268 floats: the
+// (e % 3, e / 3) read pattern of `pred` order is then bank-conflict free).  `pred` / `dpred` move as
+// 16-byte (fp32) or 8-byte (bf16) vectors, four consecutive elements per lane.
+constexpr int kPlane16 = 268;
+constexpr int kTile16 = 3 * kPlane16;
+
+__device__ __forceinline__ void stage_patch16(const float* __restrict__ base, int H, int W, int lane,
+                                              int norm_pix, float* __restrict__ tile) {
+  float4 v[6];
+  float s = 0.f;
+  const int quad = lane & 3;
+#pragma unroll
+  for (int it = 0; it < 6; ++it) {
+    const int row = it * 8 + (lane >> 2), c = row >> 4, ph = row & 15;
+    v[it] = ld_stream(reinterpret_cast<const float4*>(base + ((size_t)c * H + ph) * W + quad * 4));
+    s += (v[it].x + v[it].y) + (v[it].z + v[it].w);
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (norm_pix) {
+    mean = warp_sum(s) * (1.f / 768.f);
+    float q = 0.f;
+#pragma unroll
+    for (int it = 0; it < 6; ++it) {
+      const float a = v[it].x - mean, b = v[it].y - mean, c2 = v[it].z - mean, d = v[it].w - mean;
+      q += (a * a + b * b) + (c2 * c2 + d * d);
+    }
+    rstd = rsqrtf(warp_sum(q) * (1.f / 767.f) + 1e-6f);
+  }
+  __syncwarp();  // the previous patch's readers are done with the tile
+#pragma unroll
+  for (int it = 0; it < 6; ++it) {
+    const int row = it * 8 + (lane >> 2), c = row >> 4, ph = row & 15;
+    float4 t;
+    t.x = (v[it].x - mean) * rstd; t.y = (v[it].y - mean) * rstd;
+    t.z = (v[it].z - mean) * rstd; t.w = (v[it].w - mean) * rstd;
+    *reinterpret_cast<float4*>(tile + c * kPlane16 + ph * 16 + quad * 4) = t;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ float tile16_at(const float* tile, int e) {  // e = (ph*16 + pw)*3 + c
+  const int pix = e / 3, c = e - 3 * pix;
+  return tile[c * kPlane16 + pix];
+}
+__device__ __forceinline__ float4 ld_pred4(const float* p, size_t i) {
+  return ld_stream(reinterpret_cast<const float4*>(p + i));
+}
+__device__ __forceinline__ float4 ld_pred4(const __nv_bfloat16* p, size_t i) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p + i);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+__device__ __forceinline__ void st_pred4(float* p, size_t i, float4 v) {
+  st_stream(reinterpret_cast<float4*>(p + i), v);
+}
+__device__ __forceinline__ void st_pred4(__nv_bfloat16* p, size_t i, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p + i) = u;
+}
+
+template <typename PT, bool FAST16>
+__global__ void __launch_bounds__(256, 4) masked_mse_fwd_kernel(const PT* __restrict__ pred,
                                                              const float* __restrict__ imgs,
                                                              const float* __restrict__ mask,
                                                              long long patches, PatchGeom g,
@@ -164,6 +231,7 @@ __global__ void __launch_bounds__(256) masked_mse_fwd_kernel(const PT* __restric
                                                              float* __restrict__ mask_sum_out) {
   __shared__ float sm_l[8], sm_m[8];
   __shared__ bool is_last;
+  __shared__ __align__(16) float tiles[FAST16 ? 8 * kTile16 : 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   float acc = 0.f, macc = 0.f;
@@ -174,14 +242,27 @@ __global__ void __launch_bounds__(256) masked_mse_fwd_kernel(const PT* __restric
     const long long n = pt / g.L;
     const int l = (int)(pt % g.L);
     const float* base = patch_base(imgs, g, n, l);
-    float mean, rstd;
-    patch_stats(base, g, lane, norm_pix, mean, rstd);
     float se = 0.f;
     const size_t poff = (size_t)pt * g.PE;
-    for (int e = lane; e < g.PE; e += 32) {
-      float t = (base[elem_off(g, e)] - mean) * rstd;
-      float d = ld_pred(pred, poff + e) - t;
-      se = fmaf(d, d, se);
+    if (FAST16) {
+      float* tile = tiles + warp * kTile16;
+      stage_patch16(base, g.H, g.W, lane, norm_pix, tile);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int e0 = 4 * lane + 128 * k;
+        const float4 pv = ld_pred4(pred, poff + e0);
+        const float d0 = pv.x - tile16_at(tile, e0), d1 = pv.y - tile16_at(tile, e0 + 1);
+        const float d2 = pv.z - tile16_at(tile, e0 + 2), d3 = pv.w - tile16_at(tile, e0 + 3);
+        se += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+      }
+    } else {
+      float mean, rstd;
+      patch_stats(base, g, lane, norm_pix, mean, rstd);
+      for (int e = lane; e < g.PE; e += 32) {
+        float t = (base[elem_off(g, e)] - mean) * rstd;
+        float d = ld_pred(pred, poff + e) - t;
+        se = fmaf(d, d, se);
+      }
     }
     se = warp_sum(se);
     acc += m * se / (float)g.PE;
@@ -221,8 +302,8 @@ __global__ void __launch_bounds__(256) masked_mse_fwd_kernel(const PT* __restric
   }
 }
 
-template <typename PT>
-__global__ void __launch_bounds__(256) masked_mse_bwd_kernel(const PT* __restrict__ pred,
+template <typename PT, bool FAST16>
+__global__ void __launch_bounds__(256, 4) masked_mse_bwd_kernel(const PT* __restrict__ pred,
                                                              const float* __restrict__ imgs,
                                                              const float* __restrict__ mask,
                                                              long long patches, PatchGeom g,
@@ -230,7 +311,8 @@ __global__ void __launch_bounds__(256) masked_mse_bwd_kernel(const PT* __restric
                                                              const float* __restrict__ mask_sum,
                                                              const float* __restrict__ grad_loss,
                                                              PT* __restrict__ dpred) {
-  const int lane = threadIdx.x & 31;
+  __shared__ __align__(16) float tiles[FAST16 ? 8 * kTile16 : 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const float gl = grad_loss ? *grad_loss : 1.f;
   const float coef = 2.f * gl / ((float)g.PE * (*mask_sum));
@@ -239,18 +321,37 @@ __global__ void __launch_bounds__(256) masked_mse_bwd_kernel(const PT* __restric
     const float m = mask[pt];
     const size_t poff = (size_t)pt * g.PE;
     if (m == 0.f) {
-      for (int e = lane; e < g.PE; e += 32) st_pred(dpred, poff + e, 0.f);
+      if (FAST16) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) st_pred4(dpred, poff + 4 * lane + 128 * k, make_float4(0.f, 0.f, 0.f, 0.f));
+      } else {
+        for (int e = lane; e < g.PE; e += 32) st_pred(dpred, poff + e, 0.f);
+      }
       continue;
     }
     const long long n = pt / g.L;
     const int l = (int)(pt % g.L);
     const float* base = patch_base(imgs, g, n, l);
-    float mean, rstd;
-    patch_stats(base, g, lane, norm_pix, mean, rstd);
     const float cm = coef * m;
-    for (int e = lane; e < g.PE; e += 32) {
-      float t = (base[elem_off(g, e)] - mean) * rstd;
-      st_pred(dpred, poff + e, cm * (ld_pred(pred, poff + e) - t));
+    if (FAST16) {
+      float* tile = tiles + warp * kTile16;
+      stage_patch16(base, g.H, g.W, lane, norm_pix, tile);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int e0 = 4 * lane + 128 * k;
+        const float4 pv = ld_pred4(pred, poff + e0);
+        float4 o;
+        o.x = cm * (pv.x - tile16_at(tile, e0)); o.y = cm * (pv.y - tile16_at(tile, e0 + 1));
+        o.z = cm * (pv.z - tile16_at(tile, e0 + 2)); o.w = cm * (pv.w - tile16_at(tile, e0 + 3));
+        st_pred4(dpred, poff + e0, o);
+      }
+    } else {
+      float mean, rstd;
+      patch_stats(base, g, lane, norm_pix, mean, rstd);
+      for (int e = lane; e < g.PE; e += 32) {
+        float t = (base[elem_off(g, e)] - mean) * rstd;
+        st_pred(dpred, poff + e, cm * (ld_pred(pred, poff + e) - t));
+      }
     }
   }
 }
@@ -373,14 +474,13 @@ int mc_masked_mse_fwd(const void* pred, int pred_elem_size, const float* imgs, c
   unsigned int* counter = static_cast<unsigned int*>(ws);
   float* part = reinterpret_cast<float*>(static_cast<char*>(ws) + 256);
   MC_CUDA(cudaMemsetAsync(counter, 0, 4, st));
-  if (pred_elem_size == 4)
-    masked_mse_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)pred, imgs, mask, patches, g,
-                                                       norm_pix, part, counter, loss_out,
-                                                       mask_sum_out);
-  else
-    masked_mse_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)pred, imgs, mask,
-                                                               patches, g, norm_pix, part, counter,
-                                                               loss_out, mask_sum_out);
+  const bool fast = p == 16 && W % 4 == 0 && aligned(imgs, 16) && aligned(pred, 16);
+#define MC_MSE_FWD(PT, F)                                                                              \
+  masked_mse_fwd_kernel<PT, F><<<grid, 256, 0, st>>>((const PT*)pred, imgs, mask, patches, g, norm_pix, \
+                                                     part, counter, loss_out, mask_sum_out)
+  if (pred_elem_size == 4) { if (fast) MC_MSE_FWD(float, true); else MC_MSE_FWD(float, false); }
+  else { if (fast) MC_MSE_FWD(__nv_bfloat16, true); else MC_MSE_FWD(__nv_bfloat16, false); }
+#undef MC_MSE_FWD
   MC_LAUNCH_CHECK();
   return MC_OK;
 }
@@ -398,13 +498,13 @@ int mc_masked_mse_bwd(const void* pred, int pred_elem_size, const float* imgs, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long patches = (long long)N * g.L;
   const int grid = mse_grid(patches);
-  if (pred_elem_size == 4)
-    masked_mse_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)pred, imgs, mask, patches, g,
-                                                       norm_pix, mask_sum, grad_loss, (float*)dpred);
-  else
-    masked_mse_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
-        (const __nv_bfloat16*)pred, imgs, mask, patches, g, norm_pix, mask_sum, grad_loss,
-        (__nv_bfloat16*)dpred);
+  const bool fast = p == 16 && W % 4 == 0 && aligned(imgs, 16) && aligned(pred, 16) && aligned(dpred, 16);
+#define MC_MSE_BWD(PT, F)                                                                              \
+  masked_mse_bwd_kernel<PT, F><<<grid, 256, 0, st>>>((const PT*)pred, imgs, mask, patches, g, norm_pix, \
+                                                     mask_sum, grad_loss, (PT*)dpred)
+  if (pred_elem_size == 4) { if (fast) MC_MSE_BWD(float, true); else MC_MSE_BWD(float, false); }
+  else { if (fast) MC_MSE_BWD(__nv_bfloat16, true); else MC_MSE_BWD(__nv_bfloat16, false); }
+#undef MC_MSE_BWD
   MC_LAUNCH_CHECK();
   return MC_OK;
 }
