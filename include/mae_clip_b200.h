@@ -153,6 +153,13 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
                      float* dx, float* dw_proj, float* db_proj, float* dw_fc, float* db_fc,
                      float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
 
+/* fp32-class tensor-core GEMM the heads are built from (exposed for tests and reuse):
+ * C[M,N] = A[M,K] . B[N,K]^T (+ bias[n]); A, B, C dense row-major fp32; gelu_out (optional) =
+ * gelu(C), exact erf form.  Operands are staged as fp16 hi/lo planes inside `ws`. */
+size_t mc_tc_gemm_workspace_bytes(int M, int N, int K);
+int mc_tc_gemm(const float* A, const float* B, int M, int N, int K, const float* bias, float* C,
+               float* gelu_out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------
  * M1  MAE per-sample random masking        (NOT in the reference: north_star; oracle/mae_ref.py)
  * noise (N,L) fp32; stable ascending argsort (ties -> lower index).  Outputs:

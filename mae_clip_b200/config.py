@@ -21,4 +21,4 @@ projection_dim = 256
 dropout = 0.1
 
 # engine of the contrastive-loss / projection GEMMs: "simt_fp32", "tc_f16x3" or "tc_f16"
-gemm_mode = "simt_fp32"
+gemm_mode = "tc_f16x3"

@@ -1,0 +1,402 @@
+// fp32-class tcgen05 GEMM for the ProjectionHead: see gemm_tc.cuh.  One CTA per 128 x 128 output
+// tile (cta_group::1, M = 128, N = 128), persistent over (tile, K-split) jobs:
+//   warp 0  TMA producer: per 64-wide K chunk the hi and lo planes of the A and B row blocks (4 x 16 KB)
+//   warp 1  MMA issuer (one elected lane) + TMEM allocator: hi*hi + hi*lo + lo*hi into an fp32 TMEM tile
+//   warps 2-5  epilogue: tcgen05.ld -> scale (+ bias, + exact-erf GELU second output) -> global
+// Two TMEM tile buffers overlap the epilogue of one job with the MMAs of the next.
+#include "gemm_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace mc {
+namespace tcg {
+
+using namespace ptx;
+
+constexpr int kChunk = 128 * 128;       // 128 rows x 64 fp16 (128 bytes per row)
+constexpr int kStage = 4 * kChunk;      // A hi, A lo, B hi, B lo
+constexpr int kStages = 3;
+constexpr int kOffBar = kStages * kStage;
+constexpr int kSmem = kOffBar + 256 + 1024;
+constexpr int kThreads = 192;
+enum Bar { kFull0 = 0, kEmpty0 = 3, kTFull0 = 6, kTEmpty0 = 8, kNumBars = 10 };
+
+struct GemmParams {
+  int M, N, K;
+  int tiles_m, tiles_n, ksplit, chunks_per_split, chunks_total;
+  const float* scale_a;  // {s, 1/s}
+  const float* scale_b;
+  float* C;              // direct output (ksplit == 1) or partials (ksplit x M x N)
+  int64_t ldc;
+  const float* bias;
+  float* gelu_out;
+  int vec_ok;            // 16-byte stores allowed
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+            const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* const sbase = smem_raw + (base - raw);
+  const uint32_t bar0 = base + kOffBar;
+  auto bar = [&](int i) -> uint32_t { return bar0 + 8u * i; };
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(sbase + kOffBar + 8 * kNumBars);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int njobs = p.tiles_m * p.tiles_n * p.ksplit;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kFull0 + s), 1); mbar_init(bar(kEmpty0 + s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(kTFull0 + i), 1); mbar_init(bar(kTEmpty0 + i), 128); }
+    fence_mbar_init();
+    prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_b_hi); prefetch_tmap(&map_b_lo);
+  }
+  if (warp == 1) tmem_alloc_1cta(smem_u32(tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto job_coords = [&](int job, int& tm, int& tn, int& c0, int& c1) {
+    const int tile = job % (p.tiles_m * p.tiles_n), ks = job / (p.tiles_m * p.tiles_n);
+    tm = tile % p.tiles_m;
+    tn = tile / p.tiles_m;
+    c0 = ks * p.chunks_per_split;
+    c1 = min(c0 + p.chunks_per_split, p.chunks_total);
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+        int tm, tn, c0, c1;
+        job_coords(job, tm, tn, c0, c1);
+        for (int c = c0; c < c1; ++c, ++it) {
+          const uint32_t stage = it % kStages, par = (it / kStages) & 1;
+          mbar_wait(bar(kEmpty0 + stage), par ^ 1);
+          const uint32_t fb = bar(kFull0 + stage);
+          mbar_arrive_expect_tx(fb, kStage);
+          const uint32_t sb = base + stage * kStage;
+          tma_load_2d(sb, &map_a_hi, fb, c * 64, tm * 128);
+          tma_load_2d(sb + kChunk, &map_a_lo, fb, c * 64, tm * 128);
+          tma_load_2d(sb + 2 * kChunk, &map_b_hi, fb, c * 64, tn * 128);
+          tma_load_2d(sb + 3 * kChunk, &map_b_lo, fb, c * 64, tn * 128);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = idesc_f16(128, 128);
+      uint32_t it = 0, tt = 0;
+      for (int job = blockIdx.x; job < njobs; job += gridDim.x, ++tt) {
+        int tm, tn, c0, c1;
+        job_coords(job, tm, tn, c0, c1);
+        const uint32_t buf = tt & 1, use = tt >> 1;
+        mbar_wait(bar(kTEmpty0 + buf), (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t td = tmem_base + buf * 128;
+        for (int c = c0; c < c1; ++c, ++it) {
+          const uint32_t stage = it % kStages, par = (it / kStages) & 1;
+          mbar_wait(bar(kFull0 + stage), par);
+          tc_fence_after();
+          const uint32_t sb = base + stage * kStage;
+          const uint64_t ah = smem_desc_sw128(sb), al = smem_desc_sw128(sb + kChunk);
+          const uint64_t bh = smem_desc_sw128(sb + 2 * kChunk), bl = smem_desc_sw128(sb + 3 * kChunk);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t acc = (c > c0 || ks > 0) ? 1u : 0u;
+            mma_f16_1cta(td, desc_advance_k(ah, ks), desc_advance_k(bh, ks), idesc, acc);
+            mma_f16_1cta(td, desc_advance_k(ah, ks), desc_advance_k(bl, ks), idesc, 1u);
+            mma_f16_1cta(td, desc_advance_k(al, ks), desc_advance_k(bh, ks), idesc, 1u);
+          }
+          mma_commit_1cta(bar(kEmpty0 + stage));
+        }
+        mma_commit_1cta(bar(kTFull0 + buf));
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const uint32_t lane_field = (uint32_t)(quarter * 32) << 16;
+    const float scale = p.scale_a[1] * p.scale_b[1];
+    uint32_t tt = 0;
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x, ++tt) {
+      int tm, tn, c0, c1;
+      job_coords(job, tm, tn, c0, c1);
+      const int ks = job / (p.tiles_m * p.tiles_n);
+      const uint32_t buf = tt & 1, use = tt >> 1;
+      mbar_wait(bar(kTFull0 + buf), use & 1);
+      tc_fence_after();
+      const int row = tm * 128 + quarter * 32 + lane;
+      const bool split = p.ksplit > 1;
+      float* crow = split ? p.C + ((size_t)ks * p.M + row) * p.N : p.C + (size_t)row * p.ldc;
+      float* grow = (EPI == kEpiGelu && p.gelu_out) ? p.gelu_out + (size_t)row * p.ldc : nullptr;
+#pragma unroll 1
+      for (int cc = 0; cc < 128; cc += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + lane_field + buf * 128 + cc, v);
+        tmem_ld_wait();
+        if (cc == 96) {  // all four reads of this tile are done: release the buffer
+          tc_fence_before();
+          mbar_arrive_local(bar(kTEmpty0 + buf));
+        }
+        const int col0 = tn * 128 + cc;
+        if (row >= p.M || col0 >= p.N) continue;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          v[e] *= scale;
+          if (!split && p.bias && col0 + e < p.N) v[e] += p.bias[col0 + e];
+        }
+        if (p.vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            *reinterpret_cast<float4*>(crow + col0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+            if (EPI == kEpiGelu && grow)
+              *reinterpret_cast<float4*>(grow + col0 + e) =
+                  make_float4(gelu_erf(v[e]), gelu_erf(v[e + 1]), gelu_erf(v[e + 2]), gelu_erf(v[e + 3]));
+          }
+        } else {
+          for (int e = 0; e < 32; ++e) {
+            if (col0 + e < p.N) {
+              crow[col0 + e] = v[e];
+              if (EPI == kEpiGelu && grow) grow[col0 + e] = gelu_erf(v[e]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc_1cta(tmem_base, 256);
+}
+
+// C[m][n] = sum_ks part[ks][m][n] (+ bias[n])
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int ksplit, int M, int N,
+                                                            const float* __restrict__ bias, float* __restrict__ C,
+                                                            int64_t ldc) {
+  const size_t total = (size_t)M * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / N), n = (int)(i % N);
+    float acc = 0.f;
+    for (int k = 0; k < ksplit; ++k) acc += part[(size_t)k * total + i];
+    if (bias) acc += bias[n];
+    C[(size_t)m * ldc + n] = acc;
+  }
+}
+
+// ---- staging ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) amax2d_kernel(const float* __restrict__ src, int R, int C, int64_t lds,
+                                                     unsigned int* __restrict__ amax_bits) {
+  float a = 0.f;
+  const size_t total = (size_t)R * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    a = fmaxf(a, fabsf(src[(i / C) * lds + (i % C)]));
+  a = warp_max(a);
+  if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(amax_bits, __float_as_uint(a));
+}
+
+__device__ __forceinline__ float scale_from_amax(float amax) {
+  float s = 1.f;
+  if (amax > 0.f && amax < INFINITY) {
+    int e;
+    frexpf(amax, &e);
+    s = ldexpf(1.f, 1 - e);  // amax * s in [1, 2)
+  }
+  return s;
+}
+
+// scale slot layout: [0] = s, [1] = 1/s, [2] = amax bits (written by amax2d_kernel)
+__global__ void __launch_bounds__(256) stage_kernel(const float* __restrict__ src, int R, int C, int64_t lds,
+                                                    int pitch, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                    float* __restrict__ scale) {
+  const float s = scale_from_amax(__uint_as_float(reinterpret_cast<const unsigned int*>(scale)[2]));
+  if (blockIdx.x == 0 && threadIdx.x == 0) { scale[0] = s; scale[1] = 1.f / s; }
+  const size_t total = (size_t)R * pitch;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / pitch), c = (int)(i % pitch);
+    const float x = c < C ? src[(size_t)r * lds + c] * s : 0.f;
+    const __half h = __float2half_rn(x);
+    hi[i] = h;
+    lo[i] = __float2half_rn(x - __half2float(h));
+  }
+}
+
+// dst (C rows x R cols, pitch) = src^T, 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) stage_T_kernel(const float* __restrict__ src, int R, int C, int64_t lds,
+                                                      int pitch, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                      float* __restrict__ scale) {
+  __shared__ float tile[32][33];
+  const float s = scale_from_amax(__uint_as_float(reinterpret_cast<const unsigned int*>(scale)[2]));
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { scale[0] = s; scale[1] = 1.f / s; }
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;  // tile of src: rows r0.., cols c0..
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int r = r0 + k, c = c0 + tx;
+    tile[k][tx] = (r < R && c < C) ? src[(size_t)r * lds + c] * s : 0.f;
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int orow = c0 + k, ocol = r0 + tx;  // dst[orow][ocol] = src[ocol][orow]
+    if (orow < C && ocol < pitch) {
+      const float x = tile[tx][k];
+      const __half h = __float2half_rn(x);
+      hi[(size_t)orow * pitch + ocol] = h;
+      lo[(size_t)orow * pitch + ocol] = __float2half_rn(x - __half2float(h));
+    }
+  }
+}
+
+static size_t plane_elems(int rows, int cols) { return (size_t)rows * round_up((size_t)cols, 8); }
+
+size_t planes_bytes(int rows, int cols) {
+  return 2 * round_up(plane_elems(rows, cols) * sizeof(__half), 256) + 256;
+}
+
+Planes carve_planes(void* mem, int rows, int cols) {
+  Planes pl;
+  char* p = static_cast<char*>(mem);
+  const size_t one = round_up(plane_elems(rows, cols) * sizeof(__half), 256);
+  pl.scale = reinterpret_cast<float*>(p);
+  pl.hi = reinterpret_cast<__half*>(p + 256);
+  pl.lo = reinterpret_cast<__half*>(p + 256 + one);
+  pl.rows = rows;
+  pl.cols = cols;
+  pl.pitch = (int)round_up((size_t)cols, 8);
+  return pl;
+}
+
+int stage(const float* src, int R, int C, int64_t lds, int transpose, const Planes& dst, cudaStream_t st) {
+  MC_REQUIRE(src && dst.hi && dst.lo && dst.scale, MC_ERR_BAD_ARG, "stage: null pointer");
+  MC_REQUIRE(dst.rows == (transpose ? C : R) && dst.cols == (transpose ? R : C), MC_ERR_BAD_ARG,
+             "stage: destination planes are %d x %d, expected %d x %d", dst.rows, dst.cols, transpose ? C : R,
+             transpose ? R : C);
+  MC_CUDA(cudaMemsetAsync(dst.scale, 0, 16, st));
+  const size_t total = (size_t)R * C;
+  int ab = (int)((total + 255) / 256);
+  const int cap = num_sms() * 8;
+  if (ab > cap) ab = cap;
+  amax2d_kernel<<<ab, 256, 0, st>>>(src, R, C, lds, reinterpret_cast<unsigned int*>(dst.scale) + 2);
+  MC_LAUNCH_CHECK();
+  if (!transpose) {
+    const size_t tot = (size_t)R * dst.pitch;
+    int nb = (int)((tot + 255) / 256);
+    if (nb > cap) nb = cap;
+    stage_kernel<<<nb, 256, 0, st>>>(src, R, C, lds, dst.pitch, dst.hi, dst.lo, dst.scale);
+  } else {
+    // cover the padding columns [R, pitch) too
+    dim3 grid((dst.pitch + 31) / 32, (C + 31) / 32);
+    stage_T_kernel<<<grid, 256, 0, st>>>(src, R, C, lds, dst.pitch, dst.hi, dst.lo, dst.scale);
+  }
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
+// ---- host side of the GEMM ---------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+static int make_map(CUtensorMap* m, const __half* ptr, int rows, int cols, int pitch) {
+  EncodeTiledFn fn = encode_fn();
+  MC_REQUIRE(fn != nullptr, MC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};  // out-of-range parts of a box read as zero
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(__half)};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MC_REQUIRE(r == CUDA_SUCCESS, MC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return MC_OK;
+}
+
+static int choose_ksplit(int M, int N, int K) {
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  const int chunks = (K + 63) / 64;
+  if (tiles >= num_sms()) return 1;
+  int ks = (2 * num_sms() + tiles - 1) / tiles;
+  if (ks > chunks) ks = chunks;
+  if (ks > 64) ks = 64;
+  return ks < 1 ? 1 : ks;
+}
+
+size_t gemm_workspace_bytes(int M, int N, int K) {
+  const int ks = choose_ksplit(M, N, K);
+  return ks > 1 ? round_up((size_t)ks * M * N * sizeof(float), 256) : 256;
+}
+
+int gemm(const Planes& A, const Planes& B, int M, int N, int K, const GemmOut& out, int epilogue, void* ws,
+         size_t ws_bytes, cudaStream_t st) {
+  MC_REQUIRE(A.rows == M && A.cols == K && B.rows == N && B.cols == K, MC_ERR_BAD_ARG,
+             "tc gemm: operand shapes (%d x %d) . (%d x %d)^T do not match M=%d N=%d K=%d", A.rows, A.cols, B.rows,
+             B.cols, M, N, K);
+  MC_REQUIRE(out.C != nullptr, MC_ERR_BAD_ARG, "tc gemm: null output");
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, A.hi, A.rows, A.cols, A.pitch))) return rc;
+  if ((rc = make_map(&ma_lo, A.lo, A.rows, A.cols, A.pitch))) return rc;
+  if ((rc = make_map(&mb_hi, B.hi, B.rows, B.cols, B.pitch))) return rc;
+  if ((rc = make_map(&mb_lo, B.lo, B.rows, B.cols, B.pitch))) return rc;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.tiles_m = (M + 127) / 128;
+  p.tiles_n = (N + 127) / 128;
+  p.chunks_total = (K + 63) / 64;
+  p.ksplit = choose_ksplit(M, N, K);
+  if (epilogue == kEpiGelu) p.ksplit = 1;
+  p.chunks_per_split = (p.chunks_total + p.ksplit - 1) / p.ksplit;
+  p.ksplit = (p.chunks_total + p.chunks_per_split - 1) / p.chunks_per_split;  // no empty splits
+  p.scale_a = A.scale;
+  p.scale_b = B.scale;
+  p.bias = out.bias;
+  p.gelu_out = out.gelu_out;
+  if (p.ksplit > 1) {
+    MC_REQUIRE(ws && ws_bytes >= (size_t)p.ksplit * M * N * sizeof(float), MC_ERR_WORKSPACE,
+               "tc gemm: split-K workspace too small");
+    p.C = static_cast<float*>(ws);
+    p.ldc = N;
+    p.vec_ok = (N % 4 == 0) && aligned(ws, 16);
+  } else {
+    p.C = out.C;
+    p.ldc = out.ldc;
+    p.vec_ok = (out.ldc % 4 == 0) && aligned(out.C, 16) && (!out.gelu_out || aligned(out.gelu_out, 16));
+  }
+  const int njobs = p.tiles_m * p.tiles_n * p.ksplit;
+  const int grid = njobs < num_sms() ? njobs : num_sms();
+  if (epilogue == kEpiGelu) {
+    static bool set = false;
+    if (!set) { MC_CUDA(cudaFuncSetAttribute(gemm_kernel<kEpiGelu>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); set = true; }
+    gemm_kernel<kEpiGelu><<<grid, kThreads, kSmem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  } else {
+    static bool set = false;
+    if (!set) { MC_CUDA(cudaFuncSetAttribute(gemm_kernel<kEpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); set = true; }
+    gemm_kernel<kEpiPlain><<<grid, kThreads, kSmem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  }
+  MC_LAUNCH_CHECK();
+  if (p.ksplit > 1) {
+    const size_t total = (size_t)M * N;
+    int nb = (int)((total + 255) / 256);
+    const int cap = num_sms() * 8;
+    if (nb > cap) nb = cap;
+    splitk_reduce_kernel<<<nb, 256, 0, st>>>(static_cast<const float*>(ws), p.ksplit, M, N, out.bias, out.C, out.ldc);
+    MC_LAUNCH_CHECK();
+  }
+  return MC_OK;
+}
+
+}  // namespace tcg
+}  // namespace mc

@@ -1,0 +1,42 @@
+// fp32-class GEMM on the 5th-gen tensor cores for the ProjectionHead (modules.py:63-72 and their
+// autograd): C[M,N] = A[M,K] . B[N,K]^T with both operands staged as K-major fp16 hi/lo planes
+// (x = (hi + lo) / s, s a per-matrix power of two) and three tcgen05 passes hi*hi + hi*lo + lo*hi.
+#pragma once
+#include "common.cuh"
+
+#include <cuda_fp16.h>
+
+namespace mc {
+namespace tcg {
+
+struct Planes {          // a staged operand: rows x cols fp16, row pitch `pitch` elements (multiple of 8)
+  __half* hi;
+  __half* lo;
+  float* scale;          // device: {s, 1/s}
+  int rows, cols, pitch;
+};
+
+size_t planes_bytes(int rows, int cols);  // hi + lo + scale slot, 256-byte aligned pieces
+
+// carve `mem` (>= planes_bytes) into a Planes descriptor
+Planes carve_planes(void* mem, int rows, int cols);
+
+// dst = split(src * s): src is (R, C) fp32 with row stride lds; transpose = 1 stages src^T (C rows, R cols)
+int stage(const float* src, int R, int C, int64_t lds, int transpose, const Planes& dst, cudaStream_t st);
+
+enum Epilogue { kEpiPlain = 0, kEpiGelu = 1 };
+
+struct GemmOut {
+  float* C;              // (M, N) fp32, row stride ldc
+  int64_t ldc;
+  const float* bias;     // length N or null
+  float* gelu_out;       // kEpiGelu: gelu(C) with the same layout, or null
+};
+
+// ksplit > 1: partial products go to `ws` (ksplit x M x N fp32) and a second kernel reduces them
+size_t gemm_workspace_bytes(int M, int N, int K);
+int gemm(const Planes& A, const Planes& B, int M, int N, int K, const GemmOut& out, int epilogue, void* ws,
+         size_t ws_bytes, cudaStream_t st);
+
+}  // namespace tcg
+}  // namespace mc

@@ -5,6 +5,7 @@
 // LayerNorm are one warp-per-row pass (K2), its backward another (K2b) that also emits the
 // gamma/beta column partials.  The dropout keep-mask is an INPUT (SURVEY.md section 7 f).
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace mc {
 
@@ -245,15 +246,83 @@ static HeadWs head_ws(void* ws, int B, int /*E*/, int P) {
   return w;
 }
 
+
+// ---------------- tcgen05 path: workspace map (bump allocation, every piece 256-byte aligned) ----------------
+struct TcHeadWs {
+  // fp32 temporaries (same roles as HeadWs)
+  float *y, *hidden_tmp, *dz, *dy, *dh, *partials;
+  // staged operands
+  tcg::Planes x, wp, h, wf;                          // forward
+  tcg::Planes dyT, hT, dy_p, wfT, dpT, xT, dp_p, wpT;  // backward
+  void* gemm_ws;
+  size_t gemm_ws_bytes;
+  size_t total;
+};
+static TcHeadWs tc_head_ws(void* ws, int B, int E, int P) {
+  TcHeadWs w;
+  char* base = static_cast<char*>(ws);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += round_up(bytes, 256); return p; };
+  auto planes = [&](int rows, int cols) {
+    void* mem = take(tcg::planes_bytes(rows, cols));
+    return mem ? tcg::carve_planes(mem, rows, cols) : tcg::Planes{nullptr, nullptr, nullptr, rows, cols, 0};
+  };
+  const size_t bp = (size_t)B * P * 4;
+  w.y = reinterpret_cast<float*>(take(bp));
+  w.hidden_tmp = reinterpret_cast<float*>(take(bp));
+  w.dh = reinterpret_cast<float*>(take(bp));
+  w.dz = w.y;            // backward reuses the forward temporaries
+  w.dy = w.hidden_tmp;
+  w.partials = reinterpret_cast<float*>(take((size_t)ln_blocks(B) * 2 * P * 4));
+  w.x = planes(B, E);  w.wp = planes(P, E);  w.h = planes(B, P);  w.wf = planes(P, P);
+  w.dyT = planes(P, B); w.hT = planes(P, B); w.dy_p = planes(B, P); w.wfT = planes(P, P);
+  w.dpT = planes(P, B); w.xT = planes(E, B); w.dp_p = planes(B, P); w.wpT = planes(E, P);
+  size_t g = tcg::gemm_workspace_bytes(B, P, E);
+  size_t cands[5] = {tcg::gemm_workspace_bytes(B, P, P), tcg::gemm_workspace_bytes(P, P, B),
+                     tcg::gemm_workspace_bytes(P, E, B), tcg::gemm_workspace_bytes(B, E, P), 256};
+  for (size_t c : cands) g = c > g ? c : g;
+  w.gemm_ws_bytes = g;
+  w.gemm_ws = take(g);
+  w.total = off;
+  return w;
+}
+
+static bool use_tc(int mode) { return mode == MC_GEMM_TC_F16X3 || mode == MC_GEMM_TC_F16; }
+
 }  // namespace mc
 
 using namespace mc;
 
 extern "C" {
 
-size_t mc_proj_head_workspace_bytes(int B, int E, int P, int /*mode*/) {
+size_t mc_tc_gemm_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  return round_up(tcg::planes_bytes(M, K), 256) + round_up(tcg::planes_bytes(N, K), 256) +
+         tcg::gemm_workspace_bytes(M, N, K);
+}
+
+int mc_tc_gemm(const float* A, const float* B, int M, int N, int K, const float* bias, float* C,
+               float* gelu_out, void* ws, size_t ws_bytes, void* stream) {
+  MC_ARCH_GUARD();
+  MC_REQUIRE(A && B && C && ws, MC_ERR_BAD_ARG, "tc_gemm: null pointer");
+  MC_REQUIRE(M > 0 && N > 0 && K > 0, MC_ERR_BAD_ARG, "tc_gemm: bad sizes %d %d %d", M, N, K);
+  MC_REQUIRE(aligned(ws, 256), MC_ERR_ALIGN, "tc_gemm: workspace must be 256-byte aligned");
+  MC_REQUIRE(ws_bytes >= mc_tc_gemm_workspace_bytes(M, N, K), MC_ERR_WORKSPACE, "tc_gemm: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(ws);
+  const size_t a_bytes = round_up(tcg::planes_bytes(M, K), 256), b_bytes = round_up(tcg::planes_bytes(N, K), 256);
+  tcg::Planes pa = tcg::carve_planes(base, M, K), pb = tcg::carve_planes(base + a_bytes, N, K);
+  int rc;
+  if ((rc = tcg::stage(A, M, K, K, 0, pa, st))) return rc;
+  if ((rc = tcg::stage(B, N, K, K, 0, pb, st))) return rc;
+  tcg::GemmOut o{C, N, bias, gelu_out};
+  return tcg::gemm(pa, pb, M, N, K, o, gelu_out ? tcg::kEpiGelu : tcg::kEpiPlain, base + a_bytes + b_bytes,
+                   ws_bytes - a_bytes - b_bytes, st);
+}
+
+size_t mc_proj_head_workspace_bytes(int B, int E, int P, int mode) {
   if (B <= 0 || E <= 0 || P <= 0) return 0;
-  return head_ws(nullptr, B, E, P).total;
+  return use_tc(mode) ? tc_head_ws(nullptr, B, E, P).total : head_ws(nullptr, B, E, P).total;
 }
 
 int mc_proj_head_fwd(const float* x, int B, int E, int P, const float* w_proj, const float* b_proj,
@@ -269,22 +338,39 @@ int mc_proj_head_fwd(const float* x, int B, int E, int P, const float* w_proj, c
   MC_REQUIRE(P % 4 == 0 && P <= 1024, MC_ERR_UNSUPPORTED,
              "proj_head_fwd: projection_dim %d must be a multiple of 4 and <= 1024", P);
   MC_REQUIRE(p_drop >= 0.f && p_drop < 1.f, MC_ERR_BAD_ARG, "proj_head_fwd: dropout p=%g", p_drop);
-  // the head GEMMs run on the fp32 FMA engine for every mode until their tcgen05 variant lands
   MC_REQUIRE(mode >= MC_GEMM_SIMT_FP32 && mode <= MC_GEMM_TC_F16, MC_ERR_BAD_ARG, "proj_head_fwd: bad mode %d", mode);
   MC_REQUIRE(aligned(projected, 16) && aligned(out, 16) && aligned(gamma, 16) && aligned(beta, 16) &&
                  (!keep_mask || aligned(keep_mask, 4)) && (!z || aligned(z, 16)),
              MC_ERR_ALIGN, "proj_head_fwd: pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float scale = 1.f / (1.f - p_drop);
+  int rc;
+  if (use_tc(mode)) {
+    // tensor-core path: stage fp16 hi/lo planes, two tcgen05 GEMMs (bias + exact GELU fused into the first)
+    MC_REQUIRE(aligned(ws, 256), MC_ERR_ALIGN, "proj_head_fwd: workspace must be 256-byte aligned");
+    TcHeadWs t = tc_head_ws(ws, B, E, P);
+    MC_REQUIRE(ws_bytes >= t.total, MC_ERR_WORKSPACE, "proj_head_fwd: workspace %zu < %zu", ws_bytes, t.total);
+    float* hid_tc = hidden ? hidden : t.hidden_tmp;
+    if ((rc = tcg::stage(x, B, E, E, 0, t.x, st))) return rc;
+    if ((rc = tcg::stage(w_proj, P, E, E, 0, t.wp, st))) return rc;
+    tcg::GemmOut o1{projected, P, b_proj, hid_tc};
+    if ((rc = tcg::gemm(t.x, t.wp, B, P, E, o1, tcg::kEpiGelu, t.gemm_ws, t.gemm_ws_bytes, st))) return rc;
+    if ((rc = tcg::stage(hid_tc, B, P, P, 0, t.h, st))) return rc;
+    if ((rc = tcg::stage(w_fc, P, P, P, 0, t.wf, st))) return rc;
+    tcg::GemmOut o2{t.y, P, b_fc, nullptr};
+    if ((rc = tcg::gemm(t.h, t.wf, B, P, P, o2, tcg::kEpiPlain, t.gemm_ws, t.gemm_ws_bytes, st))) return rc;
+    MC_DISPATCH_NV(P, (launch_ln_fwd<NV>(t.y, projected, keep_mask, scale, gamma, beta, eps, B, P, z, mean, rstd,
+                                         out, st)));
+    return rc;
+  }
   HeadWs w = head_ws(ws, B, E, P);
   MC_REQUIRE(ws_bytes >= w.total, MC_ERR_WORKSPACE, "proj_head_fwd: workspace %zu < %zu", ws_bytes,
              w.total);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* hid = hidden ? hidden : w.hidden_tmp;
-  int rc;
   SgemmArgs g1{x, E, 1, w_proj, 1, E, projected, P, B, P, E, 1.f, b_proj, hid, 0};
   if ((rc = sgemm(g1, st))) return rc;
   SgemmArgs g2{hid, P, 1, w_fc, 1, P, w.y, P, B, P, P, 1.f, b_fc, nullptr, 0};
   if ((rc = sgemm(g2, st))) return rc;
-  const float scale = 1.f / (1.f - p_drop);
   MC_DISPATCH_NV(P, (launch_ln_fwd<NV>(w.y, projected, keep_mask, scale, gamma, beta, eps, B, P, z,
                                        mean, rstd, out, st)));
   return rc;
@@ -306,13 +392,61 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
   MC_REQUIRE(aligned(grad_out, 16) && aligned(z, 16) && aligned(projected, 16) && aligned(gamma, 16) &&
                  (!keep_mask || aligned(keep_mask, 4)),
              MC_ERR_ALIGN, "proj_head_bwd: pointers must be 16-byte aligned");
-  HeadWs w = head_ws(ws, B, E, P);
-  MC_REQUIRE(ws_bytes >= w.total, MC_ERR_WORKSPACE, "proj_head_bwd: workspace %zu < %zu", ws_bytes,
-             w.total);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float scale = 1.f / (1.f - p_drop);
   const int blocks = ln_blocks(B);
   int rc;
+  if (use_tc(mode)) {
+    MC_REQUIRE(aligned(ws, 256), MC_ERR_ALIGN, "proj_head_bwd: workspace must be 256-byte aligned");
+    TcHeadWs t = tc_head_ws(ws, B, E, P);
+    MC_REQUIRE(ws_bytes >= t.total, MC_ERR_WORKSPACE, "proj_head_bwd: workspace %zu < %zu", ws_bytes, t.total);
+    MC_DISPATCH_NV(P, (launch_ln_bwd<NV>(grad_out, z, mean, rstd, gamma, keep_mask, scale, B, P, t.dz, t.dy,
+                                         t.partials, blocks, st)));
+    if (rc) return rc;
+    dim3 blk(32, 32);
+    colsum_kernel<<<(2 * P + 31) / 32, blk, 0, st>>>(t.partials, blocks, 2 * P, t.dh);
+    MC_LAUNCH_CHECK();
+    MC_CUDA(cudaMemcpyAsync(dgamma, t.dh, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
+    MC_CUDA(cudaMemcpyAsync(dbeta, t.dh + P, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
+    colsum_kernel<<<(P + 31) / 32, blk, 0, st>>>(t.dy, B, P, db_fc);
+    MC_LAUNCH_CHECK();
+    // dWf[n,k] = sum_m dy[m,n] hidden[m,k]  ->  (dy^T) . (hidden^T)^T, K = B (split-K)
+    if ((rc = tcg::stage(t.dy, B, P, P, 1, t.dyT, st))) return rc;
+    if ((rc = tcg::stage(hidden, B, P, P, 1, t.hT, st))) return rc;
+    tcg::GemmOut o1{dw_fc, P, nullptr, nullptr};
+    if ((rc = tcg::gemm(t.dyT, t.hT, P, P, B, o1, tcg::kEpiPlain, t.gemm_ws, t.gemm_ws_bytes, st))) return rc;
+    // dh[m,k] = sum_n dy[m,n] Wf[n,k]  ->  dy . (Wf^T)^T
+    if ((rc = tcg::stage(t.dy, B, P, P, 0, t.dy_p, st))) return rc;
+    if ((rc = tcg::stage(w_fc, P, P, P, 1, t.wfT, st))) return rc;
+    tcg::GemmOut o2{t.dh, P, nullptr, nullptr};
+    if ((rc = tcg::gemm(t.dy_p, t.wfT, B, P, P, o2, tcg::kEpiPlain, t.gemm_ws, t.gemm_ws_bytes, st))) return rc;
+    {
+      size_t n4 = (size_t)B * P / 4;
+      int nb = (int)((n4 + 255) / 256);
+      int cap = num_sms() * 8;
+      if (nb > cap) nb = cap;
+      gelu_bwd_add_kernel<<<nb, 256, 0, st>>>(t.dh, projected, t.dz, n4);  // dp = dh * gelu'(p) + dz
+      MC_LAUNCH_CHECK();
+      colsum_kernel<<<(P + 31) / 32, blk, 0, st>>>(t.dh, B, P, db_proj);
+      MC_LAUNCH_CHECK();
+    }
+    // dWp[n,e] = sum_m dp[m,n] x[m,e]  ->  (dp^T) . (x^T)^T, K = B (split-K)
+    if ((rc = tcg::stage(t.dh, B, P, P, 1, t.dpT, st))) return rc;
+    if ((rc = tcg::stage(x, B, E, E, 1, t.xT, st))) return rc;
+    tcg::GemmOut o3{dw_proj, E, nullptr, nullptr};
+    if ((rc = tcg::gemm(t.dpT, t.xT, P, E, B, o3, tcg::kEpiPlain, t.gemm_ws, t.gemm_ws_bytes, st))) return rc;
+    if (dx) {
+      // dx[m,e] = sum_n dp[m,n] Wp[n,e]  ->  dp . (Wp^T)^T
+      if ((rc = tcg::stage(t.dh, B, P, P, 0, t.dp_p, st))) return rc;
+      if ((rc = tcg::stage(w_proj, P, E, E, 1, t.wpT, st))) return rc;
+      tcg::GemmOut o4{dx, E, nullptr, nullptr};
+      if ((rc = tcg::gemm(t.dp_p, t.wpT, B, E, P, o4, tcg::kEpiPlain, t.gemm_ws, t.gemm_ws_bytes, st))) return rc;
+    }
+    return MC_OK;
+  }
+  HeadWs w = head_ws(ws, B, E, P);
+  MC_REQUIRE(ws_bytes >= w.total, MC_ERR_WORKSPACE, "proj_head_bwd: workspace %zu < %zu", ws_bytes,
+             w.total);
   MC_DISPATCH_NV(P, (launch_ln_bwd<NV>(grad_out, z, mean, rstd, gamma, keep_mask, scale, B, P, w.dz,
                                        w.dy, w.partials, blocks, st)));
   if (rc) return rc;

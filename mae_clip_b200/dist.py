@@ -29,8 +29,9 @@ from ._lib import check, cur_stream, lib, ptr, require_cuda, workspace
 class CudaStripEngine:
     """The product engine: the three sweeps through the C ABI on this rank's GPU."""
 
-    def __init__(self, mode="simt_fp32"):
-        self.mode = _lib.GEMM_MODES[mode] if isinstance(mode, str) else int(mode)
+    def __init__(self, mode=None):
+        from .functional import _mode
+        self.mode = _mode(mode)
 
     def _ws(self, b, B, D, dev):
         return workspace(lib().mc_clip_loss_workspace_bytes(b, B, D, self.mode), dev)
@@ -141,7 +142,7 @@ class _GlobalClipLoss(torch.autograd.Function):
         return dI.to(ctx.in_dtypes[0]), dT.to(ctx.in_dtypes[1]), None, None, None
 
 
-def global_clip_loss(image_emb_local, text_emb_local, temperature: float = 1.0, mode="simt_fp32",
+def global_clip_loss(image_emb_local, text_emb_local, temperature: float = 1.0, mode=None,
                      group=None, engine=None):
     """Loss of the reference on the concatenation of every rank's (b, D) embeddings; the value is
     identical on all ranks and ``backward`` yields d loss_global / d (local embeddings) in full.

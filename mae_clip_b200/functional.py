@@ -11,6 +11,9 @@ from ._lib import check, cur_stream, lib, ptr, require_cuda, workspace
 
 
 def _mode(mode) -> int:
+    if mode is None:  # package default (config.gemm_mode): the fp32-class tensor-core engine
+        from . import config as CFG
+        mode = CFG.gemm_mode
     if isinstance(mode, int):
         return mode
     try:
@@ -124,7 +127,7 @@ class _ClipLoss(torch.autograd.Function):
         return gi, gt, None, None
 
 
-def clip_contrastive_loss(image_emb, text_emb, temperature: float = 1.0, mode="simt_fp32"):
+def clip_contrastive_loss(image_emb, text_emb, temperature: float = 1.0, mode=None):
     """Scalar soft-target bidirectional CE of ``CLIPModel.forward`` from (B, D) embeddings."""
     return _ClipLoss.apply(image_emb, text_emb, float(temperature), _mode(mode))
 
@@ -192,7 +195,7 @@ class _ProjHead(torch.autograd.Function):
 
 
 def projection_head(x, w_proj, b_proj, w_fc, b_fc, ln_weight, ln_bias, keep_mask=None,
-                    p_drop: float = 0.1, eps: float = 1e-5, mode="simt_fp32"):
+                    p_drop: float = 0.1, eps: float = 1e-5, mode=None):
     """Fused ProjectionHead forward; ``keep_mask`` (0/1, shape of the output) = training mode."""
     return _ProjHead.apply(x, w_proj, b_proj, w_fc, b_fc, ln_weight, ln_bias, keep_mask,
                            float(p_drop), float(eps), _mode(mode))

@@ -143,3 +143,24 @@ def test_head_leading_dims_and_nograd():
     assert out.shape == (3, 5, 256)
     ref = proj_head_ref.proj_head_ref(x.cpu().reshape(15, 48), *[p.detach().cpu() for p in h.parameters()])
     assert rel_err(out.reshape(15, 256), ref) < OUT_TOL
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (24, 256, 160), (1000, 256, 2048), (256, 2048, 1000), (1, 256, 768),
+                                   (300, 100, 72)])
+def test_tc_gemm_entry_point(M, N, K):
+    """mc_tc_gemm: the fp16 hi/lo x3 tcgen05 GEMM the heads are built from, against fp64 matmul."""
+    from mae_clip_b200 import _lib
+    from mae_clip_b200._lib import check, cur_stream, ptr
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(M * 3 + N * 5 + K)
+    A, Bm = torch.randn(M, K, generator=g).cuda(), torch.randn(N, K, generator=g).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    C, G = torch.zeros(M, N, device="cuda"), torch.zeros(M, N, device="cuda")
+    n = lib.mc_tc_gemm_workspace_bytes(M, N, K)
+    ws = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    check(lib.mc_tc_gemm(ptr(A), ptr(Bm), M, N, K, ptr(bias), ptr(C), ptr(G), ptr(ws), n, cur_stream()), "mc_tc_gemm")
+    ref = A.double() @ Bm.double().T + bias.double()
+    # operands are exact to ~2^-22; what remains is the tensor core's truncating fp32 accumulate, which
+    # grows with the un-split K (7e-6 at K = 2048)
+    assert rel_err(C, ref) < 2e-5
+    assert rel_err(G, torch.nn.functional.gelu(ref)) < 2e-5
