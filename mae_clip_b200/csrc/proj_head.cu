@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) gelu_bwd_add_kernel(float* __restrict__ d
 
 static int ln_blocks(int B) {
   int nb = (B + 7) / 8;
-  int cap = num_sms() * 2;
+  int cap = num_sms() * 8;  // 8 resident blocks per SM keep enough 16-byte loads in flight
   return nb < cap ? nb : cap;
 }
 

@@ -118,6 +118,35 @@ __global__ void __launch_bounds__(256) soft_ce_bwd_kernel(Strided2D preds, Strid
   }
 }
 
+// ---- backward, everything contiguous along the reduction dim: one warp per row, 16-byte vectors ----
+__global__ void __launch_bounds__(256) soft_ce_bwd_rowmajor(const float* __restrict__ preds, int64_t p_rs,
+                                                           const float* __restrict__ tg, int64_t t_rs, int rows,
+                                                           int cols, const float* __restrict__ row_lse,
+                                                           const float* __restrict__ row_tsum,
+                                                           const float* __restrict__ grad, float* __restrict__ dp,
+                                                           int64_t dp_rs, float* __restrict__ dt, int64_t dt_rs) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int nv = cols >> 2;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const float g = grad[r], lse = row_lse[r], ts = row_tsum[r];
+    const float4* pr = reinterpret_cast<const float4*>(preds + (int64_t)r * p_rs);
+    const float4* tr = reinterpret_cast<const float4*>(tg + (int64_t)r * t_rs);
+    float4* dpr = dp ? reinterpret_cast<float4*>(dp + (int64_t)r * dp_rs) : nullptr;
+    float4* dtr = dt ? reinterpret_cast<float4*>(dt + (int64_t)r * dt_rs) : nullptr;
+    for (int v = lane; v < nv; v += 32) {
+      const float4 a = ld_stream(pr + v);
+      const float lx = a.x - lse, ly = a.y - lse, lz = a.z - lse, lw = a.w - lse;
+      if (dpr) {
+        const float4 b = ld_stream(tr + v);
+        st_stream(dpr + v, make_float4(g * (__expf(lx) * ts - b.x), g * (__expf(ly) * ts - b.y),
+                                       g * (__expf(lz) * ts - b.z), g * (__expf(lw) * ts - b.w)));
+      }
+      if (dtr) st_stream(dtr + v, make_float4(-g * lx, -g * ly, -g * lz, -g * lw));
+    }
+  }
+}
+
 }  // namespace mc
 
 extern "C" {
@@ -157,6 +186,19 @@ int mc_soft_ce_bwd(const float* preds, int64_t p_rs, int64_t p_cs, const float* 
   if (rows == 0 || (!dpreds && !dtargets)) return MC_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   mc::Strided2D P{preds, p_rs, p_cs}, T{targets, t_rs, t_cs};
+  const bool vec = p_cs == 1 && t_cs == 1 && (!dpreds || dp_cs == 1) && (!dtargets || dt_cs == 1) && cols % 4 == 0 &&
+                   p_rs % 4 == 0 && t_rs % 4 == 0 && (!dpreds || dp_rs % 4 == 0) && (!dtargets || dt_rs % 4 == 0) &&
+                   mc::aligned(preds, 16) && mc::aligned(targets, 16) && (!dpreds || mc::aligned(dpreds, 16)) &&
+                   (!dtargets || mc::aligned(dtargets, 16));
+  if (vec) {
+    int nb = (rows + 7) / 8;
+    const int capv = mc::num_sms() * 8;
+    if (nb > capv) nb = capv;
+    mc::soft_ce_bwd_rowmajor<<<nb, 256, 0, st>>>(preds, p_rs, targets, t_rs, rows, cols, row_lse, row_tsum, grad_rows,
+                                                 dpreds, dp_rs, dtargets, dt_rs);
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+  }
   int fast_is_col = (p_cs == 1) ? 1 : 0;
   int64_t total = (int64_t)rows * cols;
   int blocks = (int)((total + 255) / 256);
