@@ -197,7 +197,7 @@ class Phases:
         self.torch, self._lib, self.lib = torch, _lib, _lib.lib()
         self.B, self.b, self.off, self.mode = B, b, row_offset, _lib.GEMM_MODES[mode]
         f32 = dict(device=device, dtype=torch.float32)
-        self.stats_loc = torch.empty(3, b, **f32)
+        self.stats_loc = torch.empty(4, b, **f32)  # r, c, rz, sum_j P_ij S_ij
         self.gq_loc = torch.empty(2, b, **f32)
         self.part = torch.empty(1, **f32)
         self.dI = torch.empty(b, D_EMB, **f32)
@@ -217,11 +217,12 @@ class Phases:
         ck(lib.mc_clip_prepare(p(I_all), p(T_all), B, B, D_EMB, 0, mode, p(self.planes), st), "prepare")
         if record: ev[1].record()
         ck(lib.mc_clip_stats(p(I_all), p(T_all), p(self.planes), b, B, D_EMB, off, 1.0, mode, p(self.stats_loc[0]),
-                             p(self.stats_loc[1]), p(self.stats_loc[2]), p(self.ws), self.ws.numel(), st), "stats")
-        stats_all = gather_vec(self.stats_loc) if gather_vec else self.stats_loc
+                             p(self.stats_loc[1]), p(self.stats_loc[2]), p(self.stats_loc[3]), p(self.ws), self.ws.numel(), st),
+           "stats")
+        stats_all = gather_vec(self.stats_loc[:3]) if gather_vec else self.stats_loc
         if record: ev[2].record()
         ck(lib.mc_clip_rowloss(p(I_all), p(T_all), p(self.planes), b, B, D_EMB, off, 1.0, mode, p(stats_all[0]),
-                               p(stats_all[1]), p(stats_all[2]), p(self.gq_loc[0]), p(self.gq_loc[1]), p(self.part),
+                               p(stats_all[1]), p(stats_all[2]), p(self.stats_loc[3]), p(self.gq_loc[0]), p(self.gq_loc[1]), p(self.part),
                                p(self.ws), self.ws.numel(), st), "rowloss")
         gq_all = gather_vec(self.gq_loc) if gather_vec else self.gq_loc
         if record: ev[3].record()

@@ -87,6 +87,7 @@ int mc_soft_ce_bwd(const float* preds, int64_t p_row_stride, int64_t p_col_strid
  *
  *   stats  : row_lse_s[i] = LSE_j S_ij,  col_lse_s[i] = LSE_j S_ji,
  *            row_lse_z[i] = LSE_j Z_ij            (S = T I^T / tau, Z = (I I^T + T T^T) tau/2)
+ *            row_ps[i]    = sum_j P_ij S_ij       (accumulated online; lets the next sweep skip S)
  *   rowloss: row_g[i] = sum_j P_ij G_ij, col_sum_p[i] = sum_k P_ki, loss_part = sum_i row_g[i]
  *            (P = softmax_row(Z), G = -(2S - r_i - c_j)/(2B); loss = sum over ranks of loss_part)
  *   bwd    : dI_loc, dT_loc = grad_loss * d loss / d (I_loc, T_loc), every term of the owned rows
@@ -104,13 +105,13 @@ int mc_clip_prepare(const float* I_loc, const float* T_loc, int b, int B, int D,
 
 int mc_clip_stats(const float* I_all, const float* T_all, const void* planes_all, int b, int B,
                   int D, int row_offset, float tau, int mode, float* row_lse_s_loc,
-                  float* col_lse_s_loc, float* row_lse_z_loc, void* ws, size_t ws_bytes,
-                  void* stream);
+                  float* col_lse_s_loc, float* row_lse_z_loc, float* row_ps_loc, void* ws,
+                  size_t ws_bytes, void* stream);
 int mc_clip_rowloss(const float* I_all, const float* T_all, const void* planes_all, int b, int B,
                     int D, int row_offset, float tau, int mode, const float* row_lse_s_all,
-                    const float* col_lse_s_all, const float* row_lse_z_all, float* row_g_loc,
-                    float* col_sum_p_loc, float* loss_part, void* ws, size_t ws_bytes,
-                    void* stream);
+                    const float* col_lse_s_all, const float* row_lse_z_all, const float* row_ps_loc,
+                    float* row_g_loc, float* col_sum_p_loc, float* loss_part, void* ws,
+                    size_t ws_bytes, void* stream);
 int mc_clip_bwd(const float* I_all, const float* T_all, const void* planes_all, int b, int B, int D,
                 int row_offset, float tau, int mode, const float* row_lse_s_all,
                 const float* col_lse_s_all, const float* row_lse_z_all, const float* row_g_all,

@@ -36,8 +36,8 @@ SIGNATURES = {
     "mc_clip_loss_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mc_clip_planes_bytes": (_sz, [_i, _i, _i]),
     "mc_clip_prepare": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
-    "mc_clip_stats": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _sz, _p]),
-    "mc_clip_rowloss": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mc_clip_stats": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "mc_clip_rowloss": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mc_clip_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
                          _p]),
     "mc_clip_loss_fused_workspace_bytes": (_sz, [_i, _i, _i]),

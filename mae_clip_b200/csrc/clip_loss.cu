@@ -33,7 +33,7 @@ static FusedLayout fused_layout(int B, int D, int mode) {
   FusedLayout l;
   l.vec_stride = round_up((size_t)B * 4, 256);
   l.off_vec = 0;
-  l.off_planes = round_up(5 * l.vec_stride + 256, 1024);  // + loss scalar slot; planes 1024-aligned
+  l.off_planes = round_up(6 * l.vec_stride + 256, 1024);  // + loss scalar slot; planes 1024-aligned
   size_t planes = (mode == MC_GEMM_SIMT_FP32) ? 0 : tc::planes_bytes(B, D, mode);
   l.off_phase = l.off_planes + round_up(planes, 256);
   size_t phase = (mode == MC_GEMM_SIMT_FP32) ? simt::workspace_bytes(B, B, D)
@@ -74,33 +74,33 @@ int mc_clip_prepare(const float* I_loc, const float* T_loc, int b, int B, int D,
 
 int mc_clip_stats(const float* I_all, const float* T_all, const void* planes_all, int b, int B,
                   int D, int row_offset, float tau, int mode, float* r_loc, float* c_loc,
-                  float* rz_loc, void* ws, size_t ws_bytes, void* stream) {
+                  float* rz_loc, float* ps_loc, void* ws, size_t ws_bytes, void* stream) {
   MC_ARCH_GUARD();
   int rc = check_problem("clip_stats", I_all, T_all, b, B, D, row_offset, tau, mode);
   if (rc) return rc;
-  MC_REQUIRE(r_loc && c_loc && rz_loc && ws, MC_ERR_BAD_ARG, "clip_stats: null output/workspace");
+  MC_REQUIRE(r_loc && c_loc && rz_loc && ps_loc && ws, MC_ERR_BAD_ARG, "clip_stats: null output/workspace");
   ClipProblem p{I_all, T_all, planes_all, b, B, D, row_offset, tau};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   mode = eff_mode(mode, D);
-  if (mode == MC_GEMM_SIMT_FP32) return simt::stats(p, r_loc, c_loc, rz_loc, ws, ws_bytes, st);
-  return tc::stats(p, mode, r_loc, c_loc, rz_loc, ws, ws_bytes, st);
+  if (mode == MC_GEMM_SIMT_FP32) return simt::stats(p, r_loc, c_loc, rz_loc, ps_loc, ws, ws_bytes, st);
+  return tc::stats(p, mode, r_loc, c_loc, rz_loc, ps_loc, ws, ws_bytes, st);
 }
 
 int mc_clip_rowloss(const float* I_all, const float* T_all, const void* planes_all, int b, int B,
                     int D, int row_offset, float tau, int mode, const float* r_all,
-                    const float* c_all, const float* rz_all, float* g_loc, float* q_loc,
-                    float* loss_part, void* ws, size_t ws_bytes, void* stream) {
+                    const float* c_all, const float* rz_all, const float* ps_loc, float* g_loc,
+                    float* q_loc, float* loss_part, void* ws, size_t ws_bytes, void* stream) {
   MC_ARCH_GUARD();
   int rc = check_problem("clip_rowloss", I_all, T_all, b, B, D, row_offset, tau, mode);
   if (rc) return rc;
-  MC_REQUIRE(r_all && c_all && rz_all && g_loc && q_loc && loss_part && ws, MC_ERR_BAD_ARG,
+  MC_REQUIRE(r_all && c_all && rz_all && ps_loc && g_loc && q_loc && loss_part && ws, MC_ERR_BAD_ARG,
              "clip_rowloss: null pointer");
   ClipProblem p{I_all, T_all, planes_all, b, B, D, row_offset, tau};
   ClipStatsAll s{r_all, c_all, rz_all, nullptr, nullptr};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   mode = eff_mode(mode, D);
-  if (mode == MC_GEMM_SIMT_FP32) return simt::rowloss(p, s, g_loc, q_loc, loss_part, ws, ws_bytes, st);
-  return tc::rowloss(p, mode, s, g_loc, q_loc, loss_part, ws, ws_bytes, st);
+  if (mode == MC_GEMM_SIMT_FP32) return simt::rowloss(p, s, ps_loc, g_loc, q_loc, loss_part, ws, ws_bytes, st);
+  return tc::rowloss(p, mode, s, ps_loc, g_loc, q_loc, loss_part, ws, ws_bytes, st);
 }
 
 int mc_clip_bwd(const float* I_all, const float* T_all, const void* planes_all, int b, int B, int D,
@@ -143,13 +143,14 @@ int mc_clip_loss_fwd_bwd(const float* I, const float* T, int B, int D, float tau
   float* rz = reinterpret_cast<float*>(base + l.off_vec + 2 * l.vec_stride);
   float* g = reinterpret_cast<float*>(base + l.off_vec + 3 * l.vec_stride);
   float* q = reinterpret_cast<float*>(base + l.off_vec + 4 * l.vec_stride);
+  float* ps = reinterpret_cast<float*>(base + l.off_vec + 5 * l.vec_stride);
   void* planes = base + l.off_planes;
   void* phase = base + l.off_phase;
   size_t phase_bytes = l.total - l.off_phase;
   if ((rc = mc_clip_prepare(I, T, B, B, D, 0, mode, planes, stream))) return rc;
-  if ((rc = mc_clip_stats(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, phase, phase_bytes, stream)))
+  if ((rc = mc_clip_stats(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, ps, phase, phase_bytes, stream)))
     return rc;
-  if ((rc = mc_clip_rowloss(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, g, q, loss_out, phase,
+  if ((rc = mc_clip_rowloss(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, ps, g, q, loss_out, phase,
                             phase_bytes, stream)))
     return rc;
   if (dI) {

@@ -22,9 +22,9 @@ struct ClipStatsAll {  // length-B vectors (device)
 
 namespace simt {
 size_t workspace_bytes(int b, int B, int D);
-int stats(const ClipProblem& p, float* r_loc, float* c_loc, float* rz_loc, void* ws, size_t ws_bytes,
-          cudaStream_t st);
-int rowloss(const ClipProblem& p, const ClipStatsAll& s, float* g_loc, float* q_loc,
+int stats(const ClipProblem& p, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
+          size_t ws_bytes, cudaStream_t st);
+int rowloss(const ClipProblem& p, const ClipStatsAll& s, const float* ps_loc, float* g_loc, float* q_loc,
             float* loss_part, void* ws, size_t ws_bytes, cudaStream_t st);
 int bwd(const ClipProblem& p, const ClipStatsAll& s, const float* grad_loss, float* dI, float* dT,
         void* ws, size_t ws_bytes, cudaStream_t st);
@@ -36,10 +36,10 @@ size_t workspace_bytes(int b, int B, int D, int mode);
 size_t planes_bytes(int B, int D, int mode);
 int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row_offset, int mode,
             void* planes_all, cudaStream_t st);
-int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, void* ws,
+int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
           size_t ws_bytes, cudaStream_t st);
-int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, float* g_loc, float* q_loc,
-            float* loss_part, void* ws, size_t ws_bytes, cudaStream_t st);
+int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* ps_loc, float* g_loc,
+            float* q_loc, float* loss_part, void* ws, size_t ws_bytes, cudaStream_t st);
 int bwd(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, float* dI,
         float* dT, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace tc

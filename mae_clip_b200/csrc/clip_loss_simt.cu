@@ -30,7 +30,7 @@ static Strips carve(void* ws, int b, int B) {
 // one warp per local row: three row log-sum-exps
 __global__ void __launch_bounds__(256) row_lse3_kernel(const float* S, const float* St,
                                                        const float* Z, int b, int B, float* r,
-                                                       float* c, float* rz) {
+                                                       float* c, float* rz, float* ps) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= b) return;
   Lse a, d, e;
@@ -42,7 +42,11 @@ __global__ void __launch_bounds__(256) row_lse3_kernel(const float* S, const flo
     e.add(Z[off + j]);
   }
   warp_merge_lse(a); warp_merge_lse(d); warp_merge_lse(e);
-  if (lane == 0) { r[row] = a.value(); c[row] = d.value(); rz[row] = e.value(); }
+  const float rzv = e.value();
+  float acc = 0.f;  // sum_j P_ij S_ij
+  for (int j = lane; j < B; j += 32) acc = fmaf(__expf(Z[off + j] - rzv), S[off + j], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) { r[row] = a.value(); c[row] = d.value(); rz[row] = rzv; ps[row] = acc; }
 }
 
 // one warp per local row: g_i = sum_j P_ij G_ij ; q_i = sum_k exp(Z_ik - rz_k) (Z symmetric)
@@ -110,8 +114,8 @@ __global__ void __launch_bounds__(256) grad_weights_kernel(float* S, float* St, 
   }
 }
 
-int stats(const ClipProblem& p, float* r_loc, float* c_loc, float* rz_loc, void* ws, size_t ws_bytes,
-          cudaStream_t st) {
+int stats(const ClipProblem& p, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
+          size_t ws_bytes, cudaStream_t st) {
   MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D), MC_ERR_WORKSPACE,
              "clip_stats(simt): workspace %zu < %zu", ws_bytes, workspace_bytes(p.b, p.B, p.D));
   Strips w = carve(ws, p.b, p.B);
@@ -130,13 +134,13 @@ int stats(const ClipProblem& p, float* r_loc, float* c_loc, float* rz_loc, void*
   if ((rc = sgemm(a3, st))) return rc;
   SgemmArgs a4{T_loc, D, 1, p.T_all, 1, D, w.Z, p.B, p.b, p.B, D, 0.5f * p.tau, nullptr, nullptr, 1};
   if ((rc = sgemm(a4, st))) return rc;
-  row_lse3_kernel<<<(p.b + 7) / 8, 256, 0, st>>>(w.S, w.St, w.Z, p.b, p.B, r_loc, c_loc, rz_loc);
+  row_lse3_kernel<<<(p.b + 7) / 8, 256, 0, st>>>(w.S, w.St, w.Z, p.b, p.B, r_loc, c_loc, rz_loc, ps_loc);
   MC_LAUNCH_CHECK();
   return MC_OK;
 }
 
-int rowloss(const ClipProblem& p, const ClipStatsAll& s, float* g_loc, float* q_loc,
-            float* loss_part, void* ws, size_t ws_bytes, cudaStream_t st) {
+int rowloss(const ClipProblem& p, const ClipStatsAll& s, const float* /*ps_loc: this engine keeps S*/,
+            float* g_loc, float* q_loc, float* loss_part, void* ws, size_t ws_bytes, cudaStream_t st) {
   MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D), MC_ERR_WORKSPACE,
              "clip_rowloss(simt): workspace too small");
   Strips w = carve(ws, p.b, p.B);

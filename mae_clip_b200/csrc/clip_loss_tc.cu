@@ -68,6 +68,7 @@ struct PairParams {
   float inv_tau, half_tau, inv_2B;
   const float* scale;                  // {s, 1/s, 1/s^2}: global power-of-two scale of the fp16 planes
   const float *r, *c, *rz, *g, *q;     // length-B statistics (phase dependent, may be null)
+  const float* ps;                     // row-loss sweep: sum_j P_ij S_ij of the owned rows (length b)
   float* part;                         // partial results of this phase
   const float* wscale;                 // gradient sweep: power-of-two scale of the fp16 weight tiles
 };
@@ -419,7 +420,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                     const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
                     const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
                     const uint64_t kb = desc_advance_k(bI, ks), kbl = desc_advance_k(bIl, ks);
-                    if (do_s) {
+                    if (do_s && PHASE != kRowLoss) {
                       mma_f16_pair(tS, kT, kb, idesc_tile, acc);                       // S  = T_i I_j^T
                       mma_f16_pair(tS, kT, kbl, idesc_tile, 1u);
                       mma_f16_pair(tS, desc_advance_k(aTl, ks), kb, idesc_tile, 1u);
@@ -464,9 +465,9 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                   const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
                   const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
                   const uint64_t kbI = desc_advance_k(bI, ks), kbT = desc_advance_k(bT, ks);
-                  if (do_s) {
+                  if (do_s && PHASE != kRowLoss) {
                     mma_f16_pair(tS, kT, kbI, idesc_tile, acc);
-                    if (PHASE != kRowLoss) mma_f16_pair(tSt, kI, kbT, idesc_tile, acc);
+                    mma_f16_pair(tSt, kI, kbT, idesc_tile, acc);
                   }
                   if (do_z) {
                     mma_f16_pair(tZ, kI, kbI, idesc_tile, acc);
@@ -532,6 +533,9 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         wZ = inv_s * p.half_tau * wsc * kLn2;      // 2B dZs (log2 units) -> fp16 weight
       }
       float mS = -INFINITY, sS = 0.f, mSt = -INFINITY, sSt = 0.f, mZ = -INFINITY, sZ = 0.f;  // raw-domain max, sums
+      float aPS = 0.f;  // sum_j e^{Z_ij - mZ} S_ij in raw accumulator units
+      float ps2_i = 0.f;
+      if (PHASE == kRowLoss && row_ok) ps2_i = p.ps[lrow] * kL2e;  // sum_j P_ij S_ij, log2 units
       float ag4[4] = {0.f, 0.f, 0.f, 0.f}, aq4[4] = {0.f, 0.f, 0.f, 0.f};
 
       for (int t = t0; t < t1; ++t, ++tt) {
@@ -562,8 +566,10 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         // this thread's 32 columns of the three tiles go to registers at once; the tile buffer is
         // handed back to the tensor cores before any arithmetic starts
         float vs[32], vt[32], vz[32];
-        tmem_ld32(tS, vs);
-        if (PHASE != kRowLoss) tmem_ld32(tSt, vt);
+        if (PHASE != kRowLoss) {
+          tmem_ld32(tS, vs);
+          tmem_ld32(tSt, vt);
+        }
         tmem_ld32(tZ, vz);
         tmem_ld_wait();
         tc_fence_before();
@@ -595,9 +601,38 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             sm = sm * ex2f((mx - mn) * c) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
             mx = mn;
           };
+          {  // Z first: besides its log-sum-exp, accumulate aPS = sum_j e^{Z_ij - max} S_ij (raw S units) so
+             // that the row-loss sweep does not have to recompute S.  Padding columns have vz = -inf, vs = 0.
+            if (ragged) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) if (jl0 + e >= jlim) vz[e] = -INFINITY;
+            }
+            float c4[4] = {fmaxf(vz[0], vz[4]), fmaxf(vz[1], vz[5]), fmaxf(vz[2], vz[6]), fmaxf(vz[3], vz[7])};
+#pragma unroll
+            for (int e = 8; e < 32; e += 4) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) c4[u] = fmaxf(c4[u], vz[e + u]);
+            }
+            const float mn = fmaxf(mZ, fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3])));
+            if (mn != -INFINITY) {
+              float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float w = ex2f((vz[e + u] - mn) * cZ2);
+                  a4[u] += w;
+                  b4[u] = fmaf(w, vs[e + u], b4[u]);
+                }
+              }
+              const float resc = ex2f((mZ - mn) * cZ2);
+              sZ = sZ * resc + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
+              aPS = aPS * resc + ((b4[0] + b4[1]) + (b4[2] + b4[3]));
+              mZ = mn;
+            }
+          }
           lse_add32(vs, cS2, mS, sS);
           lse_add32(vt, cS2, mSt, sSt);
-          lse_add32(vz, cZ2, mZ, sZ);
         } else if (PHASE == kRowLoss) {
           if (ragged) {
 #pragma unroll
@@ -612,9 +647,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             for (int u = 0; u < 4; ++u) {  // four independent accumulation chains
               const float z2 = vz[e + u] * cZ2;
               const float P = ex2f(z2 - rz2_i);
-              const float G = fmaf(vs[e + u], m2cS2, r2_i - ncv[u]);  // 2B G_ij log2(e)
-              ag4[u] = fmaf(P, G, ag4[u]);
-              aq4[u] += ex2f(z2 + nrzv[u]);
+              ag4[u] = fmaf(P, -ncv[u], ag4[u]);   // sum_j P_ij c_j (log2 units)
+              aq4[u] += ex2f(z2 + nrzv[u]);        // sum_j e^{Z_ij - rz_j} = colsum(P)_i by symmetry
             }
           }
         } else {
@@ -682,18 +716,20 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       // ---- end of job: write this job's partial results
       if (PHASE == kStats || PHASE == kRowLoss) {
         // four threads hold pieces of row m (lane half n1 x column half h): combine through shared memory
-        float* scratch = reinterpret_cast<float*>(sbase + kOffW);  // [3 partners][6][64]
+        float* scratch = reinterpret_cast<float*>(sbase + kOffW);  // [3 partners][7][64]
         OnlineLse2 lS, lSt, lZ;  // log2-domain (max, sum) pairs
         lS.m = mS * cS2; lS.s = sS; lSt.m = mSt * cS2; lSt.s = sSt; lZ.m = mZ * cZ2; lZ.s = sZ;
+        float aZ = aPS;          // travels with lZ: rescaled by the same factors
         const float acc_g = (ag4[0] + ag4[1]) + (ag4[2] + ag4[3]), acc_q = (aq4[0] + aq4[1]) + (aq4[2] + aq4[3]);
         const int part = 2 * h + n1;  // 0 = the row's writer
         named_bar_sync(2, kEpiThreads);
         if (part != 0) {
-          float* sc = scratch + (part - 1) * 6 * 64;
+          float* sc = scratch + (part - 1) * 7 * 64;
           if (PHASE == kStats) {
             sc[0 * 64 + m] = lS.m; sc[1 * 64 + m] = lS.s;
             sc[2 * 64 + m] = lSt.m; sc[3 * 64 + m] = lSt.s;
             sc[4 * 64 + m] = lZ.m; sc[5 * 64 + m] = lZ.s;
+            sc[6 * 64 + m] = aZ;
           } else {
             sc[0 * 64 + m] = acc_g; sc[1 * 64 + m] = acc_q;
           }
@@ -702,21 +738,24 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         if (part == 0) {
           if (PHASE == kStats) {
             for (int k = 0; k < 3; ++k) {
-              const float* sc = scratch + k * 6 * 64;
+              const float* sc = scratch + k * 7 * 64;
               lS.merge(sc[0 * 64 + m], sc[1 * 64 + m]);
               lSt.merge(sc[2 * 64 + m], sc[3 * 64 + m]);
-              lZ.merge(sc[4 * 64 + m], sc[5 * 64 + m]);
+              const float m2 = sc[4 * 64 + m], mn = fmaxf(lZ.m, m2);
+              if (mn != -INFINITY) aZ = aZ * ex2f(lZ.m - mn) + sc[6 * 64 + m] * ex2f(m2 - mn);
+              lZ.merge(m2, sc[5 * 64 + m]);
             }
             float2* out = reinterpret_cast<float2*>(p.part);
-            const size_t o = (size_t)sp * 3 * p.bpad + lrow;
+            const size_t o = (size_t)sp * 4 * p.bpad + lrow;
             out[o] = make_float2(lS.m, lS.s);
             out[o + p.bpad] = make_float2(lSt.m, lSt.s);
             out[o + 2 * (size_t)p.bpad] = make_float2(lZ.m, lZ.s);
+            out[o + 3 * (size_t)p.bpad] = make_float2(aZ * (inv_s2 * p.inv_tau), 0.f);  // natural S units, relative to lZ.m
           } else {
-            float g = acc_g, q = acc_q;
-            for (int k = 0; k < 3; ++k) { g += scratch[k * 6 * 64 + m]; q += scratch[k * 6 * 64 + 64 + m]; }
+            float pc = acc_g, q = acc_q;
+            for (int k = 0; k < 3; ++k) { pc += scratch[k * 7 * 64 + m]; q += scratch[k * 7 * 64 + 64 + m]; }
             const size_t o = (size_t)sp * 2 * p.bpad + lrow;
-            p.part[o] = g * kLn2;   // back from log2 units: 2B g_i
+            p.part[o] = pc * kLn2;  // this split's share of sum_j P_ij c_j
             p.part[o + p.bpad] = q;
           }
         }
@@ -756,32 +795,41 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stats_finalize_kernel(const float2* __restrict__ part, int nsplit, int bpad,
                                                              int b, float* __restrict__ r, float* __restrict__ c,
-                                                             float* __restrict__ rz) {
+                                                             float* __restrict__ rz, float* __restrict__ ps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b) return;
   float* outs[3] = {r, c, rz};
   for (int k = 0; k < 3; ++k) {
     OnlineLse2 l;
     l.init();
+    float a = 0.f;  // k == 2: sum_j e^{Z_ij - max} S_ij, merged with the same rescaling as the Z sum
     for (int s = 0; s < nsplit; ++s) {
-      float2 v = part[((size_t)s * 3 + k) * bpad + i];
+      const float2 v = part[((size_t)s * 4 + k) * bpad + i];
+      if (k == 2) {
+        const float mn = fmaxf(l.m, v.x);
+        if (mn != -INFINITY) a = a * ex2f(l.m - mn) + part[((size_t)s * 4 + 3) * bpad + i].x * ex2f(v.x - mn);
+      }
       l.merge(v.x, v.y);
     }
     outs[k][i] = (l.m + log2f(l.s)) * kLn2;
+    if (k == 2) ps[i] = a / l.s;
   }
 }
 
+// g_i = (r_i + sum_j P_ij c_j - 2 sum_j P_ij S_ij) / 2B ; q_i = colsum(P)_i
 __global__ void __launch_bounds__(256) rowloss_finalize_kernel(const float* __restrict__ part, int nsplit,
                                                                int bpad, int b, float inv_2B,
+                                                               const float* __restrict__ r_loc,
+                                                               const float* __restrict__ ps_loc,
                                                                float* __restrict__ g, float* __restrict__ q) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b) return;
-  float ag = 0.f, aq = 0.f;
+  float pc = 0.f, aq = 0.f;
   for (int s = 0; s < nsplit; ++s) {
-    ag += part[((size_t)s * 2) * bpad + i];
+    pc += part[((size_t)s * 2) * bpad + i];
     aq += part[((size_t)s * 2 + 1) * bpad + i];
   }
-  g[i] = ag * inv_2B;
+  g[i] = (r_loc[i] + pc - 2.f * ps_loc[i]) * inv_2B;
   q[i] = aq;
 }
 
@@ -922,7 +970,7 @@ size_t planes_bytes(int B, int D, int /*mode*/) { return supported(D) ? planes_l
 
 size_t workspace_bytes(int b, int B, int D, int /*mode*/) {
   Split s = choose_split(b, B);
-  size_t stats = (size_t)s.nsplit * 3 * s.bpad * sizeof(float2);
+  size_t stats = (size_t)s.nsplit * 4 * s.bpad * sizeof(float2);
   size_t bwdp = (size_t)s.nsplit * 2 * s.bpad * D * sizeof(float);
   return round_up(stats > bwdp ? stats : bwdp, 256) + 256;  // + the weight-scale slot
 }
@@ -962,8 +1010,8 @@ int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row
 }
 
 template <int PHASE, int PASSES>
-static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, float* part, const float* wscale,
-                       cudaStream_t st) {
+static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float* ps_loc, float* part,
+                       const float* wscale, cudaStream_t st) {
   MC_REQUIRE(supported(p.D), MC_ERR_UNSUPPORTED, "tcgen05 engine needs D in {128, 256} (got %d)", p.D);
   MC_REQUIRE(p.row_offset % 128 == 0, MC_ERR_UNSUPPORTED, "tcgen05 engine needs row_offset %% 128 == 0 (got %d)",
              p.row_offset);
@@ -990,6 +1038,7 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, float* part,
   pp.inv_tau = 1.f / p.tau; pp.half_tau = 0.5f * p.tau; pp.inv_2B = 0.5f / (float)p.B;
   pp.scale = reinterpret_cast<const float*>(base + l.off_hdr) + 1;
   pp.r = s.r; pp.c = s.c; pp.rz = s.rz; pp.g = s.g; pp.q = s.q;
+  pp.ps = ps_loc;
   pp.part = part;
   pp.wscale = wscale;
 
@@ -1020,34 +1069,34 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, float* part,
 }
 
 template <int PHASE>
-static int launch_phase(int mode, const ClipProblem& p, const ClipStatsAll& s, float* part, const float* wscale,
-                        cudaStream_t st) {
-  if (mode == MC_GEMM_TC_F16X3) return launch_pair<PHASE, 3>(p, s, part, wscale, st);
-  return launch_pair<PHASE, 1>(p, s, part, wscale, st);
+static int launch_phase(int mode, const ClipProblem& p, const ClipStatsAll& s, const float* ps_loc, float* part,
+                        const float* wscale, cudaStream_t st) {
+  if (mode == MC_GEMM_TC_F16X3) return launch_pair<PHASE, 3>(p, s, ps_loc, part, wscale, st);
+  return launch_pair<PHASE, 1>(p, s, ps_loc, part, wscale, st);
 }
 
-int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, void* ws, size_t ws_bytes,
-          cudaStream_t st) {
+int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
+          size_t ws_bytes, cudaStream_t st) {
   MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_stats(tc): workspace %zu < %zu",
              ws_bytes, workspace_bytes(p.b, p.B, p.D, mode));
   ClipStatsAll none{nullptr, nullptr, nullptr, nullptr, nullptr};
-  int rc = launch_phase<kStats>(mode, p, none, static_cast<float*>(ws), nullptr, st);
+  int rc = launch_phase<kStats>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st);
   if (rc) return rc;
   Split sp = choose_split(p.b, p.B);
   stats_finalize_kernel<<<(p.b + 255) / 256, 256, 0, st>>>(static_cast<const float2*>(ws), sp.nsplit, sp.bpad, p.b,
-                                                          r_loc, c_loc, rz_loc);
+                                                          r_loc, c_loc, rz_loc, ps_loc);
   MC_LAUNCH_CHECK();
   return MC_OK;
 }
 
-int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, float* g_loc, float* q_loc, float* loss_part,
-            void* ws, size_t ws_bytes, cudaStream_t st) {
+int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* ps_loc, float* g_loc, float* q_loc,
+            float* loss_part, void* ws, size_t ws_bytes, cudaStream_t st) {
   MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_rowloss(tc): workspace too small");
-  int rc = launch_phase<kRowLoss>(mode, p, s, static_cast<float*>(ws), nullptr, st);
+  int rc = launch_phase<kRowLoss>(mode, p, s, ps_loc, static_cast<float*>(ws), nullptr, st);
   if (rc) return rc;
   Split sp = choose_split(p.b, p.B);
   rowloss_finalize_kernel<<<(p.b + 255) / 256, 256, 0, st>>>(static_cast<const float*>(ws), sp.nsplit, sp.bpad, p.b,
-                                                            0.5f / (float)p.B, g_loc, q_loc);
+                                                            0.5f / (float)p.B, s.r + p.row_offset, ps_loc, g_loc, q_loc);
   MC_LAUNCH_CHECK();
   sum_kernel<<<1, 1024, 0, st>>>(g_loc, p.b, loss_part);
   MC_LAUNCH_CHECK();
@@ -1066,7 +1115,7 @@ int bwd(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad
                                    reinterpret_cast<const float*>(pbase + l.off_norm_i),
                                    reinterpret_cast<const float*>(pbase + l.off_norm_t), 1.f / p.tau, p.tau, wsc);
   MC_LAUNCH_CHECK();
-  int rc = launch_phase<kBwd>(mode, p, s, static_cast<float*>(ws), wsc, st);
+  int rc = launch_phase<kBwd>(mode, p, s, nullptr, static_cast<float*>(ws), wsc, st);
   if (rc) return rc;
   Split sp = choose_split(p.b, p.B);
   size_t n4 = (size_t)p.b * p.D / 4;

@@ -40,7 +40,7 @@ class CudaStripEngine:
         require_cuda(I_all, T_all)
         B, D = I_all.shape
         dev = I_all.device
-        out = torch.empty(3, b, device=dev, dtype=torch.float32)
+        out = torch.empty(4, b, device=dev, dtype=torch.float32)  # r, c, rz and sum_j P_ij S_ij (local only)
         planes = None
         with torch.cuda.device(dev):
             nb = lib().mc_clip_planes_bytes(B, D, self.mode)
@@ -52,10 +52,11 @@ class CudaStripEngine:
             ws = self._ws(b, B, D, dev)
             check(lib().mc_clip_stats(ptr(I_all), ptr(T_all), ptr(planes), b, B, D, row_offset,
                                       float(tau), self.mode, ptr(out[0]), ptr(out[1]), ptr(out[2]),
-                                      ptr(ws), ws.numel(), cur_stream()), "mc_clip_stats")
-        return out, planes
+                                      ptr(out[3]), ptr(ws), ws.numel(), cur_stream()), "mc_clip_stats")
+        return out[:3], (planes, out[3])
 
     def rowloss(self, I_all, T_all, planes, b, row_offset, tau, stats_all):
+        planes, ps_loc = planes
         B, D = I_all.shape
         dev = I_all.device
         out = torch.empty(2, b, device=dev, dtype=torch.float32)
@@ -64,11 +65,12 @@ class CudaStripEngine:
             ws = self._ws(b, B, D, dev)
             check(lib().mc_clip_rowloss(ptr(I_all), ptr(T_all), ptr(planes), b, B, D, row_offset,
                                         float(tau), self.mode, ptr(stats_all[0]), ptr(stats_all[1]),
-                                        ptr(stats_all[2]), ptr(out[0]), ptr(out[1]), ptr(part), ptr(ws),
+                                        ptr(stats_all[2]), ptr(ps_loc), ptr(out[0]), ptr(out[1]), ptr(part), ptr(ws),
                                         ws.numel(), cur_stream()), "mc_clip_rowloss")
         return out, part
 
     def bwd(self, I_all, T_all, planes, b, row_offset, tau, stats_all, gq_all, grad_loss):
+        planes, _ps_loc = planes
         B, D = I_all.shape
         dev = I_all.device
         dI = torch.empty(b, D, device=dev, dtype=torch.float32)

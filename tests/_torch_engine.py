@@ -22,7 +22,7 @@ class TorchStripEngine:
     def stats(self, I_all, T_all, b, row_offset, tau):
         S, St, Z = self._strips(I_all, T_all, b, row_offset, tau)
         out = torch.stack([torch.logsumexp(S, 1), torch.logsumexp(St, 1), torch.logsumexp(Z, 1)])
-        return out.float(), None
+        return out.float(), None  # (this stand-in keeps S, so it does not need the sum_j P_ij S_ij vector)
 
     def rowloss(self, I_all, T_all, planes, b, row_offset, tau, stats_all):
         S, St, Z = self._strips(I_all, T_all, b, row_offset, tau)

@@ -23,9 +23,9 @@ def phases(I, T, tau, mode, b=None, off=0):
     ws = torch.zeros(max(lib.mc_clip_loss_workspace_bytes(b, B, D, mode), 1), dtype=torch.uint8, device=dev)
     st = cur_stream()
     check(lib.mc_clip_prepare(ptr(I), ptr(T), B, B, D, 0, mode, ptr(planes), st), "prepare")
-    s = torch.zeros(3, b, device=dev)
+    s = torch.zeros(4, b, device=dev)
     check(lib.mc_clip_stats(ptr(I), ptr(T), ptr(planes), b, B, D, off, tau, mode, ptr(s[0]), ptr(s[1]), ptr(s[2]),
-                            ptr(ws), ws.numel(), st), "stats")
+                            ptr(s[3]), ptr(ws), ws.numel(), st), "stats")
     torch.cuda.synchronize()
     return planes, ws, s
 
@@ -56,7 +56,7 @@ for B, D, scale in sizes:
         for mode in (1, 2):
             _, _, s1 = phases(I, T, 1.0, mode)
             print(f"B={B} D={D} scale={scale} mode={mode} stats maxabs diff r/c/rz:",
-                  [(s1[k] - s0[k]).abs().max().item() for k in range(3)], "ref range", s0.min().item(), s0.max().item(),
+                  [(s1[k] - s0[k]).abs().max().item() for k in range(4)], "ref range", s0.min().item(), s0.max().item(),
                   flush=True)
             if not torch.isfinite(s1).all() or (s1 - s0).abs().max() > 1e-2:
                 print("   first rows tc:", s1[:, :4].tolist(), " simt:", s0[:, :4].tolist())
@@ -74,7 +74,7 @@ if which == "rowloss":
         for mode in (0, 1):
             planes, ws, s = phases(I, T, 1.0, mode)
             gq = torch.zeros(2, B, device="cuda"); part = torch.zeros(1, device="cuda")
-            check(lib.mc_clip_rowloss(ptr(I), ptr(T), ptr(planes), B, B, D, 0, 1.0, mode, ptr(s[0]), ptr(s[1]), ptr(s[2]),
+            check(lib.mc_clip_rowloss(ptr(I), ptr(T), ptr(planes), B, B, D, 0, 1.0, mode, ptr(s[0]), ptr(s[1]), ptr(s[2]), ptr(s[3]),
                                       ptr(gq[0]), ptr(gq[1]), ptr(part), ptr(ws), ws.numel(), cur_stream()), "rowloss")
             torch.cuda.synchronize()
             res[mode] = (s.clone(), gq.clone(), part.clone())
