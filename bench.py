@@ -200,6 +200,8 @@ class Phases:
         self.stats_loc = torch.empty(4, b, **f32)  # r, c, rz, sum_j P_ij S_ij
         self.gq_loc = torch.empty(2, b, **f32)
         self.part = torch.empty(1, **f32)
+        self.part_buf = self.part
+        self.pack = torch.zeros(3, b, **f32)
         self.dI = torch.empty(b, D_EMB, **f32)
         self.dT = torch.empty(b, D_EMB, **f32)
         nb = self.lib.mc_clip_planes_bytes(B, D_EMB, self.mode)
@@ -222,9 +224,16 @@ class Phases:
         stats_all = gather_vec(self.stats_loc[:3]) if gather_vec else self.stats_loc
         if record: ev[2].record()
         ck(lib.mc_clip_rowloss(p(I_all), p(T_all), p(self.planes), b, B, D_EMB, off, 1.0, mode, p(stats_all[0]),
-                               p(stats_all[1]), p(stats_all[2]), p(self.stats_loc[3]), p(self.gq_loc[0]), p(self.gq_loc[1]), p(self.part),
+                               p(stats_all[1]), p(stats_all[2]), p(self.stats_loc[3]), p(self.gq_loc[0]), p(self.gq_loc[1]), p(self.part_buf),
                                p(self.ws), self.ws.numel(), st), "rowloss")
-        gq_all = gather_vec(self.gq_loc) if gather_vec else self.gq_loc
+        if gather_vec:  # the loss partial rides along with the two vectors: one collective instead of two
+            self.pack[:2] = self.gq_loc
+            self.pack[2, 0:1] = self.part_buf
+            g3 = gather_vec(self.pack)
+            gq_all = g3[:2]
+            self.part = g3[2].reshape(-1, self.b)[:, 0].sum().reshape(1)
+        else:
+            gq_all = self.gq_loc
         if record: ev[3].record()
         ck(lib.mc_clip_bwd(p(I_all), p(T_all), p(self.planes), b, B, D_EMB, off, 1.0, mode, p(stats_all[0]),
                            p(stats_all[1]), p(stats_all[2]), p(gq_all[0]), p(gq_all[1]), None, p(self.dI), p(self.dT),
@@ -288,10 +297,7 @@ def run_b200(args):
 
     def one_step(record=False):
         I_all, T_all = gather_rows(I_loc), gather_rows(T_loc)
-        part = ph.step(I_all, T_all, gather_vec if world > 1 else None, record=record)
-        if world > 1:
-            dist.all_reduce(part)
-        return part
+        return ph.step(I_all, T_all, gather_vec if world > 1 else None, record=record)
 
     def barrier():
         if world > 1:
@@ -351,7 +357,6 @@ def run_b200(args):
             Il = host_I.to(dev, non_blocking=True)
             Tl = host_T.to(dev, non_blocking=True)
             part = ph.step(gather_rows(Il), gather_rows(Tl), gather_vec)
-            dist.all_reduce(part)
             out_dI.copy_(ph.dI, non_blocking=True)
             out_dT.copy_(ph.dT, non_blocking=True)
             out_loss.copy_(part, non_blocking=True)

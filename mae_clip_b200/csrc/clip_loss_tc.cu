@@ -395,7 +395,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             // single weight / X^T buffers are refilled while the tensor cores stay busy.
             const bool lagged = PHASE == kBwd && t > t0;
             for (int c = 0; c < nkc; ++c) {
-              if (lagged && c == nkc / 2) grad_half(0, t - 1 == t0);
+              if (lagged && c == nkc - 1) grad_half(0, t - 1 == t0);
               uint32_t slot_bar = 0;
               auto next_full = [&]() -> uint32_t {  // wait for the next ring slot to land
                 const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;

@@ -125,8 +125,13 @@ class _GlobalClipLoss(torch.autograd.Function):
         stats_all = _all_gather_rows(stats_loc, group) if world > 1 else stats_loc
         gq_loc, part = engine.rowloss(I_all, T_all, planes, b, row_offset, temperature, stats_all)
         if world > 1:
-            gq_all = _all_gather_rows(gq_loc, group)
-            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+            # one collective for the two vectors AND the loss partial (appended as a third row's first entry)
+            packed = torch.zeros(3, b, device=gq_loc.device, dtype=gq_loc.dtype)
+            packed[:2] = gq_loc
+            packed[2, 0] = part.reshape(())
+            gathered = _all_gather(packed, group)                       # (world, 3, b)
+            gq_all = gathered[:, :2].permute(1, 0, 2).reshape(2, world * b).contiguous()
+            part = gathered[:, 2, 0].sum().reshape(1)
         else:
             gq_all = gq_loc
         ctx.engine, ctx.cfg = engine, (b, row_offset, float(temperature))
