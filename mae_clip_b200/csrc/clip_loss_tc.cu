@@ -21,6 +21,8 @@
 #include "clip_loss.cuh"
 #include "tc_ptx.cuh"
 
+#include <type_traits>
+
 namespace mc {
 namespace tc {
 
@@ -47,19 +49,19 @@ constexpr int kOffBar = kOffConst + 8192;
 constexpr int kSmemBytes = kOffBar + 256 + 1024;  // + alignment slack
 
 enum Bar {
-  kFull0 = 0,        // +stage (<= 6)
-  kEmpty0 = 6,       // +stage
-  kAFull = 12,
-  kJobDone = 13,
-  kTmemFull0 = 14,   // +buf
-  kTmemEmpty0 = 16,  // +buf
-  kWFull = 18,
-  kGradDone = 19,
-  kXTFull = 20,
-  kAccFull = 21,
-  kAccEmpty = 22,
-  kGradDone1 = 23,   // kGradDone: column half 0, kGradDone1: column half 1
-  kNumBars = 24
+  kFull0 = 0,        // +slot (<= 9)
+  kEmpty0 = 9,       // +slot
+  kAFull = 18,
+  kJobDone = 19,
+  kTmemFull0 = 20,   // +buf
+  kTmemEmpty0 = 22,  // +buf
+  kWFull = 24,
+  kGradDone = 25,    // column half 0
+  kXTFull = 26,
+  kAccFull = 27,
+  kAccEmpty = 28,
+  kGradDone1 = 29,   // column half 1
+  kNumBars = 30
 };
 
 struct PairParams {
@@ -181,7 +183,9 @@ __global__ void __launch_bounds__(256) transpose_hi_kernel(const __half* __restr
 //   F16  : slot B  = [I_j hi | T_j hi]
 // Small slots keep 4-5 loads in flight ahead of the tensor cores, which hides the L2 latency.
 constexpr int kSlotBytes = 2 * kChunkBytes;
-constexpr int kSlots = kStageRegion / kSlotBytes;  // 6
+constexpr int kSlotsBwd = kStageRegion / kSlotBytes;                                // 6
+// the statistics / row-loss sweeps have no weight and X^T tiles: their ring extends over that space
+constexpr int kSlotsFwd = (kStageRegion + 3 * kChunkBytes + 32768) / kSlotBytes;    // 9
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -226,6 +230,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   // buffer (the epilogue empties it into registers at once) and its accumulators at 256 (dT), 256 + D/2 (dI)
   constexpr int kNBuf = (PHASE == kBwd) ? 1 : 2;
   constexpr uint32_t kAccCol = 256;
+  constexpr int kSlots = (PHASE == kBwd) ? kSlotsBwd : kSlotsFwd;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -527,10 +532,18 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       if (PHASE != kStats && row_ok) { r2_i = p.r[gi] * kL2e; c2_i = p.c[gi] * kL2e; rz2_i = p.rz[gi] * kL2e; }
       if (PHASE == kBwd && row_ok) { gh_i = p.g[gi] * (2.f * (float)p.B) * kL2e; q_i = p.q[gi]; }
       float wS = 0.f, wZ = 0.f;
+      bool fast = false;
+      float m_rc = 0.f, m_z = 0.f, fA_i = 0.f, fC_i = 0.f, fFQ_i = 0.f;
       if (PHASE == kBwd) {
-        const float wsc = *p.wscale;
+        const float wsc = p.wscale[0];
         wS = inv_s * p.inv_tau * wsc;              // 2B dS      -> fp16 weight of X_j (scaled plane)
         wZ = inv_s * p.half_tau * wsc * kLn2;      // 2B dZs (log2 units) -> fp16 weight
+        fast = p.wscale[1] != 0.f;                 // kernel-uniform: see wscale_kernel
+        m_rc = p.wscale[2];
+        m_z = p.wscale[3];
+        fA_i = ex2f(rz2_i - m_z);                  // P_ji          = P_ij          * fA_i * B_j
+        fC_i = ex2f(r2_i - m_rc);                  // e^{S_ij-c_j}  = e^{S_ij-r_i}  * fC_i * D_j
+        fFQ_i = ex2f(m_rc - c2_i) * q_i;           // e^{S_ji-c_i} q_i = e^{S_ji-r_j} * E_j * fFQ_i
       }
       float mS = -INFINITY, sS = 0.f, mSt = -INFINITY, sSt = 0.f, mZ = -INFINITY, sZ = 0.f;  // raw-domain max, sums
       float aPS = 0.f;  // sum_j e^{Z_ij - mZ} S_ij in raw accumulator units
@@ -545,14 +558,22 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           if (tid_e < 128) {
             const int jcol = t * kTileN + tid_e;
             const bool ok = jcol < p.B;
-            cst[1 * 128 + tid_e] = ok ? -p.c[jcol] * kL2e : 0.f;                                        // -c2_j
-            cst[2 * 128 + tid_e] = ok ? -p.rz[jcol] * kL2e : 0.f;                                       // -rz2_j
-            if (PHASE == kBwd) cst[4 * 128 + tid_e] = ok ? p.q[jcol] : 0.f;                             // q_j
+            const float c2 = ok ? p.c[jcol] * kL2e : 0.f, rz2 = ok ? p.rz[jcol] * kL2e : 0.f;
+            cst[1 * 128 + tid_e] = -c2;                                                                 // -c2_j
+            if (PHASE == kBwd && fast) {
+              cst[2 * 128 + tid_e] = ok ? ex2f(m_z - rz2) : 0.f;                                        // B_j
+              cst[4 * 128 + tid_e] = ok ? ex2f(m_rc - c2) * p.q[jcol] : 0.f;                            // D_j q_j
+            } else {
+              cst[2 * 128 + tid_e] = -rz2;                                                              // -rz2_j
+              if (PHASE == kBwd) cst[4 * 128 + tid_e] = ok ? p.q[jcol] : 0.f;                           // q_j
+            }
           } else if (PHASE == kBwd) {
             const int jcol = t * kTileN + tid_e - 128;
             const bool ok = jcol < p.B;
-            cst[0 * 128 + tid_e - 128] = ok ? -p.r[jcol] * kL2e : 0.f;                                  // -r2_j
+            const float r2 = ok ? p.r[jcol] * kL2e : 0.f;
+            cst[0 * 128 + tid_e - 128] = -r2;                                                           // -r2_j
             cst[3 * 128 + tid_e - 128] = ok ? p.g[jcol] * (2.f * (float)p.B) * kL2e : 0.f;              // gh_j
+            cst[5 * 128 + tid_e - 128] = ok ? ex2f(r2 - m_rc) : 0.f;                                    // E_j
           }
           named_bar_sync(1, kEpiThreads);
         }
@@ -654,44 +675,58 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         } else {
           // ---- gradient sweep: tile -> fp16 weight half-tile h -> tensor cores
           uint32_t wSp[16], wStp[16], wZp[16];
+          auto weights32 = [&](auto fast_tag) {
+            constexpr bool kFast = decltype(fast_tag)::value;
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            const float4 f0 = *reinterpret_cast<const float4*>(cst + 0 * 128 + jl0 + e);  // -r2_j
-            const float4 f1 = *reinterpret_cast<const float4*>(cst + 1 * 128 + jl0 + e);  // -c2_j
-            const float4 f2 = *reinterpret_cast<const float4*>(cst + 2 * 128 + jl0 + e);  // -rz2_j
-            const float4 f3 = *reinterpret_cast<const float4*>(cst + 3 * 128 + jl0 + e);  // gh_j
-            const float4 f4 = *reinterpret_cast<const float4*>(cst + 4 * 128 + jl0 + e);  // q_j
-            const float nr[4] = {f0.x, f0.y, f0.z, f0.w}, nc[4] = {f1.x, f1.y, f1.z, f1.w};
-            const float nrz[4] = {f2.x, f2.y, f2.z, f2.w}, gh[4] = {f3.x, f3.y, f3.z, f3.w};
-            const float qj[4] = {f4.x, f4.y, f4.z, f4.w};
-            float ms[4], mst[4], mz[4];
+            for (int e = 0; e < 32; e += 4) {
+              const float4 f0 = *reinterpret_cast<const float4*>(cst + 0 * 128 + jl0 + e);  // -r2_j
+              const float4 f1 = *reinterpret_cast<const float4*>(cst + 1 * 128 + jl0 + e);  // -c2_j
+              const float4 f2 = *reinterpret_cast<const float4*>(cst + 2 * 128 + jl0 + e);  // -rz2_j | B_j
+              const float4 f3 = *reinterpret_cast<const float4*>(cst + 3 * 128 + jl0 + e);  // gh_j
+              const float4 f4 = *reinterpret_cast<const float4*>(cst + 4 * 128 + jl0 + e);  // q_j | D_j q_j
+              const float4 f5 = kFast ? *reinterpret_cast<const float4*>(cst + 5 * 128 + jl0 + e)  // E_j
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float nr[4] = {f0.x, f0.y, f0.z, f0.w}, nc[4] = {f1.x, f1.y, f1.z, f1.w};
+              const float zc[4] = {f2.x, f2.y, f2.z, f2.w}, gh[4] = {f3.x, f3.y, f3.z, f3.w};
+              const float qc[4] = {f4.x, f4.y, f4.z, f4.w}, ej[4] = {f5.x, f5.y, f5.z, f5.w};
+              float ms[4], mst[4], mz[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float a = vs[e + u], bt = vt[e + u];
-              const float z2 = vz[e + u] * cZ2;
-              const float e1 = ex2f(fmaf(a, cS2, -r2_i));     // softmax_row(S)_ij
-              const float e2 = ex2f(fmaf(a, cS2, nc[u]));     // softmax_col(S)_ij
-              const float e3 = ex2f(fmaf(bt, cS2, nr[u]));    // softmax_row(S)_ji
-              const float e4 = ex2f(fmaf(bt, cS2, -c2_i));    // softmax_col(S)_ji
-              const float P = ex2f(z2 - rz2_i), Pt = ex2f(z2 + nrz[u]);
-              const float dS = fmaf(-2.f, P, fmaf(e2, qj[u], e1));    // 2B dS_ij
-              const float dSt = fmaf(-2.f, Pt, fmaf(e4, q_i, e3));    // 2B dS_ji
-              const float G = fmaf(a, m2cS2, r2_i - nc[u]);           // 2B G_ij log2(e)
-              const float Gt = fmaf(bt, m2cS2, c2_i - nr[u]);         // 2B G_ji log2(e)
-              const float dZs = fmaf(P, G - gh_i, Pt * (Gt - gh[u]));
-              ms[u] = dS * wS;
-              mst[u] = dSt * wS;
-              mz[u] = dZs * wZ;
+              for (int u = 0; u < 4; ++u) {
+                const float a = vs[e + u], bt = vt[e + u];
+                const float z2 = vz[e + u] * cZ2;
+                const float e1 = ex2f(fmaf(a, cS2, -r2_i));     // softmax_row(S)_ij
+                const float e3 = ex2f(fmaf(bt, cS2, nr[u]));    // softmax_row(S)_ji
+                const float P = ex2f(z2 - rz2_i);
+                float Pt, dS, dSt;
+                if (kFast) {  // three exponentials; the other three are products of per-row / per-column factors
+                  Pt = P * (fA_i * zc[u]);
+                  dS = fmaf(e1, fmaf(fC_i, qc[u], 1.f), -2.f * P);        // 2B dS_ij
+                  dSt = fmaf(e3, fmaf(ej[u], fFQ_i, 1.f), -2.f * Pt);     // 2B dS_ji
+                } else {
+                  const float e2 = ex2f(fmaf(a, cS2, nc[u]));   // softmax_col(S)_ij
+                  const float e4 = ex2f(fmaf(bt, cS2, -c2_i));  // softmax_col(S)_ji
+                  Pt = ex2f(z2 + zc[u]);
+                  dS = fmaf(-2.f, P, fmaf(e2, qc[u], e1));
+                  dSt = fmaf(-2.f, Pt, fmaf(e4, q_i, e3));
+                }
+                const float G = fmaf(a, m2cS2, r2_i - nc[u]);           // 2B G_ij log2(e)
+                const float Gt = fmaf(bt, m2cS2, c2_i - nr[u]);         // 2B G_ji log2(e)
+                const float dZs = fmaf(P, G - gh_i, Pt * (Gt - gh[u]));
+                ms[u] = dS * wS;
+                mst[u] = dSt * wS;
+                mz[u] = dZs * wZ;
+              }
+#pragma unroll
+              for (int u = 0; u < 4; u += 2) {
+                __half2 x = __floats2half2_rn(ms[u], ms[u + 1]), y = __floats2half2_rn(mst[u], mst[u + 1]);
+                __half2 w = __floats2half2_rn(mz[u], mz[u + 1]);
+                wSp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&x);
+                wStp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&y);
+                wZp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&w);
+              }
             }
-#pragma unroll
-            for (int u = 0; u < 4; u += 2) {
-              __half2 x = __floats2half2_rn(ms[u], ms[u + 1]), y = __floats2half2_rn(mst[u], mst[u + 1]);
-              __half2 w = __floats2half2_rn(mz[u], mz[u + 1]);
-              wSp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&x);
-              wStp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&y);
-              wZp[(e + u) >> 1] = *reinterpret_cast<uint32_t*>(&w);
-            }
-          }
+          };
+          if (fast) weights32(std::true_type{}); else weights32(std::false_type{});
           // The single weight buffer is used by column half 0, then half 1, of every tile: wait until
           // the gradient MMAs of the preceding half have drained it.  One barrier per half keeps every
           // waiter at most one phase behind, which the parity test needs.
@@ -716,7 +751,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       // ---- end of job: write this job's partial results
       if (PHASE == kStats || PHASE == kRowLoss) {
         // four threads hold pieces of row m (lane half n1 x column half h): combine through shared memory
-        float* scratch = reinterpret_cast<float*>(sbase + kOffW);  // [3 partners][7][64]
+        float* scratch = consts;  // [3 partners][7][64] floats; the column constants are dead once the tile loop is over
         OnlineLse2 lS, lSt, lZ;  // log2-domain (max, sum) pairs
         lS.m = mS * cS2; lS.s = sS; lSt.m = mSt * cS2; lSt.s = sSt; lZ.m = mZ * cZ2; lZ.s = sZ;
         float aZ = aPS;          // travels with lZ: rescaled by the same factors
@@ -854,24 +889,27 @@ __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ v, 
 // The largest possible weight is mapped just below 2^15 so that nothing overflows fp16 and the
 // small weights of the soft-target regime stay in the normal range.
 __global__ void __launch_bounds__(1024) wscale_kernel(const float* __restrict__ r, const float* __restrict__ c,
-                                                      const float* __restrict__ q, int B,
+                                                      const float* __restrict__ rz, const float* __restrict__ q, int B,
                                                       const float* __restrict__ scale,
                                                       const float* __restrict__ norm_i,
                                                       const float* __restrict__ norm_t, float inv_tau, float tau,
                                                       float* __restrict__ out) {
-  __shared__ float sm[6][32];
-  float v[6] = {-INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f};
+  // maxima: r, c, q, (unused), ||I||, ||T||, rz, -r, -c, -rz  (the negated ones give the minima)
+  __shared__ float sm[10][32];
+  float v[10] = {-INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
-    v[0] = fmaxf(v[0], r[i]); v[1] = fmaxf(v[1], c[i]); v[2] = fmaxf(v[2], q[i]);
+    const float ri = r[i], ci = c[i], zi = rz[i];
+    v[0] = fmaxf(v[0], ri); v[1] = fmaxf(v[1], ci); v[2] = fmaxf(v[2], q[i]);
     v[4] = fmaxf(v[4], norm_i[i]); v[5] = fmaxf(v[5], norm_t[i]);
+    v[6] = fmaxf(v[6], zi); v[7] = fmaxf(v[7], -ri); v[8] = fmaxf(v[8], -ci); v[9] = fmaxf(v[9], -zi);
   }
-  for (int k = 0; k < 6; ++k) {
+  for (int k = 0; k < 10; ++k) {
     v[k] = warp_max(v[k]);
     if ((threadIdx.x & 31) == 0) sm[k][threadIdx.x >> 5] = v[k];
   }
   __syncthreads();
   if (threadIdx.x < 32) {
-    for (int k = 0; k < 6; ++k) v[k] = warp_max(sm[k][threadIdx.x]);
+    for (int k = 0; k < 10; ++k) v[k] = warp_max(sm[k][threadIdx.x]);
     if (threadIdx.x == 0) {
       v[3] = scale[1];  // 1 / s: weights multiply the scaled plane
       const float gmax = fmaxf(v[0] + v[1] + 2.f * v[4] * v[5] * inv_tau, 1.f);
@@ -883,6 +921,16 @@ __global__ void __launch_bounds__(1024) wscale_kernel(const float* __restrict__ 
       int k = 15 - e;
       k = k < -60 ? -60 : (k > 60 ? 60 : k);
       out[0] = ldexpf(1.f, k);
+      // Fast exponentials: with every row/column statistic within 60 binades of each other,
+      // e^{S - c_j} = e^{S - r_i} * 2^{r2_i - M} * 2^{M - c2_j} (and likewise for P_ji) can neither
+      // overflow nor lose a term that matters (an underflowed factor implies a term below 2^-66).
+      const float kL2e = 1.4426950408889634f;
+      const float hi_rc = fmaxf(v[0], v[1]), lo_rc = -fmaxf(v[7], v[8]);
+      const float hi_z = v[6], lo_z = -v[9];
+      const bool fast = (hi_rc - lo_rc) * kL2e <= 60.f && (hi_z - lo_z) * kL2e <= 60.f;
+      out[1] = fast ? 1.f : 0.f;
+      out[2] = 0.5f * (hi_rc + lo_rc) * kL2e;  // M_rc, log2 units
+      out[3] = 0.5f * (hi_z + lo_z) * kL2e;    // M_z
     }
   }
 }
@@ -1111,7 +1159,7 @@ int bwd(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad
   const char* pbase = static_cast<const char*>(p.planes_all);
   float* wsc = wscale_slot(ws, p.b, p.B, p.D);
   MC_REQUIRE(p.planes_all != nullptr, MC_ERR_BAD_ARG, "clip_bwd(tc): planes buffer missing");
-  wscale_kernel<<<1, 1024, 0, st>>>(s.r, s.c, s.q, p.B, reinterpret_cast<const float*>(pbase + l.off_hdr) + 1,
+  wscale_kernel<<<1, 1024, 0, st>>>(s.r, s.c, s.rz, s.q, p.B, reinterpret_cast<const float*>(pbase + l.off_hdr) + 1,
                                    reinterpret_cast<const float*>(pbase + l.off_norm_i),
                                    reinterpret_cast<const float*>(pbase + l.off_norm_t), 1.f / p.tau, p.tau, wsc);
   MC_LAUNCH_CHECK();

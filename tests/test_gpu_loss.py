@@ -66,6 +66,23 @@ def test_loss_vs_oracle_seeded(B, scale, tau, mode):
         assert rel_err(dT, ref_dT) < gt
 
 
+@pytest.mark.parametrize("mode", ALL_MODES)
+def test_loss_wide_norm_spread(mode):
+    """Rows of very different norms: the row/column statistics span hundreds of binades, which
+    switches the gradient sweep from its factored-exponential path to the six-exponential one."""
+    B = 384
+    g = torch.Generator().manual_seed(5)
+    w = torch.logspace(-1.3, 0.0, B)[torch.randperm(B, generator=g)].unsqueeze(1)
+    I = loss_ref.make_embeddings(B, 256, seed=12, scale=1.0) * w
+    T = loss_ref.make_embeddings(B, 256, seed=13, scale=1.0) * w
+    ref_loss, ref_dI, ref_dT, stats = loss_ref.clip_loss_closed_form(I.numpy(), T.numpy(), 1.0)
+    assert (stats["row_lse_z"].max() - stats["row_lse_z"].min()) * 1.4427 > 60
+    loss, dI, dT = _run(I, T, 1.0, mode)
+    lt, gt = _tols(mode)
+    assert abs(loss.item() - ref_loss) <= lt * abs(ref_loss)
+    assert rel_err(dI, ref_dI) < gt and rel_err(dT, ref_dT) < gt
+
+
 @pytest.mark.parametrize("mode", FP32_MODES)
 def test_loss_other_dims(mode):
     """D is a constructor argument of the heads (modules.py:59): not only 256."""
