@@ -11,7 +11,9 @@ materialised, and the tensor-core roofline is only meaningful at that size (C2's
 3.8 GFLOP, launch-bound problem).  The global batch is FIXED as N grows ("strong" scaling): rank r
 owns rows [r B/N, (r+1) B/N).  A step = one forward + backward of the loss over the whole global
 batch from fp32 embeddings already in HBM: stage operands, row/col statistics sweep, row-loss
-sweep, gradient sweep (+ NCCL all-gathers when N > 1).  At N = 1 the line also carries the C2
+sweep, gradient sweep.  When N > 1 the exchange steps run over mapped peer memory by default
+(--transport peer: the embedding all-gather is fused into the operand staging, statistics are pushed
+by our own kernels; --transport nccl keeps the torch.distributed all-gathers).  At N = 1 the line also carries the C2
 latency and C5 MAE numbers under "extra".
 
 e2e is the same step through the C-ABI entry point that takes HOST buffers
@@ -48,6 +50,8 @@ def parse():
     ap.add_argument("--mode", default="auto")
     ap.add_argument("--batch", type=int, default=0, help="global batch (default: 32768 for c4, 1024 for c2)")
     ap.add_argument("--cpu-sample-batch", type=int, default=4096)
+    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: peer = our kernels over mapped peer memory (default), nccl = torch.distributed all-gathers")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -156,7 +160,7 @@ def run_reference(args):
     if rank != 0:
         return
     B = args.batch or (32768 if args.workload == "c4" else 1024)
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)  # exactly K timed steps after W warm-ups
     cb = cpu_reference_leg(args, B, steps, warmup)
     line = {"impl": "reference", "metric": "contrastive loss fwd+bwd samples/s", "value": cb["value"],
             "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
@@ -246,6 +250,31 @@ class Phases:
         return [e[i].elapsed_time(e[i + 1]) for i in range(4)]
 
 
+class PeerPhases:
+    """Same step over the peer-memory transport (mae_clip_b200/dist.py PeerStep): every exchange is a
+    kernel of libmae_clip_b200.so on this stream; the embedding all-gather is fused into the staging."""
+
+    def __init__(self, B, b, rank, mode, device):
+        from mae_clip_b200.dist import PeerStep
+        from mae_clip_b200.peer import get_exchange
+        self.step_impl = PeerStep(get_exchange(b, D_EMB), mode)
+        self.part = self.dI = self.dT = None
+        self.ev = []
+
+    def step(self, I_loc, T_loc, record=False):
+        ev = [] if record else None
+        loss, saved = self.step_impl.forward(I_loc, T_loc, 1.0, ev)
+        self.dI, self.dT = self.step_impl.backward(saved, 1.0, None, ev)
+        self.part = loss.reshape(1)
+        if record:
+            self.ev = ev
+        return self.part
+
+    def phase_ms(self):
+        e = self.ev  # start, staged, stats exchanged, row loss exchanged, gradients
+        return [e[i].elapsed_time(e[i + 1]) for i in range(4)]
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -292,11 +321,19 @@ def run_b200(args):
         dist.all_gather_into_tensor(buf.view(-1), x.contiguous().view(-1))
         return buf.permute(1, 0, 2).reshape(k, B).contiguous()
 
-    ph = Phases(B, b, rank * b, mode, dev)
+    transport = args.transport
+    if transport == "auto":
+        transport = "peer" if (world > 1 and mode != "simt_fp32" and b % 128 == 0) else "nccl"
+    if world == 1:
+        transport = "none"
+    ph = PeerPhases(B, b, rank, mode, dev) if transport == "peer" else Phases(B, b, rank * b, mode, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def one_step(record=False):
-        I_all, T_all = gather_rows(I_loc), gather_rows(T_loc)
+    def one_step(record=False, I=None, T=None):
+        I, T = (I_loc if I is None else I), (T_loc if T is None else T)
+        if transport == "peer":
+            return ph.step(I, T, record=record)
+        I_all, T_all = gather_rows(I), gather_rows(T)
         return ph.step(I_all, T_all, gather_vec if world > 1 else None, record=record)
 
     def barrier():
@@ -356,7 +393,7 @@ def run_b200(args):
         def e2e_step():
             Il = host_I.to(dev, non_blocking=True)
             Tl = host_T.to(dev, non_blocking=True)
-            part = ph.step(gather_rows(Il), gather_rows(Tl), gather_vec)
+            part = one_step(False, Il, Tl)
             out_dI.copy_(ph.dI, non_blocking=True)
             out_dT.copy_(ph.dT, non_blocking=True)
             out_loss.copy_(part, non_blocking=True)
@@ -399,7 +436,8 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": {"simt_fp32": "fp32", "tc_f16x3": "fp32 (fp16 hi+lo split operands, 3 tcgen05 passes, fp32 accumulate)",
                       "tc_f16": "fp16 operands, fp32 accumulate"}[mode],
-            "data": "synthetic", "config": workload_config(args, B, mode), "loss": loss_val,
+            "data": "synthetic", "config": dict(workload_config(args, B, mode), transport=(
+                transport + "-" + ph.step_impl.exchange_mode if transport == "peer" else transport)), "loss": loss_val,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": emax.item() / e_steps},
             "gpu_launches": int(launches),
@@ -423,6 +461,9 @@ def run_b200(args):
             line["extra"] = extras(dev, mode, peaks)
         print(json.dumps(line))
     if world > 1:
+        if transport == "peer":
+            from mae_clip_b200 import peer
+            peer.close_all()
         dist.destroy_process_group()
 
 

@@ -103,6 +103,30 @@ size_t mc_clip_planes_bytes(int B, int D, int mode);
 int mc_clip_prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row_offset,
                     int mode, void* planes_all, void* stream);
 
+/* Peer-memory staging for the row-sharded loss (one process per GPU; tcgen05 modes only): the
+ * embedding all-gather is fused into prepare.  mc_clip_amax() reduces this rank's shards to the
+ * bit pattern of their largest magnitude (and optionally copies them into the exchange region);
+ * after every rank's value has been published into `amax_slots` (world words, see
+ * mc_peer_publish / mc_peer_barrier) mc_clip_prepare_peers() pulls each global row from its
+ * owner - I_peers_host[q] / T_peers_host[q] are HOST arrays of `world` device pointers to rank
+ * q's (b, D) fp32 shards, mapped on this device - and writes the local planes of all world*b rows.
+ * I_all / T_all of the three phases below may then be NULL.
+ * mc_clip_push_shards() is the push form of the same exchange: this rank's shards are stored into
+ * rows [rank*b, (rank+1)*b) of EVERY rank's (world*b, D) fp32 image (I_all_dst_host[q] /
+ * T_all_dst_host[q]: HOST arrays of the images' base pointers) with posted NVLink stores while the
+ * local amax is reduced; the last block publishes it into amax_slots_host[q][rank].  `scratch`:
+ * two zero-initialised device words private to this rank (re-armed by the kernel).  After a
+ * barrier, mc_clip_prepare_peers() is called with every I_peers_host[q] pointing into the LOCAL
+ * image. */
+int mc_clip_push_shards(const float* I_loc, const float* T_loc, int b, int D, int rank, int world,
+                        float* const* I_all_dst_host, float* const* T_all_dst_host,
+                        unsigned int* const* amax_slots_host, unsigned int* scratch, void* stream);
+int mc_clip_amax(const float* I_loc, const float* T_loc, int b, int D, float* I_copy, float* T_copy,
+                 unsigned int* amax_bits, void* stream);
+int mc_clip_prepare_peers(const float* const* I_peers_host, const float* const* T_peers_host, int world,
+                          int b, int D, int mode, const unsigned int* amax_slots, void* planes_all,
+                          void* stream);
+
 int mc_clip_stats(const float* I_all, const float* T_all, const void* planes_all, int b, int B,
                   int D, int row_offset, float tau, int mode, float* row_lse_s_loc,
                   float* col_lse_s_loc, float* row_lse_z_loc, float* row_ps_loc, void* ws,
@@ -131,6 +155,33 @@ size_t mc_clip_loss_host_workspace_bytes(int B, int D, int mode);
 int mc_clip_loss_fwd_bwd_host(const float* I_host, const float* T_host, int B, int D, float tau,
                               int mode, float* loss_host, float* dI_host, float* dT_host,
                               void* dws, size_t dws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Peer memory (SURVEY.md section 8 e; the reference is single-process).  Each rank allocates one
+ * exchange region, ships its 64-byte CUDA IPC handle to the other local ranks (any transport;
+ * mae_clip_b200/dist.py uses torch.distributed) and maps theirs.  The kernels then load / store
+ * peer memory directly over NVLink / NVSwitch:
+ *   mc_peer_barrier  all ranks: epoch = ++*epoch_counter (a private device word, zero at
+ *                    creation; every rank issues the same sequence of barriers, so no launch
+ *                    argument depends on the step and the step can be graph-captured);
+ *                    flag[rank] := epoch in every peer's flag array (MC_PEER_MAX_WORLD
+ *                    zero-initialised words at flag_ptrs_host[q]), then wait until every peer
+ *                    wrote the same epoch here.  A peer that does not arrive within timeout_s
+ *                    (<= 0: 20 s) traps the kernel.
+ *   mc_peer_publish  dst[q][dst_offset + kk*dst_stride + i] = src[kk*src_stride + i] (32-bit
+ *                    words, kk < k, i < n) for every peer q < world.
+ * mc_peer_alloc zero-fills the region and synchronises the device (set-up time, not the hot path).
+ * ------------------------------------------------------------------------- */
+#define MC_PEER_HANDLE_BYTES 64
+#define MC_PEER_MAX_WORLD 16
+int mc_peer_alloc(size_t bytes, void** dev_ptr_out, void* ipc_handle_out /* MC_PEER_HANDLE_BYTES */);
+int mc_peer_open(const void* ipc_handle, void** dev_ptr_out);
+int mc_peer_close(void* dev_ptr);
+int mc_peer_free(void* dev_ptr);
+int mc_peer_barrier(void* const* flag_ptrs_host, int rank, int world, unsigned int* epoch_counter,
+                    double timeout_s, void* stream);
+int mc_peer_publish(const void* src, int k, int n, int64_t src_stride, void* const* dst_ptrs_host,
+                    int64_t dst_stride, int64_t dst_offset, int world, void* stream);
 
 /* ---------------------------------------------------------------------------
  * L1-L2  ProjectionHead                                    modules.py:55-76

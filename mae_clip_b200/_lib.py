@@ -36,6 +36,15 @@ SIGNATURES = {
     "mc_clip_loss_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mc_clip_planes_bytes": (_sz, [_i, _i, _i]),
     "mc_clip_prepare": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "mc_clip_amax": (_i, [_p, _p, _i, _i, _p, _p, _p, _p]),
+    "mc_clip_push_shards": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "mc_clip_prepare_peers": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "mc_peer_alloc": (_i, [_sz, _p, _p]),
+    "mc_peer_open": (_i, [_p, _p]),
+    "mc_peer_close": (_i, [_p]),
+    "mc_peer_free": (_i, [_p]),
+    "mc_peer_barrier": (_i, [_p, _i, _i, _p, C.c_double, _p]),
+    "mc_peer_publish": (_i, [_p, _i, _i, _i64, _p, _i64, _i64, _i, _p]),
     "mc_clip_stats": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "mc_clip_rowloss": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mc_clip_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,

@@ -7,7 +7,6 @@ namespace mc {
 
 static int check_problem(const char* who, const float* I_all, const float* T_all, int b, int B, int D,
                          int row_offset, float tau, int mode) {
-  MC_REQUIRE(I_all && T_all, MC_ERR_BAD_ARG, "%s: null embedding pointer", who);
   MC_REQUIRE(b > 0 && B > 0 && D > 0 && b <= B, MC_ERR_BAD_ARG, "%s: bad sizes b=%d B=%d D=%d", who,
              b, B, D);
   MC_REQUIRE(row_offset >= 0 && row_offset + b <= B, MC_ERR_BAD_ARG, "%s: row_offset %d out of range",
@@ -15,6 +14,10 @@ static int check_problem(const char* who, const float* I_all, const float* T_all
   MC_REQUIRE(tau > 0.f, MC_ERR_BAD_ARG, "%s: temperature must be positive (got %g)", who, tau);
   MC_REQUIRE(mode >= MC_GEMM_SIMT_FP32 && mode <= MC_GEMM_TC_F16, MC_ERR_BAD_ARG, "%s: bad mode %d",
              who, mode);
+  // the tcgen05 engine reads the staged planes only; the fp32 embeddings may then be absent
+  // (peer-memory staging never assembles them)
+  MC_REQUIRE((I_all && T_all) || (mode != MC_GEMM_SIMT_FP32 && tc::supported(D)), MC_ERR_BAD_ARG,
+             "%s: null embedding pointer", who);
   return MC_OK;
 }
 
@@ -70,6 +73,34 @@ int mc_clip_prepare(const float* I_loc, const float* T_loc, int b, int B, int D,
   MC_REQUIRE(planes_all, MC_ERR_BAD_ARG, "clip_prepare: planes_all is null");
   return tc::prepare(I_loc, T_loc, b, B, D, row_offset, mode, planes_all,
                      static_cast<cudaStream_t>(stream));
+}
+
+int mc_clip_amax(const float* I_loc, const float* T_loc, int b, int D, float* I_copy, float* T_copy,
+                 unsigned int* amax_bits, void* stream) {
+  MC_ARCH_GUARD();
+  MC_REQUIRE(I_loc && T_loc && amax_bits && b > 0 && D > 0, MC_ERR_BAD_ARG, "clip_amax: bad argument");
+  return tc::amax_copy(I_loc, T_loc, b, D, I_copy, T_copy, amax_bits, static_cast<cudaStream_t>(stream));
+}
+
+int mc_clip_push_shards(const float* I_loc, const float* T_loc, int b, int D, int rank, int world,
+                        float* const* I_all_dst_host, float* const* T_all_dst_host,
+                        unsigned int* const* amax_slots_host, unsigned int* scratch, void* stream) {
+  MC_ARCH_GUARD();
+  MC_REQUIRE(I_loc && T_loc && I_all_dst_host && T_all_dst_host && amax_slots_host && scratch && b > 0 && D > 0,
+             MC_ERR_BAD_ARG, "clip_push_shards: bad argument");
+  return tc::push_shards(I_loc, T_loc, b, D, rank, world, I_all_dst_host, T_all_dst_host, amax_slots_host, scratch,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int mc_clip_prepare_peers(const float* const* I_peers_host, const float* const* T_peers_host, int world, int b,
+                          int D, int mode, const unsigned int* amax_slots, void* planes_all, void* stream) {
+  MC_ARCH_GUARD();
+  MC_REQUIRE(I_peers_host && T_peers_host && amax_slots && planes_all && b > 0 && D > 0, MC_ERR_BAD_ARG,
+             "clip_prepare_peers: bad argument");
+  MC_REQUIRE(mode == MC_GEMM_TC_F16X3 || mode == MC_GEMM_TC_F16, MC_ERR_UNSUPPORTED,
+             "clip_prepare_peers: peer staging feeds the tcgen05 engine only (mode %d)", mode);
+  return tc::prepare_peers(I_peers_host, T_peers_host, world, b, D, mode, amax_slots, planes_all,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int mc_clip_stats(const float* I_all, const float* T_all, const void* planes_all, int b, int B,

@@ -36,6 +36,12 @@ size_t workspace_bytes(int b, int B, int D, int mode);
 size_t planes_bytes(int B, int D, int mode);
 int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row_offset, int mode,
             void* planes_all, cudaStream_t st);
+int amax_copy(const float* I_loc, const float* T_loc, int b, int D, float* I_copy, float* T_copy,
+              unsigned int* amax_bits, cudaStream_t st);
+int push_shards(const float* I_loc, const float* T_loc, int b, int D, int rank, int world, float* const* I_dst,
+                float* const* T_dst, unsigned int* const* amax_slots, unsigned int* scratch, cudaStream_t st);
+int prepare_peers(const float* const* I_peers, const float* const* T_peers, int world, int b, int D, int mode,
+                  const unsigned int* amax_slots, void* planes_all, cudaStream_t st);
 int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
           size_t ws_bytes, cudaStream_t st);
 int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* ps_loc, float* g_loc,

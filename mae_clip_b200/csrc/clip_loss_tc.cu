@@ -111,69 +111,6 @@ __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ I, 
   if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(amax_bits, __float_as_uint(a));
 }
 
-__global__ void __launch_bounds__(256) stage_planes_kernel(const float* __restrict__ I_loc,
-                                                           const float* __restrict__ T_loc, int b, int B,
-                                                           int Bp, int D, int row_offset, int rows_total,
-                                                           __half* __restrict__ Xh, __half* __restrict__ Xl,
-                                                           float* __restrict__ hdr, float* __restrict__ norm_i,
-                                                           float* __restrict__ norm_t) {
-  const int wrow = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (wrow >= rows_total) return;
-  // One power-of-two scale for both matrices, bringing the largest magnitude into [1, 2): exact in
-  // fp32; hi keeps 11 significant bits of an element, hi + lo is exact to ~2^-25 of the global maximum.
-  const float amax = __uint_as_float(reinterpret_cast<const unsigned int*>(hdr)[0]);
-  float s = 1.f;
-  if (amax > 0.f && amax < INFINITY) {
-    int e;
-    frexpf(amax, &e);        // amax = f * 2^e, f in [0.5, 1)
-    s = ldexpf(1.f, 1 - e);  // amax * s in [1, 2)
-  }
-  if (wrow == 0 && lane == 0) { hdr[1] = s; hdr[2] = 1.f / s; hdr[3] = (1.f / s) * (1.f / s); }
-  // rows [0, b): local rows; rows [b, rows_total): zero padding rows B .. Bp-1
-  const bool pad = wrow >= b;
-  const int gi = pad ? (B + (wrow - b)) : (row_offset + wrow);
-  const int K2 = 2 * D;
-  __half* xh = Xh + (size_t)gi * K2;
-  __half* xl = Xl + (size_t)gi * K2;
-  if (pad) {
-    for (int k = lane; k < K2; k += 32) { xh[k] = __float2half_rn(0.f); xl[k] = __float2half_rn(0.f); }
-    if (lane == 0) { norm_i[gi] = 0.f; norm_t[gi] = 0.f; }
-    return;
-  }
-  const float* pi = I_loc + (size_t)wrow * D;
-  const float* pt = T_loc + (size_t)wrow * D;
-  float ni = 0.f, nt = 0.f;
-  for (int k = lane; k < K2; k += 32) {
-    const float raw = (k < D ? pi[k] : pt[k - D]);
-    if (k < D) ni = fmaf(raw, raw, ni); else nt = fmaf(raw, raw, nt);
-    const float x = raw * s;
-    const __half h = __float2half_rn(x);
-    xh[k] = h;
-    xl[k] = __float2half_rn(x - __half2float(h));
-  }
-  ni = warp_sum(ni);
-  nt = warp_sum(nt);
-  if (lane == 0) { norm_i[gi] = sqrtf(ni); norm_t[gi] = sqrtf(nt); }
-}
-
-// XhT[k][j] = Xh[j][k] for j in [j_begin, j_end), 64 x 64 tiles through shared memory
-__global__ void __launch_bounds__(256) transpose_hi_kernel(const __half* __restrict__ Xh,
-                                                           __half* __restrict__ XhT, int Bp, int K2, int j_begin,
-                                                           int j_end) {
-  __shared__ __half tile[64][66];
-  const int j0 = j_begin + blockIdx.x * 64, k0 = blockIdx.y * 64;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
-  for (int r = ty; r < 64; r += 4) {
-    int j = j0 + r;
-    tile[r][tx] = (j < j_end) ? Xh[(size_t)j * K2 + k0 + tx] : __float2half_rn(0.f);
-  }
-  __syncthreads();
-  for (int r = ty; r < 64; r += 4) {
-    int j = j0 + tx;
-    if (j < j_end) XhT[(size_t)(k0 + r) * Bp + j] = tile[tx][r];
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // the pair kernel
 // ------------------------------------------------------------------------------------------
@@ -1026,6 +963,241 @@ static float* wscale_slot(void* ws, int b, int B, int D) {
   return reinterpret_cast<float*>(static_cast<char*>(ws) + workspace_bytes(b, B, D, 0) - 256);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Peer-memory staging (row-sharded loss, one process per GPU): the embedding all-gather is fused
+// into the operand staging.  Rank q keeps its (b, D) fp32 shards in a region every peer has
+// mapped over NVLink; each rank pulls every row straight from its owner with 16-byte loads while
+// it writes its local fp16 hi / lo planes, so the fp32 global batch is never assembled in HBM and
+// no collective library call sits between the towers and the first sweep.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+struct PeerRows {
+  const float* I[kMaxPeers];
+  const float* T[kMaxPeers];
+};
+
+// local part of the global scale: largest magnitude of this rank's shards (+ optional copy of the
+// shards into the exchange region, so the towers' output is read once)
+__global__ void __launch_bounds__(256) amax_copy_kernel(const float4* __restrict__ I, const float4* __restrict__ T,
+                                                        size_t n4, float4* __restrict__ I_copy,
+                                                        float4* __restrict__ T_copy,
+                                                        unsigned int* __restrict__ amax_bits) {
+  float a = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 x = I[i], y = T[i];
+    if (I_copy) I_copy[i] = x;
+    if (T_copy) T_copy[i] = y;
+    a = fmaxf(a, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+    a = fmaxf(a, fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
+  }
+  a = warp_max(a);
+  if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(amax_bits, __float_as_uint(a));
+}
+
+// Fused staging: a block owns 32 global rows.  Each warp pulls four rows of [I_i || T_i] (16-byte
+// loads, all in flight before the first use: they may cross NVLink), writes the scaled fp16 hi / lo
+// planes and the row norms, and parks hi in a shared tile from which the block writes its
+// 32-column slice of the transposed plane (64-byte runs) - fp32 rows are read once and the hi
+// plane is never re-read.  Row gi belongs to rank gi / b (src.I[q] / src.T[q] = rank q's rows).
+template <int D>
+__global__ void __launch_bounds__(256) stage_fused_kernel(PeerRows src, int b, int B, int Bp,
+                                                          const unsigned int* amax_slots, int nslots,
+                                                          __half* __restrict__ Xh, __half* __restrict__ Xl,
+                                                          __half* __restrict__ XhT, float* hdr,
+                                                          float* __restrict__ norm_i, float* __restrict__ norm_t) {
+  constexpr int K2 = 2 * D, kVec = K2 / 128, kRows = 32, kPitch = K2 + 2;  // pitch in halfs: odd word count
+  __shared__ __align__(16) __half tile[kRows * kPitch];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * kRows;
+  unsigned int abits = 0;
+  for (int q = 0; q < nslots; ++q) abits = max(abits, amax_slots[q]);
+  const float amax = __uint_as_float(abits);
+  float s = 1.f;
+  if (amax > 0.f && amax < INFINITY) {
+    int e;
+    frexpf(amax, &e);        // amax = f * 2^e, f in [0.5, 1)
+    s = ldexpf(1.f, 1 - e);  // amax * s in [1, 2)
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    reinterpret_cast<unsigned int*>(hdr)[0] = abits;
+    hdr[1] = s; hdr[2] = 1.f / s; hdr[3] = (1.f / s) * (1.f / s);
+  }
+  float4 v[4][kVec];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gi = j0 + warp * 4 + i;
+    if (gi < B) {
+      const int q = gi / b, lr = gi - q * b;
+      const float4* pi = reinterpret_cast<const float4*>(src.I[q] + (size_t)lr * D);
+      const float4* pt = reinterpret_cast<const float4*>(src.T[q] + (size_t)lr * D);
+#pragma unroll
+      for (int u = 0; u < kVec; ++u) {
+        const int c = lane + 32 * u;
+        v[i][u] = (c < D / 4) ? pi[c] : pt[c - D / 4];
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < kVec; ++u) v[i][u] = make_float4(0.f, 0.f, 0.f, 0.f);  // zero padding rows B .. Bp-1
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = warp * 4 + i, gi = j0 + r;
+    if (gi >= Bp) continue;
+    uint2* xh = reinterpret_cast<uint2*>(Xh + (size_t)gi * K2);
+    uint2* xl = reinterpret_cast<uint2*>(Xl + (size_t)gi * K2);
+    uint32_t* trow = reinterpret_cast<uint32_t*>(tile + r * kPitch);
+    float ni = 0.f, nt = 0.f;
+#pragma unroll
+    for (int u = 0; u < kVec; ++u) {
+      const int c = lane + 32 * u;
+      const float raw[4] = {v[i][u].x, v[i][u].y, v[i][u].z, v[i][u].w};
+      __half h[4], l[4];
+      float nn = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        nn = fmaf(raw[e], raw[e], nn);
+        const float x = raw[e] * s;
+        h[e] = __float2half_rn(x);
+        l[e] = __float2half_rn(x - __half2float(h[e]));
+      }
+      if (c < D / 4) ni += nn; else nt += nn;
+      __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
+      __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
+      const uint32_t a0 = *reinterpret_cast<uint32_t*>(&h01), a1 = *reinterpret_cast<uint32_t*>(&h23);
+      xh[c] = make_uint2(a0, a1);
+      xl[c] = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+      trow[2 * c] = a0;
+      trow[2 * c + 1] = a1;
+    }
+    ni = warp_sum(ni);
+    nt = warp_sum(nt);
+    if (lane == 0) { norm_i[gi] = sqrtf(ni); norm_t[gi] = sqrtf(nt); }
+  }
+  __syncthreads();
+  // transposed slice: XhT[k][j0 .. j0+32).  A warp instruction covers two k rows: lanes 0-15 -> k, 16-31 -> k+1,
+  // each lane the pair of rows (2l, 2l+1); the odd word pitch keeps the column reads conflict-free.
+  if (j0 + kRows > Bp) return;  // Bp is a multiple of 128: never taken, keeps the stores in range by construction
+  const int l16 = lane & 15, kk = lane >> 4;
+  for (int k = warp * 2 + kk; k < K2; k += 16) {
+    const __half lo = tile[(2 * l16) * kPitch + k], hi = tile[(2 * l16 + 1) * kPitch + k];
+    __half2 pr = __halves2half2(lo, hi);
+    *reinterpret_cast<uint32_t*>(XhT + (size_t)k * Bp + j0 + 2 * l16) = *reinterpret_cast<uint32_t*>(&pr);
+  }
+}
+
+// Push variant of the exchange: every rank writes its shards into ALL ranks' (B, D) fp32 images
+// of the global batch (posted NVLink stores, no round trip) while it reduces its local amax; the
+// last block to finish publishes that amax into every rank's slot and re-arms the scratch words.
+struct PushDst {
+  float* I[kMaxPeers];
+  float* T[kMaxPeers];
+  unsigned int* slots[kMaxPeers];
+};
+__global__ void __launch_bounds__(256) push_shards_kernel(const float4* __restrict__ I, const float4* __restrict__ T,
+                                                          size_t n4, size_t dst_off4, PushDst dst, int rank, int world,
+                                                          unsigned int* __restrict__ scratch /* {amax, blocks done} */) {
+  float a = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 x = I[i], y = T[i];
+    for (int q = 0; q < world; ++q) {
+      reinterpret_cast<float4*>(dst.I[q])[dst_off4 + i] = x;
+      reinterpret_cast<float4*>(dst.T[q])[dst_off4 + i] = y;
+    }
+    a = fmaxf(a, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+    a = fmaxf(a, fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
+  }
+  a = warp_max(a);
+  if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(scratch, __float_as_uint(a));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(scratch + 1, 1u) + 1u;
+    if (done == gridDim.x) {
+      __threadfence();
+      const unsigned int bits = atomicExch(scratch, 0u);  // read the final maximum and re-arm
+      scratch[1] = 0u;
+      for (int q = 0; q < world; ++q) dst.slots[q][rank] = bits;
+    }
+  }
+}
+
+static void launch_stage_fused(const PeerRows& src, int b, int B, int D, const PlanesLayout& l,
+                               const unsigned int* amax_slots, int nslots, __half* Xh, __half* Xl, __half* XhT,
+                               float* hdr, float* norm_i, float* norm_t, cudaStream_t st) {
+  const int blocks = l.Bp / 32;
+  if (D == 256)
+    stage_fused_kernel<256><<<blocks, 256, 0, st>>>(src, b, B, l.Bp, amax_slots, nslots, Xh, Xl, XhT, hdr, norm_i, norm_t);
+  else
+    stage_fused_kernel<128><<<blocks, 256, 0, st>>>(src, b, B, l.Bp, amax_slots, nslots, Xh, Xl, XhT, hdr, norm_i, norm_t);
+}
+
+int push_shards(const float* I_loc, const float* T_loc, int b, int D, int rank, int world, float* const* I_dst,
+                float* const* T_dst, unsigned int* const* amax_slots, unsigned int* scratch, cudaStream_t st) {
+  MC_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, MC_ERR_BAD_ARG,
+             "clip_push_shards: rank %d / world %d outside [1, %d]", rank, world, kMaxPeers);
+  MC_REQUIRE(D % 4 == 0 && aligned(I_loc, 16) && aligned(T_loc, 16), MC_ERR_ALIGN,
+             "clip_push_shards: shards must be 16-byte aligned with D %% 4 == 0");
+  PushDst dst;
+  for (int q = 0; q < kMaxPeers; ++q) { dst.I[q] = nullptr; dst.T[q] = nullptr; dst.slots[q] = nullptr; }
+  for (int q = 0; q < world; ++q) {
+    MC_REQUIRE(I_dst[q] && T_dst[q] && amax_slots[q] && aligned(I_dst[q], 16) && aligned(T_dst[q], 16), MC_ERR_ALIGN,
+               "clip_push_shards: destination of rank %d null or not 16-byte aligned", q);
+    dst.I[q] = I_dst[q]; dst.T[q] = T_dst[q]; dst.slots[q] = amax_slots[q];
+  }
+  const size_t n4 = (size_t)b * D / 4;
+  int nb = (int)((n4 + 255) / 256);
+  if (nb > num_sms() * 4) nb = num_sms() * 4;
+  push_shards_kernel<<<nb, 256, 0, st>>>(reinterpret_cast<const float4*>(I_loc), reinterpret_cast<const float4*>(T_loc), n4,
+                                         (size_t)rank * n4, dst, rank, world, scratch);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
+int amax_copy(const float* I_loc, const float* T_loc, int b, int D, float* I_copy, float* T_copy,
+              unsigned int* amax_bits, cudaStream_t st) {
+  MC_REQUIRE(D % 4 == 0 && aligned(I_loc, 16) && aligned(T_loc, 16) && (!I_copy || aligned(I_copy, 16)) &&
+                 (!T_copy || aligned(T_copy, 16)),
+             MC_ERR_ALIGN, "clip_amax: embeddings must be 16-byte aligned with D %% 4 == 0");
+  MC_CUDA(cudaMemsetAsync(amax_bits, 0, 4, st));
+  const size_t n4 = (size_t)b * D / 4;
+  int ab = (int)((n4 + 255) / 256);
+  if (ab > num_sms() * 8) ab = num_sms() * 8;
+  amax_copy_kernel<<<ab, 256, 0, st>>>(reinterpret_cast<const float4*>(I_loc), reinterpret_cast<const float4*>(T_loc), n4,
+                                       reinterpret_cast<float4*>(I_copy), reinterpret_cast<float4*>(T_copy), amax_bits);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
+int prepare_peers(const float* const* I_peers, const float* const* T_peers, int world, int b, int D, int /*mode*/,
+                  const unsigned int* amax_slots, void* planes_all, cudaStream_t st) {
+  MC_REQUIRE(supported(D), MC_ERR_UNSUPPORTED, "tcgen05 engine needs D in {128, 256} (got %d)", D);
+  MC_REQUIRE(world >= 1 && world <= kMaxPeers, MC_ERR_BAD_ARG, "clip_prepare_peers: world %d outside [1, %d]", world,
+             kMaxPeers);
+  MC_REQUIRE(aligned(planes_all, 256), MC_ERR_ALIGN, "clip_prepare_peers: planes buffer must be 256-byte aligned");
+  PeerRows src;
+  for (int q = 0; q < kMaxPeers; ++q) { src.I[q] = nullptr; src.T[q] = nullptr; }
+  for (int q = 0; q < world; ++q) {
+    MC_REQUIRE(I_peers[q] && T_peers[q] && aligned(I_peers[q], 16) && aligned(T_peers[q], 16), MC_ERR_ALIGN,
+               "clip_prepare_peers: shard pointers of rank %d null or not 16-byte aligned", q);
+    src.I[q] = I_peers[q];
+    src.T[q] = T_peers[q];
+  }
+  const int B = world * b;
+  PlanesLayout l = planes_layout(B, D);
+  char* base = static_cast<char*>(planes_all);
+  __half* Xh = reinterpret_cast<__half*>(base + l.off_hi);
+  __half* Xl = reinterpret_cast<__half*>(base + l.off_lo);
+  __half* XhT = reinterpret_cast<__half*>(base + l.off_hiT);
+  float* hdr = reinterpret_cast<float*>(base + l.off_hdr);
+  float* norm_i = reinterpret_cast<float*>(base + l.off_norm_i);
+  float* norm_t = reinterpret_cast<float*>(base + l.off_norm_t);
+  launch_stage_fused(src, b, B, D, l, amax_slots, world, Xh, Xl, XhT, hdr, norm_i, norm_t, st);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
 int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row_offset, int /*mode*/,
             void* planes_all, cudaStream_t st) {
   MC_REQUIRE(supported(D), MC_ERR_UNSUPPORTED, "tcgen05 engine needs D in {128, 256} (got %d)", D);
@@ -1047,12 +1219,12 @@ int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row
   if (ab > num_sms() * 8) ab = num_sms() * 8;
   amax_kernel<<<ab, 256, 0, st>>>(I_loc, T_loc, n, reinterpret_cast<unsigned int*>(hdr));
   MC_LAUNCH_CHECK();
-  const int rows_total = l.Bp;
-  stage_planes_kernel<<<(rows_total + 7) / 8, 256, 0, st>>>(I_loc, T_loc, b, B, l.Bp, D, row_offset, rows_total, Xh,
-                                                           Xl, hdr, norm_i, norm_t);
-  MC_LAUNCH_CHECK();
-  dim3 grid((l.Bp + 63) / 64, 2 * D / 64);
-  transpose_hi_kernel<<<grid, 256, 0, st>>>(Xh, XhT, l.Bp, 2 * D, 0, l.Bp);
+  PeerRows src;
+  for (int q = 0; q < kMaxPeers; ++q) { src.I[q] = nullptr; src.T[q] = nullptr; }
+  src.I[0] = I_loc;
+  src.T[0] = T_loc;
+  MC_REQUIRE(aligned(I_loc, 16) && aligned(T_loc, 16), MC_ERR_ALIGN, "clip_prepare: embeddings must be 16-byte aligned");
+  launch_stage_fused(src, B, B, D, l, reinterpret_cast<const unsigned int*>(hdr), 1, Xh, Xl, XhT, hdr, norm_i, norm_t, st);
   MC_LAUNCH_CHECK();
   return MC_OK;
 }

@@ -16,8 +16,21 @@ One process per GPU.  Rank r owns rows [r*b, (r+1)*b) of the global (B, D) embed
 The sweeps are the C-ABI phases ``mc_clip_stats / mc_clip_rowloss / mc_clip_bwd``.  The engine is
 injectable so the collective choreography can be tested on CPU with gloo (tests supply a torch
 engine; the product engine below is CUDA-only).
+
+Two transports carry the exchange steps on GPUs:
+
+  ``peer``  (default for the tcgen05 engines) our own kernels over mapped peer memory
+            (``mae_clip_b200/peer.py``): the embedding all-gather is fused into the operand staging
+            and the vectors are pushed straight into every peer's region - no collective-library
+            call per step;
+  ``nccl``  the all-gathers below through ``torch.distributed`` (any engine, any backend; also the
+            path the CPU/gloo tests exercise).
+
+``MAE_CLIP_TRANSPORT=nccl|peer`` overrides the choice.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.distributed as dist
@@ -149,11 +162,147 @@ class _GlobalClipLoss(torch.autograd.Function):
         return dI.to(ctx.in_dtypes[0]), dT.to(ctx.in_dtypes[1]), None, None, None
 
 
+# ------------------------------------------------------------------------------------------------
+# peer-memory transport
+# ------------------------------------------------------------------------------------------------
+class PeerStep:
+    """One forward (+ backward) of the row-sharded loss over a ``PeerExchange``: every exchange step
+    is a kernel of libmae_clip_b200.so on the caller's stream.  Shared by the autograd Function
+    below and by ``bench.py`` (``events``: optional list filled with CUDA events between phases)."""
+
+    def __init__(self, exchange, mode, exchange_mode=None):
+        from .functional import _mode
+        self.ex = exchange
+        self.mode = _mode(mode)
+        self.exchange_mode = exchange_mode or os.environ.get("MAE_CLIP_PEER_MODE", "push")
+        if self.exchange_mode not in ("push", "pull"):
+            raise ValueError(f"unknown peer exchange mode {self.exchange_mode!r}")
+        if self.mode == _lib.GEMM_SIMT_FP32 or lib().mc_clip_planes_bytes(exchange.B, exchange.D, self.mode) == 0:
+            raise ValueError("the peer transport feeds the tcgen05 engines (D in {128, 256}); use transport='nccl'")
+        if exchange.b % 128:
+            raise ValueError(f"tcgen05 engine: rows per rank must be a multiple of 128 (got {exchange.b})")
+
+    def forward(self, I_loc, T_loc, tau, events=None):
+        ex, mode, L = self.ex, self.mode, lib()
+        b, B, D, rank, world = ex.b, ex.B, ex.D, ex.rank, ex.world
+        dev = I_loc.device
+        f32 = dict(device=dev, dtype=torch.float32)
+
+        def mark():
+            if events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                events.append(e)
+
+        with torch.cuda.device(dev):
+            st = cur_stream()
+            mark()
+            pull = self.exchange_mode == "pull"
+            shard = rank * b * D * 4
+            if pull:
+                # local amax + copy of the shards into our rows of the region (peers read them there);
+                # amax to every rank's slot
+                check(L.mc_clip_amax(ptr(I_loc), ptr(T_loc), b, D, ex.local(ex.off_emb_i + shard),
+                                     ex.local(ex.off_emb_t + shard), ex.local(ex.OFF_AMAX_LOCAL), st), "mc_clip_amax")
+                ex.publish(ex.local(ex.OFF_AMAX_LOCAL), 1, 1, 0, ex.OFF_AMAX_SLOTS, 0, rank)
+            else:
+                # posted stores of our shards into every rank's image of the batch + amax, one kernel
+                check(L.mc_clip_push_shards(ptr(I_loc), ptr(T_loc), b, D, rank, world, ex.table(ex.off_emb_i),
+                                            ex.table(ex.off_emb_t), ex.table(ex.OFF_AMAX_SLOTS),
+                                            ex.local(ex.OFF_PUSH_SCRATCH), st), "mc_clip_push_shards")
+            ex.barrier()
+            planes = torch.empty(L.mc_clip_planes_bytes(B, D, mode), device=dev, dtype=torch.uint8)
+            tab_i, tab_t = ex.row_tables(pull)
+            check(L.mc_clip_prepare_peers(tab_i, tab_t, world, b, D, mode, ex.local(ex.OFF_AMAX_SLOTS), ptr(planes), st),
+                  "mc_clip_prepare_peers")
+            mark()
+            ws = workspace(L.mc_clip_loss_workspace_bytes(b, B, D, mode), dev)
+            loc = torch.empty(6, b, **f32)  # r, c, rz, sum_j P_ij S_ij, g, q of the owned rows
+            check(L.mc_clip_stats(None, None, ptr(planes), b, B, D, rank * b, float(tau), mode, ptr(loc[0]), ptr(loc[1]),
+                                  ptr(loc[2]), ptr(loc[3]), ptr(ws), ws.numel(), st), "mc_clip_stats")
+            ex.publish(ptr(loc), 3, b, b, ex.OFF_VECS, ex.vec_stride, rank * b)
+            ex.barrier()
+            mark()
+            check(L.mc_clip_rowloss(None, None, ptr(planes), b, B, D, rank * b, float(tau), mode, ex.vec(0), ex.vec(1),
+                                    ex.vec(2), ptr(loc[3]), ptr(loc[4]), ptr(loc[5]), ex.local(ex.OFF_PART_LOCAL),
+                                    ptr(ws), ws.numel(), st), "mc_clip_rowloss")
+            ex.publish(ptr(loc[4]), 2, b, b, ex.OFF_VECS + 4 * 3 * ex.vec_stride, ex.vec_stride, rank * b)
+            ex.publish(ex.local(ex.OFF_PART_LOCAL), 1, 1, 0, ex.OFF_PART_SLOTS, 0, rank)
+            ex.barrier()
+            # out of the region: backward (and a second forward before it) never touch peer memory
+            vecs = torch.empty(5, B, **f32)
+            parts = torch.empty(world, **f32)
+            ex.copy_out(ex.OFF_VECS, 5, B, ex.vec_stride, vecs, B)
+            ex.copy_out(ex.OFF_PART_SLOTS, 1, world, 0, parts, 0)
+            loss = parts.sum()
+            mark()
+        return loss, (planes, vecs)
+
+    def backward(self, saved, tau, grad_loss=None, events=None):
+        ex, mode, L = self.ex, self.mode, lib()
+        planes, vecs = saved
+        b, B, D = ex.b, ex.B, ex.D
+        dev = planes.device
+        dI = torch.empty(b, D, device=dev, dtype=torch.float32)
+        dT = torch.empty(b, D, device=dev, dtype=torch.float32)
+        gl = None if grad_loss is None else grad_loss.reshape(1).to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            ws = workspace(L.mc_clip_loss_workspace_bytes(b, B, D, mode), dev)
+            check(L.mc_clip_bwd(None, None, ptr(planes), b, B, D, ex.rank * b, float(tau), mode, ptr(vecs[0]),
+                                ptr(vecs[1]), ptr(vecs[2]), ptr(vecs[3]), ptr(vecs[4]), ptr(gl), ptr(dI), ptr(dT),
+                                ptr(ws), ws.numel(), cur_stream()), "mc_clip_bwd")
+            if events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                events.append(e)
+        return dI, dT
+
+
+class _PeerGlobalClipLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image_emb, text_emb, temperature, step):
+        I = image_emb.detach().float().contiguous()
+        T = text_emb.detach().float().contiguous()
+        loss, saved = step.forward(I, T, temperature)
+        ctx.step, ctx.saved, ctx.tau = step, saved, float(temperature)
+        ctx.in_dtypes = (image_emb.dtype, text_emb.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        dI, dT = ctx.step.backward(ctx.saved, ctx.tau, grad_loss)
+        return dI.to(ctx.in_dtypes[0]), dT.to(ctx.in_dtypes[1]), None, None
+
+
+def _pick_transport(transport, image_emb, mode, engine, world):
+    """'peer' when every precondition of the peer-memory path holds, else 'nccl'."""
+    want = transport or os.environ.get("MAE_CLIP_TRANSPORT", "auto")
+    if want not in ("auto", "peer", "nccl"):
+        raise ValueError(f"unknown transport {want!r}")
+    if want == "nccl" or engine is not None or world == 1 or not image_emb.is_cuda:
+        if want == "peer" and (engine is not None or not image_emb.is_cuda):
+            raise ValueError("transport='peer' needs CUDA tensors and the built-in engine")
+        return "nccl"
+    from .functional import _mode
+    b, D = image_emb.shape
+    ok = (_mode(mode) != _lib.GEMM_SIMT_FP32 and lib().mc_clip_planes_bytes(b * world, D, _mode(mode)) > 0
+          and b % 128 == 0 and world <= 16)
+    if want == "peer" and not ok:
+        raise ValueError("transport='peer' needs a tcgen05 engine (D in {128, 256}) and rows per rank % 128 == 0")
+    return "peer" if ok else "nccl"
+
+
 def global_clip_loss(image_emb_local, text_emb_local, temperature: float = 1.0, mode=None,
-                     group=None, engine=None):
+                     group=None, engine=None, transport=None):
     """Loss of the reference on the concatenation of every rank's (b, D) embeddings; the value is
     identical on all ranks and ``backward`` yields d loss_global / d (local embeddings) in full.
     (Under DDP, which averages parameter gradients over ranks, multiply the loss by the world
     size to obtain the single-process gradient.)"""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if _pick_transport(transport, image_emb_local, mode, engine, world) == "peer":
+        from .peer import get_exchange
+        b, D = image_emb_local.shape
+        step = PeerStep(get_exchange(b, D, group), mode)
+        return _PeerGlobalClipLoss.apply(image_emb_local, text_emb_local, float(temperature), step)
     engine = engine if engine is not None else CudaStripEngine(mode)
     return _GlobalClipLoss.apply(image_emb_local, text_emb_local, float(temperature), engine, group)

@@ -1,0 +1,164 @@
+"""Peer-memory exchange for the row-sharded contrastive loss (SURVEY.md section 8 e).
+
+One process per GPU.  Every rank owns one exchange region (``mc_peer_alloc``), ships its CUDA IPC
+handle to the other local ranks through ``torch.distributed`` (plumbing) and maps theirs; from then
+on the data path is OUR kernels loading / storing peer memory over NVLink / NVSwitch - no
+collective-library call per step:
+
+  * the embedding all-gather is fused into the operand staging (``mc_clip_prepare_peers`` pulls
+    each fp32 row from its owner while it writes the local fp16 planes);
+  * the row statistics, (g, q) vectors and loss partials are pushed into every peer's region by
+    ``mc_peer_publish`` and fenced by ``mc_peer_barrier`` (flag exchange, system-scope
+    release / acquire).
+
+The reference is single-process (nothing under /root/reference to cite); the result is, by
+definition, the reference loss (``CLIP.py:34-43``) on the concatenated batch.
+
+Region layout (bytes): [0, 64) barrier flags | 128 private barrier epoch | [256, 320) amax slots | [512, 576) loss-partial
+slots | 768 local amax, 772 local loss partial, 784 push scratch (2 words) | 1024.. five length-B vectors
+(r, c, rz, g, q) | then two (B, D) fp32 images of the global batch (image / text embeddings): in
+"pull" mode each rank fills only its own rows and peers read them from there; in "push" mode every
+rank stores its rows into all ranks' images and the staging reads locally.
+
+Why the region can be reused every step without extra fences (B_k = k-th barrier of a step):
+  shards + amax slots written before B_1, read by peers between B_1 and B_2;  r, c, rz pushed
+  between B_1 and B_2, read after B_2;  g, q, partials pushed between B_2 and B_3, read after B_3
+  and copied out of the region right there (backward never touches peer memory).  A rank can only
+  write step n+1's data after passing B_1(n+1) / B_2(n+1), which every peer enters only after its
+  own stream finished reading step n's.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from ._lib import check, cur_stream, lib
+
+_HANDLE_BYTES = 64
+MAX_WORLD = 16
+
+
+def _round_up(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+class PeerExchange:
+    """The mapped exchange regions of every rank of ``group`` for a (b, D) shard shape."""
+
+    OFF_FLAGS, OFF_EPOCH, OFF_AMAX_SLOTS, OFF_PART_SLOTS, OFF_AMAX_LOCAL, OFF_PART_LOCAL, OFF_VECS = \
+        0, 128, 256, 512, 768, 772, 1024
+    OFF_PUSH_SCRATCH = 784  # {amax accumulator, blocks-done counter} of mc_clip_push_shards
+
+    def __init__(self, b: int, D: int, group=None, device=None):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerExchange needs an initialised torch.distributed process group")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > MAX_WORLD:
+            raise ValueError(f"peer exchange supports up to {MAX_WORLD} ranks on one NVLink domain (got {self.world})")
+        self.b, self.D, self.B = b, D, b * self.world
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.vec_stride = _round_up(self.B, 64)                         # floats
+        # (B, D) fp32 images of the global batch: pull mode uses only the owner's rows of each
+        self.off_emb_i = _round_up(self.OFF_VECS + 5 * self.vec_stride * 4, 256)
+        self.off_emb_t = self.off_emb_i + _round_up(self.B * D * 4, 256)
+        self.nbytes = self.off_emb_t + _round_up(self.B * D * 4, 256)
+        self.ptrs = [0] * self.world
+        self._tables = {}
+        self._local = C.c_void_p()
+        self._open = []
+        with torch.cuda.device(self.device):
+            handle = C.create_string_buffer(_HANDLE_BYTES)
+            check(lib().mc_peer_alloc(self.nbytes, C.byref(self._local), handle), "mc_peer_alloc")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (self.rank, bytes(handle.raw), self.nbytes), group=group)
+            for q, (rq, hq, nq) in enumerate(handles):
+                if rq != q or nq != self.nbytes:
+                    raise RuntimeError("peer exchange: ranks disagree on the region size (different b / D per rank?)")
+                if q == self.rank:
+                    self.ptrs[q] = self._local.value
+                    continue
+                p = C.c_void_p()
+                check(lib().mc_peer_open(C.create_string_buffer(hq, _HANDLE_BYTES), C.byref(p)), "mc_peer_open")
+                self._open.append(p)
+                self.ptrs[q] = p.value
+        dist.barrier(group=group)  # every region is mapped (and zero-filled) before the first flag is written
+
+    # ---- pointer helpers ----------------------------------------------------------------------
+    def local(self, offset: int = 0) -> C.c_void_p:
+        return C.c_void_p(self.ptrs[self.rank] + offset)
+
+    def table(self, offset: int = 0):
+        """Host array of ``world`` device pointers: every rank's region + offset (C-ABI ``void* const*``)."""
+        t = self._tables.get(offset)
+        if t is None:
+            t = self._tables[offset] = (C.c_void_p * self.world)(*[p + offset for p in self.ptrs])
+        return t
+
+    def row_tables(self, pull: bool):
+        """Per-owner source pointers for mc_clip_prepare_peers: rank q's rows in q's region (pull) or in ours (push)."""
+        key = ("rows", pull)
+        t = self._tables.get(key)
+        if t is None:
+            shard = self.b * self.D * 4
+            base = self.ptrs if pull else [self.ptrs[self.rank]] * self.world
+            t = self._tables[key] = tuple(
+                (C.c_void_p * self.world)(*[base[q] + off + q * shard for q in range(self.world)])
+                for off in (self.off_emb_i, self.off_emb_t))
+        return t
+
+    def vec(self, k: int) -> C.c_void_p:
+        """Local copy of the k-th length-B vector (0 r, 1 c, 2 rz, 3 g, 4 q)."""
+        return self.local(self.OFF_VECS + 4 * k * self.vec_stride)
+
+    # ---- primitives ---------------------------------------------------------------------------
+    def barrier(self, timeout_s: float = 20.0):
+        check(lib().mc_peer_barrier(self.table(self.OFF_FLAGS), self.rank, self.world, self.local(self.OFF_EPOCH),
+                                    float(timeout_s), cur_stream()), "mc_peer_barrier")
+
+    def publish(self, src, k: int, n: int, src_stride: int, dst_offset_bytes: int, dst_stride: int, dst_index: int):
+        """Push k vectors of n words from local ``src`` to [dst_offset + kk*dst_stride + dst_index + i] of every rank."""
+        check(lib().mc_peer_publish(src, k, n, src_stride, self.table(dst_offset_bytes), dst_stride, dst_index,
+                                    self.world, cur_stream()), "mc_peer_publish")
+
+    def copy_out(self, src_offset_bytes: int, k: int, n: int, src_stride: int, dst: torch.Tensor, dst_stride: int):
+        """Copy k vectors of n words from the local region into an ordinary tensor (same kernel, one target)."""
+        tab = (C.c_void_p * 1)(dst.data_ptr())
+        check(lib().mc_peer_publish(self.local(src_offset_bytes), k, n, src_stride, tab, dst_stride, 0, 1,
+                                    cur_stream()), "mc_peer_publish(copy out)")
+
+    def close(self):
+        if self._local is None:
+            return
+        torch.cuda.synchronize(self.device)
+        try:
+            dist.barrier(group=self.group)  # nobody unmaps while a peer may still be reading
+        except Exception:
+            pass
+        with torch.cuda.device(self.device):
+            for p in self._open:
+                lib().mc_peer_close(p)
+            lib().mc_peer_free(self._local)
+        self._open, self._local = [], None
+
+
+_cache = {}
+
+
+def get_exchange(b: int, D: int, group=None) -> PeerExchange:
+    """One exchange per (group, device, b, D): set-up costs a device synchronisation and an object
+    all-gather, so it is created on first use and kept."""
+    key = (id(group) if group is not None else 0, torch.cuda.current_device(), b, D)
+    ex = _cache.get(key)
+    if ex is None:
+        ex = _cache[key] = PeerExchange(b, D, group)
+    return ex
+
+
+def close_all():
+    for ex in list(_cache.values()):
+        ex.close()
+    _cache.clear()

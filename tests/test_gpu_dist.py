@@ -24,7 +24,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, b, mode, ret):
+def _worker(rank, world, port, b, mode, transport, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -33,26 +33,36 @@ def _worker(rank, world, port, b, mode, ret):
         from mae_clip_b200.dist import global_clip_loss
         I = loss_ref.make_embeddings(b, 256, seed=1000 + rank, scale=0.15).cuda().requires_grad_(True)
         T = loss_ref.make_embeddings(b, 256, seed=2000 + rank, scale=0.15).cuda().requires_grad_(True)
-        loss = global_clip_loss(I, T, 1.0, mode=mode)
-        (loss * 2.0).backward()
+        if transport.startswith("peer"):
+            os.environ["MAE_CLIP_PEER_MODE"] = transport.split("-")[1]
+            transport = "peer"
+        for _ in range(3 if transport == "peer" else 1):  # the exchange region is reused step after step
+            I.grad = T.grad = None
+            loss = global_clip_loss(I, T, 1.0, mode=mode, transport=transport)
+            (loss * 2.0).backward()
         ret[rank] = (loss.detach().cpu(), I.grad.cpu(), T.grad.cpu())
+        if transport == "peer":
+            from mae_clip_b200 import peer
+            peer.close_all()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["simt_fp32", "tc_f16x3"])
-def test_global_loss_two_gpus(mode):
+@pytest.mark.parametrize("mode,transport", [("simt_fp32", "nccl"), ("tc_f16x3", "nccl"), ("tc_f16x3", "peer-push"),
+                                            ("tc_f16x3", "peer-pull"), ("tc_f16", "peer-push")])
+def test_global_loss_two_gpus(mode, transport):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     world, b = 2, 384
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), b, mode, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), b, mode, transport, ret), nprocs=world, join=True)
     I = torch.cat([loss_ref.make_embeddings(b, 256, seed=1000 + r, scale=0.15) for r in range(world)])
     T = torch.cat([loss_ref.make_embeddings(b, 256, seed=2000 + r, scale=0.15) for r in range(world)])
     ref_loss, ref_dI, ref_dT, _ = loss_ref.clip_loss_closed_form(I.numpy(), T.numpy(), 1.0, grad_loss=2.0)
     for r in range(world):
         loss, dI, dT = ret[r]
-        assert abs(loss.item() - ref_loss) < 1e-4 * abs(ref_loss)
-        assert rel_err(dI, ref_dI[r * b:(r + 1) * b]) < 1e-3
-        assert rel_err(dT, ref_dT[r * b:(r + 1) * b]) < 1e-3
+        lt, gt = (2e-3, 3e-2) if mode == "tc_f16" else (1e-4, 1e-3)  # single fp16 pass: stated looser
+        assert abs(loss.item() - ref_loss) < lt * abs(ref_loss)
+        assert rel_err(dI, ref_dI[r * b:(r + 1) * b]) < gt
+        assert rel_err(dT, ref_dT[r * b:(r + 1) * b]) < gt
