@@ -249,6 +249,16 @@ int mc_restore_tokens(const void* x_kept, int elem_size, const void* mask_token,
                       const int64_t* ids_restore, int N, int L, int Dm, int len_keep, void* out,
                       void* stream);
 
+/* "next" row 1: the optimiser step of the training driver      main.py:103-105, main.py:59
+ * (torch.optim.AdamW, decoupled weight decay, no amsgrad).  params / grads / exp_avg /
+ * exp_avg_sq: HOST arrays of `ntensors` device pointers (dense fp32), numel: HOST array of
+ * element counts.  `step` counts from 1 (bias correction).  grad_scale: optional device scalar
+ * multiplied into every gradient (NULL = 1).  One launch per 48 tensors. */
+int mc_adamw_step(int ntensors, float* const* params, const float* const* grads,
+                  float* const* exp_avg, float* const* exp_avg_sq, const int64_t* numel, double lr,
+                  double beta1, double beta2, double eps, double weight_decay, int step,
+                  const float* grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

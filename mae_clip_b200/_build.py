@@ -44,7 +44,8 @@ def _headers_mtime() -> float:
 
 
 def _compile_one(src: str, obj: str, verbose: bool) -> str:
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-c", src, "-o", obj]
+    extra = os.environ.get("MAE_CLIP_NVCC_EXTRA", "").split()  # e.g. -DMC_... for A/B builds of a kernel variant
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", INCLUDE, "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     if r.returncode != 0:

@@ -11,7 +11,8 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmae_clip_b200.so")
+# MAE_CLIP_B200_LIB: load another build of the same ABI (A/B timing of kernel variants); never a fallback
+LIB_PATH = os.environ.get("MAE_CLIP_B200_LIB") or os.path.join(_PKG, "libmae_clip_b200.so")
 
 GEMM_SIMT_FP32 = 0
 GEMM_TC_F16X3 = 1
@@ -66,6 +67,8 @@ SIGNATURES = {
     "mc_masked_mse_fwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "mc_masked_mse_bwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "mc_patchify": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "mc_adamw_step": (_i, [_i, _p, _p, _p, _p, _p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i, _p,
+                           _p]),
     "mc_restore_tokens": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _p, _p]),
 }
 

@@ -50,6 +50,63 @@ __global__ void argsort_mask_kernel(const float* __restrict__ noise, int L, int 
 }
 
 // ------------------------------------------------------------------------------------------
+// M1 fused (L <= 1024): one block per sample does the whole op.  The stable argsort is a RANK
+// sort - position of element i = number of 64-bit keys smaller than key i (keys are unique: the
+// index sits in the low word) - i.e. one pass of broadcast shared-memory reads per element and a
+// single barrier instead of the 36 barrier-separated stages of a 256-key bitonic network; the rank
+// IS ids_restore[i], so nothing is scattered.  The block then copies its len_keep kept rows with
+// 16-byte vectors, all of a row's loads in flight at once; blocks finish sorting at different
+// times, so the latency-bound sort of one sample overlaps the HBM-bound copy of another.
+// ------------------------------------------------------------------------------------------
+template <typename V, int kMaxVecPerLane>
+__global__ void __launch_bounds__(256) random_masking_fused_kernel(const float* __restrict__ noise, int L, int len_keep,
+                                                                   float* __restrict__ mask,
+                                                                   int64_t* __restrict__ ids_restore,
+                                                                   int64_t* __restrict__ ids_keep,
+                                                                   const V* __restrict__ src, int row_vecs,
+                                                                   V* __restrict__ out) {
+  extern __shared__ unsigned long long keys[];           // [L] keys, then [len_keep] kept indices
+  int* keep_idx = reinterpret_cast<int*>(keys + L);
+  const int n = blockIdx.x;
+  const float* row = noise + (size_t)n * L;
+  for (int i = threadIdx.x; i < L; i += blockDim.x)
+    keys[i] = ((unsigned long long)sortable_bits(row[i]) << 32) | (unsigned)i;
+  __syncthreads();
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const unsigned long long mine = keys[i];
+    int rank = 0;
+    int j = 0;
+    for (; j + 4 <= L; j += 4)
+      rank += (keys[j] < mine) + (keys[j + 1] < mine) + (keys[j + 2] < mine) + (keys[j + 3] < mine);
+    for (; j < L; ++j) rank += keys[j] < mine;
+    ids_restore[(size_t)n * L + i] = rank;
+    mask[(size_t)n * L + i] = rank < len_keep ? 0.f : 1.f;
+    if (rank < len_keep) {
+      keep_idx[rank] = i;
+      if (ids_keep) ids_keep[(size_t)n * len_keep + rank] = i;
+    }
+  }
+  if (src == nullptr) return;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < len_keep; r += 8) {
+    const V* sp = src + ((size_t)n * L + keep_idx[r]) * row_vecs;
+    V* dp = out + ((size_t)n * len_keep + r) * row_vecs;
+    if (row_vecs <= 32 * kMaxVecPerLane) {
+      V v[kMaxVecPerLane];
+#pragma unroll
+      for (int u = 0; u < kMaxVecPerLane; ++u)
+        if (lane + 32 * u < row_vecs) v[u] = sp[lane + 32 * u];
+#pragma unroll
+      for (int u = 0; u < kMaxVecPerLane; ++u)
+        if (lane + 32 * u < row_vecs) dp[lane + 32 * u] = v[u];
+    } else {
+      for (int c = lane; c < row_vecs; c += 32) dp[c] = sp[c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // M1b: row gather with a default.  Output row (n, r): idx = index[n*out_rows + r]; when
 // idx < limit copy src row (n, idx), else fill (zeros or a broadcast token).  One warp per row,
 // VEC-byte vectors.  Used for the keep-gather, its backward (scatter expressed as a gather through
@@ -414,6 +471,20 @@ int mc_random_masking(const void* x, int elem_size, const float* noise, int N, i
   if (threads > 512) threads = 512;
   const bool need_keep = (x != nullptr) || ids_keep;
   MC_REQUIRE(!x || ids_keep, MC_ERR_BAD_ARG, "random_masking: ids_keep buffer is required with x");
+  if (x) {
+    MC_REQUIRE(elem_size == 2 || elem_size == 4, MC_ERR_BAD_ARG, "random_masking: elem_size %d", elem_size);
+    MC_REQUIRE(Dm > 0, MC_ERR_BAD_ARG, "random_masking: Dm=%d", Dm);
+  }
+  const size_t row_bytes = x ? (size_t)Dm * elem_size : 0;
+  if (L <= 1024 && (!x || (row_bytes % 16 == 0 && aligned(x, 16) && aligned(x_masked, 16)))) {
+    // fused rank-sort + keep-gather: one launch, one block per sample
+    const size_t smem = (size_t)L * 8 + (size_t)(len_keep > 0 ? len_keep : 1) * 4;
+    random_masking_fused_kernel<uint4, 8><<<N, 256, smem, st>>>(
+        noise, L, len_keep, mask, ids_restore, need_keep ? ids_keep : nullptr,
+        (x && len_keep > 0) ? static_cast<const uint4*>(x) : nullptr, (int)(row_bytes / 16), static_cast<uint4*>(x_masked));
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+  }
   argsort_mask_kernel<<<N, threads, (size_t)LP * 8, st>>>(noise, L, LP, len_keep, mask, ids_restore,
                                                           need_keep ? ids_keep : nullptr);
   MC_LAUNCH_CHECK();

@@ -194,7 +194,8 @@ def test_cross_entropy_golden(golden):
     np.testing.assert_allclose(st.grad.cpu().numpy(), z["sq.ref_dtargets_T"], rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("rows,cols", [(1, 1), (3, 5), (257, 1023), (1024, 1024), (100, 4097)])
+@pytest.mark.parametrize("rows,cols", [(1, 1), (3, 5), (257, 1023), (1024, 1024), (100, 4097), (260, 1000),
+                                       (4096, 333), (36, 130)])
 @pytest.mark.parametrize("transposed", [False, True])
 def test_cross_entropy_vs_oracle(rows, cols, transposed):
     import mae_clip_b200 as m
