@@ -249,6 +249,26 @@ int mc_restore_tokens(const void* x_kept, int elem_size, const void* mask_token,
                       const int64_t* ids_restore, int N, int L, int Dm, int len_keep, void* out,
                       void* stream);
 
+/* backward of mc_restore_tokens: grad_out (N,L,Dm) -> d x_kept (N,len_keep,Dm) (rows whose
+ * ids_restore < len_keep) and d mask_token (Dm) = column sum of the other rows (fp32 accumulate,
+ * written in the element type; is_bf16 selects bf16 vs fp16 when elem_size == 2).  Rows must be
+ * 16-byte multiples of at most 16 KB. */
+size_t mc_restore_tokens_bwd_workspace_bytes(int N, int L, int Dm);
+int mc_restore_tokens_bwd(const void* grad_out, int elem_size, int is_bf16,
+                          const int64_t* ids_restore, int N, int L, int Dm, int len_keep,
+                          void* dx_kept, void* dmask_token, void* ws, size_t ws_bytes, void* stream);
+
+/* "next" row 3: inference-side retrieval                       inference.py:42-46 (find_matches)
+ *   scores[q][n] = <text[q] / max(|text[q]|, 1e-12), image[n] / max(|image[n]|, 1e-12)>   (F.normalize + matmul)
+ *   out_vals / out_idx (Q, k): the k largest scores of every query, descending, ties -> lower index
+ *   (torch.topk leaves tie order unspecified).  The image bank (N, D) fp32 is streamed once.
+ *   scores_out: optional (Q, N) fp32 buffer that receives the full similarity matrix (NULL: it
+ *   lives in `ws`).  k = 0 computes the scores only.  k <= 1024, k <= N. */
+size_t mc_similarity_topk_workspace_bytes(int Q, long long N, int D);
+int mc_similarity_topk(const float* text, int Q, const float* image, long long N, int D, int k,
+                       float* out_vals, int64_t* out_idx, float* scores_out, void* ws,
+                       size_t ws_bytes, void* stream);
+
 /* "next" row 1: the optimiser step of the training driver      main.py:103-105, main.py:59
  * (torch.optim.AdamW, decoupled weight decay, no amsgrad).  params / grads / exp_avg /
  * exp_avg_sq: HOST arrays of `ntensors` device pointers (dense fp32), numel: HOST array of

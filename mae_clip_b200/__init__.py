@@ -10,6 +10,7 @@ from .CLIP import CLIPModel, cross_entropy  # noqa: F401
 from .functional import clip_contrastive_loss, projection_head  # noqa: F401
 from .mae import (masked_mse_loss, patchify, random_masking, random_masking_with_ids,  # noqa: F401
                   restore_tokens)
+from .inference import find_matches, get_image_embeddings, similarity_topk  # noqa: F401
 from .modules import ImageEncoder, ProjectionHead, TextEncoder  # noqa: F401
 
 __version__ = "0.1.0"

@@ -2,6 +2,8 @@
 // NOT IN THE REFERENCE (/root/reference holds no MAE code - SURVEY.md section 0.2); the contract
 // is BASELINE.json's north_star as restated by oracle/mae_ref.py.  All kernels are HBM-bound
 // byte movers: coalesced 16-byte rows, no tensor cores.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mc {
@@ -137,6 +139,120 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const V* __restrict__ 
       for (int v = lane; v < row_vecs; v += 32) dst[v] = zero;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward of the decoder-side un-shuffle (restore_tokens): every row (n, l) of grad_out goes either
+// to d x_kept[n, ids_restore[n, l]] (a copy: targets are unique) or into the column sum that is the
+// mask token's gradient.  A block walks its rows four at a time (four 16-byte loads in flight per
+// thread), each thread owning fixed columns; block partials are merged in a fixed order by a
+// second kernel (deterministic, no atomics).
+// ------------------------------------------------------------------------------------------
+template <typename E> struct Vec16;  // 16 bytes of E <-> floats
+template <> struct Vec16<float> {
+  static constexpr int kN = 4;
+  __device__ static void unpack(const uint4& u, float* f) {
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+  }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int kN = 8;
+  __device__ static void unpack(const uint4& u, float* f) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+};
+template <> struct Vec16<__half> {
+  static constexpr int kN = 8;
+  __device__ static void unpack(const uint4& u, float* f) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      f[2 * i] = __low2float(h);
+      f[2 * i + 1] = __high2float(h);
+    }
+  }
+};
+
+constexpr int kRestoreVecsPerThread = 4;  // rows up to 256 * 4 * 16 bytes = 16 KB
+
+template <typename E>
+__global__ void __launch_bounds__(256) restore_bwd_kernel(const uint4* __restrict__ gout,
+                                                          const int64_t* __restrict__ ids_restore, long long rows, int L,
+                                                          int row_vecs, int len_keep, uint4* __restrict__ dx_kept,
+                                                          float* __restrict__ partial /* [gridDim.x][row_vecs * kN] */) {
+  constexpr int kN = Vec16<E>::kN;
+  float acc[kRestoreVecsPerThread][kN];
+#pragma unroll
+  for (int a = 0; a < kRestoreVecsPerThread; ++a)
+#pragma unroll
+    for (int e = 0; e < kN; ++e) acc[a][e] = 0.f;
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long beg = (long long)blockIdx.x * per, end = min(rows, beg + per);
+  for (long long r0 = beg; r0 < end; r0 += 4) {
+    long long dstrow[4];
+    uint4 v[4][kRestoreVecsPerThread];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long row = r0 + u;
+      dstrow[u] = -2;  // out of range
+      if (row < end) {
+        const long long idx = ids_restore[row];
+        dstrow[u] = idx < len_keep ? (row / L) * len_keep + idx : -1;
+#pragma unroll
+        for (int a = 0; a < kRestoreVecsPerThread; ++a) {
+          const int c = threadIdx.x + 256 * a;
+          if (c < row_vecs) v[u][a] = ld_stream(gout + row * row_vecs + c);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (dstrow[u] == -2) continue;
+#pragma unroll
+      for (int a = 0; a < kRestoreVecsPerThread; ++a) {
+        const int c = threadIdx.x + 256 * a;
+        if (c >= row_vecs) continue;
+        if (dstrow[u] >= 0) {
+          dx_kept[dstrow[u] * row_vecs + c] = v[u][a];
+        } else {
+          float f[kN];
+          Vec16<E>::unpack(v[u][a], f);
+#pragma unroll
+          for (int e = 0; e < kN; ++e) acc[a][e] += f[e];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < kRestoreVecsPerThread; ++a) {
+    const int c = threadIdx.x + 256 * a;
+    if (c >= row_vecs) continue;
+#pragma unroll
+    for (int e = 0; e < kN; ++e) partial[(size_t)blockIdx.x * row_vecs * kN + (size_t)c * kN + e] = acc[a][e];
+  }
+}
+
+template <typename E>
+__global__ void __launch_bounds__(256) restore_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int Dm,
+                                                                   E* __restrict__ dtoken) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= Dm) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * Dm + d];
+  if constexpr (sizeof(E) == 4) dtoken[d] = s;
+  else dtoken[d] = static_cast<E>(s);
+}
+
+static int restore_bwd_grid(long long rows) {
+  long long nb = (rows + 15) / 16;
+  const long long cap = (long long)num_sms() * 4;
+  return (int)(nb < cap ? nb : cap);
 }
 
 static int launch_gather(const void* src, int src_rows, const int64_t* index, int out_rows, int N,
@@ -520,6 +636,49 @@ int mc_restore_tokens(const void* x_kept, int elem_size, const void* mask_token,
   MC_REQUIRE(elem_size == 2 || elem_size == 4, MC_ERR_BAD_ARG, "restore_tokens: elem_size %d", elem_size);
   return launch_gather(x_kept, len_keep, ids_restore, L, N, (size_t)Dm * elem_size, len_keep,
                        mask_token, out, static_cast<cudaStream_t>(stream));
+}
+
+size_t mc_restore_tokens_bwd_workspace_bytes(int N, int L, int Dm) {
+  if (N <= 0 || L <= 0 || Dm <= 0) return 0;
+  return (size_t)restore_bwd_grid((long long)N * L) * Dm * sizeof(float);
+}
+
+int mc_restore_tokens_bwd(const void* grad_out, int elem_size, int is_bf16, const int64_t* ids_restore, int N, int L,
+                          int Dm, int len_keep, void* dx_kept, void* dmask_token, void* ws, size_t ws_bytes,
+                          void* stream) {
+  MC_ARCH_GUARD();
+  MC_REQUIRE(grad_out && ids_restore && dmask_token && ws && (dx_kept || len_keep == 0), MC_ERR_BAD_ARG,
+             "restore_tokens_bwd: null pointer");
+  MC_REQUIRE(N > 0 && L > 0 && Dm > 0 && len_keep >= 0 && len_keep <= L, MC_ERR_BAD_ARG, "restore_tokens_bwd: bad sizes");
+  MC_REQUIRE(elem_size == 2 || elem_size == 4, MC_ERR_BAD_ARG, "restore_tokens_bwd: elem_size %d", elem_size);
+  const size_t row_bytes = (size_t)Dm * elem_size;
+  MC_REQUIRE(row_bytes % 16 == 0 && row_bytes <= (size_t)256 * kRestoreVecsPerThread * 16 && aligned(grad_out, 16) &&
+                 (!dx_kept || aligned(dx_kept, 16)),
+             MC_ERR_UNSUPPORTED, "restore_tokens_bwd: rows must be 16-byte multiples of at most 16 KB, 16-byte aligned");
+  MC_REQUIRE(ws_bytes >= mc_restore_tokens_bwd_workspace_bytes(N, L, Dm), MC_ERR_WORKSPACE,
+             "restore_tokens_bwd: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long rows = (long long)N * L;
+  const int grid = restore_bwd_grid(rows), row_vecs = (int)(row_bytes / 16);
+  float* partial = static_cast<float*>(ws);
+  const uint4* go = static_cast<const uint4*>(grad_out);
+  uint4* dx = static_cast<uint4*>(dx_kept);
+  const int fb = (Dm + 255) / 256;
+  if (elem_size == 4) {
+    restore_bwd_kernel<float><<<grid, 256, 0, st>>>(go, ids_restore, rows, L, row_vecs, len_keep, dx, partial);
+    MC_LAUNCH_CHECK();
+    restore_bwd_finalize_kernel<float><<<fb, 256, 0, st>>>(partial, grid, Dm, static_cast<float*>(dmask_token));
+  } else if (is_bf16) {
+    restore_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(go, ids_restore, rows, L, row_vecs, len_keep, dx, partial);
+    MC_LAUNCH_CHECK();
+    restore_bwd_finalize_kernel<__nv_bfloat16><<<fb, 256, 0, st>>>(partial, grid, Dm, static_cast<__nv_bfloat16*>(dmask_token));
+  } else {
+    restore_bwd_kernel<__half><<<grid, 256, 0, st>>>(go, ids_restore, rows, L, row_vecs, len_keep, dx, partial);
+    MC_LAUNCH_CHECK();
+    restore_bwd_finalize_kernel<__half><<<fb, 256, 0, st>>>(partial, grid, Dm, static_cast<__half*>(dmask_token));
+  }
+  MC_LAUNCH_CHECK();
+  return MC_OK;
 }
 
 size_t mc_masked_mse_workspace_bytes(int N, int L) {

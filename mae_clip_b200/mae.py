@@ -57,17 +57,42 @@ def patchify(imgs: torch.Tensor, patch_size: int = 16, norm_pix: bool = False) -
     return out
 
 
+class _RestoreTokens(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_kept, mask_token, ids_restore):
+        require_cuda(x_kept, mask_token, ids_restore)
+        if x_kept.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            raise TypeError(f"restore_tokens: unsupported dtype {x_kept.dtype}")
+        x_kept = x_kept.contiguous()
+        token = mask_token.to(x_kept.dtype).reshape(-1).contiguous()
+        ids_restore = ids_restore.contiguous()
+        N, keep, D = x_kept.shape
+        L = ids_restore.shape[1]
+        out = torch.empty(N, L, D, device=x_kept.device, dtype=x_kept.dtype)
+        with torch.cuda.device(x_kept.device):
+            check(lib().mc_restore_tokens(ptr(x_kept), x_kept.element_size(), ptr(token), ptr(ids_restore), N, L, D,
+                                          keep, ptr(out), cur_stream()), "mc_restore_tokens")
+        ctx.save_for_backward(ids_restore)
+        ctx.cfg = (N, L, D, keep, mask_token.shape, mask_token.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ids_restore, = ctx.saved_tensors
+        N, L, D, keep, tok_shape, tok_dtype = ctx.cfg
+        g = grad_out.contiguous()
+        dx = torch.empty(N, keep, D, device=g.device, dtype=g.dtype)
+        dtok = torch.empty(D, device=g.device, dtype=g.dtype)
+        with torch.cuda.device(g.device):
+            from ._lib import workspace
+            ws = workspace(lib().mc_restore_tokens_bwd_workspace_bytes(N, L, D), g.device)
+            check(lib().mc_restore_tokens_bwd(ptr(g), g.element_size(), int(g.dtype == torch.bfloat16), ptr(ids_restore), N,
+                                              L, D, keep, ptr(dx), ptr(dtok), ptr(ws), ws.numel(), cur_stream()),
+                  "mc_restore_tokens_bwd")
+        return dx, dtok.reshape(tok_shape).to(tok_dtype), None
+
+
 def restore_tokens(x_kept: torch.Tensor, mask_token: torch.Tensor, ids_restore: torch.Tensor):
-    """Decoder-side glue: (N, len_keep, D) kept tokens + a (D,) mask token -> (N, L, D) in original
-    patch order.  No autograd yet (SURVEY.md section 8 f rank 2)."""
-    require_cuda(x_kept, mask_token, ids_restore)
-    x_kept = x_kept.contiguous()
-    mask_token = mask_token.to(x_kept.dtype).reshape(-1).contiguous()
-    N, keep, D = x_kept.shape
-    L = ids_restore.shape[1]
-    out = torch.empty(N, L, D, device=x_kept.device, dtype=x_kept.dtype)
-    with torch.cuda.device(x_kept.device):
-        check(lib().mc_restore_tokens(ptr(x_kept), x_kept.element_size(), ptr(mask_token),
-                                      ptr(ids_restore.contiguous()), N, L, D, keep, ptr(out),
-                                      cur_stream()), "mc_restore_tokens")
-    return out
+    """Decoder-side glue (SURVEY.md section 8 f rank 2): (N, len_keep, D) kept tokens + a (D,) mask
+    token -> (N, L, D) in original patch order.  Differentiable in the kept tokens and the mask token."""
+    return _RestoreTokens.apply(x_kept, mask_token, ids_restore)

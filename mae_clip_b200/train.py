@@ -183,6 +183,7 @@ class GraphedStep:
         with torch.cuda.graph(self.graph):
             self.static_loss = loss_fn(*self.static_in)
             self.static_loss.backward()
+        self.static_grads = [p.grad for p in self.params]  # written by every replay
         self.loss_fn = loss_fn
 
     def _eager(self, loss_fn):
@@ -198,6 +199,8 @@ class GraphedStep:
         for dst, src in zip(self.static_in, inputs):
             dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        for p, g in zip(self.params, self.static_grads):
+            p.grad = g  # re-attach: callers may have cleared .grad (zero_grad(set_to_none=True)) since the last replay
         if self.optimizer is not None:
             # bias corrections change every step: the optimiser launch stays outside the graph (one launch)
             self.optimizer.step()

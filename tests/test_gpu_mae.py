@@ -121,3 +121,35 @@ def test_masked_mse_full_size_properties():
     la = m.masked_mse_loss(pred, imgs, mask)
     per_patch = ((pred - target) ** 2).mean(-1)
     assert abs(la.item() - ((per_patch * mask).sum() / mask.sum()).item()) < 1e-5 * la.item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N,L,D,ratio", [(8, 196, 768, 0.75), (3, 50, 64, 0.5), (5, 196, 512, 0.9), (2, 16, 8, 0.0)])
+def test_restore_tokens_forward_backward(dtype, N, L, D, ratio):
+    """Decoder-side un-shuffle (SURVEY 8 f rank 2) against oracle/mae_ref.restore_tokens_ref (cat mask tokens +
+    gather through ids_restore, as in the published MAE decoder): forward bit-exact, gradients of the kept tokens
+    bit-exact (a copy) and of the mask token to fp32-accumulation accuracy."""
+    import mae_clip_b200 as m
+    g = torch.Generator().manual_seed(N * 100 + L)
+    noise = torch.rand(N, L, generator=g)
+    keep = mae_ref.len_keep_for(L, ratio)
+    ids_restore = torch.argsort(torch.argsort(noise, dim=1, stable=True), dim=1, stable=True)
+    xk = torch.randn(N, keep, D, generator=g).to(dtype)
+    tok = torch.randn(D, generator=g).to(dtype)
+    go = torch.randn(N, L, D, generator=g).to(dtype)
+
+    def ref(xk, tok):
+        xk = xk.clone().requires_grad_(True)
+        tok = tok.clone().requires_grad_(True)
+        out = mae_ref.restore_tokens_ref(xk, tok, ids_restore)
+        out.backward(go.to(out.dtype))
+        return out.detach(), xk.grad, tok.grad
+
+    o_ref, dx_ref, dt_ref = ref(xk.float(), tok.float())
+    xc, tc = xk.cuda().requires_grad_(True), tok.cuda().requires_grad_(True)
+    out = m.restore_tokens(xc, tc, ids_restore.cuda())
+    out.backward(go.cuda())
+    assert out.dtype == dtype and torch.equal(out.detach().cpu().float(), o_ref)
+    assert torch.equal(xc.grad.cpu().float(), dx_ref)
+    tol = 1e-6 if dtype == torch.float32 else 8e-3  # bf16: the result is rounded once to bf16
+    assert rel_err(tc.grad.float(), dt_ref) < tol
