@@ -199,6 +199,28 @@ __global__ void __launch_bounds__(256) amax2d_kernel(const float* __restrict__ s
   if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(amax_bits, __float_as_uint(a));
 }
 
+// dense case (lds == C): the matrix is one flat array; four 16-byte loads in flight per thread
+__global__ void __launch_bounds__(256) amax_flat_kernel(const float4* __restrict__ src, size_t n4,
+                                                        unsigned int* __restrict__ amax_bits) {
+  float a = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    const float4 v0 = ld_stream(src + i), v1 = ld_stream(src + i + stride), v2 = ld_stream(src + i + 2 * stride),
+                 v3 = ld_stream(src + i + 3 * stride);
+    a = fmaxf(a, fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))));
+    a = fmaxf(a, fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))));
+    a = fmaxf(a, fmaxf(fmaxf(fabsf(v2.x), fabsf(v2.y)), fmaxf(fabsf(v2.z), fabsf(v2.w))));
+    a = fmaxf(a, fmaxf(fmaxf(fabsf(v3.x), fabsf(v3.y)), fmaxf(fabsf(v3.z), fabsf(v3.w))));
+  }
+  for (; i < n4; i += stride) {
+    const float4 v = ld_stream(src + i);
+    a = fmaxf(a, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  a = warp_max(a);
+  if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(amax_bits, __float_as_uint(a));
+}
+
 __device__ __forceinline__ float scale_from_amax(float amax) {
   float s = 1.f;
   if (amax > 0.f && amax < INFINITY) {
@@ -250,6 +272,97 @@ __global__ void __launch_bounds__(256) stage_T_kernel(const float* __restrict__ 
   }
 }
 
+__device__ __forceinline__ void split4(const float4 v, float s, uint2& h, uint2& l) {
+  const float x[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
+  __half hh[4], ll[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    hh[e] = __float2half_rn(x[e]);
+    ll[e] = __float2half_rn(x[e] - __half2float(hh[e]));
+  }
+  __half2 h01 = __halves2half2(hh[0], hh[1]), h23 = __halves2half2(hh[2], hh[3]);
+  __half2 l01 = __halves2half2(ll[0], ll[1]), l23 = __halves2half2(ll[2], ll[3]);
+  h = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+  l = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+}
+
+// dense, pitch == C == lds: flat 16-byte loads, 8-byte stores to each plane
+__global__ void __launch_bounds__(256) stage_flat_kernel(const float4* __restrict__ src, size_t n4,
+                                                         uint2* __restrict__ hi, uint2* __restrict__ lo,
+                                                         float* __restrict__ scale) {
+  const float s = scale_from_amax(__uint_as_float(reinterpret_cast<const unsigned int*>(scale)[2]));
+  if (blockIdx.x == 0 && threadIdx.x == 0) { scale[0] = s; scale[1] = 1.f / s; }
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld_stream(src + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      uint2 h, l;
+      split4(v[u], s, h, l);
+      hi[i + u * stride] = h;
+      lo[i + u * stride] = l;
+    }
+  }
+  for (; i < n4; i += stride) {
+    uint2 h, l;
+    split4(ld_stream(src + i), s, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// transposing stage, 64 x 64 tiles: 16-byte loads along the source rows, 32-byte runs per thread along the
+// destination rows (a warp writes eight full 128-byte lines per plane).  Needs R % 64 == 0 handled by guards,
+// C % 4 == 0, lds % 4 == 0, pitch % 8 == 0.
+__global__ void __launch_bounds__(256) stage_T64_kernel(const float* __restrict__ src, int R, int C, int64_t lds,
+                                                        int pitch, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                        float* __restrict__ scale) {
+  __shared__ float tile[64][65];
+  const float s = scale_from_amax(__uint_as_float(reinterpret_cast<const unsigned int*>(scale)[2]));
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { scale[0] = s; scale[1] = 1.f / s; }
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int lc4 = threadIdx.x & 15, lr = threadIdx.x >> 4;  // 16 float4 columns x 16 rows per pass
+  float4 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + lr + 16 * i, c = c0 + 4 * lc4;
+    v[i] = (r < R && c < C) ? ld_stream(reinterpret_cast<const float4*>(src + (size_t)r * lds + c))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);  // C % 4 == 0: a float4 is inside or outside
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float* t = &tile[lr + 16 * i][4 * lc4];
+    t[0] = v[i].x * s; t[1] = v[i].y * s; t[2] = v[i].z * s; t[3] = v[i].w * s;
+  }
+  __syncthreads();
+  // destination row = source column c0 + orow; this thread writes 16 consecutive destination columns
+  const int orow = threadIdx.x >> 2, seg = threadIdx.x & 3;
+  const int drow = c0 + orow, dcol0 = r0 + 16 * seg;
+  if (drow >= C || dcol0 >= pitch) return;
+  uint32_t hw[8], lw[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float x0 = tile[16 * seg + 2 * j][orow], x1 = tile[16 * seg + 2 * j + 1][orow];
+    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+    __half2 hh = __halves2half2(h0, h1);
+    __half2 ll = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+    hw[j] = *reinterpret_cast<uint32_t*>(&hh);
+    lw[j] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  uint4* ph = reinterpret_cast<uint4*>(hi + (size_t)drow * pitch + dcol0);
+  uint4* pl = reinterpret_cast<uint4*>(lo + (size_t)drow * pitch + dcol0);
+  if (dcol0 + 16 <= pitch) {
+    ph[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); ph[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+    pl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]); pl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+  } else {  // pitch % 8 == 0: the row ends after the first half
+    ph[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    pl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
 static size_t plane_elems(int rows, int cols) { return (size_t)rows * round_up((size_t)cols, 8); }
 
 size_t planes_bytes(int rows, int cols) {
@@ -279,13 +392,33 @@ int stage(const float* src, int R, int C, int64_t lds, int transpose, const Plan
   int ab = (int)((total + 255) / 256);
   const int cap = num_sms() * 8;
   if (ab > cap) ab = cap;
-  amax2d_kernel<<<ab, 256, 0, st>>>(src, R, C, lds, reinterpret_cast<unsigned int*>(dst.scale) + 2);
+  const bool flat = lds == C && total % 4 == 0 && aligned(src, 16);
+  if (flat) {
+    int fb = (int)((total / 4 + 1023) / 1024);
+    if (fb > cap) fb = cap;
+    if (fb < 1) fb = 1;
+    amax_flat_kernel<<<fb, 256, 0, st>>>(reinterpret_cast<const float4*>(src), total / 4,
+                                         reinterpret_cast<unsigned int*>(dst.scale) + 2);
+  } else {
+    amax2d_kernel<<<ab, 256, 0, st>>>(src, R, C, lds, reinterpret_cast<unsigned int*>(dst.scale) + 2);
+  }
   MC_LAUNCH_CHECK();
   if (!transpose) {
-    const size_t tot = (size_t)R * dst.pitch;
-    int nb = (int)((tot + 255) / 256);
-    if (nb > cap) nb = cap;
-    stage_kernel<<<nb, 256, 0, st>>>(src, R, C, lds, dst.pitch, dst.hi, dst.lo, dst.scale);
+    if (flat && dst.pitch == C) {
+      int fb = (int)((total / 4 + 1023) / 1024);
+      if (fb > cap) fb = cap;
+      if (fb < 1) fb = 1;
+      stage_flat_kernel<<<fb, 256, 0, st>>>(reinterpret_cast<const float4*>(src), total / 4,
+                                            reinterpret_cast<uint2*>(dst.hi), reinterpret_cast<uint2*>(dst.lo), dst.scale);
+    } else {
+      const size_t tot = (size_t)R * dst.pitch;
+      int nb = (int)((tot + 255) / 256);
+      if (nb > cap) nb = cap;
+      stage_kernel<<<nb, 256, 0, st>>>(src, R, C, lds, dst.pitch, dst.hi, dst.lo, dst.scale);
+    }
+  } else if (C % 4 == 0 && lds % 4 == 0 && aligned(src, 16)) {
+    dim3 grid((dst.pitch + 63) / 64, (C + 63) / 64);  // covers the padding columns [R, pitch) too
+    stage_T64_kernel<<<grid, 256, 0, st>>>(src, R, C, lds, dst.pitch, dst.hi, dst.lo, dst.scale);
   } else {
     // cover the padding columns [R, pitch) too
     dim3 grid((dst.pitch + 31) / 32, (C + 31) / 32);

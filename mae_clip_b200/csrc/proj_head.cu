@@ -175,6 +175,41 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
   if (threadIdx.x == 0 && oc < cols) out[oc] = v;
 }
 
+// first stage of a tall column sum: block b sums its contiguous slice of rows with 16-byte loads
+// (four in flight per thread) and writes part[b][cols]; colsum_kernel then folds the few partial rows.
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ in, int rows, int cols,
+                                                             float* __restrict__ part) {
+  __shared__ float4 sm[256];
+  const int cols4 = cols >> 2, rsubs = 256 / cols4;
+  const int c4 = threadIdx.x % cols4, rsub = threadIdx.x / cols4;
+  const int per = (rows + gridDim.x - 1) / gridDim.x;
+  const int rbeg = blockIdx.x * per, rend = min(rows, rbeg + per);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rsub < rsubs) {
+    const float4* p = reinterpret_cast<const float4*>(in) + c4;
+    int r = rbeg + rsub;
+    for (; r + 3 * rsubs < rend; r += 4 * rsubs) {
+      const float4 a = ld_stream(p + (size_t)r * cols4), b = ld_stream(p + (size_t)(r + rsubs) * cols4);
+      const float4 c = ld_stream(p + (size_t)(r + 2 * rsubs) * cols4), d = ld_stream(p + (size_t)(r + 3 * rsubs) * cols4);
+      acc.x += (a.x + b.x) + (c.x + d.x); acc.y += (a.y + b.y) + (c.y + d.y);
+      acc.z += (a.z + b.z) + (c.z + d.z); acc.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; r < rend; r += rsubs) {
+      const float4 a = ld_stream(p + (size_t)r * cols4);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  if (rsub == 0) {
+    for (int k = 1; k < rsubs; ++k) {
+      const float4 o = sm[k * cols4 + c4];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    reinterpret_cast<float4*>(part + (size_t)blockIdx.x * cols)[c4] = acc;
+  }
+}
+
 // dp = dh * gelu'(projected) + dz   (in place on dh)
 __global__ void __launch_bounds__(256) gelu_bwd_add_kernel(float* __restrict__ dh,
                                                            const float* __restrict__ projected,
@@ -196,6 +231,26 @@ static int ln_blocks(int B) {
   int nb = (B + 7) / 8;
   int cap = num_sms() * 8;  // 8 resident blocks per SM keep enough 16-byte loads in flight
   return nb < cap ? nb : cap;
+}
+
+// out[c] = sum_r in[r][c]; tall inputs go through per-block partials in `scratch` (>= scratch_rows x cols floats)
+static int colsum_rows(const float* in, int rows, int cols, float* out, float* scratch, int scratch_rows,
+                       cudaStream_t st) {
+  dim3 blk(32, 32);
+  const bool two_stage = rows >= 4096 && cols % 4 == 0 && cols <= 1024 && aligned(in, 16) && scratch && scratch_rows >= 8;
+  if (!two_stage) {
+    colsum_kernel<<<(cols + 31) / 32, blk, 0, st>>>(in, rows, cols, out);
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+  }
+  int nb = (rows + 63) / 64;
+  if (nb > scratch_rows) nb = scratch_rows;
+  if (nb > num_sms() * 4) nb = num_sms() * 4;
+  colsum_partial_kernel<<<nb, 256, 0, st>>>(in, rows, cols, scratch);
+  MC_LAUNCH_CHECK();
+  colsum_kernel<<<(cols + 31) / 32, blk, 0, st>>>(scratch, nb, cols, out);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
 }
 
 template <int NV>
@@ -408,8 +463,7 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
     MC_LAUNCH_CHECK();
     MC_CUDA(cudaMemcpyAsync(dgamma, t.dh, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
     MC_CUDA(cudaMemcpyAsync(dbeta, t.dh + P, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
-    colsum_kernel<<<(P + 31) / 32, blk, 0, st>>>(t.dy, B, P, db_fc);
-    MC_LAUNCH_CHECK();
+    if ((rc = colsum_rows(t.dy, B, P, db_fc, t.partials, 2 * blocks, st))) return rc;  // partials are free again
     // dWf[n,k] = sum_m dy[m,n] hidden[m,k]  ->  (dy^T) . (hidden^T)^T, K = B (split-K)
     if ((rc = tcg::stage(t.dy, B, P, P, 1, t.dyT, st))) return rc;
     if ((rc = tcg::stage(hidden, B, P, P, 1, t.hT, st))) return rc;
@@ -427,8 +481,7 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
       if (nb > cap) nb = cap;
       gelu_bwd_add_kernel<<<nb, 256, 0, st>>>(t.dh, projected, t.dz, n4);  // dp = dh * gelu'(p) + dz
       MC_LAUNCH_CHECK();
-      colsum_kernel<<<(P + 31) / 32, blk, 0, st>>>(t.dh, B, P, db_proj);
-      MC_LAUNCH_CHECK();
+      if ((rc = colsum_rows(t.dh, B, P, db_proj, t.partials, 2 * blocks, st))) return rc;
     }
     // dWp[n,e] = sum_m dp[m,n] x[m,e]  ->  (dp^T) . (x^T)^T, K = B (split-K)
     if ((rc = tcg::stage(t.dh, B, P, P, 1, t.dpT, st))) return rc;
@@ -458,8 +511,7 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
     MC_LAUNCH_CHECK();
     MC_CUDA(cudaMemcpyAsync(dgamma, w.dh, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
     MC_CUDA(cudaMemcpyAsync(dbeta, w.dh + P, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
-    colsum_kernel<<<(P + 31) / 32, blk, 0, st>>>(w.dy, B, P, db_fc);
-    MC_LAUNCH_CHECK();
+    if ((rc = colsum_rows(w.dy, B, P, db_fc, w.partials, 2 * blocks, st))) return rc;
   }
   // dWf[n,k] = sum_m dy[m,n] hidden[m,k]
   SgemmArgs g1{w.dy, 1, P, hidden, P, 1, dw_fc, P, P, P, B, 1.f, nullptr, nullptr, 0};
@@ -474,9 +526,7 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
     if (nb > cap) nb = cap;
     gelu_bwd_add_kernel<<<nb, 256, 0, st>>>(w.dh, projected, w.dz, n4);
     MC_LAUNCH_CHECK();
-    dim3 blk(32, 32);
-    colsum_kernel<<<(P + 31) / 32, blk, 0, st>>>(w.dh, B, P, db_proj);
-    MC_LAUNCH_CHECK();
+    if ((rc = colsum_rows(w.dh, B, P, db_proj, w.partials, 2 * blocks, st))) return rc;
   }
   // dWp[n,e] = sum_m dp[m,n] x[m,e]
   SgemmArgs g3{w.dh, 1, P, x, E, 1, dw_proj, E, P, E, B, 1.f, nullptr, nullptr, 0};
