@@ -269,6 +269,13 @@ int mc_similarity_topk(const float* text, int Q, const float* image, long long N
                        float* out_vals, int64_t* out_idx, float* scores_out, void* ws,
                        size_t ws_bytes, void* stream);
 
+/* "next" row 4: image side of the data feed        dataset.py:33-34,49 (A.Normalize + permute + float)
+ * hwc: (N, H, W, 3) uint8 DEVICE pixels (after the reference's cv2 resize, which stays on the host);
+ * out_nchw: (N, 3, H, W) fp32 = (pixel - mean*max_pixel_value) * (1 / (std*max_pixel_value)).
+ * mean3_host / std3_host: HOST arrays of three floats (albumentations defaults: ImageNet statistics). */
+int mc_normalize_images(const uint8_t* hwc, int N, int H, int W, const float* mean3_host,
+                        const float* std3_host, float max_pixel_value, float* out_nchw, void* stream);
+
 /* "next" row 1: the optimiser step of the training driver      main.py:103-105, main.py:59
  * (torch.optim.AdamW, decoupled weight decay, no amsgrad).  params / grads / exp_avg /
  * exp_avg_sq: HOST arrays of `ntensors` device pointers (dense fp32), numel: HOST array of
