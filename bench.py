@@ -496,29 +496,68 @@ def extras(dev, mode, peaks):
     ms = timeit(c2)
     out["c2_loss_fwd_bwd_B1024"] = {"ms": ms, "samples_per_s": 1024 / (ms * 1e-3)}
 
+    # C2 again with the whole fwd+bwd captured in one CUDA graph (launch-bound regime)
+    from mae_clip_b200.train import GraphedStep
+    Ig, Tg = I.detach().clone().requires_grad_(True), T.detach().clone().requires_grad_(True)
+    gs = GraphedStep(lambda a, b: m.clip_contrastive_loss(a, b, 1.0, mode=mode), [Ig, Tg], [])
+    ms = timeit(lambda: gs.graph.replay())
+    out["c2_loss_fwd_bwd_B1024_cuda_graph"] = {"ms": ms, "samples_per_s": 1024 / (ms * 1e-3)}
+
+    # C5 (N = 1024, 196 patches x 768, ratio 0.75) through the C ABI with pre-allocated outputs; algorithmic bytes of
+    # SURVEY 8(d); every working set is several times the 126 MB L2, so nothing is flushed
+    from mae_clip_b200._lib import check as ck, cur_stream as cs, lib as L_, ptr as p_
+    lib = L_()
     N, L, P = 1024, 196, 768
+    keep = int(L * 0.25)
     x = torch.randn(N, L, P, device=dev)
     noise = torch.rand(N, L, device=dev)
     imgs = torch.randn(N, 3, 224, 224, device=dev)
-    pred = torch.randn(N, L, P, device=dev, requires_grad=True)
-    keep = int(L * 0.25)
-    ms = timeit(lambda: m.random_masking(x, 0.75, noise), iters=10)
-    bytes_m1 = 16 * N * L + 2 * N * keep * P * 4
-    out["c5_random_masking_N1024_r075"] = {"ms": ms, "GBps": bytes_m1 / ms / 1e6, "frac_hbm": bytes_m1 / ms / 1e6 / peaks["hbm"]}
-    _xm, mask, _r = m.random_masking(x, 0.75, noise)
-    r_eff = (L - keep) / L
-    ms_f = timeit(lambda: m.masked_mse_loss(pred.detach(), imgs, mask), iters=10)
-    bytes_f = r_eff * N * L * P * 8 + 4 * N * L
-    out["c5_masked_mse_fwd_N1024_r075"] = {"ms": ms_f, "GBps": bytes_f / ms_f / 1e6, "frac_hbm": bytes_f / ms_f / 1e6 / peaks["hbm"]}
+    pred = torch.randn(N, L, P, device=dev)
+    dpred = torch.empty_like(pred)
+    xm = torch.empty(N, keep, P, device=dev)
+    mask = torch.empty(N, L, device=dev)
+    restore = torch.empty(N, L, device=dev, dtype=torch.int64)
+    ids_keep = torch.empty(N, keep, device=dev, dtype=torch.int64)
+    loss, msum = torch.empty((), device=dev), torch.empty((), device=dev)
+    ws = torch.empty(lib.mc_masked_mse_workspace_bytes(N, L), dtype=torch.uint8, device=dev)
 
-    def fb():
-        pred.grad = None
-        m.masked_mse_loss(pred, imgs, mask).backward()
-    ms_fb = timeit(fb, iters=10)
-    bytes_fb = 2 * bytes_f + N * L * P * 4
-    out["c5_masked_mse_fwd_bwd_N1024_r075"] = {"ms": ms_fb, "GBps": bytes_fb / ms_fb / 1e6,
-                                               "frac_hbm": bytes_fb / ms_fb / 1e6 / peaks["hbm"],
-                                               "samples_per_s": N / (ms_fb * 1e-3)}
+    def hbm(name, fn, nbytes, **kw):
+        ms = timeit(fn, iters=10)
+        out[name] = dict(ms=ms, GBps=nbytes / ms / 1e6, frac_hbm=nbytes / ms / 1e6 / peaks["hbm"], **kw)
+        return ms
+
+    hbm("c5_random_masking_N1024_r075",
+        lambda: ck(lib.mc_random_masking(p_(x), 4, p_(noise), N, L, P, keep, p_(xm), p_(mask), p_(restore), p_(ids_keep), cs())),
+        16 * N * L + 2 * N * keep * P * 4)
+    r_eff = (L - keep) / L
+    bytes_f = r_eff * N * L * P * 8 + 4 * N * L
+    ms_f = hbm("c5_masked_mse_fwd_N1024_r075",
+               lambda: ck(lib.mc_masked_mse_fwd(p_(pred), 4, p_(imgs), p_(mask), N, 224, 224, 16, 1, p_(loss), p_(msum), p_(ws),
+                                                ws.numel(), cs())), bytes_f)
+    ms_b = hbm("c5_masked_mse_bwd_N1024_r075",
+               lambda: ck(lib.mc_masked_mse_bwd(p_(pred), 4, p_(imgs), p_(mask), N, 224, 224, 16, 1, p_(msum), None, p_(dpred),
+                                                cs())), bytes_f + N * L * P * 4)
+    out["c5_masked_mse_fwd_bwd_N1024_r075"] = {"ms": ms_f + ms_b, "samples_per_s": N / ((ms_f + ms_b) * 1e-3)}
+    del x, xm, pred, dpred, imgs
+
+    # L1-L2: one ProjectionHead forward + backward (dropout on), image head E = 2048 (dx needed) and text head E = 768
+    for E, need_dx in ((2048, True), (768, False)):
+        Bh = 32768
+        h = m.ProjectionHead(E, gemm_mode=mode).to(dev).train()
+        xx = torch.randn(Bh, E, device=dev, requires_grad=need_dx)
+        keepm = (torch.rand(Bh, 256, device=dev) > 0.1).to(torch.uint8)
+        go = torch.randn(Bh, 256, device=dev)
+
+        def head_step():
+            for q in h.parameters():
+                q.grad = None
+            xx.grad = None
+            h(xx, keep_mask=keepm).backward(go)
+        ms = timeit(head_step, iters=5, warm=3)
+        flops = 2.0 * Bh * 256 * (E + 256) * 3 - (0 if need_dx else 2.0 * Bh * E * 256)
+        out[f"proj_head_fwd_bwd_B{Bh}_E{E}"] = {"ms": ms, "algorithmic_TFLOPs": flops / ms / 1e9,
+                                                "samples_per_s": Bh / (ms * 1e-3)}
+        del h, xx, keepm, go
     return out
 
 

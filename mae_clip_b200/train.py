@@ -166,8 +166,10 @@ class GraphedStep:
     elsewhere; the step counter advances on the host per replay."""
 
     def __init__(self, loss_fn, example_inputs, params, optimizer=None, warmup=3):
-        self.static_in = [t.clone() for t in example_inputs]
-        self.params = [p for p in params if p.requires_grad]
+        # inputs that require grad (e.g. embeddings fed to the loss) keep that property on their static copies;
+        # their gradients are then read from ``static_in[i].grad`` after a replay
+        self.static_in = [t.detach().clone().requires_grad_(t.requires_grad) for t in example_inputs]
+        self.params = [p for p in params if p.requires_grad] + [t for t in self.static_in if t.requires_grad]
         self.optimizer = optimizer
         if optimizer is not None and not isinstance(optimizer, AdamW):
             raise TypeError("GraphedStep captures mae_clip_b200.AdamW (its launch carries the step as an argument)")
@@ -196,8 +198,9 @@ class GraphedStep:
         return loss
 
     def __call__(self, *inputs):
-        for dst, src in zip(self.static_in, inputs):
-            dst.copy_(src, non_blocking=True)
+        with torch.no_grad():
+            for dst, src in zip(self.static_in, inputs):
+                dst.copy_(src, non_blocking=True)
         self.graph.replay()
         for p, g in zip(self.params, self.static_grads):
             p.grad = g  # re-attach: callers may have cleared .grad (zero_grad(set_to_none=True)) since the last replay

@@ -142,12 +142,13 @@ def test_graphed_step_matches_eager():
     def loss_fn(I, T):
         return m.clip_contrastive_loss(head(I), T, 1.0)
 
-    gs = GraphedStep(loss_fn, [I0, T0], params)
+    gs = GraphedStep(loss_fn, [I0, T0.requires_grad_(True)], params)  # the text embeddings want a gradient too
     for seed in (5, 6):
         I = loss_ref.make_embeddings(B, 256, seed=seed, scale=0.3).cuda()
-        T = loss_ref.make_embeddings(B, 256, seed=seed + 10, scale=0.3).cuda()
+        T = loss_ref.make_embeddings(B, 256, seed=seed + 10, scale=0.3).cuda().requires_grad_(True)
         lg = gs(I, T).clone()
         graph_grads = [p.grad.clone() for p in params]
+        graph_dT = gs.static_in[1].grad.clone()
         for p in params:
             p.grad = None
         le = loss_fn(I, T)
@@ -155,3 +156,4 @@ def test_graphed_step_matches_eager():
         assert abs(lg.item() - le.item()) <= 1e-6 * abs(le.item())
         for gg, p in zip(graph_grads, params):
             assert rel_err(gg, p.grad) < 1e-6
+        assert rel_err(graph_dT, T.grad) < 1e-6
