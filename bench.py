@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--workload", default="c4", choices=["c4", "c2"])
     ap.add_argument("--mode", default="auto")
     ap.add_argument("--batch", type=int, default=0, help="global batch (default: 32768 for c4, 1024 for c2)")
-    ap.add_argument("--cpu-sample-batch", type=int, default=4096)
+    ap.add_argument("--cpu-sample-batch", type=int, default=8192,
+                    help="rows of the bounded CPU sample (the reference materialises ~20 B x B fp32 tensors: 5 GiB at 8192)")
     ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: peer = our kernels over mapped peer memory (default), nccl = torch.distributed all-gathers")
     ap.add_argument("--no-extra", action="store_true")

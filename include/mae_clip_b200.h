@@ -12,8 +12,10 @@
  *  - every pointer is a DEVICE pointer unless the name ends in `_host`;
  *  - tensors are dense row-major unless strides are passed explicitly;
  *  - `stream` is a cudaStream_t passed as void* (0 = default stream);
- *  - no entry point allocates device memory: scratch comes in through
- *    `ws`/`ws_bytes`, sized by the matching `*_workspace_bytes` query;
+ *  - no entry point on the step path allocates device memory: scratch comes
+ *    in through `ws`/`ws_bytes`, sized by the matching `*_workspace_bytes`
+ *    query (the one exception is the set-up call mc_peer_alloc, which creates
+ *    the exchange region other processes map);
  *  - every entry point returns an mc_status (0 = ok) and never throws;
  *    mc_last_error_string() describes the last failure on the calling thread;
  *  - entry points are re-entrant; the library keeps no mutable global state
