@@ -1263,11 +1263,8 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float*
   pp.wscale = wscale;
 
   auto kern = pair_kernel<PHASE, PASSES>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};  // per template instantiation, one bit per device
+  MC_CUDA(ensure_dynamic_smem(kern, kSmemBytes, attr_done));
   const long njobs = (long)sp.n_row_blocks * sp.nsplit;
   int npairs = num_sms() / 2;
   if (njobs < npairs) npairs = (int)njobs;

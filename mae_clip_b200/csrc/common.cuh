@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/mae_clip_b200.h"
@@ -51,14 +52,32 @@ void count_launch();
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cached[64];  // per device; 0 = not queried yet
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::atomic<int>& slot = cached[dev & 63];
+  int n = slot.load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    slot.store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory, once per device (the attribute is
+// per context).  `done` is a per-kernel bit mask of devices already configured; a racing second
+// call just sets the same attribute again.
+template <typename F>
+inline cudaError_t ensure_dynamic_smem(F* kernel, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
 }
 
 // ---- device helpers ----

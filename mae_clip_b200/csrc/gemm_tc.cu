@@ -511,12 +511,12 @@ int gemm(const Planes& A, const Planes& B, int M, int N, int K, const GemmOut& o
   const int njobs = p.tiles_m * p.tiles_n * p.ksplit;
   const int grid = njobs < num_sms() ? njobs : num_sms();
   if (epilogue == kEpiGelu) {
-    static bool set = false;
-    if (!set) { MC_CUDA(cudaFuncSetAttribute(gemm_kernel<kEpiGelu>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); set = true; }
+    static std::atomic<unsigned long long> done{0};
+    MC_CUDA(ensure_dynamic_smem(gemm_kernel<kEpiGelu>, kSmem, done));
     gemm_kernel<kEpiGelu><<<grid, kThreads, kSmem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   } else {
-    static bool set = false;
-    if (!set) { MC_CUDA(cudaFuncSetAttribute(gemm_kernel<kEpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); set = true; }
+    static std::atomic<unsigned long long> done{0};
+    MC_CUDA(ensure_dynamic_smem(gemm_kernel<kEpiPlain>, kSmem, done));
     gemm_kernel<kEpiPlain><<<grid, kThreads, kSmem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   }
   MC_LAUNCH_CHECK();

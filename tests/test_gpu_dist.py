@@ -66,3 +66,35 @@ def test_global_loss_two_gpus(mode, transport):
         assert abs(loss.item() - ref_loss) < lt * abs(ref_loss)
         assert rel_err(dI, ref_dI[r * b:(r + 1) * b]) < gt
         assert rel_err(dT, ref_dT[r * b:(r + 1) * b]) < gt
+
+
+@pytest.mark.parametrize("exchange_mode", ["push", "pull"])
+def test_peer_step_world1_matches_fused_path(exchange_mode):
+    """The whole peer-memory choreography (IPC region, push / pull staging, flag barrier, vector publish,
+    copy-out) on ONE GPU with a world of one: every kernel of csrc/peer.cu and the peer staging path runs,
+    and the result must equal the single-GPU fused call bit for bit (same planes, same sweeps)."""
+    import mae_clip_b200 as m
+    from mae_clip_b200 import peer
+    from mae_clip_b200.dist import PeerStep
+    if dist.is_initialized():
+        dist.destroy_process_group()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(_free_port())
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        b = 384
+        I = loss_ref.make_embeddings(b, 256, seed=11, scale=0.2).cuda()
+        T = loss_ref.make_embeddings(b, 256, seed=12, scale=0.2).cuda()
+        ex = peer.PeerExchange(b, 256)
+        step = PeerStep(ex, "tc_f16x3", exchange_mode=exchange_mode)
+        for _ in range(2):  # the region is reused
+            loss, saved = step.forward(I, T, 1.0)
+            dI, dT = step.backward(saved, 1.0, torch.tensor(2.0, device="cuda"))
+        Ic, Tc = I.clone().requires_grad_(True), T.clone().requires_grad_(True)
+        ref = m.clip_contrastive_loss(Ic, Tc, 1.0, mode="tc_f16x3")
+        (ref * 2.0).backward()
+        assert loss.item() == ref.item()
+        assert torch.equal(dI, Ic.grad) and torch.equal(dT, Tc.grad)
+        ex.close()
+    finally:
+        dist.destroy_process_group()
