@@ -86,11 +86,12 @@ def test_model_eval_loss_golden(golden):
     assert abs(loss.item() - float(z["ref_eval_loss"])) < LOSS_TOL * abs(float(z["ref_eval_loss"]))
 
 
-@pytest.mark.parametrize("B,E", [(1, 768), (32, 2048), (256, 768), (1000, 2048)])
+@pytest.mark.parametrize("B,E", [(1, 768), (32, 2048), (256, 768), (1000, 2048), (2048, 768), (2500, 2048), (4096, 768)])
 @pytest.mark.parametrize("need_dx", [True, False])
 def test_head_vs_oracle(B, E, need_dx):
     """Reference shapes (E = 2048 image / 768 text; the text tower is frozen so dx is optional,
-    modules.py:35) with a seeded dropout mask, against the CPU oracle."""
+    modules.py:35) with a seeded dropout mask, against the CPU oracle.  Below 2048 rows the default engine
+    takes the true-fp32 FMA path (launch-bound regime), from 2048 rows on the tcgen05 GEMMs (ragged 2500 too)."""
     import mae_clip_b200 as m
     g = torch.Generator().manual_seed(B + E)
     h = m.ProjectionHead(E)
