@@ -65,10 +65,13 @@ unsigned long long mc_kernel_launch_count(void);
  * Strides are in elements so the transposed views of CLIP.py:41 are accepted
  * without a copy.  row_lse / row_tsum (rows floats each) are kept for backward.
  * ------------------------------------------------------------------------- */
+/* ws: optional scratch of mc_soft_ce_workspace_bytes(rows, cols) (0 for small problems); with it the
+ * transposed-view forward splits the columns over more blocks (NULL / too small: single-kernel form). */
+size_t mc_soft_ce_workspace_bytes(int rows, int cols);
 int mc_soft_ce_fwd(const float* preds, int64_t p_row_stride, int64_t p_col_stride,
                    const float* targets, int64_t t_row_stride, int64_t t_col_stride,
                    int rows, int cols, float* loss_rows, float* row_lse, float* row_tsum,
-                   void* stream);
+                   void* ws, size_t ws_bytes, void* stream);
 /* dpreds / dtargets (either may be NULL) are written through their own element strides, so the
  * caller can give them the layout of the (possibly transposed) inputs and keep stores coalesced. */
 int mc_soft_ce_bwd(const float* preds, int64_t p_row_stride, int64_t p_col_stride,

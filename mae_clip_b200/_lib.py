@@ -31,7 +31,8 @@ SIGNATURES = {
     "mc_last_error_string": (C.c_char_p, []),
     "mc_device_supported": (_i, [_i]),
     "mc_kernel_launch_count": (C.c_ulonglong, []),
-    "mc_soft_ce_fwd": (_i, [_p, _i64, _i64, _p, _i64, _i64, _i, _i, _p, _p, _p, _p]),
+    "mc_soft_ce_workspace_bytes": (_sz, [_i, _i]),
+    "mc_soft_ce_fwd": (_i, [_p, _i64, _i64, _p, _i64, _i64, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "mc_soft_ce_bwd": (_i, [_p, _i64, _i64, _p, _i64, _i64, _i, _i, _p, _p, _p, _p, _i64, _i64, _p,
                             _i64, _i64, _p]),
     "mc_clip_loss_workspace_bytes": (_sz, [_i, _i, _i, _i]),

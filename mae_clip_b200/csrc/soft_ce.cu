@@ -102,6 +102,39 @@ __global__ void __launch_bounds__(1024) soft_ce_fwd_strided(Strided2D preds, Str
 // Memory is [c][r] with r contiguous, so a thread owns FOUR consecutive rows (one float4 per
 // column) and walks the columns of its group with four columns in flight.  block = 8 row-quads (x)
 // x 32 column groups (y): a warp touches four full 128-byte lines per load instruction.
+// Online log-sum-exp over four columns in flight for the four rows a lane owns: one running-max update (and at
+// most one rescale) per row per group of four columns, then four exponentials - about a third of the
+// instructions of an element-by-element update, which made the transposed forward issue-bound.
+template <typename Live>
+__device__ __forceinline__ void online_lse4(const float4 (&a)[4], const float4 (&b)[4], Live live, float (&m)[4],
+                                            float (&sacc)[4], float (&tsum)[4], float (&tp)[4]) {
+  float av[4][4], bv[4][4];
+  bool okv[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const bool ok = okv[u] = live(u);
+    av[u][0] = ok ? a[u].x : -INFINITY; av[u][1] = ok ? a[u].y : -INFINITY;
+    av[u][2] = ok ? a[u].z : -INFINITY; av[u][3] = ok ? a[u].w : -INFINITY;
+    bv[u][0] = ok ? b[u].x : 0.f; bv[u][1] = ok ? b[u].y : 0.f; bv[u][2] = ok ? b[u].z : 0.f; bv[u][3] = ok ? b[u].w : 0.f;
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float m4 = fmaxf(fmaxf(av[0][e], av[1][e]), fmaxf(av[2][e], av[3][e]));
+    if (m4 > m[e]) {
+      sacc[e] *= __expf(m[e] - m4);  // exp(-inf) = 0 covers the first group
+      m[e] = m4;
+    }
+    if (m[e] > -INFINITY) {  // an all-dead group before any live one leaves the accumulators untouched
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        sacc[e] += __expf(av[u][e] - m[e]);  // dead columns: exp(-inf) = 0
+        tsum[e] += bv[u][e];
+        if (okv[u]) tp[e] = fmaf(av[u][e], bv[u][e], tp[e]);  // a genuine -inf logit still propagates like torch
+      }
+    }
+  }
+}
+
 template <int QUADS>  // row-quads per block: 4 * QUADS rows, 256 / QUADS column groups
 __global__ void __launch_bounds__(256) soft_ce_fwd_tvec(const float* __restrict__ preds, int64_t p_cs,
                                                         const float* __restrict__ tg, int64_t t_cs, int rows, int cols,
@@ -124,18 +157,7 @@ __global__ void __launch_bounds__(256) soft_ce_fwd_tvec(const float* __restrict_
           b[u] = ld_stream(reinterpret_cast<const float4*>(tg + (int64_t)c * t_cs + r0));
         }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (c0 + G * u >= cols) continue;
-        const float av[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, bv[4] = {b[u].x, b[u].y, b[u].z, b[u].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (av[e] > m[e]) { sacc[e] = sacc[e] * __expf(m[e] - av[e]) + 1.f; m[e] = av[e]; }
-          else sacc[e] += __expf(av[e] - m[e]);
-          tsum[e] += bv[e];
-          tp[e] = fmaf(av[e], bv[e], tp[e]);
-        }
-      }
+      online_lse4(a, b, [&](int u) { return c0 + G * u < cols; }, m, sacc, tsum, tp);
     }
   }
 #pragma unroll
@@ -168,6 +190,82 @@ __global__ void __launch_bounds__(256) soft_ce_fwd_tvec(const float* __restrict_
       if (row_tsum) row_tsum[row] = ts;
     }
   }
+}
+
+// Column-split form for tall-enough problems: block = 64 row-quads (256 rows: a warp reads 512 contiguous
+// bytes of a column) x 4 column phases, grid.y = column slices; every block writes the (max, sum, sum t,
+// sum t*p) partials of its 256 rows for its slice, a second kernel merges the slices in a fixed order.
+__global__ void __launch_bounds__(256) soft_ce_fwd_tsplit(const float* __restrict__ preds, int64_t p_cs,
+                                                          const float* __restrict__ tg, int64_t t_cs, int rows, int cols,
+                                                          int cols_per_slice, float4* __restrict__ part /* [slices][rows] */) {
+  __shared__ float4 sm[4][256];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int r0 = (blockIdx.x * 64 + tx) * 4;
+  const int cbeg = blockIdx.y * cols_per_slice, cend = min(cols, cbeg + cols_per_slice);
+  float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, sacc[4] = {0.f, 0.f, 0.f, 0.f};
+  float tsum[4] = {0.f, 0.f, 0.f, 0.f}, tp[4] = {0.f, 0.f, 0.f, 0.f};
+  if (r0 < rows) {
+    for (int c0 = cbeg + ty; c0 < cend; c0 += 16) {
+      float4 a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + 4 * u;
+        if (c < cend) {
+          a[u] = ld_stream(reinterpret_cast<const float4*>(preds + (int64_t)c * p_cs + r0));
+          b[u] = ld_stream(reinterpret_cast<const float4*>(tg + (int64_t)c * t_cs + r0));
+        }
+      }
+      online_lse4(a, b, [&](int u) { return c0 + 4 * u < cend; }, m, sacc, tsum, tp);
+    }
+  }
+  // merge the four column phases of a row quad through shared memory: phase p holds row element e at [p][4*tx+e]
+#pragma unroll
+  for (int e = 0; e < 4; ++e) sm[ty][4 * tx + e] = make_float4(m[e], sacc[e], tsum[e], tp[e]);
+  __syncthreads();
+  const int rl = threadIdx.x;  // one of the block's 256 rows
+  const int row = blockIdx.x * 256 + rl;
+  if (row < rows) {
+    Lse t;
+    t.init();
+    float ts = 0.f, tps = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float4 v = sm[p][rl];
+      t.merge(v.x, v.y);
+      ts += v.z;
+      tps += v.w;
+    }
+    part[(size_t)blockIdx.y * rows + row] = make_float4(t.m, t.s, ts, tps);
+  }
+}
+
+__global__ void __launch_bounds__(256) soft_ce_fwd_tmerge(const float4* __restrict__ part, int slices, int rows,
+                                                          float* __restrict__ loss_rows, float* __restrict__ row_lse,
+                                                          float* __restrict__ row_tsum) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  Lse t;
+  t.init();
+  float ts = 0.f, tps = 0.f;
+  for (int s = 0; s < slices; ++s) {
+    const float4 v = part[(size_t)s * rows + row];
+    t.merge(v.x, v.y);
+    ts += v.z;
+    tps += v.w;
+  }
+  const float lse = t.value();
+  loss_rows[row] = lse * ts - tps;
+  if (row_lse) row_lse[row] = lse;
+  if (row_tsum) row_tsum[row] = ts;
+}
+
+// column slices so that ~4 blocks per SM exist; 0 = use the single-kernel form
+static int tsplit_slices(int rows, int cols) {
+  if (rows < 1024 || cols < 256) return 0;
+  const int gx = (rows / 4 + 63) / 64;
+  int slices = (mc::num_sms() * 4 + gx - 1) / gx;
+  if (slices > cols / 64) slices = cols / 64;
+  return slices < 2 ? 0 : slices;
 }
 
 // grid.x: blocks of 64 row-quads (256 rows), grid.y: column slices; thread = (row-quad, 4 column phases)
@@ -277,9 +375,15 @@ __global__ void __launch_bounds__(256) soft_ce_bwd_rowmajor(const float* __restr
 
 extern "C" {
 
+size_t mc_soft_ce_workspace_bytes(int rows, int cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  const int slices = mc::tsplit_slices(rows, cols);
+  return slices ? (size_t)slices * rows * sizeof(float4) : 0;
+}
+
 int mc_soft_ce_fwd(const float* preds, int64_t p_rs, int64_t p_cs, const float* targets,
                    int64_t t_rs, int64_t t_cs, int rows, int cols, float* loss_rows,
-                   float* row_lse, float* row_tsum, void* stream) {
+                   float* row_lse, float* row_tsum, void* ws, size_t ws_bytes, void* stream) {
   MC_ARCH_GUARD();
   MC_REQUIRE(preds && targets && loss_rows, MC_ERR_BAD_ARG, "soft_ce_fwd: null pointer");
   MC_REQUIRE(rows >= 0 && cols > 0, MC_ERR_BAD_ARG, "soft_ce_fwd: bad shape (%d, %d)", rows, cols);
@@ -292,6 +396,17 @@ int mc_soft_ce_fwd(const float* preds, int64_t p_rs, int64_t p_cs, const float* 
     int blocks = (rows + 7) / 8;
     mc::soft_ce_fwd_rowmajor<<<blocks, 256, 0, st>>>(P, T, rows, cols, loss_rows, row_lse, row_tsum,
                                                      vec_ok);
+  } else if (p_rs == 1 && t_rs == 1 && rows % 4 == 0 && p_cs % 4 == 0 && t_cs % 4 == 0 && mc::aligned(preds, 16) &&
+             mc::aligned(targets, 16) && ws && mc::aligned(ws, 16) && mc::tsplit_slices(rows, cols) > 0 &&
+             ws_bytes >= mc_soft_ce_workspace_bytes(rows, cols)) {
+    const int slices = mc::tsplit_slices(rows, cols);
+    const int cps = ((cols + slices - 1) / slices + 15) / 16 * 16;
+    const int ny = (cols + cps - 1) / cps;
+    dim3 grid((rows / 4 + 63) / 64, ny);
+    mc::soft_ce_fwd_tsplit<<<grid, 256, 0, st>>>(preds, p_cs, targets, t_cs, rows, cols, cps, static_cast<float4*>(ws));
+    MC_LAUNCH_CHECK();
+    mc::soft_ce_fwd_tmerge<<<(rows + 255) / 256, 256, 0, st>>>(static_cast<const float4*>(ws), ny, rows, loss_rows, row_lse,
+                                                              row_tsum);
   } else if (p_rs == 1 && t_rs == 1 && rows % 4 == 0 && p_cs % 4 == 0 && t_cs % 4 == 0 && mc::aligned(preds, 16) &&
              mc::aligned(targets, 16)) {
     // measured on 8192 x 8192: 32-row blocks 150 us, 16-row blocks 156 us, 128-row blocks (64 blocks only) 425 us

@@ -48,9 +48,11 @@ class _SoftCE(torch.autograd.Function):
             ctx.save_for_backward(preds, targets, lse, tsum)
             return loss
         with torch.cuda.device(preds.device):
+            nws = lib().mc_soft_ce_workspace_bytes(rows, cols)
+            ws = workspace(nws, preds.device) if nws else None
             check(lib().mc_soft_ce_fwd(ptr(preds), preds.stride(0), preds.stride(1), ptr(targets),
                                        targets.stride(0), targets.stride(1), rows, cols, ptr(loss),
-                                       ptr(lse), ptr(tsum), cur_stream()), "mc_soft_ce_fwd")
+                                       ptr(lse), ptr(tsum), ptr(ws), nws, cur_stream()), "mc_soft_ce_fwd")
         ctx.save_for_backward(preds, targets, lse, tsum)
         return loss
 

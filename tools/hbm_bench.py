@@ -99,9 +99,11 @@ t = torch.rand(R, R, device=dev)
 lr, lse, ts = (torch.empty(R, device=dev) for _ in range(3))
 g = torch.ones(R, device=dev)
 dp, dt = torch.empty_like(p), torch.empty_like(t)
-ms = timeit(lambda: check(L_.mc_soft_ce_fwd(ptr(p), R, 1, ptr(t), R, 1, R, R, ptr(lr), ptr(lse), ptr(ts), st())))
+nws = L_.mc_soft_ce_workspace_bytes(R, R)
+cws = torch.empty(max(nws, 16), dtype=torch.uint8, device=dev)
+ms = timeit(lambda: check(L_.mc_soft_ce_fwd(ptr(p), R, 1, ptr(t), R, 1, R, R, ptr(lr), ptr(lse), ptr(ts), ptr(cws), nws, st())))
 report("soft_ce_fwd 8192x8192", ms, 2 * R * R * 4 + 12 * R)
-ms = timeit(lambda: check(L_.mc_soft_ce_fwd(ptr(p), 1, R, ptr(t), 1, R, R, R, ptr(lr), ptr(lse), ptr(ts), st())))
+ms = timeit(lambda: check(L_.mc_soft_ce_fwd(ptr(p), 1, R, ptr(t), 1, R, R, R, ptr(lr), ptr(lse), ptr(ts), ptr(cws), nws, st())))
 report("soft_ce_fwd 8192x8192 (.T views)", ms, 2 * R * R * 4 + 12 * R)
 ms = timeit(lambda: check(L_.mc_soft_ce_bwd(ptr(p), R, 1, ptr(t), R, 1, R, R, ptr(lse), ptr(ts), ptr(g), ptr(dp), R, 1, None, 0, 0, st())))
 report("soft_ce_bwd 8192x8192 (dpreds)", ms, 3 * R * R * 4 + 12 * R)
