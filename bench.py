@@ -327,7 +327,19 @@ def run_b200(args):
         transport = "peer" if (world > 1 and mode != "simt_fp32" and b % 128 == 0) else "nccl"
     if world == 1:
         transport = "none"
-    ph = PeerPhases(B, b, rank, mode, dev) if transport == "peer" else Phases(B, b, rank * b, mode, dev)
+    ph = None
+    if transport == "peer":
+        from mae_clip_b200.peer import PeerUnavailable
+        try:
+            ph = PeerPhases(B, b, rank, mode, dev)
+        except PeerUnavailable as e:  # raised on every rank together (no P2P / IPC on this box)
+            if args.transport == "peer":
+                raise
+            if rank == 0:
+                print(f"bench: peer memory unavailable ({e}); using the NCCL transport", file=sys.stderr)
+            transport = "nccl"
+    if ph is None:
+        ph = Phases(B, b, rank * b, mode, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def one_step(record=False, I=None, T=None):

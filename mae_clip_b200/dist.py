@@ -300,9 +300,16 @@ def global_clip_loss(image_emb_local, text_emb_local, temperature: float = 1.0, 
     size to obtain the single-process gradient.)"""
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     if _pick_transport(transport, image_emb_local, mode, engine, world) == "peer":
-        from .peer import get_exchange
+        from .peer import PeerUnavailable, get_exchange
         b, D = image_emb_local.shape
-        step = PeerStep(get_exchange(b, D, group), mode)
-        return _PeerGlobalClipLoss.apply(image_emb_local, text_emb_local, float(temperature), step)
+        try:
+            step = PeerStep(get_exchange(b, D, group), mode)
+        except PeerUnavailable:
+            # raised on every rank together: without an explicit request the NCCL transport takes over
+            if (transport or os.environ.get("MAE_CLIP_TRANSPORT", "auto")) == "peer":
+                raise
+            step = None
+        if step is not None:
+            return _PeerGlobalClipLoss.apply(image_emb_local, text_emb_local, float(temperature), step)
     engine = engine if engine is not None else CudaStripEngine(mode)
     return _GlobalClipLoss.apply(image_emb_local, text_emb_local, float(temperature), engine, group)

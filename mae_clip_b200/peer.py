@@ -30,6 +30,7 @@ Why the region can be reused every step without extra fences (B_k = k-th barrier
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -42,6 +43,12 @@ MAX_WORLD = 16
 
 def _round_up(x: int, a: int) -> int:
     return (x + a - 1) // a * a
+
+
+class PeerUnavailable(RuntimeError):
+    """Peer memory could not be set up on at least one rank (no P2P / IPC between the devices, or a
+    container without a shared IPC namespace).  Raised on EVERY rank, so callers can fall back to the
+    NCCL transport together."""
 
 
 class PeerExchange:
@@ -70,21 +77,47 @@ class PeerExchange:
         self._tables = {}
         self._local = C.c_void_p()
         self._open = []
+        # Every rank takes part in both object all-gathers whatever happens locally, so a failure on one rank
+        # surfaces as PeerUnavailable on all of them instead of a hang.
+        err = None
+        raw = None
         with torch.cuda.device(self.device):
-            handle = C.create_string_buffer(_HANDLE_BYTES)
-            check(lib().mc_peer_alloc(self.nbytes, C.byref(self._local), handle), "mc_peer_alloc")
+            try:
+                if os.environ.get("MAE_CLIP_PEER_INJECT_FAILURE") == str(self.rank):  # test hook: the agreement path
+                    raise RuntimeError("injected set-up failure")
+                handle = C.create_string_buffer(_HANDLE_BYTES)
+                check(lib().mc_peer_alloc(self.nbytes, C.byref(self._local), handle), "mc_peer_alloc")
+                raw = bytes(handle.raw)
+            except Exception as e:  # noqa: BLE001
+                err = e
             handles = [None] * self.world
-            dist.all_gather_object(handles, (self.rank, bytes(handle.raw), self.nbytes), group=group)
-            for q, (rq, hq, nq) in enumerate(handles):
-                if rq != q or nq != self.nbytes:
-                    raise RuntimeError("peer exchange: ranks disagree on the region size (different b / D per rank?)")
-                if q == self.rank:
-                    self.ptrs[q] = self._local.value
-                    continue
-                p = C.c_void_p()
-                check(lib().mc_peer_open(C.create_string_buffer(hq, _HANDLE_BYTES), C.byref(p)), "mc_peer_open")
-                self._open.append(p)
-                self.ptrs[q] = p.value
+            dist.all_gather_object(handles, (self.rank, raw, self.nbytes), group=group)
+            if err is None:
+                try:
+                    for q, (rq, hq, nq) in enumerate(handles):
+                        if hq is None:
+                            raise PeerUnavailable(f"rank {q} could not allocate its exchange region")
+                        if rq != q or nq != self.nbytes:
+                            raise RuntimeError("peer exchange: ranks disagree on the region size (different b / D per rank?)")
+                        if q == self.rank:
+                            self.ptrs[q] = self._local.value
+                            continue
+                        p = C.c_void_p()
+                        check(lib().mc_peer_open(C.create_string_buffer(hq, _HANDLE_BYTES), C.byref(p)), "mc_peer_open")
+                        self._open.append(p)
+                        self.ptrs[q] = p.value
+                except Exception as e:  # noqa: BLE001
+                    err = e
+            oks = [None] * self.world
+            dist.all_gather_object(oks, err is None, group=group)
+            if not all(oks):
+                for p in self._open:
+                    lib().mc_peer_close(p)
+                if self._local.value:
+                    lib().mc_peer_free(self._local)
+                self._open, self._local = [], None
+                bad = [q for q, ok in enumerate(oks) if not ok]
+                raise PeerUnavailable(f"peer memory set-up failed on rank(s) {bad}" + (f": {err}" if err else ""))
         dist.barrier(group=group)  # every region is mapped (and zero-filled) before the first flag is written
 
     # ---- pointer helpers ----------------------------------------------------------------------
@@ -149,16 +182,24 @@ _cache = {}
 
 
 def get_exchange(b: int, D: int, group=None) -> PeerExchange:
-    """One exchange per (group, device, b, D): set-up costs a device synchronisation and an object
-    all-gather, so it is created on first use and kept."""
+    """One exchange per (group, device, b, D): set-up costs a device synchronisation and two object
+    all-gathers, so it is created on first use and kept.  A failed set-up is remembered too
+    (``PeerUnavailable`` is raised again without another collective round)."""
     key = (id(group) if group is not None else 0, torch.cuda.current_device(), b, D)
     ex = _cache.get(key)
     if ex is None:
-        ex = _cache[key] = PeerExchange(b, D, group)
+        try:
+            ex = PeerExchange(b, D, group)
+        except PeerUnavailable as e:
+            ex = e
+        _cache[key] = ex
+    if isinstance(ex, PeerUnavailable):
+        raise ex
     return ex
 
 
 def close_all():
     for ex in list(_cache.values()):
-        ex.close()
+        if isinstance(ex, PeerExchange):
+            ex.close()
     _cache.clear()

@@ -36,20 +36,23 @@ def _worker(rank, world, port, b, mode, transport, ret):
         if transport.startswith("peer"):
             os.environ["MAE_CLIP_PEER_MODE"] = transport.split("-")[1]
             transport = "peer"
+        elif transport == "auto-peer-fails":  # set-up fails on rank 1: every rank must fall back to NCCL together
+            os.environ["MAE_CLIP_PEER_INJECT_FAILURE"] = "1"
+            transport = None
         for _ in range(3 if transport == "peer" else 1):  # the exchange region is reused step after step
             I.grad = T.grad = None
             loss = global_clip_loss(I, T, 1.0, mode=mode, transport=transport)
             (loss * 2.0).backward()
         ret[rank] = (loss.detach().cpu(), I.grad.cpu(), T.grad.cpu())
-        if transport == "peer":
-            from mae_clip_b200 import peer
-            peer.close_all()
+        from mae_clip_b200 import peer
+        peer.close_all()
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("mode,transport", [("simt_fp32", "nccl"), ("tc_f16x3", "nccl"), ("tc_f16x3", "peer-push"),
-                                            ("tc_f16x3", "peer-pull"), ("tc_f16", "peer-push")])
+                                            ("tc_f16x3", "peer-pull"), ("tc_f16", "peer-push"),
+                                            ("tc_f16x3", "auto-peer-fails")])
 def test_global_loss_two_gpus(mode, transport):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
