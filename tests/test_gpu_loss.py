@@ -176,6 +176,42 @@ def test_abi_error_codes():
     assert lib.mc_device_supported(0) == 1
 
 
+def test_abi_error_codes_next_rows_and_peer():
+    """Bad arguments come back as status codes with a message, never as a crash or an exception across the ABI."""
+    import ctypes as C
+    from mae_clip_b200 import _lib
+    lib = _lib.lib()
+    x = torch.zeros(64, 256, device="cuda")
+    i64 = torch.zeros(64, dtype=torch.int64, device="cuda")
+    ws = torch.zeros(1 << 16, dtype=torch.uint8, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    tab = (C.c_void_p * 1)(x.data_ptr())
+    n1 = (C.c_int64 * 1)(64 * 256)
+    # AdamW: step counts from 1; betas inside [0, 1)
+    assert lib.mc_adamw_step(1, tab, tab, tab, tab, n1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0, None, None) == 1
+    assert b"step" in lib.mc_last_error_string()
+    assert lib.mc_adamw_step(1, tab, tab, tab, tab, n1, 1e-3, 1.5, 0.999, 1e-8, 0.0, 1, None, None) == 1
+    assert lib.mc_adamw_step(0, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, None, None) == 0  # empty: fine
+    # retrieval: k beyond the bank, k beyond the shared-memory limit, short workspace
+    assert lib.mc_similarity_topk(p(x), 1, p(x), 64, 256, 65, p(x), p(i64), None, p(ws), ws.numel(), None) == 1
+    assert lib.mc_similarity_topk(p(x), 1, p(x), 64, 256, 2000, p(x), p(i64), None, p(ws), ws.numel(), None) in (1, 6)
+    assert lib.mc_similarity_topk(p(x), 1, p(x), 64, 256, 4, p(x), p(i64), None, p(ws), 8, None) == 5
+    # peer primitives: world outside [1, 16], rank outside the world, null epoch counter
+    assert lib.mc_peer_barrier(tab, 0, 17, p(ws), 1.0, None) == 1
+    assert lib.mc_peer_barrier(tab, 3, 1, p(ws), 1.0, None) == 1
+    assert lib.mc_peer_barrier(tab, 0, 1, None, 1.0, None) == 1
+    assert lib.mc_peer_publish(p(x), 0, 4, 4, tab, 4, 0, 1, None) == 1
+    # peer staging feeds the tcgen05 engines only
+    assert lib.mc_clip_prepare_peers(tab, tab, 1, 64, 256, 0, p(ws), p(ws), None) == 6
+    # data feed: zero std
+    m3, s3 = (C.c_float * 3)(0.5, 0.5, 0.5), (C.c_float * 3)(0.5, 0.0, 0.5)
+    u8 = torch.zeros(1, 4, 4, 3, dtype=torch.uint8, device="cuda")
+    assert lib.mc_normalize_images(p(u8), 1, 4, 4, m3, s3, 255.0, p(x), None) == 1
+    # restore_tokens backward: rows must be 16-byte multiples
+    assert lib.mc_restore_tokens_bwd(p(x), 4, 0, p(i64), 1, 8, 3, 4, p(x), p(x), p(ws), ws.numel(), None) == 6
+    torch.cuda.synchronize()  # nothing above may have launched a faulting kernel
+
+
 # ------------------------------------------------------------------ cross_entropy (CLIP.py:46-52)
 def test_cross_entropy_golden(golden):
     import mae_clip_b200 as m
