@@ -194,21 +194,24 @@ int mc_peer_publish(const void* src, int k, int n, int64_t src_stride, void* con
  *   z = keep*y/(1-p) + projected; out = LayerNorm(z) * gamma + beta
  * keep_mask: (B, P) bytes of 0/1 or NULL (eval mode).  projected / hidden / z /
  * mean / rstd are written for backward (all (B,P) or (B)); pass NULL for
- * hidden/z/mean/rstd under no_grad to skip the stores.
+ * hidden/z/mean/rstd under no_grad to skip the stores.  fwd_amax: optional two
+ * device words the forward fills (bit patterns of max|x|, max|hidden|) and the
+ * backward reads, so it need not reduce them again (NULL on either side: recomputed).
  * ------------------------------------------------------------------------- */
 size_t mc_proj_head_workspace_bytes(int B, int E, int P, int mode);
 int mc_proj_head_fwd(const float* x, int B, int E, int P, const float* w_proj, const float* b_proj,
                      const float* w_fc, const float* b_fc, const float* gamma, const float* beta,
                      const uint8_t* keep_mask, float p_drop, float eps, int mode, float* projected,
-                     float* hidden, float* z, float* mean, float* rstd, float* out, void* ws,
-                     size_t ws_bytes, void* stream);
+                     float* hidden, float* z, float* mean, float* rstd, float* out, float* fwd_amax,
+                     void* ws, size_t ws_bytes, void* stream);
 /* dx may be NULL (frozen tower below the head: modules.py:35 / CLIP.py:18). */
 int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
                      const float* w_proj, const float* w_fc, const float* gamma,
                      const uint8_t* keep_mask, float p_drop, int mode, const float* projected,
                      const float* hidden, const float* z, const float* mean, const float* rstd,
                      float* dx, float* dw_proj, float* db_proj, float* dw_fc, float* db_fc,
-                     float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+                     float* dgamma, float* dbeta, const float* fwd_amax, void* ws, size_t ws_bytes,
+                     void* stream);
 
 /* fp32-class tensor-core GEMM the heads are built from (exposed for tests and reuse):
  * C[M,N] = A[M,K] . B[N,K]^T (+ bias[n]); A, B, C dense row-major fp32; gelu_out (optional) =

@@ -234,8 +234,8 @@ __device__ __forceinline__ float scale_from_amax(float amax) {
 // scale slot layout: [0] = s, [1] = 1/s, [2] = amax bits (written by amax2d_kernel)
 __global__ void __launch_bounds__(256) stage_kernel(const float* __restrict__ src, int R, int C, int64_t lds,
                                                     int pitch, __half* __restrict__ hi, __half* __restrict__ lo,
-                                                    float* __restrict__ scale) {
-  const float s = scale_from_amax(__uint_as_float(reinterpret_cast<const unsigned int*>(scale)[2]));
+                                                    float* __restrict__ scale, const unsigned int* __restrict__ amax_bits) {
+  const float s = scale_from_amax(__uint_as_float(amax_bits[0]));
   if (blockIdx.x == 0 && threadIdx.x == 0) { scale[0] = s; scale[1] = 1.f / s; }
   const size_t total = (size_t)R * pitch;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -250,9 +250,9 @@ __global__ void __launch_bounds__(256) stage_kernel(const float* __restrict__ sr
 // dst (C rows x R cols, pitch) = src^T, 32 x 32 tiles through shared memory
 __global__ void __launch_bounds__(256) stage_T_kernel(const float* __restrict__ src, int R, int C, int64_t lds,
                                                       int pitch, __half* __restrict__ hi, __half* __restrict__ lo,
-                                                      float* __restrict__ scale) {
+                                                      float* __restrict__ scale, const unsigned int* __restrict__ amax_bits) {
   __shared__ float tile[32][33];
-  const float s = scale_from_amax(__uint_as_float(reinterpret_cast<const unsigned int*>(scale)[2]));
+  const float s = scale_from_amax(__uint_as_float(amax_bits[0]));
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { scale[0] = s; scale[1] = 1.f / s; }
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;  // tile of src: rows r0.., cols c0..
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -289,8 +289,8 @@ __device__ __forceinline__ void split4(const float4 v, float s, uint2& h, uint2&
 // dense, pitch == C == lds: flat 16-byte loads, 8-byte stores to each plane
 __global__ void __launch_bounds__(256) stage_flat_kernel(const float4* __restrict__ src, size_t n4,
                                                          uint2* __restrict__ hi, uint2* __restrict__ lo,
-                                                         float* __restrict__ scale) {
-  const float s = scale_from_amax(__uint_as_float(reinterpret_cast<const unsigned int*>(scale)[2]));
+                                                         float* __restrict__ scale, const unsigned int* __restrict__ amax_bits) {
+  const float s = scale_from_amax(__uint_as_float(amax_bits[0]));
   if (blockIdx.x == 0 && threadIdx.x == 0) { scale[0] = s; scale[1] = 1.f / s; }
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -319,9 +319,9 @@ __global__ void __launch_bounds__(256) stage_flat_kernel(const float4* __restric
 // C % 4 == 0, lds % 4 == 0, pitch % 8 == 0.
 __global__ void __launch_bounds__(256) stage_T64_kernel(const float* __restrict__ src, int R, int C, int64_t lds,
                                                         int pitch, __half* __restrict__ hi, __half* __restrict__ lo,
-                                                        float* __restrict__ scale) {
+                                                        float* __restrict__ scale, const unsigned int* __restrict__ amax_bits) {
   __shared__ float tile[64][65];
-  const float s = scale_from_amax(__uint_as_float(reinterpret_cast<const unsigned int*>(scale)[2]));
+  const float s = scale_from_amax(__uint_as_float(amax_bits[0]));
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { scale[0] = s; scale[1] = 1.f / s; }
   const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   const int lc4 = threadIdx.x & 15, lr = threadIdx.x >> 4;  // 16 float4 columns x 16 rows per pass
@@ -382,47 +382,55 @@ Planes carve_planes(void* mem, int rows, int cols) {
   return pl;
 }
 
-int stage(const float* src, int R, int C, int64_t lds, int transpose, const Planes& dst, cudaStream_t st) {
+int stage(const float* src, int R, int C, int64_t lds, int transpose, const Planes& dst, cudaStream_t st,
+          const unsigned int* known_amax) {
   MC_REQUIRE(src && dst.hi && dst.lo && dst.scale, MC_ERR_BAD_ARG, "stage: null pointer");
   MC_REQUIRE(dst.rows == (transpose ? C : R) && dst.cols == (transpose ? R : C), MC_ERR_BAD_ARG,
              "stage: destination planes are %d x %d, expected %d x %d", dst.rows, dst.cols, transpose ? C : R,
              transpose ? R : C);
-  MC_CUDA(cudaMemsetAsync(dst.scale, 0, 16, st));
   const size_t total = (size_t)R * C;
-  int ab = (int)((total + 255) / 256);
   const int cap = num_sms() * 8;
-  if (ab > cap) ab = cap;
   const bool flat = lds == C && total % 4 == 0 && aligned(src, 16);
-  if (flat) {
-    int fb = (int)((total / 4 + 1023) / 1024);
-    if (fb > cap) fb = cap;
-    if (fb < 1) fb = 1;
-    amax_flat_kernel<<<fb, 256, 0, st>>>(reinterpret_cast<const float4*>(src), total / 4,
-                                         reinterpret_cast<unsigned int*>(dst.scale) + 2);
-  } else {
-    amax2d_kernel<<<ab, 256, 0, st>>>(src, R, C, lds, reinterpret_cast<unsigned int*>(dst.scale) + 2);
+  // max |src|: taken from `known_amax` when a producer kernel (or an earlier staging of the same tensor in the
+  // other orientation) already reduced it, else reduced here into the planes' own slot
+  const unsigned int* amax_bits = known_amax;
+  if (!amax_bits) {
+    MC_CUDA(cudaMemsetAsync(dst.scale, 0, 16, st));
+    unsigned int* slot = reinterpret_cast<unsigned int*>(dst.scale) + 2;
+    if (flat) {
+      int fb = (int)((total / 4 + 1023) / 1024);
+      if (fb > cap) fb = cap;
+      if (fb < 1) fb = 1;
+      amax_flat_kernel<<<fb, 256, 0, st>>>(reinterpret_cast<const float4*>(src), total / 4, slot);
+    } else {
+      int ab = (int)((total + 255) / 256);
+      if (ab > cap) ab = cap;
+      amax2d_kernel<<<ab, 256, 0, st>>>(src, R, C, lds, slot);
+    }
+    MC_LAUNCH_CHECK();
+    amax_bits = slot;
   }
-  MC_LAUNCH_CHECK();
   if (!transpose) {
     if (flat && dst.pitch == C) {
       int fb = (int)((total / 4 + 1023) / 1024);
       if (fb > cap) fb = cap;
       if (fb < 1) fb = 1;
       stage_flat_kernel<<<fb, 256, 0, st>>>(reinterpret_cast<const float4*>(src), total / 4,
-                                            reinterpret_cast<uint2*>(dst.hi), reinterpret_cast<uint2*>(dst.lo), dst.scale);
+                                            reinterpret_cast<uint2*>(dst.hi), reinterpret_cast<uint2*>(dst.lo), dst.scale,
+                                            amax_bits);
     } else {
       const size_t tot = (size_t)R * dst.pitch;
       int nb = (int)((tot + 255) / 256);
       if (nb > cap) nb = cap;
-      stage_kernel<<<nb, 256, 0, st>>>(src, R, C, lds, dst.pitch, dst.hi, dst.lo, dst.scale);
+      stage_kernel<<<nb, 256, 0, st>>>(src, R, C, lds, dst.pitch, dst.hi, dst.lo, dst.scale, amax_bits);
     }
   } else if (C % 4 == 0 && lds % 4 == 0 && aligned(src, 16)) {
     dim3 grid((dst.pitch + 63) / 64, (C + 63) / 64);  // covers the padding columns [R, pitch) too
-    stage_T64_kernel<<<grid, 256, 0, st>>>(src, R, C, lds, dst.pitch, dst.hi, dst.lo, dst.scale);
+    stage_T64_kernel<<<grid, 256, 0, st>>>(src, R, C, lds, dst.pitch, dst.hi, dst.lo, dst.scale, amax_bits);
   } else {
     // cover the padding columns [R, pitch) too
     dim3 grid((dst.pitch + 31) / 32, (C + 31) / 32);
-    stage_T_kernel<<<grid, 256, 0, st>>>(src, R, C, lds, dst.pitch, dst.hi, dst.lo, dst.scale);
+    stage_T_kernel<<<grid, 256, 0, st>>>(src, R, C, lds, dst.pitch, dst.hi, dst.lo, dst.scale, amax_bits);
   }
   MC_LAUNCH_CHECK();
   return MC_OK;

@@ -21,8 +21,12 @@ size_t planes_bytes(int rows, int cols);  // hi + lo + scale slot, 256-byte alig
 // carve `mem` (>= planes_bytes) into a Planes descriptor
 Planes carve_planes(void* mem, int rows, int cols);
 
-// dst = split(src * s): src is (R, C) fp32 with row stride lds; transpose = 1 stages src^T (C rows, R cols)
-int stage(const float* src, int R, int C, int64_t lds, int transpose, const Planes& dst, cudaStream_t st);
+// dst = split(src * s): src is (R, C) fp32 with row stride lds; transpose = 1 stages src^T (C rows, R cols).
+// known_amax: device word with the bit pattern of max |src| when something already reduced it (the kernel that
+// produced src, or an earlier staging of the same tensor); null = reduce it here (one more pass over src).
+int stage(const float* src, int R, int C, int64_t lds, int transpose, const Planes& dst, cudaStream_t st,
+          const unsigned int* known_amax = nullptr);
+inline const unsigned int* amax_slot(const Planes& p) { return reinterpret_cast<const unsigned int*>(p.scale) + 2; }
 
 enum Epilogue { kEpiPlain = 0, kEpiGelu = 1 };
 

@@ -87,10 +87,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
                                                      const uint8_t* __restrict__ keep, float scale,
                                                      int B, int P, float* __restrict__ dz_out,
                                                      float* __restrict__ dy_out,
-                                                     float* __restrict__ partials /*[grid][2][P]*/) {
+                                                     float* __restrict__ partials /*[grid][2][P]*/,
+                                                     unsigned int* __restrict__ dy_amax /* or null */) {
   extern __shared__ float sm[];  // [8 warps][2][P]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = P >> 2;
+  float amx = 0.f;  // max |dy| this thread wrote: saves the staging of dy a pass over it
   float4 dg[NV], db[NV], gm[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -138,8 +140,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
           d.w = m.w ? d.w * scale : 0.f;
         }
         *reinterpret_cast<float4*>(dy_out + off + 4 * v) = d;
+        amx = fmaxf(amx, fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
       }
     }
+  }
+  if (dy_amax) {
+    amx = warp_max(amx);
+    if (lane == 0 && amx > 0.f) atomicMax(dy_amax, __float_as_uint(amx));
   }
   // block-level column partials
 #pragma unroll
@@ -213,7 +220,9 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
 // dp = dh * gelu'(projected) + dz   (in place on dh)
 __global__ void __launch_bounds__(256) gelu_bwd_add_kernel(float* __restrict__ dh,
                                                            const float* __restrict__ projected,
-                                                           const float* __restrict__ dz, size_t n4) {
+                                                           const float* __restrict__ dz, size_t n4,
+                                                           unsigned int* __restrict__ dp_amax /* or null */) {
+  float amx = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (size_t)gridDim.x * blockDim.x) {
     float4 h = reinterpret_cast<float4*>(dh)[i];
@@ -224,6 +233,11 @@ __global__ void __launch_bounds__(256) gelu_bwd_add_kernel(float* __restrict__ d
     h.z = fmaf(h.z, gelu_erf_grad(p.z), d.z);
     h.w = fmaf(h.w, gelu_erf_grad(p.w), d.w);
     reinterpret_cast<float4*>(dh)[i] = h;
+    amx = fmaxf(amx, fmaxf(fmaxf(fabsf(h.x), fabsf(h.y)), fmaxf(fabsf(h.z), fabsf(h.w))));
+  }
+  if (dp_amax) {
+    amx = warp_max(amx);
+    if ((threadIdx.x & 31) == 0 && amx > 0.f) atomicMax(dp_amax, __float_as_uint(amx));
   }
 }
 
@@ -266,10 +280,11 @@ static int launch_ln_fwd(const float* y, const float* projected, const uint8_t* 
 template <int NV>
 static int launch_ln_bwd(const float* go, const float* z, const float* mean, const float* rstd,
                          const float* gamma, const uint8_t* keep, float scale, int B, int P,
-                         float* dz, float* dy, float* partials, int blocks, cudaStream_t st) {
+                         float* dz, float* dy, float* partials, int blocks, unsigned int* dy_amax,
+                         cudaStream_t st) {
   size_t smem = (size_t)8 * 2 * P * sizeof(float);
   ln_bwd_kernel<NV><<<blocks, 256, smem, st>>>(go, z, mean, rstd, gamma, keep, scale, B, P, dz, dy,
-                                               partials);
+                                               partials, dy_amax);
   MC_LAUNCH_CHECK();
   return MC_OK;
 }
@@ -306,6 +321,7 @@ static HeadWs head_ws(void* ws, int B, int /*E*/, int P) {
 struct TcHeadWs {
   // fp32 temporaries (same roles as HeadWs)
   float *y, *hidden_tmp, *dz, *dy, *dh, *partials;
+  unsigned int* amax;                                // producer-side max |.|: [0] dy, [1] dp (zeroed per backward)
   // staged operands
   tcg::Planes x, wp, h, wf;                          // forward
   tcg::Planes dyT, hT, dy_p, wfT, dpT, xT, dp_p, wpT;  // backward
@@ -329,6 +345,7 @@ static TcHeadWs tc_head_ws(void* ws, int B, int E, int P) {
   w.dz = w.y;            // backward reuses the forward temporaries
   w.dy = w.hidden_tmp;
   w.partials = reinterpret_cast<float*>(take((size_t)ln_blocks(B) * 2 * P * 4));
+  w.amax = reinterpret_cast<unsigned int*>(take(256));
   w.x = planes(B, E);  w.wp = planes(P, E);  w.h = planes(B, P);  w.wf = planes(P, P);
   w.dyT = planes(P, B); w.hT = planes(P, B); w.dy_p = planes(B, P); w.wfT = planes(P, P);
   w.dpT = planes(P, B); w.xT = planes(E, B); w.dp_p = planes(B, P); w.wpT = planes(E, P);
@@ -390,7 +407,7 @@ size_t mc_proj_head_workspace_bytes(int B, int E, int P, int mode) {
 int mc_proj_head_fwd(const float* x, int B, int E, int P, const float* w_proj, const float* b_proj,
                      const float* w_fc, const float* b_fc, const float* gamma, const float* beta,
                      const uint8_t* keep_mask, float p_drop, float eps, int mode, float* projected,
-                     float* hidden, float* z, float* mean, float* rstd, float* out, void* ws,
+                     float* hidden, float* z, float* mean, float* rstd, float* out, float* fwd_amax, void* ws,
                      size_t ws_bytes, void* stream) {
   MC_ARCH_GUARD();
   MC_REQUIRE(x && w_proj && b_proj && w_fc && b_fc && gamma && beta && projected && out && ws,
@@ -418,6 +435,10 @@ int mc_proj_head_fwd(const float* x, int B, int E, int P, const float* w_proj, c
     tcg::GemmOut o1{projected, P, b_proj, hid_tc};
     if ((rc = tcg::gemm(t.x, t.wp, B, P, E, o1, tcg::kEpiGelu, t.gemm_ws, t.gemm_ws_bytes, st))) return rc;
     if ((rc = tcg::stage(hid_tc, B, P, P, 0, t.h, st))) return rc;
+    if (fwd_amax) {  // max |x|, max |hidden|: backward stages both again (transposed) and skips the reductions
+      MC_CUDA(cudaMemcpyAsync(fwd_amax, tcg::amax_slot(t.x), 4, cudaMemcpyDeviceToDevice, st));
+      MC_CUDA(cudaMemcpyAsync(fwd_amax + 1, tcg::amax_slot(t.h), 4, cudaMemcpyDeviceToDevice, st));
+    }
     if ((rc = tcg::stage(w_fc, P, P, P, 0, t.wf, st))) return rc;
     tcg::GemmOut o2{t.y, P, b_fc, nullptr};
     if ((rc = tcg::gemm(t.h, t.wf, B, P, P, o2, tcg::kEpiPlain, t.gemm_ws, t.gemm_ws_bytes, st))) return rc;
@@ -443,7 +464,7 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
                      const uint8_t* keep_mask, float p_drop, int mode, const float* projected,
                      const float* hidden, const float* z, const float* mean, const float* rstd,
                      float* dx, float* dw_proj, float* db_proj, float* dw_fc, float* db_fc,
-                     float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream) {
+                     float* dgamma, float* dbeta, const float* fwd_amax, void* ws, size_t ws_bytes, void* stream) {
   MC_ARCH_GUARD();
   MC_REQUIRE(grad_out && x && w_proj && w_fc && gamma && projected && hidden && z && mean && rstd &&
                  dw_proj && db_proj && dw_fc && db_fc && dgamma && dbeta && ws,
@@ -462,8 +483,11 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
     MC_REQUIRE(aligned(ws, 256), MC_ERR_ALIGN, "proj_head_bwd: workspace must be 256-byte aligned");
     TcHeadWs t = tc_head_ws(ws, B, E, P);
     MC_REQUIRE(ws_bytes >= t.total, MC_ERR_WORKSPACE, "proj_head_bwd: workspace %zu < %zu", ws_bytes, t.total);
+    MC_CUDA(cudaMemsetAsync(t.amax, 0, 16, st));
+    const unsigned int* x_amax = fwd_amax ? reinterpret_cast<const unsigned int*>(fwd_amax) : nullptr;
+    const unsigned int* h_amax = fwd_amax ? reinterpret_cast<const unsigned int*>(fwd_amax) + 1 : nullptr;
     MC_DISPATCH_NV(P, (launch_ln_bwd<NV>(grad_out, z, mean, rstd, gamma, keep_mask, scale, B, P, t.dz, t.dy,
-                                         t.partials, blocks, st)));
+                                         t.partials, blocks, t.amax, st)));
     if (rc) return rc;
     dim3 blk(32, 32);
     colsum_kernel<<<(2 * P + 31) / 32, blk, 0, st>>>(t.partials, blocks, 2 * P, t.dh);
@@ -472,12 +496,12 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
     MC_CUDA(cudaMemcpyAsync(dbeta, t.dh + P, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
     if ((rc = colsum_rows(t.dy, B, P, db_fc, t.partials, 2 * blocks, st))) return rc;  // partials are free again
     // dWf[n,k] = sum_m dy[m,n] hidden[m,k]  ->  (dy^T) . (hidden^T)^T, K = B (split-K)
-    if ((rc = tcg::stage(t.dy, B, P, P, 1, t.dyT, st))) return rc;
-    if ((rc = tcg::stage(hidden, B, P, P, 1, t.hT, st))) return rc;
+    if ((rc = tcg::stage(t.dy, B, P, P, 1, t.dyT, st, t.amax))) return rc;
+    if ((rc = tcg::stage(hidden, B, P, P, 1, t.hT, st, h_amax))) return rc;
     tcg::GemmOut o1{dw_fc, P, nullptr, nullptr};
     if ((rc = tcg::gemm(t.dyT, t.hT, P, P, B, o1, tcg::kEpiPlain, t.gemm_ws, t.gemm_ws_bytes, st))) return rc;
     // dh[m,k] = sum_n dy[m,n] Wf[n,k]  ->  dy . (Wf^T)^T
-    if ((rc = tcg::stage(t.dy, B, P, P, 0, t.dy_p, st))) return rc;
+    if ((rc = tcg::stage(t.dy, B, P, P, 0, t.dy_p, st, t.amax))) return rc;
     if ((rc = tcg::stage(w_fc, P, P, P, 1, t.wfT, st))) return rc;
     tcg::GemmOut o2{t.dh, P, nullptr, nullptr};
     if ((rc = tcg::gemm(t.dy_p, t.wfT, B, P, P, o2, tcg::kEpiPlain, t.gemm_ws, t.gemm_ws_bytes, st))) return rc;
@@ -486,18 +510,18 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
       int nb = (int)((n4 + 255) / 256);
       int cap = num_sms() * 8;
       if (nb > cap) nb = cap;
-      gelu_bwd_add_kernel<<<nb, 256, 0, st>>>(t.dh, projected, t.dz, n4);  // dp = dh * gelu'(p) + dz
+      gelu_bwd_add_kernel<<<nb, 256, 0, st>>>(t.dh, projected, t.dz, n4, t.amax + 1);  // dp = dh * gelu'(p) + dz
       MC_LAUNCH_CHECK();
       if ((rc = colsum_rows(t.dh, B, P, db_proj, t.partials, 2 * blocks, st))) return rc;
     }
     // dWp[n,e] = sum_m dp[m,n] x[m,e]  ->  (dp^T) . (x^T)^T, K = B (split-K)
-    if ((rc = tcg::stage(t.dh, B, P, P, 1, t.dpT, st))) return rc;
-    if ((rc = tcg::stage(x, B, E, E, 1, t.xT, st))) return rc;
+    if ((rc = tcg::stage(t.dh, B, P, P, 1, t.dpT, st, t.amax + 1))) return rc;
+    if ((rc = tcg::stage(x, B, E, E, 1, t.xT, st, x_amax))) return rc;
     tcg::GemmOut o3{dw_proj, E, nullptr, nullptr};
     if ((rc = tcg::gemm(t.dpT, t.xT, P, E, B, o3, tcg::kEpiPlain, t.gemm_ws, t.gemm_ws_bytes, st))) return rc;
     if (dx) {
       // dx[m,e] = sum_n dp[m,n] Wp[n,e]  ->  dp . (Wp^T)^T
-      if ((rc = tcg::stage(t.dh, B, P, P, 0, t.dp_p, st))) return rc;
+      if ((rc = tcg::stage(t.dh, B, P, P, 0, t.dp_p, st, t.amax + 1))) return rc;
       if ((rc = tcg::stage(w_proj, P, E, E, 1, t.wpT, st))) return rc;
       tcg::GemmOut o4{dx, E, nullptr, nullptr};
       if ((rc = tcg::gemm(t.dp_p, t.wpT, B, E, P, o4, tcg::kEpiPlain, t.gemm_ws, t.gemm_ws_bytes, st))) return rc;
@@ -508,7 +532,7 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
   MC_REQUIRE(ws_bytes >= w.total, MC_ERR_WORKSPACE, "proj_head_bwd: workspace %zu < %zu", ws_bytes,
              w.total);
   MC_DISPATCH_NV(P, (launch_ln_bwd<NV>(grad_out, z, mean, rstd, gamma, keep_mask, scale, B, P, w.dz,
-                                       w.dy, w.partials, blocks, st)));
+                                       w.dy, w.partials, blocks, nullptr, st)));
   if (rc) return rc;
   // dgamma / dbeta: column sums of the block partials ([blocks][2P] viewed as rows x 2P)
   {
@@ -531,7 +555,7 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
     int nb = (int)((n4 + 255) / 256);
     int cap = num_sms() * 8;
     if (nb > cap) nb = cap;
-    gelu_bwd_add_kernel<<<nb, 256, 0, st>>>(w.dh, projected, w.dz, n4);
+    gelu_bwd_add_kernel<<<nb, 256, 0, st>>>(w.dh, projected, w.dz, n4, nullptr);
     MC_LAUNCH_CHECK();
     if ((rc = colsum_rows(w.dh, B, P, db_proj, w.partials, 2 * blocks, st))) return rc;
   }

@@ -157,23 +157,24 @@ class _ProjHead(torch.autograd.Function):
             z = torch.empty_like(projected)
             mean = torch.empty(B, device=dev, dtype=torch.float32)
             rstd = torch.empty_like(mean)
+            fwd_amax = torch.zeros(2, device=dev, dtype=torch.float32)  # max|x|, max|hidden| bit patterns for backward
         else:
-            hidden = z = mean = rstd = None
+            hidden = z = mean = rstd = fwd_amax = None
         with torch.cuda.device(dev):
             ws = workspace(lib().mc_proj_head_workspace_bytes(B, E, P, mode), dev)
             check(lib().mc_proj_head_fwd(ptr(x2), B, E, P, ptr(wp), ptr(bp), ptr(wf), ptr(bf), ptr(g),
                                          ptr(bt), ptr(keep_mask), float(p_drop), float(eps), mode,
                                          ptr(projected), ptr(hidden), ptr(z), ptr(mean), ptr(rstd),
-                                         ptr(out), ptr(ws), ws.numel(), cur_stream()),
+                                         ptr(out), ptr(fwd_amax), ptr(ws), ws.numel(), cur_stream()),
                   "mc_proj_head_fwd")
         if need:
-            ctx.save_for_backward(x2, wp, wf, g, keep_mask, projected, hidden, z, mean, rstd)
+            ctx.save_for_backward(x2, wp, wf, g, keep_mask, projected, hidden, z, mean, rstd, fwd_amax)
         ctx.cfg = (B, E, P, float(p_drop), mode, lead, x.dtype)
         return out.reshape(*lead, P)
 
     @staticmethod
     def backward(ctx, grad_out):
-        x2, wp, wf, g, keep_mask, projected, hidden, z, mean, rstd = ctx.saved_tensors
+        x2, wp, wf, g, keep_mask, projected, hidden, z, mean, rstd, fwd_amax = ctx.saved_tensors
         B, E, P, p_drop, mode, lead, x_dtype = ctx.cfg
         go = _f32c(grad_out.reshape(B, P))
         dev = x2.device
@@ -189,7 +190,7 @@ class _ProjHead(torch.autograd.Function):
             check(lib().mc_proj_head_bwd(ptr(go), ptr(x2), B, E, P, ptr(wp), ptr(wf), ptr(g),
                                          ptr(keep_mask), p_drop, mode, ptr(projected), ptr(hidden),
                                          ptr(z), ptr(mean), ptr(rstd), ptr(dx), ptr(dwp), ptr(dbp),
-                                         ptr(dwf), ptr(dbf), ptr(dg), ptr(dbt), ptr(ws), ws.numel(),
+                                         ptr(dwf), ptr(dbf), ptr(dg), ptr(dbt), ptr(fwd_amax), ptr(ws), ws.numel(),
                                          cur_stream()), "mc_proj_head_bwd")
         if dx is not None:
             dx = dx.reshape(*lead, E).to(x_dtype)
