@@ -65,7 +65,7 @@ def test_global_loss_two_gpus(mode, transport):
     ref_loss, ref_dI, ref_dT, _ = loss_ref.clip_loss_closed_form(I.numpy(), T.numpy(), 1.0, grad_loss=2.0)
     for r in range(world):
         loss, dI, dT = ret[r]
-        lt, gt = (2e-3, 3e-2) if mode == "tc_f16" else (1e-4, 1e-3)  # single fp16 pass: stated looser
+        lt, gt = (5e-4, 5e-3) if mode == "tc_f16" else (1e-4, 1e-3)  # single fp16 pass: stated looser
         assert abs(loss.item() - ref_loss) < lt * abs(ref_loss)
         assert rel_err(dI, ref_dI[r * b:(r + 1) * b]) < gt
         assert rel_err(dT, ref_dT[r * b:(r + 1) * b]) < gt
