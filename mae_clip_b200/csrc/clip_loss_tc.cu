@@ -167,7 +167,13 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   // buffer (the epilogue empties it into registers at once) and its accumulators at 256 (dT), 256 + D/2 (dI)
   constexpr int kNBuf = (PHASE == kBwd) ? 1 : 2;
   constexpr uint32_t kAccCol = 256;
-  constexpr int kSlots = (PHASE == kBwd) ? kSlotsBwd : kSlotsFwd;
+  // Forward sweeps of the 3-pass engine keep the LO plane of the CTA's rows resident too (the gradient sweep has no
+  // room: weights + X^T tiles): a third less L2 -> shared-memory traffic per tile, five ring slots left.
+  constexpr bool kResLo = (PHASE != kBwd) && PASSES == 3;
+  constexpr int kOffAlo = kOffStage;                                   // resident lo plane (64 KB) when kResLo
+  constexpr int kOffRing = kResLo ? kOffStage + 65536 : kOffStage;
+  constexpr int kSlots = (PHASE == kBwd) ? kSlotsBwd : (kResLo ? kSlotsFwd - 65536 / kSlotBytes : kSlotsFwd);
+  static_assert(kOffRing + kSlots * kSlotBytes <= kOffConst, "ring overlaps the column constants");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -223,9 +229,12 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           const int row_a = p.row_offset + rb * 128 + (int)rank * kRowsCta;
           const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
           mbar_wait(bar(kJobDone), (jj & 1) ^ 1);
-          if (leader) mbar_arrive_expect_tx(bar(kAFull), 2u * 2u * nkc * kChunkBytes);
+          if (leader) mbar_arrive_expect_tx(bar(kAFull), (kResLo ? 2u : 1u) * 2u * 2u * nkc * kChunkBytes);
           for (int c = 0; c < 2 * nkc; ++c)
             tma_load_2d_pair(base + kOffA + c * kChunkBytes, &map_a_hi, bar(kAFull), c * 64, row_a);
+          if (kResLo)
+            for (int c = 0; c < 2 * nkc; ++c)
+              tma_load_2d_pair(base + kOffAlo + c * kChunkBytes, &map_a_lo, bar(kAFull), c * 64, row_a);
           for (int t = t0; t < t1; ++t) {
             const int j0 = t * kTileN + 32 * (int)rank, j1 = j0 + 64;
             for (int c = 0; c < nkc; ++c) {
@@ -237,12 +246,15 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                 mbar_wait(bar(kEmpty0 + slot), par ^ 1);
                 fb = bar(kFull0 + slot);
                 if (leader) mbar_arrive_expect_tx(fb, 2u * kSlotBytes);
-                return base + kOffStage + slot * kSlotBytes;
+                return base + kOffRing + slot * kSlotBytes;
               };
               if (PASSES == 3) {
-                uint32_t sb = acquire();
-                tma_load_2d_pair(sb, &map_a_lo, fb, ci, row_a);                         // I_i lo
-                tma_load_2d_pair(sb + kChunkBytes, &map_a_lo, fb, ct, row_a);           // T_i lo
+                uint32_t sb;
+                if (!kResLo) {
+                  sb = acquire();
+                  tma_load_2d_pair(sb, &map_a_lo, fb, ci, row_a);                       // I_i lo
+                  tma_load_2d_pair(sb + kChunkBytes, &map_a_lo, fb, ct, row_a);         // T_i lo
+                }
                 sb = acquire();
                 tma_load_2d_pair(sb, &map_b_hi, fb, ci, j0);                            // I_j hi
                 tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ci, j1);
@@ -346,15 +358,23 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                 mbar_wait(bar(kFull0 + slot), par);
                 tc_fence_after();
                 slot_bar = bar(kEmpty0 + slot);
-                return base + kOffStage + slot * kSlotBytes;
+                return base + kOffRing + slot * kSlotBytes;
               };
               const uint64_t aI = smem_desc_sw128(base + kOffA + c * kChunkBytes);
               const uint64_t aT = smem_desc_sw128(base + kOffA + (nkc + c) * kChunkBytes);
               const uint32_t first = (c > 0) ? 1u : 0u;
               if (PASSES == 3) {
-                const uint32_t sa = next_full();
-                const uint32_t a_bar = slot_bar;
-                const uint64_t aIl = smem_desc_sw128(sa), aTl = smem_desc_sw128(sa + kChunkBytes);
+                uint32_t a_bar = 0;
+                uint64_t aIl, aTl;
+                if (kResLo) {
+                  aIl = smem_desc_sw128(base + kOffAlo + c * kChunkBytes);
+                  aTl = smem_desc_sw128(base + kOffAlo + (nkc + c) * kChunkBytes);
+                } else {
+                  const uint32_t sa = next_full();
+                  a_bar = slot_bar;
+                  aIl = smem_desc_sw128(sa);
+                  aTl = smem_desc_sw128(sa + kChunkBytes);
+                }
                 uint32_t sb = next_full();
                 {
                   const uint64_t bI = smem_desc_sw128(sb), bIl = smem_desc_sw128(sb + kChunkBytes);
@@ -399,7 +419,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                   }
                 }
                 mma_commit_pair(slot_bar, 3);
-                mma_commit_pair(a_bar, 3);
+                if (!kResLo) mma_commit_pair(a_bar, 3);
               } else {
                 const uint32_t sb = next_full();
                 const uint64_t bI = smem_desc_sw128(sb), bT = smem_desc_sw128(sb + kChunkBytes);
