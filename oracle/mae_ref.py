@@ -2,12 +2,15 @@
 
 TEST INFRASTRUCTURE - see ``oracle/__init__.py``.
 
-PARITY UNPINNED: ``/root/reference`` holds no MAE code (no random_masking,
-patchify, norm_pix or decoder anywhere - SURVEY.md section 0.2), so there is
-no reference file:line to follow.  This file is the *defining* restatement of
-the published MAE formulation (He et al., "Masked Autoencoders Are Scalable
-Vision Learners") that BASELINE.json's north_star names: per-sample noise
-argsort, keep/restore index gather, normalised-pixel masked-patch MSE.
+PARITY UNPINNED AGAINST THE REFERENCE: ``/root/reference`` holds no MAE code (no
+random_masking, patchify, norm_pix or decoder anywhere - SURVEY.md section 0.2),
+so there is no reference file:line to follow.  This file restates the
+published MAE formulation (He et al., "Masked Autoencoders Are Scalable Vision
+Learners") that BASELINE.json's north_star names: per-sample noise argsort,
+keep/restore index gather, normalised-pixel masked-patch MSE.  It is pinned on
+the outputs of a published implementation of that formulation, transformers'
+ViTMAE (``tests/golden/mae_hf.npz`` from ``tests/golden/make_golden_mae.py``;
+checked by ``tests/test_oracle_golden.py``).
 
 Contract fixed here (and matched bit-for-bit by the CUDA kernels):
 * ``len_keep = int(L * (1 - mask_ratio))``

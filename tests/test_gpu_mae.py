@@ -153,3 +153,33 @@ def test_restore_tokens_forward_backward(dtype, N, L, D, ratio):
     assert torch.equal(xc.grad.cpu().float(), dx_ref)
     tol = 1e-6 if dtype == torch.float32 else 8e-3  # bf16: the result is rounded once to bf16
     assert rel_err(tc.grad.float(), dt_ref) < tol
+
+
+# ------------------------------------------------------------------ golden vectors of a published implementation
+def test_mae_cuda_matches_published_vitmae_fixture(golden):
+    """CUDA path against tests/golden/mae_hf.npz (outputs of transformers' ViTMAE run unmodified, see
+    tests/golden/make_golden_mae.py): masking indices, mask and gathered tokens bit-exact; patchify bit-exact;
+    normalised-pixel masked MSE and its gradient within fp32 accumulation accuracy."""
+    import mae_clip_b200 as m
+    z = golden("mae_hf")
+    for tag in ("l196", "l50"):
+        x, noise = torch.from_numpy(z[f"mask.{tag}.x"]).cuda(), torch.from_numpy(z[f"mask.{tag}.noise"]).cuda()
+        for r in (0.5, 0.6, 0.75, 0.9):
+            k = f"mask.{tag}.r{int(r * 100)}"
+            xm, mask, restore = m.random_masking(x, r, noise)
+            assert np.array_equal(restore.cpu().numpy(), z[k + ".ref_ids_restore"])
+            assert np.array_equal(mask.cpu().numpy(), z[k + ".ref_mask"])
+            assert np.array_equal(xm.cpu().numpy(), z[k + ".ref_x_masked"])
+    imgs64 = torch.from_numpy(z["mse.s64.imgs"]).cuda()
+    assert np.array_equal(m.patchify(imgs64).cpu().numpy(), z["mse.s64.ref_patchify"])
+    for tag, nps in (("s64", (1, 0)), ("s224", (1,))):
+        imgs = torch.from_numpy(z[f"mse.{tag}.imgs"]).cuda()
+        for npx in nps:
+            k = f"mse.{tag}.np{npx}"
+            pred = torch.from_numpy(z[f"mse.{tag}.pred"]).cuda().requires_grad_(True)
+            mask = torch.from_numpy(z[k + ".mask"]).cuda()
+            loss = m.masked_mse_loss(pred, imgs, mask, patch_size=16, norm_pix_loss=bool(npx))
+            loss.backward()
+            ref = float(z[k + ".ref_loss"])
+            assert abs(loss.item() - ref) < 1e-5 * abs(ref)
+            assert rel_err(pred.grad, z[k + ".ref_dpred"]) < 1e-5
