@@ -214,6 +214,9 @@ class Phases:
         self.dT = torch.empty(b, D_EMB, **f32)
         nb = self.lib.mc_clip_planes_bytes(B, D_EMB, self.mode)
         self.planes = torch.empty(max(nb, 1), device=device, dtype=torch.uint8)
+        nf = 0 if os.environ.get("MAE_CLIP_DENSE", "0") == "1" else self.lib.mc_clip_tile_flags_bytes(b, B, D_EMB, self.mode)
+        self.flags_raw = torch.empty(nf, device=device, dtype=torch.uint8) if nf else None
+        self.flags = torch.empty(nf, device=device, dtype=torch.uint8) if nf else None
         nws = self.lib.mc_clip_loss_workspace_bytes(b, B, D_EMB, self.mode)
         self.ws = torch.empty(max(nws, 1), device=device, dtype=torch.uint8)
         self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
@@ -227,13 +230,20 @@ class Phases:
         ck(lib.mc_clip_prepare(p(I_all), p(T_all), B, B, D_EMB, 0, mode, p(self.planes), st), "prepare")
         if record: ev[1].record()
         ck(lib.mc_clip_stats(p(I_all), p(T_all), p(self.planes), b, B, D_EMB, off, 1.0, mode, p(self.stats_loc[0]),
-                             p(self.stats_loc[1]), p(self.stats_loc[2]), p(self.stats_loc[3]), p(self.ws), self.ws.numel(), st),
-           "stats")
+                             p(self.stats_loc[1]), p(self.stats_loc[2]), p(self.stats_loc[3]), p(self.flags_raw), p(self.ws),
+                             self.ws.numel(), st), "stats")
         stats_all = gather_vec(self.stats_loc[:3]) if gather_vec else self.stats_loc
+        if self.flags_raw is not None:   # tile flags: gather the raw bitmap rows of every rank, OR in the transpose
+            flags_all = self.flags_raw
+            if gather_vec:
+                import torch.distributed as dist
+                flags_all = self.torch.empty(self.flags_raw.numel() * (B // b), device=self.flags_raw.device, dtype=self.torch.uint8)
+                dist.all_gather_into_tensor(flags_all, self.flags_raw)
+            ck(lib.mc_clip_flags_finalize(p(flags_all), B, b, off, p(self.flags), st), "flags_finalize")
         if record: ev[2].record()
         ck(lib.mc_clip_rowloss(p(I_all), p(T_all), p(self.planes), b, B, D_EMB, off, 1.0, mode, p(stats_all[0]),
                                p(stats_all[1]), p(stats_all[2]), p(self.stats_loc[3]), p(self.gq_loc[0]), p(self.gq_loc[1]), p(self.part_buf),
-                               p(self.ws), self.ws.numel(), st), "rowloss")
+                               p(self.flags), p(self.ws), self.ws.numel(), st), "rowloss")
         if gather_vec:  # the loss partial rides along with the two vectors: one collective instead of two
             self.pack[:2] = self.gq_loc
             self.pack[2, 0:1] = self.part_buf
@@ -245,7 +255,7 @@ class Phases:
         if record: ev[3].record()
         ck(lib.mc_clip_bwd(p(I_all), p(T_all), p(self.planes), b, B, D_EMB, off, 1.0, mode, p(stats_all[0]),
                            p(stats_all[1]), p(stats_all[2]), p(gq_all[0]), p(gq_all[1]), None, p(self.dI), p(self.dT),
-                           p(self.ws), self.ws.numel(), st), "bwd")
+                           p(self.flags), p(self.ws), self.ws.numel(), st), "bwd")
         if record: ev[4].record()
         return self.part
 

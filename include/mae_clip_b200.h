@@ -132,20 +132,34 @@ int mc_clip_prepare_peers(const float* const* I_peers_host, const float* const* 
                           int b, int D, int mode, const unsigned int* amax_slots, void* planes_all,
                           void* stream);
 
+/* Tile flags (tcgen05 engines; optional).  The soft targets P = softmax_row(Z) are usually concentrated (for
+ * LayerNorm-ed embeddings Z_ii = 256 tau/2 towers over the off-diagonal entries), so most 128 x 128 tiles hold no
+ * P_ij above 2^-44.  mc_clip_stats can record, per (row block of 128, column tile of 128), whether the tile's
+ * largest Z_ij comes within 44 binades of max(Z_ii, running row maximum) <= rz_i - a rigorous superset of "some
+ * P_ij >= 2^-44".  mc_clip_flags_finalize ORs that with the transposed relation (P_ji, by the symmetry of Z) from
+ * the flags of ALL row blocks (the caller gathers them over ranks: [B/128][B/128] bytes).  mc_clip_rowloss then
+ * visits flagged tiles only and mc_clip_bwd skips the Z recompute and the dZ GEMMs elsewhere; the dropped terms
+ * sum to < B 2^-44 per row.  NULL pointers = dense (every tile).  mc_clip_tile_flags_bytes: size of the
+ * per-rank array (0 when the engine is the fp32 FMA one). */
+size_t mc_clip_tile_flags_bytes(int b, int B, int D, int mode);
+int mc_clip_flags_finalize(const uint8_t* flags_all, int B, int b, int row_offset, uint8_t* flags_loc,
+                           void* stream);
+
 int mc_clip_stats(const float* I_all, const float* T_all, const void* planes_all, int b, int B,
                   int D, int row_offset, float tau, int mode, float* row_lse_s_loc,
-                  float* col_lse_s_loc, float* row_lse_z_loc, float* row_ps_loc, void* ws,
-                  size_t ws_bytes, void* stream);
+                  float* col_lse_s_loc, float* row_lse_z_loc, float* row_ps_loc,
+                  uint8_t* tile_flags_loc_out, void* ws, size_t ws_bytes, void* stream);
 int mc_clip_rowloss(const float* I_all, const float* T_all, const void* planes_all, int b, int B,
                     int D, int row_offset, float tau, int mode, const float* row_lse_s_all,
                     const float* col_lse_s_all, const float* row_lse_z_all, const float* row_ps_loc,
-                    float* row_g_loc, float* col_sum_p_loc, float* loss_part, void* ws,
-                    size_t ws_bytes, void* stream);
+                    float* row_g_loc, float* col_sum_p_loc, float* loss_part,
+                    const uint8_t* tile_flags_loc, void* ws, size_t ws_bytes, void* stream);
 int mc_clip_bwd(const float* I_all, const float* T_all, const void* planes_all, int b, int B, int D,
                 int row_offset, float tau, int mode, const float* row_lse_s_all,
                 const float* col_lse_s_all, const float* row_lse_z_all, const float* row_g_all,
                 const float* col_sum_p_all, const float* grad_loss /* device scalar or NULL = 1 */,
-                float* dI_loc, float* dT_loc, void* ws, size_t ws_bytes, void* stream);
+                float* dI_loc, float* dT_loc, const uint8_t* tile_flags_loc, void* ws, size_t ws_bytes,
+                void* stream);
 
 /* Single-GPU convenience: prepare + three phases, forward and backward in one call
  * (loss_out: device scalar; dI/dT may both be NULL for forward only). */

@@ -1,6 +1,8 @@
 // C-ABI entry points of the contrastive soft-target loss (L3-L6): argument checks, engine
 // dispatch (SIMT fp32 strips vs tcgen05 fused tiles) and the single-GPU fused / host-buffer
 // conveniences.  Reference: /root/reference CLIP.py:34-43 (+ autograd at main.py:58).
+#include <stdlib.h>
+
 #include "clip_loss.cuh"
 
 namespace mc {
@@ -28,15 +30,17 @@ static int eff_mode(int mode, int D) {
 }
 
 struct FusedLayout {
-  size_t off_vec, off_planes, off_phase, total;
-  size_t vec_stride;
+  size_t off_vec, off_flags, off_planes, off_phase, total;
+  size_t vec_stride, flags_bytes;
 };
 static FusedLayout fused_layout(int B, int D, int mode) {
   mode = eff_mode(mode, D);
   FusedLayout l;
   l.vec_stride = round_up((size_t)B * 4, 256);
   l.off_vec = 0;
-  l.off_planes = round_up(6 * l.vec_stride + 256, 1024);  // + loss scalar slot; planes 1024-aligned
+  l.flags_bytes = (mode == MC_GEMM_SIMT_FP32) ? 0 : round_up(tc::tile_flags_bytes(B, B), 256);
+  l.off_flags = round_up(6 * l.vec_stride + 256, 256);    // raw flags of the statistics sweep, then the symmetrised ones
+  l.off_planes = round_up(l.off_flags + 2 * l.flags_bytes, 1024);  // planes 1024-aligned
   size_t planes = (mode == MC_GEMM_SIMT_FP32) ? 0 : tc::planes_bytes(B, D, mode);
   l.off_phase = l.off_planes + round_up(planes, 256);
   size_t phase = (mode == MC_GEMM_SIMT_FP32) ? simt::workspace_bytes(B, B, D)
@@ -75,6 +79,18 @@ int mc_clip_prepare(const float* I_loc, const float* T_loc, int b, int B, int D,
                      static_cast<cudaStream_t>(stream));
 }
 
+size_t mc_clip_tile_flags_bytes(int b, int B, int D, int mode) {
+  if (b <= 0 || B <= 0 || D <= 0 || eff_mode(mode, D) == MC_GEMM_SIMT_FP32) return 0;
+  return tc::tile_flags_bytes(b, B);
+}
+
+int mc_clip_flags_finalize(const uint8_t* flags_all, int B, int b, int row_offset, uint8_t* flags_loc, void* stream) {
+  MC_ARCH_GUARD();
+  MC_REQUIRE(flags_all && flags_loc && b > 0 && B >= b && row_offset >= 0 && row_offset + b <= B, MC_ERR_BAD_ARG,
+             "clip_flags_finalize: bad argument");
+  return tc::flags_finalize(flags_all, B, b, row_offset, flags_loc, static_cast<cudaStream_t>(stream));
+}
+
 int mc_clip_amax(const float* I_loc, const float* T_loc, int b, int D, float* I_copy, float* T_copy,
                  unsigned int* amax_bits, void* stream) {
   MC_ARCH_GUARD();
@@ -105,7 +121,7 @@ int mc_clip_prepare_peers(const float* const* I_peers_host, const float* const* 
 
 int mc_clip_stats(const float* I_all, const float* T_all, const void* planes_all, int b, int B,
                   int D, int row_offset, float tau, int mode, float* r_loc, float* c_loc,
-                  float* rz_loc, float* ps_loc, void* ws, size_t ws_bytes, void* stream) {
+                  float* rz_loc, float* ps_loc, uint8_t* tile_flags_out, void* ws, size_t ws_bytes, void* stream) {
   MC_ARCH_GUARD();
   int rc = check_problem("clip_stats", I_all, T_all, b, B, D, row_offset, tau, mode);
   if (rc) return rc;
@@ -114,13 +130,15 @@ int mc_clip_stats(const float* I_all, const float* T_all, const void* planes_all
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   mode = eff_mode(mode, D);
   if (mode == MC_GEMM_SIMT_FP32) return simt::stats(p, r_loc, c_loc, rz_loc, ps_loc, ws, ws_bytes, st);
+  p.tile_flags_out = tile_flags_out;
   return tc::stats(p, mode, r_loc, c_loc, rz_loc, ps_loc, ws, ws_bytes, st);
 }
 
 int mc_clip_rowloss(const float* I_all, const float* T_all, const void* planes_all, int b, int B,
                     int D, int row_offset, float tau, int mode, const float* r_all,
                     const float* c_all, const float* rz_all, const float* ps_loc, float* g_loc,
-                    float* q_loc, float* loss_part, void* ws, size_t ws_bytes, void* stream) {
+                    float* q_loc, float* loss_part, const uint8_t* tile_flags, void* ws, size_t ws_bytes,
+                    void* stream) {
   MC_ARCH_GUARD();
   int rc = check_problem("clip_rowloss", I_all, T_all, b, B, D, row_offset, tau, mode);
   if (rc) return rc;
@@ -131,13 +149,14 @@ int mc_clip_rowloss(const float* I_all, const float* T_all, const void* planes_a
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   mode = eff_mode(mode, D);
   if (mode == MC_GEMM_SIMT_FP32) return simt::rowloss(p, s, ps_loc, g_loc, q_loc, loss_part, ws, ws_bytes, st);
+  p.tile_flags = tile_flags;
   return tc::rowloss(p, mode, s, ps_loc, g_loc, q_loc, loss_part, ws, ws_bytes, st);
 }
 
 int mc_clip_bwd(const float* I_all, const float* T_all, const void* planes_all, int b, int B, int D,
                 int row_offset, float tau, int mode, const float* r_all, const float* c_all,
                 const float* rz_all, const float* g_all, const float* q_all, const float* grad_loss,
-                float* dI_loc, float* dT_loc, void* ws, size_t ws_bytes, void* stream) {
+                float* dI_loc, float* dT_loc, const uint8_t* tile_flags, void* ws, size_t ws_bytes, void* stream) {
   MC_ARCH_GUARD();
   int rc = check_problem("clip_bwd", I_all, T_all, b, B, D, row_offset, tau, mode);
   if (rc) return rc;
@@ -148,6 +167,7 @@ int mc_clip_bwd(const float* I_all, const float* T_all, const void* planes_all, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   mode = eff_mode(mode, D);
   if (mode == MC_GEMM_SIMT_FP32) return simt::bwd(p, s, grad_loss, dI_loc, dT_loc, ws, ws_bytes, st);
+  p.tile_flags = tile_flags;
   return tc::bwd(p, mode, s, grad_loss, dI_loc, dT_loc, ws, ws_bytes, st);
 }
 
@@ -178,14 +198,20 @@ int mc_clip_loss_fwd_bwd(const float* I, const float* T, int B, int D, float tau
   void* planes = base + l.off_planes;
   void* phase = base + l.off_phase;
   size_t phase_bytes = l.total - l.off_phase;
+  // tile flags: the statistics sweep marks the tiles that carry soft-target mass; the later sweeps skip the rest
+  // (MAE_CLIP_DENSE=1 keeps every tile: the A/B switch)
+  static const bool dense = getenv("MAE_CLIP_DENSE") != nullptr && getenv("MAE_CLIP_DENSE")[0] == '1';
+  uint8_t* flags_raw = (l.flags_bytes && !dense) ? reinterpret_cast<uint8_t*>(base + l.off_flags) : nullptr;
+  uint8_t* flags = flags_raw ? flags_raw + l.flags_bytes : nullptr;
   if ((rc = mc_clip_prepare(I, T, B, B, D, 0, mode, planes, stream))) return rc;
-  if ((rc = mc_clip_stats(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, ps, phase, phase_bytes, stream)))
+  if ((rc = mc_clip_stats(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, ps, flags_raw, phase, phase_bytes, stream)))
     return rc;
-  if ((rc = mc_clip_rowloss(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, ps, g, q, loss_out, phase,
+  if (flags_raw && (rc = mc_clip_flags_finalize(flags_raw, B, B, 0, flags, stream))) return rc;
+  if ((rc = mc_clip_rowloss(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, ps, g, q, loss_out, flags, phase,
                             phase_bytes, stream)))
     return rc;
   if (dI) {
-    if ((rc = mc_clip_bwd(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, g, q, nullptr, dI, dT, phase,
+    if ((rc = mc_clip_bwd(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, g, q, nullptr, dI, dT, flags, phase,
                           phase_bytes, stream)))
       return rc;
   }

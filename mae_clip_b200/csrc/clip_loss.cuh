@@ -10,6 +10,10 @@ struct ClipProblem {
   const void* planes_all;
   int b, B, D, row_offset;
   float tau;
+  // tile relevance of the soft targets (tcgen05 engine; see mc_clip_tile_flags_bytes): written by the statistics
+  // sweep, read (after mc_clip_flags_finalize) by the row-loss and gradient sweeps; null = dense
+  uint8_t* tile_flags_out = nullptr;
+  const uint8_t* tile_flags = nullptr;
 };
 
 struct ClipStatsAll {  // length-B vectors (device)
@@ -42,6 +46,8 @@ int push_shards(const float* I_loc, const float* T_loc, int b, int D, int rank, 
                 float* const* T_dst, unsigned int* const* amax_slots, unsigned int* scratch, cudaStream_t st);
 int prepare_peers(const float* const* I_peers, const float* const* T_peers, int world, int b, int D, int mode,
                   const unsigned int* amax_slots, void* planes_all, cudaStream_t st);
+size_t tile_flags_bytes(int b, int B);   // [row blocks of b][column tiles of B] bytes
+int flags_finalize(const uint8_t* flags_all, int B, int b, int row_offset, uint8_t* flags_loc, cudaStream_t st);
 int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
           size_t ws_bytes, cudaStream_t st);
 int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* ps_loc, float* g_loc,

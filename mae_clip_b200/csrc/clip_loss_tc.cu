@@ -73,7 +73,14 @@ struct PairParams {
   const float* ps;                     // row-loss sweep: sum_j P_ij S_ij of the owned rows (length b)
   float* part;                         // partial results of this phase
   const float* wscale;                 // gradient sweep: power-of-two scale of the fp16 weight tiles
+  // Tile relevance of the soft targets (see "tile flags" below): the statistics sweep WRITES flags_out
+  // [n_row_blocks][n_tiles] (1 = some P_ij of the tile may exceed 2^-44); the row-loss sweep skips tiles whose
+  // (symmetrised) flag is 0 and the gradient sweep skips their Z recompute and dZ GEMMs.  Null = dense.
+  uint8_t* flags_out;
+  const uint8_t* flags;
+  const float *norm_i, *norm_t;        // ||I_i||, ||T_i|| of ALL rows (statistics sweep: Z_ii lower-bounds rz_i)
 };
+constexpr float kFlagTheta2 = 44.f;    // log2 units: dropped terms are below 2^-44 of their row's soft-target mass
 
 struct PlanesLayout {
   size_t off_hdr, off_norm_i, off_norm_t, off_hi, off_lo, off_hiT, total;
@@ -236,6 +243,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             for (int c = 0; c < 2 * nkc; ++c)
               tma_load_2d_pair(base + kOffAlo + c * kChunkBytes, &map_a_lo, bar(kAFull), c * 64, row_a);
           for (int t = t0; t < t1; ++t) {
+            if (PHASE == kRowLoss && p.flags && !p.flags[(size_t)rb * p.n_tiles + t]) continue;
             const int j0 = t * kTileN + 32 * (int)rank, j1 = j0 + 64;
             for (int c = 0; c < nkc; ++c) {
               const int ci = c * 64, ct = D + c * 64;
@@ -313,6 +321,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const uint64_t xI = smem_desc_sw128(base + kOffXT), xT = smem_desc_sw128(base + kOffXT + xt_bytes);
         uint32_t it = 0, tt = 0, hh = 0, jj = 0;
         // one column half of a tile's gradient GEMMs: dT += W_S I_j + W_Z T_j, dI += W_St T_j + W_Z I_j
+        bool zg = true;  // does the tile whose gradient GEMMs are being issued carry soft-target mass (tile flag)?
         auto grad_half = [&](int h, bool first_of_job) {
           mbar_wait(bar(kWFull), hh & 1);
           mbar_wait(bar(kXTFull), hh & 1);
@@ -326,21 +335,27 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             const uint64_t kwZ = desc_advance_k(wZ, ks);
             if (do_s) {
               mma_f16_pair(tDT, desc_advance_k(wS, ks), kxI, idesc_grad, acc);   // dT += (dS/tau) I_j
-              mma_f16_pair(tDT, kwZ, kxT, idesc_grad, 1u);                       // dT += (tau/2 dZs) T_j
+              if (zg) mma_f16_pair(tDT, kwZ, kxT, idesc_grad, 1u);               // dT += (tau/2 dZs) T_j
             }
             if (do_z) {
               mma_f16_pair(tDI, desc_advance_k(wSt, ks), kxT, idesc_grad, acc);  // dI += (dS^T/tau) T_j
-              mma_f16_pair(tDI, kwZ, kxI, idesc_grad, 1u);                       // dI += (tau/2 dZs) I_j
+              if (zg) mma_f16_pair(tDI, kwZ, kxI, idesc_grad, 1u);               // dI += (tau/2 dZs) I_j
             }
           }
           mma_commit_pair(bar(h == 0 ? kGradDone : kGradDone1), 3);
         };
         for (int job = pair_id; job < njobs; job += npairs, ++jj) {
-          const int sp = job % p.nsplit;
+          const int rb = job / p.nsplit, sp = job % p.nsplit;
           const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+          const uint8_t* frow = p.flags ? p.flags + (size_t)rb * p.n_tiles : nullptr;
           mbar_wait(bar(kAFull), jj & 1);
           tc_fence_after();
-          for (int t = t0; t < t1; ++t, ++tt) {
+          bool zf = true, zf_prev = true;
+          for (int t = t0; t < t1; ++t) {
+            if (PHASE == kRowLoss && frow && !frow[t]) continue;   // every role skips the same tiles
+            zf_prev = zf;
+            zf = (PHASE != kBwd) || !frow || frow[t] != 0;         // gradient sweep: recompute Z only where P lives
+            zg = zf_prev;                                          // the woven gradient GEMMs belong to tile t - 1
             const uint32_t buf = tt % kNBuf, use = tt / kNBuf;
             mbar_wait(bar(kTmemEmpty0 + buf), (use & 1) ^ 1);
             tc_fence_after();
@@ -388,7 +403,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                       mma_f16_pair(tS, kT, kbl, idesc_tile, 1u);
                       mma_f16_pair(tS, desc_advance_k(aTl, ks), kb, idesc_tile, 1u);
                     }
-                    if (do_z) {
+                    if (do_z && zf) {
                       mma_f16_pair(tZ, kI, kb, idesc_tile, acc);                       // Z += I_i I_j^T
                       mma_f16_pair(tZ, kI, kbl, idesc_tile, 1u);
                       mma_f16_pair(tZ, desc_advance_k(aIl, ks), kb, idesc_tile, 1u);
@@ -411,7 +426,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                         mma_f16_pair(tSt, desc_advance_k(aIl, ks), kb, idesc_tile, 1u);
                       }
                     }
-                    if (do_z) {
+                    if (do_z && zf) {
                       mma_f16_pair(tZ, kT, kb, idesc_tile, 1u);                        // Z += T_i T_j^T
                       mma_f16_pair(tZ, kT, kbl, idesc_tile, 1u);
                       mma_f16_pair(tZ, desc_advance_k(aTl, ks), kb, idesc_tile, 1u);
@@ -432,7 +447,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                     mma_f16_pair(tS, kT, kbI, idesc_tile, acc);
                     mma_f16_pair(tSt, kI, kbT, idesc_tile, acc);
                   }
-                  if (do_z) {
+                  if (do_z && zf) {
                     mma_f16_pair(tZ, kI, kbI, idesc_tile, acc);
                     mma_f16_pair(tZ, kT, kbT, idesc_tile, 1u);
                   }
@@ -449,8 +464,10 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                 grad_half(1, false);
               }
             }
+            ++tt;
           }
           if (PHASE == kBwd) {
+            zg = zf;  // the last tile's own gradient GEMMs
             grad_half(0, t1 - 1 == t0);
             grad_half(1, false);
             mma_commit_pair(bar(kAccFull), 3);
@@ -507,8 +524,18 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       float ps2_i = 0.f;
       if (PHASE == kRowLoss && row_ok) ps2_i = p.ps[lrow] * kL2e;  // sum_j P_ij S_ij, log2 units
       float ag4[4] = {0.f, 0.f, 0.f, 0.f}, aq4[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint8_t* frow = p.flags ? p.flags + (size_t)rb * p.n_tiles : nullptr;
+      // tile flags (statistics sweep): rz_i >= Z_ii = (|I_i|^2 + |T_i|^2) tau / 2, so a tile whose largest Z_ij stays
+      // kFlagTheta2 binades below max(Z_ii, running maximum) cannot hold a P_ij above 2^-44
+      float zii2 = 0.f;
+      if (PHASE == kStats && p.flags_out && row_ok) {
+        const float ni = p.norm_i[gi], nt = p.norm_t[gi];
+        zii2 = (ni * ni + nt * nt) * p.half_tau * kL2e;
+      }
 
-      for (int t = t0; t < t1; ++t, ++tt) {
+      for (int t = t0; t < t1; ++t) {
+        if (PHASE == kRowLoss && frow && !frow[t]) continue;       // every role skips the same tiles
+        const bool zf = (PHASE != kBwd) || !frow || frow[t] != 0;  // gradient sweep: does this tile carry P mass?
         // ---- per-column statistics of this tile -> shared memory, one field per 128-float row
         float* cst = consts + (tt & 1) * (8 * 128);
         if (PHASE != kStats) {
@@ -548,7 +575,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           tmem_ld32(tS, vs);
           tmem_ld32(tSt, vt);
         }
-        tmem_ld32(tZ, vz);
+        if (zf) tmem_ld32(tZ, vz);   // a tile without soft-target mass has no Z accumulator at all
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive_cluster(bar(kTmemEmpty0 + buf), 0);
@@ -591,7 +618,12 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 #pragma unroll
               for (int u = 0; u < 4; ++u) c4[u] = fmaxf(c4[u], vz[e + u]);
             }
-            const float mn = fmaxf(mZ, fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3])));
+            const float cmz = fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3]));
+            if (p.flags_out) {
+              const bool hit = row_ok && cmz * cZ2 >= fmaxf(mZ * cZ2, zii2) - kFlagTheta2;
+              if (__any_sync(0xffffffffu, hit) && lane == 0) p.flags_out[(size_t)rb * p.n_tiles + t] = 1;
+            }
+            const float mn = fmaxf(mZ, cmz);
             if (mn != -INFINITY) {
               float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -632,8 +664,9 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         } else {
           // ---- gradient sweep: tile -> fp16 weight half-tile h -> tensor cores
           uint32_t wSp[16], wStp[16], wZp[16];
-          auto weights32 = [&](auto fast_tag) {
+          auto weights32 = [&](auto fast_tag, auto z_tag) {
             constexpr bool kFast = decltype(fast_tag)::value;
+            constexpr bool kZ = decltype(z_tag)::value;   // false: P_ij = P_ji = 0 on the whole tile (flag 0)
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
               const float4 f0 = *reinterpret_cast<const float4*>(cst + 0 * 128 + jl0 + e);  // -r2_j
@@ -650,28 +683,32 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const float a = vs[e + u], bt = vt[e + u];
-                const float z2 = vz[e + u] * cZ2;
                 const float e1 = ex2f(fmaf(a, cS2, -r2_i));     // softmax_row(S)_ij
                 const float e3 = ex2f(fmaf(bt, cS2, nr[u]));    // softmax_row(S)_ji
-                const float P = ex2f(z2 - rz2_i);
-                float Pt, dS, dSt;
+                float P = 0.f, Pt = 0.f, dS, dSt;
+                if (kZ) {
+                  const float z2 = vz[e + u] * cZ2;
+                  P = ex2f(z2 - rz2_i);
+                  Pt = kFast ? P * (fA_i * zc[u]) : ex2f(z2 + zc[u]);
+                }
                 if (kFast) {  // three exponentials; the other three are products of per-row / per-column factors
-                  Pt = P * (fA_i * zc[u]);
                   dS = fmaf(e1, fmaf(fC_i, qc[u], 1.f), -2.f * P);        // 2B dS_ij
                   dSt = fmaf(e3, fmaf(ej[u], fFQ_i, 1.f), -2.f * Pt);     // 2B dS_ji
                 } else {
                   const float e2 = ex2f(fmaf(a, cS2, nc[u]));   // softmax_col(S)_ij
                   const float e4 = ex2f(fmaf(bt, cS2, -c2_i));  // softmax_col(S)_ji
-                  Pt = ex2f(z2 + zc[u]);
                   dS = fmaf(-2.f, P, fmaf(e2, qc[u], e1));
                   dSt = fmaf(-2.f, Pt, fmaf(e4, q_i, e3));
                 }
-                const float G = fmaf(a, m2cS2, r2_i - nc[u]);           // 2B G_ij log2(e)
-                const float Gt = fmaf(bt, m2cS2, c2_i - nr[u]);         // 2B G_ji log2(e)
-                const float dZs = fmaf(P, G - gh_i, Pt * (Gt - gh[u]));
                 ms[u] = dS * wS;
                 mst[u] = dSt * wS;
-                mz[u] = dZs * wZ;
+                if (kZ) {
+                  const float G = fmaf(a, m2cS2, r2_i - nc[u]);           // 2B G_ij log2(e)
+                  const float Gt = fmaf(bt, m2cS2, c2_i - nr[u]);         // 2B G_ji log2(e)
+                  mz[u] = fmaf(P, G - gh_i, Pt * (Gt - gh[u])) * wZ;      // 2B dZs (log2 units) * scale
+                } else {
+                  mz[u] = 0.f;
+                }
               }
 #pragma unroll
               for (int u = 0; u < 4; u += 2) {
@@ -683,7 +720,11 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               }
             }
           };
-          if (fast) weights32(std::true_type{}); else weights32(std::false_type{});
+          if (zf) {
+            if (fast) weights32(std::true_type{}, std::true_type{}); else weights32(std::false_type{}, std::true_type{});
+          } else {
+            if (fast) weights32(std::true_type{}, std::false_type{}); else weights32(std::false_type{}, std::false_type{});
+          }
           // The single weight buffer is used by column half 0, then half 1, of every tile: wait until
           // the gradient MMAs of the preceding half have drained it.  One barrier per half keeps every
           // waiter at most one phase behind, which the parity test needs.
@@ -697,12 +738,14 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             *reinterpret_cast<uint4*>(wrow + chunk) = make_uint4(wSp[4 * k], wSp[4 * k + 1], wSp[4 * k + 2], wSp[4 * k + 3]);
             *reinterpret_cast<uint4*>(wrow + kChunkBytes + chunk) =
                 make_uint4(wStp[4 * k], wStp[4 * k + 1], wStp[4 * k + 2], wStp[4 * k + 3]);
-            *reinterpret_cast<uint4*>(wrow + 2 * kChunkBytes + chunk) =
-                make_uint4(wZp[4 * k], wZp[4 * k + 1], wZp[4 * k + 2], wZp[4 * k + 3]);
+            if (zf)
+              *reinterpret_cast<uint4*>(wrow + 2 * kChunkBytes + chunk) =
+                  make_uint4(wZp[4 * k], wZp[4 * k + 1], wZp[4 * k + 2], wZp[4 * k + 3]);
           }
           fence_proxy_async_smem();
           mbar_arrive_cluster(bar(kWFull), 0);
         }
+        ++tt;
       }
 
       // ---- end of job: write this job's partial results
@@ -1281,6 +1324,10 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float*
   pp.ps = ps_loc;
   pp.part = part;
   pp.wscale = wscale;
+  pp.flags_out = (PHASE == kStats) ? p.tile_flags_out : nullptr;
+  pp.flags = (PHASE != kStats) ? p.tile_flags : nullptr;
+  pp.norm_i = reinterpret_cast<const float*>(base + l.off_norm_i);
+  pp.norm_t = reinterpret_cast<const float*>(base + l.off_norm_t);
 
   auto kern = pair_kernel<PHASE, PASSES>;
   static std::atomic<unsigned long long> attr_done{0};  // per template instantiation, one bit per device
@@ -1312,11 +1359,41 @@ static int launch_phase(int mode, const ClipProblem& p, const ClipStatsAll& s, c
   return launch_pair<PHASE, 1>(p, s, ps_loc, part, wscale, st);
 }
 
+// ------------------------------------------------------------------------------------------
+// tile flags: flag(I, J) = 1 when some P_ij or P_ji of the 128 x 128 tile (row block I, column tile J) may exceed
+// 2^-44.  The statistics sweep decides the row side for its own row blocks; the column side of (I, J) is the row
+// side of (J, I) (Z is symmetric), which belongs to whoever owns row block J - hence the gather + transpose here.
+// ------------------------------------------------------------------------------------------
+size_t tile_flags_bytes(int b, int B) {
+  Split s = choose_split(b, B);
+  return (size_t)s.n_row_blocks * s.n_tiles;
+}
+
+// flags_all: [n_tiles][n_tiles] (all row blocks of the global batch), flags_loc: [own row blocks][n_tiles]
+__global__ void __launch_bounds__(256) flags_finalize_kernel(const uint8_t* __restrict__ flags_all, int n_tiles, int rb0,
+                                                             int nrb_loc, uint8_t* __restrict__ flags_loc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nrb_loc * n_tiles) return;
+  const int il = idx / n_tiles, j = idx - il * n_tiles, ig = rb0 + il;
+  flags_loc[idx] = (flags_all[(size_t)ig * n_tiles + j] | flags_all[(size_t)j * n_tiles + ig]) ? 1 : 0;
+}
+
+int flags_finalize(const uint8_t* flags_all, int B, int b, int row_offset, uint8_t* flags_loc, cudaStream_t st) {
+  MC_REQUIRE(row_offset % 128 == 0, MC_ERR_UNSUPPORTED, "clip_flags_finalize: row_offset %% 128 != 0");
+  Split s = choose_split(b, B);
+  const int total = s.n_row_blocks * s.n_tiles;
+  flags_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(flags_all, s.n_tiles, row_offset / 128, s.n_row_blocks,
+                                                             flags_loc);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
 int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
           size_t ws_bytes, cudaStream_t st) {
   MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_stats(tc): workspace %zu < %zu",
              ws_bytes, workspace_bytes(p.b, p.B, p.D, mode));
   ClipStatsAll none{nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (p.tile_flags_out) MC_CUDA(cudaMemsetAsync(p.tile_flags_out, 0, tile_flags_bytes(p.b, p.B), st));
   int rc = launch_phase<kStats>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st);
   if (rc) return rc;
   Split sp = choose_split(p.b, p.B);

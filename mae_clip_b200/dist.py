@@ -42,9 +42,11 @@ from ._lib import check, cur_stream, lib, ptr, require_cuda, workspace
 class CudaStripEngine:
     """The product engine: the three sweeps through the C ABI on this rank's GPU."""
 
-    def __init__(self, mode=None):
+    def __init__(self, mode=None, group=None):
         from .functional import _mode
         self.mode = _mode(mode)
+        self.group = group
+        self.sparse = os.environ.get("MAE_CLIP_DENSE", "0") != "1"   # tile flags (see mc_clip_tile_flags_bytes)
 
     def _ws(self, b, B, D, dev):
         return workspace(lib().mc_clip_loss_workspace_bytes(b, B, D, self.mode), dev)
@@ -63,27 +65,50 @@ class CudaStripEngine:
                 check(lib().mc_clip_prepare(ptr(I_all), ptr(T_all), B, B, D, 0, self.mode, ptr(planes),
                                             cur_stream()), "mc_clip_prepare")
             ws = self._ws(b, B, D, dev)
+            nf = lib().mc_clip_tile_flags_bytes(b, B, D, self.mode) if self.sparse else 0
+            flags_raw = torch.empty(nf, device=dev, dtype=torch.uint8) if nf else None
             check(lib().mc_clip_stats(ptr(I_all), ptr(T_all), ptr(planes), b, B, D, row_offset,
                                       float(tau), self.mode, ptr(out[0]), ptr(out[1]), ptr(out[2]),
-                                      ptr(out[3]), ptr(ws), ws.numel(), cur_stream()), "mc_clip_stats")
-        return out[:3], (planes, out[3])
+                                      ptr(out[3]), ptr(flags_raw), ptr(ws), ws.numel(), cur_stream()), "mc_clip_stats")
+        return out[:3], [planes, out[3], flags_raw]
+
+    def _final_flags(self, ctx, b, B, row_offset):
+        """Gather every rank's raw tile flags and OR in the transposed relation (first call after the sweep)."""
+        flags_raw = ctx[2]
+        if flags_raw is None or flags_raw.dtype == torch.bool:
+            return None if flags_raw is None else ctx[3]
+        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        if world > 1:
+            allf = torch.empty(world * flags_raw.numel(), device=flags_raw.device, dtype=torch.uint8)
+            dist.all_gather_into_tensor(allf, flags_raw, group=self.group)
+        else:
+            allf = flags_raw
+        final = torch.empty_like(flags_raw)
+        check(lib().mc_clip_flags_finalize(ptr(allf), B, b, row_offset, ptr(final), cur_stream()), "mc_clip_flags_finalize")
+        ctx[2] = torch.empty(0, dtype=torch.bool)   # marks "finalised"
+        ctx.append(final)
+        return final
 
     def rowloss(self, I_all, T_all, planes, b, row_offset, tau, stats_all):
-        planes, ps_loc = planes
+        ctx = planes
+        planes, ps_loc = ctx[0], ctx[1]
         B, D = I_all.shape
         dev = I_all.device
         out = torch.empty(2, b, device=dev, dtype=torch.float32)
         part = torch.empty(1, device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
+            flags = self._final_flags(ctx, b, B, row_offset)
             ws = self._ws(b, B, D, dev)
             check(lib().mc_clip_rowloss(ptr(I_all), ptr(T_all), ptr(planes), b, B, D, row_offset,
                                         float(tau), self.mode, ptr(stats_all[0]), ptr(stats_all[1]),
-                                        ptr(stats_all[2]), ptr(ps_loc), ptr(out[0]), ptr(out[1]), ptr(part), ptr(ws),
-                                        ws.numel(), cur_stream()), "mc_clip_rowloss")
+                                        ptr(stats_all[2]), ptr(ps_loc), ptr(out[0]), ptr(out[1]), ptr(part), ptr(flags),
+                                        ptr(ws), ws.numel(), cur_stream()), "mc_clip_rowloss")
         return out, part
 
     def bwd(self, I_all, T_all, planes, b, row_offset, tau, stats_all, gq_all, grad_loss):
-        planes, _ps_loc = planes
+        ctx = planes
+        planes = ctx[0]
+        flags = ctx[3] if len(ctx) > 3 else None
         B, D = I_all.shape
         dev = I_all.device
         dI = torch.empty(b, D, device=dev, dtype=torch.float32)
@@ -94,7 +119,7 @@ class CudaStripEngine:
             check(lib().mc_clip_bwd(ptr(I_all), ptr(T_all), ptr(planes), b, B, D, row_offset,
                                     float(tau), self.mode, ptr(stats_all[0]), ptr(stats_all[1]),
                                     ptr(stats_all[2]), ptr(gq_all[0]), ptr(gq_all[1]), ptr(gl), ptr(dI),
-                                    ptr(dT), ptr(ws), ws.numel(), cur_stream()), "mc_clip_bwd")
+                                    ptr(dT), ptr(flags), ptr(ws), ws.numel(), cur_stream()), "mc_clip_bwd")
         return dI, dT
 
 
@@ -175,6 +200,9 @@ class PeerStep:
         self.ex = exchange
         self.mode = _mode(mode)
         self.exchange_mode = exchange_mode or os.environ.get("MAE_CLIP_PEER_MODE", "push")
+        # tile flags travel as 32-bit words: every rank's share of the bitmap must be a whole number of words
+        nf = lib().mc_clip_tile_flags_bytes(exchange.b, exchange.B, exchange.D, self.mode)
+        self.flag_bytes = nf if (os.environ.get("MAE_CLIP_DENSE", "0") != "1" and nf % 4 == 0 and nf > 0) else 0
         if self.exchange_mode not in ("push", "pull"):
             raise ValueError(f"unknown peer exchange mode {self.exchange_mode!r}")
         if self.mode == _lib.GEMM_SIMT_FP32 or lib().mc_clip_planes_bytes(exchange.B, exchange.D, self.mode) == 0:
@@ -218,14 +246,23 @@ class PeerStep:
             mark()
             ws = workspace(L.mc_clip_loss_workspace_bytes(b, B, D, mode), dev)
             loc = torch.empty(6, b, **f32)  # r, c, rz, sum_j P_ij S_ij, g, q of the owned rows
+            nf = self.flag_bytes
+            flags_raw = torch.empty(nf, device=dev, dtype=torch.uint8) if nf else None
             check(L.mc_clip_stats(None, None, ptr(planes), b, B, D, rank * b, float(tau), mode, ptr(loc[0]), ptr(loc[1]),
-                                  ptr(loc[2]), ptr(loc[3]), ptr(ws), ws.numel(), st), "mc_clip_stats")
+                                  ptr(loc[2]), ptr(loc[3]), ptr(flags_raw), ptr(ws), ws.numel(), st), "mc_clip_stats")
             ex.publish(ptr(loc), 3, b, b, ex.OFF_VECS, ex.vec_stride, rank * b)
+            if nf:  # this rank's rows of the tile-flag bitmap, to every rank
+                ex.publish(ptr(flags_raw), 1, nf // 4, 0, ex.off_flags, 0, rank * (nf // 4))
             ex.barrier()
+            flags = None
+            if nf:
+                flags = torch.empty(nf, device=dev, dtype=torch.uint8)
+                check(L.mc_clip_flags_finalize(ex.local(ex.off_flags), B, b, rank * b, ptr(flags), st),
+                      "mc_clip_flags_finalize")
             mark()
             check(L.mc_clip_rowloss(None, None, ptr(planes), b, B, D, rank * b, float(tau), mode, ex.vec(0), ex.vec(1),
                                     ex.vec(2), ptr(loc[3]), ptr(loc[4]), ptr(loc[5]), ex.local(ex.OFF_PART_LOCAL),
-                                    ptr(ws), ws.numel(), st), "mc_clip_rowloss")
+                                    ptr(flags), ptr(ws), ws.numel(), st), "mc_clip_rowloss")
             ex.publish(ptr(loc[4]), 2, b, b, ex.OFF_VECS + 4 * 3 * ex.vec_stride, ex.vec_stride, rank * b)
             ex.publish(ex.local(ex.OFF_PART_LOCAL), 1, 1, 0, ex.OFF_PART_SLOTS, 0, rank)
             ex.barrier()
@@ -236,11 +273,11 @@ class PeerStep:
             ex.copy_out(ex.OFF_PART_SLOTS, 1, world, 0, parts, 0)
             loss = parts.sum()
             mark()
-        return loss, (planes, vecs)
+        return loss, (planes, vecs, flags)
 
     def backward(self, saved, tau, grad_loss=None, events=None):
         ex, mode, L = self.ex, self.mode, lib()
-        planes, vecs = saved
+        planes, vecs, flags = saved
         b, B, D = ex.b, ex.B, ex.D
         dev = planes.device
         dI = torch.empty(b, D, device=dev, dtype=torch.float32)
@@ -250,7 +287,7 @@ class PeerStep:
             ws = workspace(L.mc_clip_loss_workspace_bytes(b, B, D, mode), dev)
             check(L.mc_clip_bwd(None, None, ptr(planes), b, B, D, ex.rank * b, float(tau), mode, ptr(vecs[0]),
                                 ptr(vecs[1]), ptr(vecs[2]), ptr(vecs[3]), ptr(vecs[4]), ptr(gl), ptr(dI), ptr(dT),
-                                ptr(ws), ws.numel(), cur_stream()), "mc_clip_bwd")
+                                ptr(flags), ptr(ws), ws.numel(), cur_stream()), "mc_clip_bwd")
             if events is not None:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()
@@ -311,5 +348,5 @@ def global_clip_loss(image_emb_local, text_emb_local, temperature: float = 1.0, 
             step = None
         if step is not None:
             return _PeerGlobalClipLoss.apply(image_emb_local, text_emb_local, float(temperature), step)
-    engine = engine if engine is not None else CudaStripEngine(mode)
+    engine = engine if engine is not None else CudaStripEngine(mode, group)
     return _GlobalClipLoss.apply(image_emb_local, text_emb_local, float(temperature), engine, group)

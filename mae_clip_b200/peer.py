@@ -16,7 +16,7 @@ definition, the reference loss (``CLIP.py:34-43``) on the concatenated batch.
 
 Region layout (bytes): [0, 64) barrier flags | 128 private barrier epoch | [256, 320) amax slots | [512, 576) loss-partial
 slots | 768 local amax, 772 local loss partial, 784 push scratch (2 words) | 1024.. five length-B vectors
-(r, c, rz, g, q) | then two (B, D) fp32 images of the global batch (image / text embeddings): in
+(r, c, rz, g, q) | the [B/128][B/128]-byte tile-flag bitmap | then two (B, D) fp32 images of the global batch (image / text embeddings): in
 "pull" mode each rank fills only its own rows and peers read them from there; in "push" mode every
 rank stores its rows into all ranks' images and the staging reads locally.
 
@@ -69,8 +69,11 @@ class PeerExchange:
         self.b, self.D, self.B = b, D, b * self.world
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         self.vec_stride = _round_up(self.B, 64)                         # floats
+        # tile-flag bitmap of the whole batch ([B/128][B/128] bytes; every rank pushes its row blocks)
+        self.off_flags = _round_up(self.OFF_VECS + 5 * self.vec_stride * 4, 256)
+        nt = (self.B + 127) // 128
         # (B, D) fp32 images of the global batch: pull mode uses only the owner's rows of each
-        self.off_emb_i = _round_up(self.OFF_VECS + 5 * self.vec_stride * 4, 256)
+        self.off_emb_i = _round_up(self.off_flags + nt * nt, 256)
         self.off_emb_t = self.off_emb_i + _round_up(self.B * D * 4, 256)
         self.nbytes = self.off_emb_t + _round_up(self.B * D * 4, 256)
         self.ptrs = [0] * self.world

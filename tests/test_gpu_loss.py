@@ -258,3 +258,87 @@ def test_cross_entropy_empty_rows():
     import mae_clip_b200 as m
     out = m.cross_entropy(torch.zeros(0, 5, device="cuda"), torch.zeros(0, 5, device="cuda"))
     assert out.shape == (0,)
+
+
+# ------------------------------------------------------------------ tile flags (soft-target sparsity)
+def _phases(I, T, tau, mode, sparse):
+    """prepare -> stats -> (flags finalize) -> rowloss -> bwd through the C ABI on one GPU; returns loss, dI, dT, flags."""
+    import ctypes as C
+    from mae_clip_b200 import _lib
+    from mae_clip_b200._lib import check, cur_stream, ptr
+    lib = _lib.lib()
+    md = _lib.GEMM_MODES[mode]
+    B, D = I.shape
+    dev = I.device
+    planes = torch.empty(lib.mc_clip_planes_bytes(B, D, md), dtype=torch.uint8, device=dev)
+    ws = torch.empty(lib.mc_clip_loss_workspace_bytes(B, B, D, md), dtype=torch.uint8, device=dev)
+    st4 = torch.empty(4, B, device=dev)
+    gq = torch.empty(2, B, device=dev)
+    loss = torch.empty(1, device=dev)
+    dI, dT = torch.empty_like(I), torch.empty_like(T)
+    nf = lib.mc_clip_tile_flags_bytes(B, B, D, md) if sparse else 0
+    raw = torch.empty(nf, dtype=torch.uint8, device=dev) if nf else None
+    fin = torch.empty(nf, dtype=torch.uint8, device=dev) if nf else None
+    s = cur_stream()
+    check(lib.mc_clip_prepare(ptr(I), ptr(T), B, B, D, 0, md, ptr(planes), s))
+    check(lib.mc_clip_stats(ptr(I), ptr(T), ptr(planes), B, B, D, 0, tau, md, ptr(st4[0]), ptr(st4[1]), ptr(st4[2]), ptr(st4[3]),
+                            ptr(raw), ptr(ws), ws.numel(), s))
+    if nf:
+        check(lib.mc_clip_flags_finalize(ptr(raw), B, B, 0, ptr(fin), s))
+    check(lib.mc_clip_rowloss(ptr(I), ptr(T), ptr(planes), B, B, D, 0, tau, md, ptr(st4[0]), ptr(st4[1]), ptr(st4[2]), ptr(st4[3]),
+                              ptr(gq[0]), ptr(gq[1]), ptr(loss), ptr(fin), ptr(ws), ws.numel(), s))
+    check(lib.mc_clip_bwd(ptr(I), ptr(T), ptr(planes), B, B, D, 0, tau, md, ptr(st4[0]), ptr(st4[1]), ptr(st4[2]), ptr(gq[0]),
+                          ptr(gq[1]), None, ptr(dI), ptr(dT), ptr(fin), ptr(ws), ws.numel(), s))
+    torch.cuda.synchronize()
+    nt = (B + 127) // 128
+    return loss.item(), dI.cpu(), dT.cpu(), (fin.cpu().reshape(nt, nt) if nf else None)
+
+
+@pytest.mark.parametrize("mode", ["tc_f16x3", "tc_f16"])
+def test_tile_flags_skip_only_what_is_negligible(mode):
+    """LayerNorm-scale rows: Z_ii = 256 towers over every other Z_ij, so only the diagonal tiles carry soft-target
+    mass - the flagged sweeps must reproduce the dense ones (the dropped terms are below 2^-44) and the oracle."""
+    B = 1024 + 128
+    I = loss_ref.make_embeddings(B, 256, seed=21, scale=1.0).cuda()
+    T = loss_ref.make_embeddings(B, 256, seed=22, scale=1.0).cuda()
+    ld, dId, dTd, _ = _phases(I, T, 1.0, mode, sparse=False)
+    ls, dIs, dTs, flags = _phases(I, T, 1.0, mode, sparse=True)
+    assert torch.equal(flags, torch.eye(flags.shape[0], dtype=torch.uint8))       # diagonal tiles only
+    assert abs(ls - ld) <= 1e-6 * abs(ld)
+    assert rel_err(dIs, dId) < 1e-5 and rel_err(dTs, dTd) < 1e-5
+    ref_loss, ref_dI, ref_dT, _ = loss_ref.clip_loss_closed_form(I.cpu().numpy(), T.cpu().numpy(), 1.0)
+    lt, gt = _tols(mode)
+    assert abs(ls - ref_loss) <= lt * abs(ref_loss)
+    assert rel_err(dIs, ref_dI) < gt and rel_err(dTs, ref_dT) < gt
+
+
+def test_tile_flags_soft_regime_keeps_every_tile():
+    """Small norms: every Z_ij is within a few units of Z_ii, all tiles matter, nothing may be skipped."""
+    B = 640
+    I = loss_ref.make_embeddings(B, 256, seed=31, scale=0.1).cuda()
+    T = loss_ref.make_embeddings(B, 256, seed=32, scale=0.1).cuda()
+    ls, dIs, dTs, flags = _phases(I, T, 1.0, "tc_f16x3", sparse=True)
+    assert bool(flags.all())
+    ref_loss, ref_dI, ref_dT, _ = loss_ref.clip_loss_closed_form(I.cpu().numpy(), T.cpu().numpy(), 1.0)
+    assert abs(ls - ref_loss) <= LOSS_TOL * abs(ref_loss)
+    assert rel_err(dIs, ref_dI) < GRAD_TOL and rel_err(dTs, ref_dT) < GRAD_TOL
+
+
+def test_tile_flags_find_duplicates_across_tiles():
+    """Near-duplicate samples in different tiles share their soft-target mass (P_ij ~ 1/2): the off-diagonal tile
+    pair must be flagged (both orientations, through the transpose in mc_clip_flags_finalize) and the gradients
+    must match the oracle - a skipped tile there would be a visible error."""
+    B = 768
+    I0 = loss_ref.make_embeddings(B, 256, seed=41, scale=1.0)
+    T0 = loss_ref.make_embeddings(B, 256, seed=42, scale=1.0)
+    I0[700], T0[700] = I0[3], T0[3]                     # row 700 (tile 5) duplicates row 3 (tile 0)
+    I0[300] = I0[200] * 0.999                           # near-duplicate images only (tiles 2 and 1)
+    I, T = I0.cuda(), T0.cuda()
+    ls, dIs, dTs, flags = _phases(I, T, 1.0, "tc_f16x3", sparse=True)
+    assert flags[0, 5] == 1 and flags[5, 0] == 1
+    assert flags.sum().item() < flags.numel()           # still sparse elsewhere
+    ref_loss, ref_dI, ref_dT, _ = loss_ref.clip_loss_closed_form(I0.numpy(), T0.numpy(), 1.0)
+    assert abs(ls - ref_loss) <= LOSS_TOL * abs(ref_loss)
+    assert rel_err(dIs, ref_dI) < GRAD_TOL and rel_err(dTs, ref_dT) < GRAD_TOL
+    ld, dId, dTd, _ = _phases(I, T, 1.0, "tc_f16x3", sparse=False)
+    assert rel_err(dIs, dId) < 1e-5 and rel_err(dTs, dTd) < 1e-5
