@@ -278,6 +278,7 @@ class PeerPhases:
     def step(self, I_loc, T_loc, record=False):
         ev = [] if record else None
         loss, saved = self.step_impl.forward(I_loc, T_loc, 1.0, ev)
+        self.last_flags = saved[2]
         self.dI, self.dT = self.step_impl.backward(saved, 1.0, None, ev)
         self.part = loss.reshape(1)
         if record:
@@ -448,10 +449,15 @@ def run_b200(args):
         flops_bwd = 8.0 * B * B * D_EMB / world            # the gradient sweep: 4 GEMMs
         achieved = flops_bwd / (bwd_ms * 1e-3) / 1e12
         peak = peaks["tc_sustained"] or peaks["tc_burst"]
-        # executed tensor-core work of the gradient sweep: 4 recomputed GEMM units (S, S^T, Z with K = 2D) x passes
-        # + 4 gradient GEMM units, each 2 B^2 D / world FLOPs; the algorithmic count is the 4 gradient GEMMs
+        # executed tensor-core work of the gradient sweep, in GEMM units of 2 B^2 D / world FLOPs: S and S^T recomputed
+        # (2 units x passes) + their two gradient GEMMs, and - only on the tiles flagged as carrying soft-target mass -
+        # Z (2 units x passes, K = 2D) + the two dZ GEMMs.  The algorithmic count is the 4 gradient GEMMs.
         passes = 3 if mode == "tc_f16x3" else 1
-        exec_units = (4 * passes + 4) if mode != "simt_fp32" else 8
+        flags_t = getattr(ph, "flags", None)
+        if flags_t is None and hasattr(ph, "step_impl"):
+            flags_t = getattr(ph, "last_flags", None)
+        density = float(flags_t.float().mean().item()) if flags_t is not None else 1.0
+        exec_units = ((2 * passes + 2) + density * (2 * passes + 2)) if mode != "simt_fp32" else 8
         executed = exec_units * 2.0 * B * B * D_EMB / world / (bwd_ms * 1e-3) / 1e12
         ncu = {}
         try:
@@ -465,7 +471,10 @@ def run_b200(args):
             "dtype": {"simt_fp32": "fp32", "tc_f16x3": "fp32 (fp16 hi+lo split operands, 3 tcgen05 passes, fp32 accumulate)",
                       "tc_f16": "fp16 operands, fp32 accumulate"}[mode],
             "data": "synthetic", "config": dict(workload_config(args, B, mode), transport=(
-                transport + "-" + ph.step_impl.exchange_mode if transport == "peer" else transport)), "loss": loss_val,
+                transport + "-" + ph.step_impl.exchange_mode if transport == "peer" else transport),
+                soft_target_tiles=("every tile (dense)" if flags_t is None else
+                                   "flagged tiles only: %.4f of the %d x %d tiles can hold P_ij >= 2^-44" % (
+                                       density, flags_t.numel() // ((B + 127) // 128), (B + 127) // 128))), "loss": loss_val,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": emax.item() / e_steps},
             "gpu_launches": int(launches),
@@ -477,6 +486,7 @@ def run_b200(args):
                          "peak_source": peaks["source"] + ", bf16 sustained (fp16 runs at the same tensor rate)",
                          "traffic": ncu.get("traffic_bytes_per_launch") if (mode == "tc_f16x3" and world == 1 and B == 32768) else None,
                          "executed_tflops": executed, "executed_frac": executed / peak,
+                         "tile_flag_density": density,
                          "ncu_tensor_pipe_active_pct": ncu.get("tensor_pipe_active_pct"), "ncu_source": ncu.get("source"),
                          "algorithmic_flops_per_launch": flops_bwd,
                          "step_achieved": flops_step / (ms_per_step * 1e-3) / 1e12,

@@ -24,15 +24,15 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, b, mode, transport, ret):
+def _worker(rank, world, port, b, mode, transport, ret, scale=0.15):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from mae_clip_b200.dist import global_clip_loss
-        I = loss_ref.make_embeddings(b, 256, seed=1000 + rank, scale=0.15).cuda().requires_grad_(True)
-        T = loss_ref.make_embeddings(b, 256, seed=2000 + rank, scale=0.15).cuda().requires_grad_(True)
+        I = loss_ref.make_embeddings(b, 256, seed=1000 + rank, scale=scale).cuda().requires_grad_(True)
+        T = loss_ref.make_embeddings(b, 256, seed=2000 + rank, scale=scale).cuda().requires_grad_(True)
         if transport.startswith("peer"):
             os.environ["MAE_CLIP_PEER_MODE"] = transport.split("-")[1]
             transport = "peer"
@@ -69,6 +69,26 @@ def test_global_loss_two_gpus(mode, transport):
         assert abs(loss.item() - ref_loss) < lt * abs(ref_loss)
         assert rel_err(dI, ref_dI[r * b:(r + 1) * b]) < gt
         assert rel_err(dT, ref_dT[r * b:(r + 1) * b]) < gt
+
+
+@pytest.mark.parametrize("transport", ["peer-push", "nccl"])
+def test_global_loss_two_gpus_sparse_soft_targets(transport):
+    """LayerNorm-scale rows over two ranks at 512 rows each: only the diagonal tiles carry soft-target mass, so the
+    tile-flag bitmap really prunes (and has to cross ranks for its transposed half) - against the CPU oracle."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world, b = 2, 512
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), b, "tc_f16x3", transport, ret, 1.0), nprocs=world, join=True)
+    I = torch.cat([loss_ref.make_embeddings(b, 256, seed=1000 + r, scale=1.0) for r in range(world)])
+    T = torch.cat([loss_ref.make_embeddings(b, 256, seed=2000 + r, scale=1.0) for r in range(world)])
+    ref_loss, ref_dI, ref_dT, _ = loss_ref.clip_loss_closed_form(I.numpy(), T.numpy(), 1.0, grad_loss=2.0)
+    for r in range(world):
+        loss, dI, dT = ret[r]
+        assert abs(loss.item() - ref_loss) < 1e-4 * abs(ref_loss)
+        assert rel_err(dI, ref_dI[r * b:(r + 1) * b]) < 1e-3
+        assert rel_err(dT, ref_dT[r * b:(r + 1) * b]) < 1e-3
 
 
 @pytest.mark.parametrize("exchange_mode", ["push", "pull"])
