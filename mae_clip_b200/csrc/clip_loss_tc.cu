@@ -36,7 +36,9 @@ constexpr int kEpiThreads = 256;
 constexpr int kMaxSplit = 16;
 constexpr int kIssuers = 1;         // MMA-issuing warps per leader CTA (see the issuer role)
 
-enum Phase { kStats = 0, kRowLoss = 1, kBwd = 2 };
+enum Phase { kStats = 0, kRowLoss = 1, kBwd = 2, kStatsZ = 3 };
+// kStats with tile flags requested is the PROBE form: S, S^T at full precision, Z from the hi planes only - enough to
+// tell which tiles can hold soft-target mass; kStatsZ then computes S and the exact Z on those tiles (rz, sum P S).
 
 // shared-memory map (offsets from a 1024-byte aligned base)
 constexpr int kOffA = 0;                      // resident hi plane of the CTA's 64 rows: 2D/64 chunks
@@ -80,7 +82,8 @@ struct PairParams {
   const uint8_t* flags;
   const float *norm_i, *norm_t;        // ||I_i||, ||T_i|| of ALL rows (statistics sweep: Z_ii lower-bounds rz_i)
 };
-constexpr float kFlagTheta2 = 44.f;    // log2 units: dropped terms are below 2^-44 of their row's soft-target mass
+constexpr float kFlagTheta2 = 44.f;
+constexpr float kProbeMargin2 = 2.f;  // single-pass Z of the probe: |error| << 2 binades    // log2 units: dropped terms are below 2^-44 of their row's soft-target mass
 
 struct PlanesLayout {
   size_t off_hdr, off_norm_i, off_norm_t, off_hi, off_lo, off_hiT, total;
@@ -243,7 +246,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             for (int c = 0; c < 2 * nkc; ++c)
               tma_load_2d_pair(base + kOffAlo + c * kChunkBytes, &map_a_lo, bar(kAFull), c * 64, row_a);
           for (int t = t0; t < t1; ++t) {
-            if (PHASE == kRowLoss && p.flags && !p.flags[(size_t)rb * p.n_tiles + t]) continue;
+            if ((PHASE == kRowLoss || PHASE == kStatsZ) && p.flags && !p.flags[(size_t)rb * p.n_tiles + t]) continue;
             const int j0 = t * kTileN + 32 * (int)rank, j1 = j0 + 64;
             for (int c = 0; c < nkc; ++c) {
               const int ci = c * 64, ct = D + c * 64;
@@ -351,8 +354,9 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           mbar_wait(bar(kAFull), jj & 1);
           tc_fence_after();
           bool zf = true, zf_prev = true;
+          const bool zprobe = PHASE == kStats && p.flags_out != nullptr;  // Z from the hi planes only
           for (int t = t0; t < t1; ++t) {
-            if (PHASE == kRowLoss && frow && !frow[t]) continue;   // every role skips the same tiles
+            if ((PHASE == kRowLoss || PHASE == kStatsZ) && frow && !frow[t]) continue;   // every role skips the same tiles
             zf_prev = zf;
             zf = (PHASE != kBwd) || !frow || frow[t] != 0;         // gradient sweep: recompute Z only where P lives
             zg = zf_prev;                                          // the woven gradient GEMMs belong to tile t - 1
@@ -405,8 +409,10 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                     }
                     if (do_z && zf) {
                       mma_f16_pair(tZ, kI, kb, idesc_tile, acc);                       // Z += I_i I_j^T
-                      mma_f16_pair(tZ, kI, kbl, idesc_tile, 1u);
-                      mma_f16_pair(tZ, desc_advance_k(aIl, ks), kb, idesc_tile, 1u);
+                      if (!zprobe) {
+                        mma_f16_pair(tZ, kI, kbl, idesc_tile, 1u);
+                        mma_f16_pair(tZ, desc_advance_k(aIl, ks), kb, idesc_tile, 1u);
+                      }
                     }
                   }
                 }
@@ -420,7 +426,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                     const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
                     const uint64_t kb = desc_advance_k(bT, ks), kbl = desc_advance_k(bTl, ks);
                     if (do_s) {
-                      if (PHASE != kRowLoss) {
+                      if (PHASE != kRowLoss && PHASE != kStatsZ) {
                         mma_f16_pair(tSt, kI, kb, idesc_tile, acc);                    // St = I_i T_j^T
                         mma_f16_pair(tSt, kI, kbl, idesc_tile, 1u);
                         mma_f16_pair(tSt, desc_advance_k(aIl, ks), kb, idesc_tile, 1u);
@@ -428,8 +434,10 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                     }
                     if (do_z && zf) {
                       mma_f16_pair(tZ, kT, kb, idesc_tile, 1u);                        // Z += T_i T_j^T
-                      mma_f16_pair(tZ, kT, kbl, idesc_tile, 1u);
-                      mma_f16_pair(tZ, desc_advance_k(aTl, ks), kb, idesc_tile, 1u);
+                      if (!zprobe) {
+                        mma_f16_pair(tZ, kT, kbl, idesc_tile, 1u);
+                        mma_f16_pair(tZ, desc_advance_k(aTl, ks), kb, idesc_tile, 1u);
+                      }
                     }
                   }
                 }
@@ -445,7 +453,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                   const uint64_t kbI = desc_advance_k(bI, ks), kbT = desc_advance_k(bT, ks);
                   if (do_s && PHASE != kRowLoss) {
                     mma_f16_pair(tS, kT, kbI, idesc_tile, acc);
-                    mma_f16_pair(tSt, kI, kbT, idesc_tile, acc);
+                    if (PHASE != kStatsZ) mma_f16_pair(tSt, kI, kbT, idesc_tile, acc);
                   }
                   if (do_z && zf) {
                     mma_f16_pair(tZ, kI, kbI, idesc_tile, acc);
@@ -503,7 +511,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       const bool row_ok = lrow < p.b;
       // per-row statistics, log2 domain: r2 = r log2(e), ... ; gh = 2B g log2(e)
       float r2_i = 0.f, c2_i = 0.f, rz2_i = 0.f, gh_i = 0.f, q_i = 0.f;
-      if (PHASE != kStats && row_ok) { r2_i = p.r[gi] * kL2e; c2_i = p.c[gi] * kL2e; rz2_i = p.rz[gi] * kL2e; }
+      if (PHASE != kStats && PHASE != kStatsZ && row_ok) { r2_i = p.r[gi] * kL2e; c2_i = p.c[gi] * kL2e; rz2_i = p.rz[gi] * kL2e; }
       if (PHASE == kBwd && row_ok) { gh_i = p.g[gi] * (2.f * (float)p.B) * kL2e; q_i = p.q[gi]; }
       float wS = 0.f, wZ = 0.f;
       bool fast = false;
@@ -534,11 +542,11 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       }
 
       for (int t = t0; t < t1; ++t) {
-        if (PHASE == kRowLoss && frow && !frow[t]) continue;       // every role skips the same tiles
+        if ((PHASE == kRowLoss || PHASE == kStatsZ) && frow && !frow[t]) continue;       // every role skips the same tiles
         const bool zf = (PHASE != kBwd) || !frow || frow[t] != 0;  // gradient sweep: does this tile carry P mass?
         // ---- per-column statistics of this tile -> shared memory, one field per 128-float row
         float* cst = consts + (tt & 1) * (8 * 128);
-        if (PHASE != kStats) {
+        if (PHASE != kStats && PHASE != kStatsZ) {
           if (tid_e < 128) {
             const int jcol = t * kTileN + tid_e;
             const bool ok = jcol < p.B;
@@ -571,16 +579,15 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         // this thread's 32 columns of the three tiles go to registers at once; the tile buffer is
         // handed back to the tensor cores before any arithmetic starts
         float vs[32], vt[32], vz[32];
-        if (PHASE != kRowLoss) {
-          tmem_ld32(tS, vs);
-          tmem_ld32(tSt, vt);
-        }
+        if (PHASE != kRowLoss) tmem_ld32(tS, vs);
+        if (PHASE != kRowLoss && PHASE != kStatsZ) tmem_ld32(tSt, vt);
         if (zf) tmem_ld32(tZ, vz);   // a tile without soft-target mass has no Z accumulator at all
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive_cluster(bar(kTmemEmpty0 + buf), 0);
 
-        if (PHASE == kStats) {
+        if (PHASE == kStats || PHASE == kStatsZ) {
+          const bool zprobe = PHASE == kStats && p.flags_out != nullptr;
           auto lse_add32 = [&](float* v, float c, float& mx, float& sm) {
             if (ragged) {
 #pragma unroll
@@ -619,12 +626,12 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               for (int u = 0; u < 4; ++u) c4[u] = fmaxf(c4[u], vz[e + u]);
             }
             const float cmz = fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3]));
-            if (p.flags_out) {
-              const bool hit = row_ok && cmz * cZ2 >= fmaxf(mZ * cZ2, zii2) - kFlagTheta2;
+            if (zprobe) {  // rz_i >= Z_ii: a tile whose (hi-plane) Z stays this far below it holds no P_ij >= 2^-44
+              const bool hit = row_ok && cmz * cZ2 >= zii2 - kFlagTheta2 - kProbeMargin2;
               if (__any_sync(0xffffffffu, hit) && lane == 0) p.flags_out[(size_t)rb * p.n_tiles + t] = 1;
             }
             const float mn = fmaxf(mZ, cmz);
-            if (mn != -INFINITY) {
+            if (!zprobe && mn != -INFINITY) {
               float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
               for (int e = 0; e < 32; e += 4) {
@@ -641,8 +648,10 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               mZ = mn;
             }
           }
-          lse_add32(vs, cS2, mS, sS);
-          lse_add32(vt, cS2, mSt, sSt);
+          if (PHASE == kStats) {
+            lse_add32(vs, cS2, mS, sS);
+            lse_add32(vt, cS2, mSt, sSt);
+          }
         } else if (PHASE == kRowLoss) {
           if (ragged) {
 #pragma unroll
@@ -749,7 +758,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       }
 
       // ---- end of job: write this job's partial results
-      if (PHASE == kStats || PHASE == kRowLoss) {
+      if (PHASE == kStats || PHASE == kStatsZ || PHASE == kRowLoss) {
         // four threads hold pieces of row m (lane half n1 x column half h): combine through shared memory
         float* scratch = consts;  // [3 partners][7][64] floats; the column constants are dead once the tile loop is over
         OnlineLse2 lS, lSt, lZ;  // log2-domain (max, sum) pairs
@@ -760,7 +769,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         named_bar_sync(2, kEpiThreads);
         if (part != 0) {
           float* sc = scratch + (part - 1) * 7 * 64;
-          if (PHASE == kStats) {
+          if (PHASE == kStats || PHASE == kStatsZ) {
             sc[0 * 64 + m] = lS.m; sc[1 * 64 + m] = lS.s;
             sc[2 * 64 + m] = lSt.m; sc[3 * 64 + m] = lSt.s;
             sc[4 * 64 + m] = lZ.m; sc[5 * 64 + m] = lZ.s;
@@ -771,7 +780,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         }
         named_bar_sync(2, kEpiThreads);
         if (part == 0) {
-          if (PHASE == kStats) {
+          if (PHASE == kStats || PHASE == kStatsZ) {
             for (int k = 0; k < 3; ++k) {
               const float* sc = scratch + k * 7 * 64;
               lS.merge(sc[0 * 64 + m], sc[1 * 64 + m]);
@@ -782,10 +791,15 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             }
             float2* out = reinterpret_cast<float2*>(p.part);
             const size_t o = (size_t)sp * 4 * p.bpad + lrow;
-            out[o] = make_float2(lS.m, lS.s);
-            out[o + p.bpad] = make_float2(lSt.m, lSt.s);
-            out[o + 2 * (size_t)p.bpad] = make_float2(lZ.m, lZ.s);
-            out[o + 3 * (size_t)p.bpad] = make_float2(aZ * (inv_s2 * p.inv_tau), 0.f);  // natural S units, relative to lZ.m
+            const bool probe = PHASE == kStats && p.flags_out != nullptr;  // the Z half then comes from the kStatsZ sweep
+            if (PHASE == kStats) {
+              out[o] = make_float2(lS.m, lS.s);
+              out[o + p.bpad] = make_float2(lSt.m, lSt.s);
+            }
+            if (!probe) {
+              out[o + 2 * (size_t)p.bpad] = make_float2(lZ.m, lZ.s);
+              out[o + 3 * (size_t)p.bpad] = make_float2(aZ * (inv_s2 * p.inv_tau), 0.f);  // natural S units, relative to lZ.m
+            }
           } else {
             float pc = acc_g, q = acc_q;
             for (int k = 0; k < 3; ++k) { pc += scratch[k * 7 * 64 + m]; q += scratch[k * 7 * 64 + 64 + m]; }
@@ -1325,7 +1339,7 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float*
   pp.part = part;
   pp.wscale = wscale;
   pp.flags_out = (PHASE == kStats) ? p.tile_flags_out : nullptr;
-  pp.flags = (PHASE != kStats) ? p.tile_flags : nullptr;
+  pp.flags = (PHASE == kStatsZ) ? p.tile_flags_out : (PHASE != kStats ? p.tile_flags : nullptr);  // kStatsZ: the probe's raw flags
   pp.norm_i = reinterpret_cast<const float*>(base + l.off_norm_i);
   pp.norm_t = reinterpret_cast<const float*>(base + l.off_norm_t);
 
@@ -1396,6 +1410,9 @@ int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_
   if (p.tile_flags_out) MC_CUDA(cudaMemsetAsync(p.tile_flags_out, 0, tile_flags_bytes(p.b, p.B), st));
   int rc = launch_phase<kStats>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st);
   if (rc) return rc;
+  // with tile flags the sweep above was the probe form (S, S^T exact, Z from the hi planes -> flags); the exact Z and
+  // sum_j P_ij S_ij follow on the flagged tiles only
+  if (p.tile_flags_out && (rc = launch_phase<kStatsZ>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st))) return rc;
   Split sp = choose_split(p.b, p.B);
   stats_finalize_kernel<<<(p.b + 255) / 256, 256, 0, st>>>(static_cast<const float2*>(ws), sp.nsplit, sp.bpad, p.b,
                                                           r_loc, c_loc, rz_loc, ps_loc);
