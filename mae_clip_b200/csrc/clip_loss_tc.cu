@@ -168,6 +168,21 @@ struct OnlineLse2 {  // running log2-domain log-sum-exp
   }
 };
 
+// Sparse sweeps (row loss, exact-Z statistics): does the job (row block, column split) contain a flagged tile at all?
+// Every role evaluates this on its own and skips the job consistently (no resident loads, no barrier traffic).
+__device__ __forceinline__ bool job_has_tiles(const uint8_t* __restrict__ frow, int t0, int t1) {
+  unsigned any = 0;
+  int t = t0;
+  if ((reinterpret_cast<uintptr_t>(frow + t0) & 15) == 0) {
+    for (; t + 16 <= t1; t += 16) {
+      const uint4 v = *reinterpret_cast<const uint4*>(frow + t);
+      any |= v.x | v.y | v.z | v.w;
+    }
+  }
+  for (; t < t1; ++t) any |= frow[t];
+  return any != 0;
+}
+
 template <int PHASE, int PASSES>
 __global__ void __launch_bounds__(kThreads, 1)
 pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -234,11 +249,14 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       // ========================================================= TMA producer: resident rows + ring
       if (elect_one()) {
         uint32_t it = 0, jj = 0;
-        for (int job = pair_id; job < njobs; job += npairs, ++jj) {
+        for (int job = pair_id; job < njobs; job += npairs) {
           const int rb = job / p.nsplit, sp = job % p.nsplit;
           const int row_a = p.row_offset + rb * 128 + (int)rank * kRowsCta;
           const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-          mbar_wait(bar(kJobDone), (jj & 1) ^ 1);
+          if ((PHASE == kRowLoss || PHASE == kStatsZ) && p.flags &&
+              !job_has_tiles(p.flags + (size_t)rb * p.n_tiles, t0, t1)) continue;   // jj counts processed jobs only
+          const uint32_t jpar = jj++ & 1;
+          mbar_wait(bar(kJobDone), jpar ^ 1);
           if (leader) mbar_arrive_expect_tx(bar(kAFull), (kResLo ? 2u : 1u) * 2u * 2u * nkc * kChunkBytes);
           for (int c = 0; c < 2 * nkc; ++c)
             tma_load_2d_pair(base + kOffA + c * kChunkBytes, &map_a_hi, bar(kAFull), c * 64, row_a);
@@ -347,11 +365,13 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           }
           mma_commit_pair(bar(h == 0 ? kGradDone : kGradDone1), 3);
         };
-        for (int job = pair_id; job < njobs; job += npairs, ++jj) {
+        for (int job = pair_id; job < njobs; job += npairs) {
           const int rb = job / p.nsplit, sp = job % p.nsplit;
           const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
           const uint8_t* frow = p.flags ? p.flags + (size_t)rb * p.n_tiles : nullptr;
-          mbar_wait(bar(kAFull), jj & 1);
+          if ((PHASE == kRowLoss || PHASE == kStatsZ) && frow && !job_has_tiles(frow, t0, t1)) continue;
+          const uint32_t jpar = jj++ & 1;
+          mbar_wait(bar(kAFull), jpar);
           tc_fence_after();
           bool zf = true, zf_prev = true;
           const bool zprobe = PHASE == kStats && p.flags_out != nullptr;  // Z from the hi planes only
@@ -466,7 +486,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             mma_commit_pair(bar(kTmemFull0 + buf), 3);
             if (PHASE == kBwd) {
               if (t == t0) {
-                mbar_wait(bar(kAccEmpty), (jj & 1) ^ 1);  // the previous job's accumulators were read out
+                mbar_wait(bar(kAccEmpty), jpar ^ 1);  // the previous job's accumulators were read out
                 tc_fence_after();
               } else {
                 grad_half(1, false);
@@ -509,6 +529,23 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       const int lrow = rb * 128 + (int)rank * kRowsCta + m;  // row within this rank's strip
       const int gi = p.row_offset + lrow;
       const bool row_ok = lrow < p.b;
+      if ((PHASE == kRowLoss || PHASE == kStatsZ) && p.flags &&
+          !job_has_tiles(p.flags + (size_t)rb * p.n_tiles, t0, t1)) {
+        // no flagged tile in this (row block, column split): the other roles skip the job too; its partials are empty
+        if (2 * h + n1 == 0) {
+          if (PHASE == kStatsZ) {
+            float2* out = reinterpret_cast<float2*>(p.part);
+            const size_t o = (size_t)sp * 4 * p.bpad + lrow;
+            out[o + 2 * (size_t)p.bpad] = make_float2(-INFINITY, 0.f);
+            out[o + 3 * (size_t)p.bpad] = make_float2(0.f, 0.f);
+          } else {
+            const size_t o = (size_t)sp * 2 * p.bpad + lrow;
+            p.part[o] = 0.f;
+            p.part[o + p.bpad] = 0.f;
+          }
+        }
+        continue;
+      }
       // per-row statistics, log2 domain: r2 = r log2(e), ... ; gh = 2B g log2(e)
       float r2_i = 0.f, c2_i = 0.f, rz2_i = 0.f, gh_i = 0.f, q_i = 0.f;
       if (PHASE != kStats && PHASE != kStatsZ && row_ok) { r2_i = p.r[gi] * kL2e; c2_i = p.c[gi] * kL2e; rz2_i = p.rz[gi] * kL2e; }
@@ -885,7 +922,16 @@ __global__ void __launch_bounds__(256) rowloss_finalize_kernel(const float* __re
 __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
   __shared__ double sm[32];
   double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)v[i];
+  int i0 = 0;
+  if ((reinterpret_cast<uintptr_t>(v) & 15) == 0) {  // 16-byte loads: a quarter of the dependent round trips
+    const int n4 = n >> 2;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 x = reinterpret_cast<const float4*>(v)[i];
+      acc += ((double)x.x + (double)x.y) + ((double)x.z + (double)x.w);
+    }
+    i0 = n4 << 2;
+  }
+  for (int i = i0 + threadIdx.x; i < n; i += blockDim.x) acc += (double)v[i];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -911,12 +957,29 @@ __global__ void __launch_bounds__(1024) wscale_kernel(const float* __restrict__ 
   // maxima: r, c, q, (unused), ||I||, ||T||, rz, -r, -c, -rz  (the negated ones give the minima)
   __shared__ float sm[10][32];
   float v[10] = {-INFINITY, -INFINITY, 0.f, 0.f, 0.f, 0.f, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
-  for (int i = threadIdx.x; i < B; i += blockDim.x) {
-    const float ri = r[i], ci = c[i], zi = rz[i];
-    v[0] = fmaxf(v[0], ri); v[1] = fmaxf(v[1], ci); v[2] = fmaxf(v[2], q[i]);
-    v[4] = fmaxf(v[4], norm_i[i]); v[5] = fmaxf(v[5], norm_t[i]);
+  auto take = [&](float ri, float ci, float zi, float qi, float ni, float nt) {
+    v[0] = fmaxf(v[0], ri); v[1] = fmaxf(v[1], ci); v[2] = fmaxf(v[2], qi);
+    v[4] = fmaxf(v[4], ni); v[5] = fmaxf(v[5], nt);
     v[6] = fmaxf(v[6], zi); v[7] = fmaxf(v[7], -ri); v[8] = fmaxf(v[8], -ci); v[9] = fmaxf(v[9], -zi);
+  };
+  int i0 = 0;
+  const uintptr_t align = reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(rz) |
+                          reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(norm_i) |
+                          reinterpret_cast<uintptr_t>(norm_t);
+  if ((align & 15) == 0) {  // one block walks six length-B vectors: 16-byte loads, six independent streams in flight
+    const int B4 = B >> 2;
+    for (int i = threadIdx.x; i < B4; i += blockDim.x) {
+      const float4 a = reinterpret_cast<const float4*>(r)[i], b4 = reinterpret_cast<const float4*>(c)[i];
+      const float4 z = reinterpret_cast<const float4*>(rz)[i], qq = reinterpret_cast<const float4*>(q)[i];
+      const float4 ni = reinterpret_cast<const float4*>(norm_i)[i], nt = reinterpret_cast<const float4*>(norm_t)[i];
+      take(a.x, b4.x, z.x, qq.x, ni.x, nt.x);
+      take(a.y, b4.y, z.y, qq.y, ni.y, nt.y);
+      take(a.z, b4.z, z.z, qq.z, ni.z, nt.z);
+      take(a.w, b4.w, z.w, qq.w, ni.w, nt.w);
+    }
+    i0 = B4 << 2;
   }
+  for (int i = i0 + threadIdx.x; i < B; i += blockDim.x) take(r[i], c[i], rz[i], q[i], norm_i[i], norm_t[i]);
   for (int k = 0; k < 10; ++k) {
     v[k] = warp_max(v[k]);
     if ((threadIdx.x & 31) == 0) sm[k][threadIdx.x >> 5] = v[k];
