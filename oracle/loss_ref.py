@@ -108,3 +108,22 @@ def make_embeddings(batch: int, dim: int = 256, seed: int = 0, scale: float = 1.
     x = torch.randn(batch, dim, generator=g, dtype=torch.float32)
     x = torch.nn.functional.layer_norm(x, (dim,)) * scale
     return x.to(dtype)
+
+
+def tile_relevance(image_emb, text_emb, temperature: float = 1.0, tile: int = 128, theta_log2: float = 44.0):
+    """Exact tile relevance of the soft targets (checker for the CUDA engine's tile flags): entry (I, J) is True when
+    some P_ij >= 2^-theta or some P_ji >= 2^-theta with i in row block I and j in column tile J, where
+    P = softmax_row(Z), Z = (I I^T + T T^T) tau / 2 (``CLIP.py:35-39``).  The engine may flag MORE tiles (its test is a
+    bound), never fewer."""
+    import numpy as np
+    I = np.asarray(image_emb, dtype=np.float64)
+    T = np.asarray(text_emb, dtype=np.float64)
+    Z = (I @ I.T + T @ T.T) * (temperature / 2.0)
+    logP = Z - (Z.max(axis=1, keepdims=True) + np.log(np.exp(Z - Z.max(axis=1, keepdims=True)).sum(axis=1, keepdims=True)))
+    rel = logP >= -theta_log2 * np.log(2.0)
+    rel = rel | rel.T
+    B = Z.shape[0]
+    nt = (B + tile - 1) // tile
+    pad = nt * tile - B
+    rel = np.pad(rel, ((0, pad), (0, pad)))
+    return rel.reshape(nt, tile, nt, tile).any(axis=(1, 3))

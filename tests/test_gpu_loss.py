@@ -342,3 +342,20 @@ def test_tile_flags_find_duplicates_across_tiles():
     assert rel_err(dIs, ref_dI) < GRAD_TOL and rel_err(dTs, ref_dT) < GRAD_TOL
     ld, dId, dTd, _ = _phases(I, T, 1.0, "tc_f16x3", sparse=False)
     assert rel_err(dIs, dId) < 1e-5 and rel_err(dTs, dTd) < 1e-5
+
+
+@pytest.mark.parametrize("scale,tau", [(1.0, 1.0), (0.5, 1.0), (0.35, 1.0), (0.6, 0.25), (0.1, 1.0)])
+def test_tile_flags_are_a_superset_of_the_exact_relevance(scale, tau):
+    """The engine's flags come from a bound (probe Z against Z_ii); the oracle computes the exact set of tiles holding
+    a P_ij or P_ji >= 2^-44 in fp64.  Flags must cover it in every regime (hard, intermediate, soft), with a few rows
+    of larger norm thrown in so that rz_i > Z_ii for the others."""
+    B = 640 + 64
+    I0 = loss_ref.make_embeddings(B, 256, seed=51, scale=scale)
+    T0 = loss_ref.make_embeddings(B, 256, seed=52, scale=scale)
+    I0[5] *= 1.3; T0[400] *= 1.2; I0[401] = I0[17]          # norm outliers and a cross-tile duplicate
+    _ls, _dI, _dT, flags = _phases(I0.cuda(), T0.cuda(), tau, "tc_f16x3", sparse=True)
+    exact = torch.from_numpy(loss_ref.tile_relevance(I0.numpy(), T0.numpy(), tau))
+    assert flags.shape == exact.shape
+    assert bool((flags.bool() | ~exact).all()), "a tile with soft-target mass was not flagged"
+    if scale == 1.0:
+        assert flags.sum().item() <= exact.sum().item() + 4   # and the bound is tight in the hard regime
