@@ -5,19 +5,23 @@
 //     S  = T_i I_j^T / tau      St = I_i T_j^T / tau  (= S_ji)      Z = (I_i I_j^T + T_i T_j^T) tau/2
 // in tensor memory and reduces them in the epilogue.
 //
-// Execution model (one kernel template, three phases):
+// Execution model (one kernel template, four phases: statistics [probe form when tile flags are on], exact-Z statistics
+// on the flagged tiles, row loss, gradient):
 //   * a CTA PAIR (cluster of 2, tcgen05 cta_group::2, M = 128) owns 128 samples i, 64 per CTA; the
 //     64 x N accumulator tile of a CTA lives in TMEM as 128 lanes x N/2 columns (lanes 0-63: first
 //     half of the tile's columns, lanes 64-127: second half);
-//   * operands are fp16 planes of X = [I || T] (row-scaled by a power of two): `hi` = fp16(x),
+//   * operands are fp16 planes of X = [I || T] (scaled by one power of two): `hi` = fp16(x),
 //     `lo` = fp16(x - hi).  F16X3 issues hi*hi + hi*lo + lo*hi (relative operand error ~2^-22, i.e.
 //     fp32-class logits); F16 issues hi*hi only;
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA) + TMEM allocator, warps 2-5 = epilogue
-//     (one thread per TMEM lane).  The hi plane of the pair's own rows stays resident in shared
-//     memory for the whole job; lo planes and the column tiles stream through an mbarrier ring;
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA, one elected lane) + TMEM allocator, warp 2 = X^T tile
+//     producer (gradient sweep), warps 4-11 = epilogue (two threads per TMEM lane, 32 columns each).  The hi plane of
+//     the pair's own rows stays resident in shared memory for the whole job (the lo plane too in the forward sweeps);
+//     the column tiles stream through an mbarrier ring;
 //   * the gradient sweep converts each tile into fp16 weight tiles (dS, dS^T, dZ + dZ^T) in shared
 //     memory and feeds them straight back to the tensor cores against X^T tiles, accumulating
-//     dT_i and dI_i (64 x D each per CTA) in TMEM for the whole job.
+//     dT_i and dI_i (64 x D each per CTA) in TMEM for the whole job;
+//   * tile flags (PairParams::flags / flags_out): tiles that cannot hold soft-target mass (P_ij < 2^-44 throughout)
+//     skip their Z work in every sweep - see DESIGN.md section 4.1.
 #include "clip_loss.cuh"
 #include "tc_ptx.cuh"
 
