@@ -87,7 +87,7 @@ struct PairParams {
   const float *norm_i, *norm_t;        // ||I_i||, ||T_i|| of ALL rows (statistics sweep: Z_ii lower-bounds rz_i)
 };
 constexpr float kFlagTheta2 = 44.f;
-constexpr float kProbeMargin2 = 2.f;  // single-pass Z of the probe: |error| << 2 binades    // log2 units: dropped terms are below 2^-44 of their row's soft-target mass
+constexpr float kProbeMargin2 = 2.f;  // slack on top of the probe's worst-case rounding bound (see zmargin2)    // log2 units: dropped terms are below 2^-44 of their row's soft-target mass
 
 struct PlanesLayout {
   size_t off_hdr, off_norm_i, off_norm_t, off_hi, off_lo, off_hiT, total;
@@ -577,6 +577,9 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       // tile flags (statistics sweep): rz_i >= Z_ii = (|I_i|^2 + |T_i|^2) tau / 2, so a tile whose largest Z_ij stays
       // kFlagTheta2 binades below max(Z_ii, running maximum) cannot hold a P_ij above 2^-44
       float zii2 = 0.f;
+      // rounding of the probe: the hi planes carry 2^-11 relative error per element, so |dZ_ij| <= 2^-10 sqrt(Z_ii Z_jj)
+      // <= 2^-10 max_k Z_kk, and every |x| is below 2 / s (the planes' scale), i.e. Z_kk < 2 D (2/s)^2 tau/2
+      const float zmargin2 = kProbeMargin2 + (1.f / 512.f) * (8.f * (float)D * inv_s2 * p.half_tau * kL2e);
       if (PHASE == kStats && p.flags_out && row_ok) {
         const float ni = p.norm_i[gi], nt = p.norm_t[gi];
         zii2 = (ni * ni + nt * nt) * p.half_tau * kL2e;
@@ -668,7 +671,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             }
             const float cmz = fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3]));
             if (zprobe) {  // rz_i >= Z_ii: a tile whose (hi-plane) Z stays this far below it holds no P_ij >= 2^-44
-              const bool hit = row_ok && cmz * cZ2 >= zii2 - kFlagTheta2 - kProbeMargin2;
+              const bool hit = row_ok && cmz * cZ2 >= zii2 - kFlagTheta2 - zmargin2;
               if (__any_sync(0xffffffffu, hit) && lane == 0) p.flags_out[(size_t)rb * p.n_tiles + t] = 1;
             }
             const float mn = fmaxf(mZ, cmz);
