@@ -136,7 +136,7 @@ int mc_clip_prepare_peers(const float* const* I_peers_host, const float* const* 
  * LayerNorm-ed embeddings Z_ii = 256 tau/2 towers over the off-diagonal entries), so most 128 x 128 tiles hold no
  * P_ij above 2^-44.  When mc_clip_stats is given a flag array it runs as a PROBE (S, S^T at full precision, Z from
  * the hi planes only) that records, per (row block of 128, column tile of 128), whether the tile's largest Z_ij
- * comes within 44 (+2 for the probe's rounding) binades of Z_ii <= rz_i - a rigorous superset of "some
+ * comes within 44 binades (plus the probe's worst-case rounding bound) of Z_ii <= rz_i - a rigorous superset of "some
  * P_ij >= 2^-44" - and then computes the exact Z statistics on the flagged tiles only.  mc_clip_flags_finalize ORs that with the transposed relation (P_ji, by the symmetry of Z) from
  * the flags of ALL row blocks (the caller gathers them over ranks: [B/128][B/128] bytes).  mc_clip_rowloss then
  * visits flagged tiles only and mc_clip_bwd skips the Z recompute and the dZ GEMMs elsewhere; the dropped terms
