@@ -87,6 +87,11 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
+            # nvidia-smi needs a few hundred ms before its first sample: wait for it, or the whole (sub-second) run
+            # is over before the sampler sees anything
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 5.0 and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
