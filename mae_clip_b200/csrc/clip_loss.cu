@@ -3,6 +3,8 @@
 // conveniences.  Reference: /root/reference CLIP.py:34-43 (+ autograd at main.py:58).
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "clip_loss.cuh"
 
 namespace mc {
@@ -176,10 +178,16 @@ size_t mc_clip_loss_fused_workspace_bytes(int B, int D, int mode) {
   return fused_layout(B, D, mode).total;
 }
 
-int mc_clip_loss_fwd_bwd(const float* I, const float* T, int B, int D, float tau, int mode,
-                         float* loss_out, float* dI, float* dT, void* ws, size_t ws_bytes,
-                         void* stream) {
-  MC_ARCH_GUARD();
+// The fused single-GPU step.  The gradient sweep runs over `n_strips` row strips (the row-sharded form the ranks of
+// a multi-GPU job use, here back to back on one device); `hook`, when given, is called on the host after the loss
+// kernels (rows < 0) and after each strip's gradient kernels have been enqueued (row0, rows) - the host-buffer entry
+// uses it to start the device -> host copy of a finished strip while the next one is still being swept.
+struct StripHook {
+  int (*fn)(void* ctx, int row0, int rows);
+  void* ctx;
+};
+static int fused_run(const float* I, const float* T, int B, int D, float tau, int mode, float* loss_out, float* dI,
+                     float* dT, void* ws, size_t ws_bytes, void* stream, int n_strips, const StripHook* hook) {
   int rc = check_problem("clip_loss_fwd_bwd", I, T, B, B, D, 0, tau, mode);
   if (rc) return rc;
   MC_REQUIRE(loss_out && ws, MC_ERR_BAD_ARG, "clip_loss_fwd_bwd: null loss_out/workspace");
@@ -210,12 +218,35 @@ int mc_clip_loss_fwd_bwd(const float* I, const float* T, int B, int D, float tau
   if ((rc = mc_clip_rowloss(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, ps, g, q, loss_out, flags, phase,
                             phase_bytes, stream)))
     return rc;
-  if (dI) {
-    if ((rc = mc_clip_bwd(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, g, q, nullptr, dI, dT, flags, phase,
-                          phase_bytes, stream)))
+  if (hook && (rc = hook->fn(hook->ctx, -1, 0))) return rc;
+  if (!dI) return MC_OK;
+  // strips of whole 128-row blocks; a strip whose partial-sum workspace would not fit the step's buffer (more
+  // column splits per row block) folds the sweep back into one launch
+  const int n_blocks = (B + 127) / 128;
+  if (n_strips > n_blocks) n_strips = n_blocks;
+  if (n_strips < 1) n_strips = 1;
+  const int strip_rows = ((n_blocks + n_strips - 1) / n_strips) * 128;
+  if (n_strips > 1 && (mc_clip_loss_workspace_bytes(strip_rows, B, D, mode) > phase_bytes ||
+                       (B - (n_strips - 1) * strip_rows) <= 0))
+    n_strips = 1;
+  const int n_tiles = n_blocks;  // column tiles of B = row blocks of B
+  for (int k = 0; k < n_strips; ++k) {
+    const int row0 = n_strips == 1 ? 0 : k * strip_rows;
+    const int rows = n_strips == 1 ? B : (row0 + strip_rows <= B ? strip_rows : B - row0);
+    const uint8_t* fl = flags ? flags + (size_t)(row0 / 128) * n_tiles : nullptr;
+    if ((rc = mc_clip_bwd(I, T, planes, rows, B, D, row0, tau, mode, r, c, rz, g, q, nullptr, dI + (size_t)row0 * D,
+                          dT + (size_t)row0 * D, fl, phase, phase_bytes, stream)))
       return rc;
+    if (hook && (rc = hook->fn(hook->ctx, row0, rows))) return rc;
   }
   return MC_OK;
+}
+
+int mc_clip_loss_fwd_bwd(const float* I, const float* T, int B, int D, float tau, int mode,
+                         float* loss_out, float* dI, float* dT, void* ws, size_t ws_bytes,
+                         void* stream) {
+  MC_ARCH_GUARD();
+  return fused_run(I, T, B, D, tau, mode, loss_out, dI, dT, ws, ws_bytes, stream, 1, nullptr);
 }
 
 size_t mc_clip_loss_host_workspace_bytes(int B, int D, int mode) {
@@ -223,6 +254,49 @@ size_t mc_clip_loss_host_workspace_bytes(int B, int D, int mode) {
   size_t emb = round_up((size_t)B * D * 4, 256);
   return 4 * emb + 256 + fused_layout(B, D, mode).total;
 }
+
+// Host-buffer form.  Gradients leave the device strip by strip: a second stream copies the rows of a finished strip
+// while the next strip is being swept, so of the 2 B D 4 bytes going back only the last strip's share is exposed.
+namespace {
+struct HostCopyCtx {
+  cudaStream_t st, copy;
+  cudaEvent_t ev[8];
+  int n_ev;
+  const float *loss_dev, *gI, *gT;
+  float *loss_host, *dI_host, *dT_host;
+  int D;
+  bool want_grad;
+};
+int host_copy_hook(void* vctx, int row0, int rows) {
+  HostCopyCtx* c = static_cast<HostCopyCtx*>(vctx);
+  if (rows <= 0 || row0 < 0) {  // after the loss kernels
+    MC_CUDA(cudaMemcpyAsync(c->loss_host, c->loss_dev, 4, cudaMemcpyDeviceToHost, c->st));
+    return MC_OK;
+  }
+  if (!c->want_grad) return MC_OK;
+  const size_t off = (size_t)row0 * c->D, bytes = (size_t)rows * c->D * 4;
+  MC_REQUIRE(c->n_ev < 8, MC_ERR_BAD_ARG, "clip_loss_host: too many strips");
+  cudaEvent_t ev = c->ev[c->n_ev++];
+  MC_CUDA(cudaEventRecord(ev, c->st));
+  MC_CUDA(cudaStreamWaitEvent(c->copy, ev, 0));
+  MC_CUDA(cudaMemcpyAsync(c->dT_host + off, c->gT + off, bytes, cudaMemcpyDeviceToHost, c->copy));
+  MC_CUDA(cudaMemcpyAsync(c->dI_host + off, c->gI + off, bytes, cudaMemcpyDeviceToHost, c->copy));
+  return MC_OK;
+}
+// one copy stream per device, created on first use and kept (callers on different threads may share it: every
+// copy is ordered by the caller's own events)
+int copy_stream_for_current_device(cudaStream_t* out) {
+  static std::mutex mu;
+  static cudaStream_t streams[64] = {};
+  int dev = 0;
+  MC_CUDA(cudaGetDevice(&dev));
+  MC_REQUIRE(dev >= 0 && dev < 64, MC_ERR_BAD_ARG, "clip_loss_host: device index %d", dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (!streams[dev]) MC_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
+  *out = streams[dev];
+  return MC_OK;
+}
+}  // namespace
 
 int mc_clip_loss_fwd_bwd_host(const float* I_host, const float* T_host, int B, int D, float tau,
                               int mode, float* loss_host, float* dI_host, float* dT_host, void* dws,
@@ -243,19 +317,46 @@ int mc_clip_loss_fwd_bwd_host(const float* I_host, const float* T_host, int B, i
   void* ws = base + 4 * emb + 256;
   size_t ws_bytes = dws_bytes - (4 * emb + 256);
   size_t bytes = (size_t)B * D * 4;
-  MC_CUDA(cudaMemcpyAsync(dIin, I_host, bytes, cudaMemcpyHostToDevice, st));
-  MC_CUDA(cudaMemcpyAsync(dTin, T_host, bytes, cudaMemcpyHostToDevice, st));
-  bool want_grad = dI_host && dT_host;
-  int rc = mc_clip_loss_fwd_bwd(dIin, dTin, B, D, tau, mode, loss, want_grad ? gI : nullptr,
-                                want_grad ? gT : nullptr, ws, ws_bytes, stream);
-  if (rc) return rc;
-  MC_CUDA(cudaMemcpyAsync(loss_host, loss, 4, cudaMemcpyDeviceToHost, st));
+  const bool want_grad = dI_host && dT_host;
+  // strips only where a strip still fills the machine (>= 8192 rows: 64 row blocks x column splits) and the tcgen05
+  // engine runs; small batches and the SIMT engine keep the single sweep
+  int n_strips = 1;
+  if (want_grad && eff_mode(mode, D) != MC_GEMM_SIMT_FP32 && B >= 16384) n_strips = B >= 32768 ? 4 : 2;
+  HostCopyCtx ctx = {};
+  ctx.st = st; ctx.D = D; ctx.want_grad = want_grad;
+  ctx.loss_dev = loss; ctx.gI = gI; ctx.gT = gT;
+  ctx.loss_host = loss_host; ctx.dI_host = dI_host; ctx.dT_host = dT_host;
+  int rc = MC_OK;
+  cudaEvent_t done = nullptr;
+  int n_created = 0;
   if (want_grad) {
-    MC_CUDA(cudaMemcpyAsync(dI_host, gI, bytes, cudaMemcpyDeviceToHost, st));
-    MC_CUDA(cudaMemcpyAsync(dT_host, gT, bytes, cudaMemcpyDeviceToHost, st));
+    if ((rc = copy_stream_for_current_device(&ctx.copy))) return rc;
+    for (; n_created < n_strips; ++n_created)
+      if (cudaEventCreateWithFlags(&ctx.ev[n_created], cudaEventDisableTiming) != cudaSuccess) break;
+    if (n_created < n_strips || cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess) {
+      for (int i = 0; i < n_created; ++i) cudaEventDestroy(ctx.ev[i]);
+      MC_REQUIRE(false, MC_ERR_CUDA, "clip_loss_host: cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
   }
-  MC_CUDA(cudaStreamSynchronize(st));
-  return MC_OK;
+  auto body = [&]() -> int {
+    MC_CUDA(cudaMemcpyAsync(dTin, T_host, bytes, cudaMemcpyHostToDevice, st));
+    MC_CUDA(cudaMemcpyAsync(dIin, I_host, bytes, cudaMemcpyHostToDevice, st));
+    StripHook hook{host_copy_hook, &ctx};
+    int r2 = fused_run(dIin, dTin, B, D, tau, mode, loss, want_grad ? gI : nullptr, want_grad ? gT : nullptr, ws,
+                       ws_bytes, stream, n_strips, &hook);
+    if (r2) return r2;
+    if (want_grad) {
+      MC_CUDA(cudaEventRecord(done, ctx.copy));
+      MC_CUDA(cudaStreamWaitEvent(st, done, 0));
+    }
+    MC_CUDA(cudaStreamSynchronize(st));
+    return MC_OK;
+  };
+  rc = body();
+  if (rc && want_grad) cudaStreamSynchronize(ctx.copy);  // nothing of this call may still be in flight
+  for (int i = 0; i < n_created; ++i) cudaEventDestroy(ctx.ev[i]);
+  if (done) cudaEventDestroy(done);
+  return rc;
 }
 
 }  // extern "C"

@@ -158,6 +158,40 @@ def test_loss_host_buffer_entry_point():
         assert rel_err(dI, ref_dI) < GRAD_TOL and rel_err(dT, ref_dT) < GRAD_TOL
 
 
+@pytest.mark.parametrize("B", [16384, 16500, 32768])
+def test_loss_host_entry_strips_match_single_sweep(B):
+    """From B = 16384 the host-buffer entry runs the gradient sweep in row strips (2, 4 at 32768) and copies a strip
+    back while the next is swept: same loss and gradients as the device-resident single sweep, ragged last strip
+    included, and identical on a second call (events / copy stream reused correctly)."""
+    from mae_clip_b200 import _lib
+    lib = _lib.lib()
+    D, mode = 256, 1
+    I = loss_ref.make_embeddings(B, D, seed=3).pin_memory()
+    T = (0.6 * I + 0.8 * loss_ref.make_embeddings(B, D, seed=4)).pin_memory()   # correlated pairs: a real diagonal
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    n0 = lib.mc_clip_loss_fused_workspace_bytes(B, D, mode)
+    ws0 = torch.empty(n0, dtype=torch.uint8, device="cuda")
+    Id, Td = I.cuda(), T.cuda()
+    l0, dI0, dT0 = torch.zeros(1, device="cuda"), torch.empty_like(Id), torch.empty_like(Td)
+    _lib.check(lib.mc_clip_loss_fwd_bwd(Id.data_ptr(), Td.data_ptr(), B, D, 1.0, mode, l0.data_ptr(), dI0.data_ptr(),
+                                        dT0.data_ptr(), ws0.data_ptr(), n0, st), "mc_clip_loss_fwd_bwd")
+    n = lib.mc_clip_loss_host_workspace_bytes(B, D, mode)
+    ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    outs = []
+    for _ in range(2):
+        dI, dT = torch.full_like(I, float("nan")).pin_memory(), torch.full_like(T, float("nan")).pin_memory()
+        loss = torch.zeros(1).pin_memory()
+        _lib.check(lib.mc_clip_loss_fwd_bwd_host(I.data_ptr(), T.data_ptr(), B, D, 1.0, mode, loss.data_ptr(),
+                                                 dI.data_ptr(), dT.data_ptr(), ws.data_ptr(), n, st),
+                   "mc_clip_loss_fwd_bwd_host")
+        outs.append((loss.clone(), dI.clone(), dT.clone()))
+    loss, dI, dT = outs[0]
+    assert torch.isfinite(dI).all() and torch.isfinite(dT).all()
+    assert abs(loss.item() - l0.item()) <= 1e-6 * abs(l0.item())
+    assert rel_err(dI, dI0.cpu()) < 1e-5 and rel_err(dT, dT0.cpu()) < 1e-5
+    assert torch.equal(outs[1][1], dI) and torch.equal(outs[1][2], dT) and torch.equal(outs[1][0], loss)
+
+
 def test_abi_error_codes():
     from mae_clip_b200 import _lib
     lib = _lib.lib()
