@@ -318,10 +318,16 @@ int mc_clip_loss_fwd_bwd_host(const float* I_host, const float* T_host, int B, i
   size_t ws_bytes = dws_bytes - (4 * emb + 256);
   size_t bytes = (size_t)B * D * 4;
   const bool want_grad = dI_host && dT_host;
-  // strips only where a strip still fills the machine (>= 8192 rows: 64 row blocks x column splits) and the tcgen05
-  // engine runs; small batches and the SIMT engine keep the single sweep
+  // two strips where a strip still fills the machine (>= 8192 rows: 64 row blocks x column splits) and the tcgen05
+  // engine runs; small batches and the SIMT engine keep the single sweep.  Measured at B = 32768 (tools/e2e_strips.py,
+  // profiles/r01i_e2e_strips.json): 1 strip 9.52 ms, 2: 9.20, 3: 9.81, 4: 9.31, 6: 9.21, 8: 10.5 - every strip adds a
+  // partly filled last wave and its own finalize, which eats the shorter exposed copy beyond two
   int n_strips = 1;
-  if (want_grad && eff_mode(mode, D) != MC_GEMM_SIMT_FP32 && B >= 16384) n_strips = B >= 32768 ? 4 : 2;
+  if (want_grad && eff_mode(mode, D) != MC_GEMM_SIMT_FP32 && B >= 16384) n_strips = 2;
+  if (const char* e = getenv("MAE_CLIP_HOST_STRIPS")) {  // A/B switch (1 = the single sweep + one copy at the end)
+    const int v = atoi(e);
+    if (want_grad && v >= 1 && v <= 8 && eff_mode(mode, D) != MC_GEMM_SIMT_FP32) n_strips = v;
+  }
   HostCopyCtx ctx = {};
   ctx.st = st; ctx.D = D; ctx.want_grad = want_grad;
   ctx.loss_dev = loss; ctx.gI = gI; ctx.gT = gT;

@@ -160,7 +160,7 @@ def test_loss_host_buffer_entry_point():
 
 @pytest.mark.parametrize("B", [16384, 16500, 32768])
 def test_loss_host_entry_strips_match_single_sweep(B):
-    """From B = 16384 the host-buffer entry runs the gradient sweep in row strips (2, 4 at 32768) and copies a strip
+    """From B = 16384 the host-buffer entry runs the gradient sweep in two row strips and copies a strip
     back while the next is swept: same loss and gradients as the device-resident single sweep, ragged last strip
     included, and identical on a second call (events / copy stream reused correctly)."""
     from mae_clip_b200 import _lib
