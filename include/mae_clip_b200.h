@@ -170,7 +170,10 @@ int mc_clip_loss_fwd_bwd(const float* I, const float* T, int B, int D, float tau
                          void* stream);
 /* Same through HOST buffers (pinned or pageable): copies in, computes, copies loss/grads out
  * and synchronises the stream.  `dws`/`dws_bytes` is DEVICE scratch of at least
- * mc_clip_loss_host_workspace_bytes(). */
+ * mc_clip_loss_host_workspace_bytes().  From B = 16384 (tcgen05 engines) the gradient sweep runs
+ * as two row strips and a per-device copy stream returns a finished strip while the next one is
+ * swept (environment MAE_CLIP_HOST_STRIPS=1..8 overrides the strip count; 1 = single sweep);
+ * when the call returns nothing of it is in flight on either stream. */
 size_t mc_clip_loss_host_workspace_bytes(int B, int D, int mode);
 int mc_clip_loss_fwd_bwd_host(const float* I_host, const float* T_host, int B, int D, float tau,
                               int mode, float* loss_host, float* dI_host, float* dT_host,
