@@ -147,9 +147,11 @@ def test_head_leading_dims_and_nograd():
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (24, 256, 160), (1000, 256, 2048), (256, 2048, 1000), (1, 256, 768),
-                                   (300, 100, 72)])
+                                   (300, 100, 72), (2500, 2048, 256), (20000, 640, 200), (19000, 512, 128)])
 def test_tc_gemm_entry_point(M, N, K):
-    """mc_tc_gemm: the fp16 hi/lo x3 tcgen05 GEMM the heads are built from, against fp64 matmul."""
+    """mc_tc_gemm: the fp16 hi/lo x3 tcgen05 GEMM the heads are built from, against fp64 matmul.  The last three
+    shapes (short K, no split-K, >= 4 column tiles) are the ones the A-resident form takes under
+    MAE_CLIP_GEMM_ARES=1."""
     from mae_clip_b200 import _lib
     from mae_clip_b200._lib import check, cur_stream, ptr
     lib = _lib.lib()
