@@ -220,195 +220,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   if (warp == 1) tmem_dealloc_1cta(tmem_base, 256);
 }
 
-// ------------------------------------------------------------------------------------------------
-// A-resident form for short K (K <= 256, no split-K): a job is one 128-row block of A times a GROUP of `group`
-// consecutive column tiles.  The A chunks (hi + lo, 32 KB each) are loaded once per job into their own four slots and
-// reused by every column tile of the group; only the B chunks stream through the ring.  The plain kernel pulls
-// 256 KB from L2 per 128 x 128 tile at K = 256 (dx = dp Wp: 1 GB over the 4096 tiles, 7.4 TB/s - the L2 -> shared
-// memory fabric sets its time, profiles/r01_ncu_summary.md section 8); here a tile costs 128 KB + 128 KB / group.
-// Same roles, same TMEM double buffer, same epilogue arithmetic.
-// ------------------------------------------------------------------------------------------------
-constexpr int kAresChunks = 4;                      // K <= 256
-constexpr int kASlot = 2 * kChunk;                  // A hi + A lo of one 64-wide chunk
-constexpr int kBStage = 2 * kChunk;                 // B hi + B lo
-constexpr int kBStages = 3;
-constexpr int kAresOffB = kAresChunks * kASlot;
-constexpr int kAresOffBar = kAresOffB + kBStages * kBStage;
-constexpr int kAresSmem = kAresOffBar + 256 + 1024;
-enum AresBar { kAFull0 = 0, kAEmpty0 = 4, kBFull0 = 8, kBEmpty0 = 11, kATFull0 = 14, kATEmpty0 = 16, kAresNumBars = 18 };
-
-template <int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_ares_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                 const GemmParams p, const int group) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* const sbase = smem_raw + (base - raw);
-  const uint32_t bar0 = base + kAresOffBar;
-  auto bar = [&](int i) -> uint32_t { return bar0 + 8u * i; };
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(sbase + kAresOffBar + 8 * kAresNumBars);
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int n_groups = (p.tiles_n + group - 1) / group;
-  const int njobs = p.tiles_m * n_groups;
-  const int nch = p.chunks_total;  // 1..4
-
-  if (threadIdx.x == 0) {
-    for (int c = 0; c < kAresChunks; ++c) { mbar_init(bar(kAFull0 + c), 1); mbar_init(bar(kAEmpty0 + c), 1); }
-    for (int s = 0; s < kBStages; ++s) { mbar_init(bar(kBFull0 + s), 1); mbar_init(bar(kBEmpty0 + s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar(kATFull0 + i), 1); mbar_init(bar(kATEmpty0 + i), 128); }
-    fence_mbar_init();
-    prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_b_hi); prefetch_tmap(&map_b_lo);
-  }
-  if (warp == 1) tmem_alloc_1cta(smem_u32(tmem_slot), 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // groups run fastest: CTAs side by side work on the same row block, whose A chunks they then share in L2
-  auto job_coords = [&](int job, int& tm, int& tn0, int& tn1) {
-    tm = job / n_groups;
-    tn0 = (job % n_groups) * group;
-    tn1 = min(tn0 + group, p.tiles_n);
-  };
-
-  if (warp == 0) {
-    if (elect_one()) {
-      uint32_t itb = 0, jj = 0;
-      for (int job = blockIdx.x; job < njobs; job += gridDim.x, ++jj) {
-        int tm, tn0, tn1;
-        job_coords(job, tm, tn0, tn1);
-        for (int tn = tn0; tn < tn1; ++tn) {
-          for (int c = 0; c < nch; ++c, ++itb) {
-            if (tn == tn0) {  // this job's A chunk c: its slot is free once the previous job's last tile has used it
-              mbar_wait(bar(kAEmpty0 + c), (jj & 1) ^ 1);
-              const uint32_t fa = bar(kAFull0 + c);
-              mbar_arrive_expect_tx(fa, kASlot);
-              tma_load_2d(base + c * kASlot, &map_a_hi, fa, c * 64, tm * 128);
-              tma_load_2d(base + c * kASlot + kChunk, &map_a_lo, fa, c * 64, tm * 128);
-            }
-            const uint32_t stage = itb % kBStages, par = (itb / kBStages) & 1;
-            mbar_wait(bar(kBEmpty0 + stage), par ^ 1);
-            const uint32_t fb = bar(kBFull0 + stage);
-            mbar_arrive_expect_tx(fb, kBStage);
-            const uint32_t sb = base + kAresOffB + stage * kBStage;
-            tma_load_2d(sb, &map_b_hi, fb, c * 64, tn * 128);
-            tma_load_2d(sb + kChunk, &map_b_lo, fb, c * 64, tn * 128);
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t idesc = idesc_f16(128, 128);
-      uint32_t itb = 0, tt = 0, jj = 0;
-      for (int job = blockIdx.x; job < njobs; job += gridDim.x, ++jj) {
-        int tm, tn0, tn1;
-        job_coords(job, tm, tn0, tn1);
-        for (int tn = tn0; tn < tn1; ++tn, ++tt) {
-          const uint32_t buf = tt & 1, use = tt >> 1;
-          mbar_wait(bar(kATEmpty0 + buf), (use & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t td = tmem_base + buf * 128;
-          for (int c = 0; c < nch; ++c, ++itb) {
-            if (tn == tn0) mbar_wait(bar(kAFull0 + c), jj & 1);
-            const uint32_t stage = itb % kBStages, par = (itb / kBStages) & 1;
-            mbar_wait(bar(kBFull0 + stage), par);
-            tc_fence_after();
-            const uint32_t sa = base + c * kASlot, sb = base + kAresOffB + stage * kBStage;
-            const uint64_t ah = smem_desc_sw128(sa), al = smem_desc_sw128(sa + kChunk);
-            const uint64_t bh = smem_desc_sw128(sb), bl = smem_desc_sw128(sb + kChunk);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
-              mma_f16_1cta(td, desc_advance_k(ah, ks), desc_advance_k(bh, ks), idesc, acc);
-              mma_f16_1cta(td, desc_advance_k(ah, ks), desc_advance_k(bl, ks), idesc, 1u);
-              mma_f16_1cta(td, desc_advance_k(al, ks), desc_advance_k(bh, ks), idesc, 1u);
-            }
-            mma_commit_1cta(bar(kBEmpty0 + stage));
-            if (tn == tn1 - 1) mma_commit_1cta(bar(kAEmpty0 + c));  // last use of this job's A chunk c
-          }
-          mma_commit_1cta(bar(kATFull0 + buf));
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    const int quarter = warp & 3;
-    const uint32_t lane_field = (uint32_t)(quarter * 32) << 16;
-    const float scale = p.scale_a[1] * p.scale_b[1];
-    uint32_t tt = 0;
-    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
-      int tm, tn0, tn1;
-      job_coords(job, tm, tn0, tn1);
-      const int row = tm * 128 + quarter * 32 + lane;
-      float* crow = p.C + (size_t)row * p.ldc;
-      float* grow = (EPI == kEpiGelu && p.gelu_out) ? p.gelu_out + (size_t)row * p.ldc : nullptr;
-      for (int tn = tn0; tn < tn1; ++tn, ++tt) {
-        const uint32_t buf = tt & 1, use = tt >> 1;
-        mbar_wait(bar(kATFull0 + buf), use & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < 128; cc += 32) {
-          float v[32];
-          tmem_ld32(tmem_base + lane_field + buf * 128 + cc, v);
-          tmem_ld_wait();
-          if (cc == 96) {  // all four reads of this tile are done: release the buffer
-            tc_fence_before();
-            mbar_arrive_local(bar(kATEmpty0 + buf));
-          }
-          const int col0 = tn * 128 + cc;
-          if (row >= p.M || col0 >= p.N) continue;
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            v[e] *= scale;
-            if (p.bias && col0 + e < p.N) v[e] += p.bias[col0 + e];
-          }
-          if (p.vec_ok && col0 + 32 <= p.N) {
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              *reinterpret_cast<float4*>(crow + col0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-              if (EPI == kEpiGelu && grow)
-                *reinterpret_cast<float4*>(grow + col0 + e) =
-                    make_float4(gelu_erf(v[e]), gelu_erf(v[e + 1]), gelu_erf(v[e + 2]), gelu_erf(v[e + 3]));
-            }
-          } else {
-            for (int e = 0; e < 32; ++e) {
-              if (col0 + e < p.N) {
-                crow[col0 + e] = v[e];
-                if (EPI == kEpiGelu && grow) grow[col0 + e] = gelu_erf(v[e]);
-              }
-            }
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc_1cta(tmem_base, 256);
-}
-
-// column tiles per job of the A-resident form: whole waves of the persistent grid first, then the longest group
-// (cost model: waves x (group + 1) - a job loads A once and B `group` times)
-static int choose_ares_group(int tiles_m, int tiles_n) {
-  const int sms = num_sms();
-  int best = 1;
-  long best_cost = -1;
-  for (int g = 1; g <= tiles_n; ++g) {
-    const int n_groups = (tiles_n + g - 1) / g;
-    if ((tiles_n % g) != 0 && g != tiles_n) continue;  // equal groups only
-    const long jobs = (long)tiles_m * n_groups;
-    const long waves = (jobs + sms - 1) / sms;
-    const long cost = waves * (g + 1);
-    if (best_cost < 0 || cost < best_cost || (cost == best_cost && g > best)) { best_cost = cost; best = g; }
-  }
-  return best;
-}
-
 // C[m][n] = sum_ks part[ks][m][n] (+ bias[n])
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int ksplit, int M, int N,
                                                             const float* __restrict__ bias, float* __restrict__ C,
@@ -764,36 +575,10 @@ int gemm(const Planes& A, const Planes& B, int M, int N, int K, const GemmOut& o
     p.ldc = out.ldc;
     p.vec_ok = (out.ldc % 4 == 0) && aligned(out.C, 16) && (!out.gelu_out || aligned(out.gelu_out, 16));
   }
-  // A-resident form (short K, several column tiles per row block): MAE_CLIP_GEMM_ARES=1 switches it on (off by
-  // default until its timings are in profiles/)
-  p.coalesce = 0;
-  static const bool ares_on = getenv("MAE_CLIP_GEMM_ARES") != nullptr && getenv("MAE_CLIP_GEMM_ARES")[0] == '1';
-  // from four column tiles per row block: with two, the A reload at every job boundary (the slots are single-buffered)
-  // costs what the halved A traffic saves
-  if (ares_on && p.ksplit == 1 && p.chunks_total <= kAresChunks && p.tiles_n >= 4) {
-    int group = choose_ares_group(p.tiles_m, p.tiles_n);
-    if (const char* e = getenv("MAE_CLIP_GEMM_ARES_GROUP")) {  // A/B override
-      const int v = atoi(e);
-      if (v >= 1 && v <= p.tiles_n) group = v;
-    }
-    const int n_groups = (p.tiles_n + group - 1) / group;
-    const long jobs = (long)p.tiles_m * n_groups;
-    const int agrid = jobs < num_sms() ? (int)jobs : num_sms();
-    if (epilogue == kEpiGelu) {
-      static std::atomic<unsigned long long> done{0};
-      MC_CUDA(ensure_dynamic_smem(gemm_ares_kernel<kEpiGelu>, kAresSmem, done));
-      gemm_ares_kernel<kEpiGelu><<<agrid, kThreads, kAresSmem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p, group);
-    } else {
-      static std::atomic<unsigned long long> done{0};
-      MC_CUDA(ensure_dynamic_smem(gemm_ares_kernel<kEpiPlain>, kAresSmem, done));
-      gemm_ares_kernel<kEpiPlain><<<agrid, kThreads, kAresSmem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p, group);
-    }
-    MC_LAUNCH_CHECK();
-    return MC_OK;
-  }
-  // MAE_CLIP_GEMM_COALESCE=1: epilogue stores through the per-warp transpose (A/B switch)
-  static const bool coalesce_on = getenv("MAE_CLIP_GEMM_COALESCE") != nullptr && getenv("MAE_CLIP_GEMM_COALESCE")[0] == '1';
-  p.coalesce = coalesce_on ? 1 : 0;
+  // epilogue stores through the per-warp transpose (image head fwd+bwd 0.955 -> 0.893 ms, profiles/r01j_head_coalesce_ab.log);
+  // MAE_CLIP_GEMM_COALESCE=0 restores the per-lane row stores (A/B switch)
+  static const bool coalesce_off = getenv("MAE_CLIP_GEMM_COALESCE") != nullptr && getenv("MAE_CLIP_GEMM_COALESCE")[0] == '0';
+  p.coalesce = coalesce_off ? 0 : 1;
   const int njobs = p.tiles_m * p.tiles_n * p.ksplit;
   const int grid = njobs < num_sms() ? njobs : num_sms();
   if (epilogue == kEpiGelu) {

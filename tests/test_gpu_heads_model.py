@@ -150,8 +150,8 @@ def test_head_leading_dims_and_nograd():
                                    (300, 100, 72), (2500, 2048, 256), (20000, 640, 200), (19000, 512, 128)])
 def test_tc_gemm_entry_point(M, N, K):
     """mc_tc_gemm: the fp16 hi/lo x3 tcgen05 GEMM the heads are built from, against fp64 matmul.  The last three
-    shapes (short K, no split-K, >= 4 column tiles) are the ones the A-resident form takes under
-    MAE_CLIP_GEMM_ARES=1."""
+    shapes are the short-K, no-split-K, many-column-tile case of `dx = dp Wp` (whole and ragged row blocks: the
+    coalesced epilogue and its per-lane fallback)."""
     from mae_clip_b200 import _lib
     from mae_clip_b200._lib import check, cur_stream, ptr
     lib = _lib.lib()

@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of a head-GEMM switch: correctness with the switch on, then image-head timings off / on.
+# A/B of a head-GEMM environment switch: correctness with the switch at 1, then image-head timings at 0 / 1.
 # Usage (GPU box): bash tools/head_gemm_ab.sh MAE_CLIP_GEMM_COALESCE > gpurun_out/head_gemm_ab.log 2>&1
 set -u
 VAR=${1:-MAE_CLIP_GEMM_COALESCE}
