@@ -184,13 +184,16 @@ int mc_clip_loss_fwd_bwd_host(const float* I_host, const float* T_host, int B, i
  * exchange region, ships its 64-byte CUDA IPC handle to the other local ranks (any transport;
  * mae_clip_b200/dist.py uses torch.distributed) and maps theirs.  The kernels then load / store
  * peer memory directly over NVLink / NVSwitch:
- *   mc_peer_barrier  all ranks: epoch = ++*epoch_counter (a private device word, zero at
- *                    creation; every rank issues the same sequence of barriers, so no launch
- *                    argument depends on the step and the step can be graph-captured);
- *                    flag[rank] := epoch in every peer's flag array (MC_PEER_MAX_WORLD
- *                    zero-initialised words at flag_ptrs_host[q]), then wait until every peer
- *                    wrote the same epoch here.  A peer that does not arrive within timeout_s
- *                    (<= 0: 20 s) traps the kernel.
+ *   mc_peer_barrier  all ranks: epoch = ++epoch_counter[0] (epoch_counter: TWO private device
+ *                    words {epoch, error}, zero at creation; every rank issues the same
+ *                    sequence of barriers, so no launch argument depends on the step and the
+ *                    step can be graph-captured); flag[rank] := epoch in every peer's flag
+ *                    array (MC_PEER_MAX_WORLD zero-initialised words at flag_ptrs_host[q]),
+ *                    then wait until every peer wrote the same epoch here.  A peer that does
+ *                    not arrive within timeout_s (<= 0: 600 s, the order of a process-group
+ *                    timeout) makes the kernel record 1 + that peer's rank in epoch_counter[1]
+ *                    and return: the context stays usable (no trap), the data of the step is
+ *                    invalid, and the host decides (mae_clip_b200/peer.py: PeerExchange.check()).
  *   mc_peer_publish  dst[q][dst_offset + kk*dst_stride + i] = src[kk*src_stride + i] (32-bit
  *                    words, kk < k, i < n) for every peer q < world.
  * mc_peer_alloc zero-fills the region and synchronises the device (set-up time, not the hot path).

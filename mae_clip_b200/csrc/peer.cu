@@ -38,8 +38,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // "rank `rank` reached epoch e" and waits until rank q said the same here.  The epoch lives in
 // device memory (one private word per rank, bumped by the kernel itself: every rank runs the same
 // sequence of barriers), so a launch carries no step-dependent argument and the whole step can be
-// captured in a CUDA graph.  Epochs only grow, so the arrays never need a reset; a peer that
-// never arrives trips the timeout and traps (the caller sees a CUDA error instead of a hung GPU).
+// captured in a CUDA graph.  Epochs only grow, so the arrays never need a reset.  A peer that never
+// arrives trips the timeout: the kernel records 1 + (the rank it was waiting for) in epoch_counter[1]
+// and RETURNS - no __trap, which would poison the CUDA context with a sticky error; the host reads the
+// word (PeerExchange.check() / the NaN loss of PeerStep) and can tear the exchange down and go on over NCCL.
 __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerWords flags, int rank, int world,
                                                           uint32_t* __restrict__ epoch_counter,
                                                           unsigned long long timeout_ns) {
@@ -58,7 +60,8 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerWords flags, int r
     while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
       if (globaltimer_ns() - t0 > timeout_ns) {
         printf("mae_clip_b200: peer barrier timed out (rank %d waiting for rank %d, epoch %u)\n", rank, q, epoch);
-        __trap();
+        atomicMax(epoch_counter + 1, (uint32_t)(q + 1));
+        break;
       }
       __nanosleep(64);
     }
@@ -151,7 +154,7 @@ int mc_peer_barrier(void* const* flag_ptrs_host, int rank, int world, unsigned i
   if (rc) return rc;
   MC_REQUIRE(rank >= 0 && rank < world && epoch_counter, MC_ERR_BAD_ARG,
              "peer_barrier: rank %d outside world %d or null epoch counter", rank, world);
-  if (timeout_s <= 0.0) timeout_s = 20.0;
+  if (timeout_s <= 0.0) timeout_s = 600.0;  // the order of a process-group timeout, not of a step
   peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(w, rank, world, epoch_counter,
                                                                        (unsigned long long)(timeout_s * 1e9));
   MC_LAUNCH_CHECK();

@@ -64,19 +64,27 @@ class CudaStripEngine:
                 planes = torch.empty(nb, device=dev, dtype=torch.uint8)
                 check(lib().mc_clip_prepare(ptr(I_all), ptr(T_all), B, B, D, 0, self.mode, ptr(planes),
                                             cur_stream()), "mc_clip_prepare")
-            ws = self._ws(b, B, D, dev)
+                ws, own_ws = self._ws(b, B, D, dev), None
+            else:
+                # The fp32 FMA engine (mode simt_fp32, or any D the tcgen05 engine does not cover) KEEPS its materialised
+                # S / S^T / Z strips in the workspace from this sweep to the gradient sweep: that state must survive
+                # whatever runs between forward and backward (another loss, a head, an MAE op all use the shared
+                # scratch cache), so it lives in a tensor of its own that travels with the autograd context.
+                own_ws = torch.empty(lib().mc_clip_loss_workspace_bytes(b, B, D, self.mode), device=dev, dtype=torch.uint8)
+                ws = own_ws
             nf = lib().mc_clip_tile_flags_bytes(b, B, D, self.mode) if self.sparse else 0
             flags_raw = torch.empty(nf, device=dev, dtype=torch.uint8) if nf else None
             check(lib().mc_clip_stats(ptr(I_all), ptr(T_all), ptr(planes), b, B, D, row_offset,
                                       float(tau), self.mode, ptr(out[0]), ptr(out[1]), ptr(out[2]),
                                       ptr(out[3]), ptr(flags_raw), ptr(ws), ws.numel(), cur_stream()), "mc_clip_stats")
-        return out[:3], [planes, out[3], flags_raw]
+        return out[:3], {"planes": planes, "ps": out[3], "flags_raw": flags_raw, "flags": None, "flags_done": False,
+                         "strips": own_ws}
 
     def _final_flags(self, ctx, b, B, row_offset):
         """Gather every rank's raw tile flags and OR in the transposed relation (first call after the sweep)."""
-        flags_raw = ctx[2]
-        if flags_raw is None or flags_raw.dtype == torch.bool:
-            return None if flags_raw is None else ctx[3]
+        flags_raw = ctx["flags_raw"]
+        if flags_raw is None or ctx["flags_done"]:
+            return ctx["flags"]
         world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
         if world > 1:
             allf = torch.empty(world * flags_raw.numel(), device=flags_raw.device, dtype=torch.uint8)
@@ -85,20 +93,19 @@ class CudaStripEngine:
             allf = flags_raw
         final = torch.empty_like(flags_raw)
         check(lib().mc_clip_flags_finalize(ptr(allf), B, b, row_offset, ptr(final), cur_stream()), "mc_clip_flags_finalize")
-        ctx[2] = torch.empty(0, dtype=torch.bool)   # marks "finalised"
-        ctx.append(final)
+        ctx["flags"], ctx["flags_done"], ctx["flags_raw"] = final, True, None
         return final
 
     def rowloss(self, I_all, T_all, planes, b, row_offset, tau, stats_all):
         ctx = planes
-        planes, ps_loc = ctx[0], ctx[1]
+        planes, ps_loc = ctx["planes"], ctx["ps"]
         B, D = I_all.shape
         dev = I_all.device
         out = torch.empty(2, b, device=dev, dtype=torch.float32)
         part = torch.empty(1, device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             flags = self._final_flags(ctx, b, B, row_offset)
-            ws = self._ws(b, B, D, dev)
+            ws = ctx["strips"] if ctx["strips"] is not None else self._ws(b, B, D, dev)
             check(lib().mc_clip_rowloss(ptr(I_all), ptr(T_all), ptr(planes), b, B, D, row_offset,
                                         float(tau), self.mode, ptr(stats_all[0]), ptr(stats_all[1]),
                                         ptr(stats_all[2]), ptr(ps_loc), ptr(out[0]), ptr(out[1]), ptr(part), ptr(flags),
@@ -107,15 +114,17 @@ class CudaStripEngine:
 
     def bwd(self, I_all, T_all, planes, b, row_offset, tau, stats_all, gq_all, grad_loss):
         ctx = planes
-        planes = ctx[0]
-        flags = ctx[3] if len(ctx) > 3 else None
+        planes = ctx["planes"]
+        flags = ctx["flags"]
         B, D = I_all.shape
         dev = I_all.device
         dI = torch.empty(b, D, device=dev, dtype=torch.float32)
         dT = torch.empty(b, D, device=dev, dtype=torch.float32)
         gl = grad_loss.reshape(1).to(torch.float32).contiguous()
         with torch.cuda.device(dev):
-            ws = self._ws(b, B, D, dev)
+            # the fp32 FMA engine's gradient sweep overwrites the strips with the gradient weights: it works on a copy,
+            # so that a second backward over the same graph (retain_graph=True) still finds S / S^T / Z
+            ws = ctx["strips"].clone() if ctx["strips"] is not None else self._ws(b, B, D, dev)
             check(lib().mc_clip_bwd(ptr(I_all), ptr(T_all), ptr(planes), b, B, D, row_offset,
                                     float(tau), self.mode, ptr(stats_all[0]), ptr(stats_all[1]),
                                     ptr(stats_all[2]), ptr(gq_all[0]), ptr(gq_all[1]), ptr(gl), ptr(dI),
@@ -268,10 +277,12 @@ class PeerStep:
             ex.barrier()
             # out of the region: backward (and a second forward before it) never touch peer memory
             vecs = torch.empty(5, B, **f32)
-            parts = torch.empty(world, **f32)
+            parts = torch.empty(18, **f32)   # 16 partial slots + the barrier's {epoch, error} words, one copy
             ex.copy_out(ex.OFF_VECS, 5, B, ex.vec_stride, vecs, B)
-            ex.copy_out(ex.OFF_PART_SLOTS, 1, world, 0, parts, 0)
-            loss = parts.sum()
+            ex.copy_out(ex.OFF_PART_SLOTS, 1, 18, 0, parts, 0)
+            # a barrier that gave up on a peer (peer.py, "Skew between ranks") makes the step's loss NaN instead of
+            # silently wrong; no host synchronisation here - PeerExchange.check() names the missing rank
+            loss = torch.where(parts.view(torch.int32)[17] != 0, parts.new_full((), float("nan")), parts[:world].sum())
             mark()
         return loss, (planes, vecs, flags)
 

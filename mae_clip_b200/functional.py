@@ -106,7 +106,9 @@ class _ClipLoss(torch.autograd.Function):
             raise ValueError("image/text embeddings must both be (B, D)")
         I, T = _f32c(image_emb), _f32c(text_emb)
         B, D = I.shape
-        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        # needs_input_grad mirrors requires_grad even under torch.no_grad(): eval / inference must not pay for the
+        # gradient sweep (main.py:115 runs valid_epoch under no_grad)
+        need = torch.is_grad_enabled() and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         loss = torch.empty((), device=I.device, dtype=torch.float32)
         dI = torch.empty_like(I) if need else None
         dT = torch.empty_like(T) if need else None
@@ -148,7 +150,7 @@ class _ProjHead(torch.autograd.Function):
         wp, bp, wf, bf, g, bt = (_f32c(t) for t in (w_proj, b_proj, w_fc, b_fc, gamma, beta))
         if keep_mask is not None:
             keep_mask = keep_mask.reshape(B, P).to(torch.uint8).contiguous()
-        need = any(ctx.needs_input_grad[:7])
+        need = torch.is_grad_enabled() and any(ctx.needs_input_grad[:7])   # no backward state under no_grad
         dev = x2.device
         out = torch.empty(B, P, device=dev, dtype=torch.float32)
         projected = torch.empty(B, P, device=dev, dtype=torch.float32)
@@ -239,6 +241,8 @@ class _RandomMasking(torch.autograd.Function):
     def backward(ctx, g_masked, _gm, _gr, _gk):
         mask, ids_restore = ctx.saved_tensors
         N, L, Dm, len_keep = ctx.cfg
+        if len_keep == 0 or N == 0:   # nothing was kept (mask_ratio 1.0): no token receives a gradient
+            return torch.zeros(N, L, Dm, device=g_masked.device, dtype=g_masked.dtype), None, None
         g = g_masked.contiguous()
         gx = torch.empty(N, L, Dm, device=g.device, dtype=g.dtype)
         with torch.cuda.device(g.device):

@@ -14,8 +14,9 @@ collective-library call per step:
 The reference is single-process (nothing under /root/reference to cite); the result is, by
 definition, the reference loss (``CLIP.py:34-43``) on the concatenated batch.
 
-Region layout (bytes): [0, 64) barrier flags | 128 private barrier epoch | [256, 320) amax slots | [512, 576) loss-partial
-slots | 768 local amax, 772 local loss partial, 784 push scratch (2 words) | 1024.. five length-B vectors
+Region layout (bytes): [0, 64) barrier flags | [256, 320) amax slots | [512, 576) loss-partial slots | 576 private
+barrier epoch, 580 barrier error word (0 = fine, 1 + q = "rank q never arrived within the timeout"; next to the
+partials so that one copy brings both out) | 768 local amax, 772 local loss partial, 784 push scratch (2 words) | 1024.. five length-B vectors
 (r, c, rz, g, q) | the [B/128][B/128]-byte tile-flag bitmap | then two (B, D) fp32 images of the global batch (image / text embeddings): in
 "pull" mode each rank fills only its own rows and peers read them from there; in "push" mode every
 rank stores its rows into all ranks' images and the staging reads locally.
@@ -26,6 +27,14 @@ Why the region can be reused every step without extra fences (B_k = k-th barrier
   and copied out of the region right there (backward never touches peer memory).  A rank can only
   write step n+1's data after passing B_1(n+1) / B_2(n+1), which every peer enters only after its
   own stream finished reading step n's.
+
+Skew between ranks.  The barrier spins ON THE GPU until every peer's stream reaches the same barrier, at most
+``MAE_CLIP_PEER_TIMEOUT_S`` seconds (default 600, the order of a process-group timeout: rank-0-only validation or
+checkpointing, a data-loader stall or a first-step autotune on one rank are routine).  Rank-asymmetric GPU work that
+itself waits for a peer (an NCCL collective issued on the same stream by only some ranks) would still deadlock the
+step, as it would with NCCL.  On a timeout the kernel does NOT trap (a trap is a sticky context error): it records
+the missing rank, the step's loss comes out NaN, ``PeerExchange.check()`` raises ``PeerTimeout`` - after which the
+exchange must be closed (``close_all()``) and the job can continue over ``transport="nccl"``.
 """
 from __future__ import annotations
 
@@ -51,11 +60,23 @@ class PeerUnavailable(RuntimeError):
     NCCL transport together."""
 
 
+class PeerTimeout(RuntimeError):
+    """A peer did not reach a barrier of the exchange within the timeout (see the module docstring)."""
+
+
+def default_timeout_s() -> float:
+    try:
+        return float(os.environ.get("MAE_CLIP_PEER_TIMEOUT_S", "600"))
+    except ValueError:
+        return 600.0
+
+
 class PeerExchange:
     """The mapped exchange regions of every rank of ``group`` for a (b, D) shard shape."""
 
-    OFF_FLAGS, OFF_EPOCH, OFF_AMAX_SLOTS, OFF_PART_SLOTS, OFF_AMAX_LOCAL, OFF_PART_LOCAL, OFF_VECS = \
-        0, 128, 256, 512, 768, 772, 1024
+    OFF_FLAGS, OFF_AMAX_SLOTS, OFF_PART_SLOTS, OFF_EPOCH, OFF_AMAX_LOCAL, OFF_PART_LOCAL, OFF_VECS = \
+        0, 256, 512, 576, 768, 772, 1024
+    OFF_ERROR = OFF_EPOCH + 4  # second word of the barrier's private block: 1 + rank that never arrived, 0 = fine
     OFF_PUSH_SCRATCH = 784  # {amax accumulator, blocks-done counter} of mc_clip_push_shards
 
     def __init__(self, b: int, D: int, group=None, device=None):
@@ -151,9 +172,20 @@ class PeerExchange:
         return self.local(self.OFF_VECS + 4 * k * self.vec_stride)
 
     # ---- primitives ---------------------------------------------------------------------------
-    def barrier(self, timeout_s: float = 20.0):
+    def barrier(self, timeout_s: float | None = None):
         check(lib().mc_peer_barrier(self.table(self.OFF_FLAGS), self.rank, self.world, self.local(self.OFF_EPOCH),
-                                    float(timeout_s), cur_stream()), "mc_peer_barrier")
+                                    float(default_timeout_s() if timeout_s is None else timeout_s), cur_stream()),
+              "mc_peer_barrier")
+
+    def check(self):
+        """Synchronise and raise ``PeerTimeout`` if a barrier of this exchange gave up on a peer."""
+        w = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.copy_out(self.OFF_ERROR, 1, 1, 0, w, 0)
+        v = int(w.item())
+        if v:
+            raise PeerTimeout(f"rank {self.rank}: peer rank {v - 1} did not reach a barrier within the timeout; close the "
+                              "exchange (peer.close_all()) and continue with transport='nccl'")
 
     def publish(self, src, k: int, n: int, src_stride: int, dst_offset_bytes: int, dst_stride: int, dst_index: int):
         """Push k vectors of n words from local ``src`` to [dst_offset + kk*dst_stride + dst_index + i] of every rank."""

@@ -99,7 +99,9 @@ class AdamW(torch.optim.Optimizer):
                 s = int(st["step"])
                 if step is None:
                     step = s
-                elif step != s:  # parameters that joined later: flush what we have and continue at their count
+                elif step != s or p.device != ps[0].device:
+                    # parameters that joined later (another step count) or live on another device: flush what we have
+                    # (one launch covers one device and one bias correction) and continue with theirs
                     self._launch(group, step, ps, gs, ms, vs, grad_scale)
                     ps, gs, ms, vs, step = [], [], [], [], s
                 ps.append(p)

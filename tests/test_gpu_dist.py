@@ -121,3 +121,28 @@ def test_peer_step_world1_matches_fused_path(exchange_mode):
         ex.close()
     finally:
         dist.destroy_process_group()
+
+
+def test_peer_barrier_timeout_is_recoverable():
+    """A peer that never arrives must not poison the CUDA context (round-1 advisor finding): the barrier kernel gives
+    up after `timeout_s`, records 1 + the missing rank in the second word of its private block and returns.  Two
+    regions of ONE process stand in for two ranks; only "rank 0" ever enters the barrier."""
+    import ctypes as C
+    from mae_clip_b200 import _lib
+    lib = _lib.lib()
+    a, b, h = C.c_void_p(), C.c_void_p(), C.create_string_buffer(64)
+    _lib.check(lib.mc_peer_alloc(4096, C.byref(a), h))
+    _lib.check(lib.mc_peer_alloc(4096, C.byref(b), h))
+    try:
+        tab = (C.c_void_p * 2)(a.value, b.value)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.mc_peer_barrier(tab, 0, 2, C.c_void_p(a.value + 576), 0.05, st))
+        torch.cuda.synchronize()                                   # no trap: the context is alive
+        words = torch.zeros(2, dtype=torch.int32, device="cuda")
+        out = (C.c_void_p * 1)(words.data_ptr())
+        _lib.check(lib.mc_peer_publish(C.c_void_p(a.value + 576), 1, 2, 0, out, 0, 0, 1, st))
+        assert words.tolist() == [1, 2]                            # epoch 1, error = 1 + rank 1
+        assert torch.ones(8, device="cuda").sum().item() == 8.0   # and ordinary work still runs
+    finally:
+        lib.mc_peer_free(a)
+        lib.mc_peer_free(b)

@@ -393,3 +393,179 @@ def test_tile_flags_are_a_superset_of_the_exact_relevance(scale, tau):
     assert bool((flags.bool() | ~exact).all()), "a tile with soft-target mass was not flagged"
     if scale == 1.0:
         assert flags.sum().item() <= exact.sum().item() + 4   # and the bound is tight in the hard regime
+
+
+# ------------------------------------------------------------------ parity AT the benchmarked size (BASELINE config 4)
+def _phases_sharded(I, T, tau, mode, shard_rows):
+    """The row-sharded form of the step (what the ranks of a multi-GPU job run, mae_clip_b200/dist.py) back to back on
+    one GPU: every shard of `shard_rows` rows runs its own statistics / row-loss / gradient sweeps with a row offset,
+    the length-B vectors and the tile-flag bitmap are assembled in between exactly as the exchange steps do."""
+    from mae_clip_b200 import _lib
+    from mae_clip_b200._lib import check, cur_stream, ptr
+    lib = _lib.lib()
+    md = _lib.GEMM_MODES[mode]
+    B, D = I.shape
+    b = shard_rows
+    assert B % b == 0 and b % 128 == 0
+    W = B // b
+    dev = I.device
+    s = cur_stream()
+    planes = torch.empty(lib.mc_clip_planes_bytes(B, D, md), dtype=torch.uint8, device=dev)
+    ws = torch.empty(lib.mc_clip_loss_workspace_bytes(b, B, D, md), dtype=torch.uint8, device=dev)
+    nf = lib.mc_clip_tile_flags_bytes(b, B, D, md)
+    st4 = torch.empty(4, B, device=dev)
+    gq = torch.empty(2, B, device=dev)
+    parts = torch.empty(W, device=dev)
+    raw_all = torch.empty(W * nf, dtype=torch.uint8, device=dev)
+    fin = torch.empty(W, nf, dtype=torch.uint8, device=dev)
+    dI, dT = torch.empty_like(I), torch.empty_like(T)
+    check(lib.mc_clip_prepare(ptr(I), ptr(T), B, B, D, 0, md, ptr(planes), s))
+    for k in range(W):
+        o = k * b
+        check(lib.mc_clip_stats(ptr(I), ptr(T), ptr(planes), b, B, D, o, tau, md, ptr(st4[0, o:]), ptr(st4[1, o:]),
+                                ptr(st4[2, o:]), ptr(st4[3, o:]), ptr(raw_all[k * nf:]), ptr(ws), ws.numel(), s))
+    for k in range(W):
+        check(lib.mc_clip_flags_finalize(ptr(raw_all), B, b, k * b, ptr(fin[k]), s))
+    for k in range(W):
+        o = k * b
+        check(lib.mc_clip_rowloss(ptr(I), ptr(T), ptr(planes), b, B, D, o, tau, md, ptr(st4[0]), ptr(st4[1]), ptr(st4[2]),
+                                  ptr(st4[3, o:]), ptr(gq[0, o:]), ptr(gq[1, o:]), ptr(parts[k:]), ptr(fin[k]), ptr(ws),
+                                  ws.numel(), s))
+    for k in range(W):
+        o = k * b
+        check(lib.mc_clip_bwd(ptr(I), ptr(T), ptr(planes), b, B, D, o, tau, md, ptr(st4[0]), ptr(st4[1]), ptr(st4[2]),
+                              ptr(gq[0]), ptr(gq[1]), None, ptr(dI[o:]), ptr(dT[o:]), ptr(fin[k]), ptr(ws), ws.numel(), s))
+    torch.cuda.synchronize()
+    return parts.sum().item(), dI, dT, fin.reshape(B // 128, -1)
+
+
+_C4_CACHE = {}
+
+
+def _c4_batch_and_oracle(B, scale):
+    """bench.py's C4 batch (4096-row blocks of LayerNorm'd gaussian rows, seeds 1000 + k / 5000 + k) and its fp64
+    blockwise oracle (``oracle/loss_blockwise.py``, plain torch float64 ON THE GPU as the checker - never the product)."""
+    from oracle import loss_blockwise
+    key = (B, scale)
+    if key not in _C4_CACHE:
+        _C4_CACHE.clear()   # one batch resident at a time
+        blk = 4096
+        I = torch.cat([loss_ref.make_embeddings(blk, 256, seed=1000 + k, scale=scale) for k in range(B // blk)]).cuda()
+        T = torch.cat([loss_ref.make_embeddings(blk, 256, seed=5000 + k, scale=scale) for k in range(B // blk)]).cuda()
+        ref = loss_blockwise.clip_loss_blockwise_f64(I, T, 1.0, rows=1024)
+        _C4_CACHE[key] = (I, T, ref)
+    return _C4_CACHE[key]
+
+
+@pytest.mark.parametrize("variant", ["fused_flags", "dense", "shards4096_flags", "host_entry"])
+@pytest.mark.parametrize("B", [8192, 32768])
+def test_loss_c4_size_vs_fp64_blockwise(B, variant):
+    """The benchmarked path - B = 32768 (and 8192), D = 256, LayerNorm-scale rows (tile-flag density 1/256), probe +
+    exact-Z statistics, 4096-row shards, the strip-wise host entry - against the fp64 oracle at its own size:
+    loss <= 1e-4, gradients <= 1e-3 relative (north_star), for the fp32-class engine with tile flags on AND off."""
+    import ctypes as C
+    from mae_clip_b200 import _lib
+    I, T, (ref_loss, ref_dI, ref_dT, _stats) = _c4_batch_and_oracle(B, 1.0)
+    if variant == "fused_flags":
+        lib = _lib.lib()
+        n = lib.mc_clip_loss_fused_workspace_bytes(B, 256, 1)
+        ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+        l, dI, dT = torch.zeros(1, device="cuda"), torch.empty_like(I), torch.empty_like(T)
+        _lib.check(lib.mc_clip_loss_fwd_bwd(I.data_ptr(), T.data_ptr(), B, 256, 1.0, 1, l.data_ptr(), dI.data_ptr(),
+                                            dT.data_ptr(), ws.data_ptr(), n, _lib.cur_stream()))
+        loss = l.item()
+    elif variant == "dense":
+        loss, dI, dT, _ = _phases(I, T, 1.0, "tc_f16x3", sparse=False)
+    elif variant == "shards4096_flags":
+        loss, dI, dT, flags = _phases_sharded(I, T, 1.0, "tc_f16x3", 4096)
+        assert flags.float().mean().item() < 0.02      # the sparse path is what ran (diagonal tiles + a few neighbours)
+    else:
+        lib = _lib.lib()
+        Ih, Th = I.cpu().pin_memory(), T.cpu().pin_memory()
+        dI, dT = torch.empty_like(Ih).pin_memory(), torch.empty_like(Th).pin_memory()
+        l = torch.zeros(1).pin_memory()
+        n = lib.mc_clip_loss_host_workspace_bytes(B, 256, 1)
+        ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.mc_clip_loss_fwd_bwd_host(Ih.data_ptr(), Th.data_ptr(), B, 256, 1.0, 1, l.data_ptr(), dI.data_ptr(),
+                                                 dT.data_ptr(), ws.data_ptr(), n, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        loss = l.item()
+    assert abs(loss - ref_loss) <= LOSS_TOL * abs(ref_loss), (loss, ref_loss)
+    eI, eT = rel_err(dI, ref_dI), rel_err(dT, ref_dT)
+    print(f"c4 parity B={B} {variant}: loss rel {abs(loss - ref_loss) / abs(ref_loss):.2e}, dI {eI:.2e}, dT {eT:.2e}")
+    assert eI < GRAD_TOL and eT < GRAD_TOL, (eI, eT)
+
+
+@pytest.mark.parametrize("B", [8192, 32768])
+def test_loss_c4_size_single_pass_engine_vs_fp64_blockwise(B):
+    """Same check for the single-pass fp16 engine at ITS stated tolerance (5e-4 / 5e-3)."""
+    I, T, (ref_loss, ref_dI, ref_dT, _stats) = _c4_batch_and_oracle(B, 1.0)
+    loss, dI, dT, _ = _phases(I, T, 1.0, "tc_f16", sparse=True)
+    assert abs(loss - ref_loss) <= LOOSE_LOSS_TOL * abs(ref_loss)
+    assert rel_err(dI, ref_dI) < LOOSE_GRAD_TOL and rel_err(dT, ref_dT) < LOOSE_GRAD_TOL
+
+
+def test_loss_c4_size_soft_regime_vs_fp64_blockwise():
+    """B = 8192 with embeddings x 0.25 (every tile carries soft-target mass: flag density 1.0, the regime bench.py
+    reports as `roofline.soft`): flagged and dense sweeps against the fp64 oracle."""
+    B = 8192
+    I, T, (ref_loss, ref_dI, ref_dT, _stats) = _c4_batch_and_oracle(B, 0.25)
+    for sparse in (True, False):
+        loss, dI, dT, flags = _phases(I, T, 1.0, "tc_f16x3", sparse=sparse)
+        if sparse:
+            assert bool(flags.all())
+        assert abs(loss - ref_loss) <= LOSS_TOL * abs(ref_loss)
+        assert rel_err(dI, ref_dI) < GRAD_TOL and rel_err(dT, ref_dT) < GRAD_TOL
+
+
+# ------------------------------------------------------------------ autograd plumbing (round-1 advisor findings)
+def test_fp32_fma_engine_state_survives_other_ops_between_forward_and_backward():
+    """The fp32 FMA engine keeps its S / S^T / Z strips from the statistics sweep to the gradient sweep.  Through the
+    row-sharded Function (mae_clip_b200/dist.py) that state lives in the autograd context, not in the shared scratch
+    cache: other mae_clip_b200 ops between forward and backward, and a second backward over a retained graph, must not
+    change the gradients.  D = 64 also covers the automatic fall-back of the tcgen05 modes to this engine."""
+    import mae_clip_b200 as m
+    from mae_clip_b200.dist import global_clip_loss
+    for mode, D in (("simt_fp32", 256), ("tc_f16x3", 64)):
+        B = 192
+        I0 = loss_ref.make_embeddings(B, D, seed=71, scale=0.2)
+        T0 = loss_ref.make_embeddings(B, D, seed=72, scale=0.2)
+        I, T = I0.cuda().requires_grad_(True), T0.cuda().requires_grad_(True)
+        loss = global_clip_loss(I, T, 1.0, mode=mode)
+        # other work that goes through the same per-stream scratch buffer
+        J = loss_ref.make_embeddings(320, D, seed=73, scale=0.3).cuda().requires_grad_(True)
+        m.clip_contrastive_loss(J, J * 0.5, 1.0, mode="simt_fp32").backward()
+        global_clip_loss(J.detach(), J.detach() * 0.5, 1.0, mode=mode)
+        pred = torch.randn(4, 196, 768, device="cuda", requires_grad=True)
+        m.masked_mse_loss(pred, torch.randn(4, 3, 224, 224, device="cuda"), torch.ones(4, 196, device="cuda")).backward()
+        loss.backward(retain_graph=True)
+        g1 = (I.grad.clone(), T.grad.clone())
+        I.grad = T.grad = None
+        loss.backward()
+        ref_loss, ref_dI, ref_dT, _ = loss_ref.clip_loss_closed_form(I0.numpy(), T0.numpy(), 1.0)
+        assert abs(loss.item() - ref_loss) <= LOSS_TOL * abs(ref_loss)
+        assert rel_err(g1[0], ref_dI) < GRAD_TOL and rel_err(g1[1], ref_dT) < GRAD_TOL
+        assert torch.equal(I.grad, g1[0]) and torch.equal(T.grad, g1[1])
+
+
+def test_no_grad_forward_does_not_run_the_gradient_sweep():
+    """`main.py:115` evaluates under torch.no_grad() with parameters that require grad: the loss and the heads must not
+    run (or allocate for) their backward there."""
+    import mae_clip_b200 as m
+    from mae_clip_b200 import _lib
+    lib = _lib.lib()
+    I = loss_ref.make_embeddings(256, 256, seed=0).cuda().requires_grad_(True)
+    T = loss_ref.make_embeddings(256, 256, seed=1).cuda().requires_grad_(True)
+    n0 = lib.mc_kernel_launch_count()
+    l_grad = m.clip_contrastive_loss(I, T, 1.0)
+    n1 = lib.mc_kernel_launch_count()
+    with torch.no_grad():
+        l_eval = m.clip_contrastive_loss(I, T, 1.0)
+    n2 = lib.mc_kernel_launch_count()
+    assert l_eval.grad_fn is None and l_eval.item() == l_grad.item()
+    assert n2 - n1 < n1 - n0       # no gradient sweep / finalize launches
+    head = m.ProjectionHead(512).cuda().train()
+    x = torch.randn(64, 512, device="cuda", requires_grad=True)
+    keep = torch.ones(64, 256, dtype=torch.uint8, device="cuda")
+    with torch.no_grad():
+        out = head(x, keep_mask=keep)
+    assert out.grad_fn is None

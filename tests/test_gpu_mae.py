@@ -183,3 +183,15 @@ def test_mae_cuda_matches_published_vitmae_fixture(golden):
             ref = float(z[k + ".ref_loss"])
             assert abs(loss.item() - ref) < 1e-5 * abs(ref)
             assert rel_err(pred.grad, z[k + ".ref_dpred"]) < 1e-5
+
+
+def test_random_masking_ratio_one_backward_is_zero():
+    """mask_ratio = 1.0 keeps nothing: forward returns empty tokens, backward a zero gradient (it used to hand a NULL
+    pointer of the empty gradient to the C ABI)."""
+    import mae_clip_b200 as m
+    x = torch.randn(3, 16, 32, device="cuda", requires_grad=True)
+    noise = torch.rand(3, 16, device="cuda")
+    xm, mask, restore = m.random_masking(x, 1.0, noise)
+    assert xm.shape == (3, 0, 32) and bool((mask == 1).all())
+    (xm.sum() + 0.0 * x.sum()).backward()
+    assert torch.equal(x.grad, torch.zeros_like(x))
