@@ -100,15 +100,16 @@ class _ClipLoss(torch.autograd.Function):
     call (three sweeps over tiles, nothing of size BxB kept); backward only scales them."""
 
     @staticmethod
-    def forward(ctx, image_emb, text_emb, temperature, mode):
+    def forward(ctx, image_emb, text_emb, temperature, mode, grad_mode=True):
         require_cuda(image_emb, text_emb)
         if image_emb.dim() != 2 or image_emb.shape != text_emb.shape:
             raise ValueError("image/text embeddings must both be (B, D)")
         I, T = _f32c(image_emb), _f32c(text_emb)
         B, D = I.shape
         # needs_input_grad mirrors requires_grad even under torch.no_grad(): eval / inference must not pay for the
-        # gradient sweep (main.py:115 runs valid_epoch under no_grad)
-        need = torch.is_grad_enabled() and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        # gradient sweep (main.py:115 runs valid_epoch under no_grad).  Grad mode is always off INSIDE forward, so the
+        # caller samples it (`grad_mode`).
+        need = grad_mode and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         loss = torch.empty((), device=I.device, dtype=torch.float32)
         dI = torch.empty_like(I) if need else None
         dT = torch.empty_like(T) if need else None
@@ -128,12 +129,12 @@ class _ClipLoss(torch.autograd.Function):
         dI, dT = ctx.saved_tensors
         gi = (dI * grad_loss).to(ctx.in_dtypes[0]) if ctx.needs_input_grad[0] else None
         gt = (dT * grad_loss).to(ctx.in_dtypes[1]) if ctx.needs_input_grad[1] else None
-        return gi, gt, None, None
+        return gi, gt, None, None, None
 
 
 def clip_contrastive_loss(image_emb, text_emb, temperature: float = 1.0, mode=None):
     """Scalar soft-target bidirectional CE of ``CLIPModel.forward`` from (B, D) embeddings."""
-    return _ClipLoss.apply(image_emb, text_emb, float(temperature), _mode(mode))
+    return _ClipLoss.apply(image_emb, text_emb, float(temperature), _mode(mode), torch.is_grad_enabled())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -141,7 +142,7 @@ def clip_contrastive_loss(image_emb, text_emb, temperature: float = 1.0, mode=No
 # ------------------------------------------------------------------------------------------------
 class _ProjHead(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w_proj, b_proj, w_fc, b_fc, gamma, beta, keep_mask, p_drop, eps, mode):
+    def forward(ctx, x, w_proj, b_proj, w_fc, b_fc, gamma, beta, keep_mask, p_drop, eps, mode, grad_mode=True):
         require_cuda(x, w_proj, b_proj, w_fc, b_fc, gamma, beta, keep_mask)
         lead = x.shape[:-1]
         x2 = _f32c(x.reshape(-1, x.shape[-1]))
@@ -150,7 +151,7 @@ class _ProjHead(torch.autograd.Function):
         wp, bp, wf, bf, g, bt = (_f32c(t) for t in (w_proj, b_proj, w_fc, b_fc, gamma, beta))
         if keep_mask is not None:
             keep_mask = keep_mask.reshape(B, P).to(torch.uint8).contiguous()
-        need = torch.is_grad_enabled() and any(ctx.needs_input_grad[:7])   # no backward state under no_grad
+        need = grad_mode and any(ctx.needs_input_grad[:7])   # no backward state under no_grad (sampled by the caller)
         dev = x2.device
         out = torch.empty(B, P, device=dev, dtype=torch.float32)
         projected = torch.empty(B, P, device=dev, dtype=torch.float32)
@@ -196,14 +197,14 @@ class _ProjHead(torch.autograd.Function):
                                          cur_stream()), "mc_proj_head_bwd")
         if dx is not None:
             dx = dx.reshape(*lead, E).to(x_dtype)
-        return dx, dwp, dbp, dwf, dbf, dg, dbt, None, None, None, None
+        return dx, dwp, dbp, dwf, dbf, dg, dbt, None, None, None, None, None
 
 
 def projection_head(x, w_proj, b_proj, w_fc, b_fc, ln_weight, ln_bias, keep_mask=None,
                     p_drop: float = 0.1, eps: float = 1e-5, mode=None):
     """Fused ProjectionHead forward; ``keep_mask`` (0/1, shape of the output) = training mode."""
     return _ProjHead.apply(x, w_proj, b_proj, w_fc, b_fc, ln_weight, ln_bias, keep_mask,
-                           float(p_drop), float(eps), _mode(mode))
+                           float(p_drop), float(eps), _mode(mode), torch.is_grad_enabled())
 
 
 # ------------------------------------------------------------------------------------------------
