@@ -241,6 +241,16 @@ size_t mc_tc_gemm_workspace_bytes(int M, int N, int K);
 int mc_tc_gemm(const float* A, const float* B, int M, int N, int K, const float* bias, float* C,
                float* gelu_out, void* ws, size_t ws_bytes, void* stream);
 
+/* The pair kernels the heads run on from round 2 (csrc/head_tc.cu), exposed for tests: the activation
+ * operand is read as fp32 and split into fp16 hi / lo inside the kernel (converter warps -> tensor
+ * memory), the weights are staged as planes inside `ws`.  passes: 3 (fp32-class) or 1.
+ *   kind 0  C(M, 256) = A(M, K) . B(256, K)^T (+ bias; gelu_out = gelu(C) when given)
+ *   kind 1  C(M, N)   = A(M, K) . B(N, K)^T, K <= 256 (A stays resident in tensor memory)
+ *   kind 2  C(256, N) = A(K, 256)^T . B(K, N) (both operands transposed in the kernel; split-K) */
+size_t mc_head_gemm_workspace_bytes(int kind, int M, int N, int K);
+int mc_head_gemm(int kind, const float* A, const float* B, int M, int N, int K, const float* bias,
+                 float* C, float* gelu_out, int passes, void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------
  * M1  MAE per-sample random masking        (NOT in the reference: north_star; oracle/mae_ref.py)
  * noise (N,L) fp32; stable ascending argsort (ties -> lower index).  Outputs:

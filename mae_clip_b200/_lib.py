@@ -64,6 +64,8 @@ SIGNATURES = {
                               _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mc_tc_gemm_workspace_bytes": (_sz, [_i, _i, _i]),
     "mc_tc_gemm": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "mc_head_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "mc_head_gemm": (_i, [_i, _p, _p, _i, _i, _i, _p, _p, _p, _i, _p, _sz, _p]),
     "mc_random_masking": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "mc_random_masking_bwd": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _p, _p]),
     "mc_masked_mse_workspace_bytes": (_sz, [_i, _i]),

@@ -428,6 +428,25 @@ Planes carve_planes(void* mem, int rows, int cols) {
   return pl;
 }
 
+int amax(const float* src, int R, int C, int64_t lds, unsigned int* slot, cudaStream_t st) {
+  MC_REQUIRE(src && slot && R > 0 && C > 0, MC_ERR_BAD_ARG, "amax: bad argument");
+  MC_CUDA(cudaMemsetAsync(slot, 0, 4, st));
+  const size_t total = (size_t)R * C;
+  const int cap = num_sms() * 8;
+  if (lds == C && total % 4 == 0 && aligned(src, 16)) {
+    int fb = (int)((total / 4 + 1023) / 1024);
+    if (fb > cap) fb = cap;
+    if (fb < 1) fb = 1;
+    amax_flat_kernel<<<fb, 256, 0, st>>>(reinterpret_cast<const float4*>(src), total / 4, slot);
+  } else {
+    int ab = (int)((total + 255) / 256);
+    if (ab > cap) ab = cap;
+    amax2d_kernel<<<ab, 256, 0, st>>>(src, R, C, lds, slot);
+  }
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
 int stage(const float* src, int R, int C, int64_t lds, int transpose, const Planes& dst, cudaStream_t st,
           const unsigned int* known_amax) {
   MC_REQUIRE(src && dst.hi && dst.lo && dst.scale, MC_ERR_BAD_ARG, "stage: null pointer");

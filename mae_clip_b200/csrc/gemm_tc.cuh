@@ -26,6 +26,8 @@ Planes carve_planes(void* mem, int rows, int cols);
 // produced src, or an earlier staging of the same tensor); null = reduce it here (one more pass over src).
 int stage(const float* src, int R, int C, int64_t lds, int transpose, const Planes& dst, cudaStream_t st,
           const unsigned int* known_amax = nullptr);
+// bit pattern of max |src| over an (R, C) fp32 matrix with row stride lds -> *slot (zeroed first)
+int amax(const float* src, int R, int C, int64_t lds, unsigned int* slot, cudaStream_t st);
 inline const unsigned int* amax_slot(const Planes& p) { return reinterpret_cast<const unsigned int*>(p.scale) + 2; }
 
 enum Epilogue { kEpiPlain = 0, kEpiGelu = 1 };
