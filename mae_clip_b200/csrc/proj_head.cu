@@ -4,8 +4,11 @@
 // GEMMs: bias and exact-erf GELU are fused into the GEMM epilogue; dropout + residual +
 // LayerNorm are one warp-per-row pass (K2), its backward another (K2b) that also emits the
 // gamma/beta column partials.  The dropout keep-mask is an INPUT (SURVEY.md section 7 f).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include "head_tc.cuh"
 
 namespace mc {
 
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ y
 
 // ---------------- K2b: LayerNorm + dropout backward (warp per row, grid-stride rows) ---------
 // dz = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)), dxhat = dO * gamma
-// dy = dz * keep / (1-p);  per-block partials of dgamma = sum dO*xhat, dbeta = sum dO
+// dy = dz * keep / (1-p);  per-block partials of dgamma = sum dO*xhat, dbeta = sum dO, db_fc = sum dy
 template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ grad_out,
                                                      const float* __restrict__ z,
@@ -87,16 +90,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
                                                      const uint8_t* __restrict__ keep, float scale,
                                                      int B, int P, float* __restrict__ dz_out,
                                                      float* __restrict__ dy_out,
-                                                     float* __restrict__ partials /*[grid][2][P]*/,
+                                                     float* __restrict__ partials /*[grid][3][P]*/,
                                                      unsigned int* __restrict__ dy_amax /* or null */) {
-  extern __shared__ float sm[];  // [8 warps][2][P]
+  extern __shared__ float sm[];  // [8 warps][3][P]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = P >> 2;
   float amx = 0.f;  // max |dy| this thread wrote: saves the staging of dy a pass over it
-  float4 dg[NV], db[NV], gm[NV];
+  float4 dg[NV], db[NV], dbf[NV], gm[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    dg[k] = db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    dg[k] = db[k] = dbf[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int v = lane + 32 * k;
     gm[k] = (v < nvec) ? *reinterpret_cast<const float4*>(gamma + 4 * v) : dg[k];
   }
@@ -140,6 +143,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
           d.w = m.w ? d.w * scale : 0.f;
         }
         *reinterpret_cast<float4*>(dy_out + off + 4 * v) = d;
+        dbf[k].x += d.x; dbf[k].y += d.y; dbf[k].z += d.z; dbf[k].w += d.w;
         amx = fmaxf(amx, fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
       }
     }
@@ -153,16 +157,38 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
   for (int k = 0; k < NV; ++k) {
     const int v = lane + 32 * k;
     if (v < nvec) {
-      *reinterpret_cast<float4*>(sm + (warp * 2 + 0) * P + 4 * v) = dg[k];
-      *reinterpret_cast<float4*>(sm + (warp * 2 + 1) * P + 4 * v) = db[k];
+      *reinterpret_cast<float4*>(sm + (warp * 3 + 0) * P + 4 * v) = dg[k];
+      *reinterpret_cast<float4*>(sm + (warp * 3 + 1) * P + 4 * v) = db[k];
+      *reinterpret_cast<float4*>(sm + (warp * 3 + 2) * P + 4 * v) = dbf[k];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * P; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 3 * P; i += blockDim.x) {
     float acc = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) acc += sm[w * 2 * P + i];
-    partials[(size_t)blockIdx.x * 2 * P + i] = acc;
+    for (int w = 0; w < 8; ++w) acc += sm[w * 3 * P + i];
+    partials[(size_t)blockIdx.x * 3 * P + i] = acc;
+  }
+}
+
+// out_k[c] = sum_r in[r][k * P + c] for k = 0, 1, 2 (rows x 3P partials of ln_bwd_kernel -> dgamma, dbeta, db_fc)
+__global__ void __launch_bounds__(1024) colsum3_kernel(const float* __restrict__ in, int rows, int P,
+                                                       float* __restrict__ out0, float* __restrict__ out1,
+                                                       float* __restrict__ out2) {
+  __shared__ float sm[32][33];
+  const int cols = 3 * P;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < cols)
+    for (int r = threadIdx.y; r < rows; r += 32) acc += in[(size_t)r * cols + c];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  float v = sm[threadIdx.x][threadIdx.y];
+  v = warp_sum(v);
+  const int oc = blockIdx.x * 32 + threadIdx.y;
+  if (threadIdx.x == 0 && oc < cols) {
+    float* o = oc < P ? out0 : (oc < 2 * P ? out1 : out2);
+    o[oc % P] = v;
   }
 }
 
@@ -282,7 +308,7 @@ static int launch_ln_bwd(const float* go, const float* z, const float* mean, con
                          const float* gamma, const uint8_t* keep, float scale, int B, int P,
                          float* dz, float* dy, float* partials, int blocks, unsigned int* dy_amax,
                          cudaStream_t st) {
-  size_t smem = (size_t)8 * 2 * P * sizeof(float);
+  size_t smem = (size_t)8 * 3 * P * sizeof(float);
   ln_bwd_kernel<NV><<<blocks, 256, smem, st>>>(go, z, mean, rstd, gamma, keep, scale, B, P, dz, dy,
                                                partials, dy_amax);
   MC_LAUNCH_CHECK();
@@ -303,7 +329,7 @@ struct HeadWs {
 };
 static HeadWs head_ws(void* ws, int B, int /*E*/, int P) {
   size_t bp = round_up((size_t)B * P * 4, 256);
-  size_t part = round_up((size_t)ln_blocks(B) * 2 * P * 4, 256);
+  size_t part = round_up((size_t)ln_blocks(B) * 3 * P * 4, 256);
   char* p = static_cast<char*>(ws);
   HeadWs w;
   w.y = reinterpret_cast<float*>(p);
@@ -344,7 +370,7 @@ static TcHeadWs tc_head_ws(void* ws, int B, int E, int P) {
   w.dh = reinterpret_cast<float*>(take(bp));
   w.dz = w.y;            // backward reuses the forward temporaries
   w.dy = w.hidden_tmp;
-  w.partials = reinterpret_cast<float*>(take((size_t)ln_blocks(B) * 2 * P * 4));
+  w.partials = reinterpret_cast<float*>(take((size_t)ln_blocks(B) * 3 * P * 4));
   w.amax = reinterpret_cast<unsigned int*>(take(256));
   w.x = planes(B, E);  w.wp = planes(P, E);  w.h = planes(B, P);  w.wf = planes(P, P);
   w.dyT = planes(P, B); w.hT = planes(P, B); w.dy_p = planes(B, P); w.wfT = planes(P, P);
@@ -366,6 +392,49 @@ static TcHeadWs tc_head_ws(void* ws, int B, int E, int P) {
 constexpr int kTcMinRows = 2048;
 static bool use_tc(int mode, int B) {
   return (mode == MC_GEMM_TC_F16X3 || mode == MC_GEMM_TC_F16) && B >= kTcMinRows;
+}
+
+
+// ---------------- CTA-pair path (csrc/head_tc.cu): workspace map ----------------
+// Only WEIGHTS are staged as planes here (a few MB); activations are converted inside the GEMM kernels.
+struct PairHeadWs {
+  float *hidden_tmp, *dz, *dy, *dp, *partials, *colpart;
+  unsigned int* amax;                 // [0] x, [1] hidden (when the caller passes no fwd_amax), [2] dy, [3] dp
+  tcg::Planes wp, wf, wfT, wpT;       // (P, E), (P, P), (P, P)^T, (E, P)
+  void* tt_ws;
+  size_t tt_ws_bytes;
+  size_t total;
+};
+static PairHeadWs pair_head_ws(void* ws, int B, int E, int P) {
+  PairHeadWs w;
+  char* base = static_cast<char*>(ws);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += round_up(bytes, 256); return p; };
+  auto planes = [&](int rows, int cols) {
+    void* mem = take(tcg::planes_bytes(rows, cols));
+    return mem ? tcg::carve_planes(mem, rows, cols) : tcg::Planes{nullptr, nullptr, nullptr, rows, cols, 0};
+  };
+  const size_t bp = (size_t)B * P * 4;
+  w.hidden_tmp = reinterpret_cast<float*>(take(bp));
+  w.dz = reinterpret_cast<float*>(take(bp));
+  w.dy = w.hidden_tmp;   // backward reuses the forward temporary
+  w.dp = reinterpret_cast<float*>(take(bp));
+  w.partials = reinterpret_cast<float*>(take((size_t)ln_blocks(B) * 3 * P * 4));
+  w.colpart = reinterpret_cast<float*>(take((size_t)hg::colpart_rows(B) * P * 4));
+  w.amax = reinterpret_cast<unsigned int*>(take(256));
+  w.wp = planes(P, E); w.wf = planes(P, P); w.wfT = planes(P, P); w.wpT = planes(E, P);
+  size_t t1 = hg::tt_workspace_bytes(P, B), t2 = hg::tt_workspace_bytes(E, B);
+  w.tt_ws_bytes = t1 > t2 ? t1 : t2;
+  w.tt_ws = take(w.tt_ws_bytes);
+  w.total = off;
+  return w;
+}
+
+// The pair kernels cover the reference's shape family: projection_dim 256 (config.py:23), any embedding width that
+// is a multiple of 4.  MAE_CLIP_HEAD_PAIR=0 keeps the round-1 single-CTA GEMMs (A/B switch).
+static bool use_pair(int mode, int B, int E, int P) {
+  static const bool off = getenv("MAE_CLIP_HEAD_PAIR") != nullptr && getenv("MAE_CLIP_HEAD_PAIR")[0] == '0';
+  return !off && use_tc(mode, B) && hg::supported(P) && E % 4 == 0 && (E + 255) / 256 <= num_sms() / 2;
 }
 
 }  // namespace mc
@@ -401,6 +470,7 @@ int mc_tc_gemm(const float* A, const float* B, int M, int N, int K, const float*
 
 size_t mc_proj_head_workspace_bytes(int B, int E, int P, int mode) {
   if (B <= 0 || E <= 0 || P <= 0) return 0;
+  if (use_pair(mode, B, E, P)) return pair_head_ws(nullptr, B, E, P).total;
   return use_tc(mode, B) ? tc_head_ws(nullptr, B, E, P).total : head_ws(nullptr, B, E, P).total;
 }
 
@@ -424,6 +494,31 @@ int mc_proj_head_fwd(const float* x, int B, int E, int P, const float* w_proj, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float scale = 1.f / (1.f - p_drop);
   int rc;
+  if (use_pair(mode, B, E, P)) {
+    // CTA-pair path: x and hidden are converted fp32 -> fp16 hi/lo inside the GEMMs; bias + GELU ride on the first,
+    // dropout + residual + LayerNorm on the second (N = 256 is one tile row).  Only the weights are staged.
+    MC_REQUIRE(aligned(ws, 256), MC_ERR_ALIGN, "proj_head_fwd: workspace must be 256-byte aligned");
+    MC_REQUIRE(aligned(x, 16), MC_ERR_ALIGN, "proj_head_fwd: x must be 16-byte aligned");
+    PairHeadWs t = pair_head_ws(ws, B, E, P);
+    MC_REQUIRE(ws_bytes >= t.total, MC_ERR_WORKSPACE, "proj_head_fwd: workspace %zu < %zu", ws_bytes, t.total);
+    const int passes = mode == MC_GEMM_TC_F16X3 ? 3 : 1;
+    unsigned int* amax_x = fwd_amax ? reinterpret_cast<unsigned int*>(fwd_amax) : t.amax;
+    unsigned int* amax_h = amax_x + 1;
+    if ((rc = tcg::amax(x, B, E, E, amax_x, st))) return rc;
+    MC_CUDA(cudaMemsetAsync(amax_h, 0, 4, st));
+    if ((rc = tcg::stage(w_proj, P, E, E, 0, t.wp, st))) return rc;
+    if ((rc = tcg::stage(w_fc, P, P, P, 0, t.wf, st))) return rc;
+    float* hid = hidden ? hidden : t.hidden_tmp;
+    hg::RowArgs f1 = {};
+    f1.A = x; f1.lda = E; f1.a_amax = amax_x; f1.W = t.wp; f1.M = B; f1.K = E; f1.passes = passes;
+    f1.epilogue = hg::kEpiBiasGelu; f1.bias = b_proj; f1.out0 = projected; f1.out1 = hid; f1.out_amax = amax_h;
+    if ((rc = hg::rows_gemm(f1, st))) return rc;
+    hg::RowArgs f2 = {};
+    f2.A = hid; f2.lda = P; f2.a_amax = amax_h; f2.W = t.wf; f2.M = B; f2.K = P; f2.passes = passes;
+    f2.epilogue = hg::kEpiLN; f2.bias = b_fc; f2.in0 = projected; f2.keep = keep_mask; f2.drop_scale = scale; f2.eps = eps;
+    f2.gamma = gamma; f2.beta = beta; f2.out0 = out; f2.out1 = z; f2.mean = mean; f2.rstd = rstd;
+    return hg::rows_gemm(f2, st);
+  }
   if (use_tc(mode, B)) {
     // tensor-core path: stage fp16 hi/lo planes, two tcgen05 GEMMs (bias + exact GELU fused into the first)
     MC_REQUIRE(aligned(ws, 256), MC_ERR_ALIGN, "proj_head_fwd: workspace must be 256-byte aligned");
@@ -479,6 +574,51 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
   const float scale = 1.f / (1.f - p_drop);
   const int blocks = ln_blocks(B);
   int rc;
+  if (use_pair(mode, B, E, P)) {
+    MC_REQUIRE(aligned(ws, 256), MC_ERR_ALIGN, "proj_head_bwd: workspace must be 256-byte aligned");
+    MC_REQUIRE(aligned(x, 16) && aligned(hidden, 16) && aligned(dw_proj, 16) && aligned(dw_fc, 16) && (!dx || aligned(dx, 16)),
+               MC_ERR_ALIGN, "proj_head_bwd: tensors must be 16-byte aligned");
+    PairHeadWs t = pair_head_ws(ws, B, E, P);
+    MC_REQUIRE(ws_bytes >= t.total, MC_ERR_WORKSPACE, "proj_head_bwd: workspace %zu < %zu", ws_bytes, t.total);
+    const int passes = mode == MC_GEMM_TC_F16X3 ? 3 : 1;
+    MC_CUDA(cudaMemsetAsync(t.amax, 0, 16, st));
+    const unsigned int* amax_x = fwd_amax ? reinterpret_cast<const unsigned int*>(fwd_amax) : t.amax;
+    const unsigned int* amax_h = amax_x + 1;
+    unsigned int *amax_dy = t.amax + 2, *amax_dp = t.amax + 3;
+    if (!fwd_amax) {  // the forward did not hand its reductions over: redo them
+      if ((rc = tcg::amax(x, B, E, E, t.amax, st))) return rc;
+      if ((rc = tcg::amax(hidden, B, P, P, t.amax + 1, st))) return rc;
+    }
+    // LayerNorm + dropout backward: dz, dy, max |dy|, column partials of dgamma / dbeta / db_fc
+    MC_DISPATCH_NV(P, (launch_ln_bwd<NV>(grad_out, z, mean, rstd, gamma, keep_mask, scale, B, P, t.dz, t.dy, t.partials,
+                                         blocks, amax_dy, st)));
+    if (rc) return rc;
+    dim3 blk(32, 32);
+    colsum3_kernel<<<(3 * P + 31) / 32, blk, 0, st>>>(t.partials, blocks, P, dgamma, dbeta, db_fc);
+    MC_LAUNCH_CHECK();
+    // dp = (dy Wf) * gelu'(projected) + dz : the GELU backward is the epilogue of the GEMM; it also reduces max |dp|
+    // and the per-warp column sums of dp (db_proj)
+    if ((rc = tcg::stage(w_fc, P, P, P, 1, t.wfT, st))) return rc;
+    hg::RowArgs b1 = {};
+    b1.A = t.dy; b1.lda = P; b1.a_amax = amax_dy; b1.W = t.wfT; b1.M = B; b1.K = P; b1.passes = passes;
+    b1.epilogue = hg::kEpiGeluBwd; b1.in0 = projected; b1.in1 = t.dz; b1.out0 = t.dp; b1.out_amax = amax_dp;
+    b1.colpart = t.colpart;
+    if ((rc = hg::rows_gemm(b1, st))) return rc;
+    colsum_kernel<<<(P + 31) / 32, blk, 0, st>>>(t.colpart, hg::colpart_rows(B), P, db_proj);
+    MC_LAUNCH_CHECK();
+    // dWf = dy^T hidden, dWp = dp^T x : K is the batch; both operands are transposed inside the kernel
+    hg::TtArgs g1{t.dy, P, amax_dy, hidden, P, amax_h, B, P, passes, dw_fc, P};
+    if ((rc = hg::tt_gemm(g1, t.tt_ws, t.tt_ws_bytes, st))) return rc;
+    hg::TtArgs g2{t.dp, P, amax_dp, x, E, amax_x, B, E, passes, dw_proj, E};
+    if ((rc = hg::tt_gemm(g2, t.tt_ws, t.tt_ws_bytes, st))) return rc;
+    if (dx) {
+      // dx = dp Wp : short K, the converted row block of dp stays resident in tensor memory
+      if ((rc = tcg::stage(w_proj, P, E, E, 1, t.wpT, st))) return rc;
+      hg::AresArgs g3{t.dp, P, amax_dp, t.wpT, B, E, P, passes, dx, E};
+      if ((rc = hg::ares_gemm(g3, st))) return rc;
+    }
+    return MC_OK;
+  }
   if (use_tc(mode, B)) {
     MC_REQUIRE(aligned(ws, 256), MC_ERR_ALIGN, "proj_head_bwd: workspace must be 256-byte aligned");
     TcHeadWs t = tc_head_ws(ws, B, E, P);
@@ -490,11 +630,8 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
                                          t.partials, blocks, t.amax, st)));
     if (rc) return rc;
     dim3 blk(32, 32);
-    colsum_kernel<<<(2 * P + 31) / 32, blk, 0, st>>>(t.partials, blocks, 2 * P, t.dh);
+    colsum3_kernel<<<(3 * P + 31) / 32, blk, 0, st>>>(t.partials, blocks, P, dgamma, dbeta, db_fc);
     MC_LAUNCH_CHECK();
-    MC_CUDA(cudaMemcpyAsync(dgamma, t.dh, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
-    MC_CUDA(cudaMemcpyAsync(dbeta, t.dh + P, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
-    if ((rc = colsum_rows(t.dy, B, P, db_fc, t.partials, 2 * blocks, st))) return rc;  // partials are free again
     // dWf[n,k] = sum_m dy[m,n] hidden[m,k]  ->  (dy^T) . (hidden^T)^T, K = B (split-K)
     if ((rc = tcg::stage(t.dy, B, P, P, 1, t.dyT, st, t.amax))) return rc;
     if ((rc = tcg::stage(hidden, B, P, P, 1, t.hT, st, h_amax))) return rc;
@@ -537,12 +674,9 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
   // dgamma / dbeta: column sums of the block partials ([blocks][2P] viewed as rows x 2P)
   {
     dim3 blk(32, 32);
-    // partial rows are [dgamma(P) | dbeta(P)]
-    colsum_kernel<<<(2 * P + 31) / 32, blk, 0, st>>>(w.partials, blocks, 2 * P, w.dh);
+    // partial rows are [dgamma(P) | dbeta(P) | db_fc(P)]
+    colsum3_kernel<<<(3 * P + 31) / 32, blk, 0, st>>>(w.partials, blocks, P, dgamma, dbeta, db_fc);
     MC_LAUNCH_CHECK();
-    MC_CUDA(cudaMemcpyAsync(dgamma, w.dh, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
-    MC_CUDA(cudaMemcpyAsync(dbeta, w.dh + P, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
-    if ((rc = colsum_rows(w.dy, B, P, db_fc, w.partials, 2 * blocks, st))) return rc;
   }
   // dWf[n,k] = sum_m dy[m,n] hidden[m,k]
   SgemmArgs g1{w.dy, 1, P, hidden, P, 1, dw_fc, P, P, P, B, 1.f, nullptr, nullptr, 0};
