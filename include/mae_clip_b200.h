@@ -215,16 +215,22 @@ int mc_peer_publish(const void* src, int k, int n, int64_t src_stride, void* con
  *   z = keep*y/(1-p) + projected; out = LayerNorm(z) * gamma + beta
  * keep_mask: (B, P) bytes of 0/1 or NULL (eval mode).  projected / hidden / z /
  * mean / rstd are written for backward (all (B,P) or (B)); pass NULL for
- * hidden/z/mean/rstd under no_grad to skip the stores.  fwd_amax: optional two
- * device words the forward fills (bit patterns of max|x|, max|hidden|) and the
- * backward reads, so it need not reduce them again (NULL on either side: recomputed).
+ * hidden/z/mean/rstd under no_grad to skip the stores.  fwd_amax: optional FOUR
+ * device words the forward fills ([0], [1]: bit patterns of max|x|, max|hidden|; [2], [3]:
+ * internal) and the backward reads, so it need not reduce them again (NULL on either side:
+ * recomputed).  prev_amax: optional, the fwd_amax words of an EARLIER forward of the same
+ * head.  The fp16 operand planes take a power-of-two scale from max|x|; with prev_amax the
+ * scale comes from the earlier call, the true maximum is reduced while x streams through
+ * the GEMM, and a second, gated launch redoes the GEMM only if the old scale was outside
+ * the safe fp16 window - the 268 MB activation is then read once, not twice.  Results do
+ * not depend on prev_amax (a power-of-two scale changes nothing inside that window).
  * ------------------------------------------------------------------------- */
 size_t mc_proj_head_workspace_bytes(int B, int E, int P, int mode);
 int mc_proj_head_fwd(const float* x, int B, int E, int P, const float* w_proj, const float* b_proj,
                      const float* w_fc, const float* b_fc, const float* gamma, const float* beta,
                      const uint8_t* keep_mask, float p_drop, float eps, int mode, float* projected,
                      float* hidden, float* z, float* mean, float* rstd, float* out, float* fwd_amax,
-                     void* ws, size_t ws_bytes, void* stream);
+                     const float* prev_amax, void* ws, size_t ws_bytes, void* stream);
 /* dx may be NULL (frozen tower below the head: modules.py:35 / CLIP.py:18). */
 int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
                      const float* w_proj, const float* w_fc, const float* gamma,

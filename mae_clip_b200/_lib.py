@@ -59,7 +59,7 @@ SIGNATURES = {
     "mc_clip_loss_fwd_bwd_host": (_i, [_p, _p, _i, _i, _f, _i, _p, _p, _p, _p, _sz, _p]),
     "mc_proj_head_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mc_proj_head_fwd": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p,
-                              _p, _p, _p, _p, _sz, _p]),
+                              _p, _p, _p, _p, _p, _sz, _p]),
     "mc_proj_head_bwd": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _f, _i, _p, _p, _p, _p, _p, _p, _p,
                               _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mc_tc_gemm_workspace_bytes": (_sz, [_i, _i, _i]),

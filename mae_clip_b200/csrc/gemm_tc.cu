@@ -501,6 +501,117 @@ int stage(const float* src, int R, int C, int64_t lds, int transpose, const Plan
   return MC_OK;
 }
 
+// ---- two weight matrices in one launch -------------------------------------------------------------
+struct StageJobDev {
+  const float* src;
+  int R, C, transpose, pitch;
+  __half* hi;
+  __half* lo;
+  float* scale;
+};
+__device__ __forceinline__ void stage_job_amax(const StageJobDev& j, unsigned int* slot) {
+  float a = 0.f;
+  const size_t total = (size_t)j.R * j.C;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (total % 4 == 0 && (reinterpret_cast<uintptr_t>(j.src) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(j.src);
+    for (size_t i = t0; i < total / 4; i += stride) {
+      const float4 v = s4[i];
+      a = fmaxf(a, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+  } else {
+    for (size_t i = t0; i < total; i += stride) a = fmaxf(a, fabsf(j.src[i]));
+  }
+  a = warp_max(a);
+  if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(slot, __float_as_uint(a));
+}
+__device__ __forceinline__ void stage_job_split(const StageJobDev& j, unsigned int amax_bits, float (*tile)[33]) {
+  const float s = scale_from_amax(__uint_as_float(amax_bits));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    j.scale[0] = s; j.scale[1] = 1.f / s;
+    reinterpret_cast<unsigned int*>(j.scale)[2] = amax_bits;
+  }
+  if (!j.transpose) {
+    const size_t total = (size_t)j.R * j.pitch;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j.pitch == j.C && total % 4 == 0 && (reinterpret_cast<uintptr_t>(j.src) & 15) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(j.src);
+      uint2* h2 = reinterpret_cast<uint2*>(j.hi);
+      uint2* l2 = reinterpret_cast<uint2*>(j.lo);
+      for (size_t i = t0; i < total / 4; i += stride) {
+        uint2 h, l;
+        split4(s4[i], s, h, l);
+        h2[i] = h;
+        l2[i] = l;
+      }
+    } else {
+      for (size_t i = t0; i < total; i += stride) {
+        const int r = (int)(i / j.pitch), c = (int)(i % j.pitch);
+        const float x = c < j.C ? j.src[(size_t)r * j.C + c] * s : 0.f;
+        const __half h = __float2half_rn(x);
+        j.hi[i] = h;
+        j.lo[i] = __float2half_rn(x - __half2float(h));
+      }
+    }
+    return;
+  }
+  // transposed: dst (C rows x R cols, pitch) = src^T, 32 x 32 tiles through shared memory
+  const int tr = (j.pitch + 31) / 32, tc = (j.C + 31) / 32;   // tiles along the source rows (incl. padding) / columns
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int t = blockIdx.x; t < tr * tc; t += gridDim.x) {
+    const int r0 = (t % tr) * 32, c0 = (t / tr) * 32;
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+      const int r = r0 + k, c = c0 + tx;
+      tile[k][tx] = (r < j.R && c < j.C) ? j.src[(size_t)r * j.C + c] * s : 0.f;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+      const int orow = c0 + k, ocol = r0 + tx;
+      if (orow < j.C && ocol < j.pitch) {
+        const float x = tile[tx][k];
+        const __half h = __float2half_rn(x);
+        j.hi[(size_t)orow * j.pitch + ocol] = h;
+        j.lo[(size_t)orow * j.pitch + ocol] = __float2half_rn(x - __half2float(h));
+      }
+    }
+  }
+}
+// every block is resident (grid <= number of SMs), so a counter barrier between the two phases is safe
+__global__ void __launch_bounds__(256) stage_pair_kernel(StageJobDev a, StageJobDev b, unsigned int* sync) {
+  __shared__ float tile[32][33];
+  stage_job_amax(a, sync + 1);
+  stage_job_amax(b, sync + 2);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(sync, 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(sync) < gridDim.x) __nanosleep(32);
+    __threadfence();
+  }
+  __syncthreads();
+  const unsigned int ba = *reinterpret_cast<volatile unsigned int*>(sync + 1);
+  const unsigned int bb = *reinterpret_cast<volatile unsigned int*>(sync + 2);
+  stage_job_split(a, ba, tile);
+  stage_job_split(b, bb, tile);
+}
+
+int stage_pair(const StageJob& a, const StageJob& b, unsigned int* sync, cudaStream_t st) {
+  const StageJob* jobs[2] = {&a, &b};
+  StageJobDev d[2];
+  for (int k = 0; k < 2; ++k) {
+    const StageJob& j = *jobs[k];
+    MC_REQUIRE(j.src && j.dst.hi && j.dst.lo && j.dst.scale && sync, MC_ERR_BAD_ARG, "stage_pair: null pointer");
+    MC_REQUIRE(j.dst.rows == (j.transpose ? j.C : j.R) && j.dst.cols == (j.transpose ? j.R : j.C), MC_ERR_BAD_ARG,
+               "stage_pair: destination planes are %d x %d", j.dst.rows, j.dst.cols);
+    d[k] = StageJobDev{j.src, j.R, j.C, j.transpose, j.dst.pitch, j.dst.hi, j.dst.lo, j.dst.scale};
+  }
+  MC_CUDA(cudaMemsetAsync(sync, 0, 16, st));
+  stage_pair_kernel<<<num_sms(), 256, 0, st>>>(d[0], d[1], sync);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
 // ---- host side of the GEMM ---------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -30,6 +30,15 @@ int stage(const float* src, int R, int C, int64_t lds, int transpose, const Plan
 int amax(const float* src, int R, int C, int64_t lds, unsigned int* slot, cudaStream_t st);
 inline const unsigned int* amax_slot(const Planes& p) { return reinterpret_cast<const unsigned int*>(p.scale) + 2; }
 
+// Two small matrices (the weights of a head) staged in ONE launch: max |.| of each, a grid-wide barrier, then the
+// hi / lo split (transposed or not).  `sync` = 4 device words, zeroed by the call.  Replaces 2 x (memset + amax + stage).
+struct StageJob {
+  const float* src;   // (R, C) dense fp32
+  int R, C, transpose;
+  Planes dst;         // (R, C) planes, or (C, R) when transpose
+};
+int stage_pair(const StageJob& a, const StageJob& b, unsigned int* sync, cudaStream_t st);
+
 enum Epilogue { kEpiPlain = 0, kEpiGelu = 1 };
 
 struct GemmOut {

@@ -45,6 +45,17 @@ __device__ __forceinline__ void tmem_st32f(uint32_t taddr, const float* v) {
   tmem_st16(taddr, r);
   tmem_st16(taddr + 16, r + 16);
 }
+// 32 lanes x 16 columns of 32-bit
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem]^T over the CTA pair (A: lane = row, 32-bit columns hold two consecutive K elements)
 __device__ __forceinline__ void mma_f16_pair_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
@@ -80,6 +91,17 @@ __device__ __forceinline__ float scale_from_amax_bits(unsigned int bits) {
   return s;
 }
 
+// Was a power-of-two scale taken from `stale` (max |A| of an EARLIER call) safe for data whose true maximum is `live`?
+// stale * s lies in [1, 2), so live * s estimates live / stale within a factor of two.  Safe = no fp16 overflow
+// (live * s < 2^14) and enough of the fp16 range left for the lo plane (live * s >= 2^-5; an all-zero A is always safe).
+__device__ __forceinline__ bool scale_window_ok(unsigned int stale_bits, unsigned int live_bits) {
+  const float st = __uint_as_float(stale_bits), lv = __uint_as_float(live_bits);
+  if (!(st > 0.f) || !(st < INFINITY) || !(lv < INFINITY)) return false;
+  if (lv == 0.f) return true;
+  const float r = lv * scale_from_amax_bits(stale_bits);
+  return r < 16384.f && r >= 0.03125f;
+}
+
 // two scaled fp32 values -> packed fp16 hi pair and packed fp16 lo pair (lo = fp16(x - hi), exact difference)
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x0, x1);
@@ -87,6 +109,32 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
   const __half2 l = __floats2half2_rn(x0 - b.x, x1 - b.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// exact-erf GELU (modules.py:64, nn.GELU()) and its derivative through ONE exponential: Abramowitz-Stegun 7.1.26,
+//   erf(u) = 1 - (a1 t + ... + a5 t^5) e^{-u^2}, t = 1 / (1 + 0.3275911 u), u >= 0,  |error| <= 1.5e-7,
+// with u = |x| / sqrt(2), so that e^{-u^2} = e^{-x^2/2} is also the Gaussian of the derivative.  erff() costs ~70
+// instructions with a divergent branch; this is ~18 and keeps the epilogues inside the instruction cache.
+__device__ __forceinline__ void gelu_core(float x, float& cdf, float& gauss) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.f));
+  gauss = exp2f(-0.72134752044448170f * x * x);   // e^{-x^2/2}
+  float pl = fmaf(1.061405429f, t, -1.453152027f);
+  pl = fmaf(pl, t, 1.421413741f);
+  pl = fmaf(pl, t, -0.284496736f);
+  pl = fmaf(pl, t, 0.254829592f);
+  const float half_tail = 0.5f * pl * t * gauss;    // (1 - erf(u)) / 2
+  cdf = x >= 0.f ? 1.f - half_tail : half_tail;
+}
+__device__ __forceinline__ float gelu_as(float x) {
+  float cdf, g;
+  gelu_core(x, cdf, g);
+  return x * cdf;
+}
+__device__ __forceinline__ float gelu_grad_as(float x) {
+  float cdf, g;
+  gelu_core(x, cdf, g);
+  return fmaf(x * 0.3989422804014327f, g, cdf);
 }
 
 // ------------------------------------------------------------------------------------------------ epilogue I/O
@@ -176,17 +224,18 @@ __device__ __forceinline__ void convert_col32(uint32_t box, int col, float s, ui
 
 // ================================================================================================ row kernel
 namespace rowk {
-constexpr int kThreads = 448;   // warp 0 TMA, warp 1 MMA, warps 2-5 converter, warps 6-13 epilogue
-constexpr int kSrcSlot = 32768, kSrcSlots = 3;         // fp32 A: [128 rows][64 k] as two swizzled 32-k boxes
-constexpr int kBSlot = 32768, kBSlots = 2;             // W half of this CTA: hi [128 rows][64 k] + lo
+constexpr int kThreads = 480;   // warp 0 W producer, warp 1 MMA, warps 2-5 converter, warps 6-13 epilogue, warp 14 A producer
+constexpr int kSrcSlot = 16384, kSrcSlots = 5;         // fp32 A: one swizzled box [128 rows][32 k]; a 64-k chunk = 2 slots
+constexpr int kBSlot = 32768, kBSlots = 3;             // W half of this CTA: hi [128 rows][64 k] + lo
 constexpr int kOffSrc = 0;
-constexpr int kOffB = kOffSrc + kSrcSlots * kSrcSlot;  // 98304
-constexpr int kOffStg = kOffB + kBSlots * kBSlot;      // 163840
-constexpr int kOffLnx = kOffStg + 8 * kStgBytes;       // 200704: [2 exchanges][2 halves][128 rows] floats
-constexpr int kOffBar = kOffLnx + 2 * 2 * 128 * 4;     // 202752
+constexpr int kOffB = kOffSrc + kSrcSlots * kSrcSlot;  // 81920
+constexpr int kOffStg = kOffB + kBSlots * kBSlot;      // 180224
+constexpr int kOffLnx = kOffStg + 8 * kStgBytes;       // 217088: [2 exchanges][2 halves][128 rows] floats
+constexpr int kOffBar = kOffLnx + 8 * 128 * 4;         // 221184 (the LayerNorm exchange uses the first 2 KB; the
+                                                       // GELU-backward column sums 8 warps x 128 floats)
 constexpr int kSmem = kOffBar + 256 + 1024;
-enum Bar { kSrcFull = 0, kSrcEmpty = 3, kAFull = 6, kAEmpty = 8, kBFull = 10, kBEmpty = 12, kAccFull = 14, kAccEmpty = 15,
-           kNumBars = 16 };
+enum Bar { kSrcFull = 0, kSrcEmpty = 5, kAFull = 10, kAEmpty = 12, kBFull = 14, kBEmpty = 17, kAccFull = 20, kAccEmpty = 21,
+           kNumBars = 22 };
 constexpr uint32_t kACol = 256;       // TMEM: accumulator [0, 256), A stage s at 256 + 64 s (hi: 32 columns, lo: 32)
 }  // namespace rowk
 
@@ -207,7 +256,59 @@ struct RowParams {
   float* rstd;
   unsigned int* out_amax;
   float* colpart;
+  // scale source of A (see head_tc.cuh "scale protocol"): vmode 0 = *a_amax; 1 = first attempt with the PREVIOUS call's
+  // max |A| (*v_stale) while the true one is reduced into *a_live; 2 = redo: return at once when the stale scale was
+  // inside the safe window, else run again with *v_live; 3 = consumer of an operand produced under that protocol:
+  // *a_amax when the first attempt was valid, else *a_alt (and *amax_publish := the one chosen)
+  int vmode;
+  const unsigned int* a_alt;
+  const unsigned int* v_stale;
+  const unsigned int* v_live;
+  unsigned int* a_live;
+  unsigned int* amax_publish;
+  unsigned long long* dbg;   // optional timeline of pair 0's leader CTA (globaltimer ns), tools/head_timeline.py
 };
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define HG_MARK(idx)                                                              \
+  do {                                                                            \
+    if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(idx)] = gtime_ns();         \
+  } while (0)
+
+// The epilogue works on a warp's 32 x 32 block in two thread mappings: ROW (lane = row: what tcgen05.ld delivers, and
+// what row reductions want) and PIECE (iteration i of 8: row 4 i + (lane >> 3), columns 4 (lane & 7) .. +3: eight lanes
+// cover 128 contiguous bytes of one row, so global loads / stores are coalesced and can all be issued before first use).
+// The accumulator block crosses from one mapping to the other through the warp's staging buffer.
+__device__ __forceinline__ void stg_put_rows(float* stg, int lane, const float* v) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 4)
+    *reinterpret_cast<float4*>(stg + lane * kStgPitch + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+}
+__device__ __forceinline__ void stg_get_rows(const float* stg, int lane, float* v) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(stg + lane * kStgPitch + e);
+    v[e] = x.x; v[e + 1] = x.y; v[e + 2] = x.z; v[e + 3] = x.w;
+  }
+}
+// accumulator block (32 columns of this lane's row) -> staging buffer, 16 columns at a time (register pressure)
+__device__ __forceinline__ void tmem_to_stg_rows(uint32_t taddr, float* stg, int lane) {
+#pragma unroll
+  for (int hcol = 0; hcol < 32; hcol += 16) {
+    float v[16];
+    tmem_ld16(taddr + hcol, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 16; e += 4)
+      *reinterpret_cast<float4*>(stg + lane * kStgPitch + hcol + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+  }
+}
+__device__ __forceinline__ float amax4(float a, const float4 v) {
+  return fmaxf(a, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+}
 
 template <int EPI, int PASSES>
 __global__ void __launch_bounds__(rowk::kThreads, 1)
@@ -227,14 +328,30 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
   const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   constexpr bool kLo = PASSES == 3;
 
+  // scale source of A (uniform over the whole grid; decided before any barrier so that a redo launch can leave at once)
+  unsigned int a_bits;
+  if (p.vmode == 0) {
+    a_bits = *p.a_amax;
+  } else if (p.vmode == 1) {
+    a_bits = *p.v_stale;
+  } else {
+    const bool ok = scale_window_ok(*p.v_stale, *p.v_live);
+    if (p.vmode == 2) {
+      if (ok) return;
+      a_bits = *p.v_live;
+    } else {
+      a_bits = ok ? *p.a_amax : *p.a_alt;
+      if (p.amax_publish && blockIdx.x == 0 && threadIdx.x == 0) *p.amax_publish = a_bits;
+    }
+  }
+
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSrcSlots; ++s) { mbar_init(bar(kSrcFull + s), 1); mbar_init(bar(kSrcEmpty + s), 4); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(kAFull + s), 8);     // one lane of each converter warp, both CTAs (leader's copy is the one used)
       mbar_init(bar(kAEmpty + s), 1);
-      mbar_init(bar(kBFull + s), 1);
-      mbar_init(bar(kBEmpty + s), 1);
     }
+    for (int s = 0; s < kBSlots; ++s) { mbar_init(bar(kBFull + s), 1); mbar_init(bar(kBEmpty + s), 1); }
     mbar_init(bar(kAccFull), 1);
     mbar_init(bar(kAccEmpty), 16);       // one lane of each epilogue warp, both CTAs
     fence_mbar_init();
@@ -244,36 +361,42 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     tmem_alloc_pair(smem_u32(tmem_slot), 512);
     tmem_relinquish_pair();
   }
+  if (warp == 0) HG_MARK(0);
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) HG_MARK(1);
 
   if (warp == 0) {
-    // ============================================================ TMA producer (both CTAs: own rows of A, own half of W)
+    // ============================================================ W producer (both CTAs: own half of the W rows)
     if (elect_one()) {
       uint32_t it = 0;
       for (int tile = pair_id; tile < p.n_tiles; tile += npairs) {
-        const int row0 = tile * 256 + (int)rank * 128;
         for (int c = 0; c < p.chunks; ++c, ++it) {
-          {
-            const uint32_t slot = it % kBSlots, par = (it / kBSlots) & 1;
-            mbar_wait(bar(kBEmpty + slot), par ^ 1);
-            const uint32_t fb = bar(kBFull + slot);
-            if (leader) mbar_arrive_expect_tx(fb, (kLo ? 2u : 1u) * 2u * 16384u);
-            const uint32_t sb = base + kOffB + slot * kBSlot;
-            tma_load_2d_pair(sb, &map_wh, fb, c * 64, (int)rank * 128);
-            if (kLo) tma_load_2d_pair(sb + 16384, &map_wl, fb, c * 64, (int)rank * 128);
-          }
-          {
-            const uint32_t slot = it % kSrcSlots, par = (it / kSrcSlots) & 1;
-            mbar_wait(bar(kSrcEmpty + slot), par ^ 1);
-            const uint32_t fb = bar(kSrcFull + slot);
-            mbar_arrive_expect_tx(fb, (uint32_t)kSrcSlot);
-            const uint32_t sa = base + kOffSrc + slot * kSrcSlot;
-            tma_load_2d(sa, &map_a, fb, c * 64, row0);
-            tma_load_2d(sa + 16384, &map_a, fb, c * 64 + 32, row0);
-          }
+          const uint32_t slot = it % kBSlots, par = (it / kBSlots) & 1;
+          mbar_wait(bar(kBEmpty + slot), par ^ 1);
+          const uint32_t fb = bar(kBFull + slot);
+          if (leader) mbar_arrive_expect_tx(fb, (kLo ? 2u : 1u) * 2u * 16384u);
+          const uint32_t sb = base + kOffB + slot * kBSlot;
+          tma_load_2d_pair(sb, &map_wh, fb, c * 64, (int)rank * 128);
+          if (kLo) tma_load_2d_pair(sb + 16384, &map_wl, fb, c * 64, (int)rank * 128);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 14) {
+    // ============================================================ A producer: fp32 rows of this CTA, 32-k boxes
+    if (elect_one()) {
+      uint32_t h = 0;
+      for (int tile = pair_id; tile < p.n_tiles; tile += npairs) {
+        const int row0 = tile * 256 + (int)rank * 128;
+        for (int c = 0; c < 2 * p.chunks; ++c, ++h) {
+          const uint32_t slot = h % kSrcSlots, par = (h / kSrcSlots) & 1;
+          mbar_wait(bar(kSrcEmpty + slot), par ^ 1);
+          const uint32_t fb = bar(kSrcFull + slot);
+          mbar_arrive_expect_tx(fb, (uint32_t)kSrcSlot);
+          tma_load_2d(base + kOffSrc + slot * kSrcSlot, &map_a, fb, c * 32, row0);
         }
       }
     }
@@ -286,12 +409,16 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       for (int tile = pair_id; tile < p.n_tiles; tile += npairs, ++tt) {
         mbar_wait(bar(kAccEmpty), (tt & 1) ^ 1);   // the epilogue drained the accumulator of the previous tile
         tc_fence_after();
+        if (tt < 2 && p.dbg && blockIdx.x == 0) p.dbg[2 + 4 * tt] = gtime_ns();
         for (int c = 0; c < p.chunks; ++c, ++it) {
           const uint32_t s = it & 1, par = (it >> 1) & 1;
+          const uint32_t bs = it % kBSlots, bp = (it / kBSlots) & 1;
           mbar_wait(bar(kAFull + s), par);
-          mbar_wait(bar(kBFull + s), par);
+          if (c == 0 && tt < 2 && p.dbg && blockIdx.x == 0) p.dbg[3 + 4 * tt] = gtime_ns();
+          mbar_wait(bar(kBFull + bs), bp);
+          if (c == 0 && tt < 2 && p.dbg && blockIdx.x == 0) p.dbg[4 + 4 * tt] = gtime_ns();
           tc_fence_after();
-          const uint32_t sb = base + kOffB + s * kBSlot;
+          const uint32_t sb = base + kOffB + bs * kBSlot;
           const uint64_t bh = smem_desc_sw128(sb), bl = smem_desc_sw128(sb + 16384);
           const uint32_t ah = tmem_base + kACol + s * 64, al = ah + 32;
 #pragma unroll
@@ -304,9 +431,10 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             }
           }
           mma_commit_pair(bar(kAEmpty + s), 3);
-          mma_commit_pair(bar(kBEmpty + s), 3);
+          mma_commit_pair(bar(kBEmpty + bs), 3);
         }
         mma_commit_pair(bar(kAccFull), 3);
+        if (tt < 2 && p.dbg && blockIdx.x == 0) p.dbg[5 + 4 * tt] = gtime_ns();
       }
     }
     __syncwarp();
@@ -314,97 +442,144 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     // ============================================================ converter: fp32 rows -> fp16 hi / lo in tensor memory
     const int q = warp & 3, row = q * 32 + lane;
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
-    const float s = scale_from_amax_bits(*p.a_amax);
+    const float s = scale_from_amax_bits(a_bits);
     float amax = 0.f;
     uint32_t it = 0;
     for (int tile = pair_id; tile < p.n_tiles; tile += npairs) {
       for (int c = 0; c < p.chunks; ++c, ++it) {
-        const uint32_t ss = it % kSrcSlots, sp = (it / kSrcSlots) & 1;
         const uint32_t as = it & 1, ap = (it >> 1) & 1;
-        mbar_wait(bar(kSrcFull + ss), sp);
         mbar_wait(bar(kAEmpty + as), ap ^ 1);   // the MMAs that read this TMEM stage have completed
         tc_fence_after();
-        const uint32_t sa = base + kOffSrc + ss * kSrcSlot;
         const uint32_t ta = tmem_base + lane_field + kACol + as * 64;
 #pragma unroll
         for (int bx = 0; bx < 2; ++bx) {
+          const uint32_t h = 2 * it + bx, ss = h % kSrcSlots, sp = (h / kSrcSlots) & 1;
+          mbar_wait(bar(kSrcFull + ss), sp);
           uint32_t hw[16], lw[16];
-          convert_row32<kLo>(sa + bx * 16384, row, s, hw, lw, amax);
+          convert_row32<kLo>(base + kOffSrc + ss * kSrcSlot, row, s, hw, lw, amax);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_local(bar(kSrcEmpty + ss));   // the box is in registers
           tmem_st16(ta + bx * 16, hw);
           if (kLo) tmem_st16(ta + 32 + bx * 16, lw);
         }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive_local(bar(kSrcEmpty + ss));
-          mbar_arrive_cluster(bar(kAFull + as), 0);
-        }
+        if (lane == 0) mbar_arrive_cluster(bar(kAFull + as), 0);
       }
     }
-    (void)amax;
+    if (p.vmode == 1 && p.a_live) {   // the true max |A| (rows beyond M and columns beyond K were zero-filled by TMA)
+      amax = warp_max(amax);
+      if (lane == 0 && amax > 0.f) atomicMax(p.a_live, __float_as_uint(amax));
+    }
   } else {
-    // ============================================================ epilogue: TMEM lane = row; 8 warps = 4 lane quarters x 2 column halves
+    // ============================================================ epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves
     const int we = warp - 6, q = warp & 3, hf = we >> 2;
     const int lrow = q * 32 + lane;
     const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16);
     float* const stg = reinterpret_cast<float*>(sbase + kOffStg + we * kStgBytes);
     float* const lnx = reinterpret_cast<float*>(sbase + kOffLnx);
-    const float inv = (1.f / scale_from_amax_bits(*p.a_amax)) * p.w_scale[1];
+    const float inv = (1.f / scale_from_amax_bits(a_bits)) * p.w_scale[1];
+    const int pr = lane >> 3, pc = (lane & 7) * 4;   // piece mapping: row 4 i + pr, columns pc .. pc + 3
     float amax = 0.f;
-    float colacc[4] = {0.f, 0.f, 0.f, 0.f};
+    float* const colsm = lnx + we * 128;   // kEpiGeluBwd: this warp's running column sums (its 128 columns)
+    if (EPI == kEpiGeluBwd) {
+      for (int i = lane; i < 128; i += 32) colsm[i] = 0.f;
+      __syncwarp();
+    }
     uint32_t tt = 0;
     for (int tile = pair_id; tile < p.n_tiles; tile += npairs, ++tt) {
       const int blk_row0 = tile * 256 + (int)rank * 128 + q * 32;
       const int grow = blk_row0 + lane;
       const int rows_valid = p.M - blk_row0;   // may be <= 0 or > 32
       const bool row_ok = grow < p.M;
-      mbar_wait(bar(kAccFull), tt & 1);
-      tc_fence_after();
+      // global address of this lane's piece 0 of slab 0 (column half hf) in a (M, 256) tensor
+      const size_t poff = (size_t)(blk_row0 + pr) * 256 + hf * 128 + pc;
+
       if (EPI == kEpiPlain || EPI == kEpiBiasGelu) {
+        mbar_wait(bar(kAccFull), tt & 1);
+        tc_fence_after();
+        if (we == 0 && tt < 2) HG_MARK(10 + 2 * tt);
 #pragma unroll 1
         for (int sl = 0; sl < 4; ++sl) {
           const int col0 = hf * 128 + sl * 32;
           float v[32];
           tmem_ld32(tacc + col0, v);
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + pc));
           tmem_ld_wait();
+          stg_put_rows(stg, lane, v);
+          __syncwarp();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = p.bias ? fmaf(v[e], inv, __ldg(p.bias + col0 + e)) : v[e] * inv;
-          block_store(stg, lane, v, p.out0 + (size_t)blk_row0 * 256 + col0, 256, rows_valid, 32);
-          if (EPI == kEpiBiasGelu) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              v[e] = gelu_erf(v[e]);
-              amax = fmaxf(amax, row_ok ? fabsf(v[e]) : 0.f);
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + pr;
+            float4 a = *reinterpret_cast<const float4*>(stg + r * kStgPitch + pc);
+            a.x = fmaf(a.x, inv, b4.x); a.y = fmaf(a.y, inv, b4.y); a.z = fmaf(a.z, inv, b4.z); a.w = fmaf(a.w, inv, b4.w);
+            const size_t o = poff + (size_t)(4 * i) * 256 + sl * 32;
+            if (r < rows_valid) {
+              *reinterpret_cast<float4*>(p.out0 + o) = a;
+              if (EPI == kEpiBiasGelu) {
+                const float4 g = make_float4(gelu_as(a.x), gelu_as(a.y), gelu_as(a.z), gelu_as(a.w));
+                amax = amax4(amax, g);
+                if (p.out1) *reinterpret_cast<float4*>(p.out1 + o) = g;
+              }
             }
-            if (p.out1) block_store(stg, lane, v, p.out1 + (size_t)blk_row0 * 256 + col0, 256, rows_valid, 32);
           }
+          __syncwarp();
         }
       } else if (EPI == kEpiLN) {
-        // pass 1: z = keep * (acc + bias) / (1-p) + projected, kept in TMEM (over the accumulator) for the next passes
+        // ---- pass 1 (piece mapping): z = keep * (acc + bias) / (1-p) + projected; loads issued before the accumulator is
+        // waited for and refilled for the next slab as soon as a piece has been consumed
+        float4 P[8];
+        uint32_t Kp[8];
+        auto fetch = [&](int i, int sl) {
+          const int r = 4 * i + pr;
+          const size_t o = poff + (size_t)(4 * i) * 256 + sl * 32;
+          P[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          Kp[i] = 0x01010101u;
+          if (r < rows_valid) {
+            P[i] = ld_stream(reinterpret_cast<const float4*>(p.in0 + o));
+            if (p.keep) Kp[i] = __ldg(reinterpret_cast<const unsigned int*>(p.keep + o));
+          }
+        };
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fetch(i, 0);
+        mbar_wait(bar(kAccFull), tt & 1);
+        tc_fence_after();
+        if (we == 0 && tt < 2) HG_MARK(10 + 2 * tt);
         float sum = 0.f;
 #pragma unroll 1
         for (int sl = 0; sl < 4; ++sl) {
           const int col0 = hf * 128 + sl * 32;
-          float v[32], pv[32];
+          float v[32];
           tmem_ld32(tacc + col0, v);
-          block_load(stg, lane, p.in0 + (size_t)blk_row0 * 256 + col0, 256, rows_valid, pv);
-          uint32_t kb[8] = {0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u};
-          if (p.keep && row_ok) {
-            const uint4* kp = reinterpret_cast<const uint4*>(p.keep + (size_t)grow * 256 + col0);
-            const uint4 k0 = __ldg(kp), k1 = __ldg(kp + 1);
-            kb[0] = k0.x; kb[1] = k0.y; kb[2] = k0.z; kb[3] = k0.w; kb[4] = k1.x; kb[5] = k1.y; kb[6] = k1.z; kb[7] = k1.w;
-          }
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + pc));
           tmem_ld_wait();
+          stg_put_rows(stg, lane, v);
+          __syncwarp();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            float y = fmaf(v[e], inv, __ldg(p.bias + col0 + e));
-            if (p.keep) y = ((kb[e >> 2] >> (8 * (e & 3))) & 0xffu) ? y * p.drop_scale : 0.f;
-            v[e] = y + pv[e];
-            sum += v[e];
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + pr;
+            float4 a = *reinterpret_cast<const float4*>(stg + r * kStgPitch + pc);
+            a.x = fmaf(a.x, inv, b4.x); a.y = fmaf(a.y, inv, b4.y); a.z = fmaf(a.z, inv, b4.z); a.w = fmaf(a.w, inv, b4.w);
+            if (p.keep) {
+              const uint32_t k = Kp[i];
+              a.x = (k & 0xffu) ? a.x * p.drop_scale : 0.f;
+              a.y = (k & 0xff00u) ? a.y * p.drop_scale : 0.f;
+              a.z = (k & 0xff0000u) ? a.z * p.drop_scale : 0.f;
+              a.w = (k & 0xff000000u) ? a.w * p.drop_scale : 0.f;
+            }
+            a.x += P[i].x; a.y += P[i].y; a.z += P[i].z; a.w += P[i].w;
+            *reinterpret_cast<float4*>(stg + r * kStgPitch + pc) = a;
+            if (p.out1 && r < rows_valid) *reinterpret_cast<float4*>(p.out1 + poff + (size_t)(4 * i) * 256 + sl * 32) = a;
+            if (sl < 3) fetch(i, sl + 1);
           }
-          tmem_st32f(tacc + col0, v);
-          if (p.out1) block_store(stg, lane, v, p.out1 + (size_t)blk_row0 * 256 + col0, 256, rows_valid, 32);
+          __syncwarp();
+          stg_get_rows(stg, lane, v);      // back to the row mapping: z of this lane's row
+#pragma unroll
+          for (int e = 0; e < 32; ++e) sum += v[e];
+          tmem_st32f(tacc + col0, v);      // z stays in tensor memory (over the accumulator) for the next two passes
+          __syncwarp();
         }
         tmem_st_wait();
         lnx[(0 * 2 + hf) * 128 + lrow] = sum;
@@ -427,32 +602,79 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           const int col0 = hf * 128 + sl * 32;
           float v[32];
           tmem_ld32(tacc + col0, v);
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col0 + pc));
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.beta + col0 + pc));
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = fmaf((v[e] - mean) * rstd, __ldg(p.gamma + col0 + e), __ldg(p.beta + col0 + e));
-          block_store(stg, lane, v, p.out0 + (size_t)blk_row0 * 256 + col0, 256, rows_valid, 32);
+          for (int e = 0; e < 32; ++e) v[e] = (v[e] - mean) * rstd;
+          stg_put_rows(stg, lane, v);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + pr;
+            float4 a = *reinterpret_cast<const float4*>(stg + r * kStgPitch + pc);
+            a.x = fmaf(a.x, g4.x, t4.x); a.y = fmaf(a.y, g4.y, t4.y); a.z = fmaf(a.z, g4.z, t4.z); a.w = fmaf(a.w, g4.w, t4.w);
+            if (r < rows_valid) *reinterpret_cast<float4*>(p.out0 + poff + (size_t)(4 * i) * 256 + sl * 32) = a;
+          }
+          __syncwarp();
         }
         if (hf == 0 && row_ok) {
           if (p.mean) p.mean[grow] = mean;
           if (p.rstd) p.rstd[grow] = rstd;
         }
-      } else {  // kEpiGeluBwd: dp = dh * gelu'(projected) + dz
+      } else {
+        // ---- kEpiGeluBwd (piece mapping): dp = dh * gelu'(projected) + dz, column sums of dp, max |dp|
+        float4 P[8], Dz[8];
+        auto fetch = [&](int i, int sl) {
+          const int r = 4 * i + pr;
+          const size_t o = poff + (size_t)(4 * i) * 256 + sl * 32;
+          P[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          Dz[i] = P[i];
+          if (r < rows_valid) {
+            P[i] = ld_stream(reinterpret_cast<const float4*>(p.in0 + o));
+            Dz[i] = ld_stream(reinterpret_cast<const float4*>(p.in1 + o));
+          }
+        };
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fetch(i, 0);
+        mbar_wait(bar(kAccFull), tt & 1);
+        tc_fence_after();
+        if (we == 0 && tt < 2) HG_MARK(10 + 2 * tt);
 #pragma unroll 1
         for (int sl = 0; sl < 4; ++sl) {
           const int col0 = hf * 128 + sl * 32;
-          float v[32], pv[32], dv[32];
-          tmem_ld32(tacc + col0, v);
-          block_load(stg, lane, p.in0 + (size_t)blk_row0 * 256 + col0, 256, rows_valid, pv);
-          block_load(stg, lane, p.in1 + (size_t)blk_row0 * 256 + col0, 256, rows_valid, dv);
-          tmem_ld_wait();
+          tmem_to_stg_rows(tacc + col0, stg, lane);
+          __syncwarp();
+          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            v[e] = fmaf(v[e] * inv, gelu_erf_grad(pv[e]), dv[e]);   // rows beyond M: acc = 0 and dz = 0 -> 0
-            amax = fmaxf(amax, fabsf(v[e]));
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + pr;
+            float4 a = *reinterpret_cast<const float4*>(stg + r * kStgPitch + pc);
+            a.x = fmaf(a.x * inv, gelu_grad_as(P[i].x), Dz[i].x);   // rows beyond M: acc = 0 and dz = 0 -> 0
+            a.y = fmaf(a.y * inv, gelu_grad_as(P[i].y), Dz[i].y);
+            a.z = fmaf(a.z * inv, gelu_grad_as(P[i].z), Dz[i].z);
+            a.w = fmaf(a.w * inv, gelu_grad_as(P[i].w), Dz[i].w);
+            if (r < rows_valid) *reinterpret_cast<float4*>(p.out0 + poff + (size_t)(4 * i) * 256 + sl * 32) = a;
+            amax = amax4(amax, a);
+            cs.x += a.x; cs.y += a.y; cs.z += a.z; cs.w += a.w;
+            if (sl < 3) fetch(i, sl + 1);
           }
-          colacc[sl] += block_store_colsum(stg, lane, v, p.out0 + (size_t)blk_row0 * 256 + col0, 256, rows_valid);
+          // lanes with the same (lane & 7) hold partial sums of the same four columns: fold the four row groups
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+          }
+          if (lane < 8) {
+            float4* acc4 = reinterpret_cast<float4*>(colsm + sl * 32 + pc);
+            float4 t4 = *acc4;
+            t4.x += cs.x; t4.y += cs.y; t4.z += cs.z; t4.w += cs.w;
+            *acc4 = t4;
+          }
+          __syncwarp();
         }
       }
+      if (we == 0 && tt < 2) HG_MARK(11 + 2 * tt);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(bar(kAccEmpty), 0);
@@ -462,12 +684,13 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       if (lane == 0 && amax > 0.f) atomicMax(p.out_amax, __float_as_uint(amax));
     }
     if (EPI == kEpiGeluBwd && p.colpart) {
-#pragma unroll
-      for (int sl = 0; sl < 4; ++sl)
-        p.colpart[((size_t)blockIdx.x * 4 + q) * 256 + hf * 128 + sl * 32 + lane] = colacc[sl];
+      __syncwarp();
+      for (int i = lane; i < 128; i += 32)
+        p.colpart[((size_t)blockIdx.x * 4 + q) * 256 + hf * 128 + i] = colsm[i];
     }
   }
 
+  if (warp == 0) HG_MARK(15);
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
@@ -664,14 +887,15 @@ ares_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 // ================================================================================================ transposed-operands kernel
 namespace ttk {
 constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-5 convert A -> TMEM, warps 6-9 convert B -> smem; 2-9 epilogue
-constexpr int kSrcSlot = 32768, kSrcSlots = 3;         // 32 k rows: A box [32][128 cols] fp32 + B box [32][128 cols]
+constexpr int kSrcSlot = 32768, kSrcSlots = 5;         // 32 k rows: A box [32][128 cols] fp32 + B box [32][128 cols]
 constexpr int kOpSlot = 32768;                         // B operand of one 64-k chunk: hi [128 rows][64 k] + lo
 constexpr int kOffSrc = 0;
-constexpr int kOffOp = kOffSrc + kSrcSlots * kSrcSlot; // 98304
-constexpr int kOffStg = kOffOp + 2 * kOpSlot;          // 163840
-constexpr int kOffBar = kOffStg + 8 * kStgBytes;       // 200704
+constexpr int kOffOp = kOffSrc + kSrcSlots * kSrcSlot; // 163840
+constexpr int kOffStg = kOffSrc;                       // the epilogue runs once, after the last load was consumed: it
+                                                       // stages through the (idle) source ring
+constexpr int kOffBar = kOffOp + 2 * kOpSlot;          // 229376
 constexpr int kSmem = kOffBar + 256 + 1024;
-enum Bar { kSrcFull = 0, kSrcEmpty = 3, kOpFull = 6, kOpEmpty = 8, kAccFull = 10, kNumBars = 11 };
+enum Bar { kSrcFull = 0, kSrcEmpty = 5, kOpFull = 10, kOpEmpty = 12, kAccFull = 14, kNumBars = 15 };
 constexpr uint32_t kACol = 256;
 }  // namespace ttk
 
@@ -823,15 +1047,33 @@ tt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
-// C[m][n] = sum_ks part[ks][m][n]
+// C[m][n] = sum_ks part[ks][m][n]: a block of (64 float4 columns) x (4 split groups); every thread keeps eight loads in
+// flight, the four groups meet in shared memory in a fixed order (deterministic)
 __global__ void __launch_bounds__(256) tt_reduce_kernel(const float4* __restrict__ part, int ksplit, size_t n4, int No4,
                                                         float* __restrict__ C, int64_t ldc) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    float4 a = part[i];
-    for (int k = 1; k < ksplit; ++k) {
-      const float4 b = part[(size_t)k * n4 + i];
-      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  __shared__ float4 sm[4][64];
+  const int tx = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const size_t i = (size_t)blockIdx.x * 64 + tx;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+    int k = g;
+    for (; k + 28 < ksplit; k += 32) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = ld_stream(part + (size_t)(k + 4 * u) * n4 + i);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
     }
+    for (; k < ksplit; k += 4) {
+      const float4 v = ld_stream(part + (size_t)k * n4 + i);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  }
+  sm[g][tx] = a;
+  __syncthreads();
+  if (g == 0 && i < n4) {
+#pragma unroll
+    for (int u = 1; u < 4; ++u) { const float4 v = sm[u][tx]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
     const size_t m = i / No4, n = (i % No4) * 4;
     *reinterpret_cast<float4*>(C + m * ldc + n) = a;
   }
@@ -908,7 +1150,8 @@ static int launch_row(int passes, int npairs, const CUtensorMap& ma, const CUten
 }
 
 int rows_gemm(const RowArgs& a, cudaStream_t st) {
-  MC_REQUIRE(a.A && a.a_amax && a.W.hi && a.W.lo && a.W.scale && a.out0, MC_ERR_BAD_ARG, "head rows gemm: null pointer");
+  MC_REQUIRE(a.A && (a.a_amax || a.vmode == 1 || a.vmode == 2) && a.W.hi && a.W.lo && a.W.scale && a.out0, MC_ERR_BAD_ARG,
+             "head rows gemm: null pointer");
   MC_REQUIRE(a.M > 0 && a.K > 0 && a.K % 4 == 0 && a.lda % 4 == 0, MC_ERR_UNSUPPORTED,
              "head rows gemm: K (%d) and the row stride must be multiples of 4", a.K);
   MC_REQUIRE(a.W.rows == 256 && a.W.cols == a.K, MC_ERR_BAD_ARG, "head rows gemm: weight planes are %d x %d, expected 256 x %d",
@@ -934,6 +1177,14 @@ int rows_gemm(const RowArgs& a, cudaStream_t st) {
   p.bias = a.bias; p.out0 = a.out0; p.out1 = a.out1; p.in0 = a.in0; p.in1 = a.in1; p.keep = a.keep;
   p.drop_scale = a.drop_scale; p.eps = a.eps; p.gamma = a.gamma; p.beta = a.beta; p.mean = a.mean; p.rstd = a.rstd;
   p.out_amax = a.out_amax; p.colpart = a.colpart;
+  p.vmode = a.vmode; p.a_alt = a.a_alt; p.v_stale = a.v_stale; p.v_live = a.v_live; p.a_live = a.a_live;
+  p.amax_publish = a.amax_publish;
+  MC_REQUIRE(a.vmode >= 0 && a.vmode <= 3 && (a.vmode == 0 || (a.v_stale && a.v_live)) && (a.vmode != 3 || a.a_alt) &&
+                 (a.vmode != 1 || a.a_live),
+             MC_ERR_BAD_ARG, "head rows gemm: scale protocol pointers missing for vmode %d", a.vmode);
+  p.dbg = nullptr;
+  if (const char* e = getenv("MAE_CLIP_HG_DBG"))   // tools/head_timeline.py: device address of a 16-word timeline buffer
+    p.dbg = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
   const int npairs = row_pairs(a.M);
   switch (a.epilogue) {
     case kEpiPlain: return launch_row<kEpiPlain>(a.passes, npairs, ma, wh, wl, p, st);
@@ -1029,8 +1280,7 @@ int tt_gemm(const TtArgs& a, void* ws, size_t ws_bytes, cudaStream_t st) {
     if ((rc = launch_pairs(tt_kernel<1>, npairs, ttk::kThreads, ttk::kSmem, done, st, ma, mb, p))) return rc;
   }
   const size_t n4 = (size_t)256 * a.No / 4;
-  int nb = (int)((n4 + 255) / 256);
-  if (nb > num_sms() * 4) nb = num_sms() * 4;
+  const int nb = (int)((n4 + 63) / 64);
   tt_reduce_kernel<<<nb, 256, 0, st>>>(static_cast<const float4*>(ws), t.ksplit, n4, a.No / 4, a.C, a.ldc);
   MC_LAUNCH_CHECK();
   return MC_OK;

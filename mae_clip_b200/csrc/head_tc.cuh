@@ -36,6 +36,21 @@ struct RowArgs {
   float* rstd;
   unsigned int* out_amax;     // or null
   float* colpart;             // kEpiGeluBwd: (colpart_rows(M), 256) per-warp column sums of out0, or null
+  // Scale protocol.  The fp16 planes need a power-of-two scale from max |A|; reducing it first costs a whole pass over A
+  // (45 us for the 268 MB image features).  A power-of-two scale only matters at the ends of the fp16 range, so the
+  // scale of the PREVIOUS call is as good - provided it is checked:
+  //   vmode 1  run with the previous call's max |A| (*v_stale) while the converters reduce the true one into *a_live
+  //   vmode 2  the same launch again: every CTA returns at once when *v_live was inside the safe window of *v_stale
+  //            (no fp16 overflow, lo plane not starved), else the GEMM is redone with the exact scale
+  //   vmode 3  a consumer of what those two produced: its own operand's max is *a_amax when the first attempt stood,
+  //            *a_alt when it was redone; *amax_publish receives the one chosen
+  //   vmode 0  plain: *a_amax
+  int vmode;
+  const unsigned int* a_alt;
+  const unsigned int* v_stale;
+  const unsigned int* v_live;
+  unsigned int* a_live;
+  unsigned int* amax_publish;
 };
 int colpart_rows(int M);      // rows of RowArgs::colpart for a problem with M rows
 // C-like: out(M, 256) = A(M, K) . W(256, K)^T with the epilogue fused.  K % 4 == 0.

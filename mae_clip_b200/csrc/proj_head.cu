@@ -91,10 +91,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
                                                      int B, int P, float* __restrict__ dz_out,
                                                      float* __restrict__ dy_out,
                                                      float* __restrict__ partials /*[grid][3][P]*/,
-                                                     unsigned int* __restrict__ dy_amax /* or null */) {
+                                                     unsigned int* __restrict__ dy_amax /* or null */,
+                                                     unsigned int* __restrict__ zero_words /* 64 words to clear, or null */) {
   extern __shared__ float sm[];  // [8 warps][3][P]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = P >> 2;
+  if (zero_words && blockIdx.x == 0 && threadIdx.x < 64) zero_words[threadIdx.x] = 0u;   // counters of colsum_tall_kernel
   float amx = 0.f;  // max |dy| this thread wrote: saves the staging of dy a pass over it
   float4 dg[NV], db[NV], dbf[NV], gm[NV];
 #pragma unroll
@@ -189,6 +191,48 @@ __global__ void __launch_bounds__(1024) colsum3_kernel(const float* __restrict__
   if (threadIdx.x == 0 && oc < cols) {
     float* o = oc < P ? out0 : (oc < 2 * P ? out1 : out2);
     o[oc % P] = v;
+  }
+}
+
+// Tall column sums in ONE launch, deterministic: grid (cols / 32, kColSlices).  Block (bx, by) sums its slice of the rows
+// for 32 columns into part2[by][c]; the last slice to arrive for a column group (per-group counter, zeroed by an earlier
+// kernel of the same call and re-armed here) folds the kColSlices partial rows in a fixed order.  Output column c goes
+// to out_k[c % P] with k = c / P (the three LayerNorm-backward sums share one partial buffer).
+constexpr int kColSlices = 8;
+__global__ void __launch_bounds__(1024) colsum_tall_kernel(const float* __restrict__ in, int rows, int cols, int P,
+                                                           float* __restrict__ part2, unsigned int* __restrict__ counters,
+                                                           float* __restrict__ out0, float* __restrict__ out1,
+                                                           float* __restrict__ out2) {
+  __shared__ float sm[32][33];
+  __shared__ bool last;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int per = (rows + kColSlices - 1) / kColSlices;
+  const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  float acc = 0.f;
+  if (c < cols)
+    for (int r = r0 + threadIdx.y; r < r1; r += 32) acc += in[(size_t)r * cols + c];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  float v = sm[threadIdx.x][threadIdx.y];
+  v = warp_sum(v);
+  const int oc = blockIdx.x * 32 + threadIdx.y;
+  if (threadIdx.x == 0 && oc < cols) part2[(size_t)blockIdx.y * cols + oc] = v;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const unsigned int n = atomicAdd(counters + blockIdx.x, 1u);
+    last = n == kColSlices - 1;
+    if (last) counters[blockIdx.x] = 0u;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kColSlices; ++k) t += *reinterpret_cast<volatile const float*>(part2 + (size_t)k * cols + c);
+    float* o = c < P ? out0 : (c < 2 * P ? out1 : out2);
+    o[c % P] = t;
   }
 }
 
@@ -307,10 +351,10 @@ template <int NV>
 static int launch_ln_bwd(const float* go, const float* z, const float* mean, const float* rstd,
                          const float* gamma, const uint8_t* keep, float scale, int B, int P,
                          float* dz, float* dy, float* partials, int blocks, unsigned int* dy_amax,
-                         cudaStream_t st) {
+                         cudaStream_t st, unsigned int* zero_words = nullptr) {
   size_t smem = (size_t)8 * 3 * P * sizeof(float);
   ln_bwd_kernel<NV><<<blocks, 256, smem, st>>>(go, z, mean, rstd, gamma, keep, scale, B, P, dz, dy,
-                                               partials, dy_amax);
+                                               partials, dy_amax, zero_words);
   MC_LAUNCH_CHECK();
   return MC_OK;
 }
@@ -398,8 +442,9 @@ static bool use_tc(int mode, int B) {
 // ---------------- CTA-pair path (csrc/head_tc.cu): workspace map ----------------
 // Only WEIGHTS are staged as planes here (a few MB); activations are converted inside the GEMM kernels.
 struct PairHeadWs {
-  float *hidden_tmp, *dz, *dy, *dp, *partials, *colpart;
-  unsigned int* amax;                 // [0] x, [1] hidden (when the caller passes no fwd_amax), [2] dy, [3] dp
+  float *hidden_tmp, *dz, *dy, *dp, *partials, *colpart, *part2;
+  unsigned int* counters;             // 64 words for colsum_tall_kernel (cleared by ln_bwd_kernel)
+  unsigned int* amax;                 // [0] x, [1] hidden (when the caller passes no fwd_amax), [2] dy, [3] dp; [8..11] staging sync
   tcg::Planes wp, wf, wfT, wpT;       // (P, E), (P, P), (P, P)^T, (E, P)
   void* tt_ws;
   size_t tt_ws_bytes;
@@ -421,6 +466,8 @@ static PairHeadWs pair_head_ws(void* ws, int B, int E, int P) {
   w.dp = reinterpret_cast<float*>(take(bp));
   w.partials = reinterpret_cast<float*>(take((size_t)ln_blocks(B) * 3 * P * 4));
   w.colpart = reinterpret_cast<float*>(take((size_t)hg::colpart_rows(B) * P * 4));
+  w.part2 = reinterpret_cast<float*>(take((size_t)kColSlices * 3 * P * 4));
+  w.counters = reinterpret_cast<unsigned int*>(take(256));
   w.amax = reinterpret_cast<unsigned int*>(take(256));
   w.wp = planes(P, E); w.wf = planes(P, P); w.wfT = planes(P, P); w.wpT = planes(E, P);
   size_t t1 = hg::tt_workspace_bytes(P, B), t2 = hg::tt_workspace_bytes(E, B);
@@ -477,8 +524,8 @@ size_t mc_proj_head_workspace_bytes(int B, int E, int P, int mode) {
 int mc_proj_head_fwd(const float* x, int B, int E, int P, const float* w_proj, const float* b_proj,
                      const float* w_fc, const float* b_fc, const float* gamma, const float* beta,
                      const uint8_t* keep_mask, float p_drop, float eps, int mode, float* projected,
-                     float* hidden, float* z, float* mean, float* rstd, float* out, float* fwd_amax, void* ws,
-                     size_t ws_bytes, void* stream) {
+                     float* hidden, float* z, float* mean, float* rstd, float* out, float* fwd_amax,
+                     const float* prev_amax, void* ws, size_t ws_bytes, void* stream) {
   MC_ARCH_GUARD();
   MC_REQUIRE(x && w_proj && b_proj && w_fc && b_fc && gamma && beta && projected && out && ws,
              MC_ERR_BAD_ARG, "proj_head_fwd: null pointer");
@@ -502,21 +549,39 @@ int mc_proj_head_fwd(const float* x, int B, int E, int P, const float* w_proj, c
     PairHeadWs t = pair_head_ws(ws, B, E, P);
     MC_REQUIRE(ws_bytes >= t.total, MC_ERR_WORKSPACE, "proj_head_fwd: workspace %zu < %zu", ws_bytes, t.total);
     const int passes = mode == MC_GEMM_TC_F16X3 ? 3 : 1;
-    unsigned int* amax_x = fwd_amax ? reinterpret_cast<unsigned int*>(fwd_amax) : t.amax;
-    unsigned int* amax_h = amax_x + 1;
-    if ((rc = tcg::amax(x, B, E, E, amax_x, st))) return rc;
-    MC_CUDA(cudaMemsetAsync(amax_h, 0, 4, st));
-    if ((rc = tcg::stage(w_proj, P, E, E, 0, t.wp, st))) return rc;
-    if ((rc = tcg::stage(w_fc, P, P, P, 0, t.wf, st))) return rc;
+    // four words: [0] max |x|, [1] max |hidden| (what the backward reads), [2] / [3] max |hidden| of the first attempt /
+    // of the redo (scale protocol, head_tc.cuh)
+    unsigned int* am = fwd_amax ? reinterpret_cast<unsigned int*>(fwd_amax) : t.amax;
+    const unsigned int* stale = reinterpret_cast<const unsigned int*>(prev_amax);
+    static const bool no_stale = getenv("MAE_CLIP_HEAD_STALE_SCALE") != nullptr && getenv("MAE_CLIP_HEAD_STALE_SCALE")[0] == '0';
+    if (no_stale) stale = nullptr;
+    if (stale) {
+      MC_CUDA(cudaMemsetAsync(am, 0, 16, st));
+    } else {
+      if ((rc = tcg::amax(x, B, E, E, am, st))) return rc;   // no earlier call to take the scale from: reduce max |x| first
+      MC_CUDA(cudaMemsetAsync(am + 1, 0, 12, st));
+    }
+    if ((rc = tcg::stage_pair(tcg::StageJob{w_proj, P, E, 0, t.wp}, tcg::StageJob{w_fc, P, P, 0, t.wf}, t.amax + 8, st)))
+      return rc;
     float* hid = hidden ? hidden : t.hidden_tmp;
     hg::RowArgs f1 = {};
-    f1.A = x; f1.lda = E; f1.a_amax = amax_x; f1.W = t.wp; f1.M = B; f1.K = E; f1.passes = passes;
-    f1.epilogue = hg::kEpiBiasGelu; f1.bias = b_proj; f1.out0 = projected; f1.out1 = hid; f1.out_amax = amax_h;
-    if ((rc = hg::rows_gemm(f1, st))) return rc;
+    f1.A = x; f1.lda = E; f1.a_amax = am; f1.W = t.wp; f1.M = B; f1.K = E; f1.passes = passes;
+    f1.epilogue = hg::kEpiBiasGelu; f1.bias = b_proj; f1.out0 = projected; f1.out1 = hid;
     hg::RowArgs f2 = {};
-    f2.A = hid; f2.lda = P; f2.a_amax = amax_h; f2.W = t.wf; f2.M = B; f2.K = P; f2.passes = passes;
+    f2.A = hid; f2.lda = P; f2.W = t.wf; f2.M = B; f2.K = P; f2.passes = passes;
     f2.epilogue = hg::kEpiLN; f2.bias = b_fc; f2.in0 = projected; f2.keep = keep_mask; f2.drop_scale = scale; f2.eps = eps;
     f2.gamma = gamma; f2.beta = beta; f2.out0 = out; f2.out1 = z; f2.mean = mean; f2.rstd = rstd;
+    if (stale) {
+      f1.vmode = 1; f1.v_stale = stale; f1.v_live = am; f1.a_live = am; f1.out_amax = am + 2;
+      if ((rc = hg::rows_gemm(f1, st))) return rc;
+      f1.vmode = 2; f1.a_live = nullptr; f1.out_amax = am + 3;          // leaves at once unless the stale scale was unsafe
+      if ((rc = hg::rows_gemm(f1, st))) return rc;
+      f2.vmode = 3; f2.v_stale = stale; f2.v_live = am; f2.a_amax = am + 2; f2.a_alt = am + 3; f2.amax_publish = am + 1;
+    } else {
+      f1.out_amax = am + 1;
+      if ((rc = hg::rows_gemm(f1, st))) return rc;
+      f2.a_amax = am + 1;
+    }
     return hg::rows_gemm(f2, st);
   }
   if (use_tc(mode, B)) {
@@ -591,20 +656,24 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
     }
     // LayerNorm + dropout backward: dz, dy, max |dy|, column partials of dgamma / dbeta / db_fc
     MC_DISPATCH_NV(P, (launch_ln_bwd<NV>(grad_out, z, mean, rstd, gamma, keep_mask, scale, B, P, t.dz, t.dy, t.partials,
-                                         blocks, amax_dy, st)));
+                                         blocks, amax_dy, st, t.counters)));
     if (rc) return rc;
     dim3 blk(32, 32);
-    colsum3_kernel<<<(3 * P + 31) / 32, blk, 0, st>>>(t.partials, blocks, P, dgamma, dbeta, db_fc);
+    colsum_tall_kernel<<<dim3((3 * P + 31) / 32, kColSlices), blk, 0, st>>>(t.partials, blocks, 3 * P, P, t.part2, t.counters,
+                                                                          dgamma, dbeta, db_fc);
     MC_LAUNCH_CHECK();
     // dp = (dy Wf) * gelu'(projected) + dz : the GELU backward is the epilogue of the GEMM; it also reduces max |dp|
     // and the per-warp column sums of dp (db_proj)
-    if ((rc = tcg::stage(w_fc, P, P, P, 1, t.wfT, st))) return rc;
+    // both weights, transposed, in one launch (W_p^T is only needed for dx, but staging it costs nothing extra)
+    if ((rc = tcg::stage_pair(tcg::StageJob{w_fc, P, P, 1, t.wfT}, tcg::StageJob{w_proj, P, E, 1, t.wpT}, t.amax + 8, st)))
+      return rc;
     hg::RowArgs b1 = {};
     b1.A = t.dy; b1.lda = P; b1.a_amax = amax_dy; b1.W = t.wfT; b1.M = B; b1.K = P; b1.passes = passes;
     b1.epilogue = hg::kEpiGeluBwd; b1.in0 = projected; b1.in1 = t.dz; b1.out0 = t.dp; b1.out_amax = amax_dp;
     b1.colpart = t.colpart;
     if ((rc = hg::rows_gemm(b1, st))) return rc;
-    colsum_kernel<<<(P + 31) / 32, blk, 0, st>>>(t.colpart, hg::colpart_rows(B), P, db_proj);
+    colsum_tall_kernel<<<dim3((P + 31) / 32, kColSlices), blk, 0, st>>>(t.colpart, hg::colpart_rows(B), P, P, t.part2,
+                                                                      t.counters + 32, db_proj, nullptr, nullptr);
     MC_LAUNCH_CHECK();
     // dWf = dy^T hidden, dWp = dp^T x : K is the batch; both operands are transposed inside the kernel
     hg::TtArgs g1{t.dy, P, amax_dy, hidden, P, amax_h, B, P, passes, dw_fc, P};
@@ -613,7 +682,6 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
     if ((rc = hg::tt_gemm(g2, t.tt_ws, t.tt_ws_bytes, st))) return rc;
     if (dx) {
       // dx = dp Wp : short K, the converted row block of dp stays resident in tensor memory
-      if ((rc = tcg::stage(w_proj, P, E, E, 1, t.wpT, st))) return rc;
       hg::AresArgs g3{t.dp, P, amax_dp, t.wpT, B, E, P, passes, dx, E};
       if ((rc = hg::ares_gemm(g3, st))) return rc;
     }

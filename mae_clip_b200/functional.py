@@ -142,7 +142,8 @@ def clip_contrastive_loss(image_emb, text_emb, temperature: float = 1.0, mode=No
 # ------------------------------------------------------------------------------------------------
 class _ProjHead(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w_proj, b_proj, w_fc, b_fc, gamma, beta, keep_mask, p_drop, eps, mode, grad_mode=True):
+    def forward(ctx, x, w_proj, b_proj, w_fc, b_fc, gamma, beta, keep_mask, p_drop, eps, mode, grad_mode=True,
+                scale_state=None):
         require_cuda(x, w_proj, b_proj, w_fc, b_fc, gamma, beta, keep_mask)
         lead = x.shape[:-1]
         x2 = _f32c(x.reshape(-1, x.shape[-1]))
@@ -160,16 +161,23 @@ class _ProjHead(torch.autograd.Function):
             z = torch.empty_like(projected)
             mean = torch.empty(B, device=dev, dtype=torch.float32)
             rstd = torch.empty_like(mean)
-            fwd_amax = torch.zeros(2, device=dev, dtype=torch.float32)  # max|x|, max|hidden| bit patterns for backward
         else:
-            hidden = z = mean = rstd = fwd_amax = None
+            hidden = z = mean = rstd = None
+        # max|x|, max|hidden| bit patterns (+ two internal words): read by the backward, and - through `scale_state`, a
+        # dict the calling module keeps - by the NEXT forward of the same head as the source of its operand scale
+        fwd_amax = torch.zeros(4, device=dev, dtype=torch.float32) if (need or scale_state is not None) else None
+        prev = scale_state.get("amax") if scale_state is not None else None
+        if prev is not None and (prev.device != dev or prev.numel() != 4):
+            prev = None
         with torch.cuda.device(dev):
             ws = workspace(lib().mc_proj_head_workspace_bytes(B, E, P, mode), dev)
             check(lib().mc_proj_head_fwd(ptr(x2), B, E, P, ptr(wp), ptr(bp), ptr(wf), ptr(bf), ptr(g),
                                          ptr(bt), ptr(keep_mask), float(p_drop), float(eps), mode,
                                          ptr(projected), ptr(hidden), ptr(z), ptr(mean), ptr(rstd),
-                                         ptr(out), ptr(fwd_amax), ptr(ws), ws.numel(), cur_stream()),
+                                         ptr(out), ptr(fwd_amax), ptr(prev), ptr(ws), ws.numel(), cur_stream()),
                   "mc_proj_head_fwd")
+        if scale_state is not None:
+            scale_state["amax"] = fwd_amax
         if need:
             ctx.save_for_backward(x2, wp, wf, g, keep_mask, projected, hidden, z, mean, rstd, fwd_amax)
         ctx.cfg = (B, E, P, float(p_drop), mode, lead, x.dtype)
@@ -197,14 +205,17 @@ class _ProjHead(torch.autograd.Function):
                                          cur_stream()), "mc_proj_head_bwd")
         if dx is not None:
             dx = dx.reshape(*lead, E).to(x_dtype)
-        return dx, dwp, dbp, dwf, dbf, dg, dbt, None, None, None, None, None
+        return dx, dwp, dbp, dwf, dbf, dg, dbt, None, None, None, None, None, None
 
 
 def projection_head(x, w_proj, b_proj, w_fc, b_fc, ln_weight, ln_bias, keep_mask=None,
-                    p_drop: float = 0.1, eps: float = 1e-5, mode=None):
-    """Fused ProjectionHead forward; ``keep_mask`` (0/1, shape of the output) = training mode."""
+                    p_drop: float = 0.1, eps: float = 1e-5, mode=None, scale_state=None):
+    """Fused ProjectionHead forward; ``keep_mask`` (0/1, shape of the output) = training mode.
+    ``scale_state``: an optional dict the caller keeps between calls on the same head; the forward leaves the
+    max-magnitude words of its input there and takes the operand scale of the next call from them (see
+    ``mc_proj_head_fwd`` in the header: saves a pass over ``x``; results do not depend on it)."""
     return _ProjHead.apply(x, w_proj, b_proj, w_fc, b_fc, ln_weight, ln_bias, keep_mask,
-                           float(p_drop), float(eps), _mode(mode), torch.is_grad_enabled())
+                           float(p_drop), float(eps), _mode(mode), torch.is_grad_enabled(), scale_state)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -27,6 +27,9 @@ class ProjectionHead(nn.Module):
         self.dropout = nn.Dropout(dropout)
         self.layer_norm = nn.LayerNorm(projection_dim)
         self.gemm_mode = gemm_mode
+        # not a parameter, not a buffer (state_dict keys stay those of the reference): the max-magnitude words of the
+        # last forward, from which the next one takes the power-of-two scale of its fp16 operand planes
+        self._scale_state = {}
 
     def forward(self, x, keep_mask=None):
         """``keep_mask`` lets a caller inject the dropout noise (tests: "identical inputs and
@@ -40,7 +43,7 @@ class ProjectionHead(nn.Module):
         return F_b200.projection_head(
             x, self.projection.weight, self.projection.bias, self.fc.weight, self.fc.bias,
             self.layer_norm.weight, self.layer_norm.bias, keep_mask=keep_mask, p_drop=p,
-            eps=self.layer_norm.eps, mode=self.gemm_mode or CFG.gemm_mode)
+            eps=self.layer_norm.eps, mode=self.gemm_mode or CFG.gemm_mode, scale_state=self._scale_state)
 
 
 class ImageEncoder(nn.Module):
