@@ -215,9 +215,9 @@ int mc_peer_publish(const void* src, int k, int n, int64_t src_stride, void* con
  *   z = keep*y/(1-p) + projected; out = LayerNorm(z) * gamma + beta
  * keep_mask: (B, P) bytes of 0/1 or NULL (eval mode).  projected / hidden / z /
  * mean / rstd are written for backward (all (B,P) or (B)); pass NULL for
- * hidden/z/mean/rstd under no_grad to skip the stores.  fwd_amax: optional FOUR
+ * hidden/z/mean/rstd under no_grad to skip the stores.  fwd_amax: optional EIGHT
  * device words the forward fills ([0], [1]: bit patterns of max|x|, max|hidden|; [2], [3]:
- * internal) and the backward reads, so it need not reduce them again (NULL on either side:
+ * internal; [4], [5]: max|Wp|, max|Wf|) and the backward reads, so it need not reduce them again (NULL on either side:
  * recomputed).  prev_amax: optional, the fwd_amax words of an EARLIER forward of the same
  * head.  The fp16 operand planes take a power-of-two scale from max|x|; with prev_amax the
  * scale comes from the earlier call, the true maximum is reduced while x streams through

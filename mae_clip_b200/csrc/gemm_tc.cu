@@ -555,48 +555,76 @@ __device__ __forceinline__ void stage_job_split(const StageJobDev& j, unsigned i
     }
     return;
   }
-  // transposed: dst (C rows x R cols, pitch) = src^T, 32 x 32 tiles through shared memory
+  // transposed: dst (C rows x R cols, pitch) = src^T.  A WARP owns a 32 x 32 tile: lane = source column; it reads its
+  // column of 32 source rows (32 independent coalesced loads per warp) and writes the 32 values as 64 contiguous bytes
+  // of one destination row per plane - no shared memory, no block barrier, all tiles in flight at once.
+  (void)tile;
   const int tr = (j.pitch + 31) / 32, tc = (j.C + 31) / 32;   // tiles along the source rows (incl. padding) / columns
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int t = blockIdx.x; t < tr * tc; t += gridDim.x) {
-    const int r0 = (t % tr) * 32, c0 = (t / tr) * 32;
-    __syncthreads();
-    for (int k = ty; k < 32; k += 8) {
-      const int r = r0 + k, c = c0 + tx;
-      tile[k][tx] = (r < j.R && c < j.C) ? j.src[(size_t)r * j.C + c] * s : 0.f;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (blockDim.x >> 5), w0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (int t = w0; t < tr * tc; t += nwarps) {
+    const int r0 = (t % tr) * 32, c = (t / tr) * 32 + lane;
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = (r0 + k < j.R && c < j.C) ? j.src[(size_t)(r0 + k) * j.C + c] * s : 0.f;
+    if (c >= j.C) continue;
+    uint32_t hw[16], lw[16];
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {
+      const __half h0 = __float2half_rn(v[k]), h1 = __float2half_rn(v[k + 1]);
+      const __half2 hh = __halves2half2(h0, h1);
+      const __half2 ll = __halves2half2(__float2half_rn(v[k] - __half2float(h0)), __float2half_rn(v[k + 1] - __half2float(h1)));
+      hw[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+      lw[k >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
     }
-    __syncthreads();
-    for (int k = ty; k < 32; k += 8) {
-      const int orow = c0 + k, ocol = r0 + tx;
-      if (orow < j.C && ocol < j.pitch) {
-        const float x = tile[tx][k];
-        const __half h = __float2half_rn(x);
-        j.hi[(size_t)orow * j.pitch + ocol] = h;
-        j.lo[(size_t)orow * j.pitch + ocol] = __float2half_rn(x - __half2float(h));
+    __half* ph = j.hi + (size_t)c * j.pitch + r0;
+    __half* pl = j.lo + (size_t)c * j.pitch + r0;
+    if (r0 + 32 <= j.pitch && (reinterpret_cast<uintptr_t>(ph) & 15) == 0 && (reinterpret_cast<uintptr_t>(pl) & 15) == 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        reinterpret_cast<uint4*>(ph)[u] = make_uint4(hw[4 * u], hw[4 * u + 1], hw[4 * u + 2], hw[4 * u + 3]);
+        reinterpret_cast<uint4*>(pl)[u] = make_uint4(lw[4 * u], lw[4 * u + 1], lw[4 * u + 2], lw[4 * u + 3]);
+      }
+    } else {
+      for (int k = 0; k < 32 && r0 + k < j.pitch; ++k) {
+        const uint32_t hv = hw[k >> 1], lv = lw[k >> 1];
+        const unsigned short hb = (k & 1) ? (unsigned short)(hv >> 16) : (unsigned short)(hv & 0xffffu);
+        const unsigned short lb = (k & 1) ? (unsigned short)(lv >> 16) : (unsigned short)(lv & 0xffffu);
+        reinterpret_cast<unsigned short*>(ph)[k] = hb;
+        reinterpret_cast<unsigned short*>(pl)[k] = lb;
       }
     }
   }
 }
 // every block is resident (grid <= number of SMs), so a counter barrier between the two phases is safe
-__global__ void __launch_bounds__(256) stage_pair_kernel(StageJobDev a, StageJobDev b, unsigned int* sync) {
+__global__ void __launch_bounds__(256) stage_pair_kernel(StageJobDev a, StageJobDev b, unsigned int* sync,
+                                                         const unsigned int* known, unsigned int* amax_out) {
   __shared__ float tile[32][33];
-  stage_job_amax(a, sync + 1);
-  stage_job_amax(b, sync + 2);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(sync, 1u);
-    while (*reinterpret_cast<volatile unsigned int*>(sync) < gridDim.x) __nanosleep(32);
-    __threadfence();
+  unsigned int ba, bb;
+  if (known) {   // both maxima were reduced by an earlier call on the same (unchanged) matrices: no barrier needed
+    ba = known[0];
+    bb = known[1];
+  } else {
+    stage_job_amax(a, sync + 1);
+    stage_job_amax(b, sync + 2);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(sync, 1u);
+      while (*reinterpret_cast<volatile unsigned int*>(sync) < gridDim.x) __nanosleep(20);
+      __threadfence();
+    }
+    __syncthreads();
+    ba = *reinterpret_cast<volatile unsigned int*>(sync + 1);
+    bb = *reinterpret_cast<volatile unsigned int*>(sync + 2);
+    if (amax_out && blockIdx.x == 0 && threadIdx.x == 0) { amax_out[0] = ba; amax_out[1] = bb; }
   }
-  __syncthreads();
-  const unsigned int ba = *reinterpret_cast<volatile unsigned int*>(sync + 1);
-  const unsigned int bb = *reinterpret_cast<volatile unsigned int*>(sync + 2);
   stage_job_split(a, ba, tile);
   stage_job_split(b, bb, tile);
 }
 
-int stage_pair(const StageJob& a, const StageJob& b, unsigned int* sync, cudaStream_t st) {
+int stage_pair(const StageJob& a, const StageJob& b, unsigned int* sync, cudaStream_t st, const unsigned int* known,
+               unsigned int* amax_out) {
   const StageJob* jobs[2] = {&a, &b};
   StageJobDev d[2];
   for (int k = 0; k < 2; ++k) {
@@ -606,8 +634,8 @@ int stage_pair(const StageJob& a, const StageJob& b, unsigned int* sync, cudaStr
                "stage_pair: destination planes are %d x %d", j.dst.rows, j.dst.cols);
     d[k] = StageJobDev{j.src, j.R, j.C, j.transpose, j.dst.pitch, j.dst.hi, j.dst.lo, j.dst.scale};
   }
-  MC_CUDA(cudaMemsetAsync(sync, 0, 16, st));
-  stage_pair_kernel<<<num_sms(), 256, 0, st>>>(d[0], d[1], sync);
+  if (!known) MC_CUDA(cudaMemsetAsync(sync, 0, 16, st));
+  stage_pair_kernel<<<num_sms(), 256, 0, st>>>(d[0], d[1], sync, known, amax_out);
   MC_LAUNCH_CHECK();
   return MC_OK;
 }

@@ -37,7 +37,10 @@ struct StageJob {
   int R, C, transpose;
   Planes dst;         // (R, C) planes, or (C, R) when transpose
 };
-int stage_pair(const StageJob& a, const StageJob& b, unsigned int* sync, cudaStream_t st);
+// known: two device words with the maxima of a / b when an earlier call already reduced them (then no barrier, no
+// memset); amax_out: optional two words that receive them.
+int stage_pair(const StageJob& a, const StageJob& b, unsigned int* sync, cudaStream_t st,
+               const unsigned int* known = nullptr, unsigned int* amax_out = nullptr);
 
 enum Epilogue { kEpiPlain = 0, kEpiGelu = 1 };
 

@@ -225,18 +225,26 @@ __device__ __forceinline__ void convert_col32(uint32_t box, int col, float s, ui
 // ================================================================================================ row kernel
 namespace rowk {
 constexpr int kThreads = 480;   // warp 0 W producer, warp 1 MMA, warps 2-5 converter, warps 6-13 epilogue, warp 14 A producer
-constexpr int kSrcSlot = 16384, kSrcSlots = 5;         // fp32 A: one swizzled box [128 rows][32 k]; a 64-k chunk = 2 slots
-constexpr int kBSlot = 32768, kBSlots = 3;             // W half of this CTA: hi [128 rows][64 k] + lo
+// Two shared-memory / tensor-memory plans (template flag ASMEM):
+//   long K (x Wp^T)       A in TMEM (the MMAs then read only W from shared memory: with A there too the three passes
+//                         would need more shared-memory bandwidth than an SM has), ONE accumulator: [0, 256) + A stages
+//                         at 256 + 64 s; rings: 5 source boxes, 3 W slots
+//   K <= 256 (h Wf^T, dy Wf)  these are bound by their epilogues (HBM traffic of the fused LayerNorm / GELU backward),
+//                         so the accumulator is DOUBLE-buffered ([0, 256), [256, 512)): the epilogue of a tile runs
+//                         under the loads, conversion and MMAs of the next; A goes to shared memory instead
+//                         (2 stages of hi + lo), rings: 3 source boxes, 2 W slots
+constexpr int kSrcSlot = 16384;                        // fp32 A: one swizzled box [128 rows][32 k]; a 64-k chunk = 2 slots
+constexpr int kBSlot = 32768;                          // W half of this CTA: hi [128 rows][64 k] + lo
+constexpr int kASlot = 32768;                          // ASMEM: converted A of this CTA: hi [128 rows][64 k] + lo
 constexpr int kOffSrc = 0;
-constexpr int kOffB = kOffSrc + kSrcSlots * kSrcSlot;  // 81920
-constexpr int kOffStg = kOffB + kBSlots * kBSlot;      // 180224
+constexpr int kOffStg = 180224;                        // both plans fill [0, 180224) with their rings
 constexpr int kOffLnx = kOffStg + 8 * kStgBytes;       // 217088: [2 exchanges][2 halves][128 rows] floats
 constexpr int kOffBar = kOffLnx + 8 * 128 * 4;         // 221184 (the LayerNorm exchange uses the first 2 KB; the
                                                        // GELU-backward column sums 8 warps x 128 floats)
 constexpr int kSmem = kOffBar + 256 + 1024;
-enum Bar { kSrcFull = 0, kSrcEmpty = 5, kAFull = 10, kAEmpty = 12, kBFull = 14, kBEmpty = 17, kAccFull = 20, kAccEmpty = 21,
-           kNumBars = 22 };
-constexpr uint32_t kACol = 256;       // TMEM: accumulator [0, 256), A stage s at 256 + 64 s (hi: 32 columns, lo: 32)
+enum Bar { kSrcFull = 0, kSrcEmpty = 5, kAFull = 10, kAEmpty = 12, kBFull = 14, kBEmpty = 17, kAccFull = 20, kAccEmpty = 22,
+           kNumBars = 24 };
+constexpr uint32_t kACol = 256;       // !ASMEM: A stage s at TMEM columns 256 + 64 s (hi: 32 columns, lo: 32)
 }  // namespace rowk
 
 struct RowParams {
@@ -310,7 +318,7 @@ __device__ __forceinline__ float amax4(float a, const float4 v) {
   return fmaxf(a, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
 }
 
-template <int EPI, int PASSES>
+template <int EPI, int PASSES, bool ASMEM>
 __global__ void __launch_bounds__(rowk::kThreads, 1)
 row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_wh,
            const __grid_constant__ CUtensorMap map_wl, const RowParams p) {
@@ -327,6 +335,10 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
   const bool leader = rank == 0;
   const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   constexpr bool kLo = PASSES == 3;
+  constexpr int kSrcSlots = ASMEM ? 3 : 5, kBSlots = ASMEM ? 2 : 3, kNAcc = ASMEM ? 2 : 1;
+  constexpr int kOffA = kSrcSlots * kSrcSlot;                          // ASMEM only: 2 x kASlot
+  constexpr int kOffB = ASMEM ? kOffA + 2 * kASlot : kSrcSlots * kSrcSlot;
+  static_assert(kOffB + kBSlots * kBSlot == kOffStg, "ring plan does not fill the ring region");
 
   // scale source of A (uniform over the whole grid; decided before any barrier so that a redo launch can leave at once)
   unsigned int a_bits;
@@ -352,8 +364,10 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       mbar_init(bar(kAEmpty + s), 1);
     }
     for (int s = 0; s < kBSlots; ++s) { mbar_init(bar(kBFull + s), 1); mbar_init(bar(kBEmpty + s), 1); }
-    mbar_init(bar(kAccFull), 1);
-    mbar_init(bar(kAccEmpty), 16);       // one lane of each epilogue warp, both CTAs
+    for (int b = 0; b < kNAcc; ++b) {
+      mbar_init(bar(kAccFull + b), 1);
+      mbar_init(bar(kAccEmpty + b), 16);   // one lane of each epilogue warp, both CTAs
+    }
     fence_mbar_init();
     prefetch_tmap(&map_a); prefetch_tmap(&map_wh); prefetch_tmap(&map_wl);
   }
@@ -407,8 +421,10 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       constexpr uint32_t idesc = idesc_f16(256, 256);
       uint32_t it = 0, tt = 0;
       for (int tile = pair_id; tile < p.n_tiles; tile += npairs, ++tt) {
-        mbar_wait(bar(kAccEmpty), (tt & 1) ^ 1);   // the epilogue drained the accumulator of the previous tile
+        const uint32_t buf = ASMEM ? (tt & 1) : 0u, use = ASMEM ? (tt >> 1) : tt;
+        mbar_wait(bar(kAccEmpty + buf), (use & 1) ^ 1);   // the epilogue drained this accumulator buffer
         tc_fence_after();
+        const uint32_t td = tmem_base + buf * 256;
         if (tt < 2 && p.dbg && blockIdx.x == 0) p.dbg[2 + 4 * tt] = gtime_ns();
         for (int c = 0; c < p.chunks; ++c, ++it) {
           const uint32_t s = it & 1, par = (it >> 1) & 1;
@@ -420,20 +436,34 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           tc_fence_after();
           const uint32_t sb = base + kOffB + bs * kBSlot;
           const uint64_t bh = smem_desc_sw128(sb), bl = smem_desc_sw128(sb + 16384);
-          const uint32_t ah = tmem_base + kACol + s * 64, al = ah + 32;
+          if (ASMEM) {
+            const uint32_t sa = base + kOffA + s * kASlot;
+            const uint64_t ah = smem_desc_sw128(sa), al = smem_desc_sw128(sa + 16384);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
-            mma_f16_pair_ts(tmem_base, ah + ks * 8, desc_advance_k(bh, ks), idesc, acc);
-            if (kLo) {
-              mma_f16_pair_ts(tmem_base, ah + ks * 8, desc_advance_k(bl, ks), idesc, 1u);
-              mma_f16_pair_ts(tmem_base, al + ks * 8, desc_advance_k(bh, ks), idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
+              mma_f16_pair(td, desc_advance_k(ah, ks), desc_advance_k(bh, ks), idesc, acc);
+              if (kLo) {
+                mma_f16_pair(td, desc_advance_k(ah, ks), desc_advance_k(bl, ks), idesc, 1u);
+                mma_f16_pair(td, desc_advance_k(al, ks), desc_advance_k(bh, ks), idesc, 1u);
+              }
+            }
+          } else {
+            const uint32_t ah = tmem_base + kACol + s * 64, al = ah + 32;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
+              mma_f16_pair_ts(td, ah + ks * 8, desc_advance_k(bh, ks), idesc, acc);
+              if (kLo) {
+                mma_f16_pair_ts(td, ah + ks * 8, desc_advance_k(bl, ks), idesc, 1u);
+                mma_f16_pair_ts(td, al + ks * 8, desc_advance_k(bh, ks), idesc, 1u);
+              }
             }
           }
           mma_commit_pair(bar(kAEmpty + s), 3);
           mma_commit_pair(bar(kBEmpty + bs), 3);
         }
-        mma_commit_pair(bar(kAccFull), 3);
+        mma_commit_pair(bar(kAccFull + buf), 3);
         if (tt < 2 && p.dbg && blockIdx.x == 0) p.dbg[5 + 4 * tt] = gtime_ns();
       }
     }
@@ -451,6 +481,7 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         mbar_wait(bar(kAEmpty + as), ap ^ 1);   // the MMAs that read this TMEM stage have completed
         tc_fence_after();
         const uint32_t ta = tmem_base + lane_field + kACol + as * 64;
+        const uint32_t arow = base + kOffA + as * kASlot + (uint32_t)row * 128u;
 #pragma unroll
         for (int bx = 0; bx < 2; ++bx) {
           const uint32_t h = 2 * it + bx, ss = h % kSrcSlots, sp = (h / kSrcSlots) & 1;
@@ -459,11 +490,24 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
           convert_row32<kLo>(base + kOffSrc + ss * kSrcSlot, row, s, hw, lw, amax);
           __syncwarp();
           if (lane == 0) mbar_arrive_local(bar(kSrcEmpty + ss));   // the box is in registers
-          tmem_st16(ta + bx * 16, hw);
-          if (kLo) tmem_st16(ta + 32 + bx * 16, lw);
+          if (ASMEM) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t off = (uint32_t)(((4 * bx + i) ^ (row & 7)) << 4);
+              sts128(arow + off, hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]);
+              if (kLo) sts128(arow + 16384 + off, lw[4 * i], lw[4 * i + 1], lw[4 * i + 2], lw[4 * i + 3]);
+            }
+          } else {
+            tmem_st16(ta + bx * 16, hw);
+            if (kLo) tmem_st16(ta + 32 + bx * 16, lw);
+          }
         }
-        tmem_st_wait();
-        tc_fence_before();
+        if (ASMEM) {
+          fence_proxy_async_smem();
+        } else {
+          tmem_st_wait();
+          tc_fence_before();
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(bar(kAFull + as), 0);
       }
@@ -476,7 +520,7 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     // ============================================================ epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves
     const int we = warp - 6, q = warp & 3, hf = we >> 2;
     const int lrow = q * 32 + lane;
-    const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t tacc0 = tmem_base + ((uint32_t)(q * 32) << 16);
     float* const stg = reinterpret_cast<float*>(sbase + kOffStg + we * kStgBytes);
     float* const lnx = reinterpret_cast<float*>(sbase + kOffLnx);
     const float inv = (1.f / scale_from_amax_bits(a_bits)) * p.w_scale[1];
@@ -493,11 +537,13 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       const int grow = blk_row0 + lane;
       const int rows_valid = p.M - blk_row0;   // may be <= 0 or > 32
       const bool row_ok = grow < p.M;
+      const uint32_t buf = ASMEM ? (tt & 1) : 0u, full_par = (ASMEM ? (tt >> 1) : tt) & 1;
+      const uint32_t tacc = tacc0 + buf * 256;
       // global address of this lane's piece 0 of slab 0 (column half hf) in a (M, 256) tensor
       const size_t poff = (size_t)(blk_row0 + pr) * 256 + hf * 128 + pc;
 
       if (EPI == kEpiPlain || EPI == kEpiBiasGelu) {
-        mbar_wait(bar(kAccFull), tt & 1);
+        mbar_wait(bar(kAccFull + buf), full_par);
         tc_fence_after();
         if (we == 0 && tt < 2) HG_MARK(10 + 2 * tt);
 #pragma unroll 1
@@ -544,7 +590,7 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         };
 #pragma unroll
         for (int i = 0; i < 8; ++i) fetch(i, 0);
-        mbar_wait(bar(kAccFull), tt & 1);
+        mbar_wait(bar(kAccFull + buf), full_par);
         tc_fence_after();
         if (we == 0 && tt < 2) HG_MARK(10 + 2 * tt);
         float sum = 0.f;
@@ -637,7 +683,7 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         };
 #pragma unroll
         for (int i = 0; i < 8; ++i) fetch(i, 0);
-        mbar_wait(bar(kAccFull), tt & 1);
+        mbar_wait(bar(kAccFull + buf), full_par);
         tc_fence_after();
         if (we == 0 && tt < 2) HG_MARK(10 + 2 * tt);
 #pragma unroll 1
@@ -677,7 +723,7 @@ row_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
       if (we == 0 && tt < 2) HG_MARK(11 + 2 * tt);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(bar(kAccEmpty), 0);
+      if (lane == 0) mbar_arrive_cluster(bar(kAccEmpty + buf), 0);
     }
     if ((EPI == kEpiBiasGelu || EPI == kEpiGeluBwd) && p.out_amax) {
       amax = warp_max(amax);
@@ -719,6 +765,33 @@ struct AresParams {
   int64_t ldc;
 };
 
+// Work split of the resident kernel.  A job = (row block, range of column tiles).  Every pair first takes ONE whole row
+// block; the column tiles of the remaining row blocks are dealt out evenly in tile units (a pair then converts part
+// of a row block it shares with a neighbour), so that 128 row blocks on 74 pairs cost 1.73 blocks of time, not 2.
+struct AresJobs {
+  int n_row_blocks, n_col_tiles, npairs, pair_id;
+  int stage;     // 0: the whole row block `pair_id`; >= 1: segments of the remainder
+  long cur, end;
+  __device__ AresJobs(int nrb, int nct, int np, int pid) : n_row_blocks(nrb), n_col_tiles(nct), npairs(np), pair_id(pid), stage(0) {
+    const long rem = (long)max(nrb - np, 0) * nct;
+    cur = rem * pid / np;
+    end = rem * (pid + 1) / np;
+  }
+  __device__ bool next(int& rb, int& nt0, int& nt1) {
+    if (stage == 0) {
+      stage = 1;
+      if (pair_id < n_row_blocks) { rb = pair_id; nt0 = 0; nt1 = n_col_tiles; return true; }
+    }
+    if (cur >= end) return false;
+    rb = npairs + (int)(cur / n_col_tiles);
+    nt0 = (int)(cur % n_col_tiles);
+    const long take = min((long)(n_col_tiles - nt0), end - cur);
+    nt1 = nt0 + (int)take;
+    cur += take;
+    return true;
+  }
+};
+
 template <int PASSES>
 __global__ void __launch_bounds__(aresk::kThreads, 1)
 ares_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_wh,
@@ -758,7 +831,9 @@ ares_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   if (warp == 0) {
     if (elect_one()) {
       uint32_t is = 0, ib = 0;
-      for (int rb = pair_id; rb < p.n_row_blocks; rb += npairs) {
+      AresJobs jobs(p.n_row_blocks, p.n_col_tiles, npairs, pair_id);
+      int rb, nt0, nt1;
+      while (jobs.next(rb, nt0, nt1)) {
         const int row0 = rb * 256 + (int)rank * 128;
         for (int c = 0; c < p.chunks; ++c, ++is) {
           const uint32_t slot = is % kSrcSlots, par = (is / kSrcSlots) & 1;
@@ -769,7 +844,7 @@ ares_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           tma_load_2d(sa, &map_a, fb, c * 64, row0);
           tma_load_2d(sa + 16384, &map_a, fb, c * 64 + 32, row0);
         }
-        for (int nt = 0; nt < p.n_col_tiles; ++nt) {
+        for (int nt = nt0; nt < nt1; ++nt) {
           const int wrow = nt * 128 + (int)rank * 64;
           for (int c = 0; c < p.chunks; ++c, ++ib) {
             const uint32_t slot = ib % kBSlots, par = (ib / kBSlots) & 1;
@@ -788,14 +863,16 @@ ares_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if (leader && elect_one()) {
       constexpr uint32_t idesc = idesc_f16(256, 128);
       uint32_t ib = 0, tn = 0, nb = 0;
-      for (int rb = pair_id; rb < p.n_row_blocks; rb += npairs, ++nb) {
-        for (int nt = 0; nt < p.n_col_tiles; ++nt, ++tn) {
+      AresJobs jobs(p.n_row_blocks, p.n_col_tiles, npairs, pair_id);
+      int rb, nt0, nt1;
+      for (; jobs.next(rb, nt0, nt1); ++nb) {
+        for (int nt = nt0; nt < nt1; ++nt, ++tn) {
           const uint32_t buf = tn & 1, use = tn >> 1;
           mbar_wait(bar(kAccEmpty + buf), (use & 1) ^ 1);
           tc_fence_after();
           const uint32_t td = tmem_base + buf * 128;
           for (int c = 0; c < p.chunks; ++c, ++ib) {
-            if (nt == 0) mbar_wait(bar(kAFull + c), nb & 1);   // this row block's chunk c is in tensor memory
+            if (nt == nt0) mbar_wait(bar(kAFull + c), nb & 1);   // this job's chunk c is in tensor memory
             const uint32_t slot = ib % kBSlots, par = (ib / kBSlots) & 1;
             mbar_wait(bar(kBFull + slot), par);
             tc_fence_after();
@@ -825,7 +902,9 @@ ares_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const float s = scale_from_amax_bits(*p.a_amax);
     float amax = 0.f;
     uint32_t is = 0, nb = 0;
-    for (int rb = pair_id; rb < p.n_row_blocks; rb += npairs, ++nb) {
+    AresJobs jobs(p.n_row_blocks, p.n_col_tiles, npairs, pair_id);
+    int rb, nt0, nt1;
+    for (; jobs.next(rb, nt0, nt1); ++nb) {
       mbar_wait(bar(kAFree), (nb & 1) ^ 1);
       tc_fence_after();
       for (int c = 0; c < p.chunks; ++c, ++is) {
@@ -856,10 +935,12 @@ ares_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     float* const stg = reinterpret_cast<float*>(sbase + kOffStg + we * kStgBytes);
     const float inv = (1.f / scale_from_amax_bits(*p.a_amax)) * p.w_scale[1];
     uint32_t tn = 0;
-    for (int rb = pair_id; rb < p.n_row_blocks; rb += npairs) {
+    AresJobs jobs(p.n_row_blocks, p.n_col_tiles, npairs, pair_id);
+    int rb, nt0, nt1;
+    while (jobs.next(rb, nt0, nt1)) {
       const int blk_row0 = rb * 256 + (int)rank * 128 + q * 32;
       const int rows_valid = p.M - blk_row0;
-      for (int nt = 0; nt < p.n_col_tiles; ++nt, ++tn) {
+      for (int nt = nt0; nt < nt1; ++nt, ++tn) {
         const uint32_t buf = tn & 1, use = tn >> 1;
         mbar_wait(bar(kAccFull + buf), use & 1);
         tc_fence_after();
@@ -1141,12 +1222,22 @@ int colpart_rows(int M) { return 2 * row_pairs(M) * 4; }
 template <int EPI>
 static int launch_row(int passes, int npairs, const CUtensorMap& ma, const CUtensorMap& wh, const CUtensorMap& wl,
                       const RowParams& p, cudaStream_t st) {
+  // K <= 256: the epilogue-bound plan (A in shared memory, two accumulators); longer K: A in tensor memory
+  const bool asmem = p.K <= 256;
   if (passes == 3) {
+    if (asmem) {
+      static std::atomic<unsigned long long> done{0};
+      return launch_pairs(row_kernel<EPI, 3, true>, npairs, rowk::kThreads, rowk::kSmem, done, st, ma, wh, wl, p);
+    }
     static std::atomic<unsigned long long> done{0};
-    return launch_pairs(row_kernel<EPI, 3>, npairs, rowk::kThreads, rowk::kSmem, done, st, ma, wh, wl, p);
+    return launch_pairs(row_kernel<EPI, 3, false>, npairs, rowk::kThreads, rowk::kSmem, done, st, ma, wh, wl, p);
+  }
+  if (asmem) {
+    static std::atomic<unsigned long long> done{0};
+    return launch_pairs(row_kernel<EPI, 1, true>, npairs, rowk::kThreads, rowk::kSmem, done, st, ma, wh, wl, p);
   }
   static std::atomic<unsigned long long> done{0};
-  return launch_pairs(row_kernel<EPI, 1>, npairs, rowk::kThreads, rowk::kSmem, done, st, ma, wh, wl, p);
+  return launch_pairs(row_kernel<EPI, 1, false>, npairs, rowk::kThreads, rowk::kSmem, done, st, ma, wh, wl, p);
 }
 
 int rows_gemm(const RowArgs& a, cudaStream_t st) {

@@ -150,10 +150,6 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
       }
     }
   }
-  if (dy_amax) {
-    amx = warp_max(amx);
-    if (lane == 0 && amx > 0.f) atomicMax(dy_amax, __float_as_uint(amx));
-  }
   // block-level column partials
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -170,6 +166,18 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
 #pragma unroll
     for (int w = 0; w < 8; ++w) acc += sm[w * 3 * P + i];
     partials[(size_t)blockIdx.x * 3 * P + i] = acc;
+  }
+  if (dy_amax) {   // one atomic per block, not per warp: same-address atomics serialise in L2
+    amx = warp_max(amx);
+    __syncthreads();
+    if (lane == 0) sm[warp] = amx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = sm[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) a = fmaxf(a, sm[w]);
+      if (a > 0.f) atomicMax(dy_amax, __float_as_uint(a));
+    }
   }
 }
 
@@ -313,7 +321,9 @@ __global__ void __launch_bounds__(256) gelu_bwd_add_kernel(float* __restrict__ d
 
 static int ln_blocks(int B) {
   int nb = (B + 7) / 8;
-  int cap = num_sms() * 8;  // 8 resident blocks per SM keep enough 16-byte loads in flight
+  // ln_bwd_kernel keeps 77 registers per thread: three 256-thread blocks fit an SM.  One resident wave of grid-stride
+  // blocks (a larger grid ran 2.7 waves with a partly filled last one) - and fewer partial rows to fold afterwards.
+  int cap = num_sms() * 3;
   return nb < cap ? nb : cap;
 }
 
@@ -561,7 +571,9 @@ int mc_proj_head_fwd(const float* x, int B, int E, int P, const float* w_proj, c
       if ((rc = tcg::amax(x, B, E, E, am, st))) return rc;   // no earlier call to take the scale from: reduce max |x| first
       MC_CUDA(cudaMemsetAsync(am + 1, 0, 12, st));
     }
-    if ((rc = tcg::stage_pair(tcg::StageJob{w_proj, P, E, 0, t.wp}, tcg::StageJob{w_fc, P, P, 0, t.wf}, t.amax + 8, st)))
+    // words [4], [5] of fwd_amax: max |Wp|, max |Wf| for the backward's (transposed) staging of the same weights
+    if ((rc = tcg::stage_pair(tcg::StageJob{w_proj, P, E, 0, t.wp}, tcg::StageJob{w_fc, P, P, 0, t.wf}, t.amax + 8, st, nullptr,
+                              am + 4)))
       return rc;
     float* hid = hidden ? hidden : t.hidden_tmp;
     hg::RowArgs f1 = {};
@@ -665,7 +677,9 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
     // dp = (dy Wf) * gelu'(projected) + dz : the GELU backward is the epilogue of the GEMM; it also reduces max |dp|
     // and the per-warp column sums of dp (db_proj)
     // both weights, transposed, in one launch (W_p^T is only needed for dx, but staging it costs nothing extra)
-    if ((rc = tcg::stage_pair(tcg::StageJob{w_fc, P, P, 1, t.wfT}, tcg::StageJob{w_proj, P, E, 1, t.wpT}, t.amax + 8, st)))
+    // (the forward left max |Wp|, max |Wf| in words [4], [5] of fwd_amax: no reduction, no grid barrier here)
+    if ((rc = tcg::stage_pair(tcg::StageJob{w_proj, P, E, 1, t.wpT}, tcg::StageJob{w_fc, P, P, 1, t.wfT}, t.amax + 8, st,
+                              fwd_amax ? reinterpret_cast<const unsigned int*>(fwd_amax) + 4 : nullptr)))
       return rc;
     hg::RowArgs b1 = {};
     b1.A = t.dy; b1.lda = P; b1.a_amax = amax_dy; b1.W = t.wfT; b1.M = B; b1.K = P; b1.passes = passes;
@@ -676,13 +690,15 @@ int mc_proj_head_bwd(const float* grad_out, const float* x, int B, int E, int P,
                                                                       t.counters + 32, db_proj, nullptr, nullptr);
     MC_LAUNCH_CHECK();
     // dWf = dy^T hidden, dWp = dp^T x : K is the batch; both operands are transposed inside the kernel
+    static const int big_passes_env = getenv("MAE_CLIP_HEAD_BWD_PASSES") ? atoi(getenv("MAE_CLIP_HEAD_BWD_PASSES")) : 0;
+    const int big_passes = (big_passes_env == 1 || big_passes_env == 3) ? big_passes_env : passes;
     hg::TtArgs g1{t.dy, P, amax_dy, hidden, P, amax_h, B, P, passes, dw_fc, P};
     if ((rc = hg::tt_gemm(g1, t.tt_ws, t.tt_ws_bytes, st))) return rc;
-    hg::TtArgs g2{t.dp, P, amax_dp, x, E, amax_x, B, E, passes, dw_proj, E};
+    hg::TtArgs g2{t.dp, P, amax_dp, x, E, amax_x, B, E, big_passes, dw_proj, E};
     if ((rc = hg::tt_gemm(g2, t.tt_ws, t.tt_ws_bytes, st))) return rc;
     if (dx) {
       // dx = dp Wp : short K, the converted row block of dp stays resident in tensor memory
-      hg::AresArgs g3{t.dp, P, amax_dp, t.wpT, B, E, P, passes, dx, E};
+      hg::AresArgs g3{t.dp, P, amax_dp, t.wpT, B, E, P, big_passes, dx, E};
       if ((rc = hg::ares_gemm(g3, st))) return rc;
     }
     return MC_OK;

@@ -165,9 +165,9 @@ class _ProjHead(torch.autograd.Function):
             hidden = z = mean = rstd = None
         # max|x|, max|hidden| bit patterns (+ two internal words): read by the backward, and - through `scale_state`, a
         # dict the calling module keeps - by the NEXT forward of the same head as the source of its operand scale
-        fwd_amax = torch.zeros(4, device=dev, dtype=torch.float32) if (need or scale_state is not None) else None
+        fwd_amax = torch.empty(8, device=dev, dtype=torch.float32) if (need or scale_state is not None) else None  # the C side initialises what it reads
         prev = scale_state.get("amax") if scale_state is not None else None
-        if prev is not None and (prev.device != dev or prev.numel() != 4):
+        if prev is not None and (prev.device != dev or prev.numel() != 8):
             prev = None
         with torch.cuda.device(dev):
             ws = workspace(lib().mc_proj_head_workspace_bytes(B, E, P, mode), dev)
