@@ -22,6 +22,8 @@
 //     dT_i and dI_i (64 x D each per CTA) in TMEM for the whole job;
 //   * tile flags (PairParams::flags / flags_out): tiles that cannot hold soft-target mass (P_ij < 2^-44 throughout)
 //     skip their Z work in every sweep - see DESIGN.md section 4.1.
+#include <stdlib.h>
+
 #include "clip_loss.cuh"
 #include "tc_ptx.cuh"
 
@@ -85,6 +87,10 @@ struct PairParams {
   uint8_t* flags_out;
   const uint8_t* flags;
   const float *norm_i, *norm_t;        // ||I_i||, ||T_i|| of ALL rows (statistics sweep: Z_ii lower-bounds rz_i)
+  // Statistics sweep, column partials (see "column LSE" below): when set, the transposed strip S^T is NOT computed; each
+  // epilogue warp writes the log-sum-exp of its 32 rows for each of its 32 columns, log2 units, to
+  // colpart[(strip row / 32) * Bp + column]; mc::tc::colpart_merge folds them into c.
+  float* colpart;
 };
 constexpr float kFlagTheta2 = 44.f;
 constexpr float kProbeMargin2 = 2.f;  // slack on top of the probe's worst-case rounding bound (see zmargin2)    // log2 units: dropped terms are below 2^-44 of their row's soft-target mass
@@ -450,7 +456,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                     const uint64_t kI = desc_advance_k(aI, ks), kT = desc_advance_k(aT, ks);
                     const uint64_t kb = desc_advance_k(bT, ks), kbl = desc_advance_k(bTl, ks);
                     if (do_s) {
-                      if (PHASE != kRowLoss && PHASE != kStatsZ) {
+                      if (PHASE != kRowLoss && PHASE != kStatsZ && !(PHASE == kStats && p.colpart)) {
                         mma_f16_pair(tSt, kI, kb, idesc_tile, acc);                    // St = I_i T_j^T
                         mma_f16_pair(tSt, kI, kbl, idesc_tile, 1u);
                         mma_f16_pair(tSt, desc_advance_k(aIl, ks), kb, idesc_tile, 1u);
@@ -477,7 +483,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                   const uint64_t kbI = desc_advance_k(bI, ks), kbT = desc_advance_k(bT, ks);
                   if (do_s && PHASE != kRowLoss) {
                     mma_f16_pair(tS, kT, kbI, idesc_tile, acc);
-                    if (PHASE != kStatsZ) mma_f16_pair(tSt, kI, kbT, idesc_tile, acc);
+                    if (PHASE != kStatsZ && !(PHASE == kStats && p.colpart)) mma_f16_pair(tSt, kI, kbT, idesc_tile, acc);
                   }
                   if (do_z && zf) {
                     mma_f16_pair(tZ, kI, kbI, idesc_tile, acc);
@@ -624,7 +630,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         // handed back to the tensor cores before any arithmetic starts
         float vs[32], vt[32], vz[32];
         if (PHASE != kRowLoss) tmem_ld32(tS, vs);
-        if (PHASE != kRowLoss && PHASE != kStatsZ) tmem_ld32(tSt, vt);
+        const bool colpart = PHASE == kStats && p.colpart != nullptr;
+        if (PHASE != kRowLoss && PHASE != kStatsZ && !colpart) tmem_ld32(tSt, vt);
         if (zf) tmem_ld32(tZ, vz);   // a tile without soft-target mass has no Z accumulator at all
         tmem_ld_wait();
         tc_fence_before();
@@ -694,7 +701,55 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           }
           if (PHASE == kStats) {
             lse_add32(vs, cS2, mS, sS);
-            lse_add32(vt, cS2, mSt, sSt);
+            if (!colpart) {
+              lse_add32(vt, cS2, mSt, sSt);
+            } else {
+              // ---- column LSE without the transposed strip.  This warp holds a 32 x 32 block (lane = row, vs[c] =
+              // column jl0 + c).  (1) column maxima by a transpose-reduce: five exchange steps, each halves the values
+              // a lane keeps (lane bit set -> upper half), after which lane l owns column l; (2) every lane fetches all
+              // 32 maxima through shared memory; (3) exponentials against the column's OWN maximum (exact, no reference
+              // shared with other columns can underflow); (4) the same transpose-reduce with a sum; lane l writes
+              // max_l + log2(sum_l).  Rows beyond the strip count as -inf.
+              float a[32];
+#pragma unroll
+              for (int e = 0; e < 32; ++e) a[e] = row_ok ? vs[e] : -INFINITY;
+#pragma unroll
+              for (int s = 16; s >= 1; s >>= 1) {
+                const bool up = (lane & s) != 0;
+#pragma unroll
+                for (int k = 0; k < s; ++k) {
+                  const float keep = up ? a[k + s] : a[k], send = up ? a[k] : a[k + s];
+                  a[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, s));
+                }
+              }
+              float* cmx = consts + (warp - 4) * 32;   // the column constants are not used by this phase
+              __syncwarp();
+              cmx[lane] = a[0];
+              __syncwarp();
+              const float cm_own = a[0];
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float4 c4 = *reinterpret_cast<const float4*>(cmx + e);
+                const float cmv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float ref = cmv[u] == -INFINITY ? 0.f : cmv[u];
+                  a[e + u] = row_ok ? ex2f((vs[e + u] - ref) * cS2) : 0.f;
+                }
+              }
+#pragma unroll
+              for (int s = 16; s >= 1; s >>= 1) {
+                const bool up = (lane & s) != 0;
+#pragma unroll
+                for (int k = 0; k < s; ++k) {
+                  const float keep = up ? a[k + s] : a[k], send = up ? a[k] : a[k + s];
+                  a[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                }
+              }
+              const int g32 = (rb * 128 + (int)rank * kRowsCta + (quarter & 1) * 32) >> 5;   // 32-row group of the strip
+              p.colpart[(size_t)g32 * p.Bp + (size_t)t * kTileN + jl0 + lane] =
+                  cm_own == -INFINITY ? -INFINITY : fmaf(cm_own, cS2, lg2f(a[0]));
+            }
           }
         } else if (PHASE == kRowLoss) {
           if (ragged) {
@@ -893,6 +948,7 @@ __global__ void __launch_bounds__(256) stats_finalize_kernel(const float2* __res
   if (i >= b) return;
   float* outs[3] = {r, c, rz};
   for (int k = 0; k < 3; ++k) {
+    if (outs[k] == nullptr) continue;   // c comes from the column partials (colpart_merge_kernel)
     OnlineLse2 l;
     l.init();
     float a = 0.f;  // k == 2: sum_j e^{Z_ij - max} S_ij, merged with the same rescaling as the Z sum
@@ -906,6 +962,46 @@ __global__ void __launch_bounds__(256) stats_finalize_kernel(const float2* __res
     }
     outs[k][i] = (l.m + log2f(l.s)) * kLn2;
     if (k == 2) ps[i] = a / l.s;
+  }
+}
+
+// Column LSE from the per-32-row partials of the statistics sweep: c_j = ln2 * log2 sum_g 2^{part[g][j]}.
+// A block owns 64 columns; its four thread groups take every fourth row group (eight loads in flight per thread) and
+// meet in shared memory in a fixed order.
+__global__ void __launch_bounds__(256) colpart_merge_kernel(const float* __restrict__ part, int groups, int Bp, int B,
+                                                            float* __restrict__ c) {
+  __shared__ float sm_m[4][64], sm_s[4][64];
+  const int tx = threadIdx.x & 63, g0 = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + tx;
+  OnlineLse2 l;
+  l.init();
+  if (j < B) {
+    int g = g0;
+    for (; g + 28 < groups; g += 32) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = part[(size_t)(g + 4 * u) * Bp + j];
+      float mx = v[0];
+#pragma unroll
+      for (int u = 1; u < 8; ++u) mx = fmaxf(mx, v[u]);
+      const float mn = fmaxf(l.m, mx);
+      if (mn != -INFINITY) {
+        float acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += ex2f(v[u] - mn);
+        l.s = l.s * ex2f(l.m - mn) + acc;
+        l.m = mn;
+      }
+    }
+    for (; g < groups; g += 4) l.merge(part[(size_t)g * Bp + j], 1.f);
+  }
+  sm_m[g0][tx] = l.m;
+  sm_s[g0][tx] = l.s;
+  __syncthreads();
+  if (g0 == 0 && j < B) {
+#pragma unroll
+    for (int u = 1; u < 4; ++u) l.merge(sm_m[u][tx], sm_s[u][tx]);
+    c[j] = (l.m + log2f(l.s)) * kLn2;
   }
 }
 
@@ -1100,14 +1196,36 @@ static Split choose_split(int b, int B) {
 
 size_t planes_bytes(int B, int D, int /*mode*/) { return supported(D) ? planes_layout(B, D).total : 0; }
 
+// Column LSE of S.  Two forms (SURVEY section 7 hard part c):
+//   transposed strip  the statistics sweep also computes S^T-strip = I_i T_j^T (3 more tensor-core passes per tile)
+//                     and takes its row LSE: c of the OWNED rows, nothing to merge
+//   column partials   no transposed strip: every epilogue warp reduces its 32 x 32 block along the rows with two
+//                     transpose-reduces in registers (exact: exponentials against each column's own maximum) and writes
+//                     one log-sum-exp per column and 32-row group; colpart_merge_kernel folds the (b / 32) x B partials.
+// Measured at B = 32768 (profiles/r02_*): statistics sweep 3.19 -> see DESIGN.  The partials describe ALL columns over
+// the OWNED rows, so under row sharding they would have to be merged across ranks; they are used when one call owns
+// every row (b == B: the single-GPU step); MAE_CLIP_COLPART=0 keeps the transposed strip (A/B switch).
+static bool use_colpart(int b, int B) {
+  static const bool off = getenv("MAE_CLIP_COLPART") != nullptr && getenv("MAE_CLIP_COLPART")[0] == '0';
+  return !off && b == B;
+}
+static size_t colpart_bytes(int b, int B) {
+  if (!use_colpart(b, B)) return 0;
+  Split s = choose_split(b, B);
+  return round_up((size_t)(s.bpad / 32) * round_up((size_t)B, 128) * sizeof(float), 256);
+}
+
 size_t workspace_bytes(int b, int B, int D, int /*mode*/) {
   Split s = choose_split(b, B);
   size_t stats = (size_t)s.nsplit * 4 * s.bpad * sizeof(float2);
   size_t bwdp = (size_t)s.nsplit * 2 * s.bpad * D * sizeof(float);
-  return round_up(stats > bwdp ? stats : bwdp, 256) + 256;  // + the weight-scale slot
+  return round_up(stats > bwdp ? stats : bwdp, 256) + 256 + colpart_bytes(b, B);  // + the weight-scale slot + column partials
+}
+static float* colpart_slot(void* ws, int b, int B, int D) {
+  return reinterpret_cast<float*>(static_cast<char*>(ws) + workspace_bytes(b, B, D, 0) - colpart_bytes(b, B));
 }
 static float* wscale_slot(void* ws, int b, int B, int D) {
-  return reinterpret_cast<float*>(static_cast<char*>(ws) + workspace_bytes(b, B, D, 0) - 256);
+  return reinterpret_cast<float*>(static_cast<char*>(ws) + workspace_bytes(b, B, D, 0) - colpart_bytes(b, B) - 256);
 }
 
 
@@ -1378,7 +1496,7 @@ int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row
 
 template <int PHASE, int PASSES>
 static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float* ps_loc, float* part,
-                       const float* wscale, cudaStream_t st) {
+                       const float* wscale, cudaStream_t st, float* colpart = nullptr) {
   MC_REQUIRE(supported(p.D), MC_ERR_UNSUPPORTED, "tcgen05 engine needs D in {128, 256} (got %d)", p.D);
   MC_REQUIRE(p.row_offset % 128 == 0, MC_ERR_UNSUPPORTED, "tcgen05 engine needs row_offset %% 128 == 0 (got %d)",
              p.row_offset);
@@ -1412,6 +1530,7 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float*
   pp.flags = (PHASE == kStatsZ) ? p.tile_flags_out : (PHASE != kStats ? p.tile_flags : nullptr);  // kStatsZ: the probe's raw flags
   pp.norm_i = reinterpret_cast<const float*>(base + l.off_norm_i);
   pp.norm_t = reinterpret_cast<const float*>(base + l.off_norm_t);
+  pp.colpart = (PHASE == kStats) ? colpart : nullptr;
 
   auto kern = pair_kernel<PHASE, PASSES>;
   static std::atomic<unsigned long long> attr_done{0};  // per template instantiation, one bit per device
@@ -1438,9 +1557,9 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float*
 
 template <int PHASE>
 static int launch_phase(int mode, const ClipProblem& p, const ClipStatsAll& s, const float* ps_loc, float* part,
-                        const float* wscale, cudaStream_t st) {
-  if (mode == MC_GEMM_TC_F16X3) return launch_pair<PHASE, 3>(p, s, ps_loc, part, wscale, st);
-  return launch_pair<PHASE, 1>(p, s, ps_loc, part, wscale, st);
+                        const float* wscale, cudaStream_t st, float* colpart = nullptr) {
+  if (mode == MC_GEMM_TC_F16X3) return launch_pair<PHASE, 3>(p, s, ps_loc, part, wscale, st, colpart);
+  return launch_pair<PHASE, 1>(p, s, ps_loc, part, wscale, st, colpart);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1478,15 +1597,22 @@ int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_
              ws_bytes, workspace_bytes(p.b, p.B, p.D, mode));
   ClipStatsAll none{nullptr, nullptr, nullptr, nullptr, nullptr};
   if (p.tile_flags_out) MC_CUDA(cudaMemsetAsync(p.tile_flags_out, 0, tile_flags_bytes(p.b, p.B), st));
-  int rc = launch_phase<kStats>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st);
+  float* colpart = use_colpart(p.b, p.B) ? colpart_slot(ws, p.b, p.B, p.D) : nullptr;
+  int rc = launch_phase<kStats>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st, colpart);
   if (rc) return rc;
   // with tile flags the sweep above was the probe form (S, S^T exact, Z from the hi planes -> flags); the exact Z and
   // sum_j P_ij S_ij follow on the flagged tiles only
   if (p.tile_flags_out && (rc = launch_phase<kStatsZ>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st))) return rc;
   Split sp = choose_split(p.b, p.B);
   stats_finalize_kernel<<<(p.b + 255) / 256, 256, 0, st>>>(static_cast<const float2*>(ws), sp.nsplit, sp.bpad, p.b,
-                                                          r_loc, c_loc, rz_loc, ps_loc);
+                                                          r_loc, colpart ? nullptr : c_loc, rz_loc, ps_loc);
   MC_LAUNCH_CHECK();
+  if (colpart) {
+    // rows b .. bpad of the last row block wrote -inf partials; b == B here, so c_loc covers every column
+    const int Bp = (int)round_up((size_t)p.B, 128);
+    colpart_merge_kernel<<<(p.B + 63) / 64, 256, 0, st>>>(colpart, sp.bpad / 32, Bp, p.B, c_loc);
+    MC_LAUNCH_CHECK();
+  }
   return MC_OK;
 }
 
