@@ -150,6 +150,22 @@ int mc_clip_stats(const float* I_all, const float* T_all, const void* planes_all
                   int D, int row_offset, float tau, int mode, float* row_lse_s_loc,
                   float* col_lse_s_loc, float* row_lse_z_loc, float* row_ps_loc,
                   uint8_t* tile_flags_loc_out, void* ws, size_t ws_bytes, void* stream);
+/* Column-partials form of the statistics sweep (tcgen05 engines).  mc_clip_stats obtains the column LSE of S for the
+ * owned indices from a second, transposed strip of logits (3 more tensor-core passes per tile).  Here the transposed
+ * strip is not computed: every epilogue warp reduces its 32 x 32 block of S along the rows in registers (exact:
+ * exponentials against each column's own maximum) and the sweep returns, for EVERY column j of the global batch,
+ *     col_lse_part_all[j] = log sum_{i in the owned rows} exp(S_ij)            (B floats).
+ * The ranks exchange these vectors and mc_clip_colpart_merge folds them: col_lse_all[j] = log sum_q exp(parts[q][j])
+ * (parts: n_parts vectors, `stride` floats apart).  With b == B mc_clip_stats uses this form by itself
+ * (MAE_CLIP_COLPART=0 restores the transposed strip). */
+size_t mc_clip_stats_colpart_workspace_bytes(int b, int B, int D, int mode);
+int mc_clip_stats_colpart(const void* planes_all, int b, int B, int D, int row_offset, float tau, int mode,
+                          float* row_lse_s_loc, float* col_lse_part_all, float* row_lse_z_loc,
+                          float* row_ps_loc, uint8_t* tile_flags_loc_out, void* ws, size_t ws_bytes,
+                          void* stream);
+int mc_clip_colpart_merge(const float* parts, int n_parts, int64_t stride, int B, float* col_lse_all,
+                          void* stream);
+
 int mc_clip_rowloss(const float* I_all, const float* T_all, const void* planes_all, int b, int B,
                     int D, int row_offset, float tau, int mode, const float* row_lse_s_all,
                     const float* col_lse_s_all, const float* row_lse_z_all, const float* row_ps_loc,

@@ -50,6 +50,9 @@ SIGNATURES = {
     "mc_clip_tile_flags_bytes": (_sz, [_i, _i, _i, _i]),
     "mc_clip_flags_finalize": (_i, [_p, _i, _i, _i, _p, _p]),
     "mc_clip_stats": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mc_clip_stats_colpart_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "mc_clip_stats_colpart": (_i, [_p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mc_clip_colpart_merge": (_i, [_p, _i, _i64, _i, _p, _p]),
     "mc_clip_rowloss": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mc_clip_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
                          _p]),

@@ -136,6 +136,31 @@ int mc_clip_stats(const float* I_all, const float* T_all, const void* planes_all
   return tc::stats(p, mode, r_loc, c_loc, rz_loc, ps_loc, ws, ws_bytes, st);
 }
 
+size_t mc_clip_stats_colpart_workspace_bytes(int b, int B, int D, int mode) {
+  if (b <= 0 || B <= 0 || D <= 0 || eff_mode(mode, D) == MC_GEMM_SIMT_FP32) return 0;
+  return tc::stats_colpart_workspace_bytes(b, B, D, mode);
+}
+
+int mc_clip_stats_colpart(const void* planes_all, int b, int B, int D, int row_offset, float tau, int mode,
+                          float* r_loc, float* c_part_all, float* rz_loc, float* ps_loc, uint8_t* tile_flags_out,
+                          void* ws, size_t ws_bytes, void* stream) {
+  MC_ARCH_GUARD();
+  int rc = check_problem("clip_stats_colpart", nullptr, nullptr, b, B, D, row_offset, tau, mode);
+  if (rc) return rc;
+  MC_REQUIRE(eff_mode(mode, D) != MC_GEMM_SIMT_FP32, MC_ERR_UNSUPPORTED,
+             "clip_stats_colpart: the column-partials form belongs to the tcgen05 engines (mode %d, D %d)", mode, D);
+  MC_REQUIRE(planes_all && r_loc && c_part_all && rz_loc && ps_loc && ws, MC_ERR_BAD_ARG, "clip_stats_colpart: null pointer");
+  ClipProblem p{nullptr, nullptr, planes_all, b, B, D, row_offset, tau};
+  p.tile_flags_out = tile_flags_out;
+  return tc::stats(p, mode, r_loc, nullptr, rz_loc, ps_loc, ws, ws_bytes, static_cast<cudaStream_t>(stream), c_part_all);
+}
+
+int mc_clip_colpart_merge(const float* parts, int n_parts, int64_t stride, int B, float* col_lse_all, void* stream) {
+  MC_ARCH_GUARD();
+  MC_REQUIRE(parts && col_lse_all && n_parts > 0 && B > 0 && stride >= B, MC_ERR_BAD_ARG, "clip_colpart_merge: bad argument");
+  return tc::ranks_lse_merge(parts, n_parts, stride, B, col_lse_all, static_cast<cudaStream_t>(stream));
+}
+
 int mc_clip_rowloss(const float* I_all, const float* T_all, const void* planes_all, int b, int B,
                     int D, int row_offset, float tau, int mode, const float* r_all,
                     const float* c_all, const float* rz_all, const float* ps_loc, float* g_loc,

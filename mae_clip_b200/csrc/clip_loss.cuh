@@ -49,7 +49,9 @@ int prepare_peers(const float* const* I_peers, const float* const* T_peers, int 
 size_t tile_flags_bytes(int b, int B);   // [row blocks of b][column tiles of B] bytes
 int flags_finalize(const uint8_t* flags_all, int B, int b, int row_offset, uint8_t* flags_loc, cudaStream_t st);
 int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
-          size_t ws_bytes, cudaStream_t st);
+          size_t ws_bytes, cudaStream_t st, float* c_part_all = nullptr);
+size_t stats_colpart_workspace_bytes(int b, int B, int D, int mode);
+int ranks_lse_merge(const float* parts, int n, int64_t stride, int B, float* c, cudaStream_t st);
 int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* ps_loc, float* g_loc,
             float* q_loc, float* loss_part, void* ws, size_t ws_bytes, cudaStream_t st);
 int bwd(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, float* dI,

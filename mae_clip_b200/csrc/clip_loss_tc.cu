@@ -1005,6 +1005,24 @@ __global__ void __launch_bounds__(256) colpart_merge_kernel(const float* __restr
   }
 }
 
+// c_j = log sum_q exp(part_q[j]): the ranks' column-LSE vectors (each over that rank's rows) -> the column LSE of S
+__global__ void __launch_bounds__(256) ranks_lse_merge_kernel(const float* __restrict__ parts, int n, int64_t stride, int B,
+                                                              float* __restrict__ c) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= B) return;
+  float m = -INFINITY;
+  for (int q = 0; q < n; ++q) m = fmaxf(m, parts[(size_t)q * stride + j]);
+  float s = 0.f;
+  if (m != -INFINITY)
+    for (int q = 0; q < n; ++q) s += __expf(parts[(size_t)q * stride + j] - m);
+  c[j] = m == -INFINITY ? -INFINITY : m + __logf(s);
+}
+int ranks_lse_merge(const float* parts, int n, int64_t stride, int B, float* c, cudaStream_t st) {
+  ranks_lse_merge_kernel<<<(B + 255) / 256, 256, 0, st>>>(parts, n, stride, B, c);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
 // g_i = (r_i + sum_j P_ij c_j - 2 sum_j P_ij S_ij) / 2B ; q_i = colsum(P)_i
 __global__ void __launch_bounds__(256) rowloss_finalize_kernel(const float* __restrict__ part, int nsplit,
                                                                int bpad, int b, float inv_2B,
@@ -1209,10 +1227,14 @@ static bool use_colpart(int b, int B) {
   static const bool off = getenv("MAE_CLIP_COLPART") != nullptr && getenv("MAE_CLIP_COLPART")[0] == '0';
   return !off && b == B;
 }
-static size_t colpart_bytes(int b, int B) {
-  if (!use_colpart(b, B)) return 0;
+static size_t colpart_bytes(int b, int B, bool forced = false) {
+  if (!forced && !use_colpart(b, B)) return 0;
   Split s = choose_split(b, B);
   return round_up((size_t)(s.bpad / 32) * round_up((size_t)B, 128) * sizeof(float), 256);
+}
+// workspace of the sharded column-partials form (stats with c_part_all): the phase partials + the (b / 32) x B partials
+size_t stats_colpart_workspace_bytes(int b, int B, int D, int mode) {
+  return workspace_bytes(b, B, D, mode) - colpart_bytes(b, B) + colpart_bytes(b, B, true);
 }
 
 size_t workspace_bytes(int b, int B, int D, int /*mode*/) {
@@ -1591,13 +1613,21 @@ int flags_finalize(const uint8_t* flags_all, int B, int b, int row_offset, uint8
   return MC_OK;
 }
 
+// c_part_all (optional, B floats): the column-partials form under row sharding - receives LSE_{i in the owned rows} S_ij
+// for EVERY column j (natural log); c_loc is then not written and the caller merges the ranks' vectors (ranks_lse_merge)
 int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
-          size_t ws_bytes, cudaStream_t st) {
-  MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_stats(tc): workspace %zu < %zu",
-             ws_bytes, workspace_bytes(p.b, p.B, p.D, mode));
+          size_t ws_bytes, cudaStream_t st, float* c_part_all) {
+  const size_t need = c_part_all ? stats_colpart_workspace_bytes(p.b, p.B, p.D, mode) : workspace_bytes(p.b, p.B, p.D, mode);
+  MC_REQUIRE(ws_bytes >= need, MC_ERR_WORKSPACE, "clip_stats(tc): workspace %zu < %zu", ws_bytes, need);
   ClipStatsAll none{nullptr, nullptr, nullptr, nullptr, nullptr};
   if (p.tile_flags_out) MC_CUDA(cudaMemsetAsync(p.tile_flags_out, 0, tile_flags_bytes(p.b, p.B), st));
-  float* colpart = use_colpart(p.b, p.B) ? colpart_slot(ws, p.b, p.B, p.D) : nullptr;
+  float* colpart = nullptr;
+  if (c_part_all) {
+    colpart = reinterpret_cast<float*>(static_cast<char*>(ws) + workspace_bytes(p.b, p.B, p.D, mode) - colpart_bytes(p.b, p.B));
+    c_loc = c_part_all;
+  } else if (use_colpart(p.b, p.B)) {
+    colpart = colpart_slot(ws, p.b, p.B, p.D);
+  }
   int rc = launch_phase<kStats>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st, colpart);
   if (rc) return rc;
   // with tile flags the sweep above was the probe form (S, S^T exact, Z from the hi planes -> flags); the exact Z and
@@ -1608,7 +1638,7 @@ int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_
                                                           r_loc, colpart ? nullptr : c_loc, rz_loc, ps_loc);
   MC_LAUNCH_CHECK();
   if (colpart) {
-    // rows b .. bpad of the last row block wrote -inf partials; b == B here, so c_loc covers every column
+    // rows b .. bpad of the last row block wrote -inf partials; c_loc has B entries here (every column, over the owned rows)
     const int Bp = (int)round_up((size_t)p.B, 128);
     colpart_merge_kernel<<<(p.B + 63) / 64, 256, 0, st>>>(colpart, sp.bpad / 32, Bp, p.B, c_loc);
     MC_LAUNCH_CHECK();

@@ -218,6 +218,9 @@ class PeerStep:
             raise ValueError("the peer transport feeds the tcgen05 engines (D in {128, 256}); use transport='nccl'")
         if exchange.b % 128:
             raise ValueError(f"tcgen05 engine: rows per rank must be a multiple of 128 (got {exchange.b})")
+        # column LSE of S from column partials (no transposed strip in the statistics sweep; the ranks exchange one
+        # B-vector each and merge) - MAE_CLIP_COLPART=0 keeps the transposed strip
+        self.colpart = os.environ.get("MAE_CLIP_COLPART", "1") != "0"
 
     def forward(self, I_loc, T_loc, tau, events=None):
         ex, mode, L = self.ex, self.mode, lib()
@@ -253,16 +256,29 @@ class PeerStep:
             check(L.mc_clip_prepare_peers(tab_i, tab_t, world, b, D, mode, ex.local(ex.OFF_AMAX_SLOTS), ptr(planes), st),
                   "mc_clip_prepare_peers")
             mark()
-            ws = workspace(L.mc_clip_loss_workspace_bytes(b, B, D, mode), dev)
+            nws = max(L.mc_clip_loss_workspace_bytes(b, B, D, mode),
+                      L.mc_clip_stats_colpart_workspace_bytes(b, B, D, mode) if self.colpart else 0)
+            ws = workspace(nws, dev)
             loc = torch.empty(6, b, **f32)  # r, c, rz, sum_j P_ij S_ij, g, q of the owned rows
             nf = self.flag_bytes
             flags_raw = torch.empty(nf, device=dev, dtype=torch.uint8) if nf else None
-            check(L.mc_clip_stats(None, None, ptr(planes), b, B, D, rank * b, float(tau), mode, ptr(loc[0]), ptr(loc[1]),
-                                  ptr(loc[2]), ptr(loc[3]), ptr(flags_raw), ptr(ws), ws.numel(), st), "mc_clip_stats")
-            ex.publish(ptr(loc), 3, b, b, ex.OFF_VECS, ex.vec_stride, rank * b)
+            if self.colpart:
+                cpart = torch.empty(B, **f32)   # LSE over OUR rows of every column of S
+                check(L.mc_clip_stats_colpart(ptr(planes), b, B, D, rank * b, float(tau), mode, ptr(loc[0]), ptr(cpart),
+                                              ptr(loc[2]), ptr(loc[3]), ptr(flags_raw), ptr(ws), ws.numel(), st),
+                      "mc_clip_stats_colpart")
+                ex.publish(ptr(loc[0]), 2, b, 2 * b, ex.OFF_VECS, 2 * ex.vec_stride, rank * b)   # r -> vector 0, rz -> vector 2
+                ex.publish(ptr(cpart), 1, B, 0, ex.off_cpart, 0, rank * ex.vec_stride)
+            else:
+                check(L.mc_clip_stats(None, None, ptr(planes), b, B, D, rank * b, float(tau), mode, ptr(loc[0]), ptr(loc[1]),
+                                      ptr(loc[2]), ptr(loc[3]), ptr(flags_raw), ptr(ws), ws.numel(), st), "mc_clip_stats")
+                ex.publish(ptr(loc), 3, b, b, ex.OFF_VECS, ex.vec_stride, rank * b)
             if nf:  # this rank's rows of the tile-flag bitmap, to every rank
                 ex.publish(ptr(flags_raw), 1, nf // 4, 0, ex.off_flags, 0, rank * (nf // 4))
             ex.barrier()
+            if self.colpart:   # every rank's partial vector has landed: fold them into c (the region's local c vector)
+                check(L.mc_clip_colpart_merge(ex.local(ex.off_cpart), world, ex.vec_stride, B, ex.vec(1), st),
+                      "mc_clip_colpart_merge")
             flags = None
             if nf:
                 flags = torch.empty(nf, device=dev, dtype=torch.uint8)

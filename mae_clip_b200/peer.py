@@ -17,7 +17,7 @@ definition, the reference loss (``CLIP.py:34-43``) on the concatenated batch.
 Region layout (bytes): [0, 64) barrier flags | [256, 320) amax slots | [512, 576) loss-partial slots | 576 private
 barrier epoch, 580 barrier error word (0 = fine, 1 + q = "rank q never arrived within the timeout"; next to the
 partials so that one copy brings both out) | 768 local amax, 772 local loss partial, 784 push scratch (2 words) | 1024.. five length-B vectors
-(r, c, rz, g, q) | the [B/128][B/128]-byte tile-flag bitmap | then two (B, D) fp32 images of the global batch (image / text embeddings): in
+(r, c, rz, g, q) | the [B/128][B/128]-byte tile-flag bitmap | [world] column-LSE partial vectors of B floats | then two (B, D) fp32 images of the global batch (image / text embeddings): in
 "pull" mode each rank fills only its own rows and peers read them from there; in "push" mode every
 rank stores its rows into all ranks' images and the staging reads locally.
 
@@ -93,8 +93,10 @@ class PeerExchange:
         # tile-flag bitmap of the whole batch ([B/128][B/128] bytes; every rank pushes its row blocks)
         self.off_flags = _round_up(self.OFF_VECS + 5 * self.vec_stride * 4, 256)
         nt = (self.B + 127) // 128
+        # column-LSE partials of every rank: [world][vec_stride] floats (rank q's vector over ITS rows, all B columns)
+        self.off_cpart = _round_up(self.off_flags + nt * nt, 256)
         # (B, D) fp32 images of the global batch: pull mode uses only the owner's rows of each
-        self.off_emb_i = _round_up(self.off_flags + nt * nt, 256)
+        self.off_emb_i = _round_up(self.off_cpart + self.world * self.vec_stride * 4, 256)
         self.off_emb_t = self.off_emb_i + _round_up(self.B * D * 4, 256)
         self.nbytes = self.off_emb_t + _round_up(self.B * D * 4, 256)
         self.ptrs = [0] * self.world
