@@ -409,7 +409,15 @@ def run_b200(args):
     # library, no collective-library call) is captured ONCE in a CUDA graph and replayed: at 4096 rows per rank the step
     # is ~1.2 ms and the per-launch gaps were a fifth of it.  The peer barrier keeps its epoch in device memory for this.
     graph, launches_per_step = None, None
+    phase_ms_eager = [0.0] * 4
     if transport == "peer" and os.environ.get("MAE_CLIP_BENCH_GRAPH", "1") != "0":
+        for _ in range(args.steps):            # per-phase times from eager steps (events cannot sit inside the replayed graph)
+            flush.fill_(1)
+            barrier()
+            one_step(record=True)
+            barrier()
+            for i, v in enumerate(ph.phase_ms()):
+                phase_ms_eager[i] += v
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -456,13 +464,7 @@ def run_b200(args):
     launches = lib.mc_kernel_launch_count() - launches0
     if graph is not None:
         launches = launches_per_step * args.steps
-        for _ in range(args.steps):            # per-phase times from eager steps (events cannot sit inside the replayed graph)
-            flush.fill_(1)
-            barrier()
-            one_step(record=True)
-            barrier()
-            for i, v in enumerate(ph.phase_ms()):
-                phase_ms[i] += v
+        phase_ms = phase_ms_eager
     loss_val = float(ph.part.item())
     tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
