@@ -1191,7 +1191,13 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t col
 struct Split {
   int n_row_blocks, n_tiles, nsplit, tiles_per_split, bpad;
 };
-static Split choose_split(int b, int B) {
+// Per-job overhead of a sweep, in tiles (fitted to the 4096-row strip of B = 32768, tools/strip_sweep.py: the gradient
+// sweep pays the load of its resident rows, the pipeline fill of its weight tiles and the read-out of 2 x 64 x D
+// accumulators per job, and every extra split adds a set of partial gradients to fold: 0.578 ms with 16 splits, 0.505
+// with 2; the statistics sweep is cheap per job)
+constexpr double kOvhStats = 1.5, kOvhRowLoss = 0.5, kOvhBwd = 6.0;
+template <int PHASE> constexpr double phase_ovh() { return PHASE == kBwd ? kOvhBwd : (PHASE == kRowLoss ? kOvhRowLoss : kOvhStats); }
+static Split choose_split(int b, int B, double ovh = kOvhRowLoss) {
   Split s;
   s.n_row_blocks = (b + 127) / 128;
   s.bpad = s.n_row_blocks * 128;
@@ -1204,9 +1210,11 @@ static Split choose_split(int b, int B) {
     const int tps = (s.n_tiles + ns - 1) / ns;
     const long jobs = (long)s.n_row_blocks * ns;
     const long rounds = (jobs + npairs - 1) / npairs;
-    const double cost = (double)rounds * (tps + 0.5) + 0.02 * ns;  // 0.5 tile of per-job overhead
+    const double cost = (double)rounds * (tps + ovh) + 0.02 * ns;
     if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
   }
+  static const int forced = getenv("MAE_CLIP_NSPLIT") ? atoi(getenv("MAE_CLIP_NSPLIT")) : 0;   // experiments only
+  if (forced >= 1 && forced <= max_split) best = forced;
   s.nsplit = best;
   s.tiles_per_split = (s.n_tiles + best - 1) / best;
   return s;
@@ -1238,9 +1246,9 @@ size_t stats_colpart_workspace_bytes(int b, int B, int D, int mode) {
 }
 
 size_t workspace_bytes(int b, int B, int D, int /*mode*/) {
-  Split s = choose_split(b, B);
-  size_t stats = (size_t)s.nsplit * 4 * s.bpad * sizeof(float2);
-  size_t bwdp = (size_t)s.nsplit * 2 * s.bpad * D * sizeof(float);
+  Split s = choose_split(b, B, kOvhStats), sr = choose_split(b, B, kOvhRowLoss), sb = choose_split(b, B, kOvhBwd);
+  size_t stats = (size_t)(s.nsplit > sr.nsplit ? s.nsplit : sr.nsplit) * 4 * s.bpad * sizeof(float2);
+  size_t bwdp = (size_t)sb.nsplit * 2 * s.bpad * D * sizeof(float);
   return round_up(stats > bwdp ? stats : bwdp, 256) + 256 + colpart_bytes(b, B);  // + the weight-scale slot + column partials
 }
 static float* colpart_slot(void* ws, int b, int B, int D) {
@@ -1537,7 +1545,7 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float*
   if ((rc = make_map(&mb_lo, Xl, l.Bp, 2 * p.D, 32))) return rc;
   if ((rc = make_map(&mt, XhT, 2 * p.D, l.Bp, p.D / 2))) return rc;
 
-  Split sp = choose_split(p.b, p.B);
+  Split sp = choose_split(p.b, p.B, phase_ovh<PHASE>());
   PairParams pp;
   pp.b = p.b; pp.B = p.B; pp.Bp = l.Bp; pp.D = p.D; pp.row_offset = p.row_offset;
   pp.n_row_blocks = sp.n_row_blocks; pp.n_tiles = sp.n_tiles; pp.nsplit = sp.nsplit;
@@ -1633,7 +1641,7 @@ int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_
   // with tile flags the sweep above was the probe form (S, S^T exact, Z from the hi planes -> flags); the exact Z and
   // sum_j P_ij S_ij follow on the flagged tiles only
   if (p.tile_flags_out && (rc = launch_phase<kStatsZ>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st))) return rc;
-  Split sp = choose_split(p.b, p.B);
+  Split sp = choose_split(p.b, p.B, kOvhStats);
   stats_finalize_kernel<<<(p.b + 255) / 256, 256, 0, st>>>(static_cast<const float2*>(ws), sp.nsplit, sp.bpad, p.b,
                                                           r_loc, colpart ? nullptr : c_loc, rz_loc, ps_loc);
   MC_LAUNCH_CHECK();
@@ -1651,7 +1659,7 @@ int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* 
   MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_rowloss(tc): workspace too small");
   int rc = launch_phase<kRowLoss>(mode, p, s, ps_loc, static_cast<float*>(ws), nullptr, st);
   if (rc) return rc;
-  Split sp = choose_split(p.b, p.B);
+  Split sp = choose_split(p.b, p.B, kOvhRowLoss);
   rowloss_finalize_kernel<<<(p.b + 255) / 256, 256, 0, st>>>(static_cast<const float*>(ws), sp.nsplit, sp.bpad, p.b,
                                                             0.5f / (float)p.B, s.r + p.row_offset, ps_loc, g_loc, q_loc);
   MC_LAUNCH_CHECK();
@@ -1674,7 +1682,7 @@ int bwd(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad
   MC_LAUNCH_CHECK();
   int rc = launch_phase<kBwd>(mode, p, s, nullptr, static_cast<float*>(ws), wsc, st);
   if (rc) return rc;
-  Split sp = choose_split(p.b, p.B);
+  Split sp = choose_split(p.b, p.B, kOvhBwd);
   size_t n4 = (size_t)p.b * p.D / 4;
   int blocks = (int)((n4 + 255) / 256);
   int cap = num_sms() * 8;
