@@ -330,6 +330,15 @@ int mc_similarity_topk(const float* text, int Q, const float* image, long long N
                        float* out_vals, int64_t* out_idx, float* scores_out, void* ws,
                        size_t ws_bytes, void* stream);
 
+/* Token side of the data feed (dataset.py:19-31): the reference tokenises all captions once, padded to one length L, and
+ * builds torch.tensor(values[idx]) per sample for input_ids / attention_mask (stacked by the default collate).  Here the
+ * (N, L) int64 tables stay resident in HBM and a batch is a gather of rows by the sampler's n indices (negative indices
+ * wrap like python's).  An index outside [-N, N) sets *bad_index_flag (device int, cleared by the caller) and yields a
+ * row of zeros - the reference raises IndexError; mae_clip_b200/data.py turns the flag into one. */
+int mc_gather_token_rows(const int64_t* ids_all, const int64_t* mask_all, int64_t N, int L,
+                         const int64_t* idx, int n, int64_t* ids_out, int64_t* mask_out,
+                         int* bad_index_flag, void* stream);
+
 /* "next" row 4: image side of the data feed        dataset.py:33-34,49 (A.Normalize + permute + float)
  * hwc: (N, H, W, 3) uint8 DEVICE pixels (after the reference's cv2 resize, which stays on the host);
  * out_nchw: (N, 3, H, W) fp32 = (pixel - mean*max_pixel_value) * (1 / (std*max_pixel_value)).

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
@@ -43,10 +44,21 @@ void count_launch();
     MC_CUDA(cudaGetLastError());   \
   } while (0)
 
-#define MC_ARCH_GUARD()            \
-  do {                             \
-    int a_ = ::mc::arch_check();   \
-    if (a_ != MC_OK) return a_;    \
+// Every compute entry point of the C ABI opens with this: the sm_100 check, and an NVTX range named after the entry
+// point for the duration of the call (tracing row of SURVEY section 5: `nsys` shows the phases of a step by name,
+// `ncu --nvtx --nvtx-include "mc_clip_bwd/"` profiles the kernels of one phase; header-only NVTX v3, a no-op load of a
+// function pointer when no tool is attached).
+struct NvtxScope {
+  explicit NvtxScope(const char* name) { nvtxRangePushA(name); }
+  ~NvtxScope() { nvtxRangePop(); }
+  NvtxScope(const NvtxScope&) = delete;
+  NvtxScope& operator=(const NvtxScope&) = delete;
+};
+#define MC_ARCH_GUARD()                        \
+  ::mc::NvtxScope mc_nvtx_scope_(__func__);    \
+  do {                                         \
+    int a_ = ::mc::arch_check();               \
+    if (a_ != MC_OK) return a_;                \
   } while (0)
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }

@@ -51,7 +51,56 @@ __global__ void __launch_bounds__(256) normalize_hwc_scalar_kernel(const uint8_t
   }
 }
 
+// ---- token side of the feed (dataset.py:19-31).  The reference tokenises the whole caption list once in the dataset's
+// constructor (`tokenizer(list(captions), padding=True, truncation=True, max_length=...)`: every row padded to ONE
+// length L) and then, per sample, builds `torch.tensor(values[idx])` for input_ids / attention_mask, which the default
+// collate stacks into (n, L) int64 tensors.  Here the tokenised corpus stays RESIDENT in HBM (N x L int64 per key: 128 MB
+// for 40 k captions of 200 tokens) and a batch is one gather of rows by the sampler's indices - no per-sample host
+// work, no per-step H2D besides the n indices.  One warp per (row, key); 16-byte vectors when L is even.
+__global__ void __launch_bounds__(256) gather_token_rows_kernel(const long long* __restrict__ ids_all,
+                                                                const long long* __restrict__ mask_all, long long N, int L,
+                                                                const long long* __restrict__ idx, int n,
+                                                                long long* __restrict__ ids_out,
+                                                                long long* __restrict__ mask_out, int* __restrict__ bad) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= 2 * n) return;
+  const int row = w >> 1, key = w & 1;
+  long long src = idx[row];
+  if (src < 0) src += N;                 // python-style negative indices, as values[idx] accepts them
+  if (src < 0 || src >= N) {             // out of range: the reference raises IndexError; flag it, write zeros
+    if (lane == 0) atomicExch(bad, 1);
+    src = -1;
+  }
+  const long long* s = (key ? mask_all : ids_all) + (src < 0 ? 0 : src * L);
+  long long* d = (key ? mask_out : ids_out) + (long long)row * L;
+  if ((L & 1) == 0 && ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+    for (int i = lane; i < L / 2; i += 32) {
+      uint4 v = src < 0 ? make_uint4(0, 0, 0, 0) : reinterpret_cast<const uint4*>(s)[i];
+      reinterpret_cast<uint4*>(d)[i] = v;
+    }
+  } else {
+    for (int i = lane; i < L; i += 32) d[i] = src < 0 ? 0 : s[i];
+  }
+}
+
 }  // namespace mc
+
+extern "C" int mc_gather_token_rows(const int64_t* ids_all, const int64_t* mask_all, int64_t N, int L,
+                                    const int64_t* idx, int n, int64_t* ids_out, int64_t* mask_out,
+                                    int* bad_index_flag, void* stream) {
+  using namespace mc;
+  MC_ARCH_GUARD();
+  MC_REQUIRE(ids_all && mask_all && idx && ids_out && mask_out && bad_index_flag, MC_ERR_BAD_ARG, "gather_token_rows: null pointer");
+  MC_REQUIRE(N > 0 && L > 0 && n >= 0, MC_ERR_BAD_ARG, "gather_token_rows: bad sizes N=%lld L=%d n=%d", (long long)N, L, n);
+  if (n == 0) return MC_OK;
+  const int warps = 2 * n, blocks = (warps + 7) / 8;
+  gather_token_rows_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids_all), reinterpret_cast<const long long*>(mask_all), (long long)N, L,
+      reinterpret_cast<const long long*>(idx), n, reinterpret_cast<long long*>(ids_out),
+      reinterpret_cast<long long*>(mask_out), bad_index_flag);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
 
 extern "C" int mc_normalize_images(const uint8_t* hwc, int N, int H, int W, const float* mean3_host,
                                    const float* std3_host, float max_pixel_value, float* out_nchw, void* stream) {

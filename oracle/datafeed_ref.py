@@ -23,3 +23,15 @@ def normalize_ref(img_hwc_uint8: np.ndarray, mean=MEAN, std=STD, max_pixel_value
     img -= mean
     img *= denominator
     return np.moveaxis(img, -1, -3).copy()     # permute(2, 0, 1)
+
+
+def token_batch_ref(encoded_captions, indices):
+    """Caption half of ``/root/reference/dataset.py:25-28`` followed by the default collate: per index
+    ``{key: torch.tensor(values[idx])}``, stacked -> ``{key: (n, L) int64 array}`` (numpy restatement; python-style
+    negative indices, IndexError outside the range - exactly what ``values[idx]`` on a list does)."""
+    out = {}
+    for key in ("input_ids", "attention_mask"):
+        values = encoded_captions[key]
+        rows = [np.asarray(values[int(i)], dtype=np.int64) for i in indices]
+        out[key] = np.stack(rows) if rows else np.zeros((0, len(values[0])), dtype=np.int64)
+    return out

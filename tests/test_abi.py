@@ -112,3 +112,22 @@ def test_reference_state_dict_loads(golden):
     keys = ["projection.weight", "projection.bias", "fc.weight", "fc.bias", "layer_norm.weight", "layer_norm.bias"]
     head = m.ProjectionHead(160)
     head.load_state_dict({k: torch.from_numpy(z[f"img.{k}"]) for k in keys}, strict=True)
+
+
+def test_checkpoint_keys_match_reference_fixture():
+    """CPU side of the checkpoint compatibility (`main.py:118-121`, `inference.py:18`): the drop-in model's state_dict
+    has exactly the keys and shapes of the checkpoint the unmodified reference wrote (tests/golden/clip_checkpoint.npz);
+    the scale state a ProjectionHead keeps between calls is not part of it."""
+    import os
+    import sys
+    import numpy as np
+    import mae_clip_b200 as m
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import _tiny_towers as tt
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clip_checkpoint.npz"))
+    ref = {k[3:]: z[k].shape for k in z.files if k.startswith("sd.")}
+    model = m.CLIPModel(temperature=1.0, image_embedding=tt.IMG_DIM, text_embedding=tt.TXT_DIM,
+                        image_encoder=tt.ImageTower(), text_encoder=tt.TextTower())
+    mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert mine == {k: tuple(v) for k, v in ref.items()}
+    assert not any("scale_state" in k for k in mine)

@@ -55,3 +55,52 @@ def test_rejects_wrong_dtype():
     import mae_clip_b200.data as d
     with pytest.raises(ValueError):
         d.normalize_images(torch.zeros(1, 4, 4, 3, device="cuda"))
+
+
+# ------------------------------------------------------------------ token side (dataset.py:19-31)
+def _encoded(N, L, seed):
+    """What `tokenizer(list(captions), padding=True, ...)` leaves in `self.encoded_captions`: lists of N rows of one
+    length L (ids 101 ... 102 then padding zeros, mask ones then zeros)."""
+    rng = np.random.default_rng(seed)
+    ids, mask = [], []
+    for _ in range(N):
+        n = int(rng.integers(3, L + 1))
+        row = [101] + [int(v) for v in rng.integers(1000, 30000, size=n - 2)] + [102] + [0] * (L - n)
+        ids.append(row)
+        mask.append([1] * n + [0] * (L - n))
+    return {"input_ids": ids, "attention_mask": mask}
+
+
+@pytest.mark.parametrize("N,L", [(1000, 25), (257, 200), (40, 7), (64, 1)])
+def test_token_feed_matches_reference_getitem_and_collate(N, L):
+    """TokenFeed.batch == the reference's per-sample torch.tensor(values[idx]) + default collate, bit for bit
+    (oracle/datafeed_ref.py restates it; below it is also rebuilt with torch's own default_collate)."""
+    import mae_clip_b200.data as d
+    from torch.utils.data import default_collate
+    enc = _encoded(N, L, N + L)
+    feed = d.TokenFeed(enc)
+    assert len(feed) == N
+    rng = np.random.default_rng(1)
+    for idx in ([0], [N - 1, 0, 3 % N, 3 % N], list(rng.integers(0, N, size=300)), [-1, -N], []):
+        got = feed.batch(idx)
+        ref = datafeed_ref.token_batch_ref(enc, idx)
+        for k in ("input_ids", "attention_mask"):
+            assert got[k].dtype == torch.int64 and tuple(got[k].shape) == ref[k].shape
+            assert np.array_equal(got[k].cpu().numpy(), ref[k])
+        if idx:
+            items = [{k: torch.tensor(v[i]) for k, v in enc.items()} for i in idx]      # dataset.py:25-28
+            col = default_collate(items)
+            assert torch.equal(got["input_ids"].cpu(), col["input_ids"]) and torch.equal(got["attention_mask"].cpu(), col["attention_mask"])
+    dev_idx = torch.tensor([5 % N, 1 % N], device="cuda")
+    assert torch.equal(feed.batch(dev_idx)["input_ids"].cpu(), torch.tensor(enc["input_ids"])[dev_idx.cpu()])
+    feed.check()
+
+
+def test_token_feed_out_of_range_index_raises():
+    import mae_clip_b200.data as d
+    feed = d.TokenFeed(_encoded(10, 8, 0))
+    out = feed.batch([3, 10])
+    assert bool((out["input_ids"][1] == 0).all())
+    with pytest.raises(IndexError):
+        feed.check()
+    feed.check()       # the flag was cleared

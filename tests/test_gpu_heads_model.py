@@ -202,3 +202,36 @@ def test_head_scale_protocol_is_invisible():
     assert torch.equal(xs.grad, xs2.grad)
     for a, b in zip(h.parameters(), h2.parameters()):
         assert torch.equal(a.grad, b.grad)
+
+
+def test_reference_checkpoint_round_trip(golden, tmp_path):
+    """`main.py:118-121` saves `model.state_dict()`; `inference.py:18` loads it with `torch.load(..., map_location)` +
+    `load_state_dict`.  The fixture is a checkpoint written by the UNMODIFIED reference CLIPModel (tiny third-party
+    towers, `tests/golden/make_golden_ckpt.py`): it must load into the drop-in model with strict keys, reproduce the
+    reference's eval loss and image embeddings on the fixture batch, and survive this model's own save -> load."""
+    import mae_clip_b200 as m
+    import _tiny_towers as tt
+    z = golden("clip_checkpoint")
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    path = tmp_path / "checkpoint_1.pth"
+    torch.save(sd, path)                                                     # the file main.py:120 would have written
+    model = m.CLIPModel(temperature=1.0, image_embedding=tt.IMG_DIM, text_embedding=tt.TXT_DIM,
+                        image_encoder=tt.ImageTower(), text_encoder=tt.TextTower()).cuda()
+    assert set(model.state_dict().keys()) == set(sd.keys())
+    model.load_state_dict(torch.load(path, map_location="cuda"))            # inference.py:18, strict
+    model.eval()
+    batch = {"image": torch.from_numpy(z["batch.image"]).cuda(), "input_ids": torch.from_numpy(z["batch.input_ids"]).cuda(),
+             "attention_mask": torch.from_numpy(z["batch.attention_mask"]).cuda()}
+    with torch.no_grad():
+        loss = model(batch)
+        emb = model.image_projection(model.image_encoder(batch["image"]))   # inference.py:24-25
+    ref = float(z["ref_eval_loss"])
+    assert abs(loss.item() - ref) < LOSS_TOL * abs(ref)
+    assert rel_err(emb, z["ref_image_embeddings"]) < 1e-5
+    path2 = tmp_path / "checkpoint_2.pth"
+    torch.save(model.state_dict(), path2)                                    # main.py:120 on the drop-in model
+    again = m.CLIPModel(temperature=1.0, image_embedding=tt.IMG_DIM, text_embedding=tt.TXT_DIM,
+                        image_encoder=tt.ImageTower(), text_encoder=tt.TextTower()).cuda().eval()
+    again.load_state_dict(torch.load(path2, map_location="cuda"))
+    with torch.no_grad():
+        assert again(batch).item() == loss.item()

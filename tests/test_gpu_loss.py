@@ -396,7 +396,7 @@ def test_tile_flags_are_a_superset_of_the_exact_relevance(scale, tau):
 
 
 # ------------------------------------------------------------------ parity AT the benchmarked size (BASELINE config 4)
-def _phases_sharded(I, T, tau, mode, shard_rows):
+def _phases_sharded(I, T, tau, mode, shard_rows, colpart=False):
     """The row-sharded form of the step (what the ranks of a multi-GPU job run, mae_clip_b200/dist.py) back to back on
     one GPU: every shard of `shard_rows` rows runs its own statistics / row-loss / gradient sweeps with a row offset,
     the length-B vectors and the tile-flag bitmap are assembled in between exactly as the exchange steps do."""
@@ -420,10 +420,21 @@ def _phases_sharded(I, T, tau, mode, shard_rows):
     fin = torch.empty(W, nf, dtype=torch.uint8, device=dev)
     dI, dT = torch.empty_like(I), torch.empty_like(T)
     check(lib.mc_clip_prepare(ptr(I), ptr(T), B, B, D, 0, md, ptr(planes), s))
+    if colpart:
+        # the column-partials form: every shard returns LSE over ITS rows of every column; the vectors are merged as
+        # the ranks do after exchanging them (mae_clip_b200/dist.py PeerStep)
+        ws = torch.empty(max(ws.numel(), lib.mc_clip_stats_colpart_workspace_bytes(b, B, D, md)), dtype=torch.uint8, device=dev)
+        cparts = torch.empty(W, B, device=dev)
     for k in range(W):
         o = k * b
-        check(lib.mc_clip_stats(ptr(I), ptr(T), ptr(planes), b, B, D, o, tau, md, ptr(st4[0, o:]), ptr(st4[1, o:]),
-                                ptr(st4[2, o:]), ptr(st4[3, o:]), ptr(raw_all[k * nf:]), ptr(ws), ws.numel(), s))
+        if colpart:
+            check(lib.mc_clip_stats_colpart(ptr(planes), b, B, D, o, tau, md, ptr(st4[0, o:]), ptr(cparts[k]), ptr(st4[2, o:]),
+                                            ptr(st4[3, o:]), ptr(raw_all[k * nf:]), ptr(ws), ws.numel(), s))
+        else:
+            check(lib.mc_clip_stats(ptr(I), ptr(T), ptr(planes), b, B, D, o, tau, md, ptr(st4[0, o:]), ptr(st4[1, o:]),
+                                    ptr(st4[2, o:]), ptr(st4[3, o:]), ptr(raw_all[k * nf:]), ptr(ws), ws.numel(), s))
+    if colpart:
+        check(lib.mc_clip_colpart_merge(ptr(cparts), W, B, B, ptr(st4[1]), s))
     for k in range(W):
         check(lib.mc_clip_flags_finalize(ptr(raw_all), B, b, k * b, ptr(fin[k]), s))
     for k in range(W):
@@ -457,7 +468,7 @@ def _c4_batch_and_oracle(B, scale):
     return _C4_CACHE[key]
 
 
-@pytest.mark.parametrize("variant", ["fused_flags", "dense", "shards4096_flags", "host_entry"])
+@pytest.mark.parametrize("variant", ["fused_flags", "dense", "shards4096_flags", "shards4096_colpart", "host_entry"])
 @pytest.mark.parametrize("B", [8192, 32768])
 def test_loss_c4_size_vs_fp64_blockwise(B, variant):
     """The benchmarked path - B = 32768 (and 8192), D = 256, LayerNorm-scale rows (tile-flag density 1/256), probe +
@@ -476,8 +487,8 @@ def test_loss_c4_size_vs_fp64_blockwise(B, variant):
         loss = l.item()
     elif variant == "dense":
         loss, dI, dT, _ = _phases(I, T, 1.0, "tc_f16x3", sparse=False)
-    elif variant == "shards4096_flags":
-        loss, dI, dT, flags = _phases_sharded(I, T, 1.0, "tc_f16x3", 4096)
+    elif variant in ("shards4096_flags", "shards4096_colpart"):
+        loss, dI, dT, flags = _phases_sharded(I, T, 1.0, "tc_f16x3", 4096, colpart=variant.endswith("colpart"))
         assert flags.float().mean().item() < 0.02      # the sparse path is what ran (diagonal tiles + a few neighbours)
     else:
         lib = _lib.lib()
@@ -569,3 +580,38 @@ def test_no_grad_forward_does_not_run_the_gradient_sweep():
     with torch.no_grad():
         out = head(x, keep_mask=keep)
     assert out.grad_fn is None
+
+
+@pytest.mark.parametrize("mode", ["tc_f16x3", "tc_f16"])
+@pytest.mark.parametrize("B,shard,scale", [(640, 128, 0.1), (1000, 1000, 0.3), (768, 384, 1.0), (129, 129, 0.5)])
+def test_column_partials_statistics_match_oracle(B, shard, scale, mode):
+    """Column LSE of S from the per-warp column partials (no transposed strip): ragged batches, a strip that is the
+    whole batch, strips of one row block, rows of very different scale in one column (exponentials are taken against
+    each column's OWN maximum, so nothing underflows) - the five statistic vectors against the fp64 closed form."""
+    from mae_clip_b200 import _lib
+    from mae_clip_b200._lib import check, cur_stream, ptr
+    lib = _lib.lib()
+    md = _lib.GEMM_MODES[mode]
+    g = torch.Generator().manual_seed(B)
+    I0 = loss_ref.make_embeddings(B, 256, seed=81, scale=scale)
+    T0 = loss_ref.make_embeddings(B, 256, seed=82, scale=scale)
+    I0[1] *= 6.0; T0[B // 2] *= 6.0; I0[B - 1] *= 0.01          # a column far above and one far below the others
+    I, T = I0.cuda(), T0.cuda()
+    _l, _dI, _dT, stats = loss_ref.clip_loss_closed_form(I0.numpy(), T0.numpy(), 1.0)
+    planes = torch.empty(lib.mc_clip_planes_bytes(B, 256, md), dtype=torch.uint8, device="cuda")
+    check(lib.mc_clip_prepare(ptr(I), ptr(T), B, B, 256, 0, md, ptr(planes), cur_stream()))
+    W = (B + shard - 1) // shard
+    if B % shard or shard % 128:
+        W, shard = 1, B                       # row offsets must be multiples of 128: one strip = the whole batch
+    ws = torch.empty(lib.mc_clip_stats_colpart_workspace_bytes(shard, B, 256, md), dtype=torch.uint8, device="cuda")
+    r, rz, ps = torch.empty(B, device="cuda"), torch.empty(B, device="cuda"), torch.empty(B, device="cuda")
+    cparts = torch.empty(W, B, device="cuda")
+    for k in range(W):
+        o = k * shard
+        check(lib.mc_clip_stats_colpart(ptr(planes), shard, B, 256, o, 1.0, md, ptr(r[o:]), ptr(cparts[k]), ptr(rz[o:]), ptr(ps[o:]),
+                                        None, ptr(ws), ws.numel(), cur_stream()))
+    c = torch.empty(B, device="cuda")
+    check(lib.mc_clip_colpart_merge(ptr(cparts), W, B, B, ptr(c), cur_stream()))
+    tol = 2e-5 if mode == "tc_f16x3" else 2e-3
+    assert rel_err(c, stats["col_lse_s"]) < tol
+    assert rel_err(r, stats["row_lse_s"]) < tol and rel_err(rz, stats["row_lse_z"]) < tol
