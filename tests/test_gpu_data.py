@@ -64,8 +64,8 @@ def _encoded(N, L, seed):
     rng = np.random.default_rng(seed)
     ids, mask = [], []
     for _ in range(N):
-        n = int(rng.integers(3, L + 1))
-        row = [101] + [int(v) for v in rng.integers(1000, 30000, size=n - 2)] + [102] + [0] * (L - n)
+        n = int(rng.integers(min(3, L), L + 1))
+        row = ([101] + [int(v) for v in rng.integers(1000, 30000, size=max(n - 2, 0))] + [102])[:n] + [0] * (L - n)
         ids.append(row)
         mask.append([1] * n + [0] * (L - n))
     return {"input_ids": ids, "attention_mask": mask}
