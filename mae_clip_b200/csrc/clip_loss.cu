@@ -4,6 +4,8 @@
 #include <stdlib.h>
 
 #include <mutex>
+#include <string>
+#include <vector>
 
 #include "clip_loss.cuh"
 
@@ -211,8 +213,45 @@ struct StripHook {
   int (*fn)(void* ctx, int row0, int rows);
   void* ctx;
 };
+// MAE_CLIP_HOST_TRACE=1: the host-buffer entry records a timing event after every copy and phase and prints the
+// timeline (ms since the call's first event) to stderr - the substitute for an nsys timeline on boxes without it.
+namespace {
+struct Trace {
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  void mark(const char* name, int k, cudaStream_t s) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    marks.emplace_back(k >= 0 ? std::string(name) + "[" + std::to_string(k) + "]" : std::string(name), e);
+  }
+  void dump() {
+    if (marks.empty()) return;
+    cudaEventSynchronize(marks.back().second);
+    for (auto& m : marks) {
+      cudaEventSynchronize(m.second);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks.front().second, m.second);
+      fprintf(stderr, "[mc trace] %8.3f ms  %s\n", ms, m.first.c_str());
+      }
+    for (auto& m : marks) cudaEventDestroy(m.second);
+    marks.clear();
+  }
+};
+thread_local Trace* g_trace = nullptr;
+inline void trace_mark(const char* name, int k, cudaStream_t s) { if (g_trace) g_trace->mark(name, k, s); }
+}  // namespace
+
+// `feed`, when given: the batch is still arriving from the host in `chunks` row chunks (event k = rows of chunk k are in
+// device memory); staging and the statistics sweep then run chunk by chunk behind the copy (tc::prepare_chunk,
+// tc::stats_chunk) instead of waiting for the whole batch.
+struct ChunkFeed {
+  int chunks;
+  const cudaEvent_t* arrived;
+  unsigned int* words;  // {true max so far, scale slot, bad flag} in device memory
+};
 static int fused_run(const float* I, const float* T, int B, int D, float tau, int mode, float* loss_out, float* dI,
-                     float* dT, void* ws, size_t ws_bytes, void* stream, int n_strips, const StripHook* hook) {
+                     float* dT, void* ws, size_t ws_bytes, void* stream, int n_strips, const StripHook* hook,
+                     const ChunkFeed* feed = nullptr, double last_frac = 0.0) {
   int rc = check_problem("clip_loss_fwd_bwd", I, T, B, B, D, 0, tau, mode);
   if (rc) return rc;
   MC_REQUIRE(loss_out && ws, MC_ERR_BAD_ARG, "clip_loss_fwd_bwd: null loss_out/workspace");
@@ -236,32 +275,67 @@ static int fused_run(const float* I, const float* T, int B, int D, float tau, in
   static const bool dense = getenv("MAE_CLIP_DENSE") != nullptr && getenv("MAE_CLIP_DENSE")[0] == '1';
   uint8_t* flags_raw = (l.flags_bytes && !dense) ? reinterpret_cast<uint8_t*>(base + l.off_flags) : nullptr;
   uint8_t* flags = flags_raw ? flags_raw + l.flags_bytes : nullptr;
-  if ((rc = mc_clip_prepare(I, T, B, B, D, 0, mode, planes, stream))) return rc;
-  if ((rc = mc_clip_stats(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, ps, flags_raw, phase, phase_bytes, stream)))
-    return rc;
+  if (feed) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int emode = eff_mode(mode, D), chunk_rows = B / feed->chunks;
+    ClipProblem p{I, T, planes, B, B, D, 0, tau};
+    p.tile_flags_out = flags_raw;
+    MC_CUDA(cudaMemsetAsync(feed->words, 0, 3 * sizeof(unsigned int), st));
+    if ((rc = tc::stats_begin(p, st))) return rc;
+    for (int k = 0; k < feed->chunks; ++k) {
+      MC_CUDA(cudaStreamWaitEvent(st, feed->arrived[k], 0));
+      if ((rc = tc::prepare_chunk(I, T, B, D, k * chunk_rows, chunk_rows, planes, feed->words, st))) return rc;
+      trace_mark("staged", k, st);
+      if ((rc = tc::stats_chunk(p, emode, k, feed->chunks, phase, st))) return rc;
+      trace_mark("stats", k, st);
+    }
+    if ((rc = tc::verify_scale(feed->words, st))) return rc;
+    if ((rc = tc::stats_end(p, emode, feed->chunks, r, c, rz, ps, phase, st))) return rc;
+    trace_mark("stats_end", -1, st);
+  } else {
+    if ((rc = mc_clip_prepare(I, T, B, B, D, 0, mode, planes, stream))) return rc;
+    trace_mark("staged", -1, static_cast<cudaStream_t>(stream));
+    if ((rc = mc_clip_stats(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, ps, flags_raw, phase, phase_bytes, stream)))
+      return rc;
+    trace_mark("stats", -1, static_cast<cudaStream_t>(stream));
+  }
   if (flags_raw && (rc = mc_clip_flags_finalize(flags_raw, B, B, 0, flags, stream))) return rc;
   if ((rc = mc_clip_rowloss(I, T, planes, B, B, D, 0, tau, mode, r, c, rz, ps, g, q, loss_out, flags, phase,
                             phase_bytes, stream)))
     return rc;
+  trace_mark("rowloss", -1, static_cast<cudaStream_t>(stream));
   if (hook && (rc = hook->fn(hook->ctx, -1, 0))) return rc;
   if (!dI) return MC_OK;
   // strips of whole 128-row blocks; a strip whose partial-sum workspace would not fit the step's buffer (more
-  // column splits per row block) folds the sweep back into one launch
+  // column splits per row block) folds the sweep back into one launch.  last_frac > 0: the LAST strip takes that share
+  // of the row blocks and the others split the rest evenly (the host-buffer entry: only the last strip's copy back to
+  // the host is exposed, so it is the short one).
   const int n_blocks = (B + 127) / 128;
   if (n_strips > n_blocks) n_strips = n_blocks;
   if (n_strips < 1) n_strips = 1;
-  const int strip_rows = ((n_blocks + n_strips - 1) / n_strips) * 128;
-  if (n_strips > 1 && (mc_clip_loss_workspace_bytes(strip_rows, B, D, mode) > phase_bytes ||
-                       (B - (n_strips - 1) * strip_rows) <= 0))
-    n_strips = 1;
+  int strip_first[17];
+  {
+    int last = (last_frac > 0.0 && n_strips > 1) ? (int)(n_blocks * last_frac + 0.5) : 0;
+    if (last < 1 || last > n_blocks - (n_strips - 1)) last = 0;
+    const int head = last ? n_strips - 1 : n_strips, head_blocks = n_blocks - last;
+    const int per = (head_blocks + head - 1) / head;
+    for (int k = 0; k < head; ++k) strip_first[k] = k * per < head_blocks ? k * per : head_blocks;
+    strip_first[head] = head_blocks;
+    strip_first[n_strips] = n_blocks;
+  }
+  for (int k = 0; k < n_strips && n_strips > 1; ++k) {
+    const int rows_k = (strip_first[k + 1] - strip_first[k]) * 128;
+    if (rows_k <= 0 || mc_clip_loss_workspace_bytes(rows_k, B, D, mode) > phase_bytes) n_strips = 1;
+  }
   const int n_tiles = n_blocks;  // column tiles of B = row blocks of B
   for (int k = 0; k < n_strips; ++k) {
-    const int row0 = n_strips == 1 ? 0 : k * strip_rows;
-    const int rows = n_strips == 1 ? B : (row0 + strip_rows <= B ? strip_rows : B - row0);
+    const int row0 = n_strips == 1 ? 0 : strip_first[k] * 128;
+    const int rows = n_strips == 1 ? B : (strip_first[k + 1] * 128 <= B ? strip_first[k + 1] * 128 : B) - row0;
     const uint8_t* fl = flags ? flags + (size_t)(row0 / 128) * n_tiles : nullptr;
     if ((rc = mc_clip_bwd(I, T, planes, rows, B, D, row0, tau, mode, r, c, rz, g, q, nullptr, dI + (size_t)row0 * D,
                           dT + (size_t)row0 * D, fl, phase, phase_bytes, stream)))
       return rc;
+    trace_mark("bwd strip", k, static_cast<cudaStream_t>(stream));
     if (hook && (rc = hook->fn(hook->ctx, row0, rows))) return rc;
   }
   return MC_OK;
@@ -306,6 +380,7 @@ int host_copy_hook(void* vctx, int row0, int rows) {
   MC_CUDA(cudaStreamWaitEvent(c->copy, ev, 0));
   MC_CUDA(cudaMemcpyAsync(c->dT_host + off, c->gT + off, bytes, cudaMemcpyDeviceToHost, c->copy));
   MC_CUDA(cudaMemcpyAsync(c->dI_host + off, c->gI + off, bytes, cudaMemcpyDeviceToHost, c->copy));
+  trace_mark("d2h strip done", c->n_ev - 1, c->copy);
   return MC_OK;
 }
 // one copy stream per device, created on first use and kept (callers on different threads may share it: every
@@ -353,40 +428,99 @@ int mc_clip_loss_fwd_bwd_host(const float* I_host, const float* T_host, int B, i
     const int v = atoi(e);
     if (want_grad && v >= 1 && v <= 8 && eff_mode(mode, D) != MC_GEMM_SIMT_FP32) n_strips = v;
   }
+  // share of the row blocks the LAST strip takes (0 = equal strips).  A short last strip shortens the exposed copy,
+  // but measured at B = 32768 (tools/e2e_trace.py, profiles/r02k_e2e_trace.log) the two sweeps of an uneven split
+  // lose more to their partly filled last rounds (3/4 + 1/4: 2.99 + 1.11 ms against 1.91 + 1.92) than the copy gains
+  double last_frac = 0.0;
+  if (const char* e = getenv("MAE_CLIP_HOST_LAST_STRIP")) {
+    const double v = atof(e);
+    if (v >= 0.0 && v < 1.0) last_frac = v;
+  }
+  // row chunks of the inbound copy (MAE_CLIP_HOST_CHUNKS, 1 = copy everything, then stage): with the batch arriving
+  // in pieces, staging and the statistics sweep of the rows that have landed run behind the rest of the copy.  The
+  // planes share one power-of-two scale, which the first chunk fixes with a binade of headroom; a batch whose later
+  // rows exceed it is detected on the device (tc::verify_scale) and the step is redone from the resident copy.
+  int chunks = (eff_mode(mode, D) != MC_GEMM_SIMT_FP32 && B >= 8192) ? 2 : 1;
+  if (const char* e = getenv("MAE_CLIP_HOST_CHUNKS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 16) chunks = v;
+  }
+  if (chunks > 1 && !(eff_mode(mode, D) != MC_GEMM_SIMT_FP32 && tc::stats_chunkable(B, D, chunks))) chunks = 1;
+  unsigned int* words = reinterpret_cast<unsigned int*>(base + 4 * emb + 16);
   HostCopyCtx ctx = {};
   ctx.st = st; ctx.D = D; ctx.want_grad = want_grad;
   ctx.loss_dev = loss; ctx.gI = gI; ctx.gT = gT;
   ctx.loss_host = loss_host; ctx.dI_host = dI_host; ctx.dT_host = dT_host;
   int rc = MC_OK;
-  cudaEvent_t done = nullptr;
-  int n_created = 0;
-  if (want_grad) {
+  cudaEvent_t done = nullptr, arrived[17] = {};
+  int n_created = 0, n_arrived = 0;
+  auto destroy_all = [&]() {
+    for (int i = 0; i < n_created; ++i) cudaEventDestroy(ctx.ev[i]);
+    for (int i = 0; i < n_arrived; ++i) cudaEventDestroy(arrived[i]);
+    if (done) cudaEventDestroy(done);
+  };
+  if (want_grad || chunks > 1) {
     if ((rc = copy_stream_for_current_device(&ctx.copy))) return rc;
-    for (; n_created < n_strips; ++n_created)
-      if (cudaEventCreateWithFlags(&ctx.ev[n_created], cudaEventDisableTiming) != cudaSuccess) break;
-    if (n_created < n_strips || cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess) {
-      for (int i = 0; i < n_created; ++i) cudaEventDestroy(ctx.ev[i]);
+    bool ok = true;
+    for (; ok && want_grad && n_created < n_strips; ++n_created)
+      if (cudaEventCreateWithFlags(&ctx.ev[n_created], cudaEventDisableTiming) != cudaSuccess) { ok = false; break; }
+    const int want_arrived = chunks > 1 ? chunks + 1 : 0;  // + the "stream is free" event the copy stream waits for
+    for (; ok && n_arrived < want_arrived; ++n_arrived)
+      if (cudaEventCreateWithFlags(&arrived[n_arrived], cudaEventDisableTiming) != cudaSuccess) { ok = false; break; }
+    if (ok && cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess) ok = false;
+    if (!ok) {
+      destroy_all();
       MC_REQUIRE(false, MC_ERR_CUDA, "clip_loss_host: cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
   }
   auto body = [&]() -> int {
-    MC_CUDA(cudaMemcpyAsync(dTin, T_host, bytes, cudaMemcpyHostToDevice, st));
-    MC_CUDA(cudaMemcpyAsync(dIin, I_host, bytes, cudaMemcpyHostToDevice, st));
     StripHook hook{host_copy_hook, &ctx};
-    int r2 = fused_run(dIin, dTin, B, D, tau, mode, loss, want_grad ? gI : nullptr, want_grad ? gT : nullptr, ws,
-                       ws_bytes, stream, n_strips, &hook);
-    if (r2) return r2;
-    if (want_grad) {
-      MC_CUDA(cudaEventRecord(done, ctx.copy));
-      MC_CUDA(cudaStreamWaitEvent(st, done, 0));
+    float* gIo = want_grad ? gI : nullptr;
+    float* gTo = want_grad ? gT : nullptr;
+    auto finish = [&]() -> int {
+      if (want_grad) {
+        MC_CUDA(cudaEventRecord(done, ctx.copy));
+        MC_CUDA(cudaStreamWaitEvent(st, done, 0));
+      }
+      MC_CUDA(cudaStreamSynchronize(st));
+      return MC_OK;
+    };
+    int r2;
+    if (chunks > 1) {
+      // the copy stream may not overwrite the inbound buffers before earlier work on the caller's stream is done
+      MC_CUDA(cudaEventRecord(arrived[chunks], st));
+      MC_CUDA(cudaStreamWaitEvent(ctx.copy, arrived[chunks], 0));
+      const size_t crow = (size_t)(B / chunks) * D;
+      for (int k = 0; k < chunks; ++k) {
+        MC_CUDA(cudaMemcpyAsync(dTin + k * crow, T_host + k * crow, crow * 4, cudaMemcpyHostToDevice, ctx.copy));
+        MC_CUDA(cudaMemcpyAsync(dIin + k * crow, I_host + k * crow, crow * 4, cudaMemcpyHostToDevice, ctx.copy));
+        MC_CUDA(cudaEventRecord(arrived[k], ctx.copy));
+        trace_mark("h2d chunk arrived", k, ctx.copy);
+      }
+      ChunkFeed feed{chunks, arrived, words};
+      if ((r2 = fused_run(dIin, dTin, B, D, tau, mode, loss, gIo, gTo, ws, ws_bytes, stream, n_strips, &hook, &feed, last_frac)))
+        return r2;
+      if ((r2 = finish())) return r2;
+      unsigned int bad = 0;
+      MC_CUDA(cudaMemcpy(&bad, words + 2, sizeof(bad), cudaMemcpyDeviceToHost));
+      if (!bad) return MC_OK;
+      ctx.n_ev = 0;  // rare: a later chunk outgrew the first chunk's scale - redo from the resident fp32 copy
+    } else {
+      MC_CUDA(cudaMemcpyAsync(dTin, T_host, bytes, cudaMemcpyHostToDevice, st));
+      MC_CUDA(cudaMemcpyAsync(dIin, I_host, bytes, cudaMemcpyHostToDevice, st));
+      trace_mark("h2d arrived", -1, st);
     }
-    MC_CUDA(cudaStreamSynchronize(st));
-    return MC_OK;
+    if ((r2 = fused_run(dIin, dTin, B, D, tau, mode, loss, gIo, gTo, ws, ws_bytes, stream, n_strips, &hook, nullptr, last_frac)))
+      return r2;
+    return finish();
   };
+  Trace trace;
+  const bool tracing = getenv("MAE_CLIP_HOST_TRACE") != nullptr && getenv("MAE_CLIP_HOST_TRACE")[0] == '1';
+  if (tracing) { g_trace = &trace; trace.mark("call", -1, st); }
   rc = body();
-  if (rc && want_grad) cudaStreamSynchronize(ctx.copy);  // nothing of this call may still be in flight
-  for (int i = 0; i < n_created; ++i) cudaEventDestroy(ctx.ev[i]);
-  if (done) cudaEventDestroy(done);
+  if (tracing) { trace.mark("end", -1, st); trace.dump(); g_trace = nullptr; }
+  if (rc && ctx.copy) cudaStreamSynchronize(ctx.copy);  // nothing of this call may still be in flight
+  destroy_all();
   return rc;
 }
 

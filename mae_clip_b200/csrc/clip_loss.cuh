@@ -51,6 +51,15 @@ int flags_finalize(const uint8_t* flags_all, int B, int b, int row_offset, uint8
 int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
           size_t ws_bytes, cudaStream_t st, float* c_part_all = nullptr);
 size_t stats_colpart_workspace_bytes(int b, int B, int D, int mode);
+// the statistics sweep in pieces (host-buffer entry: one probe launch per arrived row chunk)
+int stats_begin(const ClipProblem& p, cudaStream_t st);
+int stats_chunk(const ClipProblem& p, int mode, int k, int chunks, void* ws, cudaStream_t st, float* c_part_all = nullptr);
+int stats_end(const ClipProblem& p, int mode, int chunks, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
+              cudaStream_t st, float* c_part_all = nullptr);
+int prepare_chunk(const float* I, const float* T, int B, int D, int row0, int rows, void* planes_all, unsigned int* words,
+                  cudaStream_t st);
+int verify_scale(unsigned int* words, cudaStream_t st);
+bool stats_chunkable(int B, int D, int chunks);
 int ranks_lse_merge(const float* parts, int n, int64_t stride, int B, float* c, cudaStream_t st);
 int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* ps_loc, float* g_loc,
             float* q_loc, float* loss_part, void* ws, size_t ws_bytes, cudaStream_t st);

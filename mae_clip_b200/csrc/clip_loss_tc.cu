@@ -91,7 +91,28 @@ struct PairParams {
   // epilogue warp writes the log-sum-exp of its 32 rows for each of its 32 columns, log2 units, to
   // colpart[(strip row / 32) * Bp + column]; mc::tc::colpart_merge folds them into c.
   float* colpart;
+  // Arrival-ordered launches of the statistics sweep (host-buffer entry: the batch arrives over PCIe in `chunks` row
+  // chunks of chunk_blocks row blocks; nsplit = chunks * chunk_m, so a column split lies inside one chunk).  Launch k
+  // takes the jobs (row block, column split) whose LATER chunk is k: everything that became computable when chunk k
+  // landed.  chunk_k < 0: every job.
+  int chunk_k, chunk_blocks, chunk_m;
 };
+// job index -> (row block, column split); the filtered launches enumerate their jobs densely so that the pairs stay evenly
+// loaded: first the row blocks of chunk k against the splits of chunks 0..k, then the earlier row blocks against chunk k's
+__device__ __forceinline__ int pair_njobs(const PairParams& p) {
+  if (p.chunk_k < 0) return p.n_row_blocks * p.nsplit;
+  const int rows_k = min(p.chunk_blocks, p.n_row_blocks - p.chunk_k * p.chunk_blocks);
+  return rows_k * (p.chunk_k + 1) * p.chunk_m + p.chunk_k * p.chunk_blocks * p.chunk_m;
+}
+__device__ __forceinline__ void pair_job(const PairParams& p, int job, int& rb, int& sp) {
+  if (p.chunk_k < 0) { rb = job / p.nsplit; sp = job % p.nsplit; return; }
+  const int rows_k = min(p.chunk_blocks, p.n_row_blocks - p.chunk_k * p.chunk_blocks);
+  const int w = (p.chunk_k + 1) * p.chunk_m, first = rows_k * w;
+  if (job < first) { rb = p.chunk_k * p.chunk_blocks + job / w; sp = job % w; return; }
+  job -= first;
+  rb = job / p.chunk_m;
+  sp = p.chunk_k * p.chunk_m + job % p.chunk_m;
+}
 constexpr float kFlagTheta2 = 44.f;
 constexpr float kProbeMargin2 = 2.f;  // slack on top of the probe's worst-case rounding bound (see zmargin2)    // log2 units: dropped terms are below 2^-44 of their row's soft-target mass
 
@@ -224,7 +245,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   const bool leader = rank == 0;
   const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int D = p.D, nkc = D >> 6;
-  const int njobs = p.n_row_blocks * p.nsplit;
+  const int njobs = pair_njobs(p);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSlots; ++s) { mbar_init(bar(kFull0 + s), 1); mbar_init(bar(kEmpty0 + s), kIssuers); }
@@ -260,7 +281,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       if (elect_one()) {
         uint32_t it = 0, jj = 0;
         for (int job = pair_id; job < njobs; job += npairs) {
-          const int rb = job / p.nsplit, sp = job % p.nsplit;
+          int rb, sp;
+          pair_job(p, job, rb, sp);
           const int row_a = p.row_offset + rb * 128 + (int)rank * kRowsCta;
           const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
           if ((PHASE == kRowLoss || PHASE == kStatsZ) && p.flags &&
@@ -321,7 +343,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const uint32_t xt_bytes = (uint32_t)(D / 2) * 128u;  // D/2 rows x 64 j fp16
         uint32_t tt = 0;
         for (int job = pair_id; job < njobs; job += npairs) {
-          const int sp = job % p.nsplit;
+          int rb_unused, sp;
+          pair_job(p, job, rb_unused, sp);
           const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
           for (int t = t0; t < t1; ++t, ++tt) {
             for (int h = 0; h < 2; ++h) {
@@ -376,7 +399,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           mma_commit_pair(bar(h == 0 ? kGradDone : kGradDone1), 3);
         };
         for (int job = pair_id; job < njobs; job += npairs) {
-          const int rb = job / p.nsplit, sp = job % p.nsplit;
+          int rb, sp;
+          pair_job(p, job, rb, sp);
           const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
           const uint8_t* frow = p.flags ? p.flags + (size_t)rb * p.n_tiles : nullptr;
           if ((PHASE == kRowLoss || PHASE == kStatsZ) && frow && !job_has_tiles(frow, t0, t1)) continue;
@@ -534,7 +558,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     const float m2cS2 = -2.f * cS2;
     uint32_t tt = 0, jj = 0;
     for (int job = pair_id; job < njobs; job += npairs, ++jj) {
-      const int rb = job / p.nsplit, sp = job % p.nsplit;
+      int rb, sp;
+      pair_job(p, job, rb, sp);
       const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
       const int lrow = rb * 128 + (int)rank * kRowsCta + m;  // row within this rank's strip
       const int gi = p.row_offset + lrow;
@@ -1197,7 +1222,7 @@ struct Split {
 // with 2; the statistics sweep is cheap per job)
 constexpr double kOvhStats = 1.5, kOvhRowLoss = 0.5, kOvhBwd = 6.0;
 template <int PHASE> constexpr double phase_ovh() { return PHASE == kBwd ? kOvhBwd : (PHASE == kRowLoss ? kOvhRowLoss : kOvhStats); }
-static Split choose_split(int b, int B, double ovh = kOvhRowLoss) {
+static Split choose_split(int b, int B, double ovh = kOvhRowLoss, int align = 1) {
   Split s;
   s.n_row_blocks = (b + 127) / 128;
   s.bpad = s.n_row_blocks * 128;
@@ -1206,21 +1231,40 @@ static Split choose_split(int b, int B, double ovh = kOvhRowLoss) {
   int best = 1;
   double best_cost = 1e30;
   const int max_split = s.n_tiles < kMaxSplit ? s.n_tiles : kMaxSplit;
-  for (int ns = 1; ns <= max_split; ++ns) {
+  for (int ns = align; ns <= max_split; ns += align) {   // align > 1: the column splits must not straddle a row chunk
     const int tps = (s.n_tiles + ns - 1) / ns;
-    const long jobs = (long)s.n_row_blocks * ns;
-    const long rounds = (jobs + npairs - 1) / npairs;
-    const double cost = (double)rounds * (tps + ovh) + 0.02 * ns;
+    double cost = 0.02 * ns;
+    if (align > 1) {
+      // arrival-ordered launches (PairParams::chunk_k): every launch pays its own partly filled last round
+      if (s.n_tiles % ns != 0 || s.n_row_blocks % align != 0) continue;
+      const long cb = s.n_row_blocks / align, cm = ns / align;
+      for (int k = 0; k < align; ++k) {
+        const long jobs = cb * (k + 1) * cm + (long)k * cb * cm;
+        cost += (double)((jobs + npairs - 1) / npairs) * (tps + ovh);
+      }
+    } else {
+      const long jobs = (long)s.n_row_blocks * ns;
+      cost += (double)((jobs + npairs - 1) / npairs) * (tps + ovh);
+    }
     if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
   }
   static const int forced = getenv("MAE_CLIP_NSPLIT") ? atoi(getenv("MAE_CLIP_NSPLIT")) : 0;   // experiments only
-  if (forced >= 1 && forced <= max_split) best = forced;
+  if (forced >= 1 && forced <= max_split && align == 1) best = forced;
   s.nsplit = best;
   s.tiles_per_split = (s.n_tiles + best - 1) / best;
   return s;
 }
 
 size_t planes_bytes(int B, int D, int /*mode*/) { return supported(D) ? planes_layout(B, D).total : 0; }
+
+// can the statistics sweep of a whole batch (b == B) run as `chunks` arrival-ordered launches?
+bool stats_chunkable(int B, int D, int chunks) {
+  if (!supported(D) || chunks < 2 || B % 128 != 0) return false;
+  const int nb = B / 128;
+  if (nb % chunks != 0 || chunks > kMaxSplit) return false;
+  Split sp = choose_split(B, B, kOvhStats, chunks);
+  return sp.nsplit % chunks == 0 && sp.n_tiles % sp.nsplit == 0 && sp.n_tiles == sp.n_row_blocks;
+}
 
 // Column LSE of S.  Two forms (SURVEY section 7 hard part c):
 //   transposed strip  the statistics sweep also computes S^T-strip = I_i T_j^T (3 more tensor-core passes per tile)
@@ -1247,7 +1291,8 @@ size_t stats_colpart_workspace_bytes(int b, int B, int D, int mode) {
 
 size_t workspace_bytes(int b, int B, int D, int /*mode*/) {
   Split s = choose_split(b, B, kOvhStats), sr = choose_split(b, B, kOvhRowLoss), sb = choose_split(b, B, kOvhBwd);
-  size_t stats = (size_t)(s.nsplit > sr.nsplit ? s.nsplit : sr.nsplit) * 4 * s.bpad * sizeof(float2);
+  (void)sr;
+  size_t stats = (size_t)kMaxSplit * 4 * s.bpad * sizeof(float2);   // any split count (the chunked launches align theirs)
   size_t bwdp = (size_t)sb.nsplit * 2 * s.bpad * D * sizeof(float);
   return round_up(stats > bwdp ? stats : bwdp, 256) + 256 + colpart_bytes(b, B);  // + the weight-scale slot + column partials
 }
@@ -1300,11 +1345,12 @@ __global__ void __launch_bounds__(256) stage_fused_kernel(PeerRows src, int b, i
                                                           const unsigned int* amax_slots, int nslots,
                                                           __half* __restrict__ Xh, __half* __restrict__ Xl,
                                                           __half* __restrict__ XhT, float* hdr,
-                                                          float* __restrict__ norm_i, float* __restrict__ norm_t) {
+                                                          float* __restrict__ norm_i, float* __restrict__ norm_t,
+                                                          int blk0 /* first 32-row block of this launch */) {
   constexpr int K2 = 2 * D, kVec = K2 / 128, kRows = 32, kPitch = K2 + 2;  // pitch in halfs: odd word count
   __shared__ __align__(16) __half tile[kRows * kPitch];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j0 = blockIdx.x * kRows;
+  const int j0 = (blockIdx.x + blk0) * kRows;
   unsigned int abits = 0;
   for (int q = 0; q < nslots; ++q) abits = max(abits, amax_slots[q]);
   const float amax = __uint_as_float(abits);
@@ -1423,9 +1469,9 @@ static void launch_stage_fused(const PeerRows& src, int b, int B, int D, const P
                                float* hdr, float* norm_i, float* norm_t, cudaStream_t st) {
   const int blocks = l.Bp / 32;
   if (D == 256)
-    stage_fused_kernel<256><<<blocks, 256, 0, st>>>(src, b, B, l.Bp, amax_slots, nslots, Xh, Xl, XhT, hdr, norm_i, norm_t);
+    stage_fused_kernel<256><<<blocks, 256, 0, st>>>(src, b, B, l.Bp, amax_slots, nslots, Xh, Xl, XhT, hdr, norm_i, norm_t, 0);
   else
-    stage_fused_kernel<128><<<blocks, 256, 0, st>>>(src, b, B, l.Bp, amax_slots, nslots, Xh, Xl, XhT, hdr, norm_i, norm_t);
+    stage_fused_kernel<128><<<blocks, 256, 0, st>>>(src, b, B, l.Bp, amax_slots, nslots, Xh, Xl, XhT, hdr, norm_i, norm_t, 0);
 }
 
 int push_shards(const float* I_loc, const float* T_loc, int b, int D, int rank, int world, float* const* I_dst,
@@ -1526,7 +1572,7 @@ int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row
 
 template <int PHASE, int PASSES>
 static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float* ps_loc, float* part,
-                       const float* wscale, cudaStream_t st, float* colpart = nullptr) {
+                       const float* wscale, cudaStream_t st, float* colpart = nullptr, int chunk_k = -1, int chunks = 1) {
   MC_REQUIRE(supported(p.D), MC_ERR_UNSUPPORTED, "tcgen05 engine needs D in {128, 256} (got %d)", p.D);
   MC_REQUIRE(p.row_offset % 128 == 0, MC_ERR_UNSUPPORTED, "tcgen05 engine needs row_offset %% 128 == 0 (got %d)",
              p.row_offset);
@@ -1545,7 +1591,8 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float*
   if ((rc = make_map(&mb_lo, Xl, l.Bp, 2 * p.D, 32))) return rc;
   if ((rc = make_map(&mt, XhT, 2 * p.D, l.Bp, p.D / 2))) return rc;
 
-  Split sp = choose_split(p.b, p.B, phase_ovh<PHASE>());
+  const bool chunked = chunks > 1 && (PHASE == kStats || PHASE == kStatsZ);
+  Split sp = choose_split(p.b, p.B, phase_ovh<PHASE>(), chunked ? chunks : 1);
   PairParams pp;
   pp.b = p.b; pp.B = p.B; pp.Bp = l.Bp; pp.D = p.D; pp.row_offset = p.row_offset;
   pp.n_row_blocks = sp.n_row_blocks; pp.n_tiles = sp.n_tiles; pp.nsplit = sp.nsplit;
@@ -1561,11 +1608,20 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float*
   pp.norm_i = reinterpret_cast<const float*>(base + l.off_norm_i);
   pp.norm_t = reinterpret_cast<const float*>(base + l.off_norm_t);
   pp.colpart = (PHASE == kStats) ? colpart : nullptr;
+  pp.chunk_k = (PHASE == kStats && chunked) ? chunk_k : -1;
+  pp.chunk_blocks = chunked ? sp.n_row_blocks / chunks : sp.n_row_blocks;
+  pp.chunk_m = chunked ? sp.nsplit / chunks : sp.nsplit;
+  if (chunked)
+    MC_REQUIRE(sp.n_row_blocks % chunks == 0 && sp.nsplit % chunks == 0 && sp.n_tiles % sp.nsplit == 0 &&
+                   sp.n_tiles == sp.n_row_blocks,
+               MC_ERR_UNSUPPORTED, "chunked statistics sweep: %d row blocks / %d splits do not divide into %d chunks",
+               sp.n_row_blocks, sp.nsplit, chunks);
 
   auto kern = pair_kernel<PHASE, PASSES>;
   static std::atomic<unsigned long long> attr_done{0};  // per template instantiation, one bit per device
   MC_CUDA(ensure_dynamic_smem(kern, kSmemBytes, attr_done));
-  const long njobs = (long)sp.n_row_blocks * sp.nsplit;
+  long njobs = (long)sp.n_row_blocks * sp.nsplit;
+  if (pp.chunk_k >= 0) njobs = (long)pp.chunk_blocks * (pp.chunk_k + 1) * pp.chunk_m + (long)pp.chunk_k * pp.chunk_blocks * pp.chunk_m;
   int npairs = num_sms() / 2;
   if (njobs < npairs) npairs = (int)njobs;
   cudaLaunchConfig_t cfg = {};
@@ -1587,9 +1643,9 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float*
 
 template <int PHASE>
 static int launch_phase(int mode, const ClipProblem& p, const ClipStatsAll& s, const float* ps_loc, float* part,
-                        const float* wscale, cudaStream_t st, float* colpart = nullptr) {
-  if (mode == MC_GEMM_TC_F16X3) return launch_pair<PHASE, 3>(p, s, ps_loc, part, wscale, st, colpart);
-  return launch_pair<PHASE, 1>(p, s, ps_loc, part, wscale, st, colpart);
+                        const float* wscale, cudaStream_t st, float* colpart = nullptr, int chunk_k = -1, int chunks = 1) {
+  if (mode == MC_GEMM_TC_F16X3) return launch_pair<PHASE, 3>(p, s, ps_loc, part, wscale, st, colpart, chunk_k, chunks);
+  return launch_pair<PHASE, 1>(p, s, ps_loc, part, wscale, st, colpart, chunk_k, chunks);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1622,26 +1678,34 @@ int flags_finalize(const uint8_t* flags_all, int B, int b, int row_offset, uint8
 }
 
 // c_part_all (optional, B floats): the column-partials form under row sharding - receives LSE_{i in the owned rows} S_ij
-// for EVERY column j (natural log); c_loc is then not written and the caller merges the ranks' vectors (ranks_lse_merge)
-int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
-          size_t ws_bytes, cudaStream_t st, float* c_part_all) {
-  const size_t need = c_part_all ? stats_colpart_workspace_bytes(p.b, p.B, p.D, mode) : workspace_bytes(p.b, p.B, p.D, mode);
-  MC_REQUIRE(ws_bytes >= need, MC_ERR_WORKSPACE, "clip_stats(tc): workspace %zu < %zu", ws_bytes, need);
-  ClipStatsAll none{nullptr, nullptr, nullptr, nullptr, nullptr};
+// for EVERY column j (natural log); c_loc is then not written and the caller merges the ranks' vectors (ranks_lse_merge).
+// chunks > 1 (b == B only): the probe sweep is launched once per arrived row chunk (stats_chunk), see PairParams.
+static float* stats_colpart_ptr(const ClipProblem& p, int mode, void* ws, float* c_part_all) {
+  if (c_part_all)
+    return reinterpret_cast<float*>(static_cast<char*>(ws) + workspace_bytes(p.b, p.B, p.D, mode) - colpart_bytes(p.b, p.B));
+  return use_colpart(p.b, p.B) ? colpart_slot(ws, p.b, p.B, p.D) : nullptr;
+}
+int stats_begin(const ClipProblem& p, cudaStream_t st) {
   if (p.tile_flags_out) MC_CUDA(cudaMemsetAsync(p.tile_flags_out, 0, tile_flags_bytes(p.b, p.B), st));
-  float* colpart = nullptr;
-  if (c_part_all) {
-    colpart = reinterpret_cast<float*>(static_cast<char*>(ws) + workspace_bytes(p.b, p.B, p.D, mode) - colpart_bytes(p.b, p.B));
-    c_loc = c_part_all;
-  } else if (use_colpart(p.b, p.B)) {
-    colpart = colpart_slot(ws, p.b, p.B, p.D);
-  }
-  int rc = launch_phase<kStats>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st, colpart);
-  if (rc) return rc;
-  // with tile flags the sweep above was the probe form (S, S^T exact, Z from the hi planes -> flags); the exact Z and
+  return MC_OK;
+}
+int stats_chunk(const ClipProblem& p, int mode, int k, int chunks, void* ws, cudaStream_t st, float* c_part_all) {
+  ClipStatsAll none{nullptr, nullptr, nullptr, nullptr, nullptr};
+  return launch_phase<kStats>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st,
+                              stats_colpart_ptr(p, mode, ws, c_part_all), k, chunks);
+}
+int stats_end(const ClipProblem& p, int mode, int chunks, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
+              cudaStream_t st, float* c_part_all) {
+  ClipStatsAll none{nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* colpart = stats_colpart_ptr(p, mode, ws, c_part_all);
+  if (c_part_all) c_loc = c_part_all;
+  int rc;
+  // with tile flags the sweep above was the probe form (S exact, Z from the hi planes -> flags); the exact Z and
   // sum_j P_ij S_ij follow on the flagged tiles only
-  if (p.tile_flags_out && (rc = launch_phase<kStatsZ>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st))) return rc;
-  Split sp = choose_split(p.b, p.B, kOvhStats);
+  if (p.tile_flags_out &&
+      (rc = launch_phase<kStatsZ>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st, nullptr, -1, chunks)))
+    return rc;
+  Split sp = choose_split(p.b, p.B, kOvhStats, chunks);
   stats_finalize_kernel<<<(p.b + 255) / 256, 256, 0, st>>>(static_cast<const float2*>(ws), sp.nsplit, sp.bpad, p.b,
                                                           r_loc, colpart ? nullptr : c_loc, rz_loc, ps_loc);
   MC_LAUNCH_CHECK();
@@ -1651,6 +1715,72 @@ int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_
     colpart_merge_kernel<<<(p.B + 63) / 64, 256, 0, st>>>(colpart, sp.bpad / 32, Bp, p.B, c_loc);
     MC_LAUNCH_CHECK();
   }
+  return MC_OK;
+}
+int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
+          size_t ws_bytes, cudaStream_t st, float* c_part_all) {
+  const size_t need = c_part_all ? stats_colpart_workspace_bytes(p.b, p.B, p.D, mode) : workspace_bytes(p.b, p.B, p.D, mode);
+  MC_REQUIRE(ws_bytes >= need, MC_ERR_WORKSPACE, "clip_stats(tc): workspace %zu < %zu", ws_bytes, need);
+  int rc;
+  if ((rc = stats_begin(p, st))) return rc;
+  if ((rc = stats_chunk(p, mode, -1, 1, ws, st, c_part_all))) return rc;
+  return stats_end(p, mode, 1, r_loc, c_loc, rz_loc, ps_loc, ws, st, c_part_all);
+}
+
+// ---- chunked staging (host-buffer entry): rows [row0, row0 + rows) of a batch that is still arriving.  The planes share
+// ONE power-of-two scale, so the first chunk fixes it with a binade of headroom (slot = 2 max|chunk 0|) and every chunk
+// adds to the true maximum; verify_scale() afterwards flags the (rare) batch whose later rows exceed the headroom - the
+// caller then redoes the step the plain way.  The bound the tile-flag probe relies on (|x| s < 2) holds whenever the
+// flag is clear.
+__global__ void scale_slot_kernel(const unsigned int* __restrict__ true_bits, unsigned int* __restrict__ slot) {
+  const float a = __uint_as_float(*true_bits);
+  *slot = __float_as_uint(a > 0.f && a < INFINITY ? 2.f * a : 0.f);
+}
+__global__ void scale_verify_kernel(const unsigned int* __restrict__ true_bits, const unsigned int* __restrict__ slot,
+                                    int* __restrict__ bad) {
+  *bad = (__uint_as_float(*true_bits) > __uint_as_float(*slot)) ? 1 : 0;
+}
+int prepare_chunk(const float* I, const float* T, int B, int D, int row0, int rows, void* planes_all, unsigned int* words,
+                  cudaStream_t st) {
+  // words: [0] true max so far (zeroed by the caller before the first chunk), [1] the scale slot, [2] the "bad" flag
+  MC_REQUIRE(supported(D) && row0 % 32 == 0 && rows % 32 == 0 && row0 + rows <= (int)round_up((size_t)B, 128), MC_ERR_UNSUPPORTED,
+             "clip_prepare_chunk: D %d / rows [%d, +%d) not supported", D, row0, rows);
+  MC_REQUIRE(aligned(I, 16) && aligned(T, 16) && aligned(planes_all, 256), MC_ERR_ALIGN, "clip_prepare_chunk: alignment");
+  PlanesLayout l = planes_layout(B, D);
+  char* base = static_cast<char*>(planes_all);
+  const int real_rows = row0 + rows <= B ? rows : (B > row0 ? B - row0 : 0);
+  if (real_rows > 0) {
+    const size_t n = (size_t)real_rows * D;
+    int ab = (int)((n + 255) / 256);
+    if (ab > num_sms() * 8) ab = num_sms() * 8;
+    amax_kernel<<<ab, 256, 0, st>>>(I + (size_t)row0 * D, T + (size_t)row0 * D, n, words);
+    MC_LAUNCH_CHECK();
+  }
+  if (row0 == 0) {
+    scale_slot_kernel<<<1, 1, 0, st>>>(words, words + 1);
+    MC_LAUNCH_CHECK();
+  }
+  PeerRows src;
+  for (int q = 0; q < kMaxPeers; ++q) { src.I[q] = nullptr; src.T[q] = nullptr; }
+  src.I[0] = I;
+  src.T[0] = T;
+  const int blocks = rows / 32, blk0 = row0 / 32;
+  __half* Xh = reinterpret_cast<__half*>(base + l.off_hi);
+  __half* Xl = reinterpret_cast<__half*>(base + l.off_lo);
+  __half* XhT = reinterpret_cast<__half*>(base + l.off_hiT);
+  float* hdr = reinterpret_cast<float*>(base + l.off_hdr);
+  float* norm_i = reinterpret_cast<float*>(base + l.off_norm_i);
+  float* norm_t = reinterpret_cast<float*>(base + l.off_norm_t);
+  if (D == 256)
+    stage_fused_kernel<256><<<blocks, 256, 0, st>>>(src, B, B, l.Bp, words + 1, 1, Xh, Xl, XhT, hdr, norm_i, norm_t, blk0);
+  else
+    stage_fused_kernel<128><<<blocks, 256, 0, st>>>(src, B, B, l.Bp, words + 1, 1, Xh, Xl, XhT, hdr, norm_i, norm_t, blk0);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+int verify_scale(unsigned int* words, cudaStream_t st) {
+  scale_verify_kernel<<<1, 1, 0, st>>>(words, words + 1, reinterpret_cast<int*>(words + 2));
+  MC_LAUNCH_CHECK();
   return MC_OK;
 }
 

@@ -159,13 +159,14 @@ def test_loss_host_buffer_entry_point():
 
 
 @pytest.mark.parametrize("B", [16384, 16500, 32768])
-def test_loss_host_entry_strips_match_single_sweep(B):
+def test_loss_host_entry_strips_match_single_sweep(B, monkeypatch):
     """From B = 16384 the host-buffer entry runs the gradient sweep in two row strips and copies a strip
     back while the next is swept: same loss and gradients as the device-resident single sweep, ragged last strip
     included, and identical on a second call (events / copy stream reused correctly)."""
     from mae_clip_b200 import _lib
     lib = _lib.lib()
     D, mode = 256, 1
+    monkeypatch.setenv("MAE_CLIP_HOST_CHUNKS", "1")   # the inbound side has its own test; same operand scale here
     I = loss_ref.make_embeddings(B, D, seed=3).pin_memory()
     T = (0.6 * I + 0.8 * loss_ref.make_embeddings(B, D, seed=4)).pin_memory()   # correlated pairs: a real diagonal
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -190,6 +191,79 @@ def test_loss_host_entry_strips_match_single_sweep(B):
     assert abs(loss.item() - l0.item()) <= 1e-6 * abs(l0.item())
     assert rel_err(dI, dI0.cpu()) < 1e-5 and rel_err(dT, dT0.cpu()) < 1e-5
     assert torch.equal(outs[1][1], dI) and torch.equal(outs[1][2], dT) and torch.equal(outs[1][0], loss)
+
+
+@pytest.mark.parametrize("chunks", [1, 2, 4, 8])
+@pytest.mark.parametrize("B,scale", [(8192, 1.0), (16384, 1.0), (8192, 0.25)])
+def test_loss_host_entry_chunked_inbound_copy(B, scale, chunks, monkeypatch):
+    """The host-buffer entry stages the batch and runs the statistics sweep chunk by chunk behind the inbound copy
+    (MAE_CLIP_HOST_CHUNKS row chunks, arrival-ordered launches of the sweep): every chunk count meets the parity bar
+    against the fp64 blockwise oracle - LayerNorm-scale rows (diagonal tile flags) and the soft regime (x 0.25: every
+    tile flagged) - and stays close to the device-resident step.  (The chunked form fixes the operand scale from the
+    first chunk with a binade of headroom, so the fp16 hi/lo planes differ from the resident step's in the last bit of
+    the lo plane; the fp16 rounding of the gradient weights turns that into ~1e-4 between two results that are each
+    ~3e-4 from fp64.)"""
+    from mae_clip_b200 import _lib
+    lib = _lib.lib()
+    D, mode = 256, 1
+    Id, Td, (ref_loss, ref_dI, ref_dT, _stats) = _c4_batch_and_oracle(B, scale)
+    I, T = Id.cpu().pin_memory(), Td.cpu().pin_memory()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    n0 = lib.mc_clip_loss_fused_workspace_bytes(B, D, mode)
+    ws0 = torch.empty(n0, dtype=torch.uint8, device="cuda")
+    l0, dI0, dT0 = torch.zeros(1, device="cuda"), torch.empty_like(Id), torch.empty_like(Td)
+    _lib.check(lib.mc_clip_loss_fwd_bwd(Id.data_ptr(), Td.data_ptr(), B, D, 1.0, mode, l0.data_ptr(), dI0.data_ptr(),
+                                        dT0.data_ptr(), ws0.data_ptr(), n0, st), "mc_clip_loss_fwd_bwd")
+    monkeypatch.setenv("MAE_CLIP_HOST_CHUNKS", str(chunks))
+    n = lib.mc_clip_loss_host_workspace_bytes(B, D, mode)
+    ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        dI, dT = torch.full_like(I, float("nan")).pin_memory(), torch.full_like(T, float("nan")).pin_memory()
+        loss = torch.zeros(1).pin_memory()
+        _lib.check(lib.mc_clip_loss_fwd_bwd_host(I.data_ptr(), T.data_ptr(), B, D, 1.0, mode, loss.data_ptr(),
+                                                 dI.data_ptr(), dT.data_ptr(), ws.data_ptr(), n, st),
+                   "mc_clip_loss_fwd_bwd_host")
+        assert torch.isfinite(dI).all() and torch.isfinite(dT).all()
+        assert abs(loss.item() - ref_loss) <= LOSS_TOL * abs(ref_loss)
+        eI, eT = rel_err(dI, ref_dI), rel_err(dT, ref_dT)
+        assert eI < GRAD_TOL and eT < GRAD_TOL, (eI, eT)
+        assert abs(loss.item() - l0.item()) <= 1e-5 * abs(l0.item())
+        assert rel_err(dI, dI0.cpu()) < 5e-4 and rel_err(dT, dT0.cpu()) < 5e-4
+
+
+def test_loss_host_entry_chunked_scale_outgrown(monkeypatch, capfd):
+    """Rows of a later chunk exceed the headroom of the first chunk's scale: the device-side check trips and the
+    step is redone from the resident copy - the caller sees the plain result."""
+    from mae_clip_b200 import _lib
+    lib = _lib.lib()
+    B, D, mode = 8192, 256, 1
+    I = loss_ref.make_embeddings(B, D, seed=7)
+    T = 0.6 * I + 0.8 * loss_ref.make_embeddings(B, D, seed=8)
+    monkeypatch.setenv("MAE_CLIP_HOST_CHUNKS", "4")
+    I[: B // 4] *= 0.2          # chunk 0 is small: the later rows are 5x its maximum
+    T[: B // 4] *= 0.2
+    I, T = I.pin_memory(), T.pin_memory()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    n0 = lib.mc_clip_loss_fused_workspace_bytes(B, D, mode)
+    ws0 = torch.empty(n0, dtype=torch.uint8, device="cuda")
+    Id, Td = I.cuda(), T.cuda()
+    l0, dI0, dT0 = torch.zeros(1, device="cuda"), torch.empty_like(Id), torch.empty_like(Td)
+    _lib.check(lib.mc_clip_loss_fwd_bwd(Id.data_ptr(), Td.data_ptr(), B, D, 1.0, mode, l0.data_ptr(), dI0.data_ptr(),
+                                        dT0.data_ptr(), ws0.data_ptr(), n0, st), "mc_clip_loss_fwd_bwd")
+    n = lib.mc_clip_loss_host_workspace_bytes(B, D, mode)
+    ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dI, dT = torch.full_like(I, float("nan")).pin_memory(), torch.full_like(T, float("nan")).pin_memory()
+    loss = torch.zeros(1).pin_memory()
+    monkeypatch.setenv("MAE_CLIP_HOST_TRACE", "1")      # the library prints its timeline: shows which path ran
+    capfd.readouterr()
+    _lib.check(lib.mc_clip_loss_fwd_bwd_host(I.data_ptr(), T.data_ptr(), B, D, 1.0, mode, loss.data_ptr(),
+                                             dI.data_ptr(), dT.data_ptr(), ws.data_ptr(), n, st),
+               "mc_clip_loss_fwd_bwd_host")
+    err = capfd.readouterr().err
+    assert "staged[1]" in err and err.rstrip().splitlines()[-1].endswith("end")     # chunked attempt ...
+    assert any(line.endswith(" staged") for line in err.splitlines())                # ... then the plain redo
+    assert abs(loss.item() - l0.item()) <= 1e-6 * abs(l0.item())
+    assert rel_err(dI, dI0.cpu()) < 1e-5 and rel_err(dT, dT0.cpu()) < 1e-5
 
 
 def test_abi_error_codes():

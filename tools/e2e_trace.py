@@ -1,12 +1,9 @@
-"""A/B of the host-buffer entry's inbound chunk count (MAE_CLIP_HOST_CHUNKS) and outbound strip count
-(MAE_CLIP_HOST_STRIPS): wall-clock per call of
-mc_clip_loss_fwd_bwd_host at B = 32768, pinned host buffers, L2 flushed between calls.
-Usage (GPU box): python tools/e2e_strips.py [B]"""
+"""Timeline of one mc_clip_loss_fwd_bwd_host call (MAE_CLIP_HOST_TRACE=1: CUDA-event marks after every copy and phase,
+printed to stderr by the library) for a few inbound-chunk / outbound-strip settings.
+Usage (GPU box): python tools/e2e_trace.py [B] 2> trace.log"""
 import ctypes
-import json
 import os
 import sys
-import time
 
 import torch
 
@@ -24,18 +21,17 @@ n = lib.mc_clip_loss_host_workspace_bytes(B, D, mode)
 ws = torch.empty(n, dtype=torch.uint8, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-out = {}
-combos = [(c, s) for c in (1, 2, 4, 8) for s in (1, 2, 4)] + [(4, 3), (4, 6), (16, 2)]
-for chunks, strips in combos:
+for chunks, strips, last in [(1, 1, 0), (1, 2, 0.5), (2, 2, 0.5), (2, 2, 0.375), (2, 2, 0.3125), (2, 2, 0.25),
+                             (2, 2, 0.1875), (2, 3, 0.125), (2, 3, 0.1875), (4, 2, 0.25)]:
     os.environ["MAE_CLIP_HOST_CHUNKS"] = str(chunks)
     os.environ["MAE_CLIP_HOST_STRIPS"] = str(strips)
-    ts = []
-    for it in range(8):
+    os.environ["MAE_CLIP_HOST_LAST_STRIP"] = str(last)
+    for it in range(4):
         flush.fill_(1)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        if it == 3:
+            os.environ["MAE_CLIP_HOST_TRACE"] = "1"
+            print(f"---- chunks {chunks} strips {strips} last {last}", file=sys.stderr, flush=True)
         _lib.check(lib.mc_clip_loss_fwd_bwd_host(I.data_ptr(), T.data_ptr(), B, D, 1.0, mode, loss.data_ptr(),
                                                  dI.data_ptr(), dT.data_ptr(), ws.data_ptr(), n, st), "host")
-        ts.append((time.perf_counter() - t0) * 1e3)
-    out[f"chunks{chunks}_strips{strips}"] = {"ms_median": sorted(ts[2:])[len(ts[2:]) // 2], "ms_min": min(ts[2:]), "loss": loss.item()}
-print(json.dumps(out))
+        os.environ.pop("MAE_CLIP_HOST_TRACE", None)
