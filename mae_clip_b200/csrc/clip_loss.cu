@@ -36,6 +36,9 @@ static int eff_mode(int mode, int D) {
 struct FusedLayout {
   size_t off_vec, off_flags, off_planes, off_phase, total;
   size_t vec_stride, flags_bytes;
+  // stored-weights gradient (tc::bwd_rows / tc::bwd_cols): the fp16 weights of all B x B pairs, the un-scaled soft-target
+  // part of dI and the column half's partials; all zero when that form is off
+  size_t off_w, off_diz, off_cols, cols_bytes, phase_bytes;
 };
 static FusedLayout fused_layout(int B, int D, int mode) {
   mode = eff_mode(mode, D);
@@ -49,7 +52,16 @@ static FusedLayout fused_layout(int B, int D, int mode) {
   l.off_phase = l.off_planes + round_up(planes, 256);
   size_t phase = (mode == MC_GEMM_SIMT_FP32) ? simt::workspace_bytes(B, B, D)
                                              : tc::workspace_bytes(B, B, D, mode);
-  l.total = l.off_phase + round_up(phase, 256);
+  l.phase_bytes = round_up(phase, 256);
+  l.total = l.off_phase + l.phase_bytes;
+  l.off_w = l.off_diz = l.off_cols = l.cols_bytes = 0;
+  if (mode != MC_GEMM_SIMT_FP32 && tc::stored_form_enabled(B, B, D)) {
+    l.off_w = l.total;
+    l.off_diz = l.off_w + tc::stored_weights_bytes(B, B);
+    l.off_cols = l.off_diz + round_up(round_up((size_t)B, 128) * D * sizeof(float), 256);
+    l.cols_bytes = tc::bwd_cols_workspace_bytes(B, B, D);
+    l.total = l.off_cols + l.cols_bytes;
+  }
   return l;
 }
 
@@ -210,7 +222,7 @@ size_t mc_clip_loss_fused_workspace_bytes(int B, int D, int mode) {
 // kernels (rows < 0) and after each strip's gradient kernels have been enqueued (row0, rows) - the host-buffer entry
 // uses it to start the device -> host copy of a finished strip while the next one is still being swept.
 struct StripHook {
-  int (*fn)(void* ctx, int row0, int rows);
+  int (*fn)(void* ctx, int row0, int rows, int what);   // what: 1 = dT rows are final, 2 = dI rows, 3 = both
   void* ctx;
 };
 // MAE_CLIP_HOST_TRACE=1: the host-buffer entry records a timing event after every copy and phase and prints the
@@ -269,7 +281,7 @@ static int fused_run(const float* I, const float* T, int B, int D, float tau, in
   float* ps = reinterpret_cast<float*>(base + l.off_vec + 5 * l.vec_stride);
   void* planes = base + l.off_planes;
   void* phase = base + l.off_phase;
-  size_t phase_bytes = l.total - l.off_phase;
+  size_t phase_bytes = l.phase_bytes;
   // tile flags: the statistics sweep marks the tiles that carry soft-target mass; the later sweeps skip the rest
   // (MAE_CLIP_DENSE=1 keeps every tile: the A/B switch)
   static const bool dense = getenv("MAE_CLIP_DENSE") != nullptr && getenv("MAE_CLIP_DENSE")[0] == '1';
@@ -304,7 +316,7 @@ static int fused_run(const float* I, const float* T, int B, int D, float tau, in
                             phase_bytes, stream)))
     return rc;
   trace_mark("rowloss", -1, static_cast<cudaStream_t>(stream));
-  if (hook && (rc = hook->fn(hook->ctx, -1, 0))) return rc;
+  if (hook && (rc = hook->fn(hook->ctx, -1, 0, 0))) return rc;
   if (!dI) return MC_OK;
   // strips of whole 128-row blocks; a strip whose partial-sum workspace would not fit the step's buffer (more
   // column splits per row block) folds the sweep back into one launch.  last_frac > 0: the LAST strip takes that share
@@ -328,15 +340,47 @@ static int fused_run(const float* I, const float* T, int B, int D, float tau, in
     if (rows_k <= 0 || mc_clip_loss_workspace_bytes(rows_k, B, D, mode) > phase_bytes) n_strips = 1;
   }
   const int n_tiles = n_blocks;  // column tiles of B = row blocks of B
+  const bool stored = l.off_w != 0;
+  const int Bp = n_blocks * 128;
   for (int k = 0; k < n_strips; ++k) {
     const int row0 = n_strips == 1 ? 0 : strip_first[k] * 128;
     const int rows = n_strips == 1 ? B : (strip_first[k + 1] * 128 <= B ? strip_first[k + 1] * 128 : B) - row0;
     const uint8_t* fl = flags ? flags + (size_t)(row0 / 128) * n_tiles : nullptr;
-    if ((rc = mc_clip_bwd(I, T, planes, rows, B, D, row0, tau, mode, r, c, rz, g, q, nullptr, dI + (size_t)row0 * D,
-                          dT + (size_t)row0 * D, fl, phase, phase_bytes, stream)))
-      return rc;
-    trace_mark("bwd strip", k, static_cast<cudaStream_t>(stream));
-    if (hook && (rc = hook->fn(hook->ctx, row0, rows))) return rc;
+    if (stored) {
+      // row half: dT of the strip is final; the strip's weights and the soft-target part of its dI wait for the column half
+      ClipProblem p{I, T, planes, rows, B, D, row0, tau};
+      p.tile_flags = fl;
+      ClipStatsAll s{r, c, rz, g, q};
+      if ((rc = tc::bwd_rows(p, eff_mode(mode, D), s, nullptr, dT + (size_t)row0 * D,
+                             reinterpret_cast<float*>(base + l.off_diz) + (size_t)row0 * D,
+                             base + l.off_w + (size_t)row0 * Bp * 2, phase, phase_bytes,
+                             static_cast<cudaStream_t>(stream))))
+        return rc;
+      trace_mark("bwd rows strip", k, static_cast<cudaStream_t>(stream));
+      if (hook && (rc = hook->fn(hook->ctx, row0, rows, 1))) return rc;
+    } else {
+      if ((rc = mc_clip_bwd(I, T, planes, rows, B, D, row0, tau, mode, r, c, rz, g, q, nullptr, dI + (size_t)row0 * D,
+                            dT + (size_t)row0 * D, fl, phase, phase_bytes, stream)))
+        return rc;
+      trace_mark("bwd strip", k, static_cast<cudaStream_t>(stream));
+      if (hook && (rc = hook->fn(hook->ctx, row0, rows, 3))) return rc;
+    }
+  }
+  if (stored) {
+    // column half, in as many strips of output rows as the row half had (the host entry copies a finished strip back
+    // while the next is computed)
+    ClipProblem p{I, T, planes, B, B, D, 0, tau};
+    ClipStatsAll s{r, c, rz, g, q};
+    for (int k = 0; k < n_strips; ++k) {
+      const int j0 = n_strips == 1 ? 0 : strip_first[k] * 128;
+      const int j1 = n_strips == 1 ? B : (strip_first[k + 1] * 128 <= B ? strip_first[k + 1] * 128 : B);
+      if ((rc = tc::bwd_cols(p, eff_mode(mode, D), s, nullptr, base + l.off_w, B, 0, j0, j1,
+                             reinterpret_cast<const float*>(base + l.off_diz) + (size_t)j0 * D, dI + (size_t)j0 * D,
+                             base + l.off_cols, l.cols_bytes, static_cast<cudaStream_t>(stream))))
+        return rc;
+      trace_mark("bwd cols strip", k, static_cast<cudaStream_t>(stream));
+      if (hook && (rc = hook->fn(hook->ctx, j0, j1 - j0, 2))) return rc;
+    }
   }
   return MC_OK;
 }
@@ -359,14 +403,14 @@ size_t mc_clip_loss_host_workspace_bytes(int B, int D, int mode) {
 namespace {
 struct HostCopyCtx {
   cudaStream_t st, copy;
-  cudaEvent_t ev[8];
+  cudaEvent_t ev[16];
   int n_ev;
   const float *loss_dev, *gI, *gT;
   float *loss_host, *dI_host, *dT_host;
   int D;
   bool want_grad;
 };
-int host_copy_hook(void* vctx, int row0, int rows) {
+int host_copy_hook(void* vctx, int row0, int rows, int what) {
   HostCopyCtx* c = static_cast<HostCopyCtx*>(vctx);
   if (rows <= 0 || row0 < 0) {  // after the loss kernels
     MC_CUDA(cudaMemcpyAsync(c->loss_host, c->loss_dev, 4, cudaMemcpyDeviceToHost, c->st));
@@ -374,12 +418,12 @@ int host_copy_hook(void* vctx, int row0, int rows) {
   }
   if (!c->want_grad) return MC_OK;
   const size_t off = (size_t)row0 * c->D, bytes = (size_t)rows * c->D * 4;
-  MC_REQUIRE(c->n_ev < 8, MC_ERR_BAD_ARG, "clip_loss_host: too many strips");
+  MC_REQUIRE(c->n_ev < 16, MC_ERR_BAD_ARG, "clip_loss_host: too many strips");
   cudaEvent_t ev = c->ev[c->n_ev++];
   MC_CUDA(cudaEventRecord(ev, c->st));
   MC_CUDA(cudaStreamWaitEvent(c->copy, ev, 0));
-  MC_CUDA(cudaMemcpyAsync(c->dT_host + off, c->gT + off, bytes, cudaMemcpyDeviceToHost, c->copy));
-  MC_CUDA(cudaMemcpyAsync(c->dI_host + off, c->gI + off, bytes, cudaMemcpyDeviceToHost, c->copy));
+  if (what & 1) MC_CUDA(cudaMemcpyAsync(c->dT_host + off, c->gT + off, bytes, cudaMemcpyDeviceToHost, c->copy));
+  if (what & 2) MC_CUDA(cudaMemcpyAsync(c->dI_host + off, c->gI + off, bytes, cudaMemcpyDeviceToHost, c->copy));
   trace_mark("d2h strip done", c->n_ev - 1, c->copy);
   return MC_OK;
 }
@@ -462,7 +506,7 @@ int mc_clip_loss_fwd_bwd_host(const float* I_host, const float* T_host, int B, i
   if (want_grad || chunks > 1) {
     if ((rc = copy_stream_for_current_device(&ctx.copy))) return rc;
     bool ok = true;
-    for (; ok && want_grad && n_created < n_strips; ++n_created)
+    for (; ok && want_grad && n_created < 2 * n_strips; ++n_created)   // row half + column half of every strip
       if (cudaEventCreateWithFlags(&ctx.ev[n_created], cudaEventDisableTiming) != cudaSuccess) { ok = false; break; }
     const int want_arrived = chunks > 1 ? chunks + 1 : 0;  // + the "stream is free" event the copy stream waits for
     for (; ok && n_arrived < want_arrived; ++n_arrived)

@@ -60,6 +60,14 @@ int prepare_chunk(const float* I, const float* T, int B, int D, int row0, int ro
                   cudaStream_t st);
 int verify_scale(unsigned int* words, cudaStream_t st);
 bool stats_chunkable(int B, int D, int chunks);
+// stored-weights gradient: row half (S recompute -> dT, fp16 weight strip W) + column half (dI from W)
+bool stored_form_enabled(int b, int B, int D);
+size_t stored_weights_bytes(int b, int B);
+size_t bwd_cols_workspace_bytes(int w_rows, int n_cols, int D);
+int bwd_rows(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, float* dT_loc, float* dIz_loc,
+             void* W_rows, void* ws, size_t ws_bytes, cudaStream_t st);
+int bwd_cols(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, const void* W, int w_rows,
+             int w_row_offset, int j0, int j1, const float* dIz, float* dI_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int ranks_lse_merge(const float* parts, int n, int64_t stride, int B, float* c, cudaStream_t st);
 int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* ps_loc, float* g_loc,
             float* q_loc, float* loss_part, void* ws, size_t ws_bytes, cudaStream_t st);

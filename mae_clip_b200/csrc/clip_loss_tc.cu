@@ -23,6 +23,7 @@
 //   * tile flags (PairParams::flags / flags_out): tiles that cannot hold soft-target mass (P_ij < 2^-44 throughout)
 //     skip their Z work in every sweep - see DESIGN.md section 4.1.
 #include <stdlib.h>
+#include <string.h>
 
 #include "clip_loss.cuh"
 #include "tc_ptx.cuh"
@@ -42,7 +43,11 @@ constexpr int kEpiThreads = 256;
 constexpr int kMaxSplit = 16;
 constexpr int kIssuers = 1;         // MMA-issuing warps per leader CTA (see the issuer role)
 
-enum Phase { kStats = 0, kRowLoss = 1, kBwd = 2, kStatsZ = 3 };
+enum Phase { kStats = 0, kRowLoss = 1, kBwd = 2, kStatsZ = 3, kBwdW = 4 };
+// kBwdW is the row half of the "stored weights" gradient: like kBwd it recomputes S (and, on flagged tiles only, S^T and
+// Z) and accumulates dT_i, but instead of recomputing the transposed strip everywhere to form dS^T for dI_i, it writes
+// the fp16 weight tile dS_ij to global memory (PairParams::wout); colgrad_kernel then forms dI_j = sum_i dS_ij T_i from
+// the stored tiles (5 GEMM units per tile pair instead of 8).  dI_i of this sweep holds the soft-target (dZ) part only.
 // kStats with tile flags requested is the PROBE form: S, S^T at full precision, Z from the hi planes only - enough to
 // tell which tiles can hold soft-target mass; kStatsZ then computes S and the exact Z on those tiles (rz, sum P S).
 
@@ -91,6 +96,7 @@ struct PairParams {
   // epilogue warp writes the log-sum-exp of its 32 rows for each of its 32 columns, log2 units, to
   // colpart[(strip row / 32) * Bp + column]; mc::tc::colpart_merge folds them into c.
   float* colpart;
+  __half* wout;                        // kBwdW: (bpad x Bp) fp16 weights 2B dS_ij / tau * wscale / s, row = strip row
   // Arrival-ordered launches of the statistics sweep (host-buffer entry: the batch arrives over PCIe in `chunks` row
   // chunks of chunk_blocks row blocks; nsplit = chunks * chunk_m, so a column split lies inside one chunk).  Launch k
   // takes the jobs (row block, column split) whose LATER chunk is k: everything that became computable when chunk k
@@ -221,14 +227,16 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             const __grid_constant__ CUtensorMap map_t, const PairParams p) {
   // TMEM: tile buffers of 3 x 64 columns (S, St, Z) from column 0; the gradient sweep keeps one tile
   // buffer (the epilogue empties it into registers at once) and its accumulators at 256 (dT), 256 + D/2 (dI)
-  constexpr int kNBuf = (PHASE == kBwd) ? 1 : 2;
+  constexpr bool kIsBwd = PHASE == kBwd || PHASE == kBwdW;
+  constexpr bool kW = PHASE == kBwdW;
+  constexpr int kNBuf = kIsBwd ? 1 : 2;
   constexpr uint32_t kAccCol = 256;
   // Forward sweeps of the 3-pass engine keep the LO plane of the CTA's rows resident too (the gradient sweep has no
   // room: weights + X^T tiles): a third less L2 -> shared-memory traffic per tile, five ring slots left.
-  constexpr bool kResLo = (PHASE != kBwd) && PASSES == 3;
+  constexpr bool kResLo = !kIsBwd && PASSES == 3;
   constexpr int kOffAlo = kOffStage;                                   // resident lo plane (64 KB) when kResLo
   constexpr int kOffRing = kResLo ? kOffStage + 65536 : kOffStage;
-  constexpr int kSlots = (PHASE == kBwd) ? kSlotsBwd : (kResLo ? kSlotsFwd - 65536 / kSlotBytes : kSlotsFwd);
+  constexpr int kSlots = kIsBwd ? kSlotsBwd : (kResLo ? kSlotsFwd - 65536 / kSlotBytes : kSlotsFwd);
   static_assert(kOffRing + kSlots * kSlotBytes <= kOffConst, "ring overlaps the column constants");
 
   extern __shared__ uint8_t smem_raw[];
@@ -297,37 +305,41 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               tma_load_2d_pair(base + kOffAlo + c * kChunkBytes, &map_a_lo, bar(kAFull), c * 64, row_a);
           for (int t = t0; t < t1; ++t) {
             if ((PHASE == kRowLoss || PHASE == kStatsZ) && p.flags && !p.flags[(size_t)rb * p.n_tiles + t]) continue;
+            // kBwdW: a tile without soft-target mass needs S only - no T_j planes, no I_i lo
+            const bool zt = !kW || !p.flags || p.flags[(size_t)rb * p.n_tiles + t] != 0;
             const int j0 = t * kTileN + 32 * (int)rank, j1 = j0 + 64;
             for (int c = 0; c < nkc; ++c) {
               const int ci = c * 64, ct = D + c * 64;
               uint32_t fb;
-              auto acquire = [&]() -> uint32_t {  // next ring slot: wait until the MMAs released it, arm its barrier
+              auto acquire = [&](uint32_t bytes) -> uint32_t {  // next ring slot: wait until the MMAs released it, arm its barrier
                 const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
                 ++it;
                 mbar_wait(bar(kEmpty0 + slot), par ^ 1);
                 fb = bar(kFull0 + slot);
-                if (leader) mbar_arrive_expect_tx(fb, 2u * kSlotBytes);
+                if (leader) mbar_arrive_expect_tx(fb, bytes);
                 return base + kOffRing + slot * kSlotBytes;
               };
               if (PASSES == 3) {
                 uint32_t sb;
                 if (!kResLo) {
-                  sb = acquire();
-                  tma_load_2d_pair(sb, &map_a_lo, fb, ci, row_a);                       // I_i lo
+                  sb = acquire(zt ? 2u * kSlotBytes : 2u * kChunkBytes);
+                  if (zt) tma_load_2d_pair(sb, &map_a_lo, fb, ci, row_a);               // I_i lo
                   tma_load_2d_pair(sb + kChunkBytes, &map_a_lo, fb, ct, row_a);         // T_i lo
                 }
-                sb = acquire();
+                sb = acquire(2u * kSlotBytes);
                 tma_load_2d_pair(sb, &map_b_hi, fb, ci, j0);                            // I_j hi
                 tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ci, j1);
                 tma_load_2d_pair(sb + kChunkBytes, &map_b_lo, fb, ci, j0);              // I_j lo
                 tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_lo, fb, ci, j1);
-                sb = acquire();
-                tma_load_2d_pair(sb, &map_b_hi, fb, ct, j0);                            // T_j hi
-                tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ct, j1);
-                tma_load_2d_pair(sb + kChunkBytes, &map_b_lo, fb, ct, j0);              // T_j lo
-                tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_lo, fb, ct, j1);
+                if (zt) {
+                  sb = acquire(2u * kSlotBytes);
+                  tma_load_2d_pair(sb, &map_b_hi, fb, ct, j0);                          // T_j hi
+                  tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ct, j1);
+                  tma_load_2d_pair(sb + kChunkBytes, &map_b_lo, fb, ct, j0);            // T_j lo
+                  tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_lo, fb, ct, j1);
+                }
               } else {
-                const uint32_t sb = acquire();
+                const uint32_t sb = acquire(2u * kSlotBytes);
                 tma_load_2d_pair(sb, &map_b_hi, fb, ci, j0);                            // I_j hi
                 tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ci, j1);
                 tma_load_2d_pair(sb + kChunkBytes, &map_b_hi, fb, ct, j0);              // T_j hi
@@ -339,21 +351,23 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       }
     } else if (warp == 2) {
       // ========================================================= TMA producer: X^T half tiles (gradient GEMMs)
-      if (PHASE == kBwd && elect_one()) {
+      if (kIsBwd && elect_one()) {
         const uint32_t xt_bytes = (uint32_t)(D / 2) * 128u;  // D/2 rows x 64 j fp16
         uint32_t tt = 0;
         for (int job = pair_id; job < njobs; job += npairs) {
-          int rb_unused, sp;
-          pair_job(p, job, rb_unused, sp);
+          int rb, sp;
+          pair_job(p, job, rb, sp);
           const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
           for (int t = t0; t < t1; ++t, ++tt) {
+            // kBwdW: T_j^T feeds the dZ GEMM only (dI's S part comes from the stored weights)
+            const bool zt = !kW || !p.flags || p.flags[(size_t)rb * p.n_tiles + t] != 0;
             for (int h = 0; h < 2; ++h) {
               // the previous half's MMAs are done with the buffer: (tt-1, 1) before (tt, 0); (tt, 0) before (tt, 1)
               if (h == 0) mbar_wait(bar(kGradDone1), (tt & 1) ^ 1); else mbar_wait(bar(kGradDone), tt & 1);
-              if (leader) mbar_arrive_expect_tx(bar(kXTFull), 2u * 2u * xt_bytes);
+              if (leader) mbar_arrive_expect_tx(bar(kXTFull), (zt ? 2u : 1u) * 2u * xt_bytes);
               const int jx = t * kTileN + 64 * h;
               tma_load_2d_pair(base + kOffXT, &map_t, bar(kXTFull), jx, (int)rank * (D / 2));
-              tma_load_2d_pair(base + kOffXT + xt_bytes, &map_t, bar(kXTFull), jx, D + (int)rank * (D / 2));
+              if (zt) tma_load_2d_pair(base + kOffXT + xt_bytes, &map_t, bar(kXTFull), jx, D + (int)rank * (D / 2));
             }
           }
         }
@@ -376,6 +390,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         uint32_t it = 0, tt = 0, hh = 0, jj = 0;
         // one column half of a tile's gradient GEMMs: dT += W_S I_j + W_Z T_j, dI += W_St T_j + W_Z I_j
         bool zg = true;  // does the tile whose gradient GEMMs are being issued carry soft-target mass (tile flag)?
+        bool di_live = false;  // kBwdW: has this job's dI accumulator been written yet (only flagged tiles touch it)?
         auto grad_half = [&](int h, bool first_of_job) {
           mbar_wait(bar(kWFull), hh & 1);
           mbar_wait(bar(kXTFull), hh & 1);
@@ -392,10 +407,15 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               if (zg) mma_f16_pair(tDT, kwZ, kxT, idesc_grad, 1u);               // dT += (tau/2 dZs) T_j
             }
             if (do_z) {
-              mma_f16_pair(tDI, desc_advance_k(wSt, ks), kxT, idesc_grad, acc);  // dI += (dS^T/tau) T_j
-              if (zg) mma_f16_pair(tDI, kwZ, kxI, idesc_grad, 1u);               // dI += (tau/2 dZs) I_j
+              if (kW) {
+                if (zg) mma_f16_pair(tDI, kwZ, kxI, idesc_grad, (di_live || ks > 0) ? 1u : 0u);  // dI += (tau/2 dZs) I_j
+              } else {
+                mma_f16_pair(tDI, desc_advance_k(wSt, ks), kxT, idesc_grad, acc);  // dI += (dS^T/tau) T_j
+                if (zg) mma_f16_pair(tDI, kwZ, kxI, idesc_grad, 1u);               // dI += (tau/2 dZs) I_j
+              }
             }
           }
+          if (zg) di_live = true;
           mma_commit_pair(bar(h == 0 ? kGradDone : kGradDone1), 3);
         };
         for (int job = pair_id; job < njobs; job += npairs) {
@@ -408,11 +428,12 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           mbar_wait(bar(kAFull), jpar);
           tc_fence_after();
           bool zf = true, zf_prev = true;
+          di_live = false;
           const bool zprobe = PHASE == kStats && p.flags_out != nullptr;  // Z from the hi planes only
           for (int t = t0; t < t1; ++t) {
             if ((PHASE == kRowLoss || PHASE == kStatsZ) && frow && !frow[t]) continue;   // every role skips the same tiles
             zf_prev = zf;
-            zf = (PHASE != kBwd) || !frow || frow[t] != 0;         // gradient sweep: recompute Z only where P lives
+            zf = !kIsBwd || !frow || frow[t] != 0;                 // gradient sweep: recompute Z only where P lives
             zg = zf_prev;                                          // the woven gradient GEMMs belong to tile t - 1
             const uint32_t buf = tt % kNBuf, use = tt / kNBuf;
             mbar_wait(bar(kTmemEmpty0 + buf), (use & 1) ^ 1);
@@ -421,7 +442,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             // The gradient GEMMs of tile t-1 are woven into the recompute of tile t: half 0 after the
             // first chunks (its weights are ready by then), half 1 after the last chunk, so the
             // single weight / X^T buffers are refilled while the tensor cores stay busy.
-            const bool lagged = PHASE == kBwd && t > t0;
+            const bool lagged = kIsBwd && t > t0;
             for (int c = 0; c < nkc; ++c) {
               if (lagged && c == nkc - 1) grad_half(0, t - 1 == t0);
               uint32_t slot_bar = 0;
@@ -471,6 +492,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                   }
                 }
                 mma_commit_pair(slot_bar, 3);
+                if (!kW || zf) {   // kBwdW: no T_j slot in the ring for a tile without soft-target mass
                 sb = next_full();
                 {
                   const uint64_t bT = smem_desc_sw128(sb), bTl = smem_desc_sw128(sb + kChunkBytes);
@@ -496,6 +518,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                   }
                 }
                 mma_commit_pair(slot_bar, 3);
+                }
                 if (!kResLo) mma_commit_pair(a_bar, 3);
               } else {
                 const uint32_t sb = next_full();
@@ -507,7 +530,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                   const uint64_t kbI = desc_advance_k(bI, ks), kbT = desc_advance_k(bT, ks);
                   if (do_s && PHASE != kRowLoss) {
                     mma_f16_pair(tS, kT, kbI, idesc_tile, acc);
-                    if (PHASE != kStatsZ && !(PHASE == kStats && p.colpart)) mma_f16_pair(tSt, kI, kbT, idesc_tile, acc);
+                    if (PHASE != kStatsZ && !(PHASE == kStats && p.colpart) && (!kW || zf)) mma_f16_pair(tSt, kI, kbT, idesc_tile, acc);
                   }
                   if (do_z && zf) {
                     mma_f16_pair(tZ, kI, kbI, idesc_tile, acc);
@@ -518,7 +541,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               }
             }
             mma_commit_pair(bar(kTmemFull0 + buf), 3);
-            if (PHASE == kBwd) {
+            if (kIsBwd) {
               if (t == t0) {
                 mbar_wait(bar(kAccEmpty), jpar ^ 1);  // the previous job's accumulators were read out
                 tc_fence_after();
@@ -528,7 +551,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             }
             ++tt;
           }
-          if (PHASE == kBwd) {
+          if (kIsBwd) {
             zg = zf;  // the last tile's own gradient GEMMs
             grad_half(0, t1 - 1 == t0);
             grad_half(1, false);
@@ -584,11 +607,11 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       // per-row statistics, log2 domain: r2 = r log2(e), ... ; gh = 2B g log2(e)
       float r2_i = 0.f, c2_i = 0.f, rz2_i = 0.f, gh_i = 0.f, q_i = 0.f;
       if (PHASE != kStats && PHASE != kStatsZ && row_ok) { r2_i = p.r[gi] * kL2e; c2_i = p.c[gi] * kL2e; rz2_i = p.rz[gi] * kL2e; }
-      if (PHASE == kBwd && row_ok) { gh_i = p.g[gi] * (2.f * (float)p.B) * kL2e; q_i = p.q[gi]; }
+      if (kIsBwd && row_ok) { gh_i = p.g[gi] * (2.f * (float)p.B) * kL2e; q_i = p.q[gi]; }
       float wS = 0.f, wZ = 0.f;
       bool fast = false;
       float m_rc = 0.f, m_z = 0.f, fA_i = 0.f, fC_i = 0.f, fFQ_i = 0.f;
-      if (PHASE == kBwd) {
+      if (kIsBwd) {
         const float wsc = p.wscale[0];
         wS = inv_s * p.inv_tau * wsc;              // 2B dS      -> fp16 weight of X_j (scaled plane)
         wZ = inv_s * p.half_tau * wsc * kLn2;      // 2B dZs (log2 units) -> fp16 weight
@@ -618,7 +641,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 
       for (int t = t0; t < t1; ++t) {
         if ((PHASE == kRowLoss || PHASE == kStatsZ) && frow && !frow[t]) continue;       // every role skips the same tiles
-        const bool zf = (PHASE != kBwd) || !frow || frow[t] != 0;  // gradient sweep: does this tile carry P mass?
+        const bool zf = !kIsBwd || !frow || frow[t] != 0;          // gradient sweep: does this tile carry P mass?
         // ---- per-column statistics of this tile -> shared memory, one field per 128-float row
         float* cst = consts + (tt & 1) * (8 * 128);
         if (PHASE != kStats && PHASE != kStatsZ) {
@@ -627,14 +650,14 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             const bool ok = jcol < p.B;
             const float c2 = ok ? p.c[jcol] * kL2e : 0.f, rz2 = ok ? p.rz[jcol] * kL2e : 0.f;
             cst[1 * 128 + tid_e] = -c2;                                                                 // -c2_j
-            if (PHASE == kBwd && fast) {
+            if (kIsBwd && fast) {
               cst[2 * 128 + tid_e] = ok ? ex2f(m_z - rz2) : 0.f;                                        // B_j
               cst[4 * 128 + tid_e] = ok ? ex2f(m_rc - c2) * p.q[jcol] : 0.f;                            // D_j q_j
             } else {
               cst[2 * 128 + tid_e] = -rz2;                                                              // -rz2_j
-              if (PHASE == kBwd) cst[4 * 128 + tid_e] = ok ? p.q[jcol] : 0.f;                           // q_j
+              if (kIsBwd) cst[4 * 128 + tid_e] = ok ? p.q[jcol] : 0.f;                           // q_j
             }
-          } else if (PHASE == kBwd) {
+          } else if (kIsBwd) {
             const int jcol = t * kTileN + tid_e - 128;
             const bool ok = jcol < p.B;
             const float r2 = ok ? p.r[jcol] * kL2e : 0.f;
@@ -656,7 +679,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         float vs[32], vt[32], vz[32];
         if (PHASE != kRowLoss) tmem_ld32(tS, vs);
         const bool colpart = PHASE == kStats && p.colpart != nullptr;
-        if (PHASE != kRowLoss && PHASE != kStatsZ && !colpart) tmem_ld32(tSt, vt);
+        if (PHASE != kRowLoss && PHASE != kStatsZ && !colpart && (!kW || zf)) tmem_ld32(tSt, vt);
         if (zf) tmem_ld32(tZ, vz);   // a tile without soft-target mass has no Z accumulator at all
         tmem_ld_wait();
         tc_fence_before();
@@ -815,10 +838,11 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               float ms[4], mst[4], mz[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                const float a = vs[e + u], bt = vt[e + u];
+                // kBwdW: the transposed strip exists on flagged tiles only (kZ) and feeds G_ji alone - dS_ji is not formed
+                const float a = vs[e + u], bt = (!kW || kZ) ? vt[e + u] : 0.f;
                 const float e1 = ex2f(fmaf(a, cS2, -r2_i));     // softmax_row(S)_ij
-                const float e3 = ex2f(fmaf(bt, cS2, nr[u]));    // softmax_row(S)_ji
-                float P = 0.f, Pt = 0.f, dS, dSt;
+                const float e3 = kW ? 0.f : ex2f(fmaf(bt, cS2, nr[u]));    // softmax_row(S)_ji
+                float P = 0.f, Pt = 0.f, dS, dSt = 0.f;
                 if (kZ) {
                   const float z2 = vz[e + u] * cZ2;
                   P = ex2f(z2 - rz2_i);
@@ -826,14 +850,16 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                 }
                 if (kFast) {  // three exponentials; the other three are products of per-row / per-column factors
                   dS = fmaf(e1, fmaf(fC_i, qc[u], 1.f), -2.f * P);        // 2B dS_ij
-                  dSt = fmaf(e3, fmaf(ej[u], fFQ_i, 1.f), -2.f * Pt);     // 2B dS_ji
+                  if (!kW) dSt = fmaf(e3, fmaf(ej[u], fFQ_i, 1.f), -2.f * Pt);     // 2B dS_ji
                 } else {
                   const float e2 = ex2f(fmaf(a, cS2, nc[u]));   // softmax_col(S)_ij
-                  const float e4 = ex2f(fmaf(bt, cS2, -c2_i));  // softmax_col(S)_ji
                   dS = fmaf(-2.f, P, fmaf(e2, qc[u], e1));
-                  dSt = fmaf(-2.f, Pt, fmaf(e4, q_i, e3));
+                  if (!kW) {
+                    const float e4 = ex2f(fmaf(bt, cS2, -c2_i));  // softmax_col(S)_ji
+                    dSt = fmaf(-2.f, Pt, fmaf(e4, q_i, e3));
+                  }
                 }
-                ms[u] = dS * wS;
+                ms[u] = (kW && !row_ok) ? 0.f : dS * wS;   // kBwdW: rows past the strip must store exact zeros
                 mst[u] = dSt * wS;
                 if (kZ) {
                   const float G = fmaf(a, m2cS2, r2_i - nc[u]);           // 2B G_ij log2(e)
@@ -869,14 +895,21 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           for (int k = 0; k < 4; ++k) {
             const int chunk = ((4 * n1 + k) ^ (m & 7)) * 16;
             *reinterpret_cast<uint4*>(wrow + chunk) = make_uint4(wSp[4 * k], wSp[4 * k + 1], wSp[4 * k + 2], wSp[4 * k + 3]);
-            *reinterpret_cast<uint4*>(wrow + kChunkBytes + chunk) =
-                make_uint4(wStp[4 * k], wStp[4 * k + 1], wStp[4 * k + 2], wStp[4 * k + 3]);
+            if (!kW)
+              *reinterpret_cast<uint4*>(wrow + kChunkBytes + chunk) =
+                  make_uint4(wStp[4 * k], wStp[4 * k + 1], wStp[4 * k + 2], wStp[4 * k + 3]);
             if (zf)
               *reinterpret_cast<uint4*>(wrow + 2 * kChunkBytes + chunk) =
                   make_uint4(wZp[4 * k], wZp[4 * k + 1], wZp[4 * k + 2], wZp[4 * k + 3]);
           }
           fence_proxy_async_smem();
           mbar_arrive_cluster(bar(kWFull), 0);
+          if (kW) {
+            // the same 32 weights of row lrow, columns t * 128 + jl0 .. + 31, to the stored tile (64 contiguous bytes)
+            uint4* wg = reinterpret_cast<uint4*>(p.wout + (size_t)lrow * p.Bp + (size_t)t * kTileN + jl0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wg[k] = make_uint4(wSp[4 * k], wSp[4 * k + 1], wSp[4 * k + 2], wSp[4 * k + 3]);
+          }
         }
         ++tt;
       }
@@ -937,6 +970,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         // column half h of its lane's D/2 columns
         mbar_wait(bar(kAccFull), jj & 1);
         tc_fence_after();
+        // kBwdW: the dI accumulator is written by flagged tiles only; a job without any holds no dI at all
+        const bool di_any = !kW || !frow || job_has_tiles(frow, t0, t1);
         const int half_d = D / 2, quart_d = D / 4;
         float* out_t = p.part + ((size_t)sp * 2 * p.bpad + lrow) * D + n1 * half_d + h * quart_d;
         float* out_i = out_t + (size_t)p.bpad * D;
@@ -948,6 +983,10 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(out_t + c0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
           tmem_ld32(tmem_base + lane_field + kAccCol + half_d + h * quart_d + c0, v);
           tmem_ld_wait();
+          if (!di_any) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = 0.f;
+          }
 #pragma unroll
           for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(out_i + c0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
         }
@@ -1180,6 +1219,206 @@ __global__ void __launch_bounds__(256) bwd_finalize_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// Column half of the stored-weights gradient: dI_j (+)= sum_i W_ij T_i over the rows i of a stored weight strip.
+//   W  (rows x Bp fp16, written by pair_kernel<kBwdW>)  is the A operand READ TRANSPOSED: a TMA box of {64 j, 64 i}
+//      lands in shared memory as 64 rows (i = K) of 128 bytes (64 j = M), which is exactly the canonical MN-major
+//      SWIZZLE_128B operand layout (8-row groups 1024 B apart, 64-wide M blocks `LBO` apart) - no transpose anywhere;
+//   T^T (the transposed hi plane, rows D..2D)            is the K-major B operand, as in the gradient GEMMs of kBwd.
+// A CTA pair owns 256 output rows j (cta_group::2, M = 256: lane = row, N = D columns), streams its K range through a
+// ring of 64-row stages and keeps two accumulator buffers in TMEM so that the read-out of one job overlaps the MMAs of
+// the next.  Jobs = (256-row block of j) x (K split); every job writes its own partial (deterministic fold afterwards).
+// ------------------------------------------------------------------------------------------
+constexpr int kCgThreads = 256;   // warp 0 TMA, warp 1 MMA + TMEM, warps 4-7 read-out
+constexpr int kCgStageA = 2 * 8192;                  // two 64-wide M blocks x 64 K rows x 128 B
+constexpr int kCgStages = 6;
+constexpr int kCgMaxSplit = 8;
+struct ColGradParams {
+  int Bp, D;
+  int w_rows;              // rows of the stored strip (multiple of 64)
+  int row_offset;          // global row of the strip's first row (column coordinate of T^T)
+  int j_first;             // first output row (multiple of 256 ... any multiple of 128)
+  int n_jblocks;           // 256-row blocks from j_first on
+  int j_end;               // output rows >= j_end are not written
+  int ksplit, steps_per_split, steps;   // K steps of 64 rows
+  float* part;             // [ksplit][n_jblocks * 256][D]
+};
+// MN-major SWIZZLE_128B operand: [16,30) leading byte offset (between 64-element M blocks), [32,46) stride byte offset
+// (between 8-row K groups)
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__global__ void __launch_bounds__(kCgThreads, 1)
+colgrad_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_t,
+               const ColGradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* const sbase = smem_raw + (base - raw);
+  const int D = p.D;
+  const uint32_t b_bytes = (uint32_t)(D / 2) * 128u;           // this CTA's half of the B tile: D/2 rows x 64 K
+  const uint32_t stage_bytes = kCgStageA + b_bytes;            // 32 KB at D = 256
+  const uint32_t bar0 = base + kCgStages * stage_bytes;
+  auto bar = [&](int i) -> uint32_t { return bar0 + 8u * i; };
+  enum { kFull = 0, kEmpty = kCgStages, kAccFull = 2 * kCgStages, kAccEmpty = 2 * kCgStages + 2, kBars = 2 * kCgStages + 4 };
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(sbase + kCgStages * stage_bytes + 8 * kBars);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int njobs = p.n_jblocks * p.ksplit;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kCgStages; ++s) { mbar_init(bar(kFull + s), 1); mbar_init(bar(kEmpty + s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(kAccFull + i), 1); mbar_init(bar(kAccEmpty + i), 2 * 128); }
+    fence_mbar_init();
+    prefetch_tmap(&map_w);
+    prefetch_tmap(&map_t);
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(smem_u32(tmem_slot), 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int job = pair_id; job < njobs; job += npairs) {
+        const int jb = job / p.ksplit, ks = job % p.ksplit;
+        const int j0 = p.j_first + jb * 256 + (int)rank * 128;
+        const int s0 = ks * p.steps_per_split, s1 = min(s0 + p.steps_per_split, p.steps);
+        for (int st = s0; st < s1; ++st, ++it) {
+          const uint32_t slot = it % kCgStages, par = (it / kCgStages) & 1;
+          mbar_wait(bar(kEmpty + slot), par ^ 1);
+          const uint32_t fb = bar(kFull + slot), sa = base + slot * stage_bytes;
+          if (leader) mbar_arrive_expect_tx(fb, 2u * stage_bytes);
+          const int i0 = st * 64;
+          tma_load_2d_pair(sa, &map_w, fb, j0, i0);                   // W[i0 .. +64][j0 .. +64]
+          tma_load_2d_pair(sa + 8192, &map_w, fb, j0 + 64, i0);       // W[i0 .. +64][j0 + 64 .. +128]
+          tma_load_2d_pair(sa + kCgStageA, &map_t, fb, p.row_offset + i0, D + (int)rank * (D / 2));   // T^T[d][i]
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      const uint32_t idesc = idesc_f16(256, D) | (1u << 15);   // A is MN-major
+      uint32_t it = 0, jj = 0;
+      for (int job = pair_id; job < njobs; job += npairs) {
+        const int ks = job % p.ksplit;
+        const int s0 = ks * p.steps_per_split, s1 = min(s0 + p.steps_per_split, p.steps);
+        if (s0 >= s1) continue;            // a split beyond the strip: no accumulator use (jj counts the others)
+        const uint32_t buf = jj & 1, use = jj >> 1;
+        ++jj;
+        mbar_wait(bar(kAccEmpty + buf), (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * (uint32_t)D;
+        for (int st = s0; st < s1; ++st, ++it) {
+          const uint32_t slot = it % kCgStages, par = (it / kCgStages) & 1;
+          mbar_wait(bar(kFull + slot), par);
+          tc_fence_after();
+          const uint32_t sa = base + slot * stage_bytes;
+          const uint64_t bd = smem_desc_sw128(sa + kCgStageA);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)     // 16 K rows = 2048 bytes of the MN-major tile per MMA
+            mma_f16_pair(tacc, smem_desc_mn_sw128(sa + k4 * 2048, 8192), desc_advance_k(bd, k4), idesc,
+                         (st > s0 || k4 > 0) ? 1u : 0u);
+          mma_commit_pair(bar(kEmpty + slot), 3);
+        }
+        mma_commit_pair(bar(kAccFull + buf), 3);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;                      // TMEM lane quarter
+    uint32_t jj = 0;
+    for (int job = pair_id; job < njobs; job += npairs) {
+      const int jb = job / p.ksplit, ks = job % p.ksplit;
+      const int lrow = jb * 256 + (int)rank * 128 + q * 32 + lane;    // row within the partial
+      const bool ok = p.j_first + lrow < p.j_end;
+      const int s0 = ks * p.steps_per_split;
+      const bool empty = s0 >= p.steps;          // a split beyond the strip: nothing was accumulated
+      const uint32_t buf = jj & 1, use = jj >> 1;
+      if (!empty) ++jj;
+      float* out = p.part + ((size_t)ks * p.n_jblocks * 256 + lrow) * D;
+      if (!empty) {
+        mbar_wait(bar(kAccFull + buf), use & 1);
+        tc_fence_after();
+      }
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        float v[32];
+        if (!empty) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)D + c0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = 0.f;
+        }
+        if (ok) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(out + c0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        }
+      }
+      if (!empty) {
+        tc_fence_before();
+        mbar_arrive_cluster(bar(kAccEmpty + buf), 0);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
+// fold of the row half: dT (final) and the un-scaled soft-target part of dI
+__global__ void __launch_bounds__(256) bwd_rows_finalize_kernel(const float* __restrict__ part, int nsplit, int bpad,
+                                                                int b, int D, float inv_2B,
+                                                                const float* __restrict__ grad_loss,
+                                                                const float* __restrict__ wscale,
+                                                                float* __restrict__ dT, float* __restrict__ dIz) {
+  const float scale = (grad_loss ? *grad_loss : 1.f) * inv_2B / *wscale;
+  const size_t n4 = (size_t)b * D / 4;
+  const size_t plane = (size_t)bpad * D;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 at = make_float4(0.f, 0.f, 0.f, 0.f), ai = at;
+    for (int s = 0; s < nsplit; ++s) {
+      const float4 a = reinterpret_cast<const float4*>(part + (size_t)s * 2 * plane)[i];
+      const float4 c = reinterpret_cast<const float4*>(part + ((size_t)s * 2 + 1) * plane)[i];
+      at.x += a.x; at.y += a.y; at.z += a.z; at.w += a.w;
+      ai.x += c.x; ai.y += c.y; ai.z += c.z; ai.w += c.w;
+    }
+    reinterpret_cast<float4*>(dT)[i] = make_float4(at.x * scale, at.y * scale, at.z * scale, at.w * scale);
+    reinterpret_cast<float4*>(dIz)[i] = ai;
+  }
+}
+// fold of the column half: dI_j = scale (dIz_j + sum_k part_k[j])
+__global__ void __launch_bounds__(256) bwd_cols_finalize_kernel(const float* __restrict__ part, int ksplit, size_t plane,
+                                                                int rows, int D, float inv_2B,
+                                                                const float* __restrict__ grad_loss,
+                                                                const float* __restrict__ wscale,
+                                                                const float* __restrict__ dIz, float* __restrict__ dI) {
+  const float scale = (grad_loss ? *grad_loss : 1.f) * inv_2B / *wscale;
+  const size_t n4 = (size_t)rows * D / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 a = dIz ? reinterpret_cast<const float4*>(dIz)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < ksplit; ++s) {
+      const float4 c = reinterpret_cast<const float4*>(part + (size_t)s * plane)[i];
+      a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+    }
+    reinterpret_cast<float4*>(dI)[i] = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1221,7 +1460,7 @@ struct Split {
 // accumulators per job, and every extra split adds a set of partial gradients to fold: 0.578 ms with 16 splits, 0.505
 // with 2; the statistics sweep is cheap per job)
 constexpr double kOvhStats = 1.5, kOvhRowLoss = 0.5, kOvhBwd = 6.0;
-template <int PHASE> constexpr double phase_ovh() { return PHASE == kBwd ? kOvhBwd : (PHASE == kRowLoss ? kOvhRowLoss : kOvhStats); }
+template <int PHASE> constexpr double phase_ovh() { return (PHASE == kBwd || PHASE == kBwdW) ? kOvhBwd : (PHASE == kRowLoss ? kOvhRowLoss : kOvhStats); }
 static Split choose_split(int b, int B, double ovh = kOvhRowLoss, int align = 1) {
   Split s;
   s.n_row_blocks = (b + 127) / 128;
@@ -1572,7 +1811,8 @@ int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row
 
 template <int PHASE, int PASSES>
 static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float* ps_loc, float* part,
-                       const float* wscale, cudaStream_t st, float* colpart = nullptr, int chunk_k = -1, int chunks = 1) {
+                       const float* wscale, cudaStream_t st, float* colpart = nullptr, int chunk_k = -1, int chunks = 1,
+                       __half* wout = nullptr) {
   MC_REQUIRE(supported(p.D), MC_ERR_UNSUPPORTED, "tcgen05 engine needs D in {128, 256} (got %d)", p.D);
   MC_REQUIRE(p.row_offset % 128 == 0, MC_ERR_UNSUPPORTED, "tcgen05 engine needs row_offset %% 128 == 0 (got %d)",
              p.row_offset);
@@ -1608,6 +1848,7 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float*
   pp.norm_i = reinterpret_cast<const float*>(base + l.off_norm_i);
   pp.norm_t = reinterpret_cast<const float*>(base + l.off_norm_t);
   pp.colpart = (PHASE == kStats) ? colpart : nullptr;
+  pp.wout = wout;
   pp.chunk_k = (PHASE == kStats && chunked) ? chunk_k : -1;
   pp.chunk_blocks = chunked ? sp.n_row_blocks / chunks : sp.n_row_blocks;
   pp.chunk_m = chunked ? sp.nsplit / chunks : sp.nsplit;
@@ -1643,9 +1884,10 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float*
 
 template <int PHASE>
 static int launch_phase(int mode, const ClipProblem& p, const ClipStatsAll& s, const float* ps_loc, float* part,
-                        const float* wscale, cudaStream_t st, float* colpart = nullptr, int chunk_k = -1, int chunks = 1) {
-  if (mode == MC_GEMM_TC_F16X3) return launch_pair<PHASE, 3>(p, s, ps_loc, part, wscale, st, colpart, chunk_k, chunks);
-  return launch_pair<PHASE, 1>(p, s, ps_loc, part, wscale, st, colpart, chunk_k, chunks);
+                        const float* wscale, cudaStream_t st, float* colpart = nullptr, int chunk_k = -1, int chunks = 1,
+                        __half* wout = nullptr) {
+  if (mode == MC_GEMM_TC_F16X3) return launch_pair<PHASE, 3>(p, s, ps_loc, part, wscale, st, colpart, chunk_k, chunks, wout);
+  return launch_pair<PHASE, 1>(p, s, ps_loc, part, wscale, st, colpart, chunk_k, chunks, wout);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1819,6 +2061,126 @@ int bwd(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad
   if (blocks > cap) blocks = cap;
   bwd_finalize_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(ws), sp.nsplit, sp.bpad, p.b, p.D,
                                               0.5f / (float)p.B, grad_loss, wsc, dT, dI);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
+
+// ---- stored-weights gradient (see kBwdW / colgrad_kernel) -------------------------------------------------
+static int launch_wscale(const ClipProblem& p, const ClipStatsAll& s, float* wsc, cudaStream_t st) {
+  PlanesLayout l = planes_layout(p.B, p.D);
+  const char* pbase = static_cast<const char*>(p.planes_all);
+  wscale_kernel<<<1, 1024, 0, st>>>(s.r, s.c, s.rz, s.q, p.B, reinterpret_cast<const float*>(pbase + l.off_hdr) + 1,
+                                   reinterpret_cast<const float*>(pbase + l.off_norm_i),
+                                   reinterpret_cast<const float*>(pbase + l.off_norm_t), 1.f / p.tau, p.tau, wsc);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+struct ColSplit { int n_jblocks, steps, ksplit, steps_per_split; };
+static ColSplit choose_col_split(int w_rows, int n_cols) {
+  ColSplit c;
+  c.n_jblocks = (n_cols + 255) / 256;
+  c.steps = (w_rows + 63) / 64;
+  const int npairs = num_sms() / 2;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int k = 1; k <= kCgMaxSplit && k <= c.steps; ++k) {
+    const int per = (c.steps + k - 1) / k;
+    const long jobs = (long)c.n_jblocks * k;
+    const double cost = (double)((jobs + npairs - 1) / npairs) * (per + 16.0) + 4.0 * k;   // + the partial each split adds
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = k; }
+  }
+  c.ksplit = best;
+  c.steps_per_split = (c.steps + best - 1) / best;
+  return c;
+}
+size_t stored_weights_bytes(int b, int B) { return round_up(round_up((size_t)b, 128) * round_up((size_t)B, 128) * sizeof(__half), 256); }
+size_t bwd_cols_workspace_bytes(int /*w_rows*/, int n_cols, int D) {
+  return round_up((size_t)kCgMaxSplit * ((size_t)(n_cols + 255) / 256 * 256) * D * sizeof(float), 256) + 256;
+}
+bool stored_form_enabled(int b, int B, int D) {
+  static const bool off = getenv("MAE_CLIP_BWD_FORM") != nullptr && strcmp(getenv("MAE_CLIP_BWD_FORM"), "ownrows") == 0;
+  return !off && supported(D) && stored_weights_bytes(b, B) <= ((size_t)16 << 30);
+}
+
+// Row half over the strip p.row_offset .. + p.b: dT_loc (final), dIz_loc (b x D, un-scaled soft-target part of dI of the
+// strip's rows) and the strip's rows of W (pointer to the strip's first row, row pitch Bp).
+int bwd_rows(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, float* dT_loc, float* dIz_loc,
+             void* W_rows, void* ws, size_t ws_bytes, cudaStream_t st) {
+  MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_bwd_rows: workspace too small");
+  MC_REQUIRE(aligned(dT_loc, 16) && aligned(dIz_loc, 16) && aligned(W_rows, 256), MC_ERR_ALIGN, "clip_bwd_rows: alignment");
+  MC_REQUIRE(p.planes_all != nullptr, MC_ERR_BAD_ARG, "clip_bwd_rows: planes buffer missing");
+  float* wsc = wscale_slot(ws, p.b, p.B, p.D);
+  int rc;
+  if ((rc = launch_wscale(p, s, wsc, st))) return rc;
+  if ((rc = launch_phase<kBwdW>(mode, p, s, nullptr, static_cast<float*>(ws), wsc, st, nullptr, -1, 1,
+                                static_cast<__half*>(W_rows))))
+    return rc;
+  Split sp = choose_split(p.b, p.B, kOvhBwd);
+  size_t n4 = (size_t)p.b * p.D / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  int cap = num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  bwd_rows_finalize_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(ws), sp.nsplit, sp.bpad, p.b, p.D,
+                                                   0.5f / (float)p.B, grad_loss, wsc, dT_loc, dIz_loc);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
+// Column half: dI of the rows j0 .. j1 (j0 a multiple of 128) from the stored strip W (w_rows rows whose first is the
+// global row w_row_offset): dI_out[j - j0] = scale (dIz[j - j0] + sum_i W_ij T_i).  dIz may be null (a rank that does
+// not own those rows contributes the W part only).
+int bwd_cols(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, const void* W, int w_rows,
+             int w_row_offset, int j0, int j1, const float* dIz, float* dI_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  (void)mode;
+  MC_REQUIRE(supported(p.D), MC_ERR_UNSUPPORTED, "clip_bwd_cols: D %d", p.D);
+  MC_REQUIRE(j0 % 128 == 0 && j0 >= 0 && j1 > j0 && j1 <= p.B && w_rows > 0 && w_row_offset % 64 == 0, MC_ERR_BAD_ARG,
+             "clip_bwd_cols: bad ranges (j %d..%d, rows %d at %d)", j0, j1, w_rows, w_row_offset);
+  MC_REQUIRE(ws_bytes >= bwd_cols_workspace_bytes(w_rows, j1 - j0, p.D), MC_ERR_WORKSPACE, "clip_bwd_cols: workspace too small");
+  MC_REQUIRE(aligned(W, 256) && aligned(dI_out, 16) && (!dIz || aligned(dIz, 16)), MC_ERR_ALIGN, "clip_bwd_cols: alignment");
+  PlanesLayout l = planes_layout(p.B, p.D);
+  const char* base = static_cast<const char*>(p.planes_all);
+  const int w_rows_pad = (int)round_up((size_t)w_rows, 128);
+  CUtensorMap mw, mt;
+  int rc;
+  if ((rc = make_map(&mw, W, w_rows_pad, l.Bp, 64))) return rc;
+  if ((rc = make_map(&mt, base + l.off_hiT, 2 * p.D, l.Bp, p.D / 2))) return rc;
+  ColSplit cs = choose_col_split(w_rows_pad, j1 - j0);
+  const size_t part_bytes = round_up((size_t)kCgMaxSplit * ((size_t)cs.n_jblocks * 256) * p.D * sizeof(float), 256);
+  float* wsc = reinterpret_cast<float*>(static_cast<char*>(ws) + part_bytes);
+  if ((rc = launch_wscale(p, s, wsc, st))) return rc;
+  ColGradParams cp;
+  cp.Bp = l.Bp; cp.D = p.D; cp.w_rows = w_rows_pad; cp.row_offset = w_row_offset;
+  cp.j_first = j0; cp.n_jblocks = cs.n_jblocks; cp.j_end = j1;
+  cp.ksplit = cs.ksplit; cp.steps_per_split = cs.steps_per_split; cp.steps = cs.steps;
+  cp.part = static_cast<float*>(ws);
+  const int smem = kCgStages * (kCgStageA + (p.D / 2) * 128) + 8 * 32 + 16 + 1024;
+  static std::atomic<unsigned long long> attr_done{0};
+  MC_CUDA(ensure_dynamic_smem(colgrad_kernel, smem, attr_done));
+  const long njobs = (long)cs.n_jblocks * cs.ksplit;
+  int npairs = num_sms() / 2;
+  if (njobs < npairs) npairs = (int)njobs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * npairs);
+  cfg.blockDim = dim3(kCgThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MC_CUDA(cudaLaunchKernelEx(&cfg, colgrad_kernel, mw, mt, cp));
+  count_launch();
+  const int rows = j1 - j0;
+  size_t n4 = (size_t)rows * p.D / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  int cap = num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  bwd_cols_finalize_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(ws), cs.ksplit, (size_t)cs.n_jblocks * 256 * p.D,
+                                                   rows, p.D, 0.5f / (float)p.B, grad_loss, wsc, dIz, dI_out);
   MC_LAUNCH_CHECK();
   return MC_OK;
 }
