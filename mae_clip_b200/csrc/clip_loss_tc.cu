@@ -59,7 +59,7 @@ constexpr int kOffW = kOffStage + kStageRegion;   // three 64 x 64 fp16 weight h
 constexpr int kOffXT = kOffW + 3 * kChunkBytes;   // X^T half tiles: 2 x (D/2 rows x 64 j) (<= 32 KB)
 constexpr int kOffConst = kOffXT + 32768;         // per-column constants, 2 x 128 x 8 floats
 constexpr int kOffBar = kOffConst + 8192;
-constexpr int kSmemBytes = kOffBar + 256 + 1024;  // + alignment slack
+constexpr int kSmemBytes = kOffBar + 512 + 1024;  // + alignment slack
 
 enum Bar {
   kFull0 = 0,        // +slot (<= 9)
@@ -74,7 +74,11 @@ enum Bar {
   kAccFull = 27,
   kAccEmpty = 28,
   kGradDone1 = 29,   // column half 1
-  kNumBars = 30
+  kWFull1 = 30,      // kBwdW: the column halves have their own weight and X^T buffers
+  kXTFull1 = 31,
+  kCstFull0 = 32,    // +buf: per-column constants of a tile (gradient sweep: produced by warp 3)
+  kCstEmpty0 = 34,   // +buf
+  kNumBars = 36
 };
 
 struct PairParams {
@@ -264,6 +268,9 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     mbar_init(bar(kGradDone), kIssuers);
     mbar_init(bar(kGradDone1), kIssuers);
     mbar_init(bar(kXTFull), 1);
+    mbar_init(bar(kWFull1), kEpiThreads);
+    mbar_init(bar(kXTFull1), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(kCstFull0 + i), 32); mbar_init(bar(kCstEmpty0 + i), kEpiThreads); }
     mbar_init(bar(kAccFull), kIssuers);
     mbar_init(bar(kAccEmpty), 2 * kEpiThreads);
     fence_mbar_init();
@@ -361,15 +368,71 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           for (int t = t0; t < t1; ++t, ++tt) {
             // kBwdW: T_j^T feeds the dZ GEMM only (dI's S part comes from the stored weights)
             const bool zt = !kW || !p.flags || p.flags[(size_t)rb * p.n_tiles + t] != 0;
+            if (kW && !zt) {
+              // no T_j^T tile: its buffer takes I_j^T of column half 1, so both halves load at once as soon as the
+              // previous tile's gradient MMAs are done
+              mbar_wait(bar(kGradDone1), (tt & 1) ^ 1);
+              for (int h = 0; h < 2; ++h) {
+                const uint32_t fb = bar(h == 0 ? kXTFull : kXTFull1);
+                if (leader) mbar_arrive_expect_tx(fb, 2u * xt_bytes);
+                tma_load_2d_pair(base + kOffXT + h * xt_bytes, &map_t, fb, t * kTileN + 64 * h, (int)rank * (D / 2));
+              }
+              continue;
+            }
             for (int h = 0; h < 2; ++h) {
               // the previous half's MMAs are done with the buffer: (tt-1, 1) before (tt, 0); (tt, 0) before (tt, 1)
               if (h == 0) mbar_wait(bar(kGradDone1), (tt & 1) ^ 1); else mbar_wait(bar(kGradDone), tt & 1);
-              if (leader) mbar_arrive_expect_tx(bar(kXTFull), (zt ? 2u : 1u) * 2u * xt_bytes);
+              const uint32_t fb = bar((kW && h == 1) ? kXTFull1 : kXTFull);
+              if (leader) mbar_arrive_expect_tx(fb, 2u * 2u * xt_bytes);
               const int jx = t * kTileN + 64 * h;
-              tma_load_2d_pair(base + kOffXT, &map_t, bar(kXTFull), jx, (int)rank * (D / 2));
-              if (zt) tma_load_2d_pair(base + kOffXT + xt_bytes, &map_t, bar(kXTFull), jx, D + (int)rank * (D / 2));
+              tma_load_2d_pair(base + kOffXT, &map_t, fb, jx, (int)rank * (D / 2));
+              tma_load_2d_pair(base + kOffXT + xt_bytes, &map_t, fb, jx, D + (int)rank * (D / 2));
             }
           }
+        }
+      }
+    } else if (warp == 3 && kIsBwd && kIssuers == 1) {
+      // ========================================================= per-column constants of the gradient sweep, one tile
+      // ahead of the epilogue: -r2_j, -c2_j, B_j | -rz2_j, gh_j, D_j q_j | q_j, E_j (see weights32); lane l owns the
+      // columns l, l + 32, l + 64, l + 96 of the tile
+      float* const consts = reinterpret_cast<float*>(sbase + kOffConst);
+      const float kL2e = 1.4426950408889634f;
+      const bool fast = p.wscale[1] != 0.f;
+      const float m_rc = p.wscale[2], m_z = p.wscale[3], twoB = 2.f * (float)p.B;
+      uint32_t tt = 0;
+      for (int job = pair_id; job < njobs; job += npairs) {
+        int rb, sp;
+        pair_job(p, job, rb, sp);
+        const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+        for (int t = t0; t < t1; ++t, ++tt) {
+          float vr[4], vc[4], vz[4], vg[4], vq[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int jcol = t * kTileN + lane + 32 * u;
+            const bool ok = jcol < p.B;
+            vr[u] = ok ? p.r[jcol] : 0.f; vc[u] = ok ? p.c[jcol] : 0.f; vz[u] = ok ? p.rz[jcol] : 0.f;
+            vg[u] = ok ? p.g[jcol] : 0.f; vq[u] = ok ? p.q[jcol] : 0.f;
+          }
+          mbar_wait(bar(kCstEmpty0 + (tt & 1)), ((tt >> 1) & 1) ^ 1);
+          float* dst = consts + (tt & 1) * (8 * 128);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int col = lane + 32 * u;
+            const bool ok = t * kTileN + col < p.B;
+            const float r2 = vr[u] * kL2e, c2 = vc[u] * kL2e, rz2 = vz[u] * kL2e;
+            dst[0 * 128 + col] = -r2;
+            dst[1 * 128 + col] = -c2;
+            dst[3 * 128 + col] = vg[u] * twoB * kL2e;
+            if (fast) {
+              dst[2 * 128 + col] = ok ? ex2f(m_z - rz2) : 0.f;
+              dst[4 * 128 + col] = ok ? ex2f(m_rc - c2) * vq[u] : 0.f;
+              dst[5 * 128 + col] = ok ? ex2f(r2 - m_rc) : 0.f;
+            } else {
+              dst[2 * 128 + col] = -rz2;
+              dst[4 * 128 + col] = vq[u];
+            }
+          }
+          mbar_arrive_local(bar(kCstFull0 + (tt & 1)));
         }
       }
     } else if (warp == 1 || (kIssuers == 2 && warp == 3)) {
@@ -392,18 +455,27 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         bool zg = true;  // does the tile whose gradient GEMMs are being issued carry soft-target mass (tile flag)?
         bool di_live = false;  // kBwdW: has this job's dI accumulator been written yet (only flagged tiles touch it)?
         auto grad_half = [&](int h, bool first_of_job) {
-          mbar_wait(bar(kWFull), hh & 1);
-          mbar_wait(bar(kXTFull), hh & 1);
+          if (kW) {   // per-half buffers and barriers: one phase per tile
+            mbar_wait(bar(h == 0 ? kWFull : kWFull1), (hh >> 1) & 1);
+            mbar_wait(bar(h == 0 ? kXTFull : kXTFull1), (hh >> 1) & 1);
+          } else {
+            mbar_wait(bar(kWFull), hh & 1);
+            mbar_wait(bar(kXTFull), hh & 1);
+          }
           ++hh;
           tc_fence_after();
           const uint32_t first = (first_of_job && h == 0) ? 0u : 1u;
+          // kBwdW: half 1 has its own weight buffer (the unused dS^T slot) and, on tiles without soft-target mass, its
+          // own I_j^T buffer (the unused T_j^T slot)
+          const uint64_t wS_h = (kW && h == 1) ? wSt : wS;
+          const uint64_t xI_h = (kW && h == 1 && !zg) ? xT : xI;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t acc = (first | (ks > 0)) ? 1u : 0u;
-            const uint64_t kxI = desc_advance_k(xI, ks), kxT = desc_advance_k(xT, ks);
+            const uint64_t kxI = desc_advance_k(xI_h, ks), kxT = desc_advance_k(xT, ks);
             const uint64_t kwZ = desc_advance_k(wZ, ks);
             if (do_s) {
-              mma_f16_pair(tDT, desc_advance_k(wS, ks), kxI, idesc_grad, acc);   // dT += (dS/tau) I_j
+              mma_f16_pair(tDT, desc_advance_k(wS_h, ks), kxI, idesc_grad, acc);   // dT += (dS/tau) I_j
               if (zg) mma_f16_pair(tDT, kwZ, kxT, idesc_grad, 1u);               // dT += (tau/2 dZs) T_j
             }
             if (do_z) {
@@ -444,7 +516,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             // single weight / X^T buffers are refilled while the tensor cores stay busy.
             const bool lagged = kIsBwd && t > t0;
             for (int c = 0; c < nkc; ++c) {
-              if (lagged && c == nkc - 1) grad_half(0, t - 1 == t0);
+              if (!kW && lagged && c == nkc - 1) grad_half(0, t - 1 == t0);
               uint32_t slot_bar = 0;
               auto next_full = [&]() -> uint32_t {  // wait for the next ring slot to land
                 const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
@@ -546,6 +618,9 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                 mbar_wait(bar(kAccEmpty), jpar ^ 1);  // the previous job's accumulators were read out
                 tc_fence_after();
               } else {
+                // kBwdW: nothing is woven - with per-half buffers the whole tile t is issued (and handed to the
+                // epilogue) before the issuer waits for the weights of tile t - 1
+                if (kW) grad_half(0, t - 1 == t0);
                 grad_half(1, false);
               }
             }
@@ -644,26 +719,16 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const bool zf = !kIsBwd || !frow || frow[t] != 0;          // gradient sweep: does this tile carry P mass?
         // ---- per-column statistics of this tile -> shared memory, one field per 128-float row
         float* cst = consts + (tt & 1) * (8 * 128);
-        if (PHASE != kStats && PHASE != kStatsZ) {
+        if (kIsBwd) {
+          // the per-column constants of this tile come from warp 3, one tile ahead (no global loads, no block barrier here)
+          mbar_wait(bar(kCstFull0 + (tt & 1)), (tt >> 1) & 1);
+        } else if (PHASE != kStats && PHASE != kStatsZ) {
           if (tid_e < 128) {
             const int jcol = t * kTileN + tid_e;
             const bool ok = jcol < p.B;
             const float c2 = ok ? p.c[jcol] * kL2e : 0.f, rz2 = ok ? p.rz[jcol] * kL2e : 0.f;
             cst[1 * 128 + tid_e] = -c2;                                                                 // -c2_j
-            if (kIsBwd && fast) {
-              cst[2 * 128 + tid_e] = ok ? ex2f(m_z - rz2) : 0.f;                                        // B_j
-              cst[4 * 128 + tid_e] = ok ? ex2f(m_rc - c2) * p.q[jcol] : 0.f;                            // D_j q_j
-            } else {
-              cst[2 * 128 + tid_e] = -rz2;                                                              // -rz2_j
-              if (kIsBwd) cst[4 * 128 + tid_e] = ok ? p.q[jcol] : 0.f;                           // q_j
-            }
-          } else if (kIsBwd) {
-            const int jcol = t * kTileN + tid_e - 128;
-            const bool ok = jcol < p.B;
-            const float r2 = ok ? p.r[jcol] * kL2e : 0.f;
-            cst[0 * 128 + tid_e - 128] = -r2;                                                           // -r2_j
-            cst[3 * 128 + tid_e - 128] = ok ? p.g[jcol] * (2.f * (float)p.B) * kL2e : 0.f;              // gh_j
-            cst[5 * 128 + tid_e - 128] = ok ? ex2f(r2 - m_rc) : 0.f;                                    // E_j
+            cst[2 * 128 + tid_e] = -rz2;                                                                // -rz2_j
           }
           named_bar_sync(1, kEpiThreads);
         }
@@ -887,14 +952,15 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           // The single weight buffer is used by column half 0, then half 1, of every tile: wait until
           // the gradient MMAs of the preceding half have drained it.  One barrier per half keeps every
           // waiter at most one phase behind, which the parity test needs.
-          if (h == 0) mbar_wait(bar(kGradDone1), (tt & 1) ^ 1);  // half 1 of the previous tile consumed
-          else mbar_wait(bar(kGradDone), tt & 1);                // half 0 of this tile consumed
+          if (h == 0 || (kW && !zf)) mbar_wait(bar(kGradDone1), (tt & 1) ^ 1);  // half 1 of the previous tile consumed
+          else mbar_wait(bar(kGradDone), tt & 1);                // half 0 of this tile consumed (shared dZ buffer)
           // row m of a 64 x 64 fp16 tile (128 B rows, SWIZZLE_128B): this thread owns K = 32 n1 .. +31
           uint8_t* wrow = sbase + kOffW + m * 128;
+          uint8_t* wrow_s = wrow + ((kW && h == 1) ? kChunkBytes : 0);   // kBwdW: half 1 writes the dS^T slot
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int chunk = ((4 * n1 + k) ^ (m & 7)) * 16;
-            *reinterpret_cast<uint4*>(wrow + chunk) = make_uint4(wSp[4 * k], wSp[4 * k + 1], wSp[4 * k + 2], wSp[4 * k + 3]);
+            *reinterpret_cast<uint4*>(wrow_s + chunk) = make_uint4(wSp[4 * k], wSp[4 * k + 1], wSp[4 * k + 2], wSp[4 * k + 3]);
             if (!kW)
               *reinterpret_cast<uint4*>(wrow + kChunkBytes + chunk) =
                   make_uint4(wStp[4 * k], wStp[4 * k + 1], wStp[4 * k + 2], wStp[4 * k + 3]);
@@ -903,13 +969,14 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                   make_uint4(wZp[4 * k], wZp[4 * k + 1], wZp[4 * k + 2], wZp[4 * k + 3]);
           }
           fence_proxy_async_smem();
-          mbar_arrive_cluster(bar(kWFull), 0);
+          mbar_arrive_cluster(bar((kW && h == 1) ? kWFull1 : kWFull), 0);
           if (kW) {
             // the same 32 weights of row lrow, columns t * 128 + jl0 .. + 31, to the stored tile (64 contiguous bytes)
             uint4* wg = reinterpret_cast<uint4*>(p.wout + (size_t)lrow * p.Bp + (size_t)t * kTileN + jl0);
 #pragma unroll
             for (int k = 0; k < 4; ++k) wg[k] = make_uint4(wSp[4 * k], wSp[4 * k + 1], wSp[4 * k + 2], wSp[4 * k + 3]);
           }
+          mbar_arrive_local(bar(kCstEmpty0 + (tt & 1)));   // this thread is done with the tile's constants
         }
         ++tt;
       }
