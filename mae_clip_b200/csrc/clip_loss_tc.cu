@@ -123,6 +123,23 @@ __device__ __forceinline__ void pair_job(const PairParams& p, int job, int& rb, 
   rb = job / p.chunk_m;
   sp = p.chunk_k * p.chunk_m + job % p.chunk_m;
 }
+// -DMC_WAIT_PROFILE: where do the roles of pair_kernel wait?  Cycles spent in each class of mbarrier wait, summed over the
+// pairs (issuer / producers: the elected thread; epilogue: threads 128 and 256 of the leader CTA), read back through
+// mc_debug_wait_profile (tools/wait_profile.py).  Not part of the product build.
+#ifdef MC_WAIT_PROFILE
+__device__ unsigned long long g_wait_prof[64];
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int tag, bool rec) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  if (rec) atomicAdd(&g_wait_prof[tag], (unsigned long long)(clock64() - t0));
+}
+#define MC_PROF_TOTAL(tag, t0, rec) do { if (rec) atomicAdd(&g_wait_prof[tag], (unsigned long long)(clock64() - (t0))); } while (0)
+#define MC_PROF_NOW() clock64()
+#else
+#define MC_PROF_NOW() 0LL
+#define mbar_wait_t(bar, parity, tag, rec) mbar_wait(bar, parity)
+#define MC_PROF_TOTAL(tag, t0, rec) do { } while (0)
+#endif
 constexpr float kFlagTheta2 = 44.f;
 constexpr float kProbeMargin2 = 2.f;  // slack on top of the probe's worst-case rounding bound (see zmargin2)    // log2 units: dropped terms are below 2^-44 of their row's soft-target mass
 
@@ -295,6 +312,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       // ========================================================= TMA producer: resident rows + ring
       if (elect_one()) {
         uint32_t it = 0, jj = 0;
+        [[maybe_unused]] const long long prof_t0 = MC_PROF_NOW();
         for (int job = pair_id; job < njobs; job += npairs) {
           int rb, sp;
           pair_job(p, job, rb, sp);
@@ -303,7 +321,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           if ((PHASE == kRowLoss || PHASE == kStatsZ) && p.flags &&
               !job_has_tiles(p.flags + (size_t)rb * p.n_tiles, t0, t1)) continue;   // jj counts processed jobs only
           const uint32_t jpar = jj++ & 1;
-          mbar_wait(bar(kJobDone), jpar ^ 1);
+          mbar_wait_t(bar(kJobDone), jpar ^ 1, 8, leader);
           if (leader) mbar_arrive_expect_tx(bar(kAFull), (kResLo ? 2u : 1u) * 2u * 2u * nkc * kChunkBytes);
           for (int c = 0; c < 2 * nkc; ++c)
             tma_load_2d_pair(base + kOffA + c * kChunkBytes, &map_a_hi, bar(kAFull), c * 64, row_a);
@@ -321,7 +339,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               auto acquire = [&](uint32_t bytes) -> uint32_t {  // next ring slot: wait until the MMAs released it, arm its barrier
                 const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
                 ++it;
-                mbar_wait(bar(kEmpty0 + slot), par ^ 1);
+                mbar_wait_t(bar(kEmpty0 + slot), par ^ 1, 9, leader);
                 fb = bar(kFull0 + slot);
                 if (leader) mbar_arrive_expect_tx(fb, bytes);
                 return base + kOffRing + slot * kSlotBytes;
@@ -355,6 +373,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             }
           }
         }
+        MC_PROF_TOTAL(10, prof_t0, leader);
       }
     } else if (warp == 2) {
       // ========================================================= TMA producer: X^T half tiles (gradient GEMMs)
@@ -451,16 +470,17 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const uint64_t wZ = smem_desc_sw128(base + kOffW + 2 * kChunkBytes);
         const uint64_t xI = smem_desc_sw128(base + kOffXT), xT = smem_desc_sw128(base + kOffXT + xt_bytes);
         uint32_t it = 0, tt = 0, hh = 0, jj = 0;
+        [[maybe_unused]] const long long prof_t0 = MC_PROF_NOW();
         // one column half of a tile's gradient GEMMs: dT += W_S I_j + W_Z T_j, dI += W_St T_j + W_Z I_j
         bool zg = true;  // does the tile whose gradient GEMMs are being issued carry soft-target mass (tile flag)?
         bool di_live = false;  // kBwdW: has this job's dI accumulator been written yet (only flagged tiles touch it)?
         auto grad_half = [&](int h, bool first_of_job) {
           if (kW) {   // per-half buffers and barriers: one phase per tile
-            mbar_wait(bar(h == 0 ? kWFull : kWFull1), (hh >> 1) & 1);
-            mbar_wait(bar(h == 0 ? kXTFull : kXTFull1), (hh >> 1) & 1);
+            mbar_wait_t(bar(h == 0 ? kWFull : kWFull1), (hh >> 1) & 1, 3, true);
+            mbar_wait_t(bar(h == 0 ? kXTFull : kXTFull1), (hh >> 1) & 1, 4, true);
           } else {
-            mbar_wait(bar(kWFull), hh & 1);
-            mbar_wait(bar(kXTFull), hh & 1);
+            mbar_wait_t(bar(kWFull), hh & 1, 3, true);
+            mbar_wait_t(bar(kXTFull), hh & 1, 4, true);
           }
           ++hh;
           tc_fence_after();
@@ -497,7 +517,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           const uint8_t* frow = p.flags ? p.flags + (size_t)rb * p.n_tiles : nullptr;
           if ((PHASE == kRowLoss || PHASE == kStatsZ) && frow && !job_has_tiles(frow, t0, t1)) continue;
           const uint32_t jpar = jj++ & 1;
-          mbar_wait(bar(kAFull), jpar);
+          mbar_wait_t(bar(kAFull), jpar, 0, true);
           tc_fence_after();
           bool zf = true, zf_prev = true;
           di_live = false;
@@ -508,7 +528,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             zf = !kIsBwd || !frow || frow[t] != 0;                 // gradient sweep: recompute Z only where P lives
             zg = zf_prev;                                          // the woven gradient GEMMs belong to tile t - 1
             const uint32_t buf = tt % kNBuf, use = tt / kNBuf;
-            mbar_wait(bar(kTmemEmpty0 + buf), (use & 1) ^ 1);
+            mbar_wait_t(bar(kTmemEmpty0 + buf), (use & 1) ^ 1, 1, true);
             tc_fence_after();
             const uint32_t tS = tmem_base + buf * 192, tSt = tS + 64, tZ = tS + 128;
             // The gradient GEMMs of tile t-1 are woven into the recompute of tile t: half 0 after the
@@ -521,7 +541,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               auto next_full = [&]() -> uint32_t {  // wait for the next ring slot to land
                 const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
                 ++it;
-                mbar_wait(bar(kFull0 + slot), par);
+                mbar_wait_t(bar(kFull0 + slot), par, 2, true);
                 tc_fence_after();
                 slot_bar = bar(kEmpty0 + slot);
                 return base + kOffRing + slot * kSlotBytes;
@@ -615,7 +635,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             mma_commit_pair(bar(kTmemFull0 + buf), 3);
             if (kIsBwd) {
               if (t == t0) {
-                mbar_wait(bar(kAccEmpty), jpar ^ 1);  // the previous job's accumulators were read out
+                mbar_wait_t(bar(kAccEmpty), jpar ^ 1, 5, true);  // the previous job's accumulators were read out
                 tc_fence_after();
               } else {
                 // kBwdW: nothing is woven - with per-half buffers the whole tile t is issued (and handed to the
@@ -634,6 +654,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           }
           mma_commit_pair(bar(kJobDone), 3);
         }
+        MC_PROF_TOTAL(6, prof_t0, true);
       }
     }
     __syncwarp();
@@ -655,6 +676,9 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     const float cS2 = inv_s2 * p.inv_tau * kL2e, cZ2 = inv_s2 * p.half_tau * kL2e;  // raw acc -> log2 domain
     const float m2cS2 = -2.f * cS2;
     uint32_t tt = 0, jj = 0;
+    [[maybe_unused]] const bool prof_rec = leader && (threadIdx.x == 128 || threadIdx.x == 256);
+    [[maybe_unused]] const int prof_base = threadIdx.x == 128 ? 16 : 24;
+    [[maybe_unused]] const long long prof_t0 = MC_PROF_NOW();
     for (int job = pair_id; job < njobs; job += npairs, ++jj) {
       int rb, sp;
       pair_job(p, job, rb, sp);
@@ -721,7 +745,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         float* cst = consts + (tt & 1) * (8 * 128);
         if (kIsBwd) {
           // the per-column constants of this tile come from warp 3, one tile ahead (no global loads, no block barrier here)
-          mbar_wait(bar(kCstFull0 + (tt & 1)), (tt >> 1) & 1);
+          mbar_wait_t(bar(kCstFull0 + (tt & 1)), (tt >> 1) & 1, prof_base + 0, prof_rec);
         } else if (PHASE != kStats && PHASE != kStatsZ) {
           if (tid_e < 128) {
             const int jcol = t * kTileN + tid_e;
@@ -735,7 +759,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const bool ragged = (t + 1) * kTileN > p.B;  // last tile of a batch that is not a multiple of 128
         const int jlim = p.B - t * kTileN;           // columns jl < jlim are real
         const uint32_t buf = tt % kNBuf, use = tt / kNBuf;
-        mbar_wait(bar(kTmemFull0 + buf), use & 1);
+        mbar_wait_t(bar(kTmemFull0 + buf), use & 1, prof_base + 1, prof_rec);
         tc_fence_after();
         const uint32_t tS = tmem_base + buf * 192 + lane_field + 32 * h, tSt = tS + 64, tZ = tS + 128;
 
@@ -952,8 +976,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           // The single weight buffer is used by column half 0, then half 1, of every tile: wait until
           // the gradient MMAs of the preceding half have drained it.  One barrier per half keeps every
           // waiter at most one phase behind, which the parity test needs.
-          if (h == 0 || (kW && !zf)) mbar_wait(bar(kGradDone1), (tt & 1) ^ 1);  // half 1 of the previous tile consumed
-          else mbar_wait(bar(kGradDone), tt & 1);                // half 0 of this tile consumed (shared dZ buffer)
+          if (h == 0 || (kW && !zf)) mbar_wait_t(bar(kGradDone1), (tt & 1) ^ 1, prof_base + 2, prof_rec);  // half 1 of the previous tile consumed
+          else mbar_wait_t(bar(kGradDone), tt & 1, prof_base + 2, prof_rec);                // half 0 of this tile consumed (shared dZ buffer)
           // row m of a 64 x 64 fp16 tile (128 B rows, SWIZZLE_128B): this thread owns K = 32 n1 .. +31
           uint8_t* wrow = sbase + kOffW + m * 128;
           uint8_t* wrow_s = wrow + ((kW && h == 1) ? kChunkBytes : 0);   // kBwdW: half 1 writes the dS^T slot
@@ -1035,7 +1059,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       } else {
         // accumulators: lanes 0-63 hold d in [0, D/2), lanes 64-127 hold [D/2, D); this thread reads the
         // column half h of its lane's D/2 columns
-        mbar_wait(bar(kAccFull), jj & 1);
+        mbar_wait_t(bar(kAccFull), jj & 1, prof_base + 3, prof_rec);
         tc_fence_after();
         // kBwdW: the dI accumulator is written by flagged tiles only; a job without any holds no dI at all
         const bool di_any = !kW || !frow || job_has_tiles(frow, t0, t1);
@@ -1061,6 +1085,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         mbar_arrive_cluster(bar(kAccEmpty), 0);
       }
     }
+    MC_PROF_TOTAL(prof_base + 4, prof_t0, prof_rec);
   }
 
   // teardown: nobody leaves while the peer may still touch this CTA's shared memory or TMEM
@@ -1068,6 +1093,21 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   cluster_sync_all();
   if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
 }
+#ifdef MC_WAIT_PROFILE
+}  // namespace tc
+}  // namespace mc
+extern "C" int mc_debug_wait_profile(unsigned long long* out64, int reset) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+  if (out64 && cudaMemcpyFromSymbol(out64, mc::tc::g_wait_prof, 64 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[64] = {};
+    if (cudaMemcpyToSymbol(mc::tc::g_wait_prof, z, sizeof(z)) != cudaSuccess) return 1;
+  }
+  return 0;
+}
+namespace mc {
+namespace tc {
+#endif
 
 // ------------------------------------------------------------------------------------------
 // finalize kernels: merge the per-split partials
