@@ -43,7 +43,10 @@ constexpr int kEpiThreads = 256;
 constexpr int kMaxSplit = 16;
 constexpr int kIssuers = 1;         // MMA-issuing warps per leader CTA (see the issuer role)
 
-enum Phase { kStats = 0, kRowLoss = 1, kBwd = 2, kStatsZ = 3, kBwdW = 4 };
+enum Phase { kStats = 0, kRowLoss = 1, kBwd = 2, kStatsZ = 3, kBwdW = 4, kBwdP = 5 };
+// kBwdP is the soft-target part of the gradient in the own-rows form, on the FLAGGED tiles only: dS_ij = -2 P_ij,
+// dS_ji = -2 P_ji and the dZ weights (everything that vanishes where P does).  It complements rowgrad_kernel, which
+// computes the softmax part of dS on every tile.
 // kBwdW is the row half of the "stored weights" gradient: like kBwd it recomputes S (and, on flagged tiles only, S^T and
 // Z) and accumulates dT_i, but instead of recomputing the transposed strip everywhere to form dS^T for dI_i, it writes
 // the fp16 weight tile dS_ij to global memory (PairParams::wout); colgrad_kernel then forms dI_j = sum_i dS_ij T_i from
@@ -139,6 +142,16 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int t
 #define MC_PROF_NOW() 0LL
 #define mbar_wait_t(bar, parity, tag, rec) mbar_wait(bar, parity)
 #define MC_PROF_TOTAL(tag, t0, rec) do { } while (0)
+#endif
+// Timing ablations (never in the product build; results are garbage, only the clock matters):
+//   -DMC_ABLATE_TMA  the ring producer signals its slots full without loading anything
+//   -DMC_ABLATE_EPI  the epilogue hands the tile buffer back and skips its arithmetic
+#ifdef MC_ABLATE_TMA
+#define MC_RING_LOAD(...) do { } while (0)
+#define MC_RING_ARM(fb, bytes) mbar_arrive_local(fb)
+#else
+#define MC_RING_LOAD(...) tma_load_2d_pair(__VA_ARGS__)
+#define MC_RING_ARM(fb, bytes) mbar_arrive_expect_tx(fb, bytes)
 #endif
 constexpr float kFlagTheta2 = 44.f;
 constexpr float kProbeMargin2 = 2.f;  // slack on top of the probe's worst-case rounding bound (see zmargin2)    // log2 units: dropped terms are below 2^-44 of their row's soft-target mass
@@ -248,7 +261,9 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             const __grid_constant__ CUtensorMap map_t, const PairParams p) {
   // TMEM: tile buffers of 3 x 64 columns (S, St, Z) from column 0; the gradient sweep keeps one tile
   // buffer (the epilogue empties it into registers at once) and its accumulators at 256 (dT), 256 + D/2 (dI)
-  constexpr bool kIsBwd = PHASE == kBwd || PHASE == kBwdW;
+  constexpr bool kIsBwd = PHASE == kBwd || PHASE == kBwdW || PHASE == kBwdP;
+  constexpr bool kSparse = PHASE == kRowLoss || PHASE == kStatsZ || PHASE == kBwdP;   // flagged tiles / jobs only
+  constexpr bool kP = PHASE == kBwdP;
   constexpr bool kW = PHASE == kBwdW;
   constexpr int kNBuf = kIsBwd ? 1 : 2;
   constexpr uint32_t kAccCol = 256;
@@ -318,7 +333,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           pair_job(p, job, rb, sp);
           const int row_a = p.row_offset + rb * 128 + (int)rank * kRowsCta;
           const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-          if ((PHASE == kRowLoss || PHASE == kStatsZ) && p.flags &&
+          if (kSparse && p.flags &&
               !job_has_tiles(p.flags + (size_t)rb * p.n_tiles, t0, t1)) continue;   // jj counts processed jobs only
           const uint32_t jpar = jj++ & 1;
           mbar_wait_t(bar(kJobDone), jpar ^ 1, 8, leader);
@@ -329,7 +344,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             for (int c = 0; c < 2 * nkc; ++c)
               tma_load_2d_pair(base + kOffAlo + c * kChunkBytes, &map_a_lo, bar(kAFull), c * 64, row_a);
           for (int t = t0; t < t1; ++t) {
-            if ((PHASE == kRowLoss || PHASE == kStatsZ) && p.flags && !p.flags[(size_t)rb * p.n_tiles + t]) continue;
+            if (kSparse && p.flags && !p.flags[(size_t)rb * p.n_tiles + t]) continue;
             // kBwdW: a tile without soft-target mass needs S only - no T_j planes, no I_i lo
             const bool zt = !kW || !p.flags || p.flags[(size_t)rb * p.n_tiles + t] != 0;
             const int j0 = t * kTileN + 32 * (int)rank, j1 = j0 + 64;
@@ -341,34 +356,34 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                 ++it;
                 mbar_wait_t(bar(kEmpty0 + slot), par ^ 1, 9, leader);
                 fb = bar(kFull0 + slot);
-                if (leader) mbar_arrive_expect_tx(fb, bytes);
+                if (leader) MC_RING_ARM(fb, bytes);
                 return base + kOffRing + slot * kSlotBytes;
               };
               if (PASSES == 3) {
                 uint32_t sb;
                 if (!kResLo) {
                   sb = acquire(zt ? 2u * kSlotBytes : 2u * kChunkBytes);
-                  if (zt) tma_load_2d_pair(sb, &map_a_lo, fb, ci, row_a);               // I_i lo
-                  tma_load_2d_pair(sb + kChunkBytes, &map_a_lo, fb, ct, row_a);         // T_i lo
+                  if (zt) MC_RING_LOAD(sb, &map_a_lo, fb, ci, row_a);               // I_i lo
+                  MC_RING_LOAD(sb + kChunkBytes, &map_a_lo, fb, ct, row_a);         // T_i lo
                 }
                 sb = acquire(2u * kSlotBytes);
-                tma_load_2d_pair(sb, &map_b_hi, fb, ci, j0);                            // I_j hi
-                tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ci, j1);
-                tma_load_2d_pair(sb + kChunkBytes, &map_b_lo, fb, ci, j0);              // I_j lo
-                tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_lo, fb, ci, j1);
+                MC_RING_LOAD(sb, &map_b_hi, fb, ci, j0);                            // I_j hi
+                MC_RING_LOAD(sb + 4096, &map_b_hi, fb, ci, j1);
+                MC_RING_LOAD(sb + kChunkBytes, &map_b_lo, fb, ci, j0);              // I_j lo
+                MC_RING_LOAD(sb + kChunkBytes + 4096, &map_b_lo, fb, ci, j1);
                 if (zt) {
                   sb = acquire(2u * kSlotBytes);
-                  tma_load_2d_pair(sb, &map_b_hi, fb, ct, j0);                          // T_j hi
-                  tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ct, j1);
-                  tma_load_2d_pair(sb + kChunkBytes, &map_b_lo, fb, ct, j0);            // T_j lo
-                  tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_lo, fb, ct, j1);
+                  MC_RING_LOAD(sb, &map_b_hi, fb, ct, j0);                          // T_j hi
+                  MC_RING_LOAD(sb + 4096, &map_b_hi, fb, ct, j1);
+                  MC_RING_LOAD(sb + kChunkBytes, &map_b_lo, fb, ct, j0);            // T_j lo
+                  MC_RING_LOAD(sb + kChunkBytes + 4096, &map_b_lo, fb, ct, j1);
                 }
               } else {
                 const uint32_t sb = acquire(2u * kSlotBytes);
-                tma_load_2d_pair(sb, &map_b_hi, fb, ci, j0);                            // I_j hi
-                tma_load_2d_pair(sb + 4096, &map_b_hi, fb, ci, j1);
-                tma_load_2d_pair(sb + kChunkBytes, &map_b_hi, fb, ct, j0);              // T_j hi
-                tma_load_2d_pair(sb + kChunkBytes + 4096, &map_b_hi, fb, ct, j1);
+                MC_RING_LOAD(sb, &map_b_hi, fb, ci, j0);                            // I_j hi
+                MC_RING_LOAD(sb + 4096, &map_b_hi, fb, ci, j1);
+                MC_RING_LOAD(sb + kChunkBytes, &map_b_hi, fb, ct, j0);              // T_j hi
+                MC_RING_LOAD(sb + kChunkBytes + 4096, &map_b_hi, fb, ct, j1);
               }
             }
           }
@@ -384,13 +399,16 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           int rb, sp;
           pair_job(p, job, rb, sp);
           const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-          for (int t = t0; t < t1; ++t, ++tt) {
+          for (int t = t0; t < t1; ++t) {
+            if (kSparse && p.flags && !p.flags[(size_t)rb * p.n_tiles + t]) continue;   // tt counts processed tiles
+            const uint32_t tt_cur = tt++;
+            (void)tt_cur;
             // kBwdW: T_j^T feeds the dZ GEMM only (dI's S part comes from the stored weights)
             const bool zt = !kW || !p.flags || p.flags[(size_t)rb * p.n_tiles + t] != 0;
             if (kW && !zt) {
               // no T_j^T tile: its buffer takes I_j^T of column half 1, so both halves load at once as soon as the
               // previous tile's gradient MMAs are done
-              mbar_wait(bar(kGradDone1), (tt & 1) ^ 1);
+              mbar_wait(bar(kGradDone1), (tt_cur & 1) ^ 1);
               for (int h = 0; h < 2; ++h) {
                 const uint32_t fb = bar(h == 0 ? kXTFull : kXTFull1);
                 if (leader) mbar_arrive_expect_tx(fb, 2u * xt_bytes);
@@ -400,7 +418,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             }
             for (int h = 0; h < 2; ++h) {
               // the previous half's MMAs are done with the buffer: (tt-1, 1) before (tt, 0); (tt, 0) before (tt, 1)
-              if (h == 0) mbar_wait(bar(kGradDone1), (tt & 1) ^ 1); else mbar_wait(bar(kGradDone), tt & 1);
+              if (h == 0) mbar_wait(bar(kGradDone1), (tt_cur & 1) ^ 1); else mbar_wait(bar(kGradDone), tt_cur & 1);
               const uint32_t fb = bar((kW && h == 1) ? kXTFull1 : kXTFull);
               if (leader) mbar_arrive_expect_tx(fb, 2u * 2u * xt_bytes);
               const int jx = t * kTileN + 64 * h;
@@ -423,7 +441,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         int rb, sp;
         pair_job(p, job, rb, sp);
         const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
-        for (int t = t0; t < t1; ++t, ++tt) {
+        for (int t = t0; t < t1; ++t) {
+          if (kSparse && p.flags && !p.flags[(size_t)rb * p.n_tiles + t]) continue;
           float vr[4], vc[4], vz[4], vg[4], vq[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -452,6 +471,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             }
           }
           mbar_arrive_local(bar(kCstFull0 + (tt & 1)));
+          ++tt;
         }
       }
     } else if (warp == 1 || (kIssuers == 2 && warp == 3)) {
@@ -515,15 +535,16 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           pair_job(p, job, rb, sp);
           const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
           const uint8_t* frow = p.flags ? p.flags + (size_t)rb * p.n_tiles : nullptr;
-          if ((PHASE == kRowLoss || PHASE == kStatsZ) && frow && !job_has_tiles(frow, t0, t1)) continue;
+          if (kSparse && frow && !job_has_tiles(frow, t0, t1)) continue;
           const uint32_t jpar = jj++ & 1;
           mbar_wait_t(bar(kAFull), jpar, 0, true);
           tc_fence_after();
           bool zf = true, zf_prev = true;
           di_live = false;
+          int nproc = 0;   // tiles of this job issued so far (sparse phases skip tiles)
           const bool zprobe = PHASE == kStats && p.flags_out != nullptr;  // Z from the hi planes only
           for (int t = t0; t < t1; ++t) {
-            if ((PHASE == kRowLoss || PHASE == kStatsZ) && frow && !frow[t]) continue;   // every role skips the same tiles
+            if (kSparse && frow && !frow[t]) continue;   // every role skips the same tiles
             zf_prev = zf;
             zf = !kIsBwd || !frow || frow[t] != 0;                 // gradient sweep: recompute Z only where P lives
             zg = zf_prev;                                          // the woven gradient GEMMs belong to tile t - 1
@@ -534,9 +555,9 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             // The gradient GEMMs of tile t-1 are woven into the recompute of tile t: half 0 after the
             // first chunks (its weights are ready by then), half 1 after the last chunk, so the
             // single weight / X^T buffers are refilled while the tensor cores stay busy.
-            const bool lagged = kIsBwd && t > t0;
+            const bool lagged = kIsBwd && nproc > 0;
             for (int c = 0; c < nkc; ++c) {
-              if (!kW && lagged && c == nkc - 1) grad_half(0, t - 1 == t0);
+              if (!kW && lagged && c == nkc - 1) grad_half(0, nproc == 1);
               uint32_t slot_bar = 0;
               auto next_full = [&]() -> uint32_t {  // wait for the next ring slot to land
                 const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
@@ -634,21 +655,22 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             }
             mma_commit_pair(bar(kTmemFull0 + buf), 3);
             if (kIsBwd) {
-              if (t == t0) {
+              if (nproc == 0) {
                 mbar_wait_t(bar(kAccEmpty), jpar ^ 1, 5, true);  // the previous job's accumulators were read out
                 tc_fence_after();
               } else {
                 // kBwdW: nothing is woven - with per-half buffers the whole tile t is issued (and handed to the
                 // epilogue) before the issuer waits for the weights of tile t - 1
-                if (kW) grad_half(0, t - 1 == t0);
+                if (kW) grad_half(0, nproc == 1);
                 grad_half(1, false);
               }
             }
+            ++nproc;
             ++tt;
           }
           if (kIsBwd) {
             zg = zf;  // the last tile's own gradient GEMMs
-            grad_half(0, t1 - 1 == t0);
+            grad_half(0, nproc == 1);
             grad_half(1, false);
             mma_commit_pair(bar(kAccFull), 3);
           }
@@ -675,7 +697,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     const float inv_s = p.scale[1], inv_s2 = p.scale[2];
     const float cS2 = inv_s2 * p.inv_tau * kL2e, cZ2 = inv_s2 * p.half_tau * kL2e;  // raw acc -> log2 domain
     const float m2cS2 = -2.f * cS2;
-    uint32_t tt = 0, jj = 0;
+    uint32_t tt = 0, jj = 0, jp = 0;   // jp: processed jobs (sparse phases skip jobs)
     [[maybe_unused]] const bool prof_rec = leader && (threadIdx.x == 128 || threadIdx.x == 256);
     [[maybe_unused]] const int prof_base = threadIdx.x == 128 ? 16 : 24;
     [[maybe_unused]] const long long prof_t0 = MC_PROF_NOW();
@@ -686,9 +708,10 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       const int lrow = rb * 128 + (int)rank * kRowsCta + m;  // row within this rank's strip
       const int gi = p.row_offset + lrow;
       const bool row_ok = lrow < p.b;
-      if ((PHASE == kRowLoss || PHASE == kStatsZ) && p.flags &&
+      if (kSparse && p.flags &&
           !job_has_tiles(p.flags + (size_t)rb * p.n_tiles, t0, t1)) {
         // no flagged tile in this (row block, column split): the other roles skip the job too; its partials are empty
+        if (kP) continue;   // the caller zeroed the gradient partials
         if (2 * h + n1 == 0) {
           if (PHASE == kStatsZ) {
             float2* out = reinterpret_cast<float2*>(p.part);
@@ -739,7 +762,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       }
 
       for (int t = t0; t < t1; ++t) {
-        if ((PHASE == kRowLoss || PHASE == kStatsZ) && frow && !frow[t]) continue;       // every role skips the same tiles
+        if (kSparse && frow && !frow[t]) continue;       // every role skips the same tiles
         const bool zf = !kIsBwd || !frow || frow[t] != 0;          // gradient sweep: does this tile carry P mass?
         // ---- per-column statistics of this tile -> shared memory, one field per 128-float row
         float* cst = consts + (tt & 1) * (8 * 128);
@@ -775,6 +798,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         mbar_arrive_cluster(bar(kTmemEmpty0 + buf), 0);
 
         if (PHASE == kStats || PHASE == kStatsZ) {
+#ifndef MC_ABLATE_EPI
           const bool zprobe = PHASE == kStats && p.flags_out != nullptr;
           auto lse_add32 = [&](float* v, float c, float& mx, float& sm) {
             if (ragged) {
@@ -888,6 +912,7 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                   cm_own == -INFINITY ? -INFINITY : fmaf(cm_own, cS2, lg2f(a[0]));
             }
           }
+#endif
         } else if (PHASE == kRowLoss) {
           if (ragged) {
 #pragma unroll
@@ -929,8 +954,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               for (int u = 0; u < 4; ++u) {
                 // kBwdW: the transposed strip exists on flagged tiles only (kZ) and feeds G_ji alone - dS_ji is not formed
                 const float a = vs[e + u], bt = (!kW || kZ) ? vt[e + u] : 0.f;
-                const float e1 = ex2f(fmaf(a, cS2, -r2_i));     // softmax_row(S)_ij
-                const float e3 = kW ? 0.f : ex2f(fmaf(bt, cS2, nr[u]));    // softmax_row(S)_ji
+                const float e1 = kP ? 0.f : ex2f(fmaf(a, cS2, -r2_i));     // softmax_row(S)_ij (kBwdP: rowgrad_kernel's part)
+                const float e3 = (kW || kP) ? 0.f : ex2f(fmaf(bt, cS2, nr[u]));    // softmax_row(S)_ji
                 float P = 0.f, Pt = 0.f, dS, dSt = 0.f;
                 if (kZ) {
                   const float z2 = vz[e + u] * cZ2;
@@ -941,10 +966,10 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                   dS = fmaf(e1, fmaf(fC_i, qc[u], 1.f), -2.f * P);        // 2B dS_ij
                   if (!kW) dSt = fmaf(e3, fmaf(ej[u], fFQ_i, 1.f), -2.f * Pt);     // 2B dS_ji
                 } else {
-                  const float e2 = ex2f(fmaf(a, cS2, nc[u]));   // softmax_col(S)_ij
+                  const float e2 = kP ? 0.f : ex2f(fmaf(a, cS2, nc[u]));   // softmax_col(S)_ij
                   dS = fmaf(-2.f, P, fmaf(e2, qc[u], e1));
                   if (!kW) {
-                    const float e4 = ex2f(fmaf(bt, cS2, -c2_i));  // softmax_col(S)_ji
+                    const float e4 = kP ? 0.f : ex2f(fmaf(bt, cS2, -c2_i));  // softmax_col(S)_ji
                     dSt = fmaf(-2.f, Pt, fmaf(e4, q_i, e3));
                   }
                 }
@@ -1059,7 +1084,8 @@ pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       } else {
         // accumulators: lanes 0-63 hold d in [0, D/2), lanes 64-127 hold [D/2, D); this thread reads the
         // column half h of its lane's D/2 columns
-        mbar_wait_t(bar(kAccFull), jj & 1, prof_base + 3, prof_rec);
+        mbar_wait_t(bar(kAccFull), jp & 1, prof_base + 3, prof_rec);
+        ++jp;
         tc_fence_after();
         // kBwdW: the dI accumulator is written by flagged tiles only; a job without any holds no dI at all
         const bool di_any = !kW || !frow || job_has_tiles(frow, t0, t1);
@@ -1507,6 +1533,25 @@ __global__ void __launch_bounds__(256) bwd_rows_finalize_kernel(const float* __r
     reinterpret_cast<float4*>(dIz)[i] = ai;
   }
 }
+// fold of the split row half: dT = scale (sum_s rowgrad partials + kBwdP's dT partial), dIz = kBwdP's dI partial
+__global__ void __launch_bounds__(256) bwd_rows_split_finalize_kernel(const float* __restrict__ part_r, int nsplit_r,
+                                                                      size_t plane_r, const float* __restrict__ part_p,
+                                                                      size_t plane_p, int b, int D, float inv_2B,
+                                                                      const float* __restrict__ grad_loss,
+                                                                      const float* __restrict__ wscale,
+                                                                      float* __restrict__ dT, float* __restrict__ dIz) {
+  const float scale = (grad_loss ? *grad_loss : 1.f) * inv_2B / *wscale;
+  const size_t n4 = (size_t)b * D / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 at = reinterpret_cast<const float4*>(part_p)[i];
+    for (int s = 0; s < nsplit_r; ++s) {
+      const float4 a = reinterpret_cast<const float4*>(part_r + (size_t)s * plane_r)[i];
+      at.x += a.x; at.y += a.y; at.z += a.z; at.w += a.w;
+    }
+    reinterpret_cast<float4*>(dT)[i] = make_float4(at.x * scale, at.y * scale, at.z * scale, at.w * scale);
+    reinterpret_cast<float4*>(dIz)[i] = reinterpret_cast<const float4*>(part_p + plane_p)[i];
+  }
+}
 // fold of the column half: dI_j = scale (dIz_j + sum_k part_k[j])
 __global__ void __launch_bounds__(256) bwd_cols_finalize_kernel(const float* __restrict__ part, int ksplit, size_t plane,
                                                                 int rows, int D, float inv_2B,
@@ -1523,6 +1568,329 @@ __global__ void __launch_bounds__(256) bwd_cols_finalize_kernel(const float* __r
     }
     reinterpret_cast<float4*>(dI)[i] = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Dense row half of the stored-weights gradient, the softmax part of dS only:
+//     2B dS_ij (softmax part) = softmax_row(S)_ij + q_j softmax_col(S)_ij            (the -2 P_ij term and everything
+// that depends on Z live on the flagged tiles and are added by pair_kernel<kBwdP>, which visits those tiles only).
+// Every tile needs S = T_i I_j^T alone, so this kernel is built around LARGE MMA instructions: tools/mma_issue_bench.cu shows
+// that one thread sustains the full tensor rate for every cta_group::2 shape only while it does nothing else - every
+// wait, fence or descriptor computation between two 32-cycle (M = 128, N = 128) MMAs is exposed, which is what holds
+// pair_kernel at ~50% of the tensor pipe (profiles/r02r_wait_profile_pair_kernel.json, ablation in DESIGN 4.1).
+//   * a CTA pair owns 256 rows i (128 per CTA, cta_group::2 with M = 256: TMEM lane = row); S tiles are 256 x 128
+//     (64-cycle MMAs), the gradient GEMM dT_i += W I_j is M = 256, N = D (128-cycle MMAs);
+//   * T_i hi stays resident (64 KB); a ring slot carries one 64-wide K chunk of {T_i lo, I_j hi, I_j lo} (32 KB);
+//   * TMEM: two S tile buffers (2 x 128 columns) + the dT accumulator (D columns);
+//   * the fp16 weight tile goes to shared memory (A operand of the gradient GEMM, one buffer per 64-column half, as
+//     does the I_j^T tile) and, as full 128-byte rows, to the stored strip W that colgrad_kernel turns into dI.
+// Roles: warp 0 ring producer, warp 1 MMA issuer, warp 2 I_j^T producer, warp 3 per-column constants, warps 4-11
+// epilogue (lane quarter x column half).
+// ------------------------------------------------------------------------------------------
+constexpr int kRgThreads = 384;
+constexpr int kRgRowsCta = 128;
+constexpr int kRgSlotBytes = 32768;
+constexpr int kRgSlots = 3;
+constexpr int kRgOffA = 0;                                   // T_i hi: D/64 chunks of 128 rows x 128 B
+constexpr int kRgOffRing = 65536;
+constexpr int kRgOffW = kRgOffRing + kRgSlots * kRgSlotBytes;    // 2 x (128 rows x 64 j) fp16
+constexpr int kRgOffXT = kRgOffW + 2 * 16384;                    // 2 x (D/2 rows x 64 j) fp16
+constexpr int kRgOffConst = kRgOffXT + 2 * 16384;                // 2 buffers x 2 fields x 128 floats
+constexpr int kRgOffBar = kRgOffConst + 2048;
+constexpr int kRgSmemBytes = kRgOffBar + 256 + 512;   // the dynamic segment is declared 1024-aligned; 512 bytes of slack are checked
+enum RgBar {
+  kRgFull0 = 0, kRgEmpty0 = 3, kRgAFull = 6, kRgJobDone = 7, kRgTmemFull0 = 8, kRgTmemEmpty0 = 10, kRgWFull0 = 12,
+  kRgXTFull0 = 14, kRgGradDone0 = 16, kRgAccFull = 18, kRgAccEmpty = 19, kRgCstFull0 = 20, kRgCstEmpty0 = 22, kRgNumBars = 24
+};
+struct RowGradParams {
+  int b, B, Bp, D, row_offset;
+  int n_row_blocks, n_tiles, nsplit, tiles_per_split, bpad;     // row blocks of 256
+  float inv_tau;
+  const float* scale;
+  const float *r, *c, *q;
+  const float* wscale;
+  float* part;            // [nsplit][bpad][D]
+  __half* wout;           // (bpad x Bp)
+};
+__global__ void __launch_bounds__(kRgThreads, 1)
+rowgrad_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const __grid_constant__ CUtensorMap map_t, const RowGradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  if (base - raw > 512u) __trap();   // the map below would run past the allocation
+  uint8_t* const sbase = smem_raw + (base - raw);
+  const uint32_t bar0 = base + kRgOffBar;
+  auto bar = [&](int i) -> uint32_t { return bar0 + 8u * i; };
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(sbase + kRgOffBar + 8 * kRgNumBars);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int D = p.D, nkc = D >> 6;
+  const int njobs = p.n_row_blocks * p.nsplit;
+  const uint32_t xt_bytes = (uint32_t)(D / 2) * 128u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRgSlots; ++s) { mbar_init(bar(kRgFull0 + s), 1); mbar_init(bar(kRgEmpty0 + s), 1); }
+    mbar_init(bar(kRgAFull), 1);
+    mbar_init(bar(kRgJobDone), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(kRgTmemFull0 + i), 1);
+      mbar_init(bar(kRgTmemEmpty0 + i), 2 * 256);
+      mbar_init(bar(kRgWFull0 + i), 2 * 128);
+      mbar_init(bar(kRgXTFull0 + i), 1);
+      mbar_init(bar(kRgGradDone0 + i), 1);
+      mbar_init(bar(kRgCstFull0 + i), 32);
+      mbar_init(bar(kRgCstEmpty0 + i), 256);
+    }
+    mbar_init(bar(kRgAccFull), 1);
+    mbar_init(bar(kRgAccEmpty), 2 * 256);
+    fence_mbar_init();
+    prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_b_hi); prefetch_tmap(&map_b_lo);
+    prefetch_tmap(&map_t);
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(smem_u32(tmem_slot), 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kAcc = 256;   // dT accumulator columns [256, 256 + D)
+
+  if (warp == 0) {
+    // ===================================================== ring producer
+    if (elect_one()) {
+      uint32_t it = 0, jj = 0;
+      for (int job = pair_id; job < njobs; job += npairs, ++jj) {
+        const int rb = job / p.nsplit, sp = job % p.nsplit;
+        const int row_a = p.row_offset + rb * 256 + (int)rank * kRgRowsCta;
+        const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+        mbar_wait(bar(kRgJobDone), (jj & 1) ^ 1);
+        if (leader) mbar_arrive_expect_tx(bar(kRgAFull), 2u * (uint32_t)nkc * 16384u);
+        for (int c = 0; c < nkc; ++c) tma_load_2d_pair(base + kRgOffA + c * 16384, &map_a_hi, bar(kRgAFull), D + c * 64, row_a);
+        for (int t = t0; t < t1; ++t) {
+          const int j0 = t * kTileN + 64 * (int)rank;
+          for (int c = 0; c < nkc; ++c, ++it) {
+            const uint32_t slot = it % kRgSlots, par = (it / kRgSlots) & 1;
+            mbar_wait(bar(kRgEmpty0 + slot), par ^ 1);
+            const uint32_t fb = bar(kRgFull0 + slot), sb = base + kRgOffRing + slot * kRgSlotBytes;
+            if (leader) mbar_arrive_expect_tx(fb, 2u * kRgSlotBytes);
+            tma_load_2d_pair(sb, &map_a_lo, fb, D + c * 64, row_a);            // T_i lo   (128 rows)
+            tma_load_2d_pair(sb + 16384, &map_b_hi, fb, c * 64, j0);           // I_j hi   (64 rows)
+            tma_load_2d_pair(sb + 24576, &map_b_lo, fb, c * 64, j0);           // I_j lo
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================================== I_j^T half tiles (B operand of dT += W I_j)
+    if (elect_one()) {
+      uint32_t tt = 0;
+      for (int job = pair_id; job < njobs; job += npairs) {
+        const int sp = job % p.nsplit;
+        const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+        for (int t = t0; t < t1; ++t, ++tt) {
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(bar(kRgGradDone0 + h), (tt & 1) ^ 1);     // the previous tile's half-h MMAs have drained the buffer
+            const uint32_t fb = bar(kRgXTFull0 + h);
+            if (leader) mbar_arrive_expect_tx(fb, 2u * xt_bytes);
+            tma_load_2d_pair(base + kRgOffXT + h * 16384, &map_t, fb, t * kTileN + 64 * h, (int)rank * (D / 2));
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================================================== per-column constants, one tile ahead of the epilogue
+    //   fast (statistics within 60 binades, see wscale_kernel): field 0 = 2^(M - c2_j) q_j;  else 0 = -c2_j, 1 = q_j
+    float* const consts = reinterpret_cast<float*>(sbase + kRgOffConst);
+    const float kL2e = 1.4426950408889634f;
+    const bool fast = p.wscale[1] != 0.f;
+    const float m_rc = p.wscale[2];
+    uint32_t tt = 0;
+    for (int job = pair_id; job < njobs; job += npairs) {
+      const int sp = job % p.nsplit;
+      const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+      for (int t = t0; t < t1; ++t, ++tt) {
+        float vc[4], vq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jcol = t * kTileN + lane + 32 * u;
+          const bool ok = jcol < p.B;
+          vc[u] = ok ? p.c[jcol] : 0.f;
+          vq[u] = ok ? p.q[jcol] : 0.f;
+        }
+        mbar_wait(bar(kRgCstEmpty0 + (tt & 1)), ((tt >> 1) & 1) ^ 1);
+        float* dst = consts + (tt & 1) * 256;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int col = lane + 32 * u;
+          const bool ok = t * kTileN + col < p.B;
+          const float c2 = vc[u] * kL2e;
+          if (fast) {
+            dst[col] = ok ? ex2f(m_rc - c2) * vq[u] : 0.f;
+          } else {
+            dst[col] = -c2;
+            dst[128 + col] = vq[u];
+          }
+        }
+        mbar_arrive_local(bar(kRgCstFull0 + (tt & 1)));
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc_s = idesc_f16(256, kTileN);
+      const uint32_t idesc_g = idesc_f16(256, D);
+      const uint32_t tDT = tmem_base + kAcc;
+      uint32_t it = 0, tt = 0, gt = 0, jj = 0;
+      auto grad_tile = [&](bool first_of_job) {     // dT += W I_j of the tile whose weights are in the buffers
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(bar(kRgWFull0 + h), gt & 1);
+          mbar_wait(bar(kRgXTFull0 + h), gt & 1);
+          tc_fence_after();
+          const uint64_t wd = smem_desc_sw128(base + kRgOffW + h * 16384), xd = smem_desc_sw128(base + kRgOffXT + h * 16384);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_f16_pair(tDT, desc_advance_k(wd, ks), desc_advance_k(xd, ks), idesc_g, (first_of_job && h == 0 && ks == 0) ? 0u : 1u);
+          mma_commit_pair(bar(kRgGradDone0 + h), 3);
+        }
+        ++gt;
+      };
+      for (int job = pair_id; job < njobs; job += npairs, ++jj) {
+        const int sp = job % p.nsplit;
+        const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+        mbar_wait(bar(kRgAFull), jj & 1);
+        tc_fence_after();
+        for (int t = t0; t < t1; ++t, ++tt) {
+          const uint32_t buf = tt & 1, use = tt >> 1;
+          mbar_wait(bar(kRgTmemEmpty0 + buf), (use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tS = tmem_base + buf * 128;
+          for (int c = 0; c < nkc; ++c, ++it) {
+            const uint32_t slot = it % kRgSlots, par = (it / kRgSlots) & 1;
+            mbar_wait(bar(kRgFull0 + slot), par);
+            tc_fence_after();
+            const uint32_t sb = base + kRgOffRing + slot * kRgSlotBytes;
+            const uint64_t aT = smem_desc_sw128(base + kRgOffA + c * 16384), aTl = smem_desc_sw128(sb);
+            const uint64_t bI = smem_desc_sw128(sb + 16384), bIl = smem_desc_sw128(sb + 24576);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t kT = desc_advance_k(aT, ks), kb = desc_advance_k(bI, ks);
+              mma_f16_pair(tS, kT, kb, idesc_s, (c > 0 || ks > 0) ? 1u : 0u);      // S = T_i I_j^T, three passes
+              mma_f16_pair(tS, kT, desc_advance_k(bIl, ks), idesc_s, 1u);
+              mma_f16_pair(tS, desc_advance_k(aTl, ks), kb, idesc_s, 1u);
+            }
+            mma_commit_pair(bar(kRgEmpty0 + slot), 3);
+          }
+          mma_commit_pair(bar(kRgTmemFull0 + buf), 3);
+          if (t == t0) {
+            mbar_wait(bar(kRgAccEmpty), (jj & 1) ^ 1);     // the previous job's accumulator was read out
+            tc_fence_after();
+          } else {
+            grad_tile(t - 1 == t0);
+          }
+        }
+        grad_tile(t1 - 1 == t0);
+        mma_commit_pair(bar(kRgAccFull), 3);
+        mma_commit_pair(bar(kRgJobDone), 3);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================================================== epilogue: thread = (TMEM lane m, column half h)
+    const int q4 = warp & 3, h = (warp - 4) >> 2;
+    const int m = q4 * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(q4 * 32) << 16;
+    const float* const consts = reinterpret_cast<const float*>(sbase + kRgOffConst);
+    const float kL2e = 1.4426950408889634f;
+    const float inv_s = p.scale[1], inv_s2 = p.scale[2];
+    const float cS2 = inv_s2 * p.inv_tau * kL2e;
+    const float wS = inv_s * p.inv_tau * p.wscale[0];
+    const bool fast = p.wscale[1] != 0.f;
+    const float m_rc = p.wscale[2];
+    uint32_t tt = 0, jj = 0;
+    for (int job = pair_id; job < njobs; job += npairs, ++jj) {
+      const int rb = job / p.nsplit, sp = job % p.nsplit;
+      const int t0 = sp * p.tiles_per_split, t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+      const int lrow = rb * 256 + (int)rank * kRgRowsCta + m;
+      const int gi = p.row_offset + lrow;
+      const bool row_ok = lrow < p.b;
+      const float r2_i = row_ok ? p.r[gi] * kL2e : 0.f;
+      const float fC_i = ex2f(r2_i - m_rc);
+      const float wrow = row_ok ? wS : 0.f;          // rows past the strip store exact zeros
+      for (int t = t0; t < t1; ++t, ++tt) {
+        const uint32_t buf = tt & 1, use = tt >> 1;
+        mbar_wait(bar(kRgCstFull0 + (tt & 1)), (tt >> 1) & 1);
+        const float* cst = consts + (tt & 1) * 256 + 64 * h;
+        mbar_wait(bar(kRgTmemFull0 + buf), use & 1);
+        tc_fence_after();
+        const uint32_t tS = tmem_base + buf * 128 + lane_field + 64 * h;
+        uint32_t wp[32];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          tmem_ld32(tS + 32 * half, v);
+          tmem_ld_wait();
+          if (half == 1) {
+            tc_fence_before();
+            mbar_arrive_cluster(bar(kRgTmemEmpty0 + buf), 0);
+          }
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 f0 = *reinterpret_cast<const float4*>(cst + 32 * half + e);
+            const float4 f1 = fast ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(cst + 128 + 32 * half + e);
+            const float k0[4] = {f0.x, f0.y, f0.z, f0.w}, k1[4] = {f1.x, f1.y, f1.z, f1.w};
+            float w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float a = v[e + u];
+              const float e1 = ex2f(fmaf(a, cS2, -r2_i));                       // softmax_row(S)_ij
+              float dS;
+              if (fast) dS = e1 * fmaf(fC_i, k0[u], 1.f);                       // + q_j softmax_col(S)_ij, factored
+              else dS = fmaf(ex2f(fmaf(a, cS2, k0[u])), k1[u], e1);
+              w[u] = dS * wrow;
+            }
+            __half2 x = __floats2half2_rn(w[0], w[1]), y = __floats2half2_rn(w[2], w[3]);
+            wp[16 * half + (e >> 1)] = *reinterpret_cast<uint32_t*>(&x);
+            wp[16 * half + (e >> 1) + 1] = *reinterpret_cast<uint32_t*>(&y);
+          }
+        }
+        // the half-h weight buffer: drained by the previous tile's gradient MMAs
+        mbar_wait(bar(kRgGradDone0 + h), (tt & 1) ^ 1);
+        uint8_t* wsm = sbase + kRgOffW + h * 16384 + m * 128;     // row m of a 128 x 64 fp16 tile, SWIZZLE_128B
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<uint4*>(wsm + ((k ^ (m & 7)) * 16)) = make_uint4(wp[4 * k], wp[4 * k + 1], wp[4 * k + 2], wp[4 * k + 3]);
+        fence_proxy_async_smem();
+        mbar_arrive_cluster(bar(kRgWFull0 + h), 0);
+        uint4* wg = reinterpret_cast<uint4*>(p.wout + (size_t)lrow * p.Bp + (size_t)t * kTileN + 64 * h);   // one full line
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wg[k] = make_uint4(wp[4 * k], wp[4 * k + 1], wp[4 * k + 2], wp[4 * k + 3]);
+        mbar_arrive_local(bar(kRgCstEmpty0 + (tt & 1)));
+      }
+      // ---- end of job: this job's partial dT (lane m, columns [h D/2, (h + 1) D/2))
+      mbar_wait(bar(kRgAccFull), jj & 1);
+      tc_fence_after();
+      float* out = p.part + ((size_t)sp * p.bpad + lrow) * D + h * (D / 2);
+      for (int c0 = 0; c0 < D / 2; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + lane_field + kAcc + h * (D / 2) + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(out + c0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(bar(kRgAccEmpty), 0);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1567,7 +1935,7 @@ struct Split {
 // accumulators per job, and every extra split adds a set of partial gradients to fold: 0.578 ms with 16 splits, 0.505
 // with 2; the statistics sweep is cheap per job)
 constexpr double kOvhStats = 1.5, kOvhRowLoss = 0.5, kOvhBwd = 6.0;
-template <int PHASE> constexpr double phase_ovh() { return (PHASE == kBwd || PHASE == kBwdW) ? kOvhBwd : (PHASE == kRowLoss ? kOvhRowLoss : kOvhStats); }
+template <int PHASE> constexpr double phase_ovh() { return (PHASE == kBwd || PHASE == kBwdW || PHASE == kBwdP) ? kOvhBwd : (PHASE == kRowLoss ? kOvhRowLoss : kOvhStats); }
 static Split choose_split(int b, int B, double ovh = kOvhRowLoss, int align = 1) {
   Split s;
   s.n_row_blocks = (b + 127) / 128;
@@ -1635,11 +2003,40 @@ size_t stats_colpart_workspace_bytes(int b, int B, int D, int mode) {
   return workspace_bytes(b, B, D, mode) - colpart_bytes(b, B) + colpart_bytes(b, B, true);
 }
 
+// rowgrad_kernel: row blocks of 256, tiles of 256 x 128; same cost model as choose_split (a job pays ~3 tiles of overhead)
+static Split choose_split_rows256(int b, int B) {
+  Split s;
+  s.n_row_blocks = (b + 255) / 256;
+  s.bpad = s.n_row_blocks * 256;
+  s.n_tiles = (int)(round_up((size_t)B, 128) / 128);
+  const int npairs = num_sms() / 2;
+  int best = 1;
+  double best_cost = 1e30;
+  const int max_split = s.n_tiles < kMaxSplit ? s.n_tiles : kMaxSplit;
+  for (int ns = 1; ns <= max_split; ++ns) {
+    const int tps = (s.n_tiles + ns - 1) / ns;
+    const long jobs = (long)s.n_row_blocks * ns;
+    const double cost = (double)((jobs + npairs - 1) / npairs) * (tps + 3.0) + 0.04 * ns;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
+  }
+  s.nsplit = best;
+  s.tiles_per_split = (s.n_tiles + best - 1) / best;
+  return s;
+}
+static size_t rowgrad_part_bytes(int b, int B, int D) {
+  Split s = choose_split_rows256(b, B);
+  return round_up((size_t)s.nsplit * s.bpad * D * sizeof(float), 256);
+}
+
 size_t workspace_bytes(int b, int B, int D, int /*mode*/) {
   Split s = choose_split(b, B, kOvhStats), sr = choose_split(b, B, kOvhRowLoss), sb = choose_split(b, B, kOvhBwd);
   (void)sr;
   size_t stats = (size_t)kMaxSplit * 4 * s.bpad * sizeof(float2);   // any split count (the chunked launches align theirs)
   size_t bwdp = (size_t)sb.nsplit * 2 * s.bpad * D * sizeof(float);
+  {  // the split gradient: rowgrad_kernel's dT partials (row blocks of 256) + kBwdP's single (dT, dI) partial
+    const size_t split_part = rowgrad_part_bytes(b, B, D) + (size_t)2 * s.bpad * D * sizeof(float);
+    if (split_part > bwdp) bwdp = split_part;
+  }
   return round_up(stats > bwdp ? stats : bwdp, 256) + 256 + colpart_bytes(b, B);  // + the weight-scale slot + column partials
 }
 static float* colpart_slot(void* ws, int b, int B, int D) {
@@ -1940,6 +2337,7 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float*
 
   const bool chunked = chunks > 1 && (PHASE == kStats || PHASE == kStatsZ);
   Split sp = choose_split(p.b, p.B, phase_ovh<PHASE>(), chunked ? chunks : 1);
+  if (PHASE == kBwdP) { sp.nsplit = 1; sp.tiles_per_split = sp.n_tiles; }   // a handful of flagged tiles per row block
   PairParams pp;
   pp.b = p.b; pp.B = p.B; pp.Bp = l.Bp; pp.D = p.D; pp.row_offset = p.row_offset;
   pp.n_row_blocks = sp.n_row_blocks; pp.n_tiles = sp.n_tiles; pp.nsplit = sp.nsplit;
@@ -2201,13 +2599,61 @@ static ColSplit choose_col_split(int w_rows, int n_cols) {
   c.steps_per_split = (c.steps + best - 1) / best;
   return c;
 }
-size_t stored_weights_bytes(int b, int B) { return round_up(round_up((size_t)b, 128) * round_up((size_t)B, 128) * sizeof(__half), 256); }
+size_t stored_weights_bytes(int b, int B) { return round_up(round_up((size_t)b, 256) * round_up((size_t)B, 128) * sizeof(__half), 256); }
 size_t bwd_cols_workspace_bytes(int /*w_rows*/, int n_cols, int D) {
   return round_up((size_t)kCgMaxSplit * ((size_t)(n_cols + 255) / 256 * 256) * D * sizeof(float), 256) + 256;
 }
 bool stored_form_enabled(int b, int B, int D) {
   static const bool off = getenv("MAE_CLIP_BWD_FORM") != nullptr && strcmp(getenv("MAE_CLIP_BWD_FORM"), "ownrows") == 0;
   return !off && supported(D) && stored_weights_bytes(b, B) <= ((size_t)16 << 30);
+}
+
+static int launch_rowgrad(const ClipProblem& p, int mode, const ClipStatsAll& s, float* part, const float* wscale,
+                          __half* wout, cudaStream_t st) {
+  MC_REQUIRE(mode == MC_GEMM_TC_F16X3, MC_ERR_UNSUPPORTED, "rowgrad: the split gradient belongs to the 3-pass engine");
+  MC_REQUIRE(p.row_offset % 128 == 0, MC_ERR_UNSUPPORTED, "rowgrad: row_offset %% 128 != 0 (%d)", p.row_offset);
+  PlanesLayout l = planes_layout(p.B, p.D);
+  const char* base = static_cast<const char*>(p.planes_all);
+  const void* Xh = base + l.off_hi;
+  const void* Xl = base + l.off_lo;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mt;
+  int rc;
+  if ((rc = make_map(&ma_hi, Xh, l.Bp, 2 * p.D, 128))) return rc;
+  if ((rc = make_map(&ma_lo, Xl, l.Bp, 2 * p.D, 128))) return rc;
+  if ((rc = make_map(&mb_hi, Xh, l.Bp, 2 * p.D, 64))) return rc;
+  if ((rc = make_map(&mb_lo, Xl, l.Bp, 2 * p.D, 64))) return rc;
+  if ((rc = make_map(&mt, base + l.off_hiT, 2 * p.D, l.Bp, p.D / 2))) return rc;
+  Split sp = choose_split_rows256(p.b, p.B);
+  RowGradParams rp;
+  rp.b = p.b; rp.B = p.B; rp.Bp = l.Bp; rp.D = p.D; rp.row_offset = p.row_offset;
+  rp.n_row_blocks = sp.n_row_blocks; rp.n_tiles = sp.n_tiles; rp.nsplit = sp.nsplit;
+  rp.tiles_per_split = sp.tiles_per_split; rp.bpad = sp.bpad;
+  rp.inv_tau = 1.f / p.tau;
+  rp.scale = reinterpret_cast<const float*>(base + l.off_hdr) + 1;
+  rp.r = s.r; rp.c = s.c; rp.q = s.q;
+  rp.wscale = wscale;
+  rp.part = part;
+  rp.wout = wout;
+  static std::atomic<unsigned long long> attr_done{0};
+  MC_CUDA(ensure_dynamic_smem(rowgrad_kernel, kRgSmemBytes, attr_done));
+  const long njobs = (long)sp.n_row_blocks * sp.nsplit;
+  int npairs = num_sms() / 2;
+  if (njobs < npairs) npairs = (int)njobs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * npairs);
+  cfg.blockDim = dim3(kRgThreads);
+  cfg.dynamicSmemBytes = kRgSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MC_CUDA(cudaLaunchKernelEx(&cfg, rowgrad_kernel, ma_hi, ma_lo, mb_hi, mb_lo, mt, rp));
+  count_launch();
+  return MC_OK;
 }
 
 // Row half over the strip p.row_offset .. + p.b: dT_loc (final), dIz_loc (b x D, un-scaled soft-target part of dI of the
@@ -2220,14 +2666,31 @@ int bwd_rows(const ClipProblem& p, int mode, const ClipStatsAll& s, const float*
   float* wsc = wscale_slot(ws, p.b, p.B, p.D);
   int rc;
   if ((rc = launch_wscale(p, s, wsc, st))) return rc;
-  if ((rc = launch_phase<kBwdW>(mode, p, s, nullptr, static_cast<float*>(ws), wsc, st, nullptr, -1, 1,
-                                static_cast<__half*>(W_rows))))
-    return rc;
-  Split sp = choose_split(p.b, p.B, kOvhBwd);
   size_t n4 = (size_t)p.b * p.D / 4;
   int blocks = (int)((n4 + 255) / 256);
   int cap = num_sms() * 8;
   if (blocks > cap) blocks = cap;
+  // With tile flags the sweep splits: rowgrad_kernel (softmax part of dS on every tile, large MMA shapes) + kBwdP
+  // (soft-target part on the flagged tiles).  Without flags every tile carries soft-target mass and kBwdW does both at
+  // once.  MAE_CLIP_BWD_SPLIT=0 keeps the single sweep (A/B switch).
+  static const bool split_off = getenv("MAE_CLIP_BWD_SPLIT") != nullptr && getenv("MAE_CLIP_BWD_SPLIT")[0] == '0';
+  if (p.tile_flags != nullptr && !split_off && mode == MC_GEMM_TC_F16X3) {
+    Split sr = choose_split_rows256(p.b, p.B), sp = choose_split(p.b, p.B, kOvhBwd);
+    float* part_r = static_cast<float*>(ws);
+    float* part_p = reinterpret_cast<float*>(static_cast<char*>(ws) + rowgrad_part_bytes(p.b, p.B, p.D));
+    const size_t plane_p = (size_t)sp.bpad * p.D;
+    MC_CUDA(cudaMemsetAsync(part_p, 0, 2 * plane_p * sizeof(float), st));   // row blocks without a flagged tile write nothing
+    if ((rc = launch_phase<kBwdP>(mode, p, s, nullptr, part_p, wsc, st))) return rc;
+    if ((rc = launch_rowgrad(p, mode, s, part_r, wsc, static_cast<__half*>(W_rows), st))) return rc;
+    bwd_rows_split_finalize_kernel<<<blocks, 256, 0, st>>>(part_r, sr.nsplit, (size_t)sr.bpad * p.D, part_p, plane_p, p.b, p.D,
+                                                          0.5f / (float)p.B, grad_loss, wsc, dT_loc, dIz_loc);
+    MC_LAUNCH_CHECK();
+    return MC_OK;
+  }
+  if ((rc = launch_phase<kBwdW>(mode, p, s, nullptr, static_cast<float*>(ws), wsc, st, nullptr, -1, 1,
+                                static_cast<__half*>(W_rows))))
+    return rc;
+  Split sp = choose_split(p.b, p.B, kOvhBwd);
   bwd_rows_finalize_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(ws), sp.nsplit, sp.bpad, p.b, p.D,
                                                    0.5f / (float)p.B, grad_loss, wsc, dT_loc, dIz_loc);
   MC_LAUNCH_CHECK();

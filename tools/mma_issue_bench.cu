@@ -20,7 +20,11 @@ __device__ __forceinline__ void issue_period(uint32_t tm, uint32_t accstride, ui
   }
 }
 
-__global__ void __launch_bounds__(128, 1) bench(int M, int N, int periods, int pattern, long long* out) {
+__global__ void __launch_bounds__(384, 1) bench(int M, int N, int periods, int pattern, int traffic /* 0 none, 1 st.shared, 2 ld.shared */, int traffic_warps, int extras, long long* out) {
+  __shared__ uint64_t dummy_bar[2];
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&dummy_bar[0]), 1); mbar_init(smem_u32(&dummy_bar[1]), 1); }
+  __shared__ volatile int stop_flag;
+  if (threadIdx.x == 0) stop_flag = 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -42,8 +46,13 @@ __global__ void __launch_bounds__(128, 1) bench(int M, int N, int periods, int p
     const uint32_t accstride = (M == 128) ? N / 2 : N;   // TMEM columns per accumulator
     const uint64_t a0 = smem_desc_sw128(base), b0 = smem_desc_sw128(base + 32768);
     const long long t0 = clock64();
+    const uint32_t db = smem_u32(&dummy_bar[0]), db1 = smem_u32(&dummy_bar[1]);
+    mbar_arrive_local(db1);   // phase 0 of dummy_bar[1] is complete: waiting on parity 0 succeeds at once
     for (int i = 0; i < periods; ++i) {
       const bool f = i == 0;
+      if (extras & 4) { mbar_wait(db1, 0); tc_fence_after(); }
+      if (extras & 1) mma_commit_pair(db, 1);
+      if (extras & 8) { mma_commit_pair(db, 3); }
       switch (pattern) {
         case 0: issue_period<0,0,0,0,0,0,0,0,0,0,0,0>(tm, accstride, a0, b0, idesc, f); break;   // one accumulator
         case 1: issue_period<0,1,0,1,0,1,0,1,0,1,0,1>(tm, accstride, a0, b0, idesc, f); break;   // alternate 2
@@ -57,6 +66,23 @@ __global__ void __launch_bounds__(128, 1) bench(int M, int N, int periods, int p
     mbar_wait(bar, 0);
     const long long t1 = clock64();
     if (blockIdx.x == 0) out[0] = t1 - t0;
+    stop_flag = 1;
+  } else if (warp >= 4 && warp < 4 + traffic_warps && traffic) {
+    // competing shared-memory traffic (the role TMA fills and the epilogue play in the real sweeps): 16-byte accesses,
+    // conflict-free, on a region the MMAs do not read
+    uint4* reg = reinterpret_cast<uint4*>(smem_raw + (base - raw) + 65536) + threadIdx.x;
+    uint4 v = make_uint4(threadIdx.x, 1, 2, 3);
+    unsigned long long n = 0;
+    while (!stop_flag && cluster_ctarank() == 0 || (cluster_ctarank() != 0 && n < (unsigned long long)periods * 12 * 2)) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (traffic == 1) reg[(u & 1) * 384] = v;
+        else { uint4 w = reg[(u & 1) * 384]; v.x ^= w.x; }
+      }
+      n += 8;
+    }
+    if (v.x == 0x12345) out[1] = (long long)v.x;
+    if (threadIdx.x == 128 && blockIdx.x == 0) out[2] = (long long)n;
   }
   __syncwarp();
   tc_fence_before();
@@ -65,32 +91,39 @@ __global__ void __launch_bounds__(128, 1) bench(int M, int N, int periods, int p
 }
 
 int main() {
-  long long* d; cudaMalloc(&d, 8);
+  long long* d; cudaMalloc(&d, 32);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const char* names[] = {"one accumulator", "alternate 2", "S,S,S,Z,Z,Z", "S,S,S,Z", "rotate 3", "runs of 4"};
   int shapes[][2] = {{128, 128}, {128, 256}, {256, 128}, {256, 256}};
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int extras : {0, 1, 4, 5, 8})
+  for (int traffic = 0; traffic < 1; ++traffic)
+  for (int tw = (traffic ? 2 : 8); tw <= 8; tw *= 2)
   for (auto& sh : shapes) {
-    for (int pat = 0; pat < 6; ++pat) {
+    if (sh[0] != 128 || sh[1] != 128) continue;
+    for (int pat = 3; pat < 4; ++pat) {
       const int M = sh[0], N = sh[1];
       const int accs = (M == 128 ? N / 2 : N);
       if (accs * 3 > 512 && pat == 4) continue;
       if (accs * 2 > 512 && pat != 0) continue;
       const int periods = 2048;
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(148); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 100 * 1024;
+      cfg.gridDim = dim3(148); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = 100 * 1024;
       cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim = {2,1,1};
       cfg.attrs = at; cfg.numAttrs = 1;
-      cudaLaunchKernelEx(&cfg, bench, M, N, 64, pat, d);   // warm-up
+      cudaLaunchKernelEx(&cfg, bench, M, N, 64, pat, traffic, tw, extras, d);   // warm-up
       cudaEventRecord(e0);
-      cudaError_t e = cudaLaunchKernelEx(&cfg, bench, M, N, periods, pat, d);
+      cudaError_t e = cudaLaunchKernelEx(&cfg, bench, M, N, periods, pat, traffic, tw, extras, d);
       cudaEventRecord(e1);
       cudaError_t e2 = cudaDeviceSynchronize();
       float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-      long long cyc = 0; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
+      long long res[4] = {}; cudaMemcpy(res, d, 32, cudaMemcpyDeviceToHost);
+      long long cyc = res[0];
       const double n = periods * 12.0, per = (double)cyc / n;
       const double tflops = 74.0 * n * 2.0 * M * N * 16 / (ms * 1e-3) / 1e12;
-      printf("M=%3d N=%3d %-16s %7.2f cyc/MMA  %7.1f MAC/cyc/SM  %7.1f TFLOP/s chip (%.3f ms) %s %s\n", M, N, names[pat], per,
+      const double tbytes = traffic ? (double)res[2] * 16.0 * 32 * tw / cyc : 0.0;   // competing bytes per cycle per SM
+      printf("extras=%d M=%3d N=%3d %-10s traffic %s x%d warps (%5.1f B/clk) %7.2f cyc/MMA  %7.1f MAC/cyc/SM  %7.1f TFLOP/s chip (%.3f ms) %s %s\n", extras, M, N,
+             names[pat], traffic == 0 ? "none" : (traffic == 1 ? "st.shared" : "ld.shared"), traffic ? tw : 0, tbytes, per,
              (double)M * N * 16 / per / 2, tflops, ms, cudaGetErrorString(e), cudaGetErrorString(e2));
     }
   }
