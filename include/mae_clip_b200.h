@@ -178,6 +178,31 @@ int mc_clip_bwd(const float* I_all, const float* T_all, const void* planes_all, 
                 float* dI_loc, float* dT_loc, const uint8_t* tile_flags_loc, void* ws, size_t ws_bytes,
                 void* stream);
 
+/* Stored-weights form of the gradient (tcgen05 engines).  mc_clip_bwd keeps every gradient term of the owned rows
+ * local by recomputing the transposed strip of logits (8 GEMM units per tile pair).  The stored form computes S once:
+ *   mc_clip_bwd_rows  S = T_i I_j^T over the owned strip -> dT_loc (final), the fp16 weight strip W (b x B:
+ *                     w_ij = 2B dS_ij x a power-of-two scale) and dIz_loc, the un-scaled soft-target (dZ) part of dI
+ *                     of the owned rows;
+ *   mc_clip_bwd_cols  dI_j = scale (dIz_j + sum_i w_ij T_i) for the rows j0 .. j1 of the GLOBAL batch from a stored
+ *                     strip (w_rows rows starting at global row w_row_offset) - W is read transposed by the tensor
+ *                     cores (MN-major operand), nothing is transposed in memory.  dIz NULL = W part only.
+ * 5 GEMM units per tile pair instead of 8, at the price of b x B fp16 of HBM and, under row sharding, a reduce of the
+ * ranks' (B x D) partial dI (dist.PeerStep does it over peer memory).  A call that owns every row (b == B) takes this
+ * form inside mc_clip_bwd already (its workspace size includes the buffers); MAE_CLIP_BWD_FORM=ownrows switches it off.
+ * Sizes: W = mc_clip_stored_weights_bytes(b, B); mc_clip_bwd_rows needs the workspace of mc_clip_loss_workspace_bytes
+ * for a strip (b < B) and W 256-byte aligned; mc_clip_bwd_cols needs mc_clip_bwd_cols_workspace_bytes(j1 - j0, D). */
+size_t mc_clip_stored_weights_bytes(int b, int B);
+size_t mc_clip_bwd_cols_workspace_bytes(int n_cols, int D);
+int mc_clip_bwd_rows(const void* planes_all, int b, int B, int D, int row_offset, float tau, int mode,
+                     const float* row_lse_s_all, const float* col_lse_s_all, const float* row_lse_z_all,
+                     const float* row_g_all, const float* col_sum_p_all, const float* grad_loss, float* dT_loc,
+                     float* dIz_loc, void* W_loc, const uint8_t* tile_flags_loc, void* ws, size_t ws_bytes,
+                     void* stream);
+int mc_clip_bwd_cols(const void* planes_all, int B, int D, float tau, int mode, const float* row_lse_s_all,
+                     const float* col_lse_s_all, const float* row_lse_z_all, const float* col_sum_p_all,
+                     const float* grad_loss, const void* W, int w_rows, int w_row_offset, int j0, int j1,
+                     const float* dIz, float* dI_out, void* ws, size_t ws_bytes, void* stream);
+
 /* Single-GPU convenience: prepare + three phases, forward and backward in one call
  * (loss_out: device scalar; dI/dT may both be NULL for forward only). */
 size_t mc_clip_loss_fused_workspace_bytes(int B, int D, int mode);
@@ -224,6 +249,9 @@ int mc_peer_barrier(void* const* flag_ptrs_host, int rank, int world, unsigned i
                     double timeout_s, void* stream);
 int mc_peer_publish(const void* src, int k, int n, int64_t src_stride, void* const* dst_ptrs_host,
                     int64_t dst_stride, int64_t dst_offset, int world, void* stream);
+/* out[i] = sum over ranks q of src_ptrs_host[q][i], i < n_floats (a multiple of 4; 16-byte aligned pointers, usually
+ * peer-mapped): the reduce-scatter step of the stored-weights gradient, each rank pulling its own rows. */
+int mc_peer_reduce(void* const* src_ptrs_host, int world, size_t n_floats, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------
  * L1-L2  ProjectionHead                                    modules.py:55-76

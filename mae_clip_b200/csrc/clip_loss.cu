@@ -56,11 +56,13 @@ static FusedLayout fused_layout(int B, int D, int mode) {
   l.total = l.off_phase + l.phase_bytes;
   l.off_w = l.off_diz = l.off_cols = l.cols_bytes = 0;
   if (mode != MC_GEMM_SIMT_FP32 && tc::stored_form_enabled(B, B, D)) {
-    l.off_w = l.total;
-    l.off_diz = l.off_w + tc::stored_weights_bytes(B, B);
-    l.off_cols = l.off_diz + round_up(round_up((size_t)B, 128) * D * sizeof(float), 256);
-    l.cols_bytes = tc::bwd_cols_workspace_bytes(B, B, D);
-    l.total = l.off_cols + l.cols_bytes;
+    // tc::workspace_bytes(B, B, ...) already holds the stored-weights buffers behind the sweeps' partials
+    tc::StoredLayout sl = tc::stored_layout(B, D, mode);
+    l.off_w = l.off_phase + sl.off_w;
+    l.off_diz = l.off_phase + sl.off_diz;
+    l.off_cols = l.off_phase + sl.off_cols;
+    l.cols_bytes = sl.cols_bytes;
+    l.phase_bytes = sl.off_w;     // what a row strip's sweep may use
   }
   return l;
 }
@@ -210,6 +212,51 @@ int mc_clip_bwd(const float* I_all, const float* T_all, const void* planes_all, 
   if (mode == MC_GEMM_SIMT_FP32) return simt::bwd(p, s, grad_loss, dI_loc, dT_loc, ws, ws_bytes, st);
   p.tile_flags = tile_flags;
   return tc::bwd(p, mode, s, grad_loss, dI_loc, dT_loc, ws, ws_bytes, st);
+}
+
+size_t mc_clip_stored_weights_bytes(int b, int B) {
+  if (b <= 0 || B <= 0) return 0;
+  return tc::stored_weights_bytes(b, B);
+}
+
+size_t mc_clip_bwd_cols_workspace_bytes(int n_cols, int D) {
+  if (n_cols <= 0 || D <= 0) return 0;
+  return tc::bwd_cols_workspace_bytes(0, n_cols, D);
+}
+
+int mc_clip_bwd_rows(const void* planes_all, int b, int B, int D, int row_offset, float tau, int mode,
+                     const float* r_all, const float* c_all, const float* rz_all, const float* g_all, const float* q_all,
+                     const float* grad_loss, float* dT_loc, float* dIz_loc, void* W_loc, const uint8_t* tile_flags,
+                     void* ws, size_t ws_bytes, void* stream) {
+  MC_ARCH_GUARD();
+  int rc = check_problem("clip_bwd_rows", nullptr, nullptr, b, B, D, row_offset, tau, mode);
+  if (rc) return rc;
+  MC_REQUIRE(eff_mode(mode, D) != MC_GEMM_SIMT_FP32, MC_ERR_UNSUPPORTED,
+             "clip_bwd_rows: the stored-weights form belongs to the tcgen05 engines (mode %d, D %d)", mode, D);
+  MC_REQUIRE(planes_all && r_all && c_all && rz_all && g_all && q_all && dT_loc && dIz_loc && W_loc && ws, MC_ERR_BAD_ARG,
+             "clip_bwd_rows: null pointer");
+  ClipProblem p{nullptr, nullptr, planes_all, b, B, D, row_offset, tau};
+  p.tile_flags = tile_flags;
+  ClipStatsAll s{r_all, c_all, rz_all, g_all, q_all};
+  return tc::bwd_rows(p, mode, s, grad_loss, dT_loc, dIz_loc, W_loc, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int mc_clip_bwd_cols(const void* planes_all, int B, int D, float tau, int mode, const float* r_all, const float* c_all,
+                     const float* rz_all, const float* q_all, const float* grad_loss, const void* W, int w_rows,
+                     int w_row_offset, int j0, int j1, const float* dIz, float* dI_out, void* ws, size_t ws_bytes,
+                     void* stream) {
+  MC_ARCH_GUARD();
+  int rc = check_problem("clip_bwd_cols", nullptr, nullptr, B, B, D, 0, tau, mode);
+  if (rc) return rc;
+  MC_REQUIRE(eff_mode(mode, D) != MC_GEMM_SIMT_FP32, MC_ERR_UNSUPPORTED,
+             "clip_bwd_cols: the stored-weights form belongs to the tcgen05 engines (mode %d, D %d)", mode, D);
+  MC_REQUIRE(planes_all && r_all && c_all && rz_all && q_all && W && dI_out && ws, MC_ERR_BAD_ARG, "clip_bwd_cols: null pointer");
+  MC_REQUIRE(w_rows > 0 && w_row_offset >= 0 && w_row_offset + w_rows <= B, MC_ERR_BAD_ARG,
+             "clip_bwd_cols: stored strip rows %d at %d out of range", w_rows, w_row_offset);
+  ClipProblem p{nullptr, nullptr, planes_all, B, B, D, 0, tau};
+  ClipStatsAll s{r_all, c_all, rz_all, nullptr, q_all};
+  return tc::bwd_cols(p, mode, s, grad_loss, W, w_rows, w_row_offset, j0, j1, dIz, dI_out, ws, ws_bytes,
+                      static_cast<cudaStream_t>(stream));
 }
 
 size_t mc_clip_loss_fused_workspace_bytes(int B, int D, int mode) {

@@ -36,7 +36,10 @@ int bwd(const ClipProblem& p, const ClipStatsAll& s, const float* grad_loss, flo
 
 namespace tc {
 bool supported(int D);  // embedding widths the tcgen05 engine covers (others run on the fp32 SIMT engine)
-size_t workspace_bytes(int b, int B, int D, int mode);
+size_t workspace_bytes(int b, int B, int D, int mode);       // incl. the stored-weights buffers when b == B
+size_t core_workspace_bytes(int b, int B, int D, int mode);  // the sweeps' partials only
+struct StoredLayout { size_t off_w, off_diz, off_cols, cols_bytes, total; };
+StoredLayout stored_layout(int B, int D, int mode);
 size_t planes_bytes(int B, int D, int mode);
 int prepare(const float* I_loc, const float* T_loc, int b, int B, int D, int row_offset, int mode,
             void* planes_all, cudaStream_t st);

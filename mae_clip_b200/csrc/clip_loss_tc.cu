@@ -35,6 +35,7 @@ namespace tc {
 
 using namespace ptx;
 
+
 constexpr int kTileN = 128;             // columns j per pair tile
 constexpr int kRowsCta = 64;            // samples per CTA
 constexpr int kChunkBytes = 64 * 128;   // 64 rows x 64 fp16
@@ -2000,7 +2001,7 @@ static size_t colpart_bytes(int b, int B, bool forced = false) {
 }
 // workspace of the sharded column-partials form (stats with c_part_all): the phase partials + the (b / 32) x B partials
 size_t stats_colpart_workspace_bytes(int b, int B, int D, int mode) {
-  return workspace_bytes(b, B, D, mode) - colpart_bytes(b, B) + colpart_bytes(b, B, true);
+  return core_workspace_bytes(b, B, D, mode) - colpart_bytes(b, B) + colpart_bytes(b, B, true);
 }
 
 // rowgrad_kernel: row blocks of 256, tiles of 256 x 128; same cost model as choose_split (a job pays ~3 tiles of overhead)
@@ -2028,7 +2029,7 @@ static size_t rowgrad_part_bytes(int b, int B, int D) {
   return round_up((size_t)s.nsplit * s.bpad * D * sizeof(float), 256);
 }
 
-size_t workspace_bytes(int b, int B, int D, int /*mode*/) {
+size_t core_workspace_bytes(int b, int B, int D, int /*mode*/) {
   Split s = choose_split(b, B, kOvhStats), sr = choose_split(b, B, kOvhRowLoss), sb = choose_split(b, B, kOvhBwd);
   (void)sr;
   size_t stats = (size_t)kMaxSplit * 4 * s.bpad * sizeof(float2);   // any split count (the chunked launches align theirs)
@@ -2040,10 +2041,10 @@ size_t workspace_bytes(int b, int B, int D, int /*mode*/) {
   return round_up(stats > bwdp ? stats : bwdp, 256) + 256 + colpart_bytes(b, B);  // + the weight-scale slot + column partials
 }
 static float* colpart_slot(void* ws, int b, int B, int D) {
-  return reinterpret_cast<float*>(static_cast<char*>(ws) + workspace_bytes(b, B, D, 0) - colpart_bytes(b, B));
+  return reinterpret_cast<float*>(static_cast<char*>(ws) + core_workspace_bytes(b, B, D, 0) - colpart_bytes(b, B));
 }
 static float* wscale_slot(void* ws, int b, int B, int D) {
-  return reinterpret_cast<float*>(static_cast<char*>(ws) + workspace_bytes(b, B, D, 0) - colpart_bytes(b, B) - 256);
+  return reinterpret_cast<float*>(static_cast<char*>(ws) + core_workspace_bytes(b, B, D, 0) - colpart_bytes(b, B) - 256);
 }
 
 
@@ -2429,7 +2430,7 @@ int flags_finalize(const uint8_t* flags_all, int B, int b, int row_offset, uint8
 // chunks > 1 (b == B only): the probe sweep is launched once per arrived row chunk (stats_chunk), see PairParams.
 static float* stats_colpart_ptr(const ClipProblem& p, int mode, void* ws, float* c_part_all) {
   if (c_part_all)
-    return reinterpret_cast<float*>(static_cast<char*>(ws) + workspace_bytes(p.b, p.B, p.D, mode) - colpart_bytes(p.b, p.B));
+    return reinterpret_cast<float*>(static_cast<char*>(ws) + core_workspace_bytes(p.b, p.B, p.D, mode) - colpart_bytes(p.b, p.B));
   return use_colpart(p.b, p.B) ? colpart_slot(ws, p.b, p.B, p.D) : nullptr;
 }
 int stats_begin(const ClipProblem& p, cudaStream_t st) {
@@ -2466,7 +2467,7 @@ int stats_end(const ClipProblem& p, int mode, int chunks, float* r_loc, float* c
 }
 int stats(const ClipProblem& p, int mode, float* r_loc, float* c_loc, float* rz_loc, float* ps_loc, void* ws,
           size_t ws_bytes, cudaStream_t st, float* c_part_all) {
-  const size_t need = c_part_all ? stats_colpart_workspace_bytes(p.b, p.B, p.D, mode) : workspace_bytes(p.b, p.B, p.D, mode);
+  const size_t need = c_part_all ? stats_colpart_workspace_bytes(p.b, p.B, p.D, mode) : core_workspace_bytes(p.b, p.B, p.D, mode);
   MC_REQUIRE(ws_bytes >= need, MC_ERR_WORKSPACE, "clip_stats(tc): workspace %zu < %zu", ws_bytes, need);
   int rc;
   if ((rc = stats_begin(p, st))) return rc;
@@ -2533,7 +2534,7 @@ int verify_scale(unsigned int* words, cudaStream_t st) {
 
 int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* ps_loc, float* g_loc, float* q_loc,
             float* loss_part, void* ws, size_t ws_bytes, cudaStream_t st) {
-  MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_rowloss(tc): workspace too small");
+  MC_REQUIRE(ws_bytes >= core_workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_rowloss(tc): workspace too small");
   int rc = launch_phase<kRowLoss>(mode, p, s, ps_loc, static_cast<float*>(ws), nullptr, st);
   if (rc) return rc;
   Split sp = choose_split(p.b, p.B, kOvhRowLoss);
@@ -2549,10 +2550,19 @@ int bwd(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad
         size_t ws_bytes, cudaStream_t st) {
   MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_bwd(tc): workspace too small");
   MC_REQUIRE(aligned(dI, 16) && aligned(dT, 16), MC_ERR_ALIGN, "clip_bwd(tc): gradients must be 16-byte aligned");
+  MC_REQUIRE(p.planes_all != nullptr, MC_ERR_BAD_ARG, "clip_bwd(tc): planes buffer missing");
+  if (p.b == p.B && p.row_offset == 0 && stored_form_enabled(p.b, p.B, p.D)) {
+    // a call that owns every row: the stored-weights form (row half + column half) instead of the own-rows sweep
+    StoredLayout sl = stored_layout(p.B, p.D, mode);
+    char* base = static_cast<char*>(ws);
+    int rc = bwd_rows(p, mode, s, grad_loss, dT, reinterpret_cast<float*>(base + sl.off_diz), base + sl.off_w, ws, sl.off_w, st);
+    if (rc) return rc;
+    return bwd_cols(p, mode, s, grad_loss, base + sl.off_w, p.B, 0, 0, p.B, reinterpret_cast<const float*>(base + sl.off_diz), dI,
+                    base + sl.off_cols, sl.cols_bytes, st);
+  }
   PlanesLayout l = planes_layout(p.B, p.D);
   const char* pbase = static_cast<const char*>(p.planes_all);
   float* wsc = wscale_slot(ws, p.b, p.B, p.D);
-  MC_REQUIRE(p.planes_all != nullptr, MC_ERR_BAD_ARG, "clip_bwd(tc): planes buffer missing");
   wscale_kernel<<<1, 1024, 0, st>>>(s.r, s.c, s.rz, s.q, p.B, reinterpret_cast<const float*>(pbase + l.off_hdr) + 1,
                                    reinterpret_cast<const float*>(pbase + l.off_norm_i),
                                    reinterpret_cast<const float*>(pbase + l.off_norm_t), 1.f / p.tau, p.tau, wsc);
@@ -2569,7 +2579,6 @@ int bwd(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad
   MC_LAUNCH_CHECK();
   return MC_OK;
 }
-
 
 // ---- stored-weights gradient (see kBwdW / colgrad_kernel) -------------------------------------------------
 static int launch_wscale(const ClipProblem& p, const ClipStatsAll& s, float* wsc, cudaStream_t st) {
@@ -2602,6 +2611,19 @@ static ColSplit choose_col_split(int w_rows, int n_cols) {
 size_t stored_weights_bytes(int b, int B) { return round_up(round_up((size_t)b, 256) * round_up((size_t)B, 128) * sizeof(__half), 256); }
 size_t bwd_cols_workspace_bytes(int /*w_rows*/, int n_cols, int D) {
   return round_up((size_t)kCgMaxSplit * ((size_t)(n_cols + 255) / 256 * 256) * D * sizeof(float), 256) + 256;
+}
+StoredLayout stored_layout(int B, int D, int mode) {
+  StoredLayout l;
+  l.off_w = round_up(core_workspace_bytes(B, B, D, mode), 1024);
+  l.off_diz = l.off_w + stored_weights_bytes(B, B);
+  l.off_cols = l.off_diz + round_up(round_up((size_t)B, 128) * D * sizeof(float), 256);
+  l.cols_bytes = bwd_cols_workspace_bytes(B, B, D);
+  l.total = l.off_cols + l.cols_bytes;
+  return l;
+}
+size_t workspace_bytes(int b, int B, int D, int mode) {
+  if (b == B && stored_form_enabled(b, B, D)) return stored_layout(B, D, mode).total;
+  return core_workspace_bytes(b, B, D, mode);
 }
 bool stored_form_enabled(int b, int B, int D) {
   static const bool off = getenv("MAE_CLIP_BWD_FORM") != nullptr && strcmp(getenv("MAE_CLIP_BWD_FORM"), "ownrows") == 0;
@@ -2660,7 +2682,7 @@ static int launch_rowgrad(const ClipProblem& p, int mode, const ClipStatsAll& s,
 // strip's rows) and the strip's rows of W (pointer to the strip's first row, row pitch Bp).
 int bwd_rows(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, float* dT_loc, float* dIz_loc,
              void* W_rows, void* ws, size_t ws_bytes, cudaStream_t st) {
-  MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_bwd_rows: workspace too small");
+  MC_REQUIRE(ws_bytes >= core_workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_bwd_rows: workspace too small");
   MC_REQUIRE(aligned(dT_loc, 16) && aligned(dIz_loc, 16) && aligned(W_rows, 256), MC_ERR_ALIGN, "clip_bwd_rows: alignment");
   MC_REQUIRE(p.planes_all != nullptr, MC_ERR_BAD_ARG, "clip_bwd_rows: planes buffer missing");
   float* wsc = wscale_slot(ws, p.b, p.B, p.D);

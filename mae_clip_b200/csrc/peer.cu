@@ -85,6 +85,23 @@ __global__ void __launch_bounds__(256) peer_publish_kernel(const uint32_t* __res
   }
 }
 
+// out[i] = sum_q src.p[q][i]: the reduce-scatter step of the stored-weights gradient (every rank pulls ITS rows of the
+// peers' partial dI straight out of their memory: 16-byte loads, all `world` of them in flight before the first add;
+// a fixed summation order, so every run gives the same bits)
+__global__ void __launch_bounds__(256) peer_reduce_kernel(PeerWords src, int world, size_t n4, float4* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v[kMaxPeers];
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q)
+      if (q < world) v[q] = reinterpret_cast<const float4*>(src.p[q])[i];
+    float4 a = v[0];
+#pragma unroll
+    for (int q = 1; q < kMaxPeers; ++q)
+      if (q < world) { a.x += v[q].x; a.y += v[q].y; a.z += v[q].z; a.w += v[q].w; }
+    out[i] = a;
+  }
+}
+
 static int pack(PeerWords& w, void* const* host_ptrs, int world, const char* who) {
   MC_REQUIRE(host_ptrs != nullptr && world >= 1 && world <= kMaxPeers, MC_ERR_BAD_ARG,
              "%s: world %d outside [1, %d] or null pointer table", who, world, kMaxPeers);
@@ -174,6 +191,21 @@ int mc_peer_publish(const void* src, int k, int n, int64_t src_stride, void* con
   dim3 grid(bx, world);
   peer_publish_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint32_t*>(src), k, n,
                                                                           src_stride, w, dst_stride, dst_offset, world);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
+int mc_peer_reduce(void* const* src_ptrs_host, int world, size_t n_floats, float* out, void* stream) {
+  MC_ARCH_GUARD();
+  MC_REQUIRE(out && aligned(out, 16) && n_floats > 0 && n_floats % 4 == 0, MC_ERR_BAD_ARG, "peer_reduce: bad argument");
+  PeerWords w;
+  int rc = pack(w, src_ptrs_host, world, "peer_reduce");
+  if (rc) return rc;
+  for (int q = 0; q < world; ++q) MC_REQUIRE(aligned(src_ptrs_host[q], 16), MC_ERR_ALIGN, "peer_reduce: source %d not 16-byte aligned", q);
+  const size_t n4 = n_floats / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+  peer_reduce_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, world, n4, reinterpret_cast<float4*>(out));
   MC_LAUNCH_CHECK();
   return MC_OK;
 }

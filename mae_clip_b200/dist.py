@@ -221,6 +221,13 @@ class PeerStep:
         # column LSE of S from column partials (no transposed strip in the statistics sweep; the ranks exchange one
         # B-vector each and merge) - MAE_CLIP_COLPART=0 keeps the transposed strip
         self.colpart = os.environ.get("MAE_CLIP_COLPART", "1") != "0"
+        # gradient form: "stored" computes S once per rank (row half -> dT and the fp16 weight strip, column half -> this
+        # rank's contribution to EVERY row of dI) and reduces the ranks' partial dI over peer memory; "ownrows"
+        # (MAE_CLIP_PEER_BWD=ownrows) recomputes the transposed strip instead and needs no exchange in backward
+        self.bwd_form = os.environ.get("MAE_CLIP_PEER_BWD", "stored")
+        if self.bwd_form not in ("stored", "ownrows"):
+            raise ValueError(f"unknown MAE_CLIP_PEER_BWD {self.bwd_form!r}")
+        self._stored = None   # (W strip, zero-padded dIz, column-half workspace): allocated on the first backward
 
     def forward(self, I_loc, T_loc, tau, events=None):
         ex, mode, L = self.ex, self.mode, lib()
@@ -312,9 +319,30 @@ class PeerStep:
         gl = None if grad_loss is None else grad_loss.reshape(1).to(torch.float32).contiguous()
         with torch.cuda.device(dev):
             ws = workspace(L.mc_clip_loss_workspace_bytes(b, B, D, mode), dev)
-            check(L.mc_clip_bwd(None, None, ptr(planes), b, B, D, ex.rank * b, float(tau), mode, ptr(vecs[0]),
-                                ptr(vecs[1]), ptr(vecs[2]), ptr(vecs[3]), ptr(vecs[4]), ptr(gl), ptr(dI), ptr(dT),
-                                ptr(flags), ptr(ws), ws.numel(), cur_stream()), "mc_clip_bwd")
+            if self.bwd_form == "stored" and ex.world > 1:
+                st = cur_stream()
+                if self._stored is None:
+                    Bp = (B + 127) // 128 * 128
+                    self._stored = (torch.empty(L.mc_clip_stored_weights_bytes(b, B), device=dev, dtype=torch.uint8),
+                                    torch.zeros(Bp, D, device=dev, dtype=torch.float32),   # only OUR rows are ever written
+                                    torch.empty(L.mc_clip_bwd_cols_workspace_bytes(B, D), device=dev, dtype=torch.uint8))
+                W, diz, wsc = self._stored
+                row0 = ex.rank * b
+                check(L.mc_clip_bwd_rows(ptr(planes), b, B, D, row0, float(tau), mode, ptr(vecs[0]), ptr(vecs[1]),
+                                         ptr(vecs[2]), ptr(vecs[3]), ptr(vecs[4]), ptr(gl), ptr(dT), ptr(diz[row0:]), ptr(W),
+                                         ptr(flags), ptr(ws), ws.numel(), st), "mc_clip_bwd_rows")
+                # our contribution to every row of dI goes where the peers can read it: the (B, D) image of I in the
+                # exchange region is dead once the planes are staged
+                check(L.mc_clip_bwd_cols(ptr(planes), B, D, float(tau), mode, ptr(vecs[0]), ptr(vecs[1]), ptr(vecs[2]),
+                                         ptr(vecs[4]), ptr(gl), ptr(W), b, row0, 0, B, ptr(diz), ex.local(ex.off_emb_i),
+                                         ptr(wsc), wsc.numel(), st), "mc_clip_bwd_cols")
+                ex.barrier()
+                ex.reduce_rows(ex.off_emb_i + row0 * D * 4, b * D, dI)
+                ex.barrier()   # nobody pushes the next step's shards into an image a peer is still reading
+            else:
+                check(L.mc_clip_bwd(None, None, ptr(planes), b, B, D, ex.rank * b, float(tau), mode, ptr(vecs[0]),
+                                    ptr(vecs[1]), ptr(vecs[2]), ptr(vecs[3]), ptr(vecs[4]), ptr(gl), ptr(dI), ptr(dT),
+                                    ptr(flags), ptr(ws), ws.numel(), cur_stream()), "mc_clip_bwd")
             if events is not None:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()

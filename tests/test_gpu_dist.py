@@ -105,7 +105,7 @@ def test_peer_step_world1_matches_fused_path(exchange_mode):
     os.environ["MASTER_PORT"] = str(_free_port())
     dist.init_process_group("gloo", rank=0, world_size=1)
     try:
-        b = 384
+        b = 512   # 4 x 4 tile flags: a whole number of 32-bit words, so the peer path exchanges (and uses) them like the fused call
         I = loss_ref.make_embeddings(b, 256, seed=11, scale=0.2).cuda()
         T = loss_ref.make_embeddings(b, 256, seed=12, scale=0.2).cuda()
         ex = peer.PeerExchange(b, 256)

@@ -470,7 +470,7 @@ def test_tile_flags_are_a_superset_of_the_exact_relevance(scale, tau):
 
 
 # ------------------------------------------------------------------ parity AT the benchmarked size (BASELINE config 4)
-def _phases_sharded(I, T, tau, mode, shard_rows, colpart=False):
+def _phases_sharded(I, T, tau, mode, shard_rows, colpart=False, stored=False, use_flags=True):
     """The row-sharded form of the step (what the ranks of a multi-GPU job run, mae_clip_b200/dist.py) back to back on
     one GPU: every shard of `shard_rows` rows runs its own statistics / row-loss / gradient sweeps with a row offset,
     the length-B vectors and the tile-flag bitmap are assembled in between exactly as the exchange steps do."""
@@ -516,10 +516,29 @@ def _phases_sharded(I, T, tau, mode, shard_rows, colpart=False):
         check(lib.mc_clip_rowloss(ptr(I), ptr(T), ptr(planes), b, B, D, o, tau, md, ptr(st4[0]), ptr(st4[1]), ptr(st4[2]),
                                   ptr(st4[3, o:]), ptr(gq[0, o:]), ptr(gq[1, o:]), ptr(parts[k:]), ptr(fin[k]), ptr(ws),
                                   ws.numel(), s))
-    for k in range(W):
-        o = k * b
-        check(lib.mc_clip_bwd(ptr(I), ptr(T), ptr(planes), b, B, D, o, tau, md, ptr(st4[0]), ptr(st4[1]), ptr(st4[2]),
-                              ptr(gq[0]), ptr(gq[1]), None, ptr(dI[o:]), ptr(dT[o:]), ptr(fin[k]), ptr(ws), ws.numel(), s))
+    if stored:
+        # the stored-weights form as the ranks run it (dist.PeerStep): per shard the row half (dT, the fp16 weight strip,
+        # the soft-target part of the shard's dI) and the column half over EVERY row of dI; the shards' partial dI are
+        # then summed (the peer reduce)
+        Wbuf = torch.empty(lib.mc_clip_stored_weights_bytes(b, B), dtype=torch.uint8, device=dev)
+        wsc = torch.empty(lib.mc_clip_bwd_cols_workspace_bytes(B, D), dtype=torch.uint8, device=dev)
+        Bp = (B + 127) // 128 * 128
+        dI.zero_()
+        for k in range(W):
+            o = k * b
+            diz = torch.zeros(Bp, D, device=dev)
+            part = torch.empty(B, D, device=dev)
+            check(lib.mc_clip_bwd_rows(ptr(planes), b, B, D, o, tau, md, ptr(st4[0]), ptr(st4[1]), ptr(st4[2]), ptr(gq[0]),
+                                       ptr(gq[1]), None, ptr(dT[o:]), ptr(diz[o:]), ptr(Wbuf), ptr(fin[k]) if use_flags else None,
+                                       ptr(ws), ws.numel(), s), "mc_clip_bwd_rows")
+            check(lib.mc_clip_bwd_cols(ptr(planes), B, D, tau, md, ptr(st4[0]), ptr(st4[1]), ptr(st4[2]), ptr(gq[1]), None,
+                                       ptr(Wbuf), b, o, 0, B, ptr(diz), ptr(part), ptr(wsc), wsc.numel(), s), "mc_clip_bwd_cols")
+            dI += part
+    else:
+        for k in range(W):
+            o = k * b
+            check(lib.mc_clip_bwd(ptr(I), ptr(T), ptr(planes), b, B, D, o, tau, md, ptr(st4[0]), ptr(st4[1]), ptr(st4[2]),
+                                  ptr(gq[0]), ptr(gq[1]), None, ptr(dI[o:]), ptr(dT[o:]), ptr(fin[k]), ptr(ws), ws.numel(), s))
     torch.cuda.synchronize()
     return parts.sum().item(), dI, dT, fin.reshape(B // 128, -1)
 
@@ -542,7 +561,8 @@ def _c4_batch_and_oracle(B, scale):
     return _C4_CACHE[key]
 
 
-@pytest.mark.parametrize("variant", ["fused_flags", "dense", "shards4096_flags", "shards4096_colpart", "host_entry"])
+@pytest.mark.parametrize("variant", ["fused_flags", "dense", "shards4096_flags", "shards4096_colpart", "shards4096_stored",
+                                     "shards4096_stored_noflags", "host_entry"])
 @pytest.mark.parametrize("B", [8192, 32768])
 def test_loss_c4_size_vs_fp64_blockwise(B, variant):
     """The benchmarked path - B = 32768 (and 8192), D = 256, LayerNorm-scale rows (tile-flag density 1/256), probe +
@@ -561,8 +581,9 @@ def test_loss_c4_size_vs_fp64_blockwise(B, variant):
         loss = l.item()
     elif variant == "dense":
         loss, dI, dT, _ = _phases(I, T, 1.0, "tc_f16x3", sparse=False)
-    elif variant in ("shards4096_flags", "shards4096_colpart"):
-        loss, dI, dT, flags = _phases_sharded(I, T, 1.0, "tc_f16x3", 4096, colpart=variant.endswith("colpart"))
+    elif variant.startswith("shards4096"):
+        loss, dI, dT, flags = _phases_sharded(I, T, 1.0, "tc_f16x3", 4096, colpart="flags" not in variant,
+                                              stored="stored" in variant, use_flags=not variant.endswith("noflags"))
         assert flags.float().mean().item() < 0.02      # the sparse path is what ran (diagonal tiles + a few neighbours)
     else:
         lib = _lib.lib()
