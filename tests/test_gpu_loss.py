@@ -413,7 +413,9 @@ def test_tile_flags_skip_only_what_is_negligible(mode):
     ls, dIs, dTs, flags = _phases(I, T, 1.0, mode, sparse=True)
     assert torch.equal(flags, torch.eye(flags.shape[0], dtype=torch.uint8))       # diagonal tiles only
     assert abs(ls - ld) <= 1e-6 * abs(ld)
-    assert rel_err(dIs, dId) < 1e-5 and rel_err(dTs, dTd) < 1e-5
+    # flagged and dense gradients come from different kernels (split: the softmax and soft-target parts of the weights
+    # are rounded to fp16 separately; dense: together): a few 1e-5 of fp16 weight rounding, both ~2.5e-4 from fp64
+    assert rel_err(dIs, dId) < 5e-5 and rel_err(dTs, dTd) < 5e-5
     ref_loss, ref_dI, ref_dT, _ = loss_ref.clip_loss_closed_form(I.cpu().numpy(), T.cpu().numpy(), 1.0)
     lt, gt = _tols(mode)
     assert abs(ls - ref_loss) <= lt * abs(ref_loss)
