@@ -576,7 +576,22 @@ def run_b200(args):
         if flags_t is None and hasattr(ph, "step_impl"):
             flags_t = getattr(ph, "last_flags", None)
         density = float(flags_t.float().mean().item()) if flags_t is not None else 1.0
-        exec_units = ((2 * passes + 2) + density * (2 * passes + 2)) if mode != "simt_fp32" else 8
+        # which form of the gradient ran: a call that owns every row (one GPU) and the peer transport's default take
+        # the STORED-WEIGHTS form - S once (passes) + dT GEMM in the row half, dI from the stored fp16 weights in the
+        # column half (1 unit), and on the flagged tiles only the soft-target part: the split form recomputes S, S^T, Z
+        # (K = 2D) there and runs four small GEMMs, the single sweep (no flags / MAE_CLIP_BWD_SPLIT=0) adds S^T, Z and the
+        # two dZ GEMMs to its own S; the OWN-ROWS form recomputes the transposed strip everywhere instead of storing
+        form = "ownrows"
+        if mode != "simt_fp32" and os.environ.get("MAE_CLIP_BWD_FORM") != "ownrows":
+            if world == 1 or (transport == "peer" and getattr(ph.step_impl, "bwd_form", "") == "stored"):
+                form = "stored"
+        split = form == "stored" and flags_t is not None and mode == "tc_f16x3" and os.environ.get("MAE_CLIP_BWD_SPLIT") != "0"
+        if mode == "simt_fp32":
+            exec_units = 8
+        elif form == "stored":
+            exec_units = (passes + 1) + 1 + density * ((4 * passes + 4) if split else (3 * passes + 2))
+        else:
+            exec_units = (2 * passes + 2) + density * (2 * passes + 2)
         executed = exec_units * 2.0 * B * B * D_EMB / world / (bwd_ms * 1e-3) / 1e12
         ncu = {}
         try:
@@ -604,7 +619,12 @@ def run_b200(args):
                           "rowloss": phase_ms[2] / args.steps, "bwd": bwd_ms,
                           "timed": "eager steps with events between the phases" + (
                               " (the headline ms_per_step is the graph replay)" if graph is not None else "")},
-            "roofline": {"bound": "tensor", "kernel": "gradient sweep (mc_clip_bwd)", "achieved": achieved,
+            "roofline": {"bound": "tensor",
+                         "kernel": "gradient phase (mc_clip_bwd): " + {
+                             "stored": ("rowgrad_kernel + flagged-tile sweep + colgrad_kernel" if split else
+                                        "row sweep (stores the fp16 weights) + colgrad_kernel"),
+                             "ownrows": "own-rows sweep (transposed strip recomputed)"}[form],
+                         "gradient_form": form, "achieved": achieved,
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": "%s, bf16 %s (fp16 runs at the same tensor rate); the SM clock %s during the run" % (
                              peaks["source"], peak_kind, "sat at its maximum" if at_max_clock else "was below 95% of its maximum"),
@@ -616,8 +636,13 @@ def run_b200(args):
                          "traffic_source": ncu.get("source") if traffic_ok else None,
                          "executed_tflops": executed, "executed_frac": executed / peak,
                          "executed_gemm_units": exec_units, "algorithmic_gemm_units": 4,
-                         "frac_ceiling_note": "the own-rows form executes %.2f GEMM units per 4 algorithmic ones: frac <= %.2f "
-                                              "at 100%% of the tensor peak" % (exec_units, 4.0 / exec_units),
+                         "frac_ceiling_note": "the %s form executes %.2f GEMM units per 4 algorithmic ones: frac <= %.2f "
+                                              "at 100%% of the tensor peak" % (form, exec_units, 4.0 / exec_units),
+                         # the other tensor-bound kernel of the step: the statistics sweep (S in 3 passes + the hi-plane
+                         # probe of Z, K = 2D; algorithmic forward work 6 B^2 D: S, I I^T, T T^T)
+                         "stats_sweep": {"ms": phase_ms[1] / args.steps,
+                                         "achieved": 6.0 * B * B * D_EMB / world / (phase_ms[1] / args.steps * 1e-3) / 1e12,
+                                         "frac": 6.0 * B * B * D_EMB / world / (phase_ms[1] / args.steps * 1e-3) / 1e12 / peak},
                          "tile_flag_density": density,
                          "algorithmic_flops_per_launch": flops_bwd,
                          "step_achieved": flops_step / (ms_per_step * 1e-3) / 1e12,
@@ -669,7 +694,11 @@ def regime(B, mode, dev, flush, I, T, sparse, peak, peaks):
     ms, bwd_ms = tot / n, phs[3] / n
     density = float(ph.flags.float().mean().item()) if ph.flags is not None else 1.0
     passes = 3 if mode == "tc_f16x3" else 1
-    units = (2 * passes + 2) * (1 + density)
+    if mode == "simt_fp32" or os.environ.get("MAE_CLIP_BWD_FORM") == "ownrows":
+        units = (2 * passes + 2) * (1 + density)
+    else:   # stored-weights form (see run_b200): split when tile flags exist, the single row sweep otherwise
+        split = sparse and mode == "tc_f16x3" and os.environ.get("MAE_CLIP_BWD_SPLIT") != "0"
+        units = (passes + 1) + 1 + density * ((4 * passes + 4) if split else (3 * passes + 2))
     ach = 8.0 * B * B * D_EMB / (bwd_ms * 1e-3) / 1e12
     return {"ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "loss": float(ph.part.item()),
             "phases_ms": {"prepare": phs[0] / n, "stats": phs[1] / n, "rowloss": phs[2] / n, "bwd": bwd_ms},

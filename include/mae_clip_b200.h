@@ -193,15 +193,22 @@ int mc_clip_bwd(const float* I_all, const float* T_all, const void* planes_all, 
  * for a strip (b < B) and W 256-byte aligned; mc_clip_bwd_cols needs mc_clip_bwd_cols_workspace_bytes(j1 - j0, D). */
 size_t mc_clip_stored_weights_bytes(int b, int B);
 size_t mc_clip_bwd_cols_workspace_bytes(int n_cols, int D);
+/* The stored form pays while the soft targets are concentrated (few flagged tiles); with many flagged tiles the
+ * own-rows sweep is cheaper.  mc_clip_bwd_gate writes the choice into a device word from the flags of ALL row blocks
+ * (1 = stored, 0 = own rows; break-even at 15% flagged tiles, MAE_CLIP_BWD_GATE overrides); given that word, the calls
+ * below enqueue the kernels of BOTH forms and the ones of the other form return at once - no host synchronisation.
+ * gate NULL = the stored form unconditionally.  A gated mc_clip_bwd_rows needs tile flags, the 3-pass engine and
+ * dI_loc_ownrows (where the own-rows form writes this strip's dI); mc_peer_reduce takes the same word. */
+int mc_clip_bwd_gate(const uint8_t* tile_flags_all, size_t n_flags, int* gate_out, void* stream);
 int mc_clip_bwd_rows(const void* planes_all, int b, int B, int D, int row_offset, float tau, int mode,
                      const float* row_lse_s_all, const float* col_lse_s_all, const float* row_lse_z_all,
                      const float* row_g_all, const float* col_sum_p_all, const float* grad_loss, float* dT_loc,
-                     float* dIz_loc, void* W_loc, const uint8_t* tile_flags_loc, void* ws, size_t ws_bytes,
-                     void* stream);
+                     float* dIz_loc, void* W_loc, const uint8_t* tile_flags_loc, const int* gate,
+                     float* dI_loc_ownrows, void* ws, size_t ws_bytes, void* stream);
 int mc_clip_bwd_cols(const void* planes_all, int B, int D, float tau, int mode, const float* row_lse_s_all,
                      const float* col_lse_s_all, const float* row_lse_z_all, const float* col_sum_p_all,
                      const float* grad_loss, const void* W, int w_rows, int w_row_offset, int j0, int j1,
-                     const float* dIz, float* dI_out, void* ws, size_t ws_bytes, void* stream);
+                     const float* dIz, float* dI_out, const int* gate, void* ws, size_t ws_bytes, void* stream);
 
 /* Single-GPU convenience: prepare + three phases, forward and backward in one call
  * (loss_out: device scalar; dI/dT may both be NULL for forward only). */
@@ -251,7 +258,8 @@ int mc_peer_publish(const void* src, int k, int n, int64_t src_stride, void* con
                     int64_t dst_stride, int64_t dst_offset, int world, void* stream);
 /* out[i] = sum over ranks q of src_ptrs_host[q][i], i < n_floats (a multiple of 4; 16-byte aligned pointers, usually
  * peer-mapped): the reduce-scatter step of the stored-weights gradient, each rank pulling its own rows. */
-int mc_peer_reduce(void* const* src_ptrs_host, int world, size_t n_floats, float* out, void* stream);
+int mc_peer_reduce(void* const* src_ptrs_host, int world, size_t n_floats, float* out, const int* gate /* NULL or a device
+                   word: the kernel returns unless it is 1 */, void* stream);
 
 /* ---------------------------------------------------------------------------
  * L1-L2  ProjectionHead                                    modules.py:55-76

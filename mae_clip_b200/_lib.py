@@ -47,7 +47,7 @@ SIGNATURES = {
     "mc_peer_free": (_i, [_p]),
     "mc_peer_barrier": (_i, [_p, _i, _i, _p, C.c_double, _p]),
     "mc_peer_publish": (_i, [_p, _i, _i, _i64, _p, _i64, _i64, _i, _p]),
-    "mc_peer_reduce": (_i, [_p, _i, _sz, _p, _p]),
+    "mc_peer_reduce": (_i, [_p, _i, _sz, _p, _p, _p]),
     "mc_clip_tile_flags_bytes": (_sz, [_i, _i, _i, _i]),
     "mc_clip_flags_finalize": (_i, [_p, _i, _i, _i, _p, _p]),
     "mc_clip_stats": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
@@ -59,8 +59,10 @@ SIGNATURES = {
                          _p]),
     "mc_clip_stored_weights_bytes": (_sz, [_i, _i]),
     "mc_clip_bwd_cols_workspace_bytes": (_sz, [_i, _i]),
-    "mc_clip_bwd_rows": (_i, [_p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "mc_clip_bwd_cols": (_i, [_p, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "mc_clip_bwd_gate": (_i, [_p, _sz, _p, _p]),
+    "mc_clip_bwd_rows": (_i, [_p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
+                              _p]),
+    "mc_clip_bwd_cols": (_i, [_p, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "mc_clip_loss_fused_workspace_bytes": (_sz, [_i, _i, _i]),
     "mc_clip_loss_fwd_bwd": (_i, [_p, _p, _i, _i, _f, _i, _p, _p, _p, _p, _sz, _p]),
     "mc_clip_loss_host_workspace_bytes": (_sz, [_i, _i, _i]),

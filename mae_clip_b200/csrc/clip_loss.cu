@@ -214,6 +214,12 @@ int mc_clip_bwd(const float* I_all, const float* T_all, const void* planes_all, 
   return tc::bwd(p, mode, s, grad_loss, dI_loc, dT_loc, ws, ws_bytes, st);
 }
 
+int mc_clip_bwd_gate(const uint8_t* tile_flags, size_t n_flags, int* gate_out, void* stream) {
+  MC_ARCH_GUARD();
+  MC_REQUIRE(tile_flags && n_flags > 0 && gate_out, MC_ERR_BAD_ARG, "clip_bwd_gate: bad argument");
+  return tc::bwd_gate(tile_flags, n_flags, gate_out, static_cast<cudaStream_t>(stream));
+}
+
 size_t mc_clip_stored_weights_bytes(int b, int B) {
   if (b <= 0 || B <= 0) return 0;
   return tc::stored_weights_bytes(b, B);
@@ -227,7 +233,7 @@ size_t mc_clip_bwd_cols_workspace_bytes(int n_cols, int D) {
 int mc_clip_bwd_rows(const void* planes_all, int b, int B, int D, int row_offset, float tau, int mode,
                      const float* r_all, const float* c_all, const float* rz_all, const float* g_all, const float* q_all,
                      const float* grad_loss, float* dT_loc, float* dIz_loc, void* W_loc, const uint8_t* tile_flags,
-                     void* ws, size_t ws_bytes, void* stream) {
+                     const int* gate, float* dI_loc_ownrows, void* ws, size_t ws_bytes, void* stream) {
   MC_ARCH_GUARD();
   int rc = check_problem("clip_bwd_rows", nullptr, nullptr, b, B, D, row_offset, tau, mode);
   if (rc) return rc;
@@ -237,14 +243,16 @@ int mc_clip_bwd_rows(const void* planes_all, int b, int B, int D, int row_offset
              "clip_bwd_rows: null pointer");
   ClipProblem p{nullptr, nullptr, planes_all, b, B, D, row_offset, tau};
   p.tile_flags = tile_flags;
+  p.gate = gate;
   ClipStatsAll s{r_all, c_all, rz_all, g_all, q_all};
-  return tc::bwd_rows(p, mode, s, grad_loss, dT_loc, dIz_loc, W_loc, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  return tc::bwd_rows(p, mode, s, grad_loss, dT_loc, dIz_loc, W_loc, ws, ws_bytes, static_cast<cudaStream_t>(stream),
+                      dI_loc_ownrows);
 }
 
 int mc_clip_bwd_cols(const void* planes_all, int B, int D, float tau, int mode, const float* r_all, const float* c_all,
                      const float* rz_all, const float* q_all, const float* grad_loss, const void* W, int w_rows,
-                     int w_row_offset, int j0, int j1, const float* dIz, float* dI_out, void* ws, size_t ws_bytes,
-                     void* stream) {
+                     int w_row_offset, int j0, int j1, const float* dIz, float* dI_out, const int* gate, void* ws,
+                     size_t ws_bytes, void* stream) {
   MC_ARCH_GUARD();
   int rc = check_problem("clip_bwd_cols", nullptr, nullptr, B, B, D, 0, tau, mode);
   if (rc) return rc;
@@ -254,6 +262,7 @@ int mc_clip_bwd_cols(const void* planes_all, int B, int D, float tau, int mode, 
   MC_REQUIRE(w_rows > 0 && w_row_offset >= 0 && w_row_offset + w_rows <= B, MC_ERR_BAD_ARG,
              "clip_bwd_cols: stored strip rows %d at %d out of range", w_rows, w_row_offset);
   ClipProblem p{nullptr, nullptr, planes_all, B, B, D, 0, tau};
+  p.gate = gate;
   ClipStatsAll s{r_all, c_all, rz_all, nullptr, q_all};
   return tc::bwd_cols(p, mode, s, grad_loss, W, w_rows, w_row_offset, j0, j1, dIz, dI_out, ws, ws_bytes,
                       static_cast<cudaStream_t>(stream));
@@ -387,7 +396,14 @@ static int fused_run(const float* I, const float* T, int B, int D, float tau, in
     if (rows_k <= 0 || mc_clip_loss_workspace_bytes(rows_k, B, D, mode) > phase_bytes) n_strips = 1;
   }
   const int n_tiles = n_blocks;  // column tiles of B = row blocks of B
-  const bool stored = l.off_w != 0;
+  // the stored-weights form needs tile flags (its dense kernel computes the softmax part only) and the 3-pass engine;
+  // which form actually runs is decided on the device from the flag density (tc::bwd_gate)
+  const bool stored = l.off_w != 0 && flags != nullptr && eff_mode(mode, D) == MC_GEMM_TC_F16X3;
+  int* gate = nullptr;
+  if (stored) {
+    gate = reinterpret_cast<int*>(base + l.off_vec + 6 * l.vec_stride);
+    if ((rc = tc::bwd_gate(flags, tc::tile_flags_bytes(B, B), gate, static_cast<cudaStream_t>(stream)))) return rc;
+  }
   const int Bp = n_blocks * 128;
   for (int k = 0; k < n_strips; ++k) {
     const int row0 = n_strips == 1 ? 0 : strip_first[k] * 128;
@@ -397,11 +413,12 @@ static int fused_run(const float* I, const float* T, int B, int D, float tau, in
       // row half: dT of the strip is final; the strip's weights and the soft-target part of its dI wait for the column half
       ClipProblem p{I, T, planes, rows, B, D, row0, tau};
       p.tile_flags = fl;
+      p.gate = gate;
       ClipStatsAll s{r, c, rz, g, q};
       if ((rc = tc::bwd_rows(p, eff_mode(mode, D), s, nullptr, dT + (size_t)row0 * D,
                              reinterpret_cast<float*>(base + l.off_diz) + (size_t)row0 * D,
                              base + l.off_w + (size_t)row0 * Bp * 2, phase, phase_bytes,
-                             static_cast<cudaStream_t>(stream))))
+                             static_cast<cudaStream_t>(stream), dI + (size_t)row0 * D)))
         return rc;
       trace_mark("bwd rows strip", k, static_cast<cudaStream_t>(stream));
       if (hook && (rc = hook->fn(hook->ctx, row0, rows, 1))) return rc;
@@ -417,6 +434,7 @@ static int fused_run(const float* I, const float* T, int B, int D, float tau, in
     // column half, in as many strips of output rows as the row half had (the host entry copies a finished strip back
     // while the next is computed)
     ClipProblem p{I, T, planes, B, B, D, 0, tau};
+    p.gate = gate;
     ClipStatsAll s{r, c, rz, g, q};
     for (int k = 0; k < n_strips; ++k) {
       const int j0 = n_strips == 1 ? 0 : strip_first[k] * 128;

@@ -14,6 +14,9 @@ struct ClipProblem {
   // sweep, read (after mc_clip_flags_finalize) by the row-loss and gradient sweeps; null = dense
   uint8_t* tile_flags_out = nullptr;
   const uint8_t* tile_flags = nullptr;
+  // Gradient form switch on the device (see tc::bwd_gate): 1 = the stored-weights / split kernels run, 0 = the own-rows
+  // sweep runs; every gradient kernel is launched and the ones of the other form return at once.  Null = chosen on the host.
+  const int* gate = nullptr;
 };
 
 struct ClipStatsAll {  // length-B vectors (device)
@@ -68,7 +71,8 @@ bool stored_form_enabled(int b, int B, int D);
 size_t stored_weights_bytes(int b, int B);
 size_t bwd_cols_workspace_bytes(int w_rows, int n_cols, int D);
 int bwd_rows(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, float* dT_loc, float* dIz_loc,
-             void* W_rows, void* ws, size_t ws_bytes, cudaStream_t st);
+             void* W_rows, void* ws, size_t ws_bytes, cudaStream_t st, float* dI_loc_ownrows = nullptr);
+int bwd_gate(const uint8_t* flags, size_t n_flags, int* gate_out, cudaStream_t st);
 int bwd_cols(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, const void* W, int w_rows,
              int w_row_offset, int j0, int j1, const float* dIz, float* dI_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int ranks_lse_merge(const float* parts, int n, int64_t stride, int B, float* c, cudaStream_t st);

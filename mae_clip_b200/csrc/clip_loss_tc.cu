@@ -104,6 +104,8 @@ struct PairParams {
   // epilogue warp writes the log-sum-exp of its 32 rows for each of its 32 columns, log2 units, to
   // colpart[(strip row / 32) * Bp + column]; mc::tc::colpart_merge folds them into c.
   float* colpart;
+  const int* gate;                     // gradient form switch (ClipProblem::gate): the kernel returns unless *gate == gate_want
+  int gate_want;
   __half* wout;                        // kBwdW: (bpad x Bp) fp16 weights 2B dS_ij / tau * wscale / s, row = strip row
   // Arrival-ordered launches of the statistics sweep (host-buffer entry: the batch arrives over PCIe in `chunks` row
   // chunks of chunk_blocks row blocks; nsplit = chunks * chunk_m, so a column split lies inside one chunk).  Launch k
@@ -260,6 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
             const __grid_constant__ CUtensorMap map_t, const PairParams p) {
+  if (p.gate != nullptr && *p.gate != p.gate_want) return;   // the other gradient form runs (uniform over the grid)
   // TMEM: tile buffers of 3 x 64 columns (S, St, Z) from column 0; the gradient sweep keeps one tile
   // buffer (the epilogue empties it into registers at once) and its accumulators at 256 (dT), 256 + D/2 (dI)
   constexpr bool kIsBwd = PHASE == kBwd || PHASE == kBwdW || PHASE == kBwdP;
@@ -1335,7 +1338,9 @@ __global__ void __launch_bounds__(256) bwd_finalize_kernel(const float* __restri
                                                            int b, int D, float inv_2B,
                                                            const float* __restrict__ grad_loss,
                                                            const float* __restrict__ wscale,
-                                                           float* __restrict__ dT, float* __restrict__ dI) {
+                                                           float* __restrict__ dT, float* __restrict__ dI,
+                                                           const int* __restrict__ gate = nullptr, int gate_want = 0) {
+  if (gate != nullptr && *gate != gate_want) return;
   const float scale = (grad_loss ? *grad_loss : 1.f) * inv_2B / *wscale;
   const size_t n4 = (size_t)b * D / 4;
   const size_t plane = (size_t)bpad * D;
@@ -1375,6 +1380,7 @@ struct ColGradParams {
   int j_end;               // output rows >= j_end are not written
   int ksplit, steps_per_split, steps;   // K steps of 64 rows
   float* part;             // [ksplit][n_jblocks * 256][D]
+  const int* gate;         // runs only while *gate == 1 (null: always)
 };
 // MN-major SWIZZLE_128B operand: [16,30) leading byte offset (between 64-element M blocks), [32,46) stride byte offset
 // (between 8-row K groups)
@@ -1390,6 +1396,7 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t 
 __global__ void __launch_bounds__(kCgThreads, 1)
 colgrad_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_t,
                const ColGradParams p) {
+  if (p.gate != nullptr && *p.gate != 1) return;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1540,7 +1547,9 @@ __global__ void __launch_bounds__(256) bwd_rows_split_finalize_kernel(const floa
                                                                       size_t plane_p, int b, int D, float inv_2B,
                                                                       const float* __restrict__ grad_loss,
                                                                       const float* __restrict__ wscale,
-                                                                      float* __restrict__ dT, float* __restrict__ dIz) {
+                                                                      float* __restrict__ dT, float* __restrict__ dIz,
+                                                                      const int* __restrict__ gate) {
+  if (gate != nullptr && *gate != 1) return;
   const float scale = (grad_loss ? *grad_loss : 1.f) * inv_2B / *wscale;
   const size_t n4 = (size_t)b * D / 4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -1558,7 +1567,9 @@ __global__ void __launch_bounds__(256) bwd_cols_finalize_kernel(const float* __r
                                                                 int rows, int D, float inv_2B,
                                                                 const float* __restrict__ grad_loss,
                                                                 const float* __restrict__ wscale,
-                                                                const float* __restrict__ dIz, float* __restrict__ dI) {
+                                                                const float* __restrict__ dIz, float* __restrict__ dI,
+                                                                const int* __restrict__ gate) {
+  if (gate != nullptr && *gate != 1) return;
   const float scale = (grad_loss ? *grad_loss : 1.f) * inv_2B / *wscale;
   const size_t n4 = (size_t)rows * D / 4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -1612,11 +1623,13 @@ struct RowGradParams {
   const float* wscale;
   float* part;            // [nsplit][bpad][D]
   __half* wout;           // (bpad x Bp)
+  const int* gate;        // runs only while *gate == 1 (null: always)
 };
 __global__ void __launch_bounds__(kRgThreads, 1)
 rowgrad_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const __grid_constant__ CUtensorMap map_t, const RowGradParams p) {
+  if (p.gate != nullptr && *p.gate != 1) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -2355,6 +2368,8 @@ static int launch_pair(const ClipProblem& p, const ClipStatsAll& s, const float*
   pp.norm_t = reinterpret_cast<const float*>(base + l.off_norm_t);
   pp.colpart = (PHASE == kStats) ? colpart : nullptr;
   pp.wout = wout;
+  pp.gate = (PHASE == kBwd || PHASE == kBwdW || PHASE == kBwdP) ? p.gate : nullptr;
+  pp.gate_want = PHASE == kBwd ? 0 : 1;
   pp.chunk_k = (PHASE == kStats && chunked) ? chunk_k : -1;
   pp.chunk_blocks = chunked ? sp.n_row_blocks / chunks : sp.n_row_blocks;
   pp.chunk_m = chunked ? sp.nsplit / chunks : sp.nsplit;
@@ -2548,16 +2563,25 @@ int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* 
 
 int bwd(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, float* dI, float* dT, void* ws,
         size_t ws_bytes, cudaStream_t st) {
-  MC_REQUIRE(ws_bytes >= workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_bwd(tc): workspace too small");
+  const bool use_stored = p.b == p.B && p.row_offset == 0 && stored_form_enabled(p.b, p.B, p.D) && p.tile_flags != nullptr &&
+                          mode == MC_GEMM_TC_F16X3;
+  MC_REQUIRE(ws_bytes >= (use_stored ? workspace_bytes(p.b, p.B, p.D, mode) : core_workspace_bytes(p.b, p.B, p.D, mode)),
+             MC_ERR_WORKSPACE, "clip_bwd(tc): workspace too small");
   MC_REQUIRE(aligned(dI, 16) && aligned(dT, 16), MC_ERR_ALIGN, "clip_bwd(tc): gradients must be 16-byte aligned");
   MC_REQUIRE(p.planes_all != nullptr, MC_ERR_BAD_ARG, "clip_bwd(tc): planes buffer missing");
-  if (p.b == p.B && p.row_offset == 0 && stored_form_enabled(p.b, p.B, p.D)) {
-    // a call that owns every row: the stored-weights form (row half + column half) instead of the own-rows sweep
+  if (use_stored) {
+    // a call that owns every row and has tile flags: the stored-weights form (row half + column half) while the soft
+    // targets are concentrated, the own-rows sweep otherwise - decided on the device from the flag density
     StoredLayout sl = stored_layout(p.B, p.D, mode);
     char* base = static_cast<char*>(ws);
-    int rc = bwd_rows(p, mode, s, grad_loss, dT, reinterpret_cast<float*>(base + sl.off_diz), base + sl.off_w, ws, sl.off_w, st);
+    ClipProblem pg = p;
+    int* gate = reinterpret_cast<int*>(wscale_slot(ws, p.b, p.B, p.D) + 16);
+    int rc = bwd_gate(p.tile_flags, tile_flags_bytes(p.b, p.B), gate, st);
     if (rc) return rc;
-    return bwd_cols(p, mode, s, grad_loss, base + sl.off_w, p.B, 0, 0, p.B, reinterpret_cast<const float*>(base + sl.off_diz), dI,
+    pg.gate = gate;
+    rc = bwd_rows(pg, mode, s, grad_loss, dT, reinterpret_cast<float*>(base + sl.off_diz), base + sl.off_w, ws, sl.off_w, st, dI);
+    if (rc) return rc;
+    return bwd_cols(pg, mode, s, grad_loss, base + sl.off_w, p.B, 0, 0, p.B, reinterpret_cast<const float*>(base + sl.off_diz), dI,
                     base + sl.off_cols, sl.cols_bytes, st);
   }
   PlanesLayout l = planes_layout(p.B, p.D);
@@ -2656,6 +2680,7 @@ static int launch_rowgrad(const ClipProblem& p, int mode, const ClipStatsAll& s,
   rp.wscale = wscale;
   rp.part = part;
   rp.wout = wout;
+  rp.gate = p.gate;
   static std::atomic<unsigned long long> attr_done{0};
   MC_CUDA(ensure_dynamic_smem(rowgrad_kernel, kRgSmemBytes, attr_done));
   const long njobs = (long)sp.n_row_blocks * sp.nsplit;
@@ -2680,8 +2705,31 @@ static int launch_rowgrad(const ClipProblem& p, int mode, const ClipStatsAll& s,
 
 // Row half over the strip p.row_offset .. + p.b: dT_loc (final), dIz_loc (b x D, un-scaled soft-target part of dI of the
 // strip's rows) and the strip's rows of W (pointer to the strip's first row, row pitch Bp).
+// 1 = concentrated soft targets (few flagged tiles): the stored-weights / split form pays; 0 = own-rows sweep
+__global__ void __launch_bounds__(1024) bwd_gate_kernel(const uint8_t* __restrict__ flags, size_t n, float thresh, int* __restrict__ gate) {
+  __shared__ unsigned int sm[32];
+  unsigned int cnt = 0;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) cnt += flags[i] != 0;
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    cnt = sm[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (threadIdx.x == 0) *gate = ((float)cnt <= thresh * (float)n) ? 1 : 0;
+  }
+}
+int bwd_gate(const uint8_t* flags, size_t n_flags, int* gate_out, cudaStream_t st) {
+  // break-even of the two forms: the split form executes 5 + 16 d GEMM units, the flagged part at about half
+  // the efficiency of the dense kernels; the own-rows sweep 8 + 8 d
+  static const float thresh = getenv("MAE_CLIP_BWD_GATE") ? (float)atof(getenv("MAE_CLIP_BWD_GATE")) : 0.15f;
+  bwd_gate_kernel<<<1, 1024, 0, st>>>(flags, n_flags, thresh, gate_out);
+  MC_LAUNCH_CHECK();
+  return MC_OK;
+}
+
 int bwd_rows(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, float* dT_loc, float* dIz_loc,
-             void* W_rows, void* ws, size_t ws_bytes, cudaStream_t st) {
+             void* W_rows, void* ws, size_t ws_bytes, cudaStream_t st, float* dI_loc_ownrows) {
   MC_REQUIRE(ws_bytes >= core_workspace_bytes(p.b, p.B, p.D, mode), MC_ERR_WORKSPACE, "clip_bwd_rows: workspace too small");
   MC_REQUIRE(aligned(dT_loc, 16) && aligned(dIz_loc, 16) && aligned(W_rows, 256), MC_ERR_ALIGN, "clip_bwd_rows: alignment");
   MC_REQUIRE(p.planes_all != nullptr, MC_ERR_BAD_ARG, "clip_bwd_rows: planes buffer missing");
@@ -2705,10 +2753,21 @@ int bwd_rows(const ClipProblem& p, int mode, const ClipStatsAll& s, const float*
     if ((rc = launch_phase<kBwdP>(mode, p, s, nullptr, part_p, wsc, st))) return rc;
     if ((rc = launch_rowgrad(p, mode, s, part_r, wsc, static_cast<__half*>(W_rows), st))) return rc;
     bwd_rows_split_finalize_kernel<<<blocks, 256, 0, st>>>(part_r, sr.nsplit, (size_t)sr.bpad * p.D, part_p, plane_p, p.b, p.D,
-                                                          0.5f / (float)p.B, grad_loss, wsc, dT_loc, dIz_loc);
+                                                          0.5f / (float)p.B, grad_loss, wsc, dT_loc, dIz_loc, p.gate);
     MC_LAUNCH_CHECK();
+    if (p.gate != nullptr) {
+      // the own-rows sweep of the same strip, for the batches whose soft targets are NOT concentrated (gate == 0): it
+      // shares the partial-sum buffer (only one of the two forms executes) and writes dT_loc and the caller's dI rows
+      MC_REQUIRE(dI_loc_ownrows != nullptr && aligned(dI_loc_ownrows, 16), MC_ERR_BAD_ARG,
+                 "clip_bwd_rows: a gated call needs the dI rows of the own-rows form");
+      if ((rc = launch_phase<kBwd>(mode, p, s, nullptr, static_cast<float*>(ws), wsc, st))) return rc;
+      bwd_finalize_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(ws), sp.nsplit, sp.bpad, p.b, p.D,
+                                                  0.5f / (float)p.B, grad_loss, wsc, dT_loc, dI_loc_ownrows, p.gate, 0);
+      MC_LAUNCH_CHECK();
+    }
     return MC_OK;
   }
+  MC_REQUIRE(p.gate == nullptr, MC_ERR_BAD_ARG, "clip_bwd_rows: the form switch needs tile flags and the 3-pass engine");
   if ((rc = launch_phase<kBwdW>(mode, p, s, nullptr, static_cast<float*>(ws), wsc, st, nullptr, -1, 1,
                                 static_cast<__half*>(W_rows))))
     return rc;
@@ -2746,6 +2805,7 @@ int bwd_cols(const ClipProblem& p, int mode, const ClipStatsAll& s, const float*
   cp.j_first = j0; cp.n_jblocks = cs.n_jblocks; cp.j_end = j1;
   cp.ksplit = cs.ksplit; cp.steps_per_split = cs.steps_per_split; cp.steps = cs.steps;
   cp.part = static_cast<float*>(ws);
+  cp.gate = p.gate;
   const int smem = kCgStages * (kCgStageA + (p.D / 2) * 128) + 8 * 32 + 16 + 1024;
   static std::atomic<unsigned long long> attr_done{0};
   MC_CUDA(ensure_dynamic_smem(colgrad_kernel, smem, attr_done));
@@ -2772,7 +2832,7 @@ int bwd_cols(const ClipProblem& p, int mode, const ClipStatsAll& s, const float*
   int cap = num_sms() * 8;
   if (blocks > cap) blocks = cap;
   bwd_cols_finalize_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(ws), cs.ksplit, (size_t)cs.n_jblocks * 256 * p.D,
-                                                   rows, p.D, 0.5f / (float)p.B, grad_loss, wsc, dIz, dI_out);
+                                                   rows, p.D, 0.5f / (float)p.B, grad_loss, wsc, dIz, dI_out, p.gate);
   MC_LAUNCH_CHECK();
   return MC_OK;
 }

@@ -88,7 +88,9 @@ __global__ void __launch_bounds__(256) peer_publish_kernel(const uint32_t* __res
 // out[i] = sum_q src.p[q][i]: the reduce-scatter step of the stored-weights gradient (every rank pulls ITS rows of the
 // peers' partial dI straight out of their memory: 16-byte loads, all `world` of them in flight before the first add;
 // a fixed summation order, so every run gives the same bits)
-__global__ void __launch_bounds__(256) peer_reduce_kernel(PeerWords src, int world, size_t n4, float4* __restrict__ out) {
+__global__ void __launch_bounds__(256) peer_reduce_kernel(PeerWords src, int world, size_t n4, float4* __restrict__ out,
+                                                          const int* __restrict__ gate) {
+  if (gate != nullptr && *gate != 1) return;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 v[kMaxPeers];
 #pragma unroll
@@ -195,7 +197,7 @@ int mc_peer_publish(const void* src, int k, int n, int64_t src_stride, void* con
   return MC_OK;
 }
 
-int mc_peer_reduce(void* const* src_ptrs_host, int world, size_t n_floats, float* out, void* stream) {
+int mc_peer_reduce(void* const* src_ptrs_host, int world, size_t n_floats, float* out, const int* gate, void* stream) {
   MC_ARCH_GUARD();
   MC_REQUIRE(out && aligned(out, 16) && n_floats > 0 && n_floats % 4 == 0, MC_ERR_BAD_ARG, "peer_reduce: bad argument");
   PeerWords w;
@@ -205,7 +207,7 @@ int mc_peer_reduce(void* const* src_ptrs_host, int world, size_t n_floats, float
   const size_t n4 = n_floats / 4;
   int blocks = (int)((n4 + 255) / 256);
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
-  peer_reduce_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, world, n4, reinterpret_cast<float4*>(out));
+  peer_reduce_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, world, n4, reinterpret_cast<float4*>(out), gate);
   MC_LAUNCH_CHECK();
   return MC_OK;
 }

@@ -319,25 +319,31 @@ class PeerStep:
         gl = None if grad_loss is None else grad_loss.reshape(1).to(torch.float32).contiguous()
         with torch.cuda.device(dev):
             ws = workspace(L.mc_clip_loss_workspace_bytes(b, B, D, mode), dev)
-            if self.bwd_form == "stored" and ex.world > 1:
+            if self.bwd_form == "stored" and ex.world > 1 and flags is not None and mode == _lib.GEMM_TC_F16X3:
                 st = cur_stream()
                 if self._stored is None:
                     Bp = (B + 127) // 128 * 128
                     self._stored = (torch.empty(L.mc_clip_stored_weights_bytes(b, B), device=dev, dtype=torch.uint8),
                                     torch.zeros(Bp, D, device=dev, dtype=torch.float32),   # only OUR rows are ever written
-                                    torch.empty(L.mc_clip_bwd_cols_workspace_bytes(B, D), device=dev, dtype=torch.uint8))
-                W, diz, wsc = self._stored
+                                    torch.empty(L.mc_clip_bwd_cols_workspace_bytes(B, D), device=dev, dtype=torch.uint8),
+                                    torch.zeros(1, device=dev, dtype=torch.int32))
+                W, diz, wsc, gate = self._stored
                 row0 = ex.rank * b
+                # stored form or own-rows sweep: decided on the device from the flag density of the WHOLE bitmap (every
+                # rank holds it after the forward exchange), so all ranks take the same branch
+                nt = (B + 127) // 128
+                check(L.mc_clip_bwd_gate(ex.local(ex.off_flags), nt * nt, ptr(gate), st), "mc_clip_bwd_gate")
+                gp = gate
                 check(L.mc_clip_bwd_rows(ptr(planes), b, B, D, row0, float(tau), mode, ptr(vecs[0]), ptr(vecs[1]),
                                          ptr(vecs[2]), ptr(vecs[3]), ptr(vecs[4]), ptr(gl), ptr(dT), ptr(diz[row0:]), ptr(W),
-                                         ptr(flags), ptr(ws), ws.numel(), st), "mc_clip_bwd_rows")
+                                         ptr(flags), ptr(gp), ptr(dI), ptr(ws), ws.numel(), st), "mc_clip_bwd_rows")
                 # our contribution to every row of dI goes where the peers can read it: the (B, D) image of I in the
                 # exchange region is dead once the planes are staged
                 check(L.mc_clip_bwd_cols(ptr(planes), B, D, float(tau), mode, ptr(vecs[0]), ptr(vecs[1]), ptr(vecs[2]),
                                          ptr(vecs[4]), ptr(gl), ptr(W), b, row0, 0, B, ptr(diz), ex.local(ex.off_emb_i),
-                                         ptr(wsc), wsc.numel(), st), "mc_clip_bwd_cols")
+                                         ptr(gp), ptr(wsc), wsc.numel(), st), "mc_clip_bwd_cols")
                 ex.barrier()
-                ex.reduce_rows(ex.off_emb_i + row0 * D * 4, b * D, dI)
+                ex.reduce_rows(ex.off_emb_i + row0 * D * 4, b * D, dI, gp)
                 ex.barrier()   # nobody pushes the next step's shards into an image a peer is still reading
             else:
                 check(L.mc_clip_bwd(None, None, ptr(planes), b, B, D, ex.rank * b, float(tau), mode, ptr(vecs[0]),

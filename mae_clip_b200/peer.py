@@ -194,10 +194,11 @@ class PeerExchange:
         check(lib().mc_peer_publish(src, k, n, src_stride, self.table(dst_offset_bytes), dst_stride, dst_index,
                                     self.world, cur_stream()), "mc_peer_publish")
 
-    def reduce_rows(self, src_offset_bytes: int, n_floats: int, out: torch.Tensor):
-        """out[i] = sum over ranks q of (q's region + src_offset_bytes)[i]: every rank pulls its own rows of the peers' partials."""
+    def reduce_rows(self, src_offset_bytes: int, n_floats: int, out: torch.Tensor, gate=None):
+        """out[i] = sum over ranks q of (q's region + src_offset_bytes)[i]: every rank pulls its own rows of the peers'
+        partials (``gate``: optional device word, the kernel returns unless it is 1)."""
         check(lib().mc_peer_reduce(self.table(src_offset_bytes), self.world, n_floats, C.c_void_p(out.data_ptr()),
-                                   cur_stream()), "mc_peer_reduce")
+                                   None if gate is None else C.c_void_p(gate.data_ptr()), cur_stream()), "mc_peer_reduce")
 
     def copy_out(self, src_offset_bytes: int, k: int, n: int, src_stride: int, dst: torch.Tensor, dst_stride: int):
         """Copy k vectors of n words from the local region into an ordinary tensor (same kernel, one target)."""

@@ -472,7 +472,7 @@ def test_tile_flags_are_a_superset_of_the_exact_relevance(scale, tau):
 
 
 # ------------------------------------------------------------------ parity AT the benchmarked size (BASELINE config 4)
-def _phases_sharded(I, T, tau, mode, shard_rows, colpart=False, stored=False, use_flags=True):
+def _phases_sharded(I, T, tau, mode, shard_rows, colpart=False, stored=False, use_flags=True, gated=False):
     """The row-sharded form of the step (what the ranks of a multi-GPU job run, mae_clip_b200/dist.py) back to back on
     one GPU: every shard of `shard_rows` rows runs its own statistics / row-loss / gradient sweeps with a row offset,
     the length-B vectors and the tile-flag bitmap are assembled in between exactly as the exchange steps do."""
@@ -525,17 +525,24 @@ def _phases_sharded(I, T, tau, mode, shard_rows, colpart=False, stored=False, us
         Wbuf = torch.empty(lib.mc_clip_stored_weights_bytes(b, B), dtype=torch.uint8, device=dev)
         wsc = torch.empty(lib.mc_clip_bwd_cols_workspace_bytes(B, D), dtype=torch.uint8, device=dev)
         Bp = (B + 127) // 128 * 128
-        dI.zero_()
+        # gated: the form (stored / own rows) is chosen on the device from the density of the whole flag bitmap
+        gate = torch.full((1,), -1, dtype=torch.int32, device=dev) if gated else None
+        if gated:
+            check(lib.mc_clip_bwd_gate(ptr(fin), fin.numel(), ptr(gate), s), "mc_clip_bwd_gate")
+        dI_sum = torch.zeros_like(dI)
         for k in range(W):
             o = k * b
             diz = torch.zeros(Bp, D, device=dev)
-            part = torch.empty(B, D, device=dev)
+            part = torch.zeros(B, D, device=dev)
             check(lib.mc_clip_bwd_rows(ptr(planes), b, B, D, o, tau, md, ptr(st4[0]), ptr(st4[1]), ptr(st4[2]), ptr(gq[0]),
                                        ptr(gq[1]), None, ptr(dT[o:]), ptr(diz[o:]), ptr(Wbuf), ptr(fin[k]) if use_flags else None,
-                                       ptr(ws), ws.numel(), s), "mc_clip_bwd_rows")
+                                       ptr(gate), ptr(dI[o:]) if gated else None, ptr(ws), ws.numel(), s), "mc_clip_bwd_rows")
             check(lib.mc_clip_bwd_cols(ptr(planes), B, D, tau, md, ptr(st4[0]), ptr(st4[1]), ptr(st4[2]), ptr(gq[1]), None,
-                                       ptr(Wbuf), b, o, 0, B, ptr(diz), ptr(part), ptr(wsc), wsc.numel(), s), "mc_clip_bwd_cols")
-            dI += part
+                                       ptr(Wbuf), b, o, 0, B, ptr(diz), ptr(part), ptr(gate), ptr(wsc), wsc.numel(), s), "mc_clip_bwd_cols")
+            dI_sum += part
+        if not gated or gate.item() == 1:
+            dI = dI_sum       # the stored form ran: the shards' partial dI summed (the peer reduce)
+        _phases_sharded.last_gate = None if gate is None else gate.item()
     else:
         for k in range(W):
             o = k * b
@@ -564,7 +571,7 @@ def _c4_batch_and_oracle(B, scale):
 
 
 @pytest.mark.parametrize("variant", ["fused_flags", "dense", "shards4096_flags", "shards4096_colpart", "shards4096_stored",
-                                     "shards4096_stored_noflags", "host_entry"])
+                                     "shards4096_stored_noflags", "shards4096_stored_gated", "host_entry"])
 @pytest.mark.parametrize("B", [8192, 32768])
 def test_loss_c4_size_vs_fp64_blockwise(B, variant):
     """The benchmarked path - B = 32768 (and 8192), D = 256, LayerNorm-scale rows (tile-flag density 1/256), probe +
@@ -585,7 +592,10 @@ def test_loss_c4_size_vs_fp64_blockwise(B, variant):
         loss, dI, dT, _ = _phases(I, T, 1.0, "tc_f16x3", sparse=False)
     elif variant.startswith("shards4096"):
         loss, dI, dT, flags = _phases_sharded(I, T, 1.0, "tc_f16x3", 4096, colpart="flags" not in variant,
-                                              stored="stored" in variant, use_flags=not variant.endswith("noflags"))
+                                              stored="stored" in variant, use_flags=not variant.endswith("noflags"),
+                                              gated=variant.endswith("gated"))
+        if variant.endswith("gated"):
+            assert _phases_sharded.last_gate == 1     # concentrated soft targets: the stored form ran
         assert flags.float().mean().item() < 0.02      # the sparse path is what ran (diagonal tiles + a few neighbours)
     else:
         lib = _lib.lib()
@@ -621,6 +631,14 @@ def test_loss_c4_size_soft_regime_vs_fp64_blockwise():
         loss, dI, dT, flags = _phases(I, T, 1.0, "tc_f16x3", sparse=sparse)
         if sparse:
             assert bool(flags.all())
+        assert abs(loss - ref_loss) <= LOSS_TOL * abs(ref_loss)
+        assert rel_err(dI, ref_dI) < GRAD_TOL and rel_err(dT, ref_dT) < GRAD_TOL
+    # row shards with the device-side choice of the gradient form: every tile is flagged, so the gate picks the own-rows
+    # sweep (0) and the stored-weights kernels return at once; forced stored form (no gate) for the same batch
+    for gated in (True, False):
+        loss, dI, dT, flags = _phases_sharded(I, T, 1.0, "tc_f16x3", 4096, colpart=True, stored=True, gated=gated)
+        if gated:
+            assert _phases_sharded.last_gate == 0
         assert abs(loss - ref_loss) <= LOSS_TOL * abs(ref_loss)
         assert rel_err(dI, ref_dI) < GRAD_TOL and rel_err(dT, ref_dT) < GRAD_TOL
 
