@@ -1,6 +1,7 @@
 // L3-L6, engines MC_GEMM_TC_F16X3 / MC_GEMM_TC_F16: the contrastive soft-target loss on the 5th-gen
 // tensor cores.  Reference arithmetic: /root/reference CLIP.py:34-43 and its autograd (main.py:58),
-// closed form in SURVEY.md section 8 row L6.  No B x B tensor ever reaches HBM: every sweep
+// closed form in SURVEY.md section 8 row L6.  No B x B tensor of logits or targets ever reaches HBM (the stored-weights
+// gradient keeps ONE b x B fp16 strip of gradient weights between its two halves, see kBwdW / rowgrad_kernel): every sweep
 // recomputes the 128 x 128 tiles of
 //     S  = T_i I_j^T / tau      St = I_i T_j^T / tau  (= S_ji)      Z = (I_i I_j^T + T_i T_j^T) tau/2
 // in tensor memory and reduces them in the epilogue.
@@ -2651,7 +2652,9 @@ size_t workspace_bytes(int b, int B, int D, int mode) {
 }
 bool stored_form_enabled(int b, int B, int D) {
   static const bool off = getenv("MAE_CLIP_BWD_FORM") != nullptr && strcmp(getenv("MAE_CLIP_BWD_FORM"), "ownrows") == 0;
-  return !off && supported(D) && stored_weights_bytes(b, B) <= ((size_t)16 << 30);
+  // small problems are launch-bound: the own-rows sweep is one kernel + one fold (C2's B = 1024: 0.18 ms against 0.25 ms for
+  // the ten launches of the stored form); from 4096 x 4096 logits on the saved tensor work dominates
+  return !off && supported(D) && (double)b * (double)B >= 4096.0 * 4096.0 && stored_weights_bytes(b, B) <= ((size_t)16 << 30);
 }
 
 static int launch_rowgrad(const ClipProblem& p, int mode, const ClipStatsAll& s, float* part, const float* wscale,

@@ -643,6 +643,21 @@ def test_loss_c4_size_soft_regime_vs_fp64_blockwise():
         assert rel_err(dI, ref_dI) < GRAD_TOL and rel_err(dT, ref_dT) < GRAD_TOL
 
 
+@pytest.mark.parametrize("scale", [1.0, 0.25])
+@pytest.mark.parametrize("B,b", [(1152, 384), (1280, 1280), (640, 128)])
+def test_stored_weights_gradient_small_and_ragged_shapes(B, b, scale):
+    """mc_clip_bwd_rows / mc_clip_bwd_cols called directly at sizes below the automatic switch (4096 x 4096 logits), where
+    the padded shapes matter: B not a multiple of 256 (rowgrad_kernel's row blocks and colgrad_kernel's column blocks are
+    256 wide), strips of 128 - 1280 rows, concentrated and soft targets - against the closed-form fp64 oracle."""
+    I = loss_ref.make_embeddings(B, 256, seed=31, scale=scale).cuda()
+    T = loss_ref.make_embeddings(B, 256, seed=32, scale=scale).cuda()
+    ref_loss, ref_dI, ref_dT, _ = loss_ref.clip_loss_closed_form(I.cpu().numpy(), T.cpu().numpy(), 1.0)
+    for gated in (False, True):
+        loss, dI, dT, _flags = _phases_sharded(I, T, 1.0, "tc_f16x3", b, colpart=True, stored=True, gated=gated)
+        assert abs(loss - ref_loss) <= LOSS_TOL * abs(ref_loss)
+        assert rel_err(dI, ref_dI) < GRAD_TOL and rel_err(dT, ref_dT) < GRAD_TOL, (gated, rel_err(dI, ref_dI), rel_err(dT, ref_dT))
+
+
 # ------------------------------------------------------------------ autograd plumbing (round-1 advisor findings)
 def test_fp32_fma_engine_state_survives_other_ops_between_forward_and_backward():
     """The fp32 FMA engine keeps its S / S^T / Z strips from the statistics sweep to the gradient sweep.  Through the
