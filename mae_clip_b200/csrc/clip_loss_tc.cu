@@ -1909,6 +1909,363 @@ rowgrad_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
+// Statistics sweep on large MMA instructions (same skeleton as rowgrad_kernel: CTA pair of 256 rows, cta_group::2 with
+// M = 256, TMEM lane = row, 256 x 128 tiles, 64-cycle MMAs).  Two kinds, launched one after the other:
+//   kRsS  S = T_i I_j^T in three passes -> row LSE of S (online, one partial per job) and the per-32-row column partials
+//         of the column LSE (the transpose-reduce of pair_kernel<kStats>, twice per tile: a thread holds 64 columns).
+//         T_i hi resident (64 KB); ring slot = one 64-wide K chunk of {T_i lo, I_j hi, I_j lo} (32 KB, 4 slots).
+//   kRsZ  the tile-flag PROBE: Z = (I_i I_j^T + T_i T_j^T) tau/2 from the hi planes only -> flags.  I_i hi and T_i hi
+//         resident (128 KB); ring slot = {I_j hi, T_j hi} of one K chunk (16 KB, 5 slots).  Z is symmetric, so a call that
+//         owns every row visits the tiles ON OR ABOVE the diagonal only: a warp flags (row block, tile) by the row
+//         criterion (max_j Z_ij against Z_ii) and the transposed pair (tile, row block) by the column criterion against
+//         the smallest Z_jj of the tile (a superset of the per-column test, as rigorous as the row one).
+// Four tile buffers of 128 TMEM columns.  Jobs are (256-row block, column split), optionally filtered by arrival chunk
+// (see PairParams::chunk_k).
+// ------------------------------------------------------------------------------------------
+enum RsKind { kRsS = 0, kRsZ = 1 };
+constexpr int kRsThreads = 384;
+constexpr int kRsNBuf = 4;
+constexpr int kRsOffScratch = 212992;                       // 208 KB: per-warp column maxima / end-of-job merge (2 KB)
+constexpr int kRsOffBar = kRsOffScratch + 2048;
+constexpr int kRsSmemBytes = kRsOffBar + 256 + 512;
+enum RsBar { kRsFull0 = 0, kRsEmpty0 = 5, kRsAFull = 10, kRsJobDone = 11, kRsTmemFull0 = 12, kRsTmemEmpty0 = 16, kRsNumBars = 20 };
+struct RowSweepParams {
+  int b, B, Bp, D, row_offset;
+  int n_row_blocks, n_tiles, nsplit, tiles_per_split, bpad;     // row blocks of 256
+  int chunk_k, chunk_blocks, chunk_m;                            // arrival-ordered launches (chunk_k < 0: every job)
+  int tri;                                                       // kRsZ: tiles on or above the diagonal only
+  float inv_tau, half_tau;
+  const float* scale;
+  float2* part;             // kRsS: [nsplit][bpad] (row max in log2 units, sum)
+  float* colpart;           // kRsS: [(bpad / 32)][Bp]
+  uint8_t* flags_out;       // kRsZ: [row blocks of 128][n_tiles]
+  const float *norm_i, *norm_t;
+  const float* tile_min_zjj2;   // kRsZ, tri: smallest Z_jj (log2 units) of every column tile
+};
+__device__ __forceinline__ int rs_njobs(const RowSweepParams& p) {
+  if (p.chunk_k < 0) return p.n_row_blocks * p.nsplit;
+  return p.chunk_blocks * (p.chunk_k + 1) * p.chunk_m + p.chunk_k * p.chunk_blocks * p.chunk_m;
+}
+__device__ __forceinline__ void rs_job(const RowSweepParams& p, int job, int& rb, int& sp) {
+  if (p.chunk_k < 0) { rb = job / p.nsplit; sp = job % p.nsplit; return; }
+  const int w = (p.chunk_k + 1) * p.chunk_m, first = p.chunk_blocks * w;
+  if (job < first) { rb = p.chunk_k * p.chunk_blocks + job / w; sp = job % w; return; }
+  job -= first;
+  rb = job / p.chunk_m;
+  sp = p.chunk_k * p.chunk_m + job % p.chunk_m;
+}
+// tile range of a job; kRsZ in triangle mode starts at the row block's own diagonal tile
+template <int KIND>
+__device__ __forceinline__ void rs_tiles(const RowSweepParams& p, int rb, int sp, int& t0, int& t1) {
+  t0 = sp * p.tiles_per_split;
+  t1 = min(t0 + p.tiles_per_split, p.n_tiles);
+  if (KIND == kRsZ && p.tri) t0 = max(t0, 2 * rb);
+}
+template <int KIND>
+__global__ void __launch_bounds__(kRsThreads, 1)
+rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const RowSweepParams p) {
+  constexpr int kSlotBytes_ = KIND == kRsS ? 32768 : 16384;
+  constexpr int kSlots = KIND == kRsS ? 4 : 5;
+  constexpr int kOffRing = KIND == kRsS ? 65536 : 131072;
+  static_assert(kOffRing + kSlots * kSlotBytes_ <= kRsOffScratch, "ring overlaps the scratch");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  if (base - raw > 512u) __trap();
+  uint8_t* const sbase = smem_raw + (base - raw);
+  const uint32_t bar0 = base + kRsOffBar;
+  auto bar = [&](int i) -> uint32_t { return bar0 + 8u * i; };
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(sbase + kRsOffBar + 8 * kRsNumBars);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int D = p.D, nkc = D >> 6;
+  const int njobs = rs_njobs(p);
+  const int n_res = KIND == kRsS ? nkc : 2 * nkc;     // resident 16 KB chunks of this CTA's rows
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSlots; ++s) { mbar_init(bar(kRsFull0 + s), 1); mbar_init(bar(kRsEmpty0 + s), 1); }
+    mbar_init(bar(kRsAFull), 1);
+    mbar_init(bar(kRsJobDone), 1);
+    for (int i = 0; i < kRsNBuf; ++i) { mbar_init(bar(kRsTmemFull0 + i), 1); mbar_init(bar(kRsTmemEmpty0 + i), 2 * 256); }
+    fence_mbar_init();
+    prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_b_hi); prefetch_tmap(&map_b_lo);
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(smem_u32(tmem_slot), 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== producer: resident rows + ring
+    if (elect_one()) {
+      uint32_t it = 0, jj = 0;
+      for (int job = pair_id; job < njobs; job += npairs) {
+        int rb, sp, t0, t1;
+        rs_job(p, job, rb, sp);
+        rs_tiles<KIND>(p, rb, sp, t0, t1);
+        if (t0 >= t1) continue;
+        const int row_a = p.row_offset + rb * 256 + (int)rank * 128;
+        mbar_wait(bar(kRsJobDone), (jj & 1) ^ 1);
+        ++jj;
+        if (leader) mbar_arrive_expect_tx(bar(kRsAFull), 2u * (uint32_t)n_res * 16384u);
+        if (KIND == kRsS) {
+          for (int c = 0; c < nkc; ++c) tma_load_2d_pair(base + c * 16384, &map_a_hi, bar(kRsAFull), D + c * 64, row_a);   // T_i hi
+        } else {
+          for (int c = 0; c < 2 * nkc; ++c) tma_load_2d_pair(base + c * 16384, &map_a_hi, bar(kRsAFull), c * 64, row_a);   // [I_i | T_i] hi
+        }
+        for (int t = t0; t < t1; ++t) {
+          const int j0 = t * kTileN + 64 * (int)rank;
+          for (int c = 0; c < nkc; ++c, ++it) {
+            const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
+            mbar_wait(bar(kRsEmpty0 + slot), par ^ 1);
+            const uint32_t fb = bar(kRsFull0 + slot), sb = base + kOffRing + slot * kSlotBytes_;
+            if (leader) mbar_arrive_expect_tx(fb, 2u * kSlotBytes_);
+            if (KIND == kRsS) {
+              tma_load_2d_pair(sb, &map_a_lo, fb, D + c * 64, row_a);            // T_i lo   (128 rows)
+              tma_load_2d_pair(sb + 16384, &map_b_hi, fb, c * 64, j0);           // I_j hi   (64 rows)
+              tma_load_2d_pair(sb + 24576, &map_b_lo, fb, c * 64, j0);           // I_j lo
+            } else {
+              tma_load_2d_pair(sb, &map_b_hi, fb, c * 64, j0);                   // I_j hi
+              tma_load_2d_pair(sb + 8192, &map_b_hi, fb, D + c * 64, j0);        // T_j hi
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = idesc_f16(256, kTileN);
+      uint32_t it = 0, tt = 0, jj = 0;
+      for (int job = pair_id; job < njobs; job += npairs) {
+        int rb, sp, t0, t1;
+        rs_job(p, job, rb, sp);
+        rs_tiles<KIND>(p, rb, sp, t0, t1);
+        if (t0 >= t1) continue;
+        mbar_wait(bar(kRsAFull), jj & 1);
+        ++jj;
+        tc_fence_after();
+        for (int t = t0; t < t1; ++t, ++tt) {
+          const uint32_t buf = tt % kRsNBuf, use = tt / kRsNBuf;
+          mbar_wait(bar(kRsTmemEmpty0 + buf), (use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tD = tmem_base + buf * 128;
+          for (int c = 0; c < nkc; ++c, ++it) {
+            const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
+            mbar_wait(bar(kRsFull0 + slot), par);
+            tc_fence_after();
+            const uint32_t sb = base + kOffRing + slot * kSlotBytes_;
+            if (KIND == kRsS) {
+              const uint64_t aT = smem_desc_sw128(base + c * 16384), aTl = smem_desc_sw128(sb);
+              const uint64_t bI = smem_desc_sw128(sb + 16384), bIl = smem_desc_sw128(sb + 24576);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t kT = desc_advance_k(aT, ks), kb = desc_advance_k(bI, ks);
+                mma_f16_pair(tD, kT, kb, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                mma_f16_pair(tD, kT, desc_advance_k(bIl, ks), idesc, 1u);
+                mma_f16_pair(tD, desc_advance_k(aTl, ks), kb, idesc, 1u);
+              }
+            } else {
+              const uint64_t aI = smem_desc_sw128(base + c * 16384), aT = smem_desc_sw128(base + (nkc + c) * 16384);
+              const uint64_t bI = smem_desc_sw128(sb), bT = smem_desc_sw128(sb + 8192);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                mma_f16_pair(tD, desc_advance_k(aI, ks), desc_advance_k(bI, ks), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                mma_f16_pair(tD, desc_advance_k(aT, ks), desc_advance_k(bT, ks), idesc, 1u);
+              }
+            }
+            mma_commit_pair(bar(kRsEmpty0 + slot), 3);
+          }
+          mma_commit_pair(bar(kRsTmemFull0 + buf), 3);
+        }
+        mma_commit_pair(bar(kRsJobDone), 3);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================================================== epilogue: thread = (TMEM lane m, column half h)
+    const int q4 = warp & 3, h = (warp - 4) >> 2;
+    const int m = q4 * 32 + lane;
+    const uint32_t lane_field = (uint32_t)(q4 * 32) << 16;
+    float* const scratch = reinterpret_cast<float*>(sbase + kRsOffScratch);
+    const float kL2e = 1.4426950408889634f;
+    const float inv_s2 = p.scale[2];
+    const float cS2 = inv_s2 * p.inv_tau * kL2e, cZ2 = inv_s2 * p.half_tau * kL2e;
+    const float zmargin2 = kProbeMargin2 + (1.f / 512.f) * (8.f * (float)D * inv_s2 * p.half_tau * kL2e);
+    uint32_t tt = 0;
+    for (int job = pair_id; job < njobs; job += npairs) {
+      int rb, sp, t0, t1;
+      rs_job(p, job, rb, sp);
+      const int lrow = rb * 256 + (int)rank * 128 + m;
+      const int gi = p.row_offset + lrow;
+      const bool row_ok = lrow < p.b;
+      rs_tiles<KIND>(p, rb, sp, t0, t1);
+      if (t0 >= t1) continue;                                 // kRsZ below the diagonal: nothing to do (kRsS never)
+      float mS = -INFINITY, sS = 0.f;
+      float zii2 = 0.f;
+      if (KIND == kRsZ && row_ok) {
+        const float ni = p.norm_i[gi], nt = p.norm_t[gi];
+        zii2 = (ni * ni + nt * nt) * p.half_tau * kL2e;
+      }
+      const int rb128 = rb * 2 + (int)rank;                   // this CTA's 128-row block of the strip
+      for (int t = t0; t < t1; ++t, ++tt) {
+        const uint32_t buf = tt % kRsNBuf, use = tt / kRsNBuf;
+        mbar_wait(bar(kRsTmemFull0 + buf), use & 1);
+        tc_fence_after();
+        const uint32_t tD = tmem_base + buf * 128 + lane_field + 64 * h;
+        const bool ragged = (t + 1) * kTileN > p.B;
+        float cmz = -INFINITY;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          tmem_ld32(tD + 32 * half, v);
+          tmem_ld_wait();
+          if (half == 1) {
+            tc_fence_before();
+            mbar_arrive_cluster(bar(kRsTmemEmpty0 + buf), 0);
+          }
+          const int jl0 = 64 * h + 32 * half;                 // first tile column of these 32
+          if (ragged) {
+            const int jlim = p.B - t * kTileN;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) if (jl0 + e >= jlim) v[e] = -INFINITY;
+          }
+          float c4[4] = {fmaxf(v[0], v[4]), fmaxf(v[1], v[5]), fmaxf(v[2], v[6]), fmaxf(v[3], v[7])};
+#pragma unroll
+          for (int e = 8; e < 32; e += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) c4[u] = fmaxf(c4[u], v[e + u]);
+          }
+          const float cm = fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3]));
+          if (KIND == kRsZ) {
+            cmz = fmaxf(cmz, cm);
+          } else {
+            // ---- row LSE of S, online (exact differences: an unchanged maximum rescales by exactly 1)
+            const float mn = fmaxf(mS, cm);
+            if (mn != -INFINITY) {
+              float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a4[u] += ex2f((v[e + u] - mn) * cS2);
+              }
+              sS = sS * ex2f((mS - mn) * cS2) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
+              mS = mn;
+            }
+            // ---- column partials: this warp's 32 x 32 block (lane = row) -> LSE over its rows of each column
+            float a[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) a[e] = row_ok ? v[e] : -INFINITY;
+#pragma unroll
+            for (int s2 = 16; s2 >= 1; s2 >>= 1) {
+              const bool up = (lane & s2) != 0;
+#pragma unroll
+              for (int k = 0; k < s2; ++k) {
+                const float keep = up ? a[k + s2] : a[k], send = up ? a[k] : a[k + s2];
+                a[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, s2));
+              }
+            }
+            float* cmx = scratch + (warp - 4) * 32;
+            __syncwarp();
+            cmx[lane] = a[0];
+            __syncwarp();
+            const float cm_own = a[0];
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 q4v = *reinterpret_cast<const float4*>(cmx + e);
+              const float cmv[4] = {q4v.x, q4v.y, q4v.z, q4v.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float ref = cmv[u] == -INFINITY ? 0.f : cmv[u];
+                a[e + u] = row_ok ? ex2f((v[e + u] - ref) * cS2) : 0.f;
+              }
+            }
+#pragma unroll
+            for (int s2 = 16; s2 >= 1; s2 >>= 1) {
+              const bool up = (lane & s2) != 0;
+#pragma unroll
+              for (int k = 0; k < s2; ++k) {
+                const float keep = up ? a[k + s2] : a[k], send = up ? a[k] : a[k + s2];
+                a[k] = keep + __shfl_xor_sync(0xffffffffu, send, s2);
+              }
+            }
+            const int g32 = (rb * 256 + (int)rank * 128 + q4 * 32) >> 5;
+            p.colpart[(size_t)g32 * p.Bp + (size_t)t * kTileN + jl0 + lane] =
+                cm_own == -INFINITY ? -INFINITY : fmaf(cm_own, cS2, lg2f(a[0]));
+          }
+        }
+        if (KIND == kRsZ) {
+          // row criterion: rz_i >= Z_ii, so a row whose largest (hi-plane) Z stays 44 binades + the rounding bound below it
+          // holds no P_ij >= 2^-44 in this tile
+          const float z2 = row_ok ? cmz * cZ2 : -INFINITY;
+          const bool hit = z2 >= zii2 - kFlagTheta2 - zmargin2;
+          if (__any_sync(0xffffffffu, hit) && lane == 0) p.flags_out[(size_t)rb128 * p.n_tiles + t] = 1;
+          if (p.tri && t != rb128) {
+            // column criterion for the transposed tile (rows of tile t, columns of this row block), by Z_ij = Z_ji
+            const float wm = warp_max(z2);
+            if (lane == 0 && wm >= p.tile_min_zjj2[t] - kFlagTheta2 - zmargin2) p.flags_out[(size_t)t * p.n_tiles + rb128] = 1;
+          }
+        }
+      }
+      if (KIND == kRsS) {
+        // ---- end of job: the two column halves of a row meet in shared memory (h = 1 hands over, h = 0 writes)
+        named_bar_sync(2, 256);
+        float* sc = scratch + 256;       // behind the per-warp column maxima: [2][128]
+        if (h == 1) { sc[m] = mS * cS2; sc[128 + m] = sS; }
+        named_bar_sync(2, 256);
+        if (h == 0) {
+          OnlineLse2 l;
+          l.m = mS * cS2; l.s = sS;
+          l.merge(sc[m], sc[128 + m]);
+          p.part[(size_t)sp * p.bpad + lrow] = make_float2(l.m, l.s);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
+// smallest Z_jj (log2 units) of every 128-column tile (kRsZ, triangle mode)
+__global__ void __launch_bounds__(128) tile_min_zjj_kernel(const float* __restrict__ norm_i, const float* __restrict__ norm_t,
+                                                           int B, float half_tau, float* __restrict__ out) {
+  __shared__ float sm[4];
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  float z = INFINITY;
+  if (j < B) {
+    const float ni = norm_i[j], nt = norm_t[j];
+    z = (ni * ni + nt * nt) * half_tau * 1.4426950408889634f;
+  }
+  for (int o = 16; o > 0; o >>= 1) z = fminf(z, __shfl_xor_sync(0xffffffffu, z, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = z;
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = fminf(fminf(sm[0], sm[1]), fminf(sm[2], sm[3]));
+}
+// row LSE of S from rowsweep_kernel<kRsS>'s partials
+__global__ void __launch_bounds__(256) rowsweep_finalize_kernel(const float2* __restrict__ part, int nsplit, int bpad, int b,
+                                                                float* __restrict__ r) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  OnlineLse2 l;
+  l.init();
+  for (int s = 0; s < nsplit; ++s) {
+    const float2 v = part[(size_t)s * bpad + i];
+    l.merge(v.x, v.y);
+  }
+  r[i] = (l.m + log2f(l.s)) * kLn2;
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -2010,16 +2367,18 @@ static bool use_colpart(int b, int B) {
 }
 static size_t colpart_bytes(int b, int B, bool forced = false) {
   if (!forced && !use_colpart(b, B)) return 0;
-  Split s = choose_split(b, B);
-  return round_up((size_t)(s.bpad / 32) * round_up((size_t)B, 128) * sizeof(float), 256);
+  return round_up((round_up((size_t)b, 256) / 32) * round_up((size_t)B, 128) * sizeof(float), 256);   // rowsweep_kernel pads to 256 rows
 }
 // workspace of the sharded column-partials form (stats with c_part_all): the phase partials + the (b / 32) x B partials
 size_t stats_colpart_workspace_bytes(int b, int B, int D, int mode) {
   return core_workspace_bytes(b, B, D, mode) - colpart_bytes(b, B) + colpart_bytes(b, B, true);
 }
 
+static size_t rowsweep_extra_bytes(int b, int B) {
+  return round_up((size_t)kMaxSplit * round_up((size_t)b, 256) * sizeof(float2), 256) + round_up(round_up((size_t)B, 128) / 128 * sizeof(float), 256);
+}
 // rowgrad_kernel: row blocks of 256, tiles of 256 x 128; same cost model as choose_split (a job pays ~3 tiles of overhead)
-static Split choose_split_rows256(int b, int B) {
+static Split choose_split_rows256(int b, int B, int align = 1, double ovh = 3.0) {
   Split s;
   s.n_row_blocks = (b + 255) / 256;
   s.bpad = s.n_row_blocks * 256;
@@ -2028,10 +2387,20 @@ static Split choose_split_rows256(int b, int B) {
   int best = 1;
   double best_cost = 1e30;
   const int max_split = s.n_tiles < kMaxSplit ? s.n_tiles : kMaxSplit;
-  for (int ns = 1; ns <= max_split; ++ns) {
+  for (int ns = align; ns <= max_split; ns += align) {
     const int tps = (s.n_tiles + ns - 1) / ns;
-    const long jobs = (long)s.n_row_blocks * ns;
-    const double cost = (double)((jobs + npairs - 1) / npairs) * (tps + 3.0) + 0.04 * ns;
+    double cost = 0.04 * ns;
+    if (align > 1) {   // arrival-ordered launches: see choose_split
+      if (s.n_tiles % ns != 0 || s.n_row_blocks % align != 0) continue;
+      const long cb = s.n_row_blocks / align, cm = ns / align;
+      for (int k = 0; k < align; ++k) {
+        const long jobs = cb * (k + 1) * cm + (long)k * cb * cm;
+        cost += (double)((jobs + npairs - 1) / npairs) * (tps + ovh);
+      }
+    } else {
+      const long jobs = (long)s.n_row_blocks * ns;
+      cost += (double)((jobs + npairs - 1) / npairs) * (tps + ovh);
+    }
     if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
   }
   s.nsplit = best;
@@ -2047,6 +2416,7 @@ size_t core_workspace_bytes(int b, int B, int D, int /*mode*/) {
   Split s = choose_split(b, B, kOvhStats), sr = choose_split(b, B, kOvhRowLoss), sb = choose_split(b, B, kOvhBwd);
   (void)sr;
   size_t stats = (size_t)kMaxSplit * 4 * s.bpad * sizeof(float2);   // any split count (the chunked launches align theirs)
+  stats += rowsweep_extra_bytes(b, B);                               // rowsweep_kernel: row-LSE partials + per-tile min Z_jj
   size_t bwdp = (size_t)sb.nsplit * 2 * s.bpad * D * sizeof(float);
   {  // the split gradient: rowgrad_kernel's dT partials (row blocks of 256) + kBwdP's single (dT, dI) partial
     const size_t split_part = rowgrad_part_bytes(b, B, D) + (size_t)2 * s.bpad * D * sizeof(float);
@@ -2449,12 +2819,100 @@ static float* stats_colpart_ptr(const ClipProblem& p, int mode, void* ws, float*
     return reinterpret_cast<float*>(static_cast<char*>(ws) + core_workspace_bytes(p.b, p.B, p.D, mode) - colpart_bytes(p.b, p.B));
   return use_colpart(p.b, p.B) ? colpart_slot(ws, p.b, p.B, p.D) : nullptr;
 }
+// ---- statistics sweep on rowsweep_kernel (probe form with column partials, 3-pass engine, from 4096 x 4096 logits on)
+static bool rowsweep_ok(const ClipProblem& p, int mode, const float* colpart, int chunks) {
+  static const bool off = getenv("MAE_CLIP_STATS_ROWSWEEP") != nullptr && getenv("MAE_CLIP_STATS_ROWSWEEP")[0] == '0';
+  if (off || mode != MC_GEMM_TC_F16X3 || colpart == nullptr || p.tile_flags_out == nullptr) return false;
+  if ((double)p.b * (double)p.B < 4096.0 * 4096.0 || p.row_offset % 128 != 0) return false;
+  if (chunks > 1) {
+    Split s = choose_split_rows256(p.b, p.B, chunks, 2.0);
+    if (s.n_row_blocks % chunks != 0 || s.nsplit % chunks != 0 || s.n_tiles % s.nsplit != 0 || p.b != p.B) return false;
+  }
+  return true;
+}
+static float2* rowsweep_part(const ClipProblem& p, void* ws) {
+  Split s = choose_split(p.b, p.B, kOvhStats);
+  return reinterpret_cast<float2*>(static_cast<char*>(ws) + (size_t)kMaxSplit * 4 * s.bpad * sizeof(float2));
+}
+static float* rowsweep_tile_min(const ClipProblem& p, void* ws) {
+  return reinterpret_cast<float*>(reinterpret_cast<char*>(rowsweep_part(p, ws)) +
+                                  round_up((size_t)kMaxSplit * round_up((size_t)p.b, 256) * sizeof(float2), 256));
+}
+template <int KIND>
+static int launch_rowsweep(const ClipProblem& p, void* ws, float* colpart, int chunk_k, int chunks, cudaStream_t st) {
+  PlanesLayout l = planes_layout(p.B, p.D);
+  const char* base = static_cast<const char*>(p.planes_all);
+  const void* Xh = base + l.off_hi;
+  const void* Xl = base + l.off_lo;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map(&ma_hi, Xh, l.Bp, 2 * p.D, 128))) return rc;
+  if ((rc = make_map(&ma_lo, Xl, l.Bp, 2 * p.D, 128))) return rc;
+  if ((rc = make_map(&mb_hi, Xh, l.Bp, 2 * p.D, 64))) return rc;
+  if ((rc = make_map(&mb_lo, Xl, l.Bp, 2 * p.D, 64))) return rc;
+  const bool chunked = chunks > 1;
+  Split sp = choose_split_rows256(p.b, p.B, chunked ? chunks : 1, 2.0);
+  RowSweepParams rp;
+  rp.b = p.b; rp.B = p.B; rp.Bp = l.Bp; rp.D = p.D; rp.row_offset = p.row_offset;
+  rp.n_row_blocks = sp.n_row_blocks; rp.n_tiles = sp.n_tiles; rp.nsplit = sp.nsplit;
+  rp.tiles_per_split = sp.tiles_per_split; rp.bpad = sp.bpad;
+  rp.chunk_k = chunked ? chunk_k : -1;
+  rp.chunk_blocks = chunked ? sp.n_row_blocks / chunks : sp.n_row_blocks;
+  rp.chunk_m = chunked ? sp.nsplit / chunks : sp.nsplit;
+  rp.tri = (p.b == p.B && p.row_offset == 0) ? 1 : 0;
+  rp.inv_tau = 1.f / p.tau; rp.half_tau = 0.5f * p.tau;
+  rp.scale = reinterpret_cast<const float*>(base + l.off_hdr) + 1;
+  rp.part = rowsweep_part(p, ws);
+  rp.colpart = colpart;
+  rp.flags_out = p.tile_flags_out;
+  rp.norm_i = reinterpret_cast<const float*>(base + l.off_norm_i);
+  rp.norm_t = reinterpret_cast<const float*>(base + l.off_norm_t);
+  rp.tile_min_zjj2 = rowsweep_tile_min(p, ws);
+  auto kern = rowsweep_kernel<KIND>;
+  static std::atomic<unsigned long long> attr_done{0};
+  MC_CUDA(ensure_dynamic_smem(kern, kRsSmemBytes, attr_done));
+  long njobs = (long)sp.n_row_blocks * sp.nsplit;
+  if (rp.chunk_k >= 0) njobs = (long)rp.chunk_blocks * (rp.chunk_k + 1) * rp.chunk_m + (long)rp.chunk_k * rp.chunk_blocks * rp.chunk_m;
+  int npairs = num_sms() / 2;
+  if (njobs < npairs) npairs = (int)njobs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * npairs);
+  cfg.blockDim = dim3(kRsThreads);
+  cfg.dynamicSmemBytes = kRsSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MC_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, rp));
+  count_launch();
+  return MC_OK;
+}
+
 int stats_begin(const ClipProblem& p, cudaStream_t st) {
   if (p.tile_flags_out) MC_CUDA(cudaMemsetAsync(p.tile_flags_out, 0, tile_flags_bytes(p.b, p.B), st));
   return MC_OK;
 }
 int stats_chunk(const ClipProblem& p, int mode, int k, int chunks, void* ws, cudaStream_t st, float* c_part_all) {
   ClipStatsAll none{nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* colpart_rs = stats_colpart_ptr(p, mode, ws, c_part_all);
+  if (rowsweep_ok(p, mode, colpart_rs, chunks)) {
+    // S statistics and the Z probe as two launches of rowsweep_kernel (large MMA shapes); the per-tile minima of Z_jj are
+    // recomputed at every arrival (the norms of a chunk's rows exist once it is staged)
+    PlanesLayout l = planes_layout(p.B, p.D);
+    const char* base = static_cast<const char*>(p.planes_all);
+    const int n_tiles = (int)(round_up((size_t)p.B, 128) / 128);
+    tile_min_zjj_kernel<<<n_tiles, 128, 0, st>>>(reinterpret_cast<const float*>(base + l.off_norm_i),
+                                                 reinterpret_cast<const float*>(base + l.off_norm_t), p.B, 0.5f * p.tau,
+                                                 rowsweep_tile_min(p, ws));
+    MC_LAUNCH_CHECK();
+    int rc = launch_rowsweep<kRsS>(p, ws, colpart_rs, k, chunks, st);
+    if (rc) return rc;
+    return launch_rowsweep<kRsZ>(p, ws, colpart_rs, k, chunks, st);
+  }
   return launch_phase<kStats>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st,
                               stats_colpart_ptr(p, mode, ws, c_part_all), k, chunks);
 }
@@ -2470,13 +2928,21 @@ int stats_end(const ClipProblem& p, int mode, int chunks, float* r_loc, float* c
       (rc = launch_phase<kStatsZ>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st, nullptr, -1, chunks)))
     return rc;
   Split sp = choose_split(p.b, p.B, kOvhStats, chunks);
+  const bool rs = rowsweep_ok(p, mode, colpart, chunks);
+  int col_groups = sp.bpad / 32;
+  if (rs) {   // r comes from rowsweep_kernel<kRsS>'s own partials (row blocks of 256, its own split)
+    Split sr = choose_split_rows256(p.b, p.B, chunks > 1 ? chunks : 1, 2.0);
+    rowsweep_finalize_kernel<<<(p.b + 255) / 256, 256, 0, st>>>(rowsweep_part(p, ws), sr.nsplit, sr.bpad, p.b, r_loc);
+    MC_LAUNCH_CHECK();
+    col_groups = sr.bpad / 32;
+  }
   stats_finalize_kernel<<<(p.b + 255) / 256, 256, 0, st>>>(static_cast<const float2*>(ws), sp.nsplit, sp.bpad, p.b,
-                                                          r_loc, colpart ? nullptr : c_loc, rz_loc, ps_loc);
+                                                          rs ? nullptr : r_loc, colpart ? nullptr : c_loc, rz_loc, ps_loc);
   MC_LAUNCH_CHECK();
   if (colpart) {
     // rows b .. bpad of the last row block wrote -inf partials; c_loc has B entries here (every column, over the owned rows)
     const int Bp = (int)round_up((size_t)p.B, 128);
-    colpart_merge_kernel<<<(p.B + 63) / 64, 256, 0, st>>>(colpart, sp.bpad / 32, Bp, p.B, c_loc);
+    colpart_merge_kernel<<<(p.B + 63) / 64, 256, 0, st>>>(colpart, col_groups, Bp, p.B, c_loc);
     MC_LAUNCH_CHECK();
   }
   return MC_OK;
