@@ -396,6 +396,7 @@ static int fused_run(const float* I, const float* T, int B, int D, float tau, in
     if (rows_k <= 0 || mc_clip_loss_workspace_bytes(rows_k, B, D, mode) > phase_bytes) n_strips = 1;
   }
   const int n_tiles = n_blocks;  // column tiles of B = row blocks of B
+  int last_strip_rows = B;
   // the stored-weights form needs tile flags (its dense kernel computes the softmax part only) and the 3-pass engine;
   // which form actually runs is decided on the device from the flag density (tc::bwd_gate)
   const bool stored = l.off_w != 0 && flags != nullptr && eff_mode(mode, D) == MC_GEMM_TC_F16X3;
@@ -420,6 +421,7 @@ static int fused_run(const float* I, const float* T, int B, int D, float tau, in
                              base + l.off_w + (size_t)row0 * Bp * 2, phase, phase_bytes,
                              static_cast<cudaStream_t>(stream), dI + (size_t)row0 * D)))
         return rc;
+      last_strip_rows = rows;
       trace_mark("bwd rows strip", k, static_cast<cudaStream_t>(stream));
       if (hook && (rc = hook->fn(hook->ctx, row0, rows, 1))) return rc;
     } else {
@@ -441,7 +443,8 @@ static int fused_run(const float* I, const float* T, int B, int D, float tau, in
       const int j1 = n_strips == 1 ? B : (strip_first[k + 1] * 128 <= B ? strip_first[k + 1] * 128 : B);
       if ((rc = tc::bwd_cols(p, eff_mode(mode, D), s, nullptr, base + l.off_w, B, 0, j0, j1,
                              reinterpret_cast<const float*>(base + l.off_diz) + (size_t)j0 * D, dI + (size_t)j0 * D,
-                             base + l.off_cols, l.cols_bytes, static_cast<cudaStream_t>(stream))))
+                             base + l.off_cols, l.cols_bytes, static_cast<cudaStream_t>(stream),
+                             tc::bwd_rows_wscale(phase, last_strip_rows, B, D))))
         return rc;
       trace_mark("bwd cols strip", k, static_cast<cudaStream_t>(stream));
       if (hook && (rc = hook->fn(hook->ctx, j0, j1 - j0, 2))) return rc;

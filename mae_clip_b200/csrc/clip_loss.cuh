@@ -73,8 +73,10 @@ size_t bwd_cols_workspace_bytes(int w_rows, int n_cols, int D);
 int bwd_rows(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, float* dT_loc, float* dIz_loc,
              void* W_rows, void* ws, size_t ws_bytes, cudaStream_t st, float* dI_loc_ownrows = nullptr);
 int bwd_gate(const uint8_t* flags, size_t n_flags, int* gate_out, cudaStream_t st);
+const float* bwd_rows_wscale(void* ws, int b, int B, int D);   // where bwd_rows(ws, strip of b rows) left the weight scale
 int bwd_cols(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, const void* W, int w_rows,
-             int w_row_offset, int j0, int j1, const float* dIz, float* dI_out, void* ws, size_t ws_bytes, cudaStream_t st);
+             int w_row_offset, int j0, int j1, const float* dIz, float* dI_out, void* ws, size_t ws_bytes, cudaStream_t st,
+             const float* wscale_ready = nullptr);
 int ranks_lse_merge(const float* parts, int n, int64_t stride, int B, float* c, cudaStream_t st);
 int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* ps_loc, float* g_loc,
             float* q_loc, float* loss_part, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -3070,7 +3070,7 @@ int bwd(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad
     rc = bwd_rows(pg, mode, s, grad_loss, dT, reinterpret_cast<float*>(base + sl.off_diz), base + sl.off_w, ws, sl.off_w, st, dI);
     if (rc) return rc;
     return bwd_cols(pg, mode, s, grad_loss, base + sl.off_w, p.B, 0, 0, p.B, reinterpret_cast<const float*>(base + sl.off_diz), dI,
-                    base + sl.off_cols, sl.cols_bytes, st);
+                    base + sl.off_cols, sl.cols_bytes, st, wscale_slot(ws, p.b, p.B, p.D));
   }
   PlanesLayout l = planes_layout(p.B, p.D);
   const char* pbase = static_cast<const char*>(p.planes_all);
@@ -3120,6 +3120,7 @@ static ColSplit choose_col_split(int w_rows, int n_cols) {
   c.steps_per_split = (c.steps + best - 1) / best;
   return c;
 }
+const float* bwd_rows_wscale(void* ws, int b, int B, int D) { return wscale_slot(ws, b, B, D); }
 size_t stored_weights_bytes(int b, int B) { return round_up(round_up((size_t)b, 256) * round_up((size_t)B, 128) * sizeof(__half), 256); }
 size_t bwd_cols_workspace_bytes(int /*w_rows*/, int n_cols, int D) {
   return round_up((size_t)kCgMaxSplit * ((size_t)(n_cols + 255) / 256 * 256) * D * sizeof(float), 256) + 256;
@@ -3199,7 +3200,16 @@ static int launch_rowgrad(const ClipProblem& p, int mode, const ClipStatsAll& s,
 __global__ void __launch_bounds__(1024) bwd_gate_kernel(const uint8_t* __restrict__ flags, size_t n, float thresh, int* __restrict__ gate) {
   __shared__ unsigned int sm[32];
   unsigned int cnt = 0;
-  for (size_t i = threadIdx.x; i < n; i += blockDim.x) cnt += flags[i] != 0;
+  size_t i0 = 0;
+  if ((reinterpret_cast<uintptr_t>(flags) & 15) == 0) {   // 16 flags per load
+    const size_t n16 = n >> 4;
+    for (size_t i = threadIdx.x; i < n16; i += blockDim.x) {
+      const uint4 v = reinterpret_cast<const uint4*>(flags)[i];
+      cnt += (__popc(__vcmpne4(v.x, 0u)) + __popc(__vcmpne4(v.y, 0u)) + __popc(__vcmpne4(v.z, 0u)) + __popc(__vcmpne4(v.w, 0u))) >> 3;
+    }
+    i0 = n16 << 4;
+  }
+  for (size_t i = i0 + threadIdx.x; i < n; i += blockDim.x) cnt += flags[i] != 0;
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = cnt;
   __syncthreads();
@@ -3272,7 +3282,8 @@ int bwd_rows(const ClipProblem& p, int mode, const ClipStatsAll& s, const float*
 // global row w_row_offset): dI_out[j - j0] = scale (dIz[j - j0] + sum_i W_ij T_i).  dIz may be null (a rank that does
 // not own those rows contributes the W part only).
 int bwd_cols(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, const void* W, int w_rows,
-             int w_row_offset, int j0, int j1, const float* dIz, float* dI_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+             int w_row_offset, int j0, int j1, const float* dIz, float* dI_out, void* ws, size_t ws_bytes, cudaStream_t st,
+             const float* wscale_ready) {
   (void)mode;
   MC_REQUIRE(supported(p.D), MC_ERR_UNSUPPORTED, "clip_bwd_cols: D %d", p.D);
   MC_REQUIRE(j0 % 128 == 0 && j0 >= 0 && j1 > j0 && j1 <= p.B && w_rows > 0 && w_row_offset % 64 == 0, MC_ERR_BAD_ARG,
@@ -3288,8 +3299,14 @@ int bwd_cols(const ClipProblem& p, int mode, const ClipStatsAll& s, const float*
   if ((rc = make_map(&mt, base + l.off_hiT, 2 * p.D, l.Bp, p.D / 2))) return rc;
   ColSplit cs = choose_col_split(w_rows_pad, j1 - j0);
   const size_t part_bytes = round_up((size_t)kCgMaxSplit * ((size_t)cs.n_jblocks * 256) * p.D * sizeof(float), 256);
-  float* wsc = reinterpret_cast<float*>(static_cast<char*>(ws) + part_bytes);
-  if ((rc = launch_wscale(p, s, wsc, st))) return rc;
+  // the power-of-two scale of the stored weights: the row half's own word when the caller still has it (same stream),
+  // else recomputed from the statistics (deterministic: the same value)
+  const float* wsc = wscale_ready;
+  if (wsc == nullptr) {
+    float* w2 = reinterpret_cast<float*>(static_cast<char*>(ws) + part_bytes);
+    if ((rc = launch_wscale(p, s, w2, st))) return rc;
+    wsc = w2;
+  }
   ColGradParams cp;
   cp.Bp = l.Bp; cp.D = p.D; cp.w_rows = w_rows_pad; cp.row_offset = w_row_offset;
   cp.j_first = j0; cp.n_jblocks = cs.n_jblocks; cp.j_end = j1;
