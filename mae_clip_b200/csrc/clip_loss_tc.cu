@@ -3314,8 +3314,10 @@ int bwd_cols(const ClipProblem& p, int mode, const ClipStatsAll& s, const float*
   cp.part = static_cast<float*>(ws);
   cp.gate = p.gate;
   const int smem = kCgStages * (kCgStageA + (p.D / 2) * 128) + 8 * 32 + 16 + 1024;
+  // the opt-in is set once per device: ask for the largest layout (D = 256) whatever this call's width is
+  const int smem_max = kCgStages * (kCgStageA + 128 * 128) + 8 * 32 + 16 + 1024;
   static std::atomic<unsigned long long> attr_done{0};
-  MC_CUDA(ensure_dynamic_smem(colgrad_kernel, smem, attr_done));
+  MC_CUDA(ensure_dynamic_smem(colgrad_kernel, smem_max, attr_done));
   const long njobs = (long)cs.n_jblocks * cs.ksplit;
   int npairs = num_sms() / 2;
   if (njobs < npairs) npairs = (int)njobs;

@@ -199,6 +199,34 @@ class _GlobalClipLoss(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # peer-memory transport
 # ------------------------------------------------------------------------------------------------
+class _Trace:
+    """MAE_CLIP_PEER_TRACE=1: a CUDA event after every exchange / sweep call of a PeerStep, printed as a timeline (ms since
+    the step's first mark) by rank 0 - the substitute for an nsys timeline of the multi-GPU step."""
+
+    def __init__(self):
+        self.on = os.environ.get("MAE_CLIP_PEER_TRACE", "0") == "1"
+        self.marks = []
+
+    def mark(self, label):
+        if self.on:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((label, e))
+
+    def dump(self, rank):
+        if not self.on or not self.marks:
+            return
+        torch.cuda.synchronize()
+        if rank == 0:
+            t0 = self.marks[0][1]
+            prev = 0.0
+            for label, e in self.marks:
+                t = t0.elapsed_time(e)
+                print(f"[peer trace] {t:8.3f} ms  (+{t - prev:6.3f})  {label}", flush=True)
+                prev = t
+        self.marks = []
+
+
 class PeerStep:
     """One forward (+ backward) of the row-sharded loss over a ``PeerExchange``: every exchange step
     is a kernel of libmae_clip_b200.so on the caller's stream.  Shared by the autograd Function
@@ -228,6 +256,7 @@ class PeerStep:
         if self.bwd_form not in ("stored", "ownrows"):
             raise ValueError(f"unknown MAE_CLIP_PEER_BWD {self.bwd_form!r}")
         self._stored = None   # (W strip, zero-padded dIz, column-half workspace): allocated on the first backward
+        self.trace = _Trace()
 
     def forward(self, I_loc, T_loc, tau, events=None):
         ex, mode, L = self.ex, self.mode, lib()
@@ -244,6 +273,7 @@ class PeerStep:
         with torch.cuda.device(dev):
             st = cur_stream()
             mark()
+            self.trace.mark("forward")
             pull = self.exchange_mode == "pull"
             shard = rank * b * D * 4
             if pull:
@@ -251,17 +281,22 @@ class PeerStep:
                 # amax to every rank's slot
                 check(L.mc_clip_amax(ptr(I_loc), ptr(T_loc), b, D, ex.local(ex.off_emb_i + shard),
                                      ex.local(ex.off_emb_t + shard), ex.local(ex.OFF_AMAX_LOCAL), st), "mc_clip_amax")
+                self.trace.mark("mc_clip_amax")
                 ex.publish(ex.local(ex.OFF_AMAX_LOCAL), 1, 1, 0, ex.OFF_AMAX_SLOTS, 0, rank)
+                self.trace.mark("ex.publish")
             else:
                 # posted stores of our shards into every rank's image of the batch + amax, one kernel
                 check(L.mc_clip_push_shards(ptr(I_loc), ptr(T_loc), b, D, rank, world, ex.table(ex.off_emb_i),
                                             ex.table(ex.off_emb_t), ex.table(ex.OFF_AMAX_SLOTS),
                                             ex.local(ex.OFF_PUSH_SCRATCH), st), "mc_clip_push_shards")
+                self.trace.mark("mc_clip_push_shards")
             ex.barrier()
+            self.trace.mark("barrier")
             planes = torch.empty(L.mc_clip_planes_bytes(B, D, mode), device=dev, dtype=torch.uint8)
             tab_i, tab_t = ex.row_tables(pull)
             check(L.mc_clip_prepare_peers(tab_i, tab_t, world, b, D, mode, ex.local(ex.OFF_AMAX_SLOTS), ptr(planes), st),
                   "mc_clip_prepare_peers")
+            self.trace.mark("mc_clip_prepare_peers")
             mark()
             nws = max(L.mc_clip_loss_workspace_bytes(b, B, D, mode),
                       L.mc_clip_stats_colpart_workspace_bytes(b, B, D, mode) if self.colpart else 0)
@@ -274,35 +309,50 @@ class PeerStep:
                 check(L.mc_clip_stats_colpart(ptr(planes), b, B, D, rank * b, float(tau), mode, ptr(loc[0]), ptr(cpart),
                                               ptr(loc[2]), ptr(loc[3]), ptr(flags_raw), ptr(ws), ws.numel(), st),
                       "mc_clip_stats_colpart")
+                self.trace.mark("mc_clip_stats_colpart")
                 ex.publish(ptr(loc[0]), 2, b, 2 * b, ex.OFF_VECS, 2 * ex.vec_stride, rank * b)   # r -> vector 0, rz -> vector 2
+                self.trace.mark("ex.publish")
                 ex.publish(ptr(cpart), 1, B, 0, ex.off_cpart, 0, rank * ex.vec_stride)
+                self.trace.mark("ex.publish")
             else:
                 check(L.mc_clip_stats(None, None, ptr(planes), b, B, D, rank * b, float(tau), mode, ptr(loc[0]), ptr(loc[1]),
                                       ptr(loc[2]), ptr(loc[3]), ptr(flags_raw), ptr(ws), ws.numel(), st), "mc_clip_stats")
+                self.trace.mark("mc_clip_stats")
                 ex.publish(ptr(loc), 3, b, b, ex.OFF_VECS, ex.vec_stride, rank * b)
+                self.trace.mark("ex.publish")
             if nf:  # this rank's rows of the tile-flag bitmap, to every rank
                 ex.publish(ptr(flags_raw), 1, nf // 4, 0, ex.off_flags, 0, rank * (nf // 4))
+                self.trace.mark("ex.publish")
             ex.barrier()
+            self.trace.mark("barrier")
             if self.colpart:   # every rank's partial vector has landed: fold them into c (the region's local c vector)
                 check(L.mc_clip_colpart_merge(ex.local(ex.off_cpart), world, ex.vec_stride, B, ex.vec(1), st),
                       "mc_clip_colpart_merge")
+                self.trace.mark("mc_clip_colpart_merge")
             flags = None
             if nf:
                 flags = torch.empty(nf, device=dev, dtype=torch.uint8)
                 check(L.mc_clip_flags_finalize(ex.local(ex.off_flags), B, b, rank * b, ptr(flags), st),
                       "mc_clip_flags_finalize")
+                self.trace.mark("mc_clip_flags_finalize")
             mark()
             check(L.mc_clip_rowloss(None, None, ptr(planes), b, B, D, rank * b, float(tau), mode, ex.vec(0), ex.vec(1),
                                     ex.vec(2), ptr(loc[3]), ptr(loc[4]), ptr(loc[5]), ex.local(ex.OFF_PART_LOCAL),
                                     ptr(flags), ptr(ws), ws.numel(), st), "mc_clip_rowloss")
+            self.trace.mark("mc_clip_rowloss")
             ex.publish(ptr(loc[4]), 2, b, b, ex.OFF_VECS + 4 * 3 * ex.vec_stride, ex.vec_stride, rank * b)
+            self.trace.mark("ex.publish")
             ex.publish(ex.local(ex.OFF_PART_LOCAL), 1, 1, 0, ex.OFF_PART_SLOTS, 0, rank)
+            self.trace.mark("ex.publish")
             ex.barrier()
+            self.trace.mark("barrier")
             # out of the region: backward (and a second forward before it) never touch peer memory
             vecs = torch.empty(5, B, **f32)
             parts = torch.empty(18, **f32)   # 16 partial slots + the barrier's {epoch, error} words, one copy
             ex.copy_out(ex.OFF_VECS, 5, B, ex.vec_stride, vecs, B)
+            self.trace.mark("ex.copy_out")
             ex.copy_out(ex.OFF_PART_SLOTS, 1, 18, 0, parts, 0)
+            self.trace.mark("ex.copy_out")
             # a barrier that gave up on a peer (peer.py, "Skew between ranks") makes the step's loss NaN instead of
             # silently wrong; no host synchronisation here - PeerExchange.check() names the missing rank
             loss = torch.where(parts.view(torch.int32)[17] != 0, parts.new_full((), float("nan")), parts[:world].sum())
@@ -334,26 +384,34 @@ class PeerStep:
                 # rank holds it after the forward exchange), so all ranks take the same branch
                 nt = (B + 127) // 128
                 check(L.mc_clip_bwd_gate(ex.local(ex.off_flags), nt * nt, ptr(gate), st), "mc_clip_bwd_gate")
+                self.trace.mark("mc_clip_bwd_gate")
                 gp = gate
                 check(L.mc_clip_bwd_rows(ptr(planes), b, B, D, row0, float(tau), mode, ptr(vecs[0]), ptr(vecs[1]),
                                          ptr(vecs[2]), ptr(vecs[3]), ptr(vecs[4]), ptr(gl), ptr(dT), ptr(diz[row0:]), ptr(W),
                                          ptr(flags), ptr(gp), ptr(dI), ptr(ws), ws.numel(), st), "mc_clip_bwd_rows")
+                self.trace.mark("mc_clip_bwd_rows")
                 # our contribution to every row of dI goes where the peers can read it: the (B, D) image of I in the
                 # exchange region is dead once the planes are staged
                 check(L.mc_clip_bwd_cols(ptr(planes), B, D, float(tau), mode, ptr(vecs[0]), ptr(vecs[1]), ptr(vecs[2]),
                                          ptr(vecs[4]), ptr(gl), ptr(W), b, row0, 0, B, ptr(diz), ex.local(ex.off_emb_i),
                                          ptr(gp), ptr(wsc), wsc.numel(), st), "mc_clip_bwd_cols")
+                self.trace.mark("mc_clip_bwd_cols")
                 ex.barrier()
+                self.trace.mark("barrier")
                 ex.reduce_rows(ex.off_emb_i + row0 * D * 4, b * D, dI, gp)
+                self.trace.mark("ex.reduce_rows")
                 ex.barrier()   # nobody pushes the next step's shards into an image a peer is still reading
+                self.trace.mark("barrier")
             else:
                 check(L.mc_clip_bwd(None, None, ptr(planes), b, B, D, ex.rank * b, float(tau), mode, ptr(vecs[0]),
                                     ptr(vecs[1]), ptr(vecs[2]), ptr(vecs[3]), ptr(vecs[4]), ptr(gl), ptr(dI), ptr(dT),
                                     ptr(flags), ptr(ws), ws.numel(), cur_stream()), "mc_clip_bwd")
+                self.trace.mark("mc_clip_bwd")
             if events is not None:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()
                 events.append(e)
+            self.trace.dump(ex.rank)
         return dI, dT
 
 

@@ -658,6 +658,23 @@ def test_stored_weights_gradient_small_and_ragged_shapes(B, b, scale):
         assert rel_err(dI, ref_dI) < GRAD_TOL and rel_err(dT, ref_dT) < GRAD_TOL, (gated, rel_err(dI, ref_dI), rel_err(dT, ref_dT))
 
 
+@pytest.mark.parametrize("B,D,scale", [(4096, 128, 1.0), (4096, 256, 1.0), (4224, 128, 0.3)])
+def test_large_tile_kernels_at_their_smallest_size(B, D, scale):
+    """From 4096 x 4096 logits on the fused step runs rowsweep_kernel (statistics) and rowgrad_kernel + colgrad_kernel
+    (stored-weights gradient): both embedding widths of the tcgen05 engine, a batch that is not a multiple of 256, and
+    a batch whose soft targets are not concentrated (the device-side gate then takes the own-rows sweep) against the
+    closed-form fp64 oracle."""
+    import mae_clip_b200 as m
+    I = loss_ref.make_embeddings(B, D, seed=41, scale=scale)
+    T = loss_ref.make_embeddings(B, D, seed=42, scale=scale)
+    Ic, Tc = I.cuda().requires_grad_(True), T.cuda().requires_grad_(True)
+    loss = m.clip_contrastive_loss(Ic, Tc, 1.0, mode="tc_f16x3")
+    loss.backward()
+    ref_loss, ref_dI, ref_dT, _ = loss_ref.clip_loss_closed_form(I.numpy(), T.numpy(), 1.0)
+    assert abs(loss.item() - ref_loss) <= LOSS_TOL * abs(ref_loss)
+    assert rel_err(Ic.grad, ref_dI) < GRAD_TOL and rel_err(Tc.grad, ref_dT) < GRAD_TOL
+
+
 # ------------------------------------------------------------------ autograd plumbing (round-1 advisor findings)
 def test_fp32_fma_engine_state_survives_other_ops_between_forward_and_backward():
     """The fp32 FMA engine keeps its S / S^T / Z strips from the statistics sweep to the gradient sweep.  Through the
