@@ -197,7 +197,7 @@ size_t mc_clip_bwd_cols_workspace_bytes(int n_cols, int D);
  * own-rows sweep is cheaper.  mc_clip_bwd_gate writes the choice into a device word from the flags of ALL row blocks
  * (1 = stored, 0 = own rows; break-even at 15% flagged tiles, MAE_CLIP_BWD_GATE overrides); given that word, the calls
  * below enqueue the kernels of BOTH forms and the ones of the other form return at once - no host synchronisation.
- * gate NULL = the stored form unconditionally.  A gated mc_clip_bwd_rows needs tile flags, the 3-pass engine and
+ * gate NULL = the stored form unconditionally.  A gated mc_clip_bwd_rows needs tile flags and
  * dI_loc_ownrows (where the own-rows form writes this strip's dI); mc_peer_reduce takes the same word. */
 int mc_clip_bwd_gate(const uint8_t* tile_flags_all, size_t n_flags, int* gate_out, void* stream);
 int mc_clip_bwd_rows(const void* planes_all, int b, int B, int D, int row_offset, float tau, int mode,

@@ -399,7 +399,7 @@ static int fused_run(const float* I, const float* T, int B, int D, float tau, in
   int last_strip_rows = B;
   // the stored-weights form needs tile flags (its dense kernel computes the softmax part only) and the 3-pass engine;
   // which form actually runs is decided on the device from the flag density (tc::bwd_gate)
-  const bool stored = l.off_w != 0 && flags != nullptr && eff_mode(mode, D) == MC_GEMM_TC_F16X3;
+  const bool stored = l.off_w != 0 && flags != nullptr && eff_mode(mode, D) != MC_GEMM_SIMT_FP32;
   int* gate = nullptr;
   if (stored) {
     gate = reinterpret_cast<int*>(base + l.off_vec + 6 * l.vec_stride);

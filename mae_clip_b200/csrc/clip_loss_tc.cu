@@ -1647,6 +1647,7 @@ struct RowGradParams {
   __half* wout;           // (bpad x Bp)
   const int* gate;        // runs only while *gate == 1 (null: always)
 };
+template <int PASSES>
 __global__ void __launch_bounds__(kRgThreads, 1)
 rowgrad_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -1715,10 +1716,10 @@ rowgrad_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint32_t slot = it % kRgSlots, par = (it / kRgSlots) & 1;
             mbar_wait(bar(kRgEmpty0 + slot), par ^ 1);
             const uint32_t fb = bar(kRgFull0 + slot), sb = base + kRgOffRing + slot * kRgSlotBytes;
-            if (leader) mbar_arrive_expect_tx(fb, 2u * kRgSlotBytes);
-            tma_load_2d_pair(sb, &map_a_lo, fb, D + c * 64, row_a);            // T_i lo   (128 rows)
+            if (leader) mbar_arrive_expect_tx(fb, PASSES == 3 ? 2u * kRgSlotBytes : 2u * 8192u);
+            if (PASSES == 3) tma_load_2d_pair(sb, &map_a_lo, fb, D + c * 64, row_a);            // T_i lo   (128 rows)
             tma_load_2d_pair(sb + 16384, &map_b_hi, fb, c * 64, j0);           // I_j hi   (64 rows)
-            tma_load_2d_pair(sb + 24576, &map_b_lo, fb, c * 64, j0);           // I_j lo
+            if (PASSES == 3) tma_load_2d_pair(sb + 24576, &map_b_lo, fb, c * 64, j0);           // I_j lo
           }
         }
       }
@@ -1817,9 +1818,11 @@ rowgrad_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t kT = desc_advance_k(aT, ks), kb = desc_advance_k(bI, ks);
-              mma_f16_pair(tS, kT, kb, idesc_s, (c > 0 || ks > 0) ? 1u : 0u);      // S = T_i I_j^T, three passes
-              mma_f16_pair(tS, kT, desc_advance_k(bIl, ks), idesc_s, 1u);
-              mma_f16_pair(tS, desc_advance_k(aTl, ks), kb, idesc_s, 1u);
+              mma_f16_pair(tS, kT, kb, idesc_s, (c > 0 || ks > 0) ? 1u : 0u);      // S = T_i I_j^T, three passes (or one)
+              if (PASSES == 3) {
+                mma_f16_pair(tS, kT, desc_advance_k(bIl, ks), idesc_s, 1u);
+                mma_f16_pair(tS, desc_advance_k(aTl, ks), kb, idesc_s, 1u);
+              }
             }
             mma_commit_pair(bar(kRgEmpty0 + slot), 3);
           }
@@ -1982,7 +1985,7 @@ __device__ __forceinline__ void rs_tiles(const RowSweepParams& p, int rb, int sp
   t1 = min(t0 + p.tiles_per_split, p.n_tiles);
   if (KIND == kRsZ && p.tri) t0 = max(t0, 2 * rb);
 }
-template <int KIND>
+template <int KIND, int PASSES>
 __global__ void __launch_bounds__(kRsThreads, 1)
 rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -2049,11 +2052,11 @@ rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
             mbar_wait(bar(kRsEmpty0 + slot), par ^ 1);
             const uint32_t fb = bar(kRsFull0 + slot), sb = base + kOffRing + slot * kSlotBytes_;
-            if (leader) mbar_arrive_expect_tx(fb, 2u * kSlotBytes_);
+            if (leader) mbar_arrive_expect_tx(fb, (KIND == kRsS && PASSES != 3) ? 2u * 8192u : 2u * kSlotBytes_);
             if (KIND == kRsS) {
-              tma_load_2d_pair(sb, &map_a_lo, fb, D + c * 64, row_a);            // T_i lo   (128 rows)
+              if (PASSES == 3) tma_load_2d_pair(sb, &map_a_lo, fb, D + c * 64, row_a);            // T_i lo   (128 rows)
               tma_load_2d_pair(sb + 16384, &map_b_hi, fb, c * 64, j0);           // I_j hi   (64 rows)
-              tma_load_2d_pair(sb + 24576, &map_b_lo, fb, c * 64, j0);           // I_j lo
+              if (PASSES == 3) tma_load_2d_pair(sb + 24576, &map_b_lo, fb, c * 64, j0);           // I_j lo
             } else {
               tma_load_2d_pair(sb, &map_b_hi, fb, c * 64, j0);                   // I_j hi
               tma_load_2d_pair(sb + 8192, &map_b_hi, fb, D + c * 64, j0);        // T_j hi
@@ -2092,8 +2095,10 @@ rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
               for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t kT = desc_advance_k(aT, ks), kb = desc_advance_k(bI, ks);
                 mma_f16_pair(tD, kT, kb, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-                mma_f16_pair(tD, kT, desc_advance_k(bIl, ks), idesc, 1u);
-                mma_f16_pair(tD, desc_advance_k(aTl, ks), kb, idesc, 1u);
+                if (PASSES == 3) {
+                  mma_f16_pair(tD, kT, desc_advance_k(bIl, ks), idesc, 1u);
+                  mma_f16_pair(tD, desc_advance_k(aTl, ks), kb, idesc, 1u);
+                }
               }
             } else {
               const uint64_t aI = smem_desc_sw128(base + c * 16384), aT = smem_desc_sw128(base + (nkc + c) * 16384);
@@ -2843,7 +2848,7 @@ static float* stats_colpart_ptr(const ClipProblem& p, int mode, void* ws, float*
 // ---- statistics sweep on rowsweep_kernel (probe form with column partials, 3-pass engine, from 4096 x 4096 logits on)
 static bool rowsweep_ok(const ClipProblem& p, int mode, const float* colpart, int chunks) {
   static const bool off = getenv("MAE_CLIP_STATS_ROWSWEEP") != nullptr && getenv("MAE_CLIP_STATS_ROWSWEEP")[0] == '0';
-  if (off || mode != MC_GEMM_TC_F16X3 || colpart == nullptr || p.tile_flags_out == nullptr) return false;
+  if (off || (mode != MC_GEMM_TC_F16X3 && mode != MC_GEMM_TC_F16) || colpart == nullptr || p.tile_flags_out == nullptr) return false;
   if ((double)p.b * (double)p.B < 4096.0 * 4096.0 || p.row_offset % 128 != 0) return false;
   if (chunks > 1) {
     Split s = choose_split_rows256(p.b, p.B, chunks, 2.0);
@@ -2859,7 +2864,7 @@ static float* rowsweep_tile_min(const ClipProblem& p, void* ws) {
   return reinterpret_cast<float*>(reinterpret_cast<char*>(rowsweep_part(p, ws)) +
                                   round_up((size_t)kMaxSplit * round_up((size_t)p.b, 256) * sizeof(float2), 256));
 }
-template <int KIND>
+template <int KIND, int PASSES>
 static int launch_rowsweep(const ClipProblem& p, void* ws, float* colpart, int chunk_k, int chunks, cudaStream_t st) {
   PlanesLayout l = planes_layout(p.B, p.D);
   const char* base = static_cast<const char*>(p.planes_all);
@@ -2889,7 +2894,7 @@ static int launch_rowsweep(const ClipProblem& p, void* ws, float* colpart, int c
   rp.norm_i = reinterpret_cast<const float*>(base + l.off_norm_i);
   rp.norm_t = reinterpret_cast<const float*>(base + l.off_norm_t);
   rp.tile_min_zjj2 = rowsweep_tile_min(p, ws);
-  auto kern = rowsweep_kernel<KIND>;
+  auto kern = rowsweep_kernel<KIND, PASSES>;
   static std::atomic<unsigned long long> attr_done{0};
   MC_CUDA(ensure_dynamic_smem(kern, kRsSmemBytes, attr_done));
   long njobs = (long)sp.n_row_blocks * sp.nsplit;
@@ -2930,9 +2935,10 @@ int stats_chunk(const ClipProblem& p, int mode, int k, int chunks, void* ws, cud
                                                  reinterpret_cast<const float*>(base + l.off_norm_t), p.B, 0.5f * p.tau,
                                                  rowsweep_tile_min(p, ws));
     MC_LAUNCH_CHECK();
-    int rc = launch_rowsweep<kRsS>(p, ws, colpart_rs, k, chunks, st);
+    int rc = mode == MC_GEMM_TC_F16X3 ? launch_rowsweep<kRsS, 3>(p, ws, colpart_rs, k, chunks, st)
+                                      : launch_rowsweep<kRsS, 1>(p, ws, colpart_rs, k, chunks, st);
     if (rc) return rc;
-    return launch_rowsweep<kRsZ>(p, ws, colpart_rs, k, chunks, st);
+    return launch_rowsweep<kRsZ, 3>(p, ws, colpart_rs, k, chunks, st);   // the probe reads the hi planes only in either engine
   }
   return launch_phase<kStats>(mode, p, none, nullptr, static_cast<float*>(ws), nullptr, st,
                               stats_colpart_ptr(p, mode, ws, c_part_all), k, chunks);
@@ -3052,7 +3058,7 @@ int rowloss(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* 
 int bwd(const ClipProblem& p, int mode, const ClipStatsAll& s, const float* grad_loss, float* dI, float* dT, void* ws,
         size_t ws_bytes, cudaStream_t st) {
   const bool use_stored = p.b == p.B && p.row_offset == 0 && stored_form_enabled(p.b, p.B, p.D) && p.tile_flags != nullptr &&
-                          mode == MC_GEMM_TC_F16X3;
+                          (mode == MC_GEMM_TC_F16X3 || mode == MC_GEMM_TC_F16);
   MC_REQUIRE(ws_bytes >= (use_stored ? workspace_bytes(p.b, p.B, p.D, mode) : core_workspace_bytes(p.b, p.B, p.D, mode)),
              MC_ERR_WORKSPACE, "clip_bwd(tc): workspace too small");
   MC_REQUIRE(aligned(dI, 16) && aligned(dT, 16), MC_ERR_ALIGN, "clip_bwd(tc): gradients must be 16-byte aligned");
@@ -3147,7 +3153,6 @@ bool stored_form_enabled(int b, int B, int D) {
 
 static int launch_rowgrad(const ClipProblem& p, int mode, const ClipStatsAll& s, float* part, const float* wscale,
                           __half* wout, cudaStream_t st) {
-  MC_REQUIRE(mode == MC_GEMM_TC_F16X3, MC_ERR_UNSUPPORTED, "rowgrad: the split gradient belongs to the 3-pass engine");
   MC_REQUIRE(p.row_offset % 128 == 0, MC_ERR_UNSUPPORTED, "rowgrad: row_offset %% 128 != 0 (%d)", p.row_offset);
   PlanesLayout l = planes_layout(p.B, p.D);
   const char* base = static_cast<const char*>(p.planes_all);
@@ -3172,8 +3177,10 @@ static int launch_rowgrad(const ClipProblem& p, int mode, const ClipStatsAll& s,
   rp.part = part;
   rp.wout = wout;
   rp.gate = p.gate;
-  static std::atomic<unsigned long long> attr_done{0};
-  MC_CUDA(ensure_dynamic_smem(rowgrad_kernel, kRgSmemBytes, attr_done));
+  const bool three = mode == MC_GEMM_TC_F16X3;
+  static std::atomic<unsigned long long> attr_done3{0}, attr_done1{0};
+  if (three) MC_CUDA(ensure_dynamic_smem(rowgrad_kernel<3>, kRgSmemBytes, attr_done3));
+  else MC_CUDA(ensure_dynamic_smem(rowgrad_kernel<1>, kRgSmemBytes, attr_done1));
   const long njobs = (long)sp.n_row_blocks * sp.nsplit;
   int npairs = num_sms() / 2;
   if (njobs < npairs) npairs = (int)njobs;
@@ -3189,7 +3196,8 @@ static int launch_rowgrad(const ClipProblem& p, int mode, const ClipStatsAll& s,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MC_CUDA(cudaLaunchKernelEx(&cfg, rowgrad_kernel, ma_hi, ma_lo, mb_hi, mb_lo, mt, rp));
+  if (three) MC_CUDA(cudaLaunchKernelEx(&cfg, rowgrad_kernel<3>, ma_hi, ma_lo, mb_hi, mb_lo, mt, rp));
+  else MC_CUDA(cudaLaunchKernelEx(&cfg, rowgrad_kernel<1>, ma_hi, ma_lo, mb_hi, mb_lo, mt, rp));
   count_launch();
   return MC_OK;
 }
@@ -3244,7 +3252,7 @@ int bwd_rows(const ClipProblem& p, int mode, const ClipStatsAll& s, const float*
   // (soft-target part on the flagged tiles).  Without flags every tile carries soft-target mass and kBwdW does both at
   // once.  MAE_CLIP_BWD_SPLIT=0 keeps the single sweep (A/B switch).
   static const bool split_off = getenv("MAE_CLIP_BWD_SPLIT") != nullptr && getenv("MAE_CLIP_BWD_SPLIT")[0] == '0';
-  if (p.tile_flags != nullptr && !split_off && mode == MC_GEMM_TC_F16X3) {
+  if (p.tile_flags != nullptr && !split_off && (mode == MC_GEMM_TC_F16X3 || mode == MC_GEMM_TC_F16)) {
     Split sr = choose_split_rows256(p.b, p.B), sp = choose_split(p.b, p.B, kOvhBwd);
     float* part_r = static_cast<float*>(ws);
     float* part_p = reinterpret_cast<float*>(static_cast<char*>(ws) + rowgrad_part_bytes(p.b, p.B, p.D));
@@ -3267,7 +3275,7 @@ int bwd_rows(const ClipProblem& p, int mode, const ClipStatsAll& s, const float*
     }
     return MC_OK;
   }
-  MC_REQUIRE(p.gate == nullptr, MC_ERR_BAD_ARG, "clip_bwd_rows: the form switch needs tile flags and the 3-pass engine");
+  MC_REQUIRE(p.gate == nullptr, MC_ERR_BAD_ARG, "clip_bwd_rows: the form switch needs tile flags");
   if ((rc = launch_phase<kBwdW>(mode, p, s, nullptr, static_cast<float*>(ws), wsc, st, nullptr, -1, 1,
                                 static_cast<__half*>(W_rows))))
     return rc;

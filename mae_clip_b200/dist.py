@@ -369,7 +369,7 @@ class PeerStep:
         gl = None if grad_loss is None else grad_loss.reshape(1).to(torch.float32).contiguous()
         with torch.cuda.device(dev):
             ws = workspace(L.mc_clip_loss_workspace_bytes(b, B, D, mode), dev)
-            if (self.bwd_form == "stored" and ex.world > 1 and flags is not None and mode == _lib.GEMM_TC_F16X3
+            if (self.bwd_form == "stored" and ex.world > 1 and flags is not None and mode != _lib.GEMM_SIMT_FP32
                     and b * B >= 4096 * 4096):   # smaller strips are launch-bound: one own-rows sweep
                 st = cur_stream()
                 if self._stored is None:
