@@ -2187,34 +2187,24 @@ rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
               sS = sS * ex2f((mS - mn) * cS2) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
               mS = mn;
             }
-            // ---- column partials: this warp's 32 x 32 block (lane = row) -> LSE over its rows of each column
+            // ---- column partials: this warp's 32 x 32 block (lane = row) -> LSE over its rows of each column.  The 32 column
+            // maxima come from redux.sync.max.f32 (one CREDUX per column, the result is warp-uniform, so every lane can
+            // take its exponentials against the column's OWN maximum - exact, no shared reference that could underflow);
+            // the sums from a transpose-reduce in registers (five exchange steps, lane l ends up owning column l).
             float a[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) a[e] = row_ok ? v[e] : -INFINITY;
-#pragma unroll
-            for (int s2 = 16; s2 >= 1; s2 >>= 1) {
-              const bool up = (lane & s2) != 0;
-#pragma unroll
-              for (int k = 0; k < s2; ++k) {
-                const float keep = up ? a[k + s2] : a[k], send = up ? a[k] : a[k + s2];
-                a[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, s2));
-              }
-            }
             float* cmx = scratch + (warp - 4) * 32;
             __syncwarp();
-            cmx[lane] = a[0];
-            __syncwarp();
-            const float cm_own = a[0];
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const float4 q4v = *reinterpret_cast<const float4*>(cmx + e);
-              const float cmv[4] = {q4v.x, q4v.y, q4v.z, q4v.w};
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float ref = cmv[u] == -INFINITY ? 0.f : cmv[u];
-                a[e + u] = row_ok ? ex2f((v[e + u] - ref) * cS2) : 0.f;
-              }
+            for (int e = 0; e < 32; ++e) {
+              float cme;
+              const float in = row_ok ? v[e] : -INFINITY;
+              asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(cme) : "f"(in));
+              if (lane == 0) cmx[e] = cme;
+              const float ref = cme == -INFINITY ? 0.f : cme;
+              a[e] = row_ok ? ex2f((v[e] - ref) * cS2) : 0.f;
             }
+            __syncwarp();
+            const float cm_own = cmx[lane];
 #pragma unroll
             for (int s2 = 16; s2 >= 1; s2 >>= 1) {
               const bool up = (lane & s2) != 0;
