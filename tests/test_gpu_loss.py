@@ -454,12 +454,14 @@ def test_tile_flags_find_duplicates_across_tiles():
     assert rel_err(dIs, dId) < 1e-5 and rel_err(dTs, dTd) < 1e-5
 
 
+@pytest.mark.parametrize("B", [640 + 64, 4096, 4096 + 128])
 @pytest.mark.parametrize("scale,tau", [(1.0, 1.0), (0.5, 1.0), (0.35, 1.0), (0.6, 0.25), (0.1, 1.0)])
-def test_tile_flags_are_a_superset_of_the_exact_relevance(scale, tau):
+def test_tile_flags_are_a_superset_of_the_exact_relevance(scale, tau, B):
     """The engine's flags come from a bound (probe Z against Z_ii); the oracle computes the exact set of tiles holding
     a P_ij or P_ji >= 2^-44 in fp64.  Flags must cover it in every regime (hard, intermediate, soft), with a few rows
-    of larger norm thrown in so that rz_i > Z_ii for the others."""
-    B = 640 + 64
+    of larger norm thrown in so that rz_i > Z_ii for the others.  B = 704 runs the probe of pair_kernel<kStats>; from
+    4096 on rowsweep_kernel<kRsZ> (tiles on or above the diagonal, row criterion + column criterion against the smallest
+    Z_jj of the tile) - 4224 is not a multiple of 256."""
     I0 = loss_ref.make_embeddings(B, 256, seed=51, scale=scale)
     T0 = loss_ref.make_embeddings(B, 256, seed=52, scale=scale)
     I0[5] *= 1.3; T0[400] *= 1.2; I0[401] = I0[17]          # norm outliers and a cross-tile duplicate
