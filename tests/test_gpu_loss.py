@@ -473,6 +473,26 @@ def test_tile_flags_are_a_superset_of_the_exact_relevance(scale, tau, B):
         assert flags.sum().item() <= exact.sum().item() + 4   # and the bound is tight in the hard regime
 
 
+@pytest.mark.parametrize("scale", [1.0, 0.45])
+def test_tile_flags_of_row_shards_cover_the_single_call_flags(scale):
+    """Under row sharding rowsweep_kernel<kRsZ> probes every tile of the strip with the row criterion only (the raw flags
+    of a strip also drive its exact-Z statistics, so they must be complete per rank); after mc_clip_flags_finalize (which
+    ORs the transposed relation over all shards) the bitmap must cover what the single call (upper triangle, row + column
+    criteria) flags - which the test above pins on the exact fp64 relevance.  Near-duplicates far apart included."""
+    B = 8192
+    I = loss_ref.make_embeddings(B, 256, seed=61, scale=scale)
+    T = loss_ref.make_embeddings(B, 256, seed=62, scale=scale)
+    I[7000] = I[100]; T[7000] = T[100]; I[4200] = I[4100]; T[130] = T[8000]       # cross-tile near-duplicates
+    Ic, Tc = I.cuda(), T.cuda()
+    _l, _dI, _dT, single = _phases(Ic, Tc, 1.0, "tc_f16x3", sparse=True)
+    for b in (2048, 4096):
+        _l2, _dI2, _dT2, sharded = _phases_sharded(Ic, Tc, 1.0, "tc_f16x3", b, colpart=True)
+        assert sharded.shape == single.shape
+        assert bool((sharded.cpu().bool() | ~single.cpu().bool()).all()), "a tile flagged by the single call is missing under sharding"
+        if scale == 1.0:
+            assert sharded.sum().item() <= single.sum().item() + 8
+
+
 # ------------------------------------------------------------------ parity AT the benchmarked size (BASELINE config 4)
 def _phases_sharded(I, T, tau, mode, shard_rows, colpart=False, stored=False, use_flags=True, gated=False):
     """The row-sharded form of the step (what the ranks of a multi-GPU job run, mae_clip_b200/dist.py) back to back on
