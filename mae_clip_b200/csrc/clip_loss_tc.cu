@@ -2204,14 +2204,25 @@ rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             float a[32];
             float* cmx = scratch + (warp - 4) * 32;
             __syncwarp();
+            if (!ragged && __all_sync(0xffffffffu, row_ok)) {
+              // common case (every row of the warp is real, every column of the tile too): no masks, no -inf handling
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              float cme;
-              const float in = row_ok ? v[e] : -INFINITY;
-              asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(cme) : "f"(in));
-              if (lane == 0) cmx[e] = cme;
-              const float ref = cme == -INFINITY ? 0.f : cme;
-              a[e] = row_ok ? ex2f((v[e] - ref) * cS2) : 0.f;
+              for (int e = 0; e < 32; ++e) {
+                float cme;
+                asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(cme) : "f"(v[e]));
+                if (lane == 0) cmx[e] = cme;
+                a[e] = ex2f((v[e] - cme) * cS2);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                float cme;
+                const float in = row_ok ? v[e] : -INFINITY;
+                asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(cme) : "f"(in));
+                if (lane == 0) cmx[e] = cme;
+                const float ref = cme == -INFINITY ? 0.f : cme;
+                a[e] = row_ok ? ex2f((v[e] - ref) * cS2) : 0.f;
+              }
             }
             __syncwarp();
             const float cm_own = cmx[lane];
