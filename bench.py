@@ -148,6 +148,10 @@ def cpu_sample_batch(args, B_work):
         Bs = min(B_work, 16384)
         while Bs > 1024 and 20 * Bs * Bs * 4 * 1.5 > avail:
             Bs //= 2
+        # keep the whole CPU leg within ~2 minutes: ~8 s per step at B = 16384 on 16 cores, O(B^2)
+        n_steps = max(1, getattr(args, "_cpu_steps", 3))
+        while Bs > 2048 and n_steps * 8.0 * (Bs / 16384.0) ** 2 * (16.0 / max(1, os.cpu_count() or 1)) > 120.0:
+            Bs //= 2
     return Bs
 
 
@@ -158,6 +162,7 @@ def cpu_reference_leg(args, B_work, steps, warmup):
     from oracle import loss_ref
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    args._cpu_steps = steps + warmup
     Bs = cpu_sample_batch(args, B_work)
     I = make_shard(Bs, 0)
     T = make_shard(Bs, 1)
