@@ -721,6 +721,26 @@ def test_fused_step_is_bit_deterministic():
             assert all(torch.equal(a, b) for a, b in zip(ref, cur))
 
 
+@pytest.mark.parametrize("B", [2048, 4096])
+def test_gradient_error_grows_with_the_logit_magnitude(B):
+    """The fp32-class engine's remaining error is the tensor core's truncating fp32 accumulation, proportional to the size
+    of the logits: rows of norm 16 (what the reference's LayerNorm emits) give ~2.7e-4 on the gradients, norm 24 ~6.5e-4,
+    norm 32 ~2.1e-3 - the last one is OUTSIDE the 1e-3 bar and is pinned here so that the limit stays documented
+    (DESIGN 4.1 "Precision"); the loss itself stays at 1e-6 throughout.  Same numbers on the small-problem kernels
+    (B = 2048) and the large-tile ones (B = 4096)."""
+    import mae_clip_b200 as m
+    from oracle import loss_blockwise
+    for scale, bound in ((1.0, 1e-3), (1.5, 1e-3), (2.0, 4e-3)):
+        I = loss_ref.make_embeddings(B, 256, seed=81, scale=scale).cuda()
+        T = loss_ref.make_embeddings(B, 256, seed=82, scale=scale).cuda()
+        ref_loss, ref_dI, ref_dT, _ = loss_blockwise.clip_loss_blockwise_f64(I, T, 1.0, rows=1024)
+        Ic, Tc = I.clone().requires_grad_(True), T.clone().requires_grad_(True)
+        loss = m.clip_contrastive_loss(Ic, Tc, 1.0, mode="tc_f16x3")
+        loss.backward()
+        assert abs(loss.item() - ref_loss) <= 1e-5 * abs(ref_loss)
+        assert rel_err(Ic.grad, ref_dI) < bound and rel_err(Tc.grad, ref_dT) < bound, (scale, rel_err(Ic.grad, ref_dI))
+
+
 # ------------------------------------------------------------------ autograd plumbing (round-1 advisor findings)
 def test_fp32_fma_engine_state_survives_other_ops_between_forward_and_backward():
     """The fp32 FMA engine keeps its S / S^T / Z strips from the statistics sweep to the gradient sweep.  Through the

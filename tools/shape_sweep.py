@@ -1,0 +1,38 @@
+import sys, os, ctypes
+sys.path.insert(0, "/root/repo")
+import torch
+import mae_clip_b200 as m
+from mae_clip_b200 import _lib
+from oracle import loss_blockwise, loss_ref
+lib = _lib.lib()
+def rel(a, b):
+    a, b = a.double().cpu().reshape(-1), b.double().cpu().reshape(-1)
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+bad = 0
+for (B, D, scale, mode) in [(4097, 256, 1.0, "tc_f16x3"), (4100, 128, 1.0, "tc_f16x3"), (5000, 256, 1.0, "tc_f16x3"), (8191, 256, 1.0, "tc_f16x3"),
+                            (12345, 256, 1.0, "tc_f16x3"), (6000, 256, 0.3, "tc_f16x3"), (9999, 128, 1.0, "tc_f16x3"), (4352, 256, 1.0, "tc_f16"),
+                            (7777, 256, 0.5, "tc_f16x3"), (20000, 256, 1.0, "tc_f16x3"), (4096, 256, 2.0, "tc_f16x3")]:
+    I = loss_ref.make_embeddings(B, D, seed=B, scale=scale).cuda()
+    T = loss_ref.make_embeddings(B, D, seed=B + 1, scale=scale).cuda()
+    ref_loss, ref_dI, ref_dT, _ = loss_blockwise.clip_loss_blockwise_f64(I, T, 1.0, rows=1024)
+    Ic, Tc = I.clone().requires_grad_(True), T.clone().requires_grad_(True)
+    loss = m.clip_contrastive_loss(Ic, Tc, 1.0, mode=mode)
+    loss.backward()
+    tl, tg = (1e-4, 1e-3) if mode == "tc_f16x3" else (5e-4, 5e-3)
+    el, eI, eT = abs(loss.item() - ref_loss) / abs(ref_loss), rel(Ic.grad, ref_dI), rel(Tc.grad, ref_dT)
+    ok = el <= tl and eI < tg and eT < tg
+    # host entry
+    md = _lib.GEMM_MODES[mode]
+    Ih, Th = I.cpu().pin_memory(), T.cpu().pin_memory()
+    oI, oT, ol = torch.empty_like(Ih).pin_memory(), torch.empty_like(Th).pin_memory(), torch.zeros(1).pin_memory()
+    nh = lib.mc_clip_loss_host_workspace_bytes(B, D, md)
+    wsh = torch.zeros(nh, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mc_clip_loss_fwd_bwd_host(Ih.data_ptr(), Th.data_ptr(), B, D, 1.0, md, ol.data_ptr(), oI.data_ptr(), oT.data_ptr(),
+                                             wsh.data_ptr(), nh, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "host")
+    hl, hI, hT = abs(ol.item() - ref_loss) / abs(ref_loss), rel(oI, ref_dI), rel(oT, ref_dT)
+    okh = hl <= tl and hI < tg and hT < tg
+    print(f"B={B} D={D} scale={scale} {mode}: fused loss {el:.1e} dI {eI:.1e} dT {eT:.1e} {'ok' if ok else 'FAIL'} | host loss {hl:.1e} dI {hI:.1e} dT {hT:.1e} {'ok' if okh else 'FAIL'}", flush=True)
+    bad += (not ok) + (not okh)
+    del I, T, Ic, Tc, ref_dI, ref_dT, wsh
+    torch.cuda.empty_cache()
+print("FAILURES", bad)
