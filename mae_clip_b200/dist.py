@@ -460,7 +460,12 @@ def global_clip_loss(image_emb_local, text_emb_local, temperature: float = 1.0, 
         from .peer import PeerUnavailable, get_exchange
         b, D = image_emb_local.shape
         try:
-            step = PeerStep(get_exchange(b, D, group), mode)
+            ex = get_exchange(b, D, group)
+            # one PeerStep per (exchange, engine): it owns the stored-weights buffers of the backward (b x B fp16)
+            cache = ex.__dict__.setdefault("_peer_steps", {})
+            step = cache.get(mode)
+            if step is None:
+                step = cache[mode] = PeerStep(ex, mode)
         except PeerUnavailable:
             # raised on every rank together: without an explicit request the NCCL transport takes over
             if (transport or os.environ.get("MAE_CLIP_TRANSPORT", "auto")) == "peer":
