@@ -658,6 +658,10 @@ def run_b200(args):
         if world == 1 and mode != "simt_fp32" and not args.no_extra:
             # the two regimes the tile flags separate, measured in this run: every tile computed (flags off), and the
             # soft-target regime (embeddings x 0.25: every tile carries mass, flag density 1.0, flags on)
+            try:
+                line["roofline"]["gradient_halves"] = gradient_halves(ph, B, mode, flush, peak)
+            except Exception as e:  # noqa: BLE001 - context only
+                line["roofline"]["gradient_halves"] = {"error": f"{type(e).__name__}: {e}"}
             line["roofline"]["dense"] = regime(B, mode, dev, flush, I_loc, T_loc, False, peak, peaks)
             line["roofline"]["soft"] = regime(B, mode, dev, flush, I_loc * 0.25, T_loc * 0.25, True, peak, peaks)
         if not args.no_cpu_baseline and world == 1:
@@ -675,6 +679,48 @@ def run_b200(args):
             from mae_clip_b200 import peer
             peer.close_all()
         dist.destroy_process_group()
+
+
+def gradient_halves(ph, B, mode, flush, peak):
+    """The two halves of the stored-weights gradient timed separately with CUDA events through their own C-ABI entry
+    points, on the statistics the last timed step left in `ph` (one GPU): the row half is the flagged-tile sweep +
+    rowgrad_kernel + fold (S in 3 passes + the dT GEMM: 4 GEMM units), the column half colgrad_kernel + fold (1 unit,
+    bound by the 2 B^2 bytes of fp16 weights it reads)."""
+    import torch
+    lib, ck, p = ph.lib, ph._lib.check, ph._lib.ptr
+    if ph.flags is None or B * B < 4096 * 4096:
+        return None
+    dev = ph.dI.device
+    md = ph.mode
+    W = torch.empty(lib.mc_clip_stored_weights_bytes(B, B), device=dev, dtype=torch.uint8)
+    diz = torch.zeros((B + 127) // 128 * 128, D_EMB, device=dev)
+    wsc = torch.empty(lib.mc_clip_bwd_cols_workspace_bytes(B, D_EMB), device=dev, dtype=torch.uint8)
+    st = ph._lib.cur_stream()
+    s = ph.stats_loc
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    rows_ms = cols_ms = 0.0
+    n = 5
+    for it in range(n + 2):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ev[0].record()
+        ck(lib.mc_clip_bwd_rows(p(ph.planes), B, B, D_EMB, 0, 1.0, md, p(s[0]), p(s[1]), p(s[2]), p(ph.gq_loc[0]), p(ph.gq_loc[1]),
+                                None, p(ph.dT), p(diz), p(W), p(ph.flags), None, None, p(ph.ws), ph.ws.numel(), st), "bwd_rows")
+        ev[1].record()
+        ck(lib.mc_clip_bwd_cols(p(ph.planes), B, D_EMB, 1.0, md, p(s[0]), p(s[1]), p(s[2]), p(ph.gq_loc[1]), None, p(W), B, 0, 0, B,
+                                p(diz), p(ph.dI), None, p(wsc), wsc.numel(), st), "bwd_cols")
+        ev[2].record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            rows_ms += ev[0].elapsed_time(ev[1]) / n
+            cols_ms += ev[1].elapsed_time(ev[2]) / n
+    unit = 2.0 * B * B * D_EMB / 1e12
+    passes = 3 if md == 1 else 1
+    return {"rows_ms": rows_ms, "cols_ms": cols_ms,
+            "rows_executed_TFLOPs": (passes + 1) * unit / (rows_ms * 1e-3), "rows_executed_frac": (passes + 1) * unit / (rows_ms * 1e-3) / peak,
+            "cols_executed_TFLOPs": unit / (cols_ms * 1e-3), "cols_GBps_weights_read": 2.0 * B * B / (cols_ms * 1e-3) / 1e9,
+            "note": "row half = flagged-tile sweep + rowgrad_kernel + fold (executed: S x passes + dT GEMM); column half = "
+                    "colgrad_kernel + fold (HBM-bound on the stored fp16 weights)"}
 
 
 def regime(B, mode, dev, flush, I, T, sparse, peak, peaks):
