@@ -91,6 +91,29 @@ def test_global_loss_two_gpus_sparse_soft_targets(transport):
         assert rel_err(dT, ref_dT[r * b:(r + 1) * b]) < 1e-3
 
 
+@pytest.mark.parametrize("scale", [1.0, 0.3])
+def test_global_loss_two_gpus_stored_weights_gradient(scale):
+    """4096 rows per rank (B = 8192): large enough for the peer transport's stored-weights backward - row half and column
+    half per rank, the partial dI of every rank reduced over peer memory - and for the large-tile statistics kernels.
+    LayerNorm-scale rows take the stored form (device-side gate = 1); rows x 0.3 flag every tile, the gate falls back to the
+    own-rows sweep and the reduce kernels return at once.  Against the fp64 blockwise oracle on the concatenated batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from oracle import loss_blockwise
+    world, b = 2, 4096
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), b, "tc_f16x3", "peer-push", ret, scale), nprocs=world, join=True)
+    I = torch.cat([loss_ref.make_embeddings(b, 256, seed=1000 + r, scale=scale) for r in range(world)]).cuda()
+    T = torch.cat([loss_ref.make_embeddings(b, 256, seed=2000 + r, scale=scale) for r in range(world)]).cuda()
+    ref_loss, ref_dI, ref_dT, _ = loss_blockwise.clip_loss_blockwise_f64(I, T, 1.0, rows=1024)
+    for r in range(world):
+        loss, dI, dT = ret[r]
+        assert abs(loss.item() - ref_loss) < 1e-4 * abs(ref_loss)
+        assert rel_err(dI, 2.0 * ref_dI[r * b:(r + 1) * b]) < 1e-3      # the workers back-propagate 2 x loss
+        assert rel_err(dT, 2.0 * ref_dT[r * b:(r + 1) * b]) < 1e-3
+
+
 @pytest.mark.parametrize("exchange_mode", ["push", "pull"])
 def test_peer_step_world1_matches_fused_path(exchange_mode):
     """The whole peer-memory choreography (IPC region, push / pull staging, flag barrier, vector publish,
