@@ -6,8 +6,17 @@
 //     S  = T_i I_j^T / tau      St = I_i T_j^T / tau  (= S_ji)      Z = (I_i I_j^T + T_i T_j^T) tau/2
 // in tensor memory and reduces them in the epilogue.
 //
-// Execution model (one kernel template, four phases: statistics [probe form when tile flags are on], exact-Z statistics
-// on the flagged tiles, row loss, gradient):
+// Kernels in this file (DESIGN.md 4.1 has the dispatch table and the measurements behind it):
+//   pair_kernel<PHASE, PASSES>      128 x 128 tiles over a CTA pair of 128 rows: every phase for small problems, the flagged-
+//                                   tile sweeps (exact-Z statistics, row loss, soft-target part of the gradient) and the
+//                                   own-rows gradient always
+//   rowsweep_kernel<KIND, PASSES>   256 x 128 tiles over a CTA pair of 256 rows: S statistics / tile-flag probe of Z
+//   rowgrad_kernel<PASSES>          same skeleton: S -> softmax part of the gradient weights -> dT, stores the weights
+//   colgrad_kernel                  dI from the stored weights (MN-major tcgen05 operand)
+// and the staging, fold and gate kernels around them.
+//
+// pair_kernel's execution model (one kernel template; phases: statistics [probe form when tile flags are on], exact-Z
+// statistics on the flagged tiles, row loss, gradient in its own-rows / stored-weights / flagged-tile forms):
 //   * a CTA PAIR (cluster of 2, tcgen05 cta_group::2, M = 128) owns 128 samples i, 64 per CTA; the
 //     64 x N accumulator tile of a CTA lives in TMEM as 128 lanes x N/2 columns (lanes 0-63: first
 //     half of the tile's columns, lanes 64-127: second half);
@@ -15,7 +24,8 @@
 //     `lo` = fp16(x - hi).  F16X3 issues hi*hi + hi*lo + lo*hi (relative operand error ~2^-22, i.e.
 //     fp32-class logits); F16 issues hi*hi only;
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA, one elected lane) + TMEM allocator, warp 2 = X^T tile
-//     producer (gradient sweep), warps 4-11 = epilogue (two threads per TMEM lane, 32 columns each).  The hi plane of
+//     producer (gradient sweeps), warp 3 = per-column constants of the gradient sweeps (one tile ahead of the epilogue),
+//     warps 4-11 = epilogue (two threads per TMEM lane, 32 columns each).  The hi plane of
 //     the pair's own rows stays resident in shared memory for the whole job (the lo plane too in the forward sweeps);
 //     the column tiles stream through an mbarrier ring;
 //   * the gradient sweep converts each tile into fp16 weight tiles (dS, dS^T, dZ + dZ^T) in shared
