@@ -2366,6 +2366,7 @@ static Split choose_split(int b, int B, double ovh = kOvhRowLoss, int align = 1)
   const int max_split = s.n_tiles < kMaxSplit ? s.n_tiles : kMaxSplit;
   for (int ns = align; ns <= max_split; ns += align) {   // align > 1: the column splits must not straddle a row chunk
     const int tps = (s.n_tiles + ns - 1) / ns;
+    if ((long)(ns - 1) * tps >= s.n_tiles) continue;     // the last split would be empty (the gradient roles assume >= 1 tile per job)
     double cost = 0.02 * ns;
     if (align > 1) {
       // arrival-ordered launches (PairParams::chunk_k): every launch pays its own partly filled last round
@@ -2436,6 +2437,7 @@ static Split choose_split_rows256(int b, int B, int align = 1, double ovh = 3.0)
   const int max_split = s.n_tiles < kMaxSplit ? s.n_tiles : kMaxSplit;
   for (int ns = align; ns <= max_split; ns += align) {
     const int tps = (s.n_tiles + ns - 1) / ns;
+    if ((long)(ns - 1) * tps >= s.n_tiles) continue;     // no empty last split: rowgrad_kernel's roles assume >= 1 tile per job
     double cost = 0.04 * ns;
     if (align > 1) {   // arrival-ordered launches: see choose_split
       if (s.n_tiles % ns != 0 || s.n_row_blocks % align != 0) continue;
