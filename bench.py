@@ -415,7 +415,9 @@ def run_b200(args):
     # is ~1.2 ms and the per-launch gaps were a fifth of it.  The peer barrier keeps its epoch in device memory for this.
     graph, launches_per_step = None, None
     phase_ms_eager = [0.0] * 4
-    if transport == "peer" and os.environ.get("MAE_CLIP_BENCH_GRAPH", "1") != "0":
+    # N = 1: the same capture (22 launches of our library, no host sync inside the step); the gaps between the short
+    # finalize/staging kernels are ~1% of the step.
+    if (transport == "peer" or world == 1) and os.environ.get("MAE_CLIP_BENCH_GRAPH", "1") != "0":
         for _ in range(args.steps):            # per-phase times from eager steps (events cannot sit inside the replayed graph)
             flush.fill_(1)
             barrier()
@@ -444,10 +446,11 @@ def run_b200(args):
             if rank == 0:
                 print(f"bench: CUDA graph capture of the step failed ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
             graph = None
-        ok = torch.tensor([1 if graph is not None else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)       # every rank replays, or none does
-        if not ok.item():
-            graph = None
+        if world > 1:
+            ok = torch.tensor([1 if graph is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)       # every rank replays, or none does
+            if not ok.item():
+                graph = None
 
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.mc_kernel_launch_count()
@@ -590,6 +593,8 @@ def run_b200(args):
         if mode != "simt_fp32" and os.environ.get("MAE_CLIP_BWD_FORM") != "ownrows":
             if world == 1 or (transport == "peer" and getattr(ph.step_impl, "bwd_form", "") == "stored"):
                 form = "stored"
+        if form == "stored" and flags_t is not None and density > GATE_DENSITY:
+            form = "ownrows"    # the device-side gate (mc_clip_bwd_gate) chose the own-rows kernels for this batch
         split = form == "stored" and flags_t is not None and mode == "tc_f16x3" and os.environ.get("MAE_CLIP_BWD_SPLIT") != "0"
         if mode == "simt_fp32":
             exec_units = 8
@@ -723,6 +728,9 @@ def gradient_halves(ph, B, mode, flush, peak):
                     "colgrad_kernel + fold (HBM-bound on the stored fp16 weights)"}
 
 
+GATE_DENSITY = 0.15   # mc_clip_bwd_gate: the stored-weights gradient runs iff the tile-flag density is at most this
+
+
 def regime(B, mode, dev, flush, I, T, sparse, peak, peaks):
     """The same step in another soft-target regime (see run_b200): ms per step and the gradient sweep's roofline terms."""
     import torch
@@ -745,7 +753,8 @@ def regime(B, mode, dev, flush, I, T, sparse, peak, peaks):
     ms, bwd_ms = tot / n, phs[3] / n
     density = float(ph.flags.float().mean().item()) if ph.flags is not None else 1.0
     passes = 3 if mode == "tc_f16x3" else 1
-    if mode == "simt_fp32" or os.environ.get("MAE_CLIP_BWD_FORM") == "ownrows":
+    gated_out = ph.flags is not None and density > GATE_DENSITY   # the device-side gate picks the own-rows kernels
+    if mode == "simt_fp32" or os.environ.get("MAE_CLIP_BWD_FORM") == "ownrows" or gated_out:
         units = (2 * passes + 2) * (1 + density)
     else:   # stored-weights form (see run_b200): split when tile flags exist, the single row sweep otherwise
         split = sparse and mode == "tc_f16x3" and os.environ.get("MAE_CLIP_BWD_SPLIT") != "0"
