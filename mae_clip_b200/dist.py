@@ -11,7 +11,11 @@ One process per GPU.  Rank r owns rows [r*b, (r+1)*b) of the global (B, D) embed
             all-gather those + the partial                                  2 x B + W floats
   backward  sweep 3 -> dI_loc, dT_loc with EVERY term of the owned rows (strip of dS, transposed
             strip of dS, dZ + dZ^T by symmetry of Z): no gradient reduce-scatter is needed, only the
-            small vectors above ever cross NVLink after the embedding all-gather.
+            small vectors above ever cross NVLink after the embedding all-gather.  (This is the
+            OWN-ROWS form.  The peer transport's default from 4096 x 4096 logits per rank on is the
+            STORED-WEIGHTS form: S once per rank, dT and the fp16 weight strip from the row half,
+            this rank's contribution to every row of dI from the column half, then a peer-memory
+            reduce-scatter of the partial dI - see ``PeerStep.backward`` and DESIGN.md section 5.)
 
 The sweeps are the C-ABI phases ``mc_clip_stats / mc_clip_rowloss / mc_clip_bwd``.  The engine is
 injectable so the collective choreography can be tested on CPU with gloo (tests supply a torch
@@ -346,7 +350,8 @@ class PeerStep:
             self.trace.mark("ex.publish")
             ex.barrier()
             self.trace.mark("barrier")
-            # out of the region: backward (and a second forward before it) never touch peer memory
+            # out of the region: backward reads its vectors from these copies, so a second forward before it is harmless
+            # (the stored-weights backward reuses only the dead image of I and the latest flag bitmap, see backward)
             vecs = torch.empty(5, B, **f32)
             parts = torch.empty(18, **f32)   # 16 partial slots + the barrier's {epoch, error} words, one copy
             ex.copy_out(ex.OFF_VECS, 5, B, ex.vec_stride, vecs, B)
@@ -381,7 +386,8 @@ class PeerStep:
                 W, diz, wsc, gate = self._stored
                 row0 = ex.rank * b
                 # stored form or own-rows sweep: decided on the device from the flag density of the WHOLE bitmap (every
-                # rank holds it after the forward exchange), so all ranks take the same branch
+                # rank holds it after the forward exchange), so all ranks take the same branch.  The bitmap in the region
+                # is the LATEST forward's; after two forwards the older backward may take the other (equally exact) form.
                 nt = (B + 127) // 128
                 check(L.mc_clip_bwd_gate(ex.local(ex.off_flags), nt * nt, ptr(gate), st), "mc_clip_bwd_gate")
                 self.trace.mark("mc_clip_bwd_gate")

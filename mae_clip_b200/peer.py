@@ -24,9 +24,13 @@ rank stores its rows into all ranks' images and the staging reads locally.
 Why the region can be reused every step without extra fences (B_k = k-th barrier of a step):
   shards + amax slots written before B_1, read by peers between B_1 and B_2;  r, c, rz pushed
   between B_1 and B_2, read after B_2;  g, q, partials pushed between B_2 and B_3, read after B_3
-  and copied out of the region right there (backward never touches peer memory).  A rank can only
-  write step n+1's data after passing B_1(n+1) / B_2(n+1), which every peer enters only after its
-  own stream finished reading step n's.
+  and copied out of the region right there.  A rank can only write step n+1's data after passing
+  B_1(n+1) / B_2(n+1), which every peer enters only after its own stream finished reading step n's.
+  The own-rows backward never touches peer memory.  The stored-weights backward (``dist.PeerStep``)
+  does: each rank writes its partial dI for ALL B rows into its OWN (B, D) image of the image
+  embeddings - dead since the operand staging after B_1 - then B_4, every rank sums its rows of the
+  peers' images (``mc_peer_reduce``), then B_5 so that no rank pushes the next step's shards into an
+  image a peer is still reading.  Like a collective, that backward must run on every rank of the group.
 
 Skew between ranks.  The barrier spins ON THE GPU until every peer's stream reaches the same barrier, at most
 ``MAE_CLIP_PEER_TIMEOUT_S`` seconds (default 600, the order of a process-group timeout: rank-0-only validation or
