@@ -37,6 +37,7 @@ from __future__ import annotations
 import os
 
 import torch
+from torch.autograd.function import once_differentiable
 import torch.distributed as dist
 
 from . import _lib
@@ -192,6 +193,7 @@ class _GlobalClipLoss(torch.autograd.Function):
         return part.reshape(())
 
     @staticmethod
+    @once_differentiable   # the C library's gradients are not themselves differentiable
     def backward(ctx, grad_loss):
         I_all, T_all, stats_all, gq_all = ctx.saved_tensors
         b, row_offset, tau = ctx.cfg
@@ -432,6 +434,7 @@ class _PeerGlobalClipLoss(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable   # the C library's gradients are not themselves differentiable
     def backward(ctx, grad_loss):
         dI, dT = ctx.step.backward(ctx.saved, ctx.tau, grad_loss)
         return dI.to(ctx.in_dtypes[0]), dT.to(ctx.in_dtypes[1]), None, None

@@ -5,6 +5,7 @@ Each Function only marshals pointers/sizes; all arithmetic happens in the CUDA l
 from __future__ import annotations
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 from ._lib import check, cur_stream, lib, ptr, require_cuda, workspace
@@ -57,6 +58,7 @@ class _SoftCE(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable   # the C library's gradients are not themselves differentiable
     def backward(ctx, grad):
         preds, targets, lse, tsum = ctx.saved_tensors
         rows, cols = preds.shape
@@ -125,6 +127,7 @@ class _ClipLoss(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable   # the C library's gradients are not themselves differentiable
     def backward(ctx, grad_loss):
         dI, dT = ctx.saved_tensors
         gi = (dI * grad_loss).to(ctx.in_dtypes[0]) if ctx.needs_input_grad[0] else None
@@ -184,6 +187,7 @@ class _ProjHead(torch.autograd.Function):
         return out.reshape(*lead, P)
 
     @staticmethod
+    @once_differentiable   # the C library's gradients are not themselves differentiable
     def backward(ctx, grad_out):
         x2, wp, wf, g, keep_mask, projected, hidden, z, mean, rstd, fwd_amax = ctx.saved_tensors
         B, E, P, p_drop, mode, lead, x_dtype = ctx.cfg
@@ -250,6 +254,7 @@ class _RandomMasking(torch.autograd.Function):
         return x_masked, mask, ids_restore, ids_keep
 
     @staticmethod
+    @once_differentiable   # the C library's gradients are not themselves differentiable
     def backward(ctx, g_masked, _gm, _gr, _gk):
         mask, ids_restore = ctx.saved_tensors
         N, L, Dm, len_keep = ctx.cfg
@@ -296,6 +301,7 @@ class _MaskedMSE(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable   # the C library's gradients are not themselves differentiable
     def backward(ctx, grad_loss):
         pred, imgs, mask, msum = ctx.saved_tensors
         N, H, W, patch, norm_pix = ctx.cfg

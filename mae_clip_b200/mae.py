@@ -6,6 +6,7 @@ formulation that BASELINE.json's north_star names and ``oracle/mae_ref.py`` rest
 from __future__ import annotations
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import functional as F_b200
 from ._lib import check, cur_stream, lib, ptr, require_cuda
@@ -77,6 +78,7 @@ class _RestoreTokens(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable   # the C library's gradients are not themselves differentiable
     def backward(ctx, grad_out):
         ids_restore, = ctx.saved_tensors
         N, L, D, keep, tok_shape, tok_dtype = ctx.cfg
