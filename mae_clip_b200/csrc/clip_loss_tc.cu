@@ -171,7 +171,7 @@ constexpr float kFlagTheta2 = 44.f;
 constexpr float kProbeMargin2 = 2.f;  // slack on top of the probe's worst-case rounding bound (see zmargin2)    // log2 units: dropped terms are below 2^-44 of their row's soft-target mass
 
 struct PlanesLayout {
-  size_t off_hdr, off_norm_i, off_norm_t, off_hi, off_lo, off_hiT, total;
+  size_t off_hdr, off_norm_i, off_norm_t, off_rho, off_hi, off_lo, off_hiT, total;
   int Bp;
 };
 static PlanesLayout planes_layout(int B, int D) {
@@ -182,7 +182,8 @@ static PlanesLayout planes_layout(int B, int D) {
   l.off_hdr = 0;              // {amax bits, s, 1/s, 1/s^2}
   l.off_norm_i = 1024;        // ||I_i||_2
   l.off_norm_t = 1024 + vec;  // ||T_i||_2
-  l.off_hi = 1024 + 2 * vec;
+  l.off_rho = 1024 + 2 * vec; // norm of the dimensions the tile-flag probe does NOT multiply out (probe_chunks)
+  l.off_hi = 1024 + 3 * vec;
   l.off_lo = l.off_hi + plane;
   l.off_hiT = l.off_lo + plane;
   l.total = l.off_hiT + plane;
@@ -191,6 +192,20 @@ static PlanesLayout planes_layout(int B, int D) {
 
 // D/4 accumulator columns per epilogue thread must be a multiple of the 32-column TMEM load
 bool supported(int D) { return D == 128 || D == 256; }
+
+// The tile-flag probe of rowsweep_kernel<kRsZ> multiplies out only the first probe_chunks(D) 64-wide K chunks of each
+// half of X = [I || T] and bounds the rest of Z_ij by Cauchy-Schwarz with the per-row norm rho of the left-out
+// dimensions (written by the staging kernel): Z_ij <= E_ij + tau/2 rho_i rho_j.  Still a rigorous superset of the
+// relevant tiles, at half (D = 256) of the probe's MMA work; a batch whose bound is too loose to be useful is
+// detected on the device and probed in full (probe_gate_kernel).  Default: two chunks (128 dimensions) of each tower -
+// for LayerNorm rows that leaves the bound ~38 nats below the threshold at B = 8192, while ONE chunk does not work at all
+// (the left-out energy of a row fluctuates by +-10%, which eats the threshold: measured, half of all tiles flagged);
+// D = 128 is therefore probed in full.  MAE_CLIP_PROBE_CHUNKS = D / 64 restores the full probe everywhere.
+static int probe_chunks(int D) {
+  static const int env = getenv("MAE_CLIP_PROBE_CHUNKS") ? atoi(getenv("MAE_CLIP_PROBE_CHUNKS")) : 2;
+  const int nkc = D / 64;
+  return env < 1 ? 1 : (env > nkc ? nkc : env);
+}
 
 // ------------------------------------------------------------------------------------------
 // staging: fp32 embeddings -> scaled fp16 hi / lo planes of X = [I || T], the per-row scale, and
@@ -1985,6 +2000,11 @@ struct RowSweepParams {
   uint8_t* flags_out;       // kRsZ: [row blocks of 128][n_tiles]
   const float *norm_i, *norm_t;
   const float* tile_min_zjj2;   // kRsZ, tri: smallest Z_jj (log2 units) of every column tile
+  int pk;                       // kRsZ: 64-wide K chunks of each half that are multiplied out (see probe_chunks)
+  const float* rho;             // kRsZ: norm of the left-out dimensions of every row (nullptr: nothing is left out)
+  const float* tile_max_rho;    // kRsZ: largest rho of every column tile
+  const float* tile_max_n;      // kRsZ: largest row norm sqrt(|I_j|^2 + |T_j|^2) of every column tile
+  const int* gate;              // kRsZ: optional device word, the launch returns unless it is 1 (the full re-probe)
 };
 __device__ __forceinline__ int rs_njobs(const RowSweepParams& p) {
   if (p.chunk_k < 0) return p.n_row_blocks * p.nsplit;
@@ -2027,9 +2047,11 @@ rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  if (KIND == kRsZ && p.gate != nullptr && *p.gate != 1) return;   // kernel-uniform: the partial probe was good enough
   const int D = p.D, nkc = D >> 6;
+  const int nkz = KIND == kRsS ? nkc : p.pk;          // K chunks (per half of X) a tile multiplies out
   const int njobs = rs_njobs(p);
-  const int n_res = KIND == kRsS ? nkc : 2 * nkc;     // resident 16 KB chunks of this CTA's rows
+  const int n_res = KIND == kRsS ? nkc : 2 * nkz;     // resident 16 KB chunks of this CTA's rows
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSlots; ++s) { mbar_init(bar(kRsFull0 + s), 1); mbar_init(bar(kRsEmpty0 + s), 1); }
@@ -2064,11 +2086,14 @@ rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         if (KIND == kRsS) {
           for (int c = 0; c < nkc; ++c) tma_load_2d_pair(base + c * 16384, &map_a_hi, bar(kRsAFull), D + c * 64, row_a);   // T_i hi
         } else {
-          for (int c = 0; c < 2 * nkc; ++c) tma_load_2d_pair(base + c * 16384, &map_a_hi, bar(kRsAFull), c * 64, row_a);   // [I_i | T_i] hi
+          for (int c = 0; c < nkz; ++c) {                                                                   // I_i hi, T_i hi
+            tma_load_2d_pair(base + c * 16384, &map_a_hi, bar(kRsAFull), c * 64, row_a);
+            tma_load_2d_pair(base + (nkc + c) * 16384, &map_a_hi, bar(kRsAFull), D + c * 64, row_a);
+          }
         }
         for (int t = t0; t < t1; ++t) {
           const int j0 = t * kTileN + 64 * (int)rank;
-          for (int c = 0; c < nkc; ++c, ++it) {
+          for (int c = 0; c < nkz; ++c, ++it) {
             const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
             mbar_wait(bar(kRsEmpty0 + slot), par ^ 1);
             const uint32_t fb = bar(kRsFull0 + slot), sb = base + kOffRing + slot * kSlotBytes_;
@@ -2103,7 +2128,7 @@ rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           mbar_wait(bar(kRsTmemEmpty0 + buf), (use & 1) ^ 1);
           tc_fence_after();
           const uint32_t tD = tmem_base + buf * 128;
-          for (int c = 0; c < nkc; ++c, ++it) {
+          for (int c = 0; c < nkz; ++c, ++it) {
             const uint32_t slot = it % kSlots, par = (it / kSlots) & 1;
             mbar_wait(bar(kRsFull0 + slot), par);
             tc_fence_after();
@@ -2157,10 +2182,21 @@ rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       rs_tiles<KIND>(p, rb, sp, t0, t1);
       if (t0 >= t1) continue;                                 // kRsZ below the diagonal: nothing to do (kRsS never)
       float mS = -INFINITY, sS = 0.f;
-      float zii2 = 0.f;
+      float zii2 = 0.f, rho2 = 0.f, rnd2 = 0.f;
       if (KIND == kRsZ && row_ok) {
         const float ni = p.norm_i[gi], nt = p.norm_t[gi];
         zii2 = (ni * ni + nt * nt) * p.half_tau * kL2e;
+        if (p.rho != nullptr) {
+          // left-out dimensions: Z_ij <= E_ij + tau/2 rho_i rho_j (Cauchy-Schwarz; 1.0001 covers the fp32 norms' rounding).
+          // The worst-case rounding bound of the full probe (zmargin2: every |x s| < 2) would swallow what the partial
+          // probe has left of the threshold, so its rounding term comes from the norms as well: the hi planes are within
+          // 2^-11 relative of x (normal halfs), so |E_ij - E_ij(hi)| <= tau/2 2^-10 (1 + 2^-12) |x_i| |x_j| by
+          // Cauchy-Schwarz again; the factor 1.05 also covers the truncating fp32 accumulation of the tensor cores over
+          // K <= 256 (<= 256 2^-22 = 6% of 2^-10, relative to the same |x_i| |x_j|); subnormal halfs (absolute error
+          // 2^-25 each) are covered by the margin at the comparison.
+          rho2 = p.rho[gi] * p.half_tau * kL2e * 1.0001f;
+          rnd2 = sqrtf(ni * ni + nt * nt) * p.half_tau * kL2e * (1.07f / 1024.f);
+        }
       }
       const int rb128 = rb * 2 + (int)rank;                   // this CTA's 128-row block of the strip
       for (int t = t0; t < t1; ++t, ++tt) {
@@ -2253,13 +2289,20 @@ rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         if (KIND == kRsZ) {
           // row criterion: rz_i >= Z_ii, so a row whose largest (hi-plane) Z stays 44 binades + the rounding bound below it
           // holds no P_ij >= 2^-44 in this tile
-          const float z2 = row_ok ? cmz * cZ2 : -INFINITY;
-          const bool hit = z2 >= zii2 - kFlagTheta2 - zmargin2;
+          float z2 = -INFINITY, zm2 = zmargin2;
+          if (row_ok) {
+            z2 = cmz * cZ2;
+            if (p.rho != nullptr) {
+              z2 += fmaf(rho2, p.tile_max_rho[t], rnd2 * p.tile_max_n[t]);
+              zm2 = kProbeMargin2 + 8.f * (float)D * 2.98e-8f * cZ2;      // slack + 2 D products of |x s| < 2 with a 2^-25 error, twice
+            }
+          }
+          const bool hit = z2 >= zii2 - kFlagTheta2 - zm2;
           if (__any_sync(0xffffffffu, hit) && lane == 0) p.flags_out[(size_t)rb128 * p.n_tiles + t] = 1;
           if (p.tri && t != rb128) {
             // column criterion for the transposed tile (rows of tile t, columns of this row block), by Z_ij = Z_ji
             const float wm = warp_max(z2);
-            if (lane == 0 && wm >= p.tile_min_zjj2[t] - kFlagTheta2 - zmargin2) p.flags_out[(size_t)t * p.n_tiles + rb128] = 1;
+            if (lane == 0 && wm >= p.tile_min_zjj2[t] - kFlagTheta2 - zm2) p.flags_out[(size_t)t * p.n_tiles + rb128] = 1;
           }
         }
       }
@@ -2284,19 +2327,58 @@ rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 }
 
 // smallest Z_jj (log2 units) of every 128-column tile (kRsZ, triangle mode)
+// and the largest rho (norm of the dimensions the probe leaves out) of the same tile
 __global__ void __launch_bounds__(128) tile_min_zjj_kernel(const float* __restrict__ norm_i, const float* __restrict__ norm_t,
-                                                           int B, float half_tau, float* __restrict__ out) {
-  __shared__ float sm[4];
+                                                           const float* __restrict__ rho, int B, float half_tau,
+                                                           float* __restrict__ out, float* __restrict__ out_rho,
+                                                           float* __restrict__ out_n) {
+  __shared__ float sm[4], sr[4], sn[4];
   const int j = blockIdx.x * 128 + threadIdx.x;
-  float z = INFINITY;
+  float z = INFINITY, r = 0.f, n = 0.f;
   if (j < B) {
     const float ni = norm_i[j], nt = norm_t[j];
     z = (ni * ni + nt * nt) * half_tau * 1.4426950408889634f;
+    r = rho[j];
+    n = sqrtf(ni * ni + nt * nt);
   }
-  for (int o = 16; o > 0; o >>= 1) z = fminf(z, __shfl_xor_sync(0xffffffffu, z, o));
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = z;
+  for (int o = 16; o > 0; o >>= 1) {
+    z = fminf(z, __shfl_xor_sync(0xffffffffu, z, o));
+    r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+    n = fmaxf(n, __shfl_xor_sync(0xffffffffu, n, o));
+  }
+  if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = z; sr[threadIdx.x >> 5] = r; sn[threadIdx.x >> 5] = n; }
   __syncthreads();
-  if (threadIdx.x == 0) out[blockIdx.x] = fminf(fminf(sm[0], sm[1]), fminf(sm[2], sm[3]));
+  if (threadIdx.x == 0) {
+    out[blockIdx.x] = fminf(fminf(sm[0], sm[1]), fminf(sm[2], sm[3]));
+    out_rho[blockIdx.x] = fmaxf(fmaxf(sr[0], sr[1]), fmaxf(sr[2], sr[3]));
+    out_n[blockIdx.x] = fmaxf(fmaxf(sn[0], sn[1]), fmaxf(sn[2], sn[3]));
+  }
+}
+// The partial probe's verdict: with more flagged tiles than a concentrated batch can have (its diagonal + 1/64 of all
+// tiles) the Cauchy-Schwarz bound was too loose for this batch - clear the bitmap and let the full probe run (*gate = 1).
+__global__ void __launch_bounds__(1024) probe_gate_kernel(uint8_t* __restrict__ flags, int n, int limit, int* __restrict__ gate) {
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  int c = 0;
+  const bool vec = (reinterpret_cast<uintptr_t>(flags) & 15) == 0 && n % 16 == 0;   // flag bytes are 0 / 1
+  if (vec) {
+    for (int i = threadIdx.x; i < n / 16; i += blockDim.x) {
+      const uint4 w = reinterpret_cast<const uint4*>(flags)[i];
+      c += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) c += flags[i] != 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt, c);
+  __syncthreads();
+  const bool redo = cnt > limit;
+  if (redo) {
+    if (vec) for (int i = threadIdx.x; i < n / 16; i += blockDim.x) reinterpret_cast<uint4*>(flags)[i] = make_uint4(0u, 0u, 0u, 0u);
+    else for (int i = threadIdx.x; i < n; i += blockDim.x) flags[i] = 0;
+  }
+  if (threadIdx.x == 0) *gate = redo ? 1 : 0;
 }
 // row LSE of S from rowsweep_kernel<kRsS>'s partials
 __global__ void __launch_bounds__(256) rowsweep_finalize_kernel(const float2* __restrict__ part, int nsplit, int bpad, int b,
@@ -2423,7 +2505,7 @@ size_t stats_colpart_workspace_bytes(int b, int B, int D, int mode) {
 }
 
 static size_t rowsweep_extra_bytes(int b, int B) {
-  return round_up((size_t)kMaxSplit * round_up((size_t)b, 256) * sizeof(float2), 256) + round_up(round_up((size_t)B, 128) / 128 * sizeof(float), 256);
+  return round_up((size_t)kMaxSplit * round_up((size_t)b, 256) * sizeof(float2), 256) + round_up(3 * (round_up((size_t)B, 128) / 128) * sizeof(float) + 16, 256);   // tile min Z_jj, tile max rho / norm, the probe gate
 }
 // rowgrad_kernel: row blocks of 256, tiles of 256 x 128; same cost model as choose_split (a job pays ~3 tiles of overhead)
 static Split choose_split_rows256(int b, int B, int align = 1, double ovh = 3.0) {
@@ -2523,7 +2605,8 @@ __global__ void __launch_bounds__(256) stage_fused_kernel(PeerRows src, int b, i
                                                           __half* __restrict__ Xh, __half* __restrict__ Xl,
                                                           __half* __restrict__ XhT, float* hdr,
                                                           float* __restrict__ norm_i, float* __restrict__ norm_t,
-                                                          int blk0 /* first 32-row block of this launch */) {
+                                                          int blk0 /* first 32-row block of this launch */,
+                                                          float* __restrict__ rho, int tail_c0 /* first float4 of a half the probe leaves out */) {
   constexpr int K2 = 2 * D, kVec = K2 / 128, kRows = 32, kPitch = K2 + 2;  // pitch in halfs: odd word count
   __shared__ __align__(16) __half tile[kRows * kPitch];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -2566,7 +2649,7 @@ __global__ void __launch_bounds__(256) stage_fused_kernel(PeerRows src, int b, i
     uint2* xh = reinterpret_cast<uint2*>(Xh + (size_t)gi * K2);
     uint2* xl = reinterpret_cast<uint2*>(Xl + (size_t)gi * K2);
     uint32_t* trow = reinterpret_cast<uint32_t*>(tile + r * kPitch);
-    float ni = 0.f, nt = 0.f;
+    float ni = 0.f, nt = 0.f, nr = 0.f;
 #pragma unroll
     for (int u = 0; u < kVec; ++u) {
       const int c = lane + 32 * u;
@@ -2581,6 +2664,7 @@ __global__ void __launch_bounds__(256) stage_fused_kernel(PeerRows src, int b, i
         l[e] = __float2half_rn(x - __half2float(h[e]));
       }
       if (c < D / 4) ni += nn; else nt += nn;
+      if ((c < D / 4 ? c : c - D / 4) >= tail_c0) nr += nn;
       __half2 h01 = __halves2half2(h[0], h[1]), h23 = __halves2half2(h[2], h[3]);
       __half2 l01 = __halves2half2(l[0], l[1]), l23 = __halves2half2(l[2], l[3]);
       const uint32_t a0 = *reinterpret_cast<uint32_t*>(&h01), a1 = *reinterpret_cast<uint32_t*>(&h23);
@@ -2591,7 +2675,8 @@ __global__ void __launch_bounds__(256) stage_fused_kernel(PeerRows src, int b, i
     }
     ni = warp_sum(ni);
     nt = warp_sum(nt);
-    if (lane == 0) { norm_i[gi] = sqrtf(ni); norm_t[gi] = sqrtf(nt); }
+    nr = warp_sum(nr);
+    if (lane == 0) { norm_i[gi] = sqrtf(ni); norm_t[gi] = sqrtf(nt); rho[gi] = sqrtf(nr); }
   }
   __syncthreads();
   // transposed slice: XhT[k][j0 .. j0+32).  A warp instruction covers two k rows: lanes 0-15 -> k, 16-31 -> k+1,
@@ -2646,9 +2731,11 @@ static void launch_stage_fused(const PeerRows& src, int b, int B, int D, const P
                                float* hdr, float* norm_i, float* norm_t, cudaStream_t st) {
   const int blocks = l.Bp / 32;
   if (D == 256)
-    stage_fused_kernel<256><<<blocks, 256, 0, st>>>(src, b, B, l.Bp, amax_slots, nslots, Xh, Xl, XhT, hdr, norm_i, norm_t, 0);
+    stage_fused_kernel<256><<<blocks, 256, 0, st>>>(src, b, B, l.Bp, amax_slots, nslots, Xh, Xl, XhT, hdr, norm_i, norm_t, 0,
+                                                    norm_i + (l.off_rho - l.off_norm_i) / 4, 16 * probe_chunks(D));
   else
-    stage_fused_kernel<128><<<blocks, 256, 0, st>>>(src, b, B, l.Bp, amax_slots, nslots, Xh, Xl, XhT, hdr, norm_i, norm_t, 0);
+    stage_fused_kernel<128><<<blocks, 256, 0, st>>>(src, b, B, l.Bp, amax_slots, nslots, Xh, Xl, XhT, hdr, norm_i, norm_t, 0,
+                                                    norm_i + (l.off_rho - l.off_norm_i) / 4, 16 * probe_chunks(D));
 }
 
 int push_shards(const float* I_loc, const float* T_loc, int b, int D, int rank, int world, float* const* I_dst,
@@ -2887,8 +2974,19 @@ static float* rowsweep_tile_min(const ClipProblem& p, void* ws) {
   return reinterpret_cast<float*>(reinterpret_cast<char*>(rowsweep_part(p, ws)) +
                                   round_up((size_t)kMaxSplit * round_up((size_t)p.b, 256) * sizeof(float2), 256));
 }
+static float* rowsweep_tile_max_rho(const ClipProblem& p, void* ws) {
+  return rowsweep_tile_min(p, ws) + round_up((size_t)p.B, 128) / 128;
+}
+static float* rowsweep_tile_max_n(const ClipProblem& p, void* ws) {
+  return rowsweep_tile_max_rho(p, ws) + round_up((size_t)p.B, 128) / 128;
+}
+static int* rowsweep_probe_gate(const ClipProblem& p, void* ws) {
+  return reinterpret_cast<int*>(rowsweep_tile_max_n(p, ws) + round_up((size_t)p.B, 128) / 128);
+}
+// full_reprobe (kRsZ): every K chunk multiplied out, gated on the device by probe_gate_kernel's verdict
 template <int KIND, int PASSES>
-static int launch_rowsweep(const ClipProblem& p, void* ws, float* colpart, int chunk_k, int chunks, cudaStream_t st) {
+static int launch_rowsweep(const ClipProblem& p, void* ws, float* colpart, int chunk_k, int chunks, cudaStream_t st,
+                           bool full_reprobe = false) {
   PlanesLayout l = planes_layout(p.B, p.D);
   const char* base = static_cast<const char*>(p.planes_all);
   const void* Xh = base + l.off_hi;
@@ -2917,6 +3015,11 @@ static int launch_rowsweep(const ClipProblem& p, void* ws, float* colpart, int c
   rp.norm_i = reinterpret_cast<const float*>(base + l.off_norm_i);
   rp.norm_t = reinterpret_cast<const float*>(base + l.off_norm_t);
   rp.tile_min_zjj2 = rowsweep_tile_min(p, ws);
+  rp.pk = full_reprobe ? p.D / 64 : probe_chunks(p.D);
+  rp.rho = rp.pk < p.D / 64 ? reinterpret_cast<const float*>(base + l.off_rho) : nullptr;
+  rp.tile_max_rho = rowsweep_tile_max_rho(p, ws);
+  rp.tile_max_n = rowsweep_tile_max_n(p, ws);
+  rp.gate = full_reprobe ? rowsweep_probe_gate(p, ws) : nullptr;
   auto kern = rowsweep_kernel<KIND, PASSES>;
   static std::atomic<unsigned long long> attr_done{0};
   MC_CUDA(ensure_dynamic_smem(kern, kRsSmemBytes, attr_done));
@@ -2955,8 +3058,9 @@ int stats_chunk(const ClipProblem& p, int mode, int k, int chunks, void* ws, cud
     const char* base = static_cast<const char*>(p.planes_all);
     const int n_tiles = (int)(round_up((size_t)p.B, 128) / 128);
     tile_min_zjj_kernel<<<n_tiles, 128, 0, st>>>(reinterpret_cast<const float*>(base + l.off_norm_i),
-                                                 reinterpret_cast<const float*>(base + l.off_norm_t), p.B, 0.5f * p.tau,
-                                                 rowsweep_tile_min(p, ws));
+                                                 reinterpret_cast<const float*>(base + l.off_norm_t),
+                                                 reinterpret_cast<const float*>(base + l.off_rho), p.B, 0.5f * p.tau,
+                                                 rowsweep_tile_min(p, ws), rowsweep_tile_max_rho(p, ws), rowsweep_tile_max_n(p, ws));
     MC_LAUNCH_CHECK();
     int rc = mode == MC_GEMM_TC_F16X3 ? launch_rowsweep<kRsS, 3>(p, ws, colpart_rs, k, chunks, st)
                                       : launch_rowsweep<kRsS, 1>(p, ws, colpart_rs, k, chunks, st);
@@ -2972,6 +3076,14 @@ int stats_end(const ClipProblem& p, int mode, int chunks, float* r_loc, float* c
   float* colpart = stats_colpart_ptr(p, mode, ws, c_part_all);
   if (c_part_all) c_loc = c_part_all;
   int rc;
+  // a partial probe (probe_chunks) whose bound was too loose for this batch flags far more tiles than a concentrated
+  // batch has: the device decides, clears the bitmap and re-probes with every K chunk (both launches are always enqueued)
+  if (rowsweep_ok(p, mode, colpart, chunks) && probe_chunks(p.D) < p.D / 64) {
+    const int nflag = (int)tile_flags_bytes(p.b, p.B);
+    probe_gate_kernel<<<1, 1024, 0, st>>>(p.tile_flags_out, nflag, (p.b + 127) / 128 + nflag / 64, rowsweep_probe_gate(p, ws));
+    MC_LAUNCH_CHECK();
+    if ((rc = launch_rowsweep<kRsZ, 3>(p, ws, colpart, -1, 1, st, true))) return rc;
+  }
   // with tile flags the sweep above was the probe form (S exact, Z from the hi planes -> flags); the exact Z and
   // sum_j P_ij S_ij follow on the flagged tiles only
   if (p.tile_flags_out &&
@@ -3052,9 +3164,11 @@ int prepare_chunk(const float* I, const float* T, int B, int D, int row0, int ro
   float* norm_i = reinterpret_cast<float*>(base + l.off_norm_i);
   float* norm_t = reinterpret_cast<float*>(base + l.off_norm_t);
   if (D == 256)
-    stage_fused_kernel<256><<<blocks, 256, 0, st>>>(src, B, B, l.Bp, words + 1, 1, Xh, Xl, XhT, hdr, norm_i, norm_t, blk0);
+    stage_fused_kernel<256><<<blocks, 256, 0, st>>>(src, B, B, l.Bp, words + 1, 1, Xh, Xl, XhT, hdr, norm_i, norm_t, blk0,
+                                                    norm_i + (l.off_rho - l.off_norm_i) / 4, 16 * probe_chunks(D));
   else
-    stage_fused_kernel<128><<<blocks, 256, 0, st>>>(src, B, B, l.Bp, words + 1, 1, Xh, Xl, XhT, hdr, norm_i, norm_t, blk0);
+    stage_fused_kernel<128><<<blocks, 256, 0, st>>>(src, B, B, l.Bp, words + 1, 1, Xh, Xl, XhT, hdr, norm_i, norm_t, blk0,
+                                                    norm_i + (l.off_rho - l.off_norm_i) / 4, 16 * probe_chunks(D));
   MC_LAUNCH_CHECK();
   return MC_OK;
 }

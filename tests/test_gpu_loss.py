@@ -473,6 +473,50 @@ def test_tile_flags_are_a_superset_of_the_exact_relevance(scale, tau, B):
         assert flags.sum().item() <= exact.sum().item() + 4   # and the bound is tight in the hard regime
 
 
+@pytest.mark.parametrize("B", [4096, 4096 + 128])
+def test_tile_flags_partial_probe_falls_back_to_the_full_probe(B):
+    """rowsweep_kernel<kRsZ> multiplies out only the leading 128 dimensions of each tower and bounds the rest of Z_ij by
+    Cauchy-Schwarz (clip_loss_tc.cu, probe_chunks).  Rows whose leading dimensions are EMPTY make that bound useless
+    (it equals Z_ii for every pair): the partial probe flags every tile, the device-side verdict (probe_gate_kernel)
+    clears the bitmap and the full probe runs - the result must be the diagonal again, and the step must match the oracle."""
+    I0 = loss_ref.make_embeddings(B, 256, seed=71, scale=1.0)
+    T0 = loss_ref.make_embeddings(B, 256, seed=72, scale=1.0)
+    I0[:, :128] = 0.0
+    T0[:, :128] = 0.0
+    I0 *= 16.0 / I0.norm(dim=1, keepdim=True)           # back to the LayerNorm norm: Z_ii = 256, off-diagonal sigma 16
+    T0 *= 16.0 / T0.norm(dim=1, keepdim=True)
+    ls, dIs, dTs, flags = _phases(I0.cuda(), T0.cuda(), 1.0, "tc_f16x3", sparse=True)
+    nt = flags.shape[0]
+    # the diagonal (plus, at most, a borderline pair): nowhere near the all-ones bitmap of the partial probe
+    assert bool(torch.diagonal(flags).all()) and flags.sum().item() <= nt + 4
+    exact = torch.from_numpy(loss_ref.tile_relevance(I0.numpy(), T0.numpy(), 1.0))
+    assert bool((flags.bool() | ~exact).all())
+    ref_loss, ref_dI, ref_dT, _ = loss_ref.clip_loss_closed_form(I0.numpy(), T0.numpy(), 1.0)
+    assert abs(ls - ref_loss) <= LOSS_TOL * abs(ref_loss)
+    assert rel_err(dIs, ref_dI) < GRAD_TOL and rel_err(dTs, ref_dT) < GRAD_TOL
+
+
+def test_tile_flags_partial_probe_falls_back_per_row_shard():
+    """The same batch under row sharding (4096-row strips of B = 8192, the size from which a strip runs rowsweep_kernel):
+    every strip takes its own verdict and re-probes; flags and gradients must equal the single call's."""
+    B = 8192
+    I0 = loss_ref.make_embeddings(B, 256, seed=73, scale=1.0)
+    T0 = loss_ref.make_embeddings(B, 256, seed=74, scale=1.0)
+    I0[:, :128] = 0.0
+    T0[:, :128] = 0.0
+    I0 *= 16.0 / I0.norm(dim=1, keepdim=True)           # back to the LayerNorm norm: Z_ii = 256, off-diagonal sigma 16
+    T0 *= 16.0 / T0.norm(dim=1, keepdim=True)
+    Ic, Tc = I0.cuda(), T0.cuda()
+    l1, dI1, dT1, single = _phases(Ic, Tc, 1.0, "tc_f16x3", sparse=True)
+    nt = single.shape[0]
+    assert bool(torch.diagonal(single).all()) and single.sum().item() <= nt + 8
+    l2, dI2, dT2, sharded = _phases_sharded(Ic, Tc, 1.0, "tc_f16x3", 4096, colpart=True)
+    sharded = sharded.cpu()
+    assert bool(torch.diagonal(sharded).all()) and sharded.sum().item() <= nt + 8
+    assert abs(l1 - l2) <= 1e-6 * abs(l1)
+    assert rel_err(dI2.cpu(), dI1) < 5e-5 and rel_err(dT2.cpu(), dT1) < 5e-5
+
+
 @pytest.mark.parametrize("scale", [1.0, 0.45])
 def test_tile_flags_of_row_shards_cover_the_single_call_flags(scale):
     """Under row sharding rowsweep_kernel<kRsZ> probes every tile of the strip with the row criterion only (the raw flags
