@@ -552,7 +552,9 @@ int mc_clip_loss_fwd_bwd_host(const float* I_host, const float* T_host, int B, i
   // in pieces, staging and the statistics sweep of the rows that have landed run behind the rest of the copy.  The
   // planes share one power-of-two scale, which the first chunk fixes with a binade of headroom; a batch whose later
   // rows exceed it is detected on the device (tc::verify_scale) and the step is redone from the resident copy.
-  int chunks = (eff_mode(mode, D) != MC_GEMM_SIMT_FP32 && B >= 8192) ? 2 : 1;
+  // Measured at B = 32768 with the current kernels (tools/e2e_strips.py, profiles/r02ag_e2e_strips.json; chunks x strips):
+  // 1x1 5.73 ms, 2x2 5.28, 4x2 5.09, 4x3 5.06, 8x2 5.15, 16x2 5.51 - four chunks from 32768 rows on, two from 8192.
+  int chunks = (eff_mode(mode, D) != MC_GEMM_SIMT_FP32 && B >= 8192) ? (B >= 32768 ? 4 : 2) : 1;
   if (const char* e = getenv("MAE_CLIP_HOST_CHUNKS")) {
     const int v = atoi(e);
     if (v >= 1 && v <= 16) chunks = v;
