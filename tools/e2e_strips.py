@@ -25,10 +25,13 @@ ws = torch.empty(n, dtype=torch.uint8, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 out = {}
-combos = [(c, s) for c in (1, 2, 4, 8) for s in (1, 2, 4)] + [(4, 3), (4, 6), (16, 2)]
-for chunks, strips in combos:
+combos = [(c, s, 0) for c in (1, 2, 4, 8) for s in (1, 2, 4)] + [(4, 3, 0), (4, 6, 0), (16, 2, 0)]
+if len(sys.argv) > 2 and sys.argv[2] == "last":     # share of the row blocks the LAST outbound strip takes (0 = equal strips)
+    combos = [(4, 2, 0), (4, 2, 0.375), (4, 2, 0.25), (4, 2, 0.125), (4, 3, 0), (4, 3, 0.25), (4, 3, 0.125), (4, 4, 0.125)]
+for chunks, strips, last in combos:
     os.environ["MAE_CLIP_HOST_CHUNKS"] = str(chunks)
     os.environ["MAE_CLIP_HOST_STRIPS"] = str(strips)
+    os.environ["MAE_CLIP_HOST_LAST_STRIP"] = str(last)
     ts = []
     for it in range(8):
         flush.fill_(1)
@@ -37,5 +40,5 @@ for chunks, strips in combos:
         _lib.check(lib.mc_clip_loss_fwd_bwd_host(I.data_ptr(), T.data_ptr(), B, D, 1.0, mode, loss.data_ptr(),
                                                  dI.data_ptr(), dT.data_ptr(), ws.data_ptr(), n, st), "host")
         ts.append((time.perf_counter() - t0) * 1e3)
-    out[f"chunks{chunks}_strips{strips}"] = {"ms_median": sorted(ts[2:])[len(ts[2:]) // 2], "ms_min": min(ts[2:]), "loss": loss.item()}
+    out[f"chunks{chunks}_strips{strips}" + (f"_last{last}" if last else "")] = {"ms_median": sorted(ts[2:])[len(ts[2:]) // 2], "ms_min": min(ts[2:]), "loss": loss.item()}
 print(json.dumps(out))

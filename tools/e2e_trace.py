@@ -21,8 +21,11 @@ n = lib.mc_clip_loss_host_workspace_bytes(B, D, mode)
 ws = torch.empty(n, dtype=torch.uint8, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-for chunks, strips, last in [(1, 1, 0), (1, 2, 0.5), (2, 2, 0.5), (2, 2, 0.375), (2, 2, 0.3125), (2, 2, 0.25),
-                             (2, 2, 0.1875), (2, 3, 0.125), (2, 3, 0.1875), (4, 2, 0.25)]:
+COMBOS = [(1, 1, 0), (1, 2, 0.5), (2, 2, 0.5), (2, 2, 0.375), (2, 2, 0.3125), (2, 2, 0.25),
+          (2, 2, 0.1875), (2, 3, 0.125), (2, 3, 0.1875), (4, 2, 0.25)]
+if len(sys.argv) > 2 and sys.argv[2] == "default":   # the library's defaults plus their neighbours
+    COMBOS = [(4, 2, 0), (4, 3, 0), (8, 2, 0)]
+for chunks, strips, last in COMBOS:
     os.environ["MAE_CLIP_HOST_CHUNKS"] = str(chunks)
     os.environ["MAE_CLIP_HOST_STRIPS"] = str(strips)
     os.environ["MAE_CLIP_HOST_LAST_STRIP"] = str(last)
