@@ -2231,35 +2231,58 @@ rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           if (KIND == kRsZ) {
             cmz = fmaxf(cmz, cm);
           } else {
-            // ---- row LSE of S, online (exact differences: an unchanged maximum rescales by exactly 1)
-            const float mn = fmaxf(mS, cm);
-            if (mn != -INFINITY) {
+            // ---- row LSE of S, online.  The 32 exponentials are taken against the chunk's OWN row maximum cm (exact: the
+            // largest term is 1) and shared with the column partials below; the chunk's sum joins the running (mS, sS)
+            // with two more exponentials per row (an unchanged maximum rescales by exactly 1).
+            float a[32];
+            if (cm != -INFINITY) {
               float a4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
               for (int e = 0; e < 32; e += 4) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) a4[u] += ex2f((v[e + u] - mn) * cS2);
+                for (int u = 0; u < 4; ++u) { a[e + u] = ex2f((v[e + u] - cm) * cS2); a4[u] += a[e + u]; }
               }
-              sS = sS * ex2f((mS - mn) * cS2) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
+              const float mn = fmaxf(mS, cm);
+              sS = sS * ex2f((mS - mn) * cS2) + ((a4[0] + a4[1]) + (a4[2] + a4[3])) * ex2f((cm - mn) * cS2);
               mS = mn;
-            }
-            // ---- column partials: this warp's 32 x 32 block (lane = row) -> LSE over its rows of each column.  The 32 column
-            // maxima come from redux.sync.max.f32 (one CREDUX per column, the result is warp-uniform, so every lane can
-            // take its exponentials against the column's OWN maximum - exact, no shared reference that could underflow);
-            // the sums from a transpose-reduce in registers (five exchange steps, lane l ends up owning column l).
-            float a[32];
-            float* cmx = scratch + (warp - 4) * 32;
-            __syncwarp();
-            if (!ragged && __all_sync(0xffffffffu, row_ok)) {
-              // common case (every row of the warp is real, every column of the tile too): no masks, no -inf handling
-#pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                float cme;
-                asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(cme) : "f"(v[e]));
-                if (lane == 0) cmx[e] = cme;
-                a[e] = ex2f((v[e] - cme) * cS2);
-              }
             } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) a[e] = 0.f;
+            }
+            // ---- column partials: this warp's 32 x 32 block (lane = row) -> LSE over its rows of each column, from a
+            // transpose-reduce in registers (five exchange steps, lane l ends up owning column l).
+            // Common case (every row of the warp real, every column of the tile too): the SAME exponentials, weighted per
+            // row by w_i = 2^((cm_i - M) c) against the block maximum M (one CREDUX, one exponential per row): column j's
+            // sum is sum_i a_ij w_i = sum_i 2^((S_ij - M) c).  A column whose every entry lies so far below M that its sum
+            // leaves the safe range (< 2^-100: a term that underflowed could then matter by more than 2^-26 of it) sends
+            // the block down the exact path below - per-column maxima from redux.sync.max.f32 (one CREDUX per column,
+            // warp-uniform result), exponentials against the column's OWN maximum.
+            const int g32 = (rb * 256 + (int)rank * 128 + q4 * 32) >> 5;
+            float* const cp_out = p.colpart + (size_t)g32 * p.Bp + (size_t)t * kTileN + jl0 + lane;
+            bool col_done = false;
+            if (!ragged && __all_sync(0xffffffffu, row_ok)) {
+              float M;
+              asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(M) : "f"(cm));
+              const float w = ex2f((cm - M) * cS2);
+#pragma unroll
+              for (int e = 0; e < 32; ++e) a[e] *= w;
+#pragma unroll
+              for (int s2 = 16; s2 >= 1; s2 >>= 1) {
+                const bool up = (lane & s2) != 0;
+#pragma unroll
+                for (int k = 0; k < s2; ++k) {
+                  const float keep = up ? a[k + s2] : a[k], send = up ? a[k] : a[k + s2];
+                  a[k] = keep + __shfl_xor_sync(0xffffffffu, send, s2);
+                }
+              }
+              if (__all_sync(0xffffffffu, a[0] >= 7.8886e-31f)) {       // 2^-100
+                *cp_out = fmaf(M, cS2, lg2f(a[0]));
+                col_done = true;
+              }
+            }
+            if (!col_done) {
+              float* cmx = scratch + (warp - 4) * 32;
+              __syncwarp();
 #pragma unroll
               for (int e = 0; e < 32; ++e) {
                 float cme;
@@ -2269,21 +2292,19 @@ rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const float ref = cme == -INFINITY ? 0.f : cme;
                 a[e] = row_ok ? ex2f((v[e] - ref) * cS2) : 0.f;
               }
-            }
-            __syncwarp();
-            const float cm_own = cmx[lane];
+              __syncwarp();
+              const float cm_own = cmx[lane];
 #pragma unroll
-            for (int s2 = 16; s2 >= 1; s2 >>= 1) {
-              const bool up = (lane & s2) != 0;
+              for (int s2 = 16; s2 >= 1; s2 >>= 1) {
+                const bool up = (lane & s2) != 0;
 #pragma unroll
-              for (int k = 0; k < s2; ++k) {
-                const float keep = up ? a[k + s2] : a[k], send = up ? a[k] : a[k + s2];
-                a[k] = keep + __shfl_xor_sync(0xffffffffu, send, s2);
+                for (int k = 0; k < s2; ++k) {
+                  const float keep = up ? a[k + s2] : a[k], send = up ? a[k] : a[k + s2];
+                  a[k] = keep + __shfl_xor_sync(0xffffffffu, send, s2);
+                }
               }
+              *cp_out = cm_own == -INFINITY ? -INFINITY : fmaf(cm_own, cS2, lg2f(a[0]));
             }
-            const int g32 = (rb * 256 + (int)rank * 128 + q4 * 32) >> 5;
-            p.colpart[(size_t)g32 * p.Bp + (size_t)t * kTileN + jl0 + lane] =
-                cm_own == -INFINITY ? -INFINITY : fmaf(cm_own, cS2, lg2f(a[0]));
           }
         }
         if (KIND == kRsZ) {
