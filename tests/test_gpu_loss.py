@@ -840,11 +840,15 @@ def test_no_grad_forward_does_not_run_the_gradient_sweep():
 
 
 @pytest.mark.parametrize("mode", ["tc_f16x3", "tc_f16"])
-@pytest.mark.parametrize("B,shard,scale", [(640, 128, 0.1), (1000, 1000, 0.3), (768, 384, 1.0), (129, 129, 0.5)])
+@pytest.mark.parametrize("B,shard,scale", [(640, 128, 0.1), (1000, 1000, 0.3), (768, 384, 1.0), (129, 129, 0.5),
+                                           (4096, 4096, 1.0), (4096 + 128, 4096 + 128, 1.0)])
 def test_column_partials_statistics_match_oracle(B, shard, scale, mode):
     """Column LSE of S from the per-warp column partials (no transposed strip): ragged batches, a strip that is the
     whole batch, strips of one row block, rows of very different scale in one column (exponentials are taken against
-    each column's OWN maximum, so nothing underflows) - the five statistic vectors against the fp64 closed form."""
+    each column's OWN maximum, so nothing underflows) - the five statistic vectors against the fp64 closed form.
+    From 4096 rows on the sweep is rowsweep_kernel<kRsS>: its 32 x 32 blocks share one set of exponentials between the
+    row LSE and the column partials (weighted against the block maximum); the text row scaled by 6 puts logits of
+    +-300 next to +-50 in its blocks, so columns there fall out of the safe range and take the kernel's exact path."""
     from mae_clip_b200 import _lib
     from mae_clip_b200._lib import check, cur_stream, ptr
     lib = _lib.lib()
