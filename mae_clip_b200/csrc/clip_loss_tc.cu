@@ -10,7 +10,9 @@
 //   pair_kernel<PHASE, PASSES>      128 x 128 tiles over a CTA pair of 128 rows: every phase for small problems, the flagged-
 //                                   tile sweeps (exact-Z statistics, row loss, soft-target part of the gradient) and the
 //                                   own-rows gradient always
-//   rowsweep_kernel<KIND, PASSES>   256 x 128 tiles over a CTA pair of 256 rows: S statistics / tile-flag probe of Z
+//   rowsweep_kernel<KIND, PASSES>   256 x 128 tiles over a CTA pair of 256 rows: S statistics / tile-flag probe of Z (the
+//                                   probe multiplies out probe_chunks() of K and bounds the rest; probe_gate_kernel sends
+//                                   a batch the bound cannot serve back through the full probe)
 //   rowgrad_kernel<PASSES>          same skeleton: S -> softmax part of the gradient weights -> dT, stores the weights
 //   colgrad_kernel                  dI from the stored weights (MN-major tcgen05 operand)
 // and the staging, fold and gate kernels around them.
