@@ -2006,7 +2006,8 @@ struct RowSweepParams {
   const float* rho;             // kRsZ: norm of the left-out dimensions of every row (nullptr: nothing is left out)
   const float* tile_max_rho;    // kRsZ: largest rho of every column tile
   const float* tile_max_n;      // kRsZ: largest row norm sqrt(|I_j|^2 + |T_j|^2) of every column tile
-  const int* gate;              // kRsZ: optional device word, the launch returns unless it is 1 (the full re-probe)
+  const int* gate;              // kRsZ: optional device word, the launch returns unless it equals gate_want
+  int gate_want;                // 1: the full re-probe (probe_gate_kernel's verdict), 0: the partial probe (probe_hopeless_kernel)
 };
 __device__ __forceinline__ int rs_njobs(const RowSweepParams& p) {
   if (p.chunk_k < 0) return p.n_row_blocks * p.nsplit;
@@ -2049,7 +2050,7 @@ rowsweep_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  if (KIND == kRsZ && p.gate != nullptr && *p.gate != 1) return;   // kernel-uniform: the partial probe was good enough
+  if (KIND == kRsZ && p.gate != nullptr && *p.gate != p.gate_want) return;   // kernel-uniform (see RowSweepParams::gate)
   const int D = p.D, nkc = D >> 6;
   const int nkz = KIND == kRsS ? nkc : p.pk;          // K chunks (per half of X) a tile multiplies out
   const int njobs = rs_njobs(p);
@@ -2377,8 +2378,29 @@ __global__ void __launch_bounds__(128) tile_min_zjj_kernel(const float* __restri
     out_n[blockIdx.x] = fmaxf(fmaxf(sn[0], sn[1]), fmaxf(sn[2], sn[3]));
   }
 }
+// Before the partial probe: a batch for which the bound ALONE (E_ij = 0) already reaches the threshold inside most tiles
+// (small norms - the soft regime - or all the energy in the left-out dimensions) cannot be served by it; *hopeless is set
+// (sticky over the arrival-ordered launches of one statistics sweep: stats_begin clears it) and the partial probe returns
+// at once.  Only the first n_valid tiles have their rows staged yet.
+__global__ void __launch_bounds__(256) probe_hopeless_kernel(const float* __restrict__ tile_min_zjj2,
+                                                             const float* __restrict__ tile_max_rho, int n_valid,
+                                                             float half_tau, int* __restrict__ hopeless) {
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (int t = threadIdx.x; t < n_valid; t += blockDim.x) {
+    const float r = tile_max_rho[t];
+    c += r * r * half_tau * 1.4426950408889634f >= tile_min_zjj2[t] - kFlagTheta2 - kProbeMargin2;
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0 && 2 * cnt > n_valid) *hopeless = 1;
+}
 // The partial probe's verdict: with more flagged tiles than a concentrated batch can have (its diagonal + 1/64 of all
-// tiles) the Cauchy-Schwarz bound was too loose for this batch - clear the bitmap and let the full probe run (*gate = 1).
+// tiles) the Cauchy-Schwarz bound was too loose for this batch - clear the bitmap and let the full probe run (*gate = 1);
+// likewise when the partial probe was skipped as hopeless (gate[1]).
 __global__ void __launch_bounds__(1024) probe_gate_kernel(uint8_t* __restrict__ flags, int n, int limit, int* __restrict__ gate) {
   __shared__ int cnt;
   if (threadIdx.x == 0) cnt = 0;
@@ -2396,7 +2418,7 @@ __global__ void __launch_bounds__(1024) probe_gate_kernel(uint8_t* __restrict__ 
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt, c);
   __syncthreads();
-  const bool redo = cnt > limit;
+  const bool redo = cnt > limit || gate[1] != 0;
   if (redo) {
     if (vec) for (int i = threadIdx.x; i < n / 16; i += blockDim.x) reinterpret_cast<uint4*>(flags)[i] = make_uint4(0u, 0u, 0u, 0u);
     else for (int i = threadIdx.x; i < n; i += blockDim.x) flags[i] = 0;
@@ -3042,7 +3064,9 @@ static int launch_rowsweep(const ClipProblem& p, void* ws, float* colpart, int c
   rp.rho = rp.pk < p.D / 64 ? reinterpret_cast<const float*>(base + l.off_rho) : nullptr;
   rp.tile_max_rho = rowsweep_tile_max_rho(p, ws);
   rp.tile_max_n = rowsweep_tile_max_n(p, ws);
-  rp.gate = full_reprobe ? rowsweep_probe_gate(p, ws) : nullptr;
+  // gate words: [0] probe_gate_kernel's verdict (1 = re-probe in full), [1] probe_hopeless_kernel's (1 = skip the partial probe)
+  rp.gate = full_reprobe ? rowsweep_probe_gate(p, ws) : (rp.rho != nullptr ? rowsweep_probe_gate(p, ws) + 1 : nullptr);
+  rp.gate_want = full_reprobe ? 1 : 0;
   auto kern = rowsweep_kernel<KIND, PASSES>;
   static std::atomic<unsigned long long> attr_done{0};
   MC_CUDA(ensure_dynamic_smem(kern, kRsSmemBytes, attr_done));
@@ -3085,6 +3109,13 @@ int stats_chunk(const ClipProblem& p, int mode, int k, int chunks, void* ws, cud
                                                  reinterpret_cast<const float*>(base + l.off_rho), p.B, 0.5f * p.tau,
                                                  rowsweep_tile_min(p, ws), rowsweep_tile_max_rho(p, ws), rowsweep_tile_max_n(p, ws));
     MC_LAUNCH_CHECK();
+    if (probe_chunks(p.D) < p.D / 64) {
+      if (k <= 0) MC_CUDA(cudaMemsetAsync(rowsweep_probe_gate(p, ws), 0, 2 * sizeof(int), st));   // first launch of this sweep
+      const int n_valid = chunks > 1 ? (int)((long)n_tiles * (k + 1) / chunks) : n_tiles;
+      probe_hopeless_kernel<<<1, 256, 0, st>>>(rowsweep_tile_min(p, ws), rowsweep_tile_max_rho(p, ws), n_valid, 0.5f * p.tau,
+                                               rowsweep_probe_gate(p, ws) + 1);
+      MC_LAUNCH_CHECK();
+    }
     int rc = mode == MC_GEMM_TC_F16X3 ? launch_rowsweep<kRsS, 3>(p, ws, colpart_rs, k, chunks, st)
                                       : launch_rowsweep<kRsS, 1>(p, ws, colpart_rs, k, chunks, st);
     if (rc) return rc;
